@@ -1,0 +1,357 @@
+"""CPU ORACLE (test infrastructure, NOT product code) for apax's GMNN energy+forces path.
+
+This file restates, op for op and dtype for dtype, what apax's JAX code computes on
+the hot path, using PyTorch-CPU tensors so that forces come from autograd exactly as
+the reference gets them from `jax.value_and_grad`.  Only `tests/`, `__graft_entry__.smoke()`
+and `bench.py`'s CPU-baseline / `--impl reference` legs may import it; the product
+package `apax_b200` never does.
+
+Pinning status: the reference cannot be imported here (no jax/flax wheels, SURVEY.md
+§8c), and its tests hold no value-level golden vectors for this path.  The oracle is
+pinned two ways: (1) `tests/golden/make_golden.py` executes the reference's *own
+source files* for the path under a torch-backed jax/flax shim and the fixtures it
+wrote are compared with this oracle in `tests/test_oracle_golden.py`; (2) the
+reference's relational tests (360 features, padding invariance, scale/shift numerics)
+are replayed in `tests/test_oracle_reference_pins.py`.  XLA's own numerics (exp/cos
+implementations, reduction order) remain unpinned; north_star's tolerances absorb them.
+
+Each function cites the reference file:line (relative to /root/reference) it follows.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+SWISH_SCALE = 1.6765324703310907  # apax/layers/activation.py:8
+
+
+@dataclass
+class GMNNConfig:
+    """Hot-path statics (defaults = Flax-module defaults, SURVEY.md §8 header)."""
+
+    n_basis: int = 7          # apax/layers/descriptor/basis_functions.py:13
+    n_radial: int = 5         # basis_functions.py:89
+    r_min: float = 0.5        # basis_functions.py:14
+    r_max: float = 6.0        # basis_functions.py:15
+    n_contr: int = 8          # gaussian_moment_descriptor.py:18
+    use_ntk: bool = False     # apax/config/model_config.py:184-188
+    use_embed_norm: bool = True  # basis_functions.py:93
+    apply_mask: bool = True   # gaussian_moment_descriptor.py:20
+    mask_atoms: bool = True   # apax/nn/models.py:81
+    descriptor_dtype: torch.dtype = torch.float32
+    readout_dtype: torch.dtype = torch.float32
+    scale_shift_dtype: torch.dtype = torch.float64
+
+
+# ---------------------------------------------------------------------------
+# triangular index sets  (apax/layers/descriptor/triangular_indices.py:28-49)
+# ---------------------------------------------------------------------------
+def tril_2d_indices(n: int) -> np.ndarray:
+    out = []
+    for i in range(n):
+        out.append([i, i])
+        for j in range(i + 1, n):
+            out.append([i, j])
+    return np.array(out, dtype=np.int64)
+
+
+def tril_3d_indices(n: int) -> np.ndarray:
+    out = []
+    for i in range(n):
+        out.append([i, i, i])
+        for j in range(n):
+            if j != i:
+                out.append([i, j, j])
+        for j in range(i + 1, n):
+            for k in range(j + 1, n):
+                out.append([i, j, k])
+    return np.array(out, dtype=np.int64)
+
+
+# ---------------------------------------------------------------------------
+# displacement  (apax/layers/distances.py:12-67, apax/utils/jax_md_reduced/space.py)
+# ---------------------------------------------------------------------------
+def _transform_identity_jvp(box: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """space.transform (space.py:77-97): value box @ v, but JVP w.r.t. v is the identity.
+
+    value = einsum("ij,...j->...i", box, v)  (space.py:69-73); the custom JVP returns
+    dR + transform(dbox, R) (space.py:93-97); box carries no tangent on the E+F path.
+    """
+    val = torch.einsum("ij,...j->...i", box, v.detach())
+    return val + (v - v.detach())
+
+
+def periodic_displacement_unit(dR: torch.Tensor) -> torch.Tensor:
+    """space.periodic_displacement with side=1 (space.py:146-157): mod(dR+0.5,1)-0.5.
+
+    jnp.mod is fmod followed by a conditional +divisor (Python-style remainder), and
+    has unit derivative w.r.t. its first argument; torch.remainder does the same.
+    """
+    return torch.remainder(dR + 0.5, 1.0) - 0.5
+
+
+def compute_distances(R, idx, box, offsets, mode: str):
+    """make_distance_fn.compute_distances (distances.py:48-67).
+
+    mode "gas":      dr_vec = R[idx[1]] - R[idx[0]]                          (:59-62, space.free)
+    mode "offsets":  dr_vec = transform(box, R[idx[1]] - R[idx[0]]) + offsets (:12-14, :65-66)
+    mode "minimage": dr_vec = transform(box, wrap(R[idx[1]] - R[idx[0]])) + offsets
+                     (periodic_general.displacement_fn, space.py:260-282, fractional coords)
+    R is cast to float64 first (:54).  Gathers clamp out-of-range indices like JAX does.
+    """
+    R = R.to(torch.float64)
+    n = R.shape[0]
+    i0 = idx[0].long().clamp(0, n - 1)
+    i1 = idx[1].long().clamp(0, n - 1)
+    Ri, Rj = R[i0], R[i1]
+    dR = Rj - Ri
+    if mode == "gas":
+        return dR
+    box = box.to(torch.float64)
+    if mode == "offsets":
+        d = _transform_identity_jvp(box, dR)
+    elif mode == "minimage":
+        d = _transform_identity_jvp(box, periodic_displacement_unit(dR))
+    else:
+        raise ValueError(mode)
+    return d + offsets.to(torch.float64)
+
+
+# ---------------------------------------------------------------------------
+# descriptor  (apax/layers/descriptor/*.py)
+# ---------------------------------------------------------------------------
+def gaussian_basis(dr, cfg: GMNNConfig):
+    """GaussianBasis, linear spacing (basis_functions.py:19-56)."""
+    dt = dr.dtype
+    betta = cfg.n_basis ** 2 / cfg.r_max ** 2
+    rad_norm = (2.0 * betta / np.pi) ** 0.25
+    shifts = cfg.r_min + (cfg.r_max - cfg.r_min) / cfg.n_basis * np.arange(cfg.n_basis)
+    shifts = torch.as_tensor(shifts, dtype=dt)[None, :]
+    distances = shifts - dr[:, None]
+    basis = torch.exp(-betta * (distances ** 2))
+    return rad_norm * basis
+
+
+def cosine_cutoff(dr, r_max: float):
+    """basis_functions.py:82-85 (jnp.clip has zero gradient beyond the clip)."""
+    dr_clipped = torch.clamp(dr, max=r_max)
+    return 0.5 * (torch.cos(np.pi * dr_clipped / r_max) + 1.0)
+
+
+def radial_function(dr, Z_i, Z_j, emb, cfg: GMNNConfig):
+    """RadialFunction.__call__ (basis_functions.py:129-158); emb [S,S,n_radial,n_basis]."""
+    dt = cfg.descriptor_dtype
+    dr = dr.to(dt)
+    basis = gaussian_basis(dr, cfg)
+    coeffs = emb[Z_j, Z_i]  # "reverse convention" (:139-141): central species first
+    if cfg.use_embed_norm:
+        coeffs = torch.as_tensor(1.0 / np.sqrt(cfg.n_basis), dtype=dt) * coeffs
+    radial = torch.einsum("nrb,nb->nr", coeffs, basis)
+    cutoff = cosine_cutoff(dr, cfg.r_max)[:, None]
+    return radial * cutoff
+
+
+def safe_distance(dr_vec):
+    """space.distance (space.py:314-323) with util.safe_mask (util.py:72-75)."""
+    d2 = torch.sum(dr_vec ** 2, dim=-1)
+    mask = d2 > 0
+    masked = torch.where(mask, d2, torch.zeros_like(d2))
+    # safe_mask evaluates fn on the masked operand; the sqrt(0) branch is replaced by 0 and
+    # (through jnp.where) contributes no gradient.  sqrt(0) has an inf derivative that is
+    # multiplied by the zero cotangent of the masked branch -> NaN in torch, so feed 1 instead.
+    safe = torch.where(mask, masked, torch.ones_like(d2))
+    return torch.where(mask, torch.sqrt(safe), torch.zeros_like(d2))
+
+
+def geometric_moments(radial, dn, seg, n_atoms: int):
+    """moments.geometric_moments (moments.py:5-29): outer products then segment_sum.
+
+    Out-of-range segment ids are dropped, as jax.ops.segment_sum does.
+    """
+    m0 = radial
+    m1 = m0[:, :, None] * dn[:, None, :]
+    m2 = m1[:, :, :, None] * dn[:, None, None, :]
+    m3 = m2[:, :, :, :, None] * dn[:, None, None, None, :]
+    valid = (seg >= 0) & (seg < n_atoms)
+    seg_c = torch.where(valid, seg, torch.zeros_like(seg))
+
+    def segsum(x):
+        w = valid.to(x.dtype).reshape((-1,) + (1,) * (x.dim() - 1))
+        out = torch.zeros((n_atoms,) + x.shape[1:], dtype=x.dtype)
+        return out.index_add(0, seg_c, x * w)
+
+    return segsum(m0), segsum(m1), segsum(m2), segsum(m3)
+
+
+def gaussian_moment_descriptor(dr_vec, Z, idx, emb, cfg: GMNNConfig):
+    """GaussianMomentDescriptor.__call__ (gaussian_moment_descriptor.py:31-103) -> [N, n_feat]."""
+    dt = cfg.descriptor_dtype
+    dr_vec = dr_vec.to(dt)
+    n_atoms = Z.shape[0]
+    idx_i, idx_j = idx[0].long(), idx[1].long()
+    Zl = Z.long()
+    Z_i = Zl[idx_i.clamp(0, n_atoms - 1)]
+    Z_j = Zl[idx_j.clamp(0, n_atoms - 1)]
+    dr = safe_distance(dr_vec)
+    dn = dr_vec / (dr + 1e-5)[:, None]                         # :46-48 (deliberately not unit)
+    radial = radial_function(dr, Z_i, Z_j, emb.to(dt), cfg)
+    if cfg.apply_mask:                                          # masking.py:10-16
+        radial = radial * ((idx[0] - idx[1]) != 0).to(dt)[:, None]
+    m0, m1, m2, m3 = geometric_moments(radial, dn, idx_j, n_atoms)
+
+    c0 = m0
+    c1 = torch.einsum("ari,asi->ars", m1, m1)
+    c2 = torch.einsum("arij,asij->ars", m2, m2)
+    c3 = torch.einsum("arijk,asijk->ars", m3, m3)
+    c4 = torch.einsum("arij,asik,atjk->arst", m2, m2, m2)
+    c5 = torch.einsum("ari,asj,atij->arst", m1, m1, m2)
+    c6 = torch.einsum("arijk,asijl,atkl->arst", m3, m3, m2)
+    c7 = torch.einsum("arijk,asij,atk->arst", m3, m2, m1)
+
+    t2 = tril_2d_indices(cfg.n_radial)
+    t3 = tril_3d_indices(cfg.n_radial)
+    c1 = c1[:, t2[:, 0], t2[:, 1]]
+    c2 = c2[:, t2[:, 0], t2[:, 1]]
+    c3 = c3[:, t2[:, 0], t2[:, 1]]
+    c4 = c4[:, t3[:, 0], t3[:, 1], t3[:, 2]]
+    c5 = c5[:, t2[:, 0], t2[:, 1]].reshape(n_atoms, -1)
+    c6 = c6[:, t2[:, 0], t2[:, 1]].reshape(n_atoms, -1)
+    c7 = c7.reshape(n_atoms, -1)
+    feats = [c0, c1, c2, c3, c4, c5, c6, c7][: cfg.n_contr]
+    return torch.cat(feats, dim=-1), (m0, m1, m2, m3)
+
+
+# ---------------------------------------------------------------------------
+# readout, scale/shift, energy  (apax/layers/readout.py, ntk_linear.py, scaling.py, nn/models.py)
+# ---------------------------------------------------------------------------
+def vp_swish(x):
+    """variance_preserving_swish (activation.py:7-9)."""
+    return SWISH_SCALE * x * torch.sigmoid(x)
+
+
+def atomistic_readout(g, dense: Sequence[dict], cfg: GMNNConfig):
+    """AtomisticReadout (readout.py:22-50) of NTKLinear layers (ntk_linear.py:20-50), vmapped
+    over atoms (models.py:108).  dense = [{"w":[in,out],"b":[out]}, ...]."""
+    dt = cfg.readout_dtype
+    h = g.to(dt)
+    n_layers = len(dense)
+    for li, layer in enumerate(dense):
+        w, b = layer["w"].to(dt), layer["b"].to(dt)
+        wx = h @ w
+        if cfg.use_ntk:
+            h = torch.as_tensor(np.sqrt(1.0 / w.shape[0]), dtype=dt) * wx + 0.1 * b
+        else:
+            h = wx + b
+        if li < n_layers - 1:
+            h = vp_swish(h)
+    return h
+
+
+def per_element_scale_shift(h, Z, scale, shift, cfg: GMNNConfig):
+    """PerElementScaleShift.__call__ (scaling.py:40-50)."""
+    dt = cfg.scale_shift_dtype
+    Zl = Z.long()
+    return scale.to(dt)[Zl] * h.to(dt) + shift.to(dt)[Zl]
+
+
+def _params_to_torch(params: dict):
+    em = params["params"]["energy_model"] if "params" in params else params
+    emb = torch.as_tensor(np.asarray(em["representation"]["radial_fn"]["atomic_type_embedding"]))
+    ro = em["readout"]
+    dense = []
+    for li in range(len(ro)):
+        layer = ro[f"dense_{li}"]
+        dense.append({"w": torch.as_tensor(np.asarray(layer["w"])), "b": torch.as_tensor(np.asarray(layer["b"]))})
+    scale = torch.as_tensor(np.asarray(em["scale_shift"]["scale_per_element"], dtype=np.float64)).reshape(-1, 1)
+    shift = torch.as_tensor(np.asarray(em["scale_shift"]["shift_per_element"], dtype=np.float64)).reshape(-1, 1)
+    return emb, dense, scale, shift
+
+
+def energy_model(params, R, Z, idx, box, offsets, mode: str, cfg: GMNNConfig, return_aux: bool = False):
+    """EnergyModel.__call__ (models.py:87-134) without property heads / corrections.
+
+    Returns the fp64 total energy: a scalar, or [n_ens] for a shallow ensemble (:115-122).
+    """
+    emb, dense, scale, shift = _params_to_torch(params)
+    dr_vec = compute_distances(R, idx, box, offsets, mode)
+    g, moments = gaussian_moment_descriptor(dr_vec, Z, idx, emb, cfg)
+    h = atomistic_readout(g, dense, cfg)
+    E_i = per_element_scale_shift(h, Z, scale, shift, cfg)
+    if cfg.mask_atoms:                                          # masking.py:1-7
+        E_i = E_i * (Z != 0).to(E_i.dtype)[:, None]
+    if E_i.shape[1] > 1:
+        energy = torch.sum(E_i.to(torch.float64), dim=0)        # fp64_sum, math.py:7-12
+    else:
+        energy = torch.sum(E_i.to(torch.float64))
+    if return_aux:
+        return energy, {"g": g, "moments": moments, "E_i": E_i, "dr_vec": dr_vec}
+    return energy
+
+
+def _as_inputs(R, Z, idx, box, offsets):
+    R = torch.as_tensor(np.asarray(R, dtype=np.float64))
+    Z = torch.as_tensor(np.asarray(Z).astype(np.int64))
+    idx = torch.as_tensor(np.asarray(idx).astype(np.int64))
+    box = torch.as_tensor(np.asarray(box, dtype=np.float64))
+    if offsets is None:
+        offsets = np.zeros((idx.shape[1], 3))
+    offsets = torch.as_tensor(np.asarray(offsets, dtype=np.float64))
+    return R, Z, idx, box, offsets
+
+
+def energy_forces(params, R, Z, idx, box, offsets, mode: str, cfg: Optional[GMNNConfig] = None):
+    """EnergyDerivativeModel.__call__ (models.py:146-171): {"energy" f64, "forces" [N,3] f64}."""
+    cfg = cfg or GMNNConfig()
+    R, Z, idx, box, offsets = _as_inputs(R, Z, idx, box, offsets)
+    R = R.clone().requires_grad_(True)
+    energy = energy_model(params, R, Z, idx, box, offsets, mode, cfg)
+    (grad,) = torch.autograd.grad(energy, R)
+    return {"energy": float(energy.detach()), "forces": (-grad).numpy()}
+
+
+def descriptor_only(params, R, Z, idx, box, offsets, mode: str, cfg: Optional[GMNNConfig] = None):
+    """Features g [N,360] and packed moments, for kernel-stage parity tests."""
+    cfg = cfg or GMNNConfig()
+    R, Z, idx, box, offsets = _as_inputs(R, Z, idx, box, offsets)
+    with torch.no_grad():
+        _, aux = energy_model(params, R, Z, idx, box, offsets, mode, cfg, return_aux=True)
+    return {k: (v.numpy() if torch.is_tensor(v) else [m.numpy() for m in v]) for k, v in aux.items()}
+
+
+def shallow_ensemble(params, R, Z, idx, box, offsets, mode: str, cfg: Optional[GMNNConfig] = None):
+    """ShallowEnsembleModel.__call__ (models.py:209-275), force_variance=True, no chunking."""
+    cfg = cfg or GMNNConfig()
+    R, Z, idx, box, offsets = _as_inputs(R, Z, idx, box, offsets)
+    R = R.clone().requires_grad_(True)
+    e_ens = energy_model(params, R, Z, idx, box, offsets, mode, cfg)
+    n_ens = e_ens.shape[0]
+    divisor = 1.0 / (n_ens - 1)
+    e_mean = torch.mean(e_ens)
+    e_var = divisor * torch.sum((e_ens - e_mean) ** 2)
+    f_ens = []
+    for k in range(n_ens):                                       # jacrev over heads (:236)
+        (gk,) = torch.autograd.grad(e_ens[k], R, retain_graph=True)
+        f_ens.append(-gk)
+    f_ens = torch.stack(f_ens)                                   # [n_ens, N, 3]
+    f_mean = torch.mean(f_ens, dim=0)
+    f_var = divisor * torch.sum((f_ens - f_mean) ** 2, dim=0)
+    return {
+        "energy": float(e_mean.detach()),
+        "energy_ensemble": e_ens.detach().numpy(),
+        "energy_uncertainty": float(torch.sqrt(e_var).detach()),
+        "forces": f_mean.numpy(),
+        "forces_uncertainty": torch.sqrt(f_var).numpy(),
+        "forces_ensemble": f_ens.permute(1, 2, 0).contiguous().numpy(),  # [N,3,n_ens] (:262-263)
+    }
+
+
+def fp64_config(cfg: Optional[GMNNConfig] = None) -> GMNNConfig:
+    """All-fp64 variant used to calibrate how much fp32 noise the tolerances must absorb."""
+    cfg = cfg or GMNNConfig()
+    out = GMNNConfig(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+    out.descriptor_dtype = torch.float64
+    out.readout_dtype = torch.float64
+    return out

@@ -1,0 +1,190 @@
+"""Generate golden fixtures by executing the reference's OWN hot-path source files
+(/root/reference/apax/...) under the torch-backed jax/flax shim in jax_shim.py.
+
+Run by hand in the build container:  python tests/golden/make_golden.py
+Writes tests/golden/*.npz.  The GPU box has no /root/reference; tests only read the .npz.
+
+Modules executed unmodified from the reference: apax/layers/{distances,masking,readout,
+ntk_linear,activation,scaling}.py, apax/layers/descriptor/{gaussian_moment_descriptor,
+basis_functions,moments,triangular_indices}.py, apax/nn/models.py, apax/utils/math.py,
+apax/utils/jax_md_reduced/{space,partition,util,dataclasses}.py.
+vesin is absent, so multi-image lists come from oracle/neighbor_oracle.py (an INPUT to the
+reference model here, not something being checked).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import jax_shim  # noqa: E402
+
+jax_shim.install("/root/reference")
+
+from apax.layers.activation import variance_preserving_swish  # noqa: E402
+from apax.layers.descriptor.basis_functions import GaussianBasis, RadialFunction  # noqa: E402
+from apax.layers.descriptor.gaussian_moment_descriptor import GaussianMomentDescriptor  # noqa: E402
+from apax.layers.readout import AtomisticReadout  # noqa: E402
+from apax.layers.scaling import PerElementScaleShift  # noqa: E402
+from apax.nn.models import EnergyDerivativeModel, EnergyModel, ShallowEnsembleModel  # noqa: E402
+from apax.utils.jax_md_reduced import partition, space  # noqa: E402
+
+from apax_b200 import synthetic as syn  # noqa: E402
+from oracle import neighbor_oracle as no  # noqa: E402
+
+
+def to_t(tree):
+    if isinstance(tree, dict):
+        return {k: to_t(v) for k, v in tree.items()}
+    return torch.as_tensor(np.asarray(tree))
+
+
+def build_model(init_box, inference_disp_fn=None, n_ens=0, scale=1.0, shift=0.0, apply_mask=True,
+                mask_atoms=True, ensemble=False):
+    """What GMNNBuilder.build_energy_derivative_model assembles (apax/nn/builder.py:160-260) with the
+    model_config.py defaults named in SURVEY.md §8."""
+    descriptor = GaussianMomentDescriptor(
+        radial_fn=RadialFunction(n_radial=5, basis_fn=GaussianBasis(n_basis=7, r_min=0.5, r_max=6.0, dtype="fp32"),
+                                 n_species=119, emb_init="uniform", use_embed_norm=True, dtype="fp32"),
+        n_contr=8, dtype="fp32", apply_mask=apply_mask)
+    readout = AtomisticReadout(units=[256, 256], activation_fn=variance_preserving_swish, w_init="lecun",
+                               b_init="zeros", use_ntk=False, n_shallow_ensemble=n_ens, dtype="fp32")
+    scale_shift = PerElementScaleShift(n_species=119, scale=scale, shift=shift, dtype="fp64")
+    em = EnergyModel(representation=descriptor, readout=readout, scale_shift=scale_shift, init_box=init_box,
+                     inference_disp_fn=inference_disp_fn, mask_atoms=mask_atoms)
+    if ensemble:
+        return ShallowEnsembleModel(em, force_variance=True)
+    return EnergyDerivativeModel(em)
+
+
+def np_out(res):
+    return {k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in res.items()}
+
+
+def case_descriptor_unit():
+    """Geometry of tests/unit_tests/layers/descriptor/test_gaussian_moment_descriptor.py:8-31."""
+    dR = np.array([[1, 0, 0], [0, 1, 0], [-1, 0, 0], [-1, 1, 0], [0, -1, 0], [1, -1, 0]], dtype=np.float32)
+    Z = np.array([8, 1, 1])
+    idx = np.array([[1, 2, 0, 2, 0, 1], [0, 0, 1, 1, 2, 2]])
+    params = syn.gmnn_params(seed=7)
+    desc = GaussianMomentDescriptor()
+    emb = params["params"]["energy_model"]["representation"]["radial_fn"]["atomic_type_embedding"]
+    g = desc.apply({"params": {"radial_fn": {"atomic_type_embedding": torch.as_tensor(emb)}}},
+                   torch.as_tensor(dR), torch.as_tensor(Z), torch.as_tensor(idx))
+    assert tuple(g.shape) == (3, 360)
+    np.savez(os.path.join(HERE, "descriptor_unit.npz"), dR=dR, Z=Z, idx=idx, param_seed=7, g=g.numpy())
+
+
+def case_gas_padded():
+    """Geometry + scale/shift of tests/unit_tests/model/test_apax.py:10-62 (padding invariance)."""
+    R = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])
+    Z = np.array([1, 2, 2])
+    idx = np.array([[1, 2, 0, 2, 0, 1], [0, 0, 1, 1, 2, 2]])
+    box = np.zeros(3)
+    shift = np.zeros(119)
+    shift[:3] = [0.0, 100.0, 200.0]
+    scale = np.ones(119)
+    scale[:3] = [1.0, 1.2, 1.6]
+    params = syn.gmnn_params(seed=11, scale=scale, shift=shift)
+    tparams = to_t(params)
+    offsets = np.zeros((6, 3))
+    m = build_model(box, apply_mask=False, mask_atoms=False, scale=scale[:, None], shift=shift)
+    res = np_out(m.apply(tparams, torch.as_tensor(R), torch.as_tensor(Z), torch.as_tensor(idx), torch.as_tensor(box),
+                         torch.as_tensor(offsets)))
+    Rp = np.concatenate([R, np.zeros((1, 3))])
+    Zp = np.concatenate([Z, [0]])
+    idxp = np.concatenate([idx, [[0], [0]]], axis=1)
+    offp = np.zeros((7, 3))
+    mp = build_model(box, apply_mask=True, mask_atoms=True, scale=scale[:, None], shift=shift)
+    resp = np_out(mp.apply(tparams, torch.as_tensor(Rp), torch.as_tensor(Zp), torch.as_tensor(idxp),
+                           torch.as_tensor(box), torch.as_tensor(offp)))
+    assert abs(res["energy"] - resp["energy"]) < 1e-6
+    assert np.all(np.abs(res["forces"] - resp["forces"][:-1]) < 1e-6)
+    np.savez(os.path.join(HERE, "gas_padded.npz"), R=R, Z=Z, idx=idx, Rp=Rp, Zp=Zp, idxp=idxp, scale=scale, shift=shift,
+             param_seed=11, energy=res["energy"], forces=res["forces"], energy_padded=resp["energy"],
+             forces_padded=resp["forces"])
+
+
+def case_multi_image(n_mol=12, seed=3):
+    """Small periodic water box (L < 2 r_max): the vesin path of ASECalculator.calculate
+    (apax/md/ase_calc.py:386-390): frac positions, box = cell, disp_fn + Cartesian offsets."""
+    pos, Z, cell = syn.water_box(n_mol, seed)
+    idx, offsets = no.vesin_idx_offsets(pos, cell, 6.0)
+    pad = int(idx.shape[1] * 1.5)
+    idx, offsets = no.vesin_idx_offsets(pos, cell, 6.0, padded_length=pad)
+    box = cell  # ase_calc.py:359,389: box = atoms.cell.array (not transposed on this path)
+    frac = np.asarray(space.transform(torch.as_tensor(np.linalg.inv(box)), torch.as_tensor(pos)))
+    params = syn.gmnn_params(seed=1234)
+    m = build_model(np.array(cell.T))
+    res = np_out(m.apply(to_t(params), torch.as_tensor(frac), torch.as_tensor(Z.astype(np.int64)),
+                         torch.as_tensor(idx.astype(np.int64)), torch.as_tensor(box), torch.as_tensor(offsets)))
+    np.savez(os.path.join(HERE, "water_multi_image.npz"), positions=pos, frac=frac, Z=Z, cell=cell, idx=idx,
+             offsets=offsets, box=box, param_seed=1234, energy=res["energy"], forces=res["forces"])
+
+
+def case_min_image(n_mol=64, seed=5, skin=0.5):
+    """Periodic water box with L > 2 r_max: the JaxMD path (ase_calc.py:39-73, 530-542):
+    partition.neighbor_list(Sparse, fractional) + periodic_general displacement, zero offsets."""
+    pos, Z, cell = syn.water_box(n_mol, seed)
+    box = torch.as_tensor(cell.T.copy())
+    disp_fn, _ = space.periodic_general(box, fractional_coordinates=True)
+    nfn = partition.neighbor_list(disp_fn, box, 6.0, skin, fractional_coordinates=True, disable_cell_list=True,
+                                  format=partition.Sparse)
+    frac = space.transform(torch.linalg.inv(box), torch.as_tensor(pos))
+    nbrs = nfn.allocate(frac, box=box)
+    idx = nbrs.idx.numpy()
+    n_valid = int((idx[0] < len(Z)).sum())
+    # skin test on slightly moved positions (partition.py:771-779)
+    rng = np.random.default_rng(0)
+    moved_small = frac + torch.as_tensor(rng.normal(scale=0.002, size=frac.shape)) @ torch.linalg.inv(box).T
+    moved_big = frac.clone()
+    moved_big[7] += torch.as_tensor([0.0, 0.3, 0.0], dtype=torch.float64) @ torch.linalg.inv(box).T
+    same_small = nbrs.update(moved_small, box=box)
+    same_big = nbrs.update(moved_big, box=box)
+    rebuilt_small = not torch.equal(same_small.reference_position, nbrs.reference_position)
+    rebuilt_big = not torch.equal(same_big.reference_position, nbrs.reference_position)
+    params = syn.gmnn_params(seed=1234)
+    m = build_model(np.array(cell.T), inference_disp_fn=disp_fn)
+    offsets = torch.zeros((idx.shape[1], 3), dtype=torch.int64)  # jnp.full([P,3], 0) (ase_calc.py:540)
+    res = np_out(m.apply(to_t(params), frac, torch.as_tensor(Z.astype(np.int64)), nbrs.idx.long(), box, offsets))
+    np.savez(os.path.join(HERE, "water_min_image.npz"), positions=pos, frac=frac.numpy(), Z=Z, cell=cell,
+             box=box.numpy(), idx=idx, n_valid=n_valid, skin=skin, moved_small=moved_small.numpy(),
+             moved_big=moved_big.numpy(), rebuilt_small=rebuilt_small, rebuilt_big=rebuilt_big,
+             overflow=int(nbrs.did_buffer_overflow), param_seed=1234, energy=res["energy"], forces=res["forces"],
+             idx_big=same_big.idx.numpy())
+
+
+def case_ensemble(n_mol=10, seed=9, n_ens=4):
+    """Shallow ensemble (apax/nn/models.py:199-275) on a small multi-image water cell."""
+    pos, Z, cell = syn.water_box(n_mol, seed)
+    idx, offsets = no.vesin_idx_offsets(pos, cell, 6.0)
+    box = cell
+    frac = pos @ np.linalg.inv(box).T
+    frac = np.asarray(space.transform(torch.as_tensor(np.linalg.inv(box)), torch.as_tensor(pos)))
+    params = syn.gmnn_params(seed=77, n_out=n_ens, random_scale_shift=True, random_bias=True)
+    em = params["params"]["energy_model"]
+    m = build_model(np.array(cell.T), n_ens=n_ens, ensemble=True,
+                    scale=em["scale_shift"]["scale_per_element"], shift=em["scale_shift"]["shift_per_element"])
+    res = np_out(m.apply(to_t(params), torch.as_tensor(frac), torch.as_tensor(Z.astype(np.int64)),
+                         torch.as_tensor(idx.astype(np.int64)), torch.as_tensor(box), torch.as_tensor(offsets)))
+    np.savez(os.path.join(HERE, "water_ensemble.npz"), positions=pos, frac=frac, Z=Z, cell=cell, idx=idx, offsets=offsets,
+             box=box, param_seed=77, n_ens=n_ens, **res)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    case_descriptor_unit()
+    print("descriptor_unit ok")
+    case_gas_padded()
+    print("gas_padded ok")
+    case_multi_image()
+    print("multi_image ok")
+    case_min_image()
+    print("min_image ok")
+    case_ensemble()
+    print("ensemble ok")
