@@ -1,0 +1,89 @@
+"""ctypes binding of libapax_b200.so (the C ABI declared in include/apax_b200.h).
+
+There is no CPU fallback: if the library is missing or fails to load, importing this module's
+`lib()` raises.  Nothing here imports the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libapax_b200.so")
+
+OK = 0
+ERR_INVALID_ARG = -1
+ERR_UNSUPPORTED = -2
+ERR_WORKSPACE = -3
+ERR_CUDA = -4
+ERR_OVERFLOW = -5
+_ERR_NAMES = {-1: "APAX_ERR_INVALID_ARG", -2: "APAX_ERR_UNSUPPORTED", -3: "APAX_ERR_WORKSPACE", -4: "APAX_ERR_CUDA",
+              -5: "APAX_ERR_OVERFLOW"}
+
+DISP_GAS, DISP_OFFSETS, DISP_MINIMAGE, DISP_DRVEC = 0, 1, 2, 3
+
+
+class ApaxB200Error(RuntimeError):
+    def __init__(self, code: int, where: str, detail: str = ""):
+        self.code = code
+        super().__init__(f"{where}: {_ERR_NAMES.get(code, code)} {detail}".strip())
+
+
+class GmConfig(C.Structure):
+    _fields_ = [
+        ("n_species", C.c_int32), ("n_radial", C.c_int32), ("n_basis", C.c_int32), ("n_contr", C.c_int32),
+        ("n_hidden1", C.c_int32), ("n_hidden2", C.c_int32), ("n_out", C.c_int32), ("use_ntk", C.c_int32),
+        ("use_embed_norm", C.c_int32), ("mask_atoms", C.c_int32), ("r_min", C.c_float), ("r_max", C.c_float),
+    ]
+
+
+# every exported symbol of include/apax_b200.h with its signature
+_P = C.c_void_p
+_I64 = C.c_int64
+_I32 = C.c_int32
+SIGNATURES = {
+    "apax_abi_version": (C.c_int, []),
+    "apax_last_cuda_error": (C.c_char_p, []),
+    "apax_kernel_launch_count": (_I64, []),
+    "apax_gm_params_create": (C.c_int, [C.POINTER(GmConfig), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
+    "apax_gm_params_destroy": (None, [_P]),
+    "apax_gm_workspace_bytes": (C.c_size_t, [_I64, _I64, _I32]),
+    "apax_gm_energy_forces": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, C.c_size_t]),
+    "apax_gm_prepare": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, C.c_size_t]),
+    "apax_gm_compute": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, C.c_size_t]),
+    "apax_gm_descriptor": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, C.c_size_t]),
+    "apax_nl_workspace_bytes": (C.c_size_t, [_I64, _I64]),
+    "apax_nl_build_minimage": (C.c_int, [_P, _P, _P, _I64, C.c_double, _I64, _P, _P, _P, _P, C.c_size_t]),
+    "apax_nl_build_images": (C.c_int, [_P, _P, _P, _I32, _I64, C.c_double, _I64, _P, _P, _P, _P, _P, _P, C.c_size_t]),
+    "apax_nl_needs_rebuild": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, _P]),
+    "apax_ctx_create": (C.c_int, [_P, _I64, _I64, C.POINTER(_P)]),
+    "apax_ctx_destroy": (None, [_P]),
+    "apax_ctx_calculate": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, _I32, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library (once).  Raises if it has not been built -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ApaxB200Error(ERR_UNSUPPORTED, "load",
+                            f"{LIB_PATH} is missing: run `python -m apax_b200.build` (needs nvcc); there is no CPU path")
+    handle = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return _lib
+
+
+def check(code: int, where: str) -> None:
+    if code != OK:
+        detail = ""
+        if code == ERR_CUDA:
+            detail = lib().apax_last_cuda_error().decode()
+        raise ApaxB200Error(code, where, detail)

@@ -1,0 +1,1026 @@
+// GMNN energy+forces hot path on sm_100a: list preparation, fused pair kernels (moments forward,
+// force backward), packed contractions, fp32 readout GEMMs, fp64 energy/force assembly.
+//
+// Reference semantics (apax, path:line): apax/layers/distances.py:48-67, apax/layers/descriptor/
+// gaussian_moment_descriptor.py:31-103, basis_functions.py:19-158, moments.py:5-29,
+// apax/layers/readout.py:22-50, ntk_linear.py:20-50, activation.py:7-9, scaling.py:40-50,
+// apax/nn/models.py:87-171.  Nothing here is translated from the reference (which is pure JAX):
+// the reference materialises [P,200] per-pair tensors and scatter-adds them; this file keeps the 100
+// packed moment accumulators of an atom in registers, never materialises per-pair tensors, and
+// assembles forces with a deterministic transpose gather instead of atomics.
+#include <math.h>
+#include <stdio.h>
+
+#include "contract_gen.cuh"
+#include "gm_internal.cuh"
+
+namespace apax {
+
+// ================================================================================================
+// workspace
+// ================================================================================================
+size_t carve_gm_workspace(void* base, int64_t n_atoms, int64_t n_pairs, int32_t n_out, int32_t n_species,
+                          GmWorkspace* ws) {
+  Carver c(base);
+  GmWorkspace w{};
+  const int64_t N = n_atoms, P = n_pairs > 0 ? n_pairs : 1;
+  const int64_t ld = round_up(N > 0 ? N : 1, 128);
+  w.n_atoms = N;
+  w.n_pairs = n_pairs;
+  w.ld = ld;
+  w.n_out = n_out;
+  w.rowptr = c.take<int32_t>(N + 1);
+  w.trowptr = c.take<int32_t>(N + 1);
+  w.nbr = c.take<int32_t>(P);
+  w.src = c.take<int32_t>(P);
+  w.tpos = c.take<int32_t>(P);
+  w.tmp_a = c.take<int32_t>(P);
+  w.tmp_b = c.take<int32_t>(P);
+  w.cnt = c.take<int32_t>(N + 1);
+  w.tcnt = c.take<int32_t>(N + 1);
+  w.scan_scratch = c.take<int32_t>(scan_scratch_ints(N + 1));
+  w.sp_present = c.take<int32_t>(128);
+  w.sp_map = c.take<int32_t>(128);
+  w.n_sp = c.take<int32_t>(4);
+  w.embc = c.take<float>(int64_t(n_species) * n_species * EMB_STRIDE);
+  w.G = c.take<float4>(P);
+  w.D = c.take<float4>(P);
+  w.MT = c.take<float>(NPK * ld);
+  w.AT = c.take<float>(NPK * ld);
+  w.GT = c.take<float>(NFP * ld);
+  w.H1T = c.take<float>(NH * ld);
+  w.D1T = c.take<float>(NH * ld);
+  w.H2T = c.take<float>(NH * ld);
+  w.D2T = c.take<float>(NH * ld);
+  w.ebar = c.take<float>(ld);
+  w.Eatom = c.take<double>(int64_t(n_out) * ld);
+  w.partial = c.take<double>(int64_t(n_out) * 256);
+  w.Frow = c.take<double>(N * 3 + 3);
+  if (ws) *ws = w;
+  return c.bytes();
+}
+
+// ================================================================================================
+// list preparation: COO [2][P] -> CSR by central atom (rows sorted by original position) and the
+// transpose map (for every atom, the CSR slots in which it is the neighbour).  Entries with
+// idx[0]==idx[1] or an index outside [0,N) are dropped: they are exactly the (0,0)/(N,N) padding,
+// which the reference masks to zero (apax/layers/masking.py:10-16, partition.py:656).
+// ================================================================================================
+namespace {
+
+__global__ void __launch_bounds__(256) k_coo_count(const int32_t* __restrict__ idx, int64_t P, int N,
+                                                   int32_t* __restrict__ cnt, int32_t* __restrict__ tcnt) {
+  const int64_t e = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (e >= P) return;
+  const int i0 = idx[e], i1 = idx[P + e];
+  if (i0 != i1 && i0 >= 0 && i0 < N && i1 >= 0 && i1 < N) {
+    atomicAdd(&cnt[i1], 1);
+    atomicAdd(&tcnt[i0], 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_coo_fill(const int32_t* __restrict__ idx, int64_t P, int N,
+                                                  const int32_t* __restrict__ rowptr, int32_t* __restrict__ cursor,
+                                                  int32_t* __restrict__ nbr_tmp, int32_t* __restrict__ src_tmp) {
+  const int64_t e = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (e >= P) return;
+  const int i0 = idx[e], i1 = idx[P + e];
+  if (i0 != i1 && i0 >= 0 && i0 < N && i1 >= 0 && i1 < N) {
+    const int slot = rowptr[i1] + atomicAdd(&cursor[i1], 1);
+    nbr_tmp[slot] = i0;
+    src_tmp[slot] = int(e);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_transpose_fill(const int32_t* __restrict__ rowptr, int N,
+                                                        const int32_t* __restrict__ nbr,
+                                                        const int32_t* __restrict__ trowptr,
+                                                        int32_t* __restrict__ cursor, int32_t* __restrict__ tpos_tmp) {
+  const int64_t s = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (s >= rowptr[N]) return;
+  const int j = nbr[s];
+  tpos_tmp[trowptr[j] + atomicAdd(&cursor[j], 1)] = int(s);
+}
+
+__global__ void __launch_bounds__(128) k_species_mark(const int32_t* __restrict__ Z, int64_t N, int S,
+                                                      int32_t* __restrict__ present) {
+  const int64_t i = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  if (i >= N) return;
+  int z = Z[i];
+  z = z < 0 ? 0 : (z >= S ? S - 1 : z);
+  present[z] = 1;
+}
+
+__global__ void __launch_bounds__(256) k_species_build(const int32_t* __restrict__ present, int S,
+                                                       const float* __restrict__ emb, int32_t* __restrict__ sp_map,
+                                                       int32_t* __restrict__ n_sp_out, float* __restrict__ embc) {
+  __shared__ int zs[128];
+  __shared__ int n_sp;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int z = 0; z < S; ++z) {
+      if (present[z]) {
+        sp_map[z] = n;
+        zs[n++] = z;
+      } else {
+        sp_map[z] = 0;
+      }
+    }
+    n_sp = n;
+    *n_sp_out = n;
+  }
+  __syncthreads();
+  const int total = n_sp * n_sp * EMB_STRIDE;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int pair = i / EMB_STRIDE, k = i % EMB_STRIDE;
+    const int a = pair / n_sp, b = pair % n_sp;
+    embc[i] = k < NR * NB ? emb[(int64_t(zs[a]) * S + zs[b]) * (NR * NB) + k] : 0.0f;
+  }
+}
+
+}  // namespace
+
+namespace {
+__global__ void __launch_bounds__(256) k_csr_import(const int32_t* __restrict__ rowptr_in, const int32_t* __restrict__ nbr_in,
+                                                    int64_t N, int64_t P, int32_t* __restrict__ rowptr,
+                                                    int32_t* __restrict__ nbr, int32_t* __restrict__ src,
+                                                    int32_t* __restrict__ tcnt) {
+  const int64_t s = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (s <= N) rowptr[s] = rowptr_in[s];
+  if (s < P && s < rowptr_in[N]) {
+    const int j = nbr_in[s];
+    nbr[s] = j;
+    src[s] = int(s);
+    atomicAdd(&tcnt[j], 1);
+  }
+}
+}  // namespace
+
+// transpose map + compact species table; expects w.rowptr / w.nbr final and w.tcnt = counts by neighbour
+static int gm_prepare_tail(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const int32_t* Z) {
+  const int64_t N = w.n_atoms, P = w.n_pairs;
+  const int S = p->cfg.n_species;
+  APAX_TRY(exclusive_scan_i32(stream, w.tcnt, w.trowptr, N, w.scan_scratch));
+  APAX_CUDA_TRY(cudaMemsetAsync(w.tcnt, 0, sizeof(int32_t) * (N + 1), stream));
+  if (P > 0) {
+    APAX_LAUNCH(k_transpose_fill, dim3((unsigned)cdiv(P, 256)), dim3(256), 0, stream, w.rowptr, int(N), w.nbr,
+                w.trowptr, w.tcnt, w.tmp_a);
+    APAX_TRY(rowsort_i32(stream, w.trowptr, N, w.tmp_a, nullptr, w.tpos, nullptr));
+  }
+  APAX_CUDA_TRY(cudaMemsetAsync(w.sp_present, 0, sizeof(int32_t) * 128, stream));
+  APAX_LAUNCH(k_species_mark, dim3((unsigned)cdiv(N, 128)), dim3(128), 0, stream, Z, N, S, w.sp_present);
+  APAX_LAUNCH(k_species_build, dim3(1), dim3(256), 0, stream, w.sp_present, S, p->emb, w.sp_map, w.n_sp, w.embc);
+  return APAX_OK;
+}
+
+static int gm_prepare_impl(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w,
+                           const int32_t* Z, const int32_t* idx) {
+  const int64_t N = w.n_atoms, P = w.n_pairs;
+  APAX_CUDA_TRY(cudaMemsetAsync(w.cnt, 0, sizeof(int32_t) * (N + 1), stream));
+  APAX_CUDA_TRY(cudaMemsetAsync(w.tcnt, 0, sizeof(int32_t) * (N + 1), stream));
+  if (P > 0) APAX_LAUNCH(k_coo_count, dim3((unsigned)cdiv(P, 256)), dim3(256), 0, stream, idx, P, int(N), w.cnt, w.tcnt);
+  APAX_TRY(exclusive_scan_i32(stream, w.cnt, w.rowptr, N, w.scan_scratch));
+  APAX_CUDA_TRY(cudaMemsetAsync(w.cnt, 0, sizeof(int32_t) * (N + 1), stream));
+  if (P > 0) {
+    APAX_LAUNCH(k_coo_fill, dim3((unsigned)cdiv(P, 256)), dim3(256), 0, stream, idx, P, int(N), w.rowptr, w.cnt,
+                w.tmp_a, w.tmp_b);
+    // rows ordered by original COO position: deterministic whatever order the atomics landed in
+    APAX_TRY(rowsort_i32(stream, w.rowptr, N, w.tmp_b, w.tmp_a, w.src, w.nbr));
+  }
+  return gm_prepare_tail(stream, p, w, Z);
+}
+
+// list already in CSR form (rows = central atoms, e.g. straight from nl.cu): no COO pass, no row sort
+int gm_prepare_from_csr(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const int32_t* Z,
+                        const int32_t* rowptr_in, const int32_t* nbr_in) {
+  const int64_t N = w.n_atoms, P = w.n_pairs;
+  APAX_CUDA_TRY(cudaMemsetAsync(w.tcnt, 0, sizeof(int32_t) * (N + 1), stream));
+  const int64_t n = (P > N + 1 ? P : N + 1);
+  APAX_LAUNCH(k_csr_import, dim3((unsigned)cdiv(n, 256)), dim3(256), 0, stream, rowptr_in, nbr_in, N, P, w.rowptr, w.nbr,
+              w.src, w.tcnt);
+  return gm_prepare_tail(stream, p, w, Z);
+}
+
+// ================================================================================================
+// pair kernels
+// ================================================================================================
+struct DescConst {
+  float r_max;
+  float beta;       // n_basis^2 / r_max^2            (basis_functions.py:23)
+  float norm;       // (2 beta / pi)^(1/4)            (:24)
+  float two_beta;
+  float pi_f;       // float(np.pi)
+  float mu[NB];     // r_min + (r_max-r_min)/n_basis * b (:25-27)
+};
+
+struct PairGeom {
+  const double* R;
+  const int32_t* Z;
+  const double* offsets;  // [P][3] in COO order, or nullptr
+  const double* box;      // [3][3] device, unused for GAS
+  int mode;
+  int n_species;
+};
+
+namespace {
+
+__device__ __forceinline__ double wrap_unit(double x) {
+  // jnp.mod(x + 0.5, 1.0) - 0.5  (space.py:146-157): fmod then +1 if negative
+  double t = x + 0.5;
+  double m = t - trunc(t);
+  if (m < 0.0) m += 1.0;
+  return m - 0.5;
+}
+
+__device__ __forceinline__ void pair_displacement(const PairGeom& g, const double (&box)[9], const double (&Ra)[3],
+                                                  int j, int64_t coo_pos, float& dx, float& dy, float& dz) {
+  if (g.mode == APAX_DISP_DRVEC) {  // caller supplies dr_vec itself, one row per COO entry
+    dx = float(g.R[3 * coo_pos + 0]); dy = float(g.R[3 * coo_pos + 1]); dz = float(g.R[3 * coo_pos + 2]);
+    return;
+  }
+  double v0 = Ra[0] - g.R[3 * int64_t(j) + 0];
+  double v1 = Ra[1] - g.R[3 * int64_t(j) + 1];
+  double v2 = Ra[2] - g.R[3 * int64_t(j) + 2];
+  double d0, d1, d2;
+  if (g.mode == APAX_DISP_GAS) {
+    d0 = v0; d1 = v1; d2 = v2;
+  } else {
+    if (g.mode == APAX_DISP_MINIMAGE) {
+      v0 = wrap_unit(v0); v1 = wrap_unit(v1); v2 = wrap_unit(v2);
+    }
+    d0 = box[0] * v0 + box[1] * v1 + box[2] * v2;
+    d1 = box[3] * v0 + box[4] * v1 + box[5] * v2;
+    d2 = box[6] * v0 + box[7] * v1 + box[8] * v2;
+    if (g.offsets) {
+      d0 += g.offsets[3 * coo_pos + 0];
+      d1 += g.offsets[3 * coo_pos + 1];
+      d2 += g.offsets[3 * coo_pos + 2];
+    }
+  }
+  dx = float(d0); dy = float(d1); dz = float(d2);  // dr_vec.astype(float32) (gaussian_moment_descriptor.py:33)
+}
+
+__device__ __forceinline__ void load_coeffs(const float* emb, int pt, float (&c)[EMB_STRIDE]) {
+  const float4* p = reinterpret_cast<const float4*>(emb + int64_t(pt) * EMB_STRIDE);
+#pragma unroll
+  for (int q = 0; q < EMB_STRIDE / 4; ++q) {
+    const float4 v = p[q];
+    c[4 * q + 0] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+  }
+}
+
+__device__ __forceinline__ void monomials(float x, float y, float z, float (&mono)[20]) {
+  mono[0] = 1.0f; mono[1] = x; mono[2] = y; mono[3] = z;
+  const float xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
+  mono[4] = xx; mono[5] = xy; mono[6] = xz; mono[7] = yy; mono[8] = yz; mono[9] = zz;
+  mono[10] = xx * x; mono[11] = xx * y; mono[12] = xx * z; mono[13] = xy * y; mono[14] = xy * z;
+  mono[15] = xz * z; mono[16] = yy * y; mono[17] = yy * z; mono[18] = yz * z; mono[19] = zz * z;
+}
+
+__device__ __forceinline__ const float* stage_species_table(const GmWorkspace& ws, float* s_emb) {
+  const int n_sp = *ws.n_sp;
+  const float* emb = ws.embc;
+  if (n_sp <= MAX_SP_SMEM) {
+    const int total = n_sp * n_sp * EMB_STRIDE;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) s_emb[i] = ws.embc[i];
+    emb = s_emb;
+  }
+  __syncthreads();
+  return emb;
+}
+
+// ---- forward: packed moments of every atom.  LPA lanes cooperate on one atom; each lane walks a
+// strided share of the atom's CSR row with the 100 accumulators in registers; an xor-butterfly over
+// the LPA lanes finishes the segmented sum (no atomics, fixed order => bitwise reproducible).
+template <int LPA>
+__global__ void __launch_bounds__(256) k_pair_fwd(GmWorkspace ws, PairGeom geo, DescConst dc) {
+  __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * EMB_STRIDE];
+  const float* emb = stage_species_table(ws, s_emb);
+  const int n_sp = *ws.n_sp;
+  const int64_t gid = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t atom = gid / LPA;
+  const int sub = int(gid % LPA);
+  const bool valid = atom < ws.n_atoms;
+  int beg = 0, end = 0, zc = 0;
+  double Ra[3] = {0.0, 0.0, 0.0};
+  double box[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) box[i] = (geo.mode == APAX_DISP_GAS || geo.mode == APAX_DISP_DRVEC) ? 0.0 : geo.box[i];
+  if (valid) {
+    beg = ws.rowptr[atom];
+    end = ws.rowptr[atom + 1];
+    if (geo.mode != APAX_DISP_DRVEC) {
+      Ra[0] = geo.R[3 * atom + 0]; Ra[1] = geo.R[3 * atom + 1]; Ra[2] = geo.R[3 * atom + 2];
+    }
+    int z = geo.Z[atom];
+    z = z < 0 ? 0 : (z >= geo.n_species ? geo.n_species - 1 : z);
+    zc = ws.sp_map[z];
+  }
+  float acc[NPK];
+#pragma unroll
+  for (int k = 0; k < NPK; ++k) acc[k] = 0.0f;
+
+  for (int e = beg + sub; e < end; e += LPA) {
+    const int j = ws.nbr[e];
+    float dx, dy, dz;
+    pair_displacement(geo, box, Ra, j, ws.src[e], dx, dy, dz);
+    int zj = geo.Z[j];
+    zj = zj < 0 ? 0 : (zj >= geo.n_species ? geo.n_species - 1 : zj);
+    const int pt = zc * n_sp + ws.sp_map[zj];  // embeddings[Z_central, Z_neighbour] (basis_functions.py:139-141)
+    ws.G[e] = make_float4(dx, dy, dz, __int_as_float(pt));
+    const float r2 = dx * dx + dy * dy + dz * dz;
+    const float r = r2 > 0.0f ? sqrtf(r2) : 0.0f;  // space.distance + safe_mask (space.py:314-323)
+    if (r >= dc.r_max) continue;                   // cosine cutoff is exactly 0 there (basis_functions.py:82-85)
+    const float s = 1.0f / (r + 1e-5f);            // dn = dr_vec / (dr + 1e-5) (gaussian_moment_descriptor.py:46-48)
+    float c[EMB_STRIDE];
+    load_coeffs(emb, pt, c);
+    float gb[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const float t = dc.mu[b] - r;
+      gb[b] = dc.norm * expf(-dc.beta * (t * t));
+    }
+    const float fc = 0.5f * (cosf(dc.pi_f * r / dc.r_max) + 1.0f);
+    float mono[20];
+    monomials(dx * s, dy * s, dz * s, mono);
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr) {
+      float pr = 0.0f;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) pr = fmaf(c[rr * NB + b], gb[b], pr);
+      const float rho = pr * fc;
+#pragma unroll
+      for (int k = 0; k < 20; ++k) acc[rr * 20 + k] = fmaf(rho, mono[k], acc[rr * 20 + k]);
+    }
+  }
+#pragma unroll
+  for (int o = LPA / 2; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < NPK; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  }
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < NPK; ++k)
+      if ((k % LPA) == sub) ws.MT[int64_t(k) * ws.ld + atom] = acc[k];
+  }
+}
+
+// ---- backward: per-pair dE/d(dr_vec) from the packed moment adjoints of the central atom.  Pair
+// terms are recomputed from the stored fp32 displacement; nothing per-pair other than (dx,dy,dz) was
+// kept from the forward pass.  Also leaves the row sum (fp64) of the central atom in Frow.
+template <int LPA>
+__global__ void __launch_bounds__(256) k_pair_bwd(GmWorkspace ws, DescConst dc) {
+  __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * EMB_STRIDE];
+  const float* emb = stage_species_table(ws, s_emb);
+  const int64_t gid = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t atom = gid / LPA;
+  const int sub = int(gid % LPA);
+  const bool valid = atom < ws.n_atoms;
+  int beg = 0, end = 0;
+  float a[NPK];
+  if (valid) {
+    beg = ws.rowptr[atom];
+    end = ws.rowptr[atom + 1];
+#pragma unroll
+    for (int k = 0; k < NPK; ++k) a[k] = ws.AT[int64_t(k) * ws.ld + atom];
+  } else {
+#pragma unroll
+    for (int k = 0; k < NPK; ++k) a[k] = 0.0f;
+  }
+  double sx = 0.0, sy = 0.0, sz = 0.0;
+  for (int e = beg + sub; e < end; e += LPA) {
+    const float4 g = ws.G[e];
+    const float dx = g.x, dy = g.y, dz = g.z;
+    const int pt = __float_as_int(g.w);
+    const float r2 = dx * dx + dy * dy + dz * dz;
+    const float r = r2 > 0.0f ? sqrtf(r2) : 0.0f;
+    float4 out = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (r < dc.r_max) {
+      const float s = 1.0f / (r + 1e-5f);
+      const float x = dx * s, y = dy * s, z = dz * s;
+      float c[EMB_STRIDE];
+      load_coeffs(emb, pt, c);
+      float gb[NB], gd[NB];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float t = dc.mu[b] - r;
+        gb[b] = dc.norm * expf(-dc.beta * (t * t));
+        gd[b] = gb[b] * (dc.two_beta * t);  // dG_b/dr
+      }
+      float sn, cs;
+      const float arg = dc.pi_f * r / dc.r_max;
+      sincosf(arg, &sn, &cs);
+      const float fc = 0.5f * (cs + 1.0f);
+      const float fcp = -0.5f * (dc.pi_f / dc.r_max) * sn;
+      float mono[20];
+      monomials(x, y, z, mono);
+      float B[20];
+#pragma unroll
+      for (int k = 0; k < 20; ++k) B[k] = 0.0f;
+      float rbar = 0.0f;
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        float pr = 0.0f, qr = 0.0f;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          pr = fmaf(c[rr * NB + b], gb[b], pr);
+          qr = fmaf(c[rr * NB + b], gd[b], qr);
+        }
+        const float rho = pr * fc;
+        const float drho = fmaf(fcp, pr, fc * qr);  // d rho_r / dr
+        float rhobar = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 20; ++k) {
+          rhobar = fmaf(a[rr * 20 + k], mono[k], rhobar);
+          B[k] = fmaf(rho, a[rr * 20 + k], B[k]);
+        }
+        rbar = fmaf(rhobar, drho, rbar);
+      }
+      // nbar_i = sum_k B_k d mono_k / d n_i
+      const float xx = mono[4], xy = mono[5], xz = mono[6], yy = mono[7], yz = mono[8], zz = mono[9];
+      float nx = B[1] + 2.0f * x * B[4] + y * B[5] + z * B[6] + 3.0f * xx * B[10] + 2.0f * xy * B[11] +
+                 2.0f * xz * B[12] + yy * B[13] + yz * B[14] + zz * B[15];
+      float ny = B[2] + x * B[5] + 2.0f * y * B[7] + z * B[8] + xx * B[11] + 2.0f * xy * B[13] + xz * B[14] +
+                 3.0f * yy * B[16] + 2.0f * yz * B[17] + zz * B[18];
+      float nz = B[3] + x * B[6] + y * B[8] + 2.0f * z * B[9] + xx * B[12] + xy * B[14] + 2.0f * xz * B[15] +
+                 yy * B[17] + 2.0f * yz * B[18] + 3.0f * zz * B[19];
+      // n = d*s, s = 1/(r+eps):  dbar = s*nbar + (d/r) * (rbar - s^2 (nbar.d));  dr/dd = 0 at r = 0
+      const float sdot = nx * dx + ny * dy + nz * dz;
+      const float radial = r > 0.0f ? (rbar - s * s * sdot) / r : 0.0f;
+      out.x = fmaf(radial, dx, s * nx);
+      out.y = fmaf(radial, dy, s * ny);
+      out.z = fmaf(radial, dz, s * nz);
+      sx += double(out.x); sy += double(out.y); sz += double(out.z);
+    }
+    ws.D[e] = out;
+  }
+#pragma unroll
+  for (int o = LPA / 2; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    sz += __shfl_xor_sync(0xffffffffu, sz, o);
+  }
+  if (valid && sub == 0) {
+    ws.Frow[3 * atom + 0] = sx; ws.Frow[3 * atom + 1] = sy; ws.Frow[3 * atom + 2] = sz;
+  }
+}
+
+// ---- force assembly: F_a = -( sum_{e: central a} dbar_e  -  sum_{e: neighbour a} dbar_e ), both sums
+// in fp64 over fp32 per-pair values, i.e. the transpose of the two gathers R[idx[1]], R[idx[0]] in
+// distances.py:55-56 (R is fp64 there, :54).  The second sum walks the transpose map.
+template <int LPA>
+__global__ void __launch_bounds__(256) k_force_gather(GmWorkspace ws, double* __restrict__ F) {
+  const int64_t gid = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t atom = gid / LPA;
+  const int sub = int(gid % LPA);
+  const bool valid = atom < ws.n_atoms;
+  int beg = 0, end = 0;
+  if (valid) {
+    beg = ws.trowptr[atom];
+    end = ws.trowptr[atom + 1];
+  }
+  double tx = 0.0, ty = 0.0, tz = 0.0;
+  for (int k = beg + sub; k < end; k += LPA) {
+    const float4 d = ws.D[ws.tpos[k]];
+    tx += double(d.x); ty += double(d.y); tz += double(d.z);
+  }
+#pragma unroll
+  for (int o = LPA / 2; o > 0; o >>= 1) {
+    tx += __shfl_xor_sync(0xffffffffu, tx, o);
+    ty += __shfl_xor_sync(0xffffffffu, ty, o);
+    tz += __shfl_xor_sync(0xffffffffu, tz, o);
+  }
+  if (valid && sub == 0) {
+    F[3 * atom + 0] = -(ws.Frow[3 * atom + 0] - tx);
+    F[3 * atom + 1] = -(ws.Frow[3 * atom + 1] - ty);
+    F[3 * atom + 2] = -(ws.Frow[3 * atom + 2] - tz);
+  }
+}
+
+// ================================================================================================
+// contractions (thread per atom, generated straight-line code on packed moments)
+// ================================================================================================
+__global__ void __launch_bounds__(128) k_contract_fwd(GmWorkspace ws) {
+  const int64_t atom = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  if (atom >= ws.n_atoms) return;
+  float m[NPK];
+#pragma unroll
+  for (int k = 0; k < NPK; ++k) m[k] = ws.MT[int64_t(k) * ws.ld + atom];
+  float* gt = ws.GT + atom;
+  const int64_t ld = ws.ld;
+  gm_contract_forward(m, [&](int f, float v) { gt[int64_t(f) * ld] = v; });
+}
+
+__global__ void __launch_bounds__(128) k_contract_bwd(GmWorkspace ws) {
+  const int64_t atom = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  if (atom >= ws.n_atoms) return;
+  float m[NPK], a[NPK];
+#pragma unroll
+  for (int k = 0; k < NPK; ++k) {
+    m[k] = ws.MT[int64_t(k) * ws.ld + atom];
+    a[k] = 0.0f;
+  }
+  const float* gt = ws.GT + atom;
+  const int64_t ld = ws.ld;
+  gm_contract_backward(m, a, [&](int f) { return gt[int64_t(f) * ld]; });
+#pragma unroll
+  for (int k = 0; k < NPK; ++k) ws.AT[int64_t(k) * ws.ld + atom] = a[k];
+}
+
+// feature-major [360][ld] -> row-major [N][360] (only for the descriptor-only entry point)
+__global__ void __launch_bounds__(256) k_features_to_rowmajor(const float* __restrict__ GT, int64_t ld, int64_t N,
+                                                              float* __restrict__ g) {
+  __shared__ float tile[32][33];
+  const int64_t a0 = int64_t(blockIdx.x) * 32;
+  const int f0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int f = f0 + r;
+    const int64_t a = a0 + tx;
+    tile[r][tx] = (f < NF && a < N) ? GT[int64_t(f) * ld + a] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t a = a0 + r;
+    const int f = f0 + tx;
+    if (a < N && f < NF) g[a * NF + f] = tile[tx][r];
+  }
+}
+
+// ================================================================================================
+// readout: fp32 SIMT GEMM on feature-major activations.
+//   YT[n][m] = sum_k W[k][n] * X(k, m),  n in [0,NC), m in [0,ld)
+// 128(n) x 128(m) x 8(k) tiles, 256 threads, 8x8 micro-tile, register-prefetch double buffering.
+// ================================================================================================
+constexpr float kSwish = 1.6765324703310907f;  // apax/layers/activation.py:8
+
+enum { PRO_NONE = 0, PRO_HEAD = 1 };
+enum { EPI_STORE = 0, EPI_ACT = 1, EPI_MULD = 2 };
+
+struct GemmArgs {
+  const float* W;     // [K][ldw]
+  int ldw;
+  const float* XT;    // [K][ld]
+  float* YT;          // [NC][ld]   (EPI_ACT: H)
+  float* Y2T;         // EPI_ACT: act'(y) ; EPI_MULD: multiplier D (read)
+  const float* bias;  // EPI_ACT
+  const float* ebar;  // PRO_HEAD: [ld]
+  const float* wcol;  // PRO_HEAD: w2[k*wstride]
+  int wstride;
+  int K;
+  int64_t ld;
+};
+
+template <int PRO, int EPI>
+__global__ void __launch_bounds__(256, 2) k_sgemm(GemmArgs g) {
+  __shared__ __align__(16) float Ws[2][8][128];
+  __shared__ __align__(16) float Xs[2][8][128];
+  const int tid = threadIdx.x;
+  const int64_t m0 = int64_t(blockIdx.x) * 128;
+  const int n0 = blockIdx.y * 128;
+  const int lrow = tid >> 5;         // 0..7
+  const int lcol = (tid & 31) * 4;   // 0..124
+  const int tm = tid & 15, tn = tid >> 4;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+  float4 eb4 = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (PRO == PRO_HEAD) eb4 = *reinterpret_cast<const float4*>(g.ebar + m0 + lcol);
+
+  auto load_w = [&](int k0) {
+    return *reinterpret_cast<const float4*>(g.W + int64_t(k0 + lrow) * g.ldw + n0 + lcol);
+  };
+  auto load_x = [&](int k0) {
+    float4 v = *reinterpret_cast<const float4*>(g.XT + int64_t(k0 + lrow) * g.ld + m0 + lcol);
+    if (PRO == PRO_HEAD) {
+      const float wk = g.wcol[int64_t(k0 + lrow) * g.wstride];
+      v.x *= eb4.x * wk; v.y *= eb4.y * wk; v.z *= eb4.z * wk; v.w *= eb4.w * wk;
+    }
+    return v;
+  };
+
+  float4 wreg = load_w(0), xreg = load_x(0);
+  *reinterpret_cast<float4*>(&Ws[0][lrow][lcol]) = wreg;
+  *reinterpret_cast<float4*>(&Xs[0][lrow][lcol]) = xreg;
+  __syncthreads();
+  const int nk = g.K / 8;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) {
+      wreg = load_w((kt + 1) * 8);
+      xreg = load_x((kt + 1) * 8);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const float4 wa = *reinterpret_cast<const float4*>(&Ws[cur][kk][tn * 4]);
+      const float4 wb = *reinterpret_cast<const float4*>(&Ws[cur][kk][64 + tn * 4]);
+      const float4 xa = *reinterpret_cast<const float4*>(&Xs[cur][kk][tm * 4]);
+      const float4 xb = *reinterpret_cast<const float4*>(&Xs[cur][kk][64 + tm * 4]);
+      const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+      const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      *reinterpret_cast<float4*>(&Ws[cur ^ 1][lrow][lcol]) = wreg;
+      *reinterpret_cast<float4*>(&Xs[cur ^ 1][lrow][lcol]) = xreg;
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + (i < 4 ? tn * 4 + i : 64 + tn * 4 + (i - 4));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t m = m0 + (h == 0 ? tm * 4 : 64 + tm * 4);
+      float4 v = make_float4(acc[i][4 * h + 0], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
+      const int64_t o = int64_t(n) * g.ld + m;
+      if (EPI == EPI_ACT) {
+        const float b = g.bias[n];
+        float y[4] = {v.x + b, v.y + b, v.z + b, v.w + b};
+        float hh[4], dd[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float sg = 1.0f / (1.0f + expf(-y[q]));
+          hh[q] = kSwish * y[q] * sg;                       // variance_preserving_swish
+          dd[q] = kSwish * sg * (1.0f + y[q] * (1.0f - sg)); // its derivative
+        }
+        *reinterpret_cast<float4*>(g.YT + o) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+        *reinterpret_cast<float4*>(g.Y2T + o) = make_float4(dd[0], dd[1], dd[2], dd[3]);
+      } else if (EPI == EPI_MULD) {
+        const float4 d = *reinterpret_cast<const float4*>(g.Y2T + o);
+        *reinterpret_cast<float4*>(g.YT + o) = make_float4(v.x * d.x, v.y * d.y, v.z * d.z, v.w * d.w);
+      } else {
+        *reinterpret_cast<float4*>(g.YT + o) = v;
+      }
+    }
+  }
+}
+
+// ---- output layer + PerElementScaleShift + mask_by_atom (readout.py:47-50, scaling.py:40-50,
+// models.py:109-112).  Thread per atom; h = H2 . w2 + b2 in fp32, E_i in fp64.
+template <int NOUT>
+__global__ void __launch_bounds__(128) k_head(const float* __restrict__ H2T, int64_t ld, int64_t N,
+                                              const float* __restrict__ w2, const float* __restrict__ b2, int n_out,
+                                              const int32_t* __restrict__ Z, int S, const double* __restrict__ scale,
+                                              const double* __restrict__ shift, int mask_atoms,
+                                              double* __restrict__ Eatom, float* __restrict__ ebar) {
+  const int64_t m = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  if (m >= ld) return;
+  if (m >= N) {
+    ebar[m] = 0.0f;
+    for (int k = 0; k < n_out; ++k) Eatom[int64_t(k) * ld + m] = 0.0;
+    return;
+  }
+  float acc[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; ++k) acc[k] = 0.0f;
+  for (int n = 0; n < NH; ++n) {
+    const float h = H2T[int64_t(n) * ld + m];
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k)
+      if (k < n_out) acc[k] = fmaf(h, w2[n * n_out + k], acc[k]);
+  }
+  int z = Z[m];
+  const double msk = (mask_atoms && z == 0) ? 0.0 : 1.0;
+  z = z < 0 ? 0 : (z >= S ? S - 1 : z);
+  const double sc = scale[z], sh = shift[z];
+#pragma unroll
+  for (int k = 0; k < NOUT; ++k)
+    if (k < n_out) Eatom[int64_t(k) * ld + m] = (sc * double(acc[k] + b2[k]) + sh) * msk;
+  ebar[m] = float(sc * msk);  // cotangent of h after the fp64->fp32 cast
+}
+
+__device__ __forceinline__ int64_t cdiv_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- fp64 energy sum, two fixed-shape stages => deterministic (apax/utils/math.py:7-12)
+__global__ void __launch_bounds__(256) k_energy_partial(const double* __restrict__ Eatom, int64_t ld, int64_t N,
+                                                        double* __restrict__ partial) {
+  __shared__ double sm[256];
+  const int head = blockIdx.y;
+  const int64_t chunk = cdiv_dev(N, int64_t(gridDim.x));
+  const int64_t b = int64_t(blockIdx.x) * chunk, e = min(N, b + chunk);
+  double s = 0.0;
+  for (int64_t i = b + threadIdx.x; i < e; i += 256) s += Eatom[int64_t(head) * ld + i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[head * 256 + blockIdx.x] = sm[0];
+}
+
+__global__ void k_energy_final(const double* __restrict__ partial, int n_blocks, double* __restrict__ energy) {
+  const int head = blockIdx.x;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n_blocks; ++i) s += partial[head * 256 + i];
+    energy[head] = s;
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// host orchestration
+// ================================================================================================
+static DescConst make_desc_const(const apax_gm_config& cfg) {
+  DescConst dc{};
+  dc.r_max = cfg.r_max;
+  const double beta = double(cfg.n_basis) * cfg.n_basis / (double(cfg.r_max) * cfg.r_max);
+  dc.beta = float(beta);
+  dc.two_beta = float(2.0 * beta);
+  dc.norm = float(pow(2.0 * beta / M_PI, 0.25));
+  dc.pi_f = float(M_PI);
+  for (int b = 0; b < NB; ++b)
+    dc.mu[b] = float(double(cfg.r_min) + (double(cfg.r_max) - double(cfg.r_min)) / cfg.n_basis * b);
+  return dc;
+}
+
+static int pick_lpa(int64_t n_atoms) {
+  if (n_atoms >= 100000) return 4;
+  if (n_atoms >= 4096) return 8;
+  if (n_atoms >= 1024) return 16;
+  return 32;
+}
+
+template <int LPA>
+static int launch_pair_fwd(cudaStream_t s, const GmWorkspace& w, const PairGeom& geo, const DescConst& dc) {
+  APAX_LAUNCH(k_pair_fwd<LPA>, dim3((unsigned)cdiv(w.n_atoms * LPA, 256)), dim3(256), 0, s, w, geo, dc);
+  return APAX_OK;
+}
+template <int LPA>
+static int launch_pair_bwd(cudaStream_t s, const GmWorkspace& w, const DescConst& dc) {
+  APAX_LAUNCH(k_pair_bwd<LPA>, dim3((unsigned)cdiv(w.n_atoms * LPA, 256)), dim3(256), 0, s, w, dc);
+  return APAX_OK;
+}
+template <int LPA>
+static int launch_force_gather(cudaStream_t s, const GmWorkspace& w, double* F) {
+  APAX_LAUNCH(k_force_gather<LPA>, dim3((unsigned)cdiv(w.n_atoms * LPA, 256)), dim3(256), 0, s, w, F);
+  return APAX_OK;
+}
+
+#define APAX_DISPATCH_LPA(lpa, fn, ...)            \
+  do {                                             \
+    switch (lpa) {                                 \
+      case 4: APAX_TRY(fn<4>(__VA_ARGS__)); break;   \
+      case 8: APAX_TRY(fn<8>(__VA_ARGS__)); break;   \
+      case 16: APAX_TRY(fn<16>(__VA_ARGS__)); break; \
+      default: APAX_TRY(fn<32>(__VA_ARGS__)); break; \
+    }                                              \
+  } while (0)
+
+static PairGeom make_geom(const apax_gm_params_impl* p, const double* R, const int32_t* Z, const double* box,
+                          const double* offsets, int mode) {
+  PairGeom geo{};
+  geo.R = R;
+  geo.Z = Z;
+  geo.offsets = offsets;
+  geo.mode = mode;
+  geo.n_species = p->cfg.n_species;
+  geo.box = box;
+  return geo;
+}
+
+// descriptor forward: moments + contractions -> GT
+static int gm_descriptor_impl(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w,
+                              const PairGeom& geo) {
+  const DescConst dc = make_desc_const(p->cfg);
+  const int lpa = pick_lpa(w.n_atoms);
+  APAX_DISPATCH_LPA(lpa, launch_pair_fwd, stream, w, geo, dc);
+  APAX_LAUNCH(k_contract_fwd, dim3((unsigned)cdiv(w.n_atoms, 128)), dim3(128), 0, stream, w);
+  return APAX_OK;
+}
+
+static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w,
+                           const PairGeom& geo, double* energy, double* forces) {
+  const int64_t N = w.n_atoms, ld = w.ld;
+  const int n_out = p->cfg.n_out;
+  const DescConst dc = make_desc_const(p->cfg);
+  const int lpa = pick_lpa(N);
+  APAX_TRY(gm_descriptor_impl(stream, p, w, geo));
+
+  const dim3 grid_h((unsigned)(ld / 128), NH / 128);
+  {  // layer 0: 360 -> 256
+    GemmArgs a{};
+    a.W = p->w0; a.ldw = NH; a.XT = w.GT; a.YT = w.H1T; a.Y2T = w.D1T; a.bias = p->b0; a.K = NF; a.ld = ld;
+    auto kfn = k_sgemm<PRO_NONE, EPI_ACT>;
+    APAX_LAUNCH(kfn, grid_h, dim3(256), 0, stream, a);
+  }
+  {  // layer 1: 256 -> 256
+    GemmArgs a{};
+    a.W = p->w1; a.ldw = NH; a.XT = w.H1T; a.YT = w.H2T; a.Y2T = w.D2T; a.bias = p->b1; a.K = NH; a.ld = ld;
+    auto kfn = k_sgemm<PRO_NONE, EPI_ACT>;
+    APAX_LAUNCH(kfn, grid_h, dim3(256), 0, stream, a);
+  }
+  if (n_out == 1) {
+    APAX_LAUNCH(k_head<1>, dim3((unsigned)cdiv(ld, 128)), dim3(128), 0, stream, w.H2T, ld, N, p->w2, p->b2, n_out,
+                geo.Z, p->cfg.n_species, p->scale, p->shift, p->cfg.mask_atoms, w.Eatom, w.ebar);
+  } else {
+    APAX_LAUNCH(k_head<MAX_OUT>, dim3((unsigned)cdiv(ld, 128)), dim3(128), 0, stream, w.H2T, ld, N, p->w2, p->b2,
+                n_out, geo.Z, p->cfg.n_species, p->scale, p->shift, p->cfg.mask_atoms, w.Eatom, w.ebar);
+  }
+  const int n_blk = int(N < 256 * 64 ? 1 : (N / (256 * 64) > 256 ? 256 : N / (256 * 64)));
+  APAX_LAUNCH(k_energy_partial, dim3(n_blk, n_out), dim3(256), 0, stream, w.Eatom, ld, N, w.partial);
+  APAX_LAUNCH(k_energy_final, dim3(n_out), dim3(32), 0, stream, w.partial, n_blk, energy);
+  if (!forces) return APAX_OK;
+
+  for (int head = 0; head < n_out; ++head) {
+    {  // dE/dy1 = (W1 . dE/dy2) * act'(y1),  dE/dy2 = ebar * w2[:,head] * act'(y2) applied on load
+      GemmArgs a{};
+      a.W = p->w1t; a.ldw = NH; a.XT = w.D2T; a.YT = w.H1T; a.Y2T = w.D1T; a.K = NH; a.ld = ld;
+      a.ebar = w.ebar; a.wcol = p->w2 + head; a.wstride = n_out;
+      auto kfn = k_sgemm<PRO_HEAD, EPI_MULD>;
+      APAX_LAUNCH(kfn, grid_h, dim3(256), 0, stream, a);
+    }
+    {  // dE/dg = W0 . dE/dy1   (360 rows padded to 384)
+      GemmArgs a{};
+      a.W = p->w0t; a.ldw = NFP; a.XT = w.H1T; a.YT = w.GT; a.K = NH; a.ld = ld;
+      auto kfn = k_sgemm<PRO_NONE, EPI_STORE>;
+      APAX_LAUNCH(kfn, dim3((unsigned)(ld / 128), NFP / 128), dim3(256), 0, stream, a);
+    }
+    APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(N, 128)), dim3(128), 0, stream, w);
+    APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc);
+    APAX_DISPATCH_LPA(lpa, launch_force_gather, stream, w, forces + int64_t(head) * N * 3);
+  }
+  return APAX_OK;
+}
+
+int gm_compute_device(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const double* R,
+                      const int32_t* Z, const double* box, const double* offsets, int mode, double* energy,
+                      double* forces) {
+  const PairGeom geo = make_geom(p, R, Z, box, offsets, mode);
+  return gm_compute_impl(stream, p, w, geo, energy, forces);
+}
+
+}  // namespace apax
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace apax;
+
+static int validate_cfg(const apax_gm_config* c) {
+  if (!c) return APAX_ERR_INVALID_ARG;
+  if (c->n_radial != NR || c->n_basis != NB || c->n_contr != 8 || c->n_hidden1 != NH || c->n_hidden2 != NH)
+    return APAX_ERR_UNSUPPORTED;
+  if (c->n_out < 1 || c->n_out > MAX_OUT || c->n_species < 1 || c->n_species > 128) return APAX_ERR_UNSUPPORTED;
+  if (!(c->r_max > c->r_min) || !(c->r_min >= 0.f)) return APAX_ERR_INVALID_ARG;
+  return APAX_OK;
+}
+
+struct apax_gm_params : apax_gm_params_impl {};
+
+template <class T>
+static int upload(T** dst, const T* src, size_t n) {
+  APAX_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(dst), n * sizeof(T)));
+  APAX_CUDA_TRY(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return APAX_OK;
+}
+
+extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb, const float* w0, const float* b0,
+                                     const float* w1, const float* b1, const float* w2, const float* b2,
+                                     const double* scale, const double* shift, apax_gm_params** out) {
+  APAX_TRY(validate_cfg(cfg));
+  if (!emb || !w0 || !b0 || !w1 || !b1 || !w2 || !b2 || !scale || !shift || !out) return APAX_ERR_INVALID_ARG;
+  apax_gm_params* p = new apax_gm_params();
+  p->cfg = *cfg;
+  const int S = cfg->n_species, n_out = cfg->n_out;
+  // NTKLinear (ntk_linear.py:42-45): y = sqrt(1/in) * x.w + 0.1 * b, folded into the stored weights
+  auto wf = [&](int fan_in) { return cfg->use_ntk ? float(sqrt(1.0 / fan_in)) : 1.0f; };
+  const float bf = cfg->use_ntk ? 0.1f : 1.0f;
+  {
+    const size_t n = size_t(S) * S * NR * NB;
+    float* h = new float[n];
+    const float sc = cfg->use_embed_norm ? float(1.0 / sqrt(double(cfg->n_basis))) : 1.0f;
+    for (size_t i = 0; i < n; ++i) h[i] = sc * emb[i];  // embed_norm * coeffs (basis_functions.py:145-146)
+    int st = upload(&p->emb, h, n);
+    delete[] h;
+    if (st) return st;
+  }
+  {
+    float* h = new float[size_t(NF) * NH];
+    float* ht = new float[size_t(NH) * NFP]();
+    for (int k = 0; k < NF; ++k)
+      for (int n = 0; n < NH; ++n) {
+        h[size_t(k) * NH + n] = wf(NF) * w0[size_t(k) * NH + n];
+        ht[size_t(n) * NFP + k] = h[size_t(k) * NH + n];
+      }
+    int st = upload(&p->w0, h, size_t(NF) * NH);
+    if (!st) st = upload(&p->w0t, ht, size_t(NH) * NFP);
+    delete[] h;
+    delete[] ht;
+    if (st) return st;
+  }
+  {
+    float* h = new float[size_t(NH) * NH];
+    float* ht = new float[size_t(NH) * NH];
+    for (int k = 0; k < NH; ++k)
+      for (int n = 0; n < NH; ++n) {
+        h[size_t(k) * NH + n] = wf(NH) * w1[size_t(k) * NH + n];
+        ht[size_t(n) * NH + k] = h[size_t(k) * NH + n];
+      }
+    int st = upload(&p->w1, h, size_t(NH) * NH);
+    if (!st) st = upload(&p->w1t, ht, size_t(NH) * NH);
+    delete[] h;
+    delete[] ht;
+    if (st) return st;
+  }
+  {
+    float* h = new float[size_t(NH) * n_out];
+    for (size_t i = 0; i < size_t(NH) * n_out; ++i) h[i] = wf(NH) * w2[i];
+    int st = upload(&p->w2, h, size_t(NH) * n_out);
+    delete[] h;
+    if (st) return st;
+  }
+  {
+    float hb0[NH], hb1[NH], hb2[MAX_OUT];
+    for (int i = 0; i < NH; ++i) { hb0[i] = bf * b0[i]; hb1[i] = bf * b1[i]; }
+    for (int i = 0; i < n_out; ++i) hb2[i] = bf * b2[i];
+    APAX_TRY(upload(&p->b0, hb0, NH));
+    APAX_TRY(upload(&p->b1, hb1, NH));
+    APAX_TRY(upload(&p->b2, hb2, n_out));
+  }
+  APAX_TRY(upload(&p->scale, scale, S));
+  APAX_TRY(upload(&p->shift, shift, S));
+  *out = p;
+  return APAX_OK;
+}
+
+extern "C" void apax_gm_params_destroy(apax_gm_params* p) {
+  if (!p) return;
+  cudaFree(p->emb); cudaFree(p->w0); cudaFree(p->w0t); cudaFree(p->b0); cudaFree(p->w1); cudaFree(p->w1t);
+  cudaFree(p->b1); cudaFree(p->w2); cudaFree(p->b2); cudaFree(p->scale); cudaFree(p->shift);
+  delete p;
+}
+
+extern "C" size_t apax_gm_workspace_bytes(int64_t n_atoms, int64_t n_pairs, int32_t n_out) {
+  if (n_atoms < 0 || n_pairs < 0 || n_out < 1) return 0;
+  return carve_gm_workspace(nullptr, n_atoms, n_pairs, n_out, 128, nullptr);
+}
+
+static int get_ws(const apax_gm_params* p, int64_t n_atoms, int64_t n_pairs, void* workspace, size_t bytes,
+                  GmWorkspace* w) {
+  if (!p || !workspace || n_atoms < 1 || n_pairs < 0) return APAX_ERR_INVALID_ARG;
+  if (n_atoms >= (int64_t(1) << 31) - 256 || n_pairs >= (int64_t(1) << 31) - 256) return APAX_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return APAX_ERR_INVALID_ARG;
+  const size_t need = carve_gm_workspace(workspace, n_atoms, n_pairs, p->cfg.n_out, 128, w);
+  if (need > bytes) return APAX_ERR_WORKSPACE;
+  return APAX_OK;
+}
+
+extern "C" int apax_gm_prepare(apax_stream_t stream, const apax_gm_params* params, const int32_t* Z,
+                               const int32_t* idx, int64_t n_atoms, int64_t n_pairs, void* workspace,
+                               size_t workspace_bytes) {
+  GmWorkspace w;
+  APAX_TRY(get_ws(params, n_atoms, n_pairs, workspace, workspace_bytes, &w));
+  if (!Z || (n_pairs > 0 && !idx)) return APAX_ERR_INVALID_ARG;
+  return gm_prepare_impl(stream, params, w, Z, idx);
+}
+
+extern "C" int apax_gm_compute(apax_stream_t stream, const apax_gm_params* params, const double* R,
+                               const int32_t* Z, const double* box, const double* offsets, int64_t n_atoms,
+                               int64_t n_pairs, int32_t disp_mode, double* energy, double* forces, void* workspace,
+                               size_t workspace_bytes) {
+  GmWorkspace w;
+  APAX_TRY(get_ws(params, n_atoms, n_pairs, workspace, workspace_bytes, &w));
+  if (!R || !Z || !energy) return APAX_ERR_INVALID_ARG;
+  if (disp_mode < APAX_DISP_GAS || disp_mode > APAX_DISP_MINIMAGE) return APAX_ERR_INVALID_ARG;
+  if (disp_mode != APAX_DISP_GAS && !box) return APAX_ERR_INVALID_ARG;
+  const PairGeom geo = make_geom(params, R, Z, box, offsets, disp_mode);
+  return gm_compute_impl(stream, params, w, geo, energy, forces);
+}
+
+extern "C" int apax_gm_energy_forces(apax_stream_t stream, const apax_gm_params* params, const double* R,
+                                     const int32_t* Z, const int32_t* idx, const double* box, const double* offsets,
+                                     int64_t n_atoms, int64_t n_pairs, int32_t disp_mode, double* energy,
+                                     double* forces, void* workspace, size_t workspace_bytes) {
+  APAX_TRY(apax_gm_prepare(stream, params, Z, idx, n_atoms, n_pairs, workspace, workspace_bytes));
+  return apax_gm_compute(stream, params, R, Z, box, offsets, n_atoms, n_pairs, disp_mode, energy, forces, workspace,
+                         workspace_bytes);
+}
+
+extern "C" int apax_gm_descriptor(apax_stream_t stream, const apax_gm_params* params, const double* R,
+                                  const int32_t* Z, const int32_t* idx, const double* box, const double* offsets,
+                                  int64_t n_atoms, int64_t n_pairs, int32_t disp_mode, float* g, void* workspace,
+                                  size_t workspace_bytes) {
+  GmWorkspace w;
+  APAX_TRY(get_ws(params, n_atoms, n_pairs, workspace, workspace_bytes, &w));
+  if (!R || !Z || !g || (n_pairs > 0 && !idx)) return APAX_ERR_INVALID_ARG;
+  if (disp_mode < APAX_DISP_GAS || disp_mode > APAX_DISP_DRVEC) return APAX_ERR_INVALID_ARG;
+  APAX_TRY(gm_prepare_impl(stream, params, w, Z, idx));
+  if ((disp_mode == APAX_DISP_OFFSETS || disp_mode == APAX_DISP_MINIMAGE) && !box) return APAX_ERR_INVALID_ARG;
+  const PairGeom geo = make_geom(params, R, Z, box, offsets, disp_mode);
+  APAX_TRY(gm_descriptor_impl(stream, params, w, geo));
+  APAX_LAUNCH(k_features_to_rowmajor, dim3((unsigned)cdiv(n_atoms, 32), cdiv(NF, 32)), dim3(256), 0, stream, w.GT,
+              w.ld, n_atoms, g);
+  return APAX_OK;
+}

@@ -1,0 +1,82 @@
+// Internal layout of the GMNN hot-path workspace and parameter block.
+#pragma once
+#include "common.cuh"
+
+namespace apax {
+
+constexpr int NR = 5;        // radial channels
+constexpr int NB = 7;        // Gaussian basis functions
+constexpr int NPK = 100;     // packed moments per atom: 5 x (1+3+6+10)
+constexpr int NF = 360;      // descriptor features
+constexpr int NFP = 384;     // feature rows padded to a multiple of the GEMM tile
+constexpr int NH = 256;      // hidden width
+constexpr int EMB_STRIDE = 36;  // 35 coefficients padded to 9 float4
+constexpr int MAX_SP_SMEM = 8;  // compact species tables up to 8x8 are staged in shared memory
+constexpr int MAX_OUT = 16;
+
+struct apax_gm_params_impl {
+  apax_gm_config cfg;
+  // device copies
+  float* emb;    // [S][S][5][7], pre-multiplied by 1/sqrt(n_basis) when use_embed_norm
+  float* w0;     // [360][256]
+  float* w0t;    // [256][384]  (transposed, zero padded) for the backward GEMM
+  float* b0;     // [256]
+  float* w1;     // [256][256]
+  float* w1t;    // [256][256]
+  float* b1;     // [256]
+  float* w2;     // [256][n_out]
+  float* b2;     // [n_out]
+  double* scale; // [S]
+  double* shift; // [S]
+};
+
+// Everything the compute kernels need, carved out of the caller's workspace.  All feature-major
+// ("transposed") matrices have leading dimension ld = round_up(n_atoms, 128) along the atom axis.
+struct GmWorkspace {
+  int64_t n_atoms, n_pairs, ld;
+  int32_t n_out;
+  // list (CSR by central atom) + transpose
+  int32_t* rowptr;   // [N+1]
+  int32_t* trowptr;  // [N+1]
+  int32_t* nbr;      // [P] neighbour index of CSR slot
+  int32_t* src;      // [P] original COO position of CSR slot
+  int32_t* tpos;     // [P] for atom a: CSR slots in which a is the neighbour, ascending
+  int32_t* tmp_a;    // [P]
+  int32_t* tmp_b;    // [P]
+  int32_t* cnt;      // [N+1]
+  int32_t* tcnt;     // [N+1]
+  int32_t* scan_scratch;
+  // species compaction
+  int32_t* sp_present;  // [128]
+  int32_t* sp_map;      // [128] Z -> compact id
+  int32_t* n_sp;        // [1]
+  float* embc;          // [n_sp*n_sp][36]
+  // per pair
+  float4* G;  // (dx,dy,dz, pair-table index as int bits)
+  float4* D;  // dE/d(dr_vec) per pair
+  // per atom, feature-major
+  float* MT;   // [100][ld] packed moments
+  float* AT;   // [100][ld] packed moment adjoints
+  float* GT;   // [384][ld] features g, later overwritten by dE/dg
+  float* H1T;  // [256][ld] act(y1), later dE/dy1
+  float* D1T;  // [256][ld] act'(y1)
+  float* H2T;  // [256][ld]
+  float* D2T;  // [256][ld]
+  float* ebar;     // [ld]   dE/dh per atom (scale*mask) in fp32
+  double* Eatom;   // [n_out][ld]
+  double* partial; // [n_out][256]
+  double* Frow;    // [N][3] sum of dbar over the rows of the central atom
+};
+
+size_t carve_gm_workspace(void* base, int64_t n_atoms, int64_t n_pairs, int32_t n_out, int32_t n_species,
+                          GmWorkspace* ws);
+
+// exported to ctx.cu
+int gm_prepare_from_csr(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const int32_t* Z,
+                        const int32_t* rowptr_in, const int32_t* nbr_in);
+struct PairGeom;
+int gm_compute_device(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const double* R,
+                      const int32_t* Z, const double* box, const double* offsets, int mode, double* energy,
+                      double* forces);
+
+}  // namespace apax

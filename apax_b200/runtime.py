@@ -1,0 +1,287 @@
+"""Thin host runtime over the C ABI: device buffers and streams come from torch (plumbing only),
+every computation is a call into libapax_b200.so.  No oracle, no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DISP_DRVEC, DISP_GAS, DISP_MINIMAGE, DISP_OFFSETS, GmConfig, check, lib
+
+MODES = {"gas": DISP_GAS, "offsets": DISP_OFFSETS, "minimage": DISP_MINIMAGE, "drvec": DISP_DRVEC}
+N_FEATURES = 360
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.ApaxB200Error(_lib.ERR_UNSUPPORTED, "runtime", "no CUDA device: apax_b200 has no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def to_device(x, dtype: torch.dtype) -> torch.Tensor:
+    """Host array or tensor -> contiguous CUDA tensor of `dtype` (no copy if already there)."""
+    dev = _require_cuda()
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(dev)
+
+
+def default_config(n_out: int = 1, **overrides) -> dict:
+    """Flax-module defaults of the GMNN path (SURVEY.md §8 header; apax/config/model_config.py:147-227)."""
+    cfg = dict(n_species=119, n_radial=5, n_basis=7, n_contr=8, nn=[256, 256], n_out=n_out, use_ntk=False,
+               use_embed_norm=True, mask_atoms=True, r_min=0.5, r_max=6.0)
+    cfg.update(overrides)
+    return cfg
+
+
+class DeviceParams:
+    """Device-resident copy of an apax parameter tree (SURVEY.md §5 layout), owned by the C library.
+
+    Accepts {"params": {"energy_model": {...}}} or the inner "energy_model" dict; arrays may be
+    numpy / torch / anything np.asarray understands.
+    """
+
+    def __init__(self, params: dict, config: Optional[dict] = None):
+        _require_cuda()
+        tree = params.get("params", params)
+        tree = tree.get("energy_model", tree)
+        emb = np.ascontiguousarray(np.asarray(tree["representation"]["radial_fn"]["atomic_type_embedding"]), dtype=np.float32)
+        ro = tree["readout"]
+        layers = [ro[f"dense_{i}"] for i in range(len(ro))]
+        if len(layers) != 3:
+            raise _lib.ApaxB200Error(_lib.ERR_UNSUPPORTED, "DeviceParams", "readout must be [256, 256] + output layer")
+        w = [np.ascontiguousarray(np.asarray(l["w"]), dtype=np.float32) for l in layers]
+        b = [np.ascontiguousarray(np.asarray(l["b"]), dtype=np.float32) for l in layers]
+        n_out = int(w[2].shape[1])
+        cfg = default_config(n_out=n_out)
+        if config:
+            cfg.update(config)
+        cfg["n_out"] = n_out
+        cfg["n_species"] = int(emb.shape[0])
+        if emb.shape != (cfg["n_species"], cfg["n_species"], cfg["n_radial"], cfg["n_basis"]):
+            raise _lib.ApaxB200Error(_lib.ERR_INVALID_ARG, "DeviceParams", f"embedding shape {emb.shape}")
+        if w[0].shape != (N_FEATURES, 256) or w[1].shape != (256, 256) or w[2].shape[0] != 256:
+            raise _lib.ApaxB200Error(_lib.ERR_UNSUPPORTED, "DeviceParams", "dense shapes must be 360x256, 256x256, 256xn_out")
+        ss = tree["scale_shift"]
+        S = cfg["n_species"]
+        scale = np.ascontiguousarray(np.broadcast_to(np.asarray(ss["scale_per_element"], dtype=np.float64).reshape(-1), (S,)))
+        shift = np.ascontiguousarray(np.broadcast_to(np.asarray(ss["shift_per_element"], dtype=np.float64).reshape(-1), (S,)))
+        self.config = cfg
+        self.n_out = n_out
+        c = GmConfig(n_species=S, n_radial=cfg["n_radial"], n_basis=cfg["n_basis"], n_contr=cfg["n_contr"],
+                     n_hidden1=cfg["nn"][0], n_hidden2=cfg["nn"][1], n_out=n_out, use_ntk=int(cfg["use_ntk"]),
+                     use_embed_norm=int(cfg["use_embed_norm"]), mask_atoms=int(cfg["mask_atoms"]),
+                     r_min=cfg["r_min"], r_max=cfg["r_max"])
+        self._keep = (emb, w, b, scale, shift)
+        handle = C.c_void_p()
+
+        def hp(a):
+            return a.ctypes.data_as(C.c_void_p)
+
+        check(lib().apax_gm_params_create(C.byref(c), hp(emb), hp(w[0]), hp(b[0]), hp(w[1]), hp(b[1]), hp(w[2]), hp(b[2]),
+                                          hp(scale), hp(shift), C.byref(handle)), "apax_gm_params_create")
+        self.handle = handle
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                lib().apax_gm_params_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+
+class Workspace:
+    """Caller-owned scratch for the gm_* entry points, grown on demand and reused."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=_require_cuda())
+        return self.buf
+
+    @staticmethod
+    def aligned_ptr(buf: torch.Tensor) -> int:
+        return (buf.data_ptr() + 255) & ~255
+
+
+_default_ws = Workspace()
+_nl_ws = Workspace()
+
+
+def _gm_ws(n_atoms: int, n_pairs: int, n_out: int, ws: Optional[Workspace]):
+    ws = ws or _default_ws
+    nbytes = lib().apax_gm_workspace_bytes(n_atoms, n_pairs, n_out)
+    buf = ws.get(nbytes)
+    return C.c_void_p(Workspace.aligned_ptr(buf)), C.c_size_t(nbytes)
+
+
+def energy_forces(params: DeviceParams, R, Z, idx, box, offsets, mode: str = "offsets", forces: bool = True,
+                  workspace: Optional[Workspace] = None):
+    """EnergyDerivativeModel.apply (apax/nn/models.py:146-171) on the GPU.
+
+    Returns (energy f64 tensor [n_out], forces f64 tensor [n_out, N, 3] or None), asynchronous on the
+    current torch stream.
+    """
+    dev = _require_cuda()
+    R = to_device(R, torch.float64)
+    Z = to_device(Z, torch.int32)
+    idx = to_device(idx, torch.int32)
+    n_atoms, n_pairs = int(R.shape[0]), int(idx.shape[1])
+    box_d = to_device(np.zeros((3, 3)) if box is None else box, torch.float64)
+    if box_d.numel() == 3:  # apax passes np.array([0,0,0]) for gas phase
+        box_d = torch.diag(box_d)
+    off_d = None if offsets is None else to_device(offsets, torch.float64)
+    if off_d is not None and off_d.dim() == 1:  # simulate.py:71 passes a broadcast [0,0,0]
+        off_d = None if not bool(off_d.any()) else off_d.expand(n_pairs, 3).contiguous()
+    energy = torch.empty(params.n_out, dtype=torch.float64, device=dev)
+    F = torch.empty((params.n_out, n_atoms, 3), dtype=torch.float64, device=dev) if forces else None
+    wp, wb = _gm_ws(n_atoms, n_pairs, params.n_out, workspace)
+    check(lib().apax_gm_energy_forces(_stream_ptr(), params.handle, _ptr(R), _ptr(Z), _ptr(idx), _ptr(box_d), _ptr(off_d),
+                                      n_atoms, n_pairs, MODES[mode], _ptr(energy), _ptr(F), wp, wb),
+          "apax_gm_energy_forces")
+    return energy, F
+
+
+class PreparedSystem:
+    """A neighbour list prepared once (apax_gm_prepare) and evaluated many times (apax_gm_compute)."""
+
+    def __init__(self, params: DeviceParams, Z, idx, n_atoms: Optional[int] = None):
+        self.params = params
+        self.Z = to_device(Z, torch.int32)
+        self.idx = to_device(idx, torch.int32)
+        self.n_atoms = int(self.Z.shape[0]) if n_atoms is None else n_atoms
+        self.n_pairs = int(self.idx.shape[1])
+        self.ws = Workspace()
+        self.wp, self.wb = _gm_ws(self.n_atoms, self.n_pairs, params.n_out, self.ws)
+        check(lib().apax_gm_prepare(_stream_ptr(), params.handle, _ptr(self.Z), _ptr(self.idx), self.n_atoms, self.n_pairs,
+                                    self.wp, self.wb), "apax_gm_prepare")
+        dev = self.Z.device
+        self.energy = torch.empty(params.n_out, dtype=torch.float64, device=dev)
+        self.forces = torch.empty((params.n_out, self.n_atoms, 3), dtype=torch.float64, device=dev)
+
+    def compute(self, R: torch.Tensor, box: Optional[torch.Tensor], offsets: Optional[torch.Tensor], mode: str,
+                forces: bool = True):
+        check(lib().apax_gm_compute(_stream_ptr(), self.params.handle, _ptr(R), _ptr(self.Z), _ptr(box), _ptr(offsets),
+                                    self.n_atoms, self.n_pairs, MODES[mode], _ptr(self.energy),
+                                    _ptr(self.forces if forces else None), self.wp, self.wb), "apax_gm_compute")
+        return self.energy, (self.forces if forces else None)
+
+
+def descriptor(params: DeviceParams, R, Z, idx, box=None, offsets=None, mode: str = "gas",
+               workspace: Optional[Workspace] = None) -> torch.Tensor:
+    """GaussianMomentDescriptor features [N, 360] f32; with mode="drvec", R is dr_vec [P,3]."""
+    dev = _require_cuda()
+    R = to_device(R, torch.float64)
+    Z = to_device(Z, torch.int32)
+    idx = to_device(idx, torch.int32)
+    n_atoms, n_pairs = int(Z.shape[0]), int(idx.shape[1])
+    box_d = None if box is None else to_device(box, torch.float64)
+    off_d = None if offsets is None else to_device(offsets, torch.float64)
+    g = torch.empty((n_atoms, N_FEATURES), dtype=torch.float32, device=dev)
+    wp, wb = _gm_ws(n_atoms, n_pairs, params.n_out, workspace)
+    check(lib().apax_gm_descriptor(_stream_ptr(), params.handle, _ptr(R), _ptr(Z), _ptr(idx), _ptr(box_d), _ptr(off_d),
+                                   n_atoms, n_pairs, MODES[mode], _ptr(g), wp, wb), "apax_gm_descriptor")
+    return g
+
+
+# ------------------------------------------------------------------------------------------- lists
+def nl_build_minimage(frac, box, cutoff: float, capacity: int):
+    """JaxMD Sparse min-image list (partition.py:478-787): idx i32 [2,capacity] padded with N,
+    n_found i32 [1], overflow u8 [1] -- all device tensors."""
+    dev = _require_cuda()
+    frac = to_device(frac, torch.float64)
+    box = to_device(box, torch.float64)
+    n = int(frac.shape[0])
+    idx = torch.empty((2, capacity), dtype=torch.int32, device=dev)
+    n_found = torch.zeros(1, dtype=torch.int32, device=dev)
+    overflow = torch.zeros(1, dtype=torch.uint8, device=dev)
+    nbytes = lib().apax_nl_workspace_bytes(n, capacity)
+    buf = _nl_ws.get(nbytes)
+    check(lib().apax_nl_build_minimage(_stream_ptr(), _ptr(frac), _ptr(box), n, float(cutoff), capacity, _ptr(idx),
+                                       _ptr(n_found), _ptr(overflow), C.c_void_p(Workspace.aligned_ptr(buf)),
+                                       C.c_size_t(nbytes)), "apax_nl_build_minimage")
+    return idx, n_found, overflow
+
+
+def nl_build_images(positions, cell, cutoff: float, capacity: int, pbc: bool = True, want_offsets: bool = True):
+    """vesin-style full list with shifts (ase_calc.py:337-355): idx [2,capacity] zero padded,
+    shifts i32 [capacity,3], offsets f64 [capacity,3] = S @ cell, n_found, overflow."""
+    dev = _require_cuda()
+    pos = to_device(positions, torch.float64)
+    cell = to_device(cell, torch.float64)
+    n = int(pos.shape[0])
+    idx = torch.empty((2, capacity), dtype=torch.int32, device=dev)
+    shifts = torch.empty((capacity, 3), dtype=torch.int32, device=dev)
+    offsets = torch.empty((capacity, 3), dtype=torch.float64, device=dev) if want_offsets else None
+    n_found = torch.zeros(1, dtype=torch.int32, device=dev)
+    overflow = torch.zeros(1, dtype=torch.uint8, device=dev)
+    nbytes = lib().apax_nl_workspace_bytes(n, capacity)
+    buf = _nl_ws.get(nbytes)
+    check(lib().apax_nl_build_images(_stream_ptr(), _ptr(pos), _ptr(cell), int(bool(pbc)), n, float(cutoff), capacity,
+                                     _ptr(idx), _ptr(shifts), _ptr(offsets), _ptr(n_found), _ptr(overflow),
+                                     C.c_void_p(Workspace.aligned_ptr(buf)), C.c_size_t(nbytes)), "apax_nl_build_images")
+    return idx, shifts, offsets, n_found, overflow
+
+
+def nl_needs_rebuild(frac, ref, box, dr_threshold: float) -> torch.Tensor:
+    dev = _require_cuda()
+    frac = to_device(frac, torch.float64)
+    ref = to_device(ref, torch.float64)
+    box = to_device(box, torch.float64)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib().apax_nl_needs_rebuild(_stream_ptr(), _ptr(frac), _ptr(ref), _ptr(box), int(frac.shape[0]),
+                                      float(dr_threshold), _ptr(flag)), "apax_nl_needs_rebuild")
+    return flag
+
+
+class HostContext:
+    """apax_ctx_*: host buffers in, host buffers out (the reference's ASECalculator.calculate flow)."""
+
+    def __init__(self, params: DeviceParams, max_atoms: int, max_pairs: int):
+        _require_cuda()
+        self.params = params
+        self.handle = C.c_void_p()
+        check(lib().apax_ctx_create(params.handle, max_atoms, max_pairs, C.byref(self.handle)), "apax_ctx_create")
+
+    def calculate(self, positions: np.ndarray, numbers: np.ndarray, cell: np.ndarray, dr_threshold: float = 0.0,
+                  rebuild: bool = False, forces: bool = True):
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        num = np.ascontiguousarray(numbers, dtype=np.int32)
+        cel = np.ascontiguousarray(cell, dtype=np.float64)
+        n = pos.shape[0]
+        e = np.empty(self.params.n_out, dtype=np.float64)
+        f = np.empty((self.params.n_out, n, 3), dtype=np.float64) if forces else None
+        npairs = C.c_int64(0)
+        code = lib().apax_ctx_calculate(self.handle, pos.ctypes.data_as(C.c_void_p), num.ctypes.data_as(C.c_void_p),
+                                        cel.ctypes.data_as(C.c_void_p), n, float(dr_threshold), int(rebuild),
+                                        e.ctypes.data_as(C.c_void_p),
+                                        f.ctypes.data_as(C.c_void_p) if forces else C.c_void_p(0), C.byref(npairs))
+        self.n_pairs = npairs.value
+        check(code, "apax_ctx_calculate")
+        return e, f
+
+    def close(self):
+        if self.handle is not None and self.handle.value:
+            lib().apax_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

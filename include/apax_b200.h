@@ -1,0 +1,184 @@
+/* apax_b200 -- C ABI of the B200-native GMNN energy+forces path.
+ *
+ * Drop-in boundary for ONE hot path of apax (https://github.com/apax-hub/apax): periodic neighbour
+ * list -> GaussianMomentDescriptor -> per-element MLP readout -> scale/shift -> fp64 energy -> forces.
+ * apax itself has no native layer; every function below replaces a piece of JAX/Flax code that the
+ * reference traces into XLA.  The citation after each prototype names that piece (path:line relative to
+ * the apax repository).  INTEGRATION.md shows the XLA-FFI / ctypes stubs that bind these symbols.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - every device-side function is asynchronous on `stream`, never allocates, never synchronises and
+ *     never writes beyond a caller-given capacity; it returns 0 or a negative apax_status.
+ *   - conditions only the device can see (list overflow) are reported through device-side flags,
+ *     like jax_md's PartitionErrorCode (apax/utils/jax_md_reduced/partition.py:168-191).
+ *   - neighbour lists cross the boundary in apax's own COO form: int32 idx[2][P], idx[0] = neighbour,
+ *     idx[1] = central atom, dr = R[idx[1]] - R[idx[0]] (+ offsets)  (apax/layers/distances.py:48-67).
+ */
+#ifndef APAX_B200_H
+#define APAX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APAX_B200_ABI_VERSION 1
+
+typedef struct CUstream_st* apax_stream_t; /* == cudaStream_t */
+
+typedef enum {
+  APAX_OK = 0,
+  APAX_ERR_INVALID_ARG = -1,
+  APAX_ERR_UNSUPPORTED = -2, /* statics outside what the kernels are specialised for */
+  APAX_ERR_WORKSPACE = -3,   /* caller workspace too small */
+  APAX_ERR_CUDA = -4,        /* a CUDA runtime call failed (see apax_last_cuda_error) */
+  APAX_ERR_OVERFLOW = -5     /* host-visible capacity exceeded */
+} apax_status;
+
+/* Displacement branch of make_distance_fn (apax/layers/distances.py:32-67). */
+typedef enum {
+  APAX_DISP_GAS = 0,      /* dr = R[i1]-R[i0]                               (:59-62) */
+  APAX_DISP_OFFSETS = 1,  /* dr = box.(R[i1]-R[i0]) + offsets               (:12-14,:65-66) */
+  APAX_DISP_MINIMAGE = 2, /* dr = box.wrap(R[i1]-R[i0]) + offsets, R fractional
+                             (apax/utils/jax_md_reduced/space.py:260-282) */
+  APAX_DISP_DRVEC = 3     /* apax_gm_descriptor only: `R` is dr_vec f64 [n_pairs][3] itself, the argument
+                             of GaussianMomentDescriptor.__call__ (gaussian_moment_descriptor.py:31) */
+} apax_disp_mode;
+
+/* Hot-path statics (apax/config/model_config.py:12-34,147-227; Flax defaults in SURVEY.md s8). */
+typedef struct {
+  int32_t n_species;      /* 119 */
+  int32_t n_radial;       /* 5   (kernels specialised: must be 5) */
+  int32_t n_basis;        /* 7   (must be 7) */
+  int32_t n_contr;        /* 8   (must be 8 -> 360 features) */
+  int32_t n_hidden1;      /* 256 (must be 256) */
+  int32_t n_hidden2;      /* 256 (must be 256) */
+  int32_t n_out;          /* 1, or n_shallow_ensemble (<= 16) */
+  int32_t use_ntk;        /* NTKLinear scaling (apax/layers/ntk_linear.py:42-45) */
+  int32_t use_embed_norm; /* 1/sqrt(n_basis) (apax/layers/descriptor/basis_functions.py:145-146) */
+  int32_t mask_atoms;     /* mask_by_atom on E_i (apax/nn/models.py:111-112) */
+  float r_min;            /* 0.5 */
+  float r_max;            /* 6.0 */
+} apax_gm_config;
+
+/* ------------------------------------------------------------------------------------------------
+ * Parameters.  Replaces: the Flax parameter tree consumed by model.apply (layout in SURVEY.md s5;
+ * apax/layers/descriptor/basis_functions.py:110-120, apax/layers/ntk_linear.py:37-38,
+ * apax/layers/scaling.py:33-38).  Host arrays in, opaque device-resident handle out (weights are
+ * uploaded once, transposed/padded copies for the backward GEMMs are made here).
+ *   emb_host   f32 [n_species][n_species][n_radial][n_basis]
+ *   w0_host    f32 [360][256], b0_host f32 [256]; w1_host f32 [256][256], b1_host f32 [256]
+ *   w2_host    f32 [256][n_out], b2_host f32 [n_out]
+ *   scale_host, shift_host  f64 [n_species]
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct apax_gm_params apax_gm_params;
+int apax_gm_params_create(const apax_gm_config* cfg, const float* emb_host, const float* w0_host,
+                          const float* b0_host, const float* w1_host, const float* b1_host,
+                          const float* w2_host, const float* b2_host, const double* scale_host,
+                          const double* shift_host, apax_gm_params** out);
+void apax_gm_params_destroy(apax_gm_params* p);
+
+/* ------------------------------------------------------------------------------------------------
+ * Energy + forces given a neighbour list.  Replaces EnergyDerivativeModel.apply
+ * (apax/nn/models.py:146-171 = jax.value_and_grad of EnergyModel.__call__, :87-134).
+ *   R       f64 [n_atoms][3]  (fractional for OFFSETS/MINIMAGE, Cartesian for GAS)
+ *   Z       i32 [n_atoms]     (0 = padding atom)
+ *   idx     i32 [2][n_pairs]  apax COO list; entries with idx[0]==idx[1] (the (0,0) / (N,N) padding)
+ *                             contribute exactly zero (apax/layers/masking.py:10-16)
+ *   box     f64 [3][3]        as passed to model.apply (ignored for GAS)
+ *   offsets f64 [n_pairs][3]  Cartesian, or NULL for all-zero
+ *   energy  f64 [n_out]       out (n_out == 1: the scalar energy)
+ *   forces  f64 [n_out][n_atoms][3] out; for n_out == 1 this is F = -dE/dR; for a shallow ensemble
+ *                             the per-head forces -jacrev(E_ens) (apax/nn/models.py:236)
+ *   workspace: >= apax_gm_workspace_bytes(n_atoms, n_pairs, n_out) bytes, 256-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+size_t apax_gm_workspace_bytes(int64_t n_atoms, int64_t n_pairs, int32_t n_out);
+int apax_gm_energy_forces(apax_stream_t stream, const apax_gm_params* params, const double* R,
+                          const int32_t* Z, const int32_t* idx, const double* box,
+                          const double* offsets, int64_t n_atoms, int64_t n_pairs, int32_t disp_mode,
+                          double* energy, double* forces, void* workspace, size_t workspace_bytes);
+
+/* The same computation split at the list-preparation boundary, so that a list that did not change
+ * (MD between rebuilds, apax/md/simulate.py:313-354) is prepared once:
+ *   apax_gm_prepare : COO -> CSR by central atom + transpose map + compact species table, in workspace
+ *   apax_gm_compute : E, F from the prepared workspace (R may have changed; Z, idx may not).      */
+int apax_gm_prepare(apax_stream_t stream, const apax_gm_params* params, const int32_t* Z,
+                    const int32_t* idx, int64_t n_atoms, int64_t n_pairs, void* workspace,
+                    size_t workspace_bytes);
+int apax_gm_compute(apax_stream_t stream, const apax_gm_params* params, const double* R,
+                    const int32_t* Z, const double* box, const double* offsets, int64_t n_atoms,
+                    int64_t n_pairs, int32_t disp_mode, double* energy, double* forces,
+                    void* workspace, size_t workspace_bytes);
+
+/* Descriptor only.  Replaces GaussianMomentDescriptor.__call__ behind the builder seam
+ * ModelBuilder.build_descriptor (apax/nn/builder.py:79-83,248-260;
+ * apax/layers/descriptor/gaussian_moment_descriptor.py:31-103).  g: f32 [n_atoms][360] row-major out. */
+int apax_gm_descriptor(apax_stream_t stream, const apax_gm_params* params, const double* R,
+                       const int32_t* Z, const int32_t* idx, const double* box, const double* offsets,
+                       int64_t n_atoms, int64_t n_pairs, int32_t disp_mode, float* g, void* workspace,
+                       size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Neighbour lists.
+ * (1) apax_nl_build_minimage replaces partition.neighbor_list(...).allocate/update with
+ *     format=Sparse, fractional_coordinates=True, disable_cell_list=True
+ *     (apax/utils/jax_md_reduced/partition.py:478-787; predicate :640-664).  Output order is the
+ *     reference's: idx[1] (central) ascending, idx[0] ascending within it; tail padded with n_atoms.
+ *       frac     f64 [n_atoms][3] fractional positions;  box f64 [3][3] (columns = lattice vectors,
+ *                i.e. atoms.cell.array.T as at apax/md/ase_calc.py:42-43)
+ *       cutoff   r_max + dr_threshold (:574)
+ *       idx      i32 [2][capacity] out;  n_found i32 [1] out = occupancy (may exceed capacity)
+ *       overflow u8 [1] out: |= 1 (PEC.NEIGHBOR_LIST_OVERFLOW, :734) when occupancy > capacity
+ * (2) apax_nl_build_images replaces the vesin NeighborList(cutoff, full_list=True).compute(..."ijS")
+ *     calls (apax/md/ase_calc.py:337-355, apax/data/preprocessing.py:47-54): every (i, j, S) with
+ *     |r_j - r_i + S.cell| < cutoff except (i,i,0), for any cell (also L < 2 cutoff, triclinic).
+ *       pos      f64 [n_atoms][3] Cartesian; cell f64 [3][3] rows = lattice vectors; pbc 0/1
+ *       idx      i32 [2][capacity] out (idx[0]=i, idx[1]=j, rows grouped by j, sorted by (i,S));
+ *                tail padded with (0,0) like ase_calc.py:349-355
+ *       shifts   i32 [capacity][3] out (S);  offsets f64 [capacity][3] out = S @ cell (:354), or NULL
+ * (3) apax_nl_needs_rebuild replaces the skin test (partition.py:771-779): flag[0] = any atom moved
+ *     more than dr_threshold/2 (min-image metric) since `ref`.
+ * ---------------------------------------------------------------------------------------------- */
+size_t apax_nl_workspace_bytes(int64_t n_atoms, int64_t capacity);
+int apax_nl_build_minimage(apax_stream_t stream, const double* frac, const double* box,
+                           int64_t n_atoms, double cutoff, int64_t capacity, int32_t* idx,
+                           int32_t* n_found, uint8_t* overflow, void* workspace,
+                           size_t workspace_bytes);
+int apax_nl_build_images(apax_stream_t stream, const double* pos, const double* cell, int32_t pbc,
+                         int64_t n_atoms, double cutoff, int64_t capacity, int32_t* idx,
+                         int32_t* shifts, double* offsets, int32_t* n_found, uint8_t* overflow,
+                         void* workspace, size_t workspace_bytes);
+int apax_nl_needs_rebuild(apax_stream_t stream, const double* frac, const double* ref,
+                          const double* box, int64_t n_atoms, double dr_threshold, int32_t* flag);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer convenience context: what ASECalculator.calculate does per call
+ * (apax/md/ase_calc.py:357-393): positions/cell on the HOST in, neighbour list (min-image when
+ * min cell height / 2 > r_max, image list otherwise, :501-522), E+F, results on the HOST out.
+ * Owns its device buffers and stream; includes the H2D/D2H copies.  Used for the end-to-end
+ * measurement in bench.py and by non-Python hosts.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct apax_ctx apax_ctx;
+int apax_ctx_create(const apax_gm_params* params, int64_t max_atoms, int64_t max_pairs, apax_ctx** out);
+void apax_ctx_destroy(apax_ctx* ctx);
+/* positions_host f64 [n][3] Cartesian, numbers_host i32 [n], cell_host f64 [3][3] rows = lattice
+ * vectors (all-zero = gas phase is not supported here: use apax_gm_energy_forces with a list),
+ * dr_threshold = skin; rebuild = 1 forces a list rebuild, 0 applies the reference's skin test.
+ * energy_host f64 [n_out], forces_host f64 [n_out][n][3]. */
+int apax_ctx_calculate(apax_ctx* ctx, const double* positions_host, const int32_t* numbers_host,
+                       const double* cell_host, int64_t n_atoms, double dr_threshold, int32_t rebuild,
+                       double* energy_host, double* forces_host, int64_t* n_pairs_host);
+
+/* Diagnostics */
+int apax_abi_version(void);
+const char* apax_last_cuda_error(void);
+/* number of kernels launched by this library since process start (bench.py's gpu_launches) */
+int64_t apax_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APAX_B200_H */

@@ -1,0 +1,180 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Tolerances are north_star's: neighbour indices bit-exact, fp32 energies within 1e-6 relative,
+forces within 1e-5 relative + 1e-6 eV/A absolute."""
+import numpy as np
+import pytest
+import torch
+
+from apax_b200 import synthetic as syn
+from conftest import force_tolerance_ok, max_force_violation
+
+pytestmark = pytest.mark.gpu
+
+E_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from apax_b200 import runtime
+
+    assert torch.cuda.is_available()
+    return runtime
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import gmnn_oracle, neighbor_oracle
+
+    return gmnn_oracle, neighbor_oracle
+
+
+def _ef(rt, params, R, Z, idx, box, offsets, mode, cfg=None):
+    dp = rt.DeviceParams(params, cfg)
+    e, f = rt.energy_forces(dp, R, Z, idx, box, offsets, mode)
+    torch.cuda.synchronize()
+    return e.cpu().numpy(), f.cpu().numpy()
+
+
+def test_descriptor_unit_case(rt, golden):
+    d = golden("descriptor_unit")
+    dp = rt.DeviceParams(syn.gmnn_params(seed=int(d["param_seed"])))
+    g = rt.descriptor(dp, d["dR"].astype(np.float64), d["Z"], d["idx"], mode="drvec").cpu().numpy()
+    assert g.shape == (3, 360)
+    assert np.abs(g - d["g"]).max() <= 2e-6 * np.abs(d["g"]).max()
+
+
+def test_gas_phase_golden_padding_invariance(rt, golden):
+    d = golden("gas_padded")
+    p = syn.gmnn_params(seed=11, scale=d["scale"], shift=d["shift"])
+    e, f = _ef(rt, p, d["R"], d["Z"], d["idx"], None, None, "gas", {"mask_atoms": False})
+    assert abs(e[0] - d["energy"]) <= E_RTOL * abs(d["energy"])
+    assert force_tolerance_ok(f[0], d["forces"]), max_force_violation(f[0], d["forces"])
+    ep, fp = _ef(rt, p, d["Rp"], d["Zp"], d["idxp"], None, None, "gas")
+    assert abs(ep[0] - d["energy_padded"]) <= E_RTOL * abs(d["energy_padded"])
+    assert force_tolerance_ok(fp[0], d["forces_padded"])
+    # tests/unit_tests/model/test_apax.py:61-62
+    assert abs(e[0] - ep[0]) < 1e-6 and np.all(np.abs(f[0] - fp[0][:-1]) < 1e-6)
+    assert np.all(fp[0][-1] == 0.0)  # the padded atom feels exactly nothing
+
+
+def test_multi_image_golden(rt, golden):
+    d = golden("water_multi_image")
+    e, f = _ef(rt, syn.gmnn_params(seed=int(d["param_seed"])), d["frac"], d["Z"], d["idx"], d["box"], d["offsets"], "offsets")
+    assert abs(e[0] - d["energy"]) <= E_RTOL * abs(d["energy"]), (e[0], d["energy"])
+    assert force_tolerance_ok(f[0], d["forces"]), max_force_violation(f[0], d["forces"])
+
+
+def test_min_image_golden(rt, golden):
+    d = golden("water_min_image")
+    e, f = _ef(rt, syn.gmnn_params(seed=int(d["param_seed"])), d["frac"], d["Z"], d["idx"], d["box"], None, "minimage")
+    assert abs(e[0] - d["energy"]) <= E_RTOL * abs(d["energy"]), (e[0], d["energy"])
+    assert force_tolerance_ok(f[0], d["forces"]), max_force_violation(f[0], d["forces"])
+
+
+def test_shallow_ensemble_golden(rt, golden):
+    d = golden("water_ensemble")
+    n_ens = int(d["n_ens"])
+    p = syn.gmnn_params(seed=int(d["param_seed"]), n_out=n_ens, random_scale_shift=True, random_bias=True)
+    e, f = _ef(rt, p, d["frac"], d["Z"], d["idx"], d["box"], d["offsets"], "offsets")
+    assert np.all(np.abs(e - d["energy_ensemble"]) <= 2e-6 * np.abs(d["energy_ensemble"]) + 1e-6)
+    f_ens = np.transpose(f, (1, 2, 0))
+    assert force_tolerance_ok(f_ens, d["forces_ensemble"], abs_=2e-6), max_force_violation(f_ens, d["forces_ensemble"])
+
+
+@pytest.mark.parametrize("n_mol,seed", [(32, 0), (32, 1), (10, 4)])
+def test_water_multi_image_vs_oracle(rt, oracle, n_mol, seed):
+    go, no = oracle
+    pos, Z, cell = syn.water_box(n_mol, seed)
+    idx, off = no.vesin_idx_offsets(pos, cell, 6.0)
+    idx, off = no.vesin_idx_offsets(pos, cell, 6.0, padded_length=int(idx.shape[1] * 1.5))  # ase_calc.py:264
+    frac = pos @ np.linalg.inv(cell)
+    p = syn.gmnn_params(seed=1234)
+    ref = go.energy_forces(p, frac, Z, idx, cell.T, off, "offsets")
+    e, f = _ef(rt, p, frac, Z, idx, cell.T, off, "offsets")
+    assert abs(e[0] - ref["energy"]) <= E_RTOL * abs(ref["energy"]), (e[0], ref["energy"])
+    assert force_tolerance_ok(f[0], ref["forces"]), max_force_violation(f[0], ref["forces"])
+    # against the all-fp64 oracle the CUDA path must not be worse than the reference-precision oracle is
+    ref64 = go.energy_forces(p, frac, Z, idx, cell.T, off, "offsets", go.fp64_config())
+    assert max_force_violation(f[0], ref64["forces"]) < 2.0
+
+
+def test_water_1536_min_image_vs_oracle(rt, oracle):
+    go, no = oracle
+    pos, Z, cell = syn.water_box(512, 7)
+    frac = pos @ np.linalg.inv(cell)
+    idx, occ, ov = no.jaxmd_sparse_list(frac, cell.T, 6.0, 0.5)
+    assert not ov
+    p = syn.gmnn_params(seed=1234, random_scale_shift=True, random_bias=True)
+    ref = go.energy_forces(p, frac, Z, idx, cell.T, None, "minimage")
+    e, f = _ef(rt, p, frac, Z, idx, cell.T, None, "minimage")
+    assert abs(e[0] - ref["energy"]) <= E_RTOL * abs(ref["energy"]), (e[0], ref["energy"])
+    assert force_tolerance_ok(f[0], ref["forces"]), max_force_violation(f[0], ref["forces"])
+
+
+def test_unsorted_coo_and_isolated_atoms(rt, oracle):
+    go, no = oracle
+    pos, Z, cell = syn.water_box(16, 3)
+    idx, off = no.vesin_idx_offsets(pos, cell, 6.0)
+    perm = np.random.default_rng(0).permutation(idx.shape[1])
+    p = syn.gmnn_params(seed=2)
+    frac = pos @ np.linalg.inv(cell)
+    e0, f0 = _ef(rt, p, frac, Z, idx, cell.T, off, "offsets")
+    e1, f1 = _ef(rt, p, frac, Z, idx[:, perm], cell.T, off[perm], "offsets")
+    assert abs(e0[0] - e1[0]) <= 1e-6 * abs(e0[0])
+    assert force_tolerance_ok(f1[0], f0[0])
+    # no pairs at all: every atom isolated -> forces exactly zero, energy = sum of readout(0)
+    empty = np.zeros((2, 0), dtype=np.int32)
+    ref = go.energy_forces(p, frac, Z, empty, cell.T, np.zeros((0, 3)), "offsets")
+    e2, f2 = _ef(rt, p, frac, Z, empty, cell.T, None, "offsets")
+    assert abs(e2[0] - ref["energy"]) <= 1e-6 * max(1.0, abs(ref["energy"]))
+    assert np.all(f2 == 0.0)
+
+
+def test_bitwise_reproducible(rt, oracle):
+    go, no = oracle
+    pos, Z, cell = syn.water_box(64, 1)
+    frac = pos @ np.linalg.inv(cell)
+    idx = no.jaxmd_sparse_pairs(frac, cell.T, 6.0)
+    p = syn.gmnn_params(seed=9)
+    a = _ef(rt, p, frac, Z, idx, cell.T, None, "minimage")
+    b = _ef(rt, p, frac, Z, idx, cell.T, None, "minimage")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_properties_at_12288_atoms(rt):
+    """Size-independent properties where the oracle is too slow: list symmetry, sum F = 0,
+    translation invariance, invariance under atom relabelling."""
+    pos, Z, cell = syn.water_12288()
+    box = cell.T
+    frac = pos @ np.linalg.inv(cell)
+    n = len(Z)
+    cap = int(n * 130)
+    idx, n_found, ov = rt.nl_build_minimage(frac, box, 6.5, cap)
+    torch.cuda.synchronize()
+    nf = int(n_found.item())
+    assert not int(ov.item()) and 100 * n < nf < cap
+    idx_h = idx[:, :nf].cpu().numpy()
+    fwd = idx_h[0].astype(np.int64) * n + idx_h[1]
+    rev = idx_h[1].astype(np.int64) * n + idx_h[0]
+    assert np.array_equal(np.sort(fwd), np.sort(rev))            # full (symmetric) list
+    assert np.all(np.diff(idx_h[1]) >= 0)                        # grouped by central atom, ascending
+    same = np.diff(idx_h[1]) == 0
+    assert np.all(np.diff(idx_h[0])[same] > 0)                   # neighbours ascending within a row
+    assert np.all(idx[:, nf:].cpu().numpy() == n)                # padded with N
+    dp = rt.DeviceParams(syn.gmnn_params(seed=1234))
+    e, f = rt.energy_forces(dp, frac, Z, idx, box, None, "minimage")
+    e, f = e.cpu().numpy(), f.cpu().numpy()[0]
+    assert np.isfinite(e).all() and np.isfinite(f).all()
+    assert np.abs(f.sum(0)).max() < 1e-3 * np.abs(f).max()
+    # rigid translation in fractional space (wraps through the boundary)
+    e2, f2 = rt.energy_forces(dp, frac + np.array([0.37, -0.21, 0.05]), Z, idx, box, None, "minimage")
+    assert abs(e2.cpu().numpy()[0] - e[0]) <= 2e-6 * abs(e[0])
+    assert force_tolerance_ok(f2.cpu().numpy()[0], f, rel=2e-5, abs_=2e-5)
+    # relabel atoms
+    perm = np.random.default_rng(1).permutation(n)
+    inv = np.argsort(perm)
+    idx_p = torch.as_tensor(np.where(idx.cpu().numpy() < n, inv[np.minimum(idx.cpu().numpy(), n - 1)], n).astype(np.int32))
+    e3, f3 = rt.energy_forces(dp, frac[perm], Z[perm], idx_p, box, None, "minimage")
+    assert abs(e3.cpu().numpy()[0] - e[0]) <= 2e-6 * abs(e[0])
+    assert force_tolerance_ok(f3.cpu().numpy()[0], f[perm], rel=2e-5, abs_=2e-5)

@@ -1,0 +1,97 @@
+"""CPU-side checks: the generated contraction program, and that the C-ABI library loads and exports
+every symbol include/apax_b200.h declares (no compute calls without a GPU)."""
+import ctypes
+import itertools
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from apax_b200 import _lib
+from apax_b200 import synthetic as syn
+from apax_b200.csrc import gen_contract as gc
+from oracle import gmnn_oracle as go
+from oracle import neighbor_oracle as no
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _pack(m0, m1, m2, m3):
+    n = m0.shape[0]
+    out = np.zeros((100, n))
+    for r in range(5):
+        out[r * 20] = m0[:, r]
+        for i in range(3):
+            out[r * 20 + 1 + i] = m1[:, r, i]
+        for i, j in itertools.combinations_with_replacement(range(3), 2):
+            out[r * 20 + 4 + gc.pack2(i, j)] = m2[:, r, i, j]
+        for i, j, k in itertools.combinations_with_replacement(range(3), 3):
+            out[r * 20 + 10 + gc.pack3(i, j, k)] = m3[:, r, i, j, k]
+    return out
+
+
+def test_generated_contraction_program_matches_oracle():
+    blocks, nf = gc.build_program()
+    assert nf == 360
+    pos, Z, cell = syn.water_box(6, 3)
+    idx, off = no.vesin_idx_offsets(pos, cell, 6.0)
+    aux = go.descriptor_only(syn.gmnn_params(), pos @ np.linalg.inv(cell), Z, idx, cell.T, off, "offsets", go.fp64_config())
+    mp = _pack(*aux["moments"])
+    g = gc.run_forward(blocks, mp)
+    assert np.abs(g.T - aux["g"]).max() < 1e-12 * max(1.0, np.abs(aux["g"]).max())
+    # reverse mode against a finite-difference of sum(gbar * g)
+    rng = np.random.default_rng(0)
+    gbar = rng.normal(size=g.shape)
+    a = gc.run_backward(blocks, mp, gbar)
+    for slot in (0, 3, 27, 55, 99):
+        h = 1e-6
+        mp_p, mp_m = mp.copy(), mp.copy()
+        mp_p[slot] += h
+        mp_m[slot] -= h
+        fd = ((gc.run_forward(blocks, mp_p) - gc.run_forward(blocks, mp_m)) * gbar).sum(0) / (2 * h)
+        assert np.abs(fd - a[slot]).max() < 1e-5 * max(1.0, np.abs(a[slot]).max())
+
+
+def test_generated_header_is_current():
+    path = os.path.join(ROOT, "apax_b200", "csrc", "contract_gen.cuh")
+    tmp = path + ".check"
+    gc.main(tmp)
+    try:
+        assert open(tmp).read() == open(path).read()
+    finally:
+        os.remove(tmp)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "apax_b200.h")).read()
+    declared = set(re.findall(r"\b(apax_[a-z0-9_]+)\s*\(", header))
+    declared -= {"apax_gm_params", "apax_ctx"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("libapax_b200.so not built in this checkout (python -m apax_b200.build)")
+    handle = _lib.lib()
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert handle.apax_abi_version() == 1
+    assert handle.apax_gm_workspace_bytes(96, 9000, 1) > 0
+    assert handle.apax_nl_workspace_bytes(96, 9000) > 0
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "apax_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_runtime_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from apax_b200 import runtime
+
+    with pytest.raises(_lib.ApaxB200Error):
+        runtime.DeviceParams(syn.gmnn_params())

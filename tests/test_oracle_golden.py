@@ -1,0 +1,67 @@
+"""The oracle against fixtures produced by executing the reference's OWN source files
+(tests/golden/make_golden.py, under the torch-backed jax/flax shim).  CPU only."""
+import numpy as np
+import torch
+
+from apax_b200 import synthetic as syn
+from oracle import gmnn_oracle as go
+from oracle import neighbor_oracle as no
+
+
+def test_descriptor_unit_case_is_bit_exact(golden):
+    d = golden("descriptor_unit")
+    p = syn.gmnn_params(seed=int(d["param_seed"]))
+    emb = torch.as_tensor(p["params"]["energy_model"]["representation"]["radial_fn"]["atomic_type_embedding"])
+    g, _ = go.gaussian_moment_descriptor(torch.as_tensor(d["dR"]), torch.as_tensor(d["Z"]), torch.as_tensor(d["idx"]), emb,
+                                         go.GMNNConfig())
+    assert g.shape == (3, 360)  # tests/unit_tests/layers/descriptor/test_gaussian_moment_descriptor.py:30
+    assert np.array_equal(g.numpy(), d["g"])
+
+
+def test_gas_phase_padded_and_unpadded(golden):
+    d = golden("gas_padded")
+    p = syn.gmnn_params(seed=11, scale=d["scale"], shift=d["shift"])
+    r = go.energy_forces(p, d["R"], d["Z"], d["idx"], np.zeros((3, 3)), None, "gas",
+                         go.GMNNConfig(apply_mask=False, mask_atoms=False))
+    assert abs(r["energy"] - d["energy"]) < 1e-6 * abs(d["energy"])
+    assert np.abs(r["forces"] - d["forces"]).max() < 1e-6
+    rp = go.energy_forces(p, d["Rp"], d["Zp"], d["idxp"], np.zeros((3, 3)), None, "gas")
+    assert abs(rp["energy"] - d["energy_padded"]) < 1e-6 * abs(d["energy"])
+    assert np.abs(rp["forces"] - d["forces_padded"]).max() < 1e-6
+    # the reference's own assertion (tests/unit_tests/model/test_apax.py:61-62)
+    assert abs(r["energy"] - rp["energy"]) < 1e-6
+    assert np.all(np.abs(r["forces"] - rp["forces"][:-1]) < 1e-6)
+
+
+def test_multi_image_water(golden):
+    d = golden("water_multi_image")
+    p = syn.gmnn_params(seed=int(d["param_seed"]))
+    r = go.energy_forces(p, d["frac"], d["Z"], d["idx"], d["box"], d["offsets"], "offsets")
+    assert abs(r["energy"] - d["energy"]) < 1e-6 * abs(d["energy"])
+    assert np.all(np.abs(r["forces"] - d["forces"]) <= 1e-5 * np.abs(d["forces"]) + 1e-6)
+
+
+def test_min_image_water_and_neighbor_list(golden):
+    d = golden("water_min_image")
+    p = syn.gmnn_params(seed=int(d["param_seed"]))
+    r = go.energy_forces(p, d["frac"], d["Z"], d["idx"], d["box"], None, "minimage")
+    assert abs(r["energy"] - d["energy"]) < 1e-6 * abs(d["energy"])
+    assert np.all(np.abs(r["forces"] - d["forces"]) <= 1e-5 * np.abs(d["forces"]) + 1e-6)
+    # neighbour list: bit-exact indices, order and padding against partition.py run under the shim
+    idx, occ, ov = no.jaxmd_sparse_list(d["frac"], d["box"], 6.0, float(d["skin"]))
+    assert np.array_equal(idx, d["idx"])
+    assert occ == int(d["n_valid"]) and int(ov) == int(d["overflow"])
+    assert no.needs_rebuild(d["moved_small"], d["frac"], d["box"], float(d["skin"])) == bool(d["rebuilt_small"])
+    assert no.needs_rebuild(d["moved_big"], d["frac"], d["box"], float(d["skin"])) == bool(d["rebuilt_big"])
+    idxb, _, _ = no.jaxmd_sparse_list(d["moved_big"], d["box"], 6.0, float(d["skin"]), max_occupancy=d["idx"].shape[1])
+    assert np.array_equal(idxb, d["idx_big"])
+
+
+def test_shallow_ensemble(golden):
+    d = golden("water_ensemble")
+    p = syn.gmnn_params(seed=int(d["param_seed"]), n_out=int(d["n_ens"]), random_scale_shift=True, random_bias=True)
+    r = go.shallow_ensemble(p, d["frac"], d["Z"], d["idx"], d["box"], d["offsets"], "offsets")
+    for k in ("energy", "energy_ensemble", "energy_uncertainty"):
+        assert np.allclose(r[k], d[k], rtol=2e-6, atol=1e-6), k
+    for k in ("forces", "forces_uncertainty", "forces_ensemble"):
+        assert np.all(np.abs(r[k] - d[k]) <= 1e-5 * np.abs(d[k]) + 2e-6), k
