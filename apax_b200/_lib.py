@@ -45,6 +45,8 @@ SIGNATURES = {
     "apax_abi_version": (C.c_int, []),
     "apax_last_cuda_error": (C.c_char_p, []),
     "apax_kernel_launch_count": (_I64, []),
+    "apax_profile_enable": (C.c_int, [C.c_int]),
+    "apax_profile_collect": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "apax_gm_params_create": (C.c_int, [C.POINTER(GmConfig), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     "apax_gm_params_destroy": (None, [_P]),
     "apax_gm_workspace_bytes": (C.c_size_t, [_I64, _I64, _I32]),

@@ -1,10 +1,34 @@
 // Scan / row-sort primitives and ABI diagnostics.
 #include "common.cuh"
 
+#include <string.h>
+
+#include <string>
+#include <vector>
+
 namespace apax {
 
 std::atomic<int64_t> g_launch_count{0};
 thread_local cudaError_t g_last_error = cudaSuccess;
+
+bool g_profile_on = false;
+namespace {
+struct ProfRec {
+  std::string name;
+  cudaEvent_t a, b;
+};
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+void profile_before(const char* name, cudaStream_t stream) {
+  ProfRec r;
+  r.name = name;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, stream);
+  g_prof.push_back(r);
+}
+void profile_after(cudaStream_t stream) { cudaEventRecord(g_prof.back().b, stream); }
 
 // ------------------------------------------------------------------------------------------------
 // Exclusive scan: 3 launches (block sums, scan of block sums, apply).  1024 elements per block.
@@ -137,4 +161,29 @@ extern "C" {
 int apax_abi_version(void) { return APAX_B200_ABI_VERSION; }
 const char* apax_last_cuda_error(void) { return cudaGetErrorString(apax::g_last_error); }
 int64_t apax_kernel_launch_count(void) { return apax::g_launch_count.load(); }
+
+int apax_profile_enable(int on) {
+  for (auto& r : apax::g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  apax::g_prof.clear();
+  apax::g_profile_on = on != 0;
+  return APAX_OK;
+}
+
+int apax_profile_collect(char* names, int name_stride, float* ms, int max_records) {
+  int n = 0;
+  for (auto& r : apax::g_prof) {
+    if (n >= max_records) break;
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return APAX_ERR_CUDA;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return APAX_ERR_CUDA;
+    ms[n] = t;
+    strncpy(names + size_t(n) * name_stride, r.name.c_str(), name_stride - 1);
+    names[size_t(n) * name_stride + name_stride - 1] = 0;
+    ++n;
+  }
+  return n;
+}
 }

@@ -37,10 +37,18 @@ inline int check_launch() {
     if (_s != APAX_OK) return _s; \
   } while (0)
 
+// optional per-launch CUDA-event timing (apax_profile_enable): events are recorded on the launching
+// stream around every kernel of this library, so bench.py can time each kernel live
+extern bool g_profile_on;
+void profile_before(const char* name, cudaStream_t stream);
+void profile_after(cudaStream_t stream);
+
 // launch + count + error check
 #define APAX_LAUNCH(kernel, grid, block, smem, stream, ...)        \
   do {                                                             \
+    if (::apax::g_profile_on) ::apax::profile_before(#kernel, (stream)); \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
+    if (::apax::g_profile_on) ::apax::profile_after((stream));     \
     APAX_TRY(::apax::check_launch());                              \
   } while (0)
 

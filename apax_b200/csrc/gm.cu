@@ -812,14 +812,14 @@ static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
   {  // layer 0: 360 -> 256
     GemmArgs a{};
     a.W = p->w0; a.ldw = NH; a.XT = w.GT; a.YT = w.H1T; a.Y2T = w.D1T; a.bias = p->b0; a.K = NF; a.ld = ld;
-    auto kfn = k_sgemm<PRO_NONE, EPI_ACT>;
-    APAX_LAUNCH(kfn, grid_h, dim3(256), 0, stream, a);
+    auto k_sgemm_fwd_l0 = k_sgemm<PRO_NONE, EPI_ACT>;
+    APAX_LAUNCH(k_sgemm_fwd_l0, grid_h, dim3(256), 0, stream, a);
   }
   {  // layer 1: 256 -> 256
     GemmArgs a{};
     a.W = p->w1; a.ldw = NH; a.XT = w.H1T; a.YT = w.H2T; a.Y2T = w.D2T; a.bias = p->b1; a.K = NH; a.ld = ld;
-    auto kfn = k_sgemm<PRO_NONE, EPI_ACT>;
-    APAX_LAUNCH(kfn, grid_h, dim3(256), 0, stream, a);
+    auto k_sgemm_fwd_l1 = k_sgemm<PRO_NONE, EPI_ACT>;
+    APAX_LAUNCH(k_sgemm_fwd_l1, grid_h, dim3(256), 0, stream, a);
   }
   if (n_out == 1) {
     APAX_LAUNCH(k_head<1>, dim3((unsigned)cdiv(ld, 128)), dim3(128), 0, stream, w.H2T, ld, N, p->w2, p->b2, n_out,
@@ -838,14 +838,14 @@ static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
       GemmArgs a{};
       a.W = p->w1t; a.ldw = NH; a.XT = w.D2T; a.YT = w.H1T; a.Y2T = w.D1T; a.K = NH; a.ld = ld;
       a.ebar = w.ebar; a.wcol = p->w2 + head; a.wstride = n_out;
-      auto kfn = k_sgemm<PRO_HEAD, EPI_MULD>;
-      APAX_LAUNCH(kfn, grid_h, dim3(256), 0, stream, a);
+      auto k_sgemm_bwd_l1 = k_sgemm<PRO_HEAD, EPI_MULD>;
+      APAX_LAUNCH(k_sgemm_bwd_l1, grid_h, dim3(256), 0, stream, a);
     }
     {  // dE/dg = W0 . dE/dy1   (360 rows padded to 384)
       GemmArgs a{};
       a.W = p->w0t; a.ldw = NFP; a.XT = w.H1T; a.YT = w.GT; a.K = NH; a.ld = ld;
-      auto kfn = k_sgemm<PRO_NONE, EPI_STORE>;
-      APAX_LAUNCH(kfn, dim3((unsigned)(ld / 128), NFP / 128), dim3(256), 0, stream, a);
+      auto k_sgemm_bwd_l0 = k_sgemm<PRO_NONE, EPI_STORE>;
+      APAX_LAUNCH(k_sgemm_bwd_l0, dim3((unsigned)(ld / 128), NFP / 128), dim3(256), 0, stream, a);
     }
     APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(N, 128)), dim3(128), 0, stream, w);
     APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc);

@@ -399,16 +399,16 @@ static int nl_build_common(cudaStream_t stream, const double* pos, const double*
   const dim3 grid_scan((unsigned)cdiv(N * LG, 256));
   APAX_CUDA_TRY(cudaMemsetAsync(w.rowcnt, 0, sizeof(int32_t) * (N + 1), stream));
   {
-    auto kfn = k_nl_scan<MODE, false>;
-    APAX_LAUNCH(kfn, grid_scan, dim3(256), 0, stream, pos, N, w.grid, w);
+    auto k_nl_scan_count = k_nl_scan<MODE, false>;
+    APAX_LAUNCH(k_nl_scan_count, grid_scan, dim3(256), 0, stream, pos, N, w.grid, w);
   }
   APAX_TRY(exclusive_scan_i32(stream, w.rowcnt, w.rowptr, N, w.scan_scratch));
   APAX_LAUNCH(k_nl_finish_count, dim3((unsigned)cdiv(N + 1, 256)), dim3(256), 0, stream, N, capacity, w.rowptr,
               w.rowptr_c, n_found, overflow);
   APAX_CUDA_TRY(cudaMemsetAsync(w.rowcnt, 0, sizeof(int32_t) * (N + 1), stream));
   {
-    auto kfn = k_nl_scan<MODE, true>;
-    APAX_LAUNCH(kfn, grid_scan, dim3(256), 0, stream, pos, N, w.grid, w);
+    auto k_nl_scan_fill = k_nl_scan<MODE, true>;
+    APAX_LAUNCH(k_nl_scan_fill, grid_scan, dim3(256), 0, stream, pos, N, w.grid, w);
   }
   APAX_LAUNCH(k_nl_rowsort, dim3((unsigned)cdiv(N * 32, 256)), dim3(256), 0, stream, w.rowptr_c, N, w.nbr_tmp,
               MODE == 1 ? w.shift_tmp : nullptr, w.nbr, MODE == 1 ? w.shift : nullptr);

@@ -285,3 +285,23 @@ class HostContext:
             self.close()
         except Exception:
             pass
+
+
+def profile_kernels(fn, max_records: int = 4096):
+    """Run fn() with per-launch CUDA-event timing enabled; returns [(kernel name, ms), ...] in launch order."""
+    lib().apax_profile_enable(1)
+    try:
+        fn()
+        torch.cuda.synchronize()
+        stride = 64
+        names = C.create_string_buffer(stride * max_records)
+        ms = (C.c_float * max_records)()
+        n = lib().apax_profile_collect(C.cast(names, C.c_void_p), stride, C.cast(ms, C.c_void_p), max_records)
+        if n < 0:
+            check(n, "apax_profile_collect")
+        out = []
+        for i in range(n):
+            out.append((names.raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode(), float(ms[i])))
+        return out
+    finally:
+        lib().apax_profile_enable(0)

@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the GMNN energy+forces hot path (BASELINE.json metric: atom-steps/s, E+F).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path, one rank per GPU
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+Workload (config.workload): BASELINE configs[3] -- one energy+forces evaluation of the
+1 000 002-atom periodic water box (333 334 H2O, L = 215.24 A, r_max = 6 A, GMNN default statics,
+random-init weights, synthetic seeded geometry).  A "step" is one E+F evaluation of the whole box.
+  value : atom-steps/s with positions, neighbour list and weights resident in HBM (apax_gm_compute)
+  e2e   : the same metric through the host-buffer C-ABI call apax_ctx_calculate: host positions in,
+          neighbour list rebuilt on the GPU every step, host energy+forces out (copies inside)
+One JSON line on stdout (rank 0).  The oracle is used only for the cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R_MAX = 6.0
+METRIC = "atom_steps_per_s"
+UNIT = "atom-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--molecules", type=int, default=333_334, help="water molecules in the box (default: the 1M-atom box)")
+    ap.add_argument("--cpu-sample-molecules", type=int, default=4096, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="multi-GPU: strong = the same box split into slabs (BASELINE configs[3]); weak = box grows with N")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    smax.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------- helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_bytes():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, if one exists."""
+    path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as fh:
+                return json.load(fh)
+        except Exception:
+            return None
+    return None
+
+
+def cpu_baseline(params, n_mol: int, steps: int = 1):
+    """The restated reference algorithm (oracle, torch-CPU, all host threads) on a bounded sample of
+    the same workload: a smaller periodic water box at the same density.  kind = "port": apax's own
+    JAX path cannot run here (no jax wheels in the image)."""
+    import torch
+
+    from apax_b200 import synthetic as syn
+    from oracle import gmnn_oracle as go
+    from oracle import neighbor_oracle as no
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pos, Z, cell = syn.water_box(n_mol, 0)
+    frac = pos @ np.linalg.inv(cell)
+    idx = no.jaxmd_sparse_pairs_fast(frac, cell.T, R_MAX)
+    go.energy_forces(params, frac[:96], Z[:96], idx[:, (idx[0] < 96) & (idx[1] < 96)], cell.T, None, "minimage")  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        go.energy_forces(params, frac, Z, idx, cell.T, None, "minimage")
+    dt = (time.perf_counter() - t0) / steps
+    n = len(Z)
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n}-atom periodic water box (same density, r_max 6 A, list given), {steps} E+F step(s) of the "
+                      f"torch-CPU oracle, {dt:.2f} s each"}
+
+
+def init_dist(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    world, rank, local = init_dist(args)
+    if rank != 0:
+        return 0
+    from apax_b200 import synthetic as syn
+
+    params = syn.gmnn_params(seed=1234)
+    steps = max(1, args.steps)
+    # bounded sample so that the whole run ends within minutes: ~2 s per step at 12 288 atoms on 8 cores
+    n_mol = args.cpu_sample_molecules
+    import torch
+    from oracle import gmnn_oracle as go
+    from oracle import neighbor_oracle as no
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pos, Z, cell = syn.water_box(n_mol, 0)
+    frac = pos @ np.linalg.inv(cell)
+    idx = no.jaxmd_sparse_pairs_fast(frac, cell.T, R_MAX)
+    n = len(Z)
+    for _ in range(max(1, min(args.warmup, 2))):
+        go.energy_forces(params, frac, Z, idx, cell.T, None, "minimage")
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        go.energy_forces(params, frac, Z, idx, cell.T, None, "minimage")
+    dt = (time.perf_counter() - t0) / steps
+    value = n / dt
+    sample = (f"{n}-atom periodic water box per step (bounded sample of the 1 000 002-atom workload, same density and "
+              f"statics, neighbour list given); torch-CPU restatement of apax's JAX path (jax is not installable here)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "GMNN E+F, periodic water box, r_max=6A, n_basis=7, n_radial=5, readout [256,256]",
+                   "atoms_per_step": n, "list": "min-image full list given"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+
+    world, rank, local = init_dist(args)
+    if world > 1:
+        from apax_b200.md import domain
+
+        return domain.bench_multi_gpu(args, world, rank, local, METRIC, UNIT)
+
+    from apax_b200 import runtime as rt
+    from apax_b200 import synthetic as syn
+
+    torch.cuda.set_device(local)
+    lib = rt.lib()
+    t_setup = time.perf_counter()
+    pos, Z, cell = syn.water_box(args.molecules, 0)
+    n = len(Z)
+    params = syn.gmnn_params(seed=1234)
+    dp = rt.DeviceParams(params)
+    box = cell.T.copy()
+    frac_h = pos @ np.linalg.inv(cell)
+    frac = rt.to_device(frac_h, torch.float64)
+    box_d = rt.to_device(box, torch.float64)
+    cap = int(n * 96) + 4096
+    idx, n_found, overflow = rt.nl_build_minimage(frac, box_d, R_MAX, cap)
+    torch.cuda.synchronize()
+    n_pairs = int(n_found.item())
+    assert int(overflow.item()) == 0, "neighbour list capacity exceeded"
+    nbar = n_pairs / n
+    system = rt.PreparedSystem(dp, Z, idx[:, :n_pairs].contiguous())
+    del idx
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+
+    def step():
+        return system.compute(frac, box_d, None, "minimage")
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.apax_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        e, f = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = lib.apax_kernel_launch_count() - launches0
+    clocks = sampler.stop()
+    ms_per_step = ms_total / args.steps
+    value = n * args.steps / (ms_total * 1e-3)
+    energy = float(e.cpu().numpy()[0])
+    f_h = f.cpu().numpy()[0]
+    assert np.isfinite(energy) and np.isfinite(f_h).all()
+
+    # ---- per-kernel device times, live, with CUDA events on the launching stream
+    prof_steps = min(3, args.steps)
+    records = rt.profile_kernels(lambda: [step() for _ in range(prof_steps)])
+    per_kernel = {}
+    for name, ms in records:
+        per_kernel.setdefault(name, []).append(ms)
+    kernel_ms = {k: float(np.sum(v)) / prof_steps for k, v in per_kernel.items()}          # per step
+    kernel_launch_ms = {k: float(np.mean(v)) for k, v in per_kernel.items()}                # per launch
+    dominant = max(kernel_ms, key=kernel_ms.get)
+    b_alg = 52.0 + 8.0 * nbar                      # bytes per atom-step, E+F given a list
+    peak, peak_src = measured_peaks()
+    launches_per_step_dom = len(per_kernel[dominant]) / prof_steps
+    achieved = n * b_alg / (kernel_launch_ms[dominant] * 1e-3) / 1e9 / 1.0
+    traffic = ncu_traffic_bytes()
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": (traffic or {}).get("dram_bytes_per_launch") if traffic else None,
+        "kernel": dominant, "kernel_ms_per_launch": kernel_launch_ms[dominant],
+        "kernel_launches_per_step": launches_per_step_dom,
+        "kernel_share_of_step": kernel_ms[dominant] / sum(kernel_ms.values()),
+        "algorithmic_bytes_per_atom_step": b_alg, "atoms_per_launch": n, "peak_source": peak_src,
+        "step_achieved_GBps": n * b_alg / (ms_per_step * 1e-3) / 1e9,
+        "step_frac": n * b_alg / (ms_per_step * 1e-3) / 1e9 / peak,
+        "note": "path is compute-bound (fp32 CUDA cores), not HBM-bound: SURVEY.md §8d; fp32 pipe figures in DESIGN.md",
+        "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(kernel_ms.items(), key=lambda kv: -kv[1])},
+    }
+    flops_per_atom = 2 * (360 * 256 + 256 * 256) * 2  # readout GEMMs fwd + input-grad
+    gemm_ms = sum(v for k, v in kernel_ms.items() if "sgemm" in k)
+    if gemm_ms > 0:
+        roofline["readout_gemm_tflops_fp32"] = n * flops_per_atom / (gemm_ms * 1e-3) / 1e12
+
+    # ---- end to end through the host-buffer C-ABI call (H2D + list rebuild + E+F + D2H every step)
+    e2e = None
+    if not args.no_e2e:
+        del system
+        torch.cuda.empty_cache()
+        ctx = rt.HostContext(dp, n, cap)
+        Z32 = Z.astype(np.int32)
+        for _ in range(2):
+            e_h, f_hh = ctx.calculate(pos, Z32, cell, dr_threshold=0.0, rebuild=True)
+        k_e2e = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            e_h, f_hh = ctx.calculate(pos, Z32, cell, dr_threshold=0.0, rebuild=True)
+        dt = (time.perf_counter() - t0) / k_e2e
+        assert abs(e_h[0] - energy) <= 1e-9 * abs(energy) + 1e-6, (e_h[0], energy)
+        e2e = {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": int(n * 24 + n * 4 + 36 * 8),
+               "d2h_bytes_per_step": int(n * 24 + 8), "ms_per_step": dt * 1e3, "steps": k_e2e,
+               "includes": "host->device copy of positions/numbers/cell, fractional transform, cell-list neighbour "
+                           "build (every step), list preparation, E+F, device->host copy of energy and forces"}
+        ctx.close()
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_baseline(params, args.cpu_sample_molecules)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[3]: GMNN default energy+forces, 1,000,002-atom periodic water box "
+                               "(333,334 H2O, L=215.24 A), r_max=6 A, single-point (skin 0)",
+                   "atoms": n, "pairs": n_pairs, "pairs_per_atom": nbar, "list": "min-image full list, resident",
+                   "l2": "working set per step (~30 GB touched) far exceeds the 126 MB L2; no flush needed",
+                   "parallelism": "1 GPU", "energy": energy, "setup_s": setup_s},
+        "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))

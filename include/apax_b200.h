@@ -177,6 +177,12 @@ int apax_abi_version(void);
 const char* apax_last_cuda_error(void);
 /* number of kernels launched by this library since process start (bench.py's gpu_launches) */
 int64_t apax_kernel_launch_count(void);
+/* Per-launch device timing for measurement: while enabled, every kernel of this library is
+ * bracketed by CUDA events on its launching stream.  apax_profile_collect waits for them and writes
+ * up to max_records (kernel name, milliseconds) pairs in launch order; returns the count (>= 0).
+ * apax_profile_enable(0/1) also clears the record list.  Not thread-safe; off by default. */
+int apax_profile_enable(int on);
+int apax_profile_collect(char* names_host, int name_stride, float* ms_host, int max_records);
 
 #ifdef __cplusplus
 }

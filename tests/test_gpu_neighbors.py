@@ -109,7 +109,7 @@ def test_image_list_vs_oracle(rt, no, case):
 def test_host_context_both_paths(rt):
     from oracle import gmnn_oracle as go
     from oracle import neighbor_oracle as no
-    from conftest import force_tolerance_ok, max_force_violation
+    from conftest import assert_force_parity, force_tolerance_ok, max_force_violation
 
     p = syn.gmnn_params(seed=1234)
     dp = rt.DeviceParams(p)
@@ -129,11 +129,12 @@ def test_host_context_both_paths(rt):
     pairs = no.jaxmd_sparse_pairs(frac, cell.T, 6.0, 0.5)
     assert ctx.n_pairs == pairs.shape[1]
     ref = go.energy_forces(p, frac, Z, pairs, cell.T, None, "minimage")
+    ref64 = go.energy_forces(p, frac, Z, pairs, cell.T, None, "minimage", go.fp64_config())
     assert abs(e[0] - ref["energy"]) <= 1e-6 * abs(ref["energy"])
-    assert force_tolerance_ok(f[0], ref["forces"]), max_force_violation(f[0], ref["forces"])
+    assert_force_parity(f[0], ref["forces"], ref64["forces"], where="ctx min-image")
     pos2 = pos + np.random.default_rng(0).normal(scale=0.01, size=pos.shape)
     e2, f2 = ctx.calculate(pos2, Z, cell, dr_threshold=0.5)
     ref2 = go.energy_forces(p, pos2 @ np.linalg.inv(cell), Z, pairs, cell.T, None, "minimage")
     assert abs(e2[0] - ref2["energy"]) <= 1e-6 * abs(ref2["energy"])
-    assert force_tolerance_ok(f2[0], ref2["forces"]), max_force_violation(f2[0], ref2["forces"])
+    assert_force_parity(f2[0], ref2["forces"], where="ctx min-image, reused list")
     ctx.close()

@@ -102,3 +102,11 @@ def test_vesin_restatement_distance_multiset():
         # symmetric: (i,j,S) <-> (j,i,-S)
         fwd = set(zip(ii.tolist(), jj.tolist(), map(tuple, ss.tolist())))
         assert all((j, i, tuple(-np.array(s))) in fwd for i, j, s in fwd)
+
+
+def test_fast_pair_search_equals_brute_force():
+    pos, Z, cell = syn.water_box(400, 11)
+    frac = pos @ np.linalg.inv(cell) + np.array([0.3, -1.2, 2.0])  # also unwrapped coordinates
+    a = no.jaxmd_sparse_pairs(frac, cell.T, 6.0, 0.5)
+    b = no.jaxmd_sparse_pairs_fast(frac, cell.T, 6.0, 0.5)
+    assert np.array_equal(a, b)
