@@ -26,6 +26,7 @@ size_t carve_gm_workspace(void* base, int64_t n_atoms, int64_t n_pairs, int32_t 
   const int64_t N = n_atoms, P = n_pairs > 0 ? n_pairs : 1;
   const int64_t ld = round_up(N > 0 ? N : 1, 128);
   w.n_atoms = N;
+  w.n_central = N;
   w.n_pairs = n_pairs;
   w.ld = ld;
   w.n_out = n_out;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(256) k_pair_fwd(GmWorkspace ws, PairGeom geo, 
   const int64_t gid = int64_t(blockIdx.x) * 256 + threadIdx.x;
   const int64_t atom = gid / LPA;
   const int sub = int(gid % LPA);
-  const bool valid = atom < ws.n_atoms;
+  const bool valid = atom < ws.n_central;
   int beg = 0, end = 0, zc = 0;
   double Ra[3] = {0.0, 0.0, 0.0};
   double box[9];
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(256) k_pair_bwd(GmWorkspace ws, DescConst dc) 
   const int64_t gid = int64_t(blockIdx.x) * 256 + threadIdx.x;
   const int64_t atom = gid / LPA;
   const int sub = int(gid % LPA);
-  const bool valid = atom < ws.n_atoms;
+  const bool valid = atom < ws.n_central;
   int beg = 0, end = 0;
   float a[NPK];
   if (valid) {
@@ -491,9 +492,10 @@ __global__ void __launch_bounds__(256) k_force_gather(GmWorkspace ws, double* __
     tz += __shfl_xor_sync(0xffffffffu, tz, o);
   }
   if (valid && sub == 0) {
-    F[3 * atom + 0] = -(ws.Frow[3 * atom + 0] - tx);
-    F[3 * atom + 1] = -(ws.Frow[3 * atom + 1] - ty);
-    F[3 * atom + 2] = -(ws.Frow[3 * atom + 2] - tz);
+    const bool central = atom < ws.n_central;
+    F[3 * atom + 0] = -((central ? ws.Frow[3 * atom + 0] : 0.0) - tx);
+    F[3 * atom + 1] = -((central ? ws.Frow[3 * atom + 1] : 0.0) - ty);
+    F[3 * atom + 2] = -((central ? ws.Frow[3 * atom + 2] : 0.0) - tz);
   }
 }
 
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(256) k_force_gather(GmWorkspace ws, double* __
 // ================================================================================================
 __global__ void __launch_bounds__(128) k_contract_fwd(GmWorkspace ws) {
   const int64_t atom = int64_t(blockIdx.x) * 128 + threadIdx.x;
-  if (atom >= ws.n_atoms) return;
+  if (atom >= ws.n_central) return;
   float m[NPK];
 #pragma unroll
   for (int k = 0; k < NPK; ++k) m[k] = ws.MT[int64_t(k) * ws.ld + atom];
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(128) k_contract_fwd(GmWorkspace ws) {
 
 __global__ void __launch_bounds__(128) k_contract_bwd(GmWorkspace ws) {
   const int64_t atom = int64_t(blockIdx.x) * 128 + threadIdx.x;
-  if (atom >= ws.n_atoms) return;
+  if (atom >= ws.n_central) return;
   float m[NPK], a[NPK];
 #pragma unroll
   for (int k = 0; k < NPK; ++k) {
@@ -672,7 +674,7 @@ __global__ void __launch_bounds__(128) k_head(const float* __restrict__ H2T, int
                                               const int32_t* __restrict__ Z, int S, const double* __restrict__ scale,
                                               const double* __restrict__ shift, int mask_atoms,
                                               double* __restrict__ Eatom, float* __restrict__ ebar) {
-  const int64_t m = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  const int64_t m = int64_t(blockIdx.x) * 128 + threadIdx.x;  // grid covers whole 128-atom tiles
   if (m >= ld) return;
   if (m >= N) {
     ebar[m] = 0.0f;
@@ -754,12 +756,12 @@ static int pick_lpa(int64_t n_atoms) {
 
 template <int LPA>
 static int launch_pair_fwd(cudaStream_t s, const GmWorkspace& w, const PairGeom& geo, const DescConst& dc) {
-  APAX_LAUNCH(k_pair_fwd<LPA>, dim3((unsigned)cdiv(w.n_atoms * LPA, 256)), dim3(256), 0, s, w, geo, dc);
+  APAX_LAUNCH(k_pair_fwd<LPA>, dim3((unsigned)cdiv(w.n_central * LPA, 256)), dim3(256), 0, s, w, geo, dc);
   return APAX_OK;
 }
 template <int LPA>
 static int launch_pair_bwd(cudaStream_t s, const GmWorkspace& w, const DescConst& dc) {
-  APAX_LAUNCH(k_pair_bwd<LPA>, dim3((unsigned)cdiv(w.n_atoms * LPA, 256)), dim3(256), 0, s, w, dc);
+  APAX_LAUNCH(k_pair_bwd<LPA>, dim3((unsigned)cdiv(w.n_central * LPA, 256)), dim3(256), 0, s, w, dc);
   return APAX_OK;
 }
 template <int LPA>
@@ -794,21 +796,22 @@ static PairGeom make_geom(const apax_gm_params_impl* p, const double* R, const i
 static int gm_descriptor_impl(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w,
                               const PairGeom& geo) {
   const DescConst dc = make_desc_const(p->cfg);
-  const int lpa = pick_lpa(w.n_atoms);
+  const int lpa = pick_lpa(w.n_central);
   APAX_DISPATCH_LPA(lpa, launch_pair_fwd, stream, w, geo, dc);
-  APAX_LAUNCH(k_contract_fwd, dim3((unsigned)cdiv(w.n_atoms, 128)), dim3(128), 0, stream, w);
+  APAX_LAUNCH(k_contract_fwd, dim3((unsigned)cdiv(w.n_central, 128)), dim3(128), 0, stream, w);
   return APAX_OK;
 }
 
 static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w,
                            const PairGeom& geo, double* energy, double* forces) {
-  const int64_t N = w.n_atoms, ld = w.ld;
+  const int64_t N = w.n_central, ld = w.ld;  // per-central work only; ghosts enter as neighbours
   const int n_out = p->cfg.n_out;
   const DescConst dc = make_desc_const(p->cfg);
   const int lpa = pick_lpa(N);
   APAX_TRY(gm_descriptor_impl(stream, p, w, geo));
 
-  const dim3 grid_h((unsigned)(ld / 128), NH / 128);
+  const int64_t m_tiles = cdiv(N, 128);
+  const dim3 grid_h((unsigned)m_tiles, NH / 128);
   {  // layer 0: 360 -> 256
     GemmArgs a{};
     a.W = p->w0; a.ldw = NH; a.XT = w.GT; a.YT = w.H1T; a.Y2T = w.D1T; a.bias = p->b0; a.K = NF; a.ld = ld;
@@ -822,10 +825,10 @@ static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
     APAX_LAUNCH(k_sgemm_fwd_l1, grid_h, dim3(256), 0, stream, a);
   }
   if (n_out == 1) {
-    APAX_LAUNCH(k_head<1>, dim3((unsigned)cdiv(ld, 128)), dim3(128), 0, stream, w.H2T, ld, N, p->w2, p->b2, n_out,
+    APAX_LAUNCH(k_head<1>, dim3((unsigned)m_tiles), dim3(128), 0, stream, w.H2T, ld, N, p->w2, p->b2, n_out,
                 geo.Z, p->cfg.n_species, p->scale, p->shift, p->cfg.mask_atoms, w.Eatom, w.ebar);
   } else {
-    APAX_LAUNCH(k_head<MAX_OUT>, dim3((unsigned)cdiv(ld, 128)), dim3(128), 0, stream, w.H2T, ld, N, p->w2, p->b2,
+    APAX_LAUNCH(k_head<MAX_OUT>, dim3((unsigned)m_tiles), dim3(128), 0, stream, w.H2T, ld, N, p->w2, p->b2,
                 n_out, geo.Z, p->cfg.n_species, p->scale, p->shift, p->cfg.mask_atoms, w.Eatom, w.ebar);
   }
   const int n_blk = int(N < 256 * 64 ? 1 : (N / (256 * 64) > 256 ? 256 : N / (256 * 64)));
@@ -845,20 +848,22 @@ static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
       GemmArgs a{};
       a.W = p->w0t; a.ldw = NFP; a.XT = w.H1T; a.YT = w.GT; a.K = NH; a.ld = ld;
       auto k_sgemm_bwd_l0 = k_sgemm<PRO_NONE, EPI_STORE>;
-      APAX_LAUNCH(k_sgemm_bwd_l0, dim3((unsigned)(ld / 128), NFP / 128), dim3(256), 0, stream, a);
+      APAX_LAUNCH(k_sgemm_bwd_l0, dim3((unsigned)m_tiles, NFP / 128), dim3(256), 0, stream, a);
     }
     APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(N, 128)), dim3(128), 0, stream, w);
     APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc);
-    APAX_DISPATCH_LPA(lpa, launch_force_gather, stream, w, forces + int64_t(head) * N * 3);
+    APAX_DISPATCH_LPA(pick_lpa(w.n_atoms), launch_force_gather, stream, w, forces + int64_t(head) * w.n_atoms * 3);
   }
   return APAX_OK;
 }
 
 int gm_compute_device(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const double* R,
                       const int32_t* Z, const double* box, const double* offsets, int mode, double* energy,
-                      double* forces) {
+                      double* forces, int64_t n_central) {
   const PairGeom geo = make_geom(p, R, Z, box, offsets, mode);
-  return gm_compute_impl(stream, p, w, geo, energy, forces);
+  GmWorkspace wc = w;
+  if (n_central >= 0) wc.n_central = n_central;
+  return gm_compute_impl(stream, p, wc, geo, energy, forces);
 }
 
 }  // namespace apax
@@ -997,6 +1002,18 @@ extern "C" int apax_gm_compute(apax_stream_t stream, const apax_gm_params* param
   if (disp_mode != APAX_DISP_GAS && !box) return APAX_ERR_INVALID_ARG;
   const PairGeom geo = make_geom(params, R, Z, box, offsets, disp_mode);
   return gm_compute_impl(stream, params, w, geo, energy, forces);
+}
+
+extern "C" int apax_gm_compute_partial(apax_stream_t stream, const apax_gm_params* params, const double* R,
+                                       const int32_t* Z, const double* box, const double* offsets, int64_t n_atoms,
+                                       int64_t n_pairs, int64_t n_central, int32_t disp_mode, double* energy,
+                                       double* forces, void* workspace, size_t workspace_bytes) {
+  GmWorkspace w;
+  APAX_TRY(get_ws(params, n_atoms, n_pairs, workspace, workspace_bytes, &w));
+  if (!R || !Z || !energy || n_central < 1 || n_central > n_atoms) return APAX_ERR_INVALID_ARG;
+  if (disp_mode < APAX_DISP_GAS || disp_mode > APAX_DISP_MINIMAGE) return APAX_ERR_INVALID_ARG;
+  if (disp_mode != APAX_DISP_GAS && !box) return APAX_ERR_INVALID_ARG;
+  return gm_compute_device(stream, params, w, R, Z, box, offsets, disp_mode, energy, forces, n_central);
 }
 
 extern "C" int apax_gm_energy_forces(apax_stream_t stream, const apax_gm_params* params, const double* R,

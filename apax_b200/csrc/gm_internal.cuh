@@ -34,6 +34,7 @@ struct apax_gm_params_impl {
 // ("transposed") matrices have leading dimension ld = round_up(n_atoms, 128) along the atom axis.
 struct GmWorkspace {
   int64_t n_atoms, n_pairs, ld;
+  int64_t n_central;  // atoms [0, n_central) are evaluated as centrals; the rest only act as neighbours
   int32_t n_out;
   // list (CSR by central atom) + transpose
   int32_t* rowptr;   // [N+1]
@@ -77,6 +78,6 @@ int gm_prepare_from_csr(cudaStream_t stream, const apax_gm_params_impl* p, const
 struct PairGeom;
 int gm_compute_device(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const double* R,
                       const int32_t* Z, const double* box, const double* offsets, int mode, double* energy,
-                      double* forces);
+                      double* forces, int64_t n_central = -1);
 
 }  // namespace apax

@@ -1,0 +1,249 @@
+"""Spatial domain decomposition of one periodic box over the GPUs of a node (BASELINE configs[3],
+SURVEY.md §8e).  The reference has no counterpart: apax evaluates one structure on one device
+(apax/md/simulate.py:313-354).  GMNN is strictly one-hop -- E_a depends only on atoms within r_max of
+a -- so one halo exchange each way is enough:
+
+  forward halo : positions of atoms within `cutoff` of a slab face travel to the neighbouring rank
+                 (ghosts); each rank evaluates ONLY its owned atoms as centrals (no redundant compute);
+  reverse halo : the force contributions that owned centrals put on ghost atoms travel back to the
+                 owners and are added there (LAMMPS "newton on");
+  energy       : one 8-byte all-reduce.
+
+Slabs are cut along the first fractional axis; with W ranks a slab must be at least `cutoff` thick.
+Collectives are torch.distributed all_to_all_single (NCCL over NVLink on GPUs, gloo in the CPU tests);
+the messages are ~1-3 MB, i.e. latency-bound.  The local computation is injected so
+that the CPU tests can drive the same bookkeeping with the oracle.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from dataclasses import dataclass
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def _wrap01(x: torch.Tensor) -> torch.Tensor:
+    return x - torch.floor(x)
+
+
+@dataclass
+class SlabDecomposition:
+    """Index bookkeeping of one rank.  Local atom order: owned atoms (ascending global id), then
+    ghosts grouped by owner rank (ascending), ascending global id inside a group."""
+
+    rank: int
+    world: int
+    owned: torch.Tensor            # [n_owned] global ids
+    ghosts: torch.Tensor           # [n_ghost] global ids
+    ghost_owner_counts: List[int]  # how many of my ghosts each rank owns  (recv sizes, forward halo)
+    send_local: torch.Tensor       # local owned indices to send, grouped by destination rank
+    send_counts: List[int]         # per destination rank                  (send sizes, forward halo)
+
+    @property
+    def n_owned(self) -> int:
+        return int(self.owned.numel())
+
+    @property
+    def n_local(self) -> int:
+        return int(self.owned.numel() + self.ghosts.numel())
+
+    @property
+    def local_ids(self) -> torch.Tensor:
+        return torch.cat([self.owned, self.ghosts])
+
+
+def slab_of(frac_x: torch.Tensor, world: int) -> torch.Tensor:
+    s = torch.floor(_wrap01(frac_x) * world).to(torch.int64)
+    return torch.clamp(s, 0, world - 1)
+
+
+def ghost_mask(frac_x: torch.Tensor, slab: torch.Tensor, rank: int, world: int, cutoff_frac: float) -> torch.Tensor:
+    """Atoms not owned by `rank` whose periodic distance along x to the slab [rank/W, (rank+1)/W) is < cutoff_frac."""
+    x = _wrap01(frac_x)
+    lo, hi = rank / world, (rank + 1) / world
+    d_lo = torch.abs(x - lo)
+    d_lo = torch.minimum(d_lo, 1.0 - d_lo)
+    d_hi = torch.abs(x - hi)
+    d_hi = torch.minimum(d_hi, 1.0 - d_hi)
+    return (slab != rank) & (torch.minimum(d_lo, d_hi) < cutoff_frac)
+
+
+def decompose(frac: torch.Tensor, box: torch.Tensor, cutoff: float, rank: int, world: int) -> SlabDecomposition:
+    """Every rank runs this on the same global fractional positions; results are consistent by
+    construction (pure function of the inputs)."""
+    binv = torch.linalg.inv(box.to(torch.float64))
+    height_x = 1.0 / float(torch.linalg.norm(binv[0]))
+    cutoff_frac = cutoff / height_x
+    if world > 1 and 1.0 / world < cutoff_frac:
+        raise ValueError(f"slab thickness {height_x / world:.3f} A is below the cutoff {cutoff} A: use fewer ranks")
+    fx = frac[:, 0].to(torch.float64)
+    slab = slab_of(fx, world)
+    ids = torch.arange(frac.shape[0], device=frac.device)
+    owned = ids[slab == rank]
+    gm = ghost_mask(fx, slab, rank, world, cutoff_frac) if world > 1 else torch.zeros_like(slab, dtype=torch.bool)
+    ghost_ids = ids[gm]
+    owner = slab[ghost_ids]
+    order = torch.argsort(owner * frac.shape[0] + ghost_ids)
+    ghost_ids, owner = ghost_ids[order], owner[order]
+    ghost_owner_counts = torch.bincount(owner, minlength=world).tolist()
+    # what I must send: my owned atoms that are ghosts of rank r, in r's receive order (ascending global id)
+    send_local, send_counts = [], []
+    g2l = torch.full((frac.shape[0],), -1, dtype=torch.int64, device=frac.device)
+    g2l[owned] = torch.arange(owned.numel(), device=frac.device)
+    for r in range(world):
+        if r == rank or world == 1:
+            send_counts.append(0)
+            continue
+        m = ghost_mask(fx, slab, r, world, cutoff_frac) & (slab == rank)
+        loc = g2l[ids[m]]
+        send_local.append(loc)
+        send_counts.append(int(loc.numel()))
+    send_local = torch.cat(send_local) if send_local else torch.zeros(0, dtype=torch.int64, device=frac.device)
+    return SlabDecomposition(rank, world, owned, ghost_ids, ghost_owner_counts, send_local, send_counts)
+
+
+class HaloExchanger:
+    """Forward (owned -> ghosts) and reverse (ghosts -> owners, accumulate) exchanges of [n,3] f64 rows."""
+
+    def __init__(self, dec: SlabDecomposition, group=None):
+        self.dec = dec
+        self.group = group
+        dev = dec.owned.device
+        self.n_send = int(sum(dec.send_counts))
+        self.n_recv = int(sum(dec.ghost_owner_counts))
+        self.send_buf = torch.empty((self.n_send, 3), dtype=torch.float64, device=dev)
+        self.recv_buf = torch.empty((self.n_recv, 3), dtype=torch.float64, device=dev)
+        self.bytes_per_step = 2 * (self.n_send + self.n_recv) * 24
+
+    def forward(self, R_local: torch.Tensor) -> None:
+        """Fill the ghost rows of R_local ([n_local,3]) with the owners' current positions."""
+        d = self.dec
+        if d.world == 1:
+            return
+        torch.index_select(R_local, 0, d.send_local, out=self.send_buf)
+        dist.all_to_all_single(self.recv_buf, self.send_buf, d.ghost_owner_counts, d.send_counts, group=self.group)
+        R_local[d.n_owned:] = self.recv_buf
+
+    def reverse(self, F_local: torch.Tensor) -> torch.Tensor:
+        """Send the ghost rows of F_local back to their owners and add them; returns F of the owned atoms."""
+        d = self.dec
+        F_owned = F_local[: d.n_owned]
+        if d.world == 1:
+            return F_owned
+        back = torch.empty_like(self.send_buf)
+        dist.all_to_all_single(back, F_local[d.n_owned:].contiguous(), d.send_counts, d.ghost_owner_counts, group=self.group)
+        F_owned.index_add_(0, d.send_local, back)
+        return F_owned
+
+
+def evaluate(dec: SlabDecomposition, halo: HaloExchanger, R_local: torch.Tensor,
+             local_compute: Callable[[torch.Tensor, int], tuple], group=None):
+    """One energy+forces evaluation of the whole box.  local_compute(R_local, n_central) must return
+    (energy of the centrals [n_out] f64, dE/dR-based forces on ALL local atoms [n_local,3] f64)."""
+    halo.forward(R_local)
+    e_local, f_local = local_compute(R_local, dec.n_owned)
+    f_owned = halo.reverse(f_local)
+    e = e_local.clone()
+    if dec.world > 1:
+        dist.all_reduce(e, group=group)
+    return e, f_owned
+
+
+# --------------------------------------------------------------------------------------------- GPU driver
+class GpuSlabSystem:
+    """Owned + ghost atoms of this rank on its GPU, list built once, evaluated through the C ABI."""
+
+    def __init__(self, params, frac_global: np.ndarray, Z_global: np.ndarray, box: np.ndarray, cutoff: float,
+                 rank: int, world: int, group=None):
+        from apax_b200 import runtime as rt
+
+        self.rt = rt
+        dev = torch.device("cuda", torch.cuda.current_device())
+        frac = torch.as_tensor(frac_global, dtype=torch.float64, device=dev)
+        self.box = torch.as_tensor(np.ascontiguousarray(box), dtype=torch.float64, device=dev)
+        self.dec = decompose(frac, self.box, cutoff, rank, world)
+        ids = self.dec.local_ids
+        self.R_local = frac[ids].contiguous()
+        self.Z_local = torch.as_tensor(Z_global, dtype=torch.int32, device=dev)[ids].contiguous()
+        n_local = self.dec.n_local
+        cap = int(n_local * 100) + 4096
+        idx, n_found, overflow = rt.nl_build_minimage(self.R_local, self.box, cutoff, cap)
+        nf = int(n_found.item())
+        if int(overflow.item()):
+            raise RuntimeError("neighbour list capacity exceeded")
+        idx = idx[:, :nf]
+        idx = idx[:, idx[1] < self.dec.n_owned].contiguous()   # only owned atoms are centrals
+        self.n_pairs = int(idx.shape[1])
+        self.system = rt.PreparedSystem(params, self.Z_local, idx, n_central=self.dec.n_owned)
+        self.halo = HaloExchanger(self.dec, group)
+        self.group = group
+        del frac
+
+    def local_compute(self, R_local, n_central):
+        e, f = self.system.compute(R_local, self.box, None, "minimage")
+        return e, f[0]
+
+    def step(self):
+        return evaluate(self.dec, self.halo, self.R_local, self.local_compute, self.group)
+
+
+def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: str) -> int:
+    from apax_b200 import runtime as rt
+    from apax_b200 import synthetic as syn
+
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_mol = args.molecules * (world if args.scaling == "weak" else 1)
+    pos, Z, cell = syn.water_box(n_mol, 0)
+    n = len(Z)
+    params = syn.gmnn_params(seed=1234)
+    dp = rt.DeviceParams(params)
+    frac = pos @ np.linalg.inv(cell)
+    sysm = GpuSlabSystem(dp, frac, Z, cell.T.copy(), 6.0, rank, world)
+    lib = rt.lib()
+    for _ in range(max(3, args.warmup)):
+        e, f = sysm.step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = lib.apax_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        e, f = sysm.step()
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = lib.apax_kernel_launch_count() - launches0
+    stats = torch.tensor([sysm.dec.n_owned, sysm.dec.n_local - sysm.dec.n_owned, sysm.n_pairs, sysm.halo.bytes_per_step],
+                         dtype=torch.float64, device="cuda")
+    gathered = [torch.zeros_like(stats) for _ in range(world)]
+    dist.all_gather(gathered, stats)
+    if rank == 0:
+        ms_total = float(ms.item())
+        value = n * args.steps / (ms_total * 1e-3)
+        per_rank = [[int(v) for v in g.tolist()] for g in gathered]
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[3]: GMNN default energy+forces, periodic water box, r_max=6 A, "
+                                   "slab domain decomposition with forward/reverse halo exchange over NCCL",
+                       "atoms": n, "parallelism": f"{world} slabs along x", "energy": float(e.cpu()[0]),
+                       "per_rank_owned_ghost_pairs_halobytes": per_rank,
+                       "l2": "working set per step far exceeds the 126 MB L2"},
+            "gpu_launches": int(launches),
+            "e2e": None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+    return 0

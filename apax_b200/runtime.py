@@ -160,8 +160,9 @@ def energy_forces(params: DeviceParams, R, Z, idx, box, offsets, mode: str = "of
 class PreparedSystem:
     """A neighbour list prepared once (apax_gm_prepare) and evaluated many times (apax_gm_compute)."""
 
-    def __init__(self, params: DeviceParams, Z, idx, n_atoms: Optional[int] = None):
+    def __init__(self, params: DeviceParams, Z, idx, n_atoms: Optional[int] = None, n_central: Optional[int] = None):
         self.params = params
+        self.n_central = n_central
         self.Z = to_device(Z, torch.int32)
         self.idx = to_device(idx, torch.int32)
         self.n_atoms = int(self.Z.shape[0]) if n_atoms is None else n_atoms
@@ -176,9 +177,15 @@ class PreparedSystem:
 
     def compute(self, R: torch.Tensor, box: Optional[torch.Tensor], offsets: Optional[torch.Tensor], mode: str,
                 forces: bool = True):
-        check(lib().apax_gm_compute(_stream_ptr(), self.params.handle, _ptr(R), _ptr(self.Z), _ptr(box), _ptr(offsets),
-                                    self.n_atoms, self.n_pairs, MODES[mode], _ptr(self.energy),
-                                    _ptr(self.forces if forces else None), self.wp, self.wb), "apax_gm_compute")
+        if self.n_central is not None:
+            check(lib().apax_gm_compute_partial(_stream_ptr(), self.params.handle, _ptr(R), _ptr(self.Z), _ptr(box),
+                                                _ptr(offsets), self.n_atoms, self.n_pairs, self.n_central, MODES[mode],
+                                                _ptr(self.energy), _ptr(self.forces if forces else None), self.wp,
+                                                self.wb), "apax_gm_compute_partial")
+        else:
+            check(lib().apax_gm_compute(_stream_ptr(), self.params.handle, _ptr(R), _ptr(self.Z), _ptr(box), _ptr(offsets),
+                                        self.n_atoms, self.n_pairs, MODES[mode], _ptr(self.energy),
+                                        _ptr(self.forces if forces else None), self.wp, self.wb), "apax_gm_compute")
         return self.energy, (self.forces if forces else None)
 
 

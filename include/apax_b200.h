@@ -113,6 +113,16 @@ int apax_gm_compute(apax_stream_t stream, const apax_gm_params* params, const do
                     int64_t n_pairs, int32_t disp_mode, double* energy, double* forces,
                     void* workspace, size_t workspace_bytes);
 
+/* Domain-decomposed evaluation (no counterpart in the reference, which is single-device:
+ * apax/md/simulate.py:313-354).  Atoms [0, n_central) are this rank's owned atoms and are the only
+ * centrals (rows of the prepared list); atoms [n_central, n_atoms) are ghosts that only act as
+ * neighbours.  energy = sum over the centrals; forces f64 [n_out][n_atoms][3] = dE_local/dR on ALL
+ * local atoms, the ghost rows being what must be sent back to their owners. */
+int apax_gm_compute_partial(apax_stream_t stream, const apax_gm_params* params, const double* R,
+                            const int32_t* Z, const double* box, const double* offsets, int64_t n_atoms,
+                            int64_t n_pairs, int64_t n_central, int32_t disp_mode, double* energy,
+                            double* forces, void* workspace, size_t workspace_bytes);
+
 /* Descriptor only.  Replaces GaussianMomentDescriptor.__call__ behind the builder seam
  * ModelBuilder.build_descriptor (apax/nn/builder.py:79-83,248-260;
  * apax/layers/descriptor/gaussian_moment_descriptor.py:31-103).  g: f32 [n_atoms][360] row-major out. */
