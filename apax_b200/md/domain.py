@@ -156,13 +156,15 @@ def evaluate(dec: SlabDecomposition, halo: HaloExchanger, R_local: torch.Tensor,
 
 # --------------------------------------------------------------------------------------------- GPU driver
 class GpuSlabSystem:
-    """Owned + ghost atoms of this rank on its GPU, list built once, evaluated through the C ABI."""
+    """Owned + ghost atoms of this rank on its GPU, evaluated through the C ABI."""
 
     def __init__(self, params, frac_global: np.ndarray, Z_global: np.ndarray, box: np.ndarray, cutoff: float,
                  rank: int, world: int, group=None):
         from apax_b200 import runtime as rt
 
         self.rt = rt
+        self.params = params
+        self.cutoff = cutoff
         dev = torch.device("cuda", torch.cuda.current_device())
         frac = torch.as_tensor(frac_global, dtype=torch.float64, device=dev)
         self.box = torch.as_tensor(np.ascontiguousarray(box), dtype=torch.float64, device=dev)
@@ -170,19 +172,26 @@ class GpuSlabSystem:
         ids = self.dec.local_ids
         self.R_local = frac[ids].contiguous()
         self.Z_local = torch.as_tensor(Z_global, dtype=torch.int32, device=dev)[ids].contiguous()
+        self.halo = HaloExchanger(self.dec, group)
+        self.group = group
+        self.system = None
+        self.build_list()
+        del frac
+
+    def build_list(self):
+        """Min-image list over owned+ghost atoms, rows restricted to the owned (central) atoms."""
+        rt = self.rt
         n_local = self.dec.n_local
         cap = int(n_local * 100) + 4096
-        idx, n_found, overflow = rt.nl_build_minimage(self.R_local, self.box, cutoff, cap)
+        idx, n_found, overflow = rt.nl_build_minimage(self.R_local, self.box, self.cutoff, cap)
         nf = int(n_found.item())
         if int(overflow.item()):
             raise RuntimeError("neighbour list capacity exceeded")
         idx = idx[:, :nf]
-        idx = idx[:, idx[1] < self.dec.n_owned].contiguous()   # only owned atoms are centrals
+        idx = idx[:, idx[1] < self.dec.n_owned].contiguous()
         self.n_pairs = int(idx.shape[1])
-        self.system = rt.PreparedSystem(params, self.Z_local, idx, n_central=self.dec.n_owned)
-        self.halo = HaloExchanger(self.dec, group)
-        self.group = group
-        del frac
+        ws = self.system.ws if self.system is not None else None
+        self.system = rt.PreparedSystem(self.params, self.Z_local, idx, n_central=self.dec.n_owned, workspace=ws)
 
     def local_compute(self, R_local, n_central):
         e, f = self.system.compute(R_local, self.box, None, "minimage")
@@ -207,6 +216,12 @@ def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: 
     frac = pos @ np.linalg.inv(cell)
     sysm = GpuSlabSystem(dp, frac, Z, cell.T.copy(), 6.0, rank, world)
     lib = rt.lib()
+    sampler = None
+    if rank == 0:
+        import bench as _bench
+
+        sampler = _bench.ClockSampler(local)
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         e, f = sysm.step()
     torch.cuda.synchronize()
@@ -224,6 +239,57 @@ def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: 
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = lib.apax_kernel_launch_count() - launches0
+    clocks = sampler.stop(window_s=float(ms.item()) * 1e-3 + 0.1) if sampler else None
+
+    # ---- end to end: owned positions from pinned host memory in, list rebuilt, E+F, owned forces to the host
+    n_owned = sysm.dec.n_owned
+    h_pos = torch.empty((n_owned, 3), dtype=torch.float64).pin_memory()
+    h_pos.copy_(sysm.R_local[:n_owned].cpu())
+    h_f = torch.empty((n_owned, 3), dtype=torch.float64).pin_memory()
+    k_e2e = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        sysm.R_local[:n_owned].copy_(h_pos, non_blocking=True)
+        sysm.halo.forward(sysm.R_local)
+        sysm.build_list()
+        e_, f_ = sysm.step()
+        h_f.copy_(f_, non_blocking=True)
+        e_h = e_.cpu()
+        torch.cuda.synchronize()
+        return e_h
+
+    e2e_step()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        e_h = e2e_step()
+    dist.barrier()
+    dt = torch.tensor([(time.perf_counter() - t0) / k_e2e], dtype=torch.float64, device="cuda")
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+
+    verify = None
+    if getattr(args, "verify", False):
+        # rank 0 evaluates the whole box alone and every rank compares its owned atoms against it
+        ref_e = torch.zeros(1, dtype=torch.float64, device="cuda")
+        ref_f = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+        if rank == 0:
+            fr = rt.to_device(frac, torch.float64)
+            bx = rt.to_device(cell.T.copy(), torch.float64)
+            cap = int(n * 96) + 4096
+            idx, n_found, _ = rt.nl_build_minimage(fr, bx, 6.0, cap)
+            single = rt.PreparedSystem(dp, Z, idx[:, : int(n_found.item())].contiguous())
+            e1, f1 = single.compute(fr, bx, None, "minimage")
+            ref_e.copy_(e1)
+            ref_f.copy_(f1[0])
+            del single, idx
+        dist.broadcast(ref_e, 0)
+        dist.broadcast(ref_f, 0)
+        mine = ref_f[sysm.dec.owned]
+        viol = (torch.abs(f - mine) / (1e-5 * torch.abs(mine) + 1e-6)).max()
+        dist.all_reduce(viol, op=dist.ReduceOp.MAX)
+        verify = {"energy_rel_err": float(torch.abs(e[0] - ref_e[0]) / torch.abs(ref_e[0])),
+                  "max_force_violation_x_tolerance": float(viol)}
+
     stats = torch.tensor([sysm.dec.n_owned, sysm.dec.n_local - sysm.dec.n_owned, sysm.n_pairs, sysm.halo.bytes_per_step],
                          dtype=torch.float64, device="cuda")
     gathered = [torch.zeros_like(stats) for _ in range(world)]
@@ -237,13 +303,19 @@ def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: 
             "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[3]: GMNN default energy+forces, periodic water box, r_max=6 A, "
-                                   "slab domain decomposition with forward/reverse halo exchange over NCCL",
+                                   "slab domain decomposition, forward/reverse halo exchange + energy all-reduce over NCCL",
                        "atoms": n, "parallelism": f"{world} slabs along x", "energy": float(e.cpu()[0]),
                        "per_rank_owned_ghost_pairs_halobytes": per_rank,
                        "l2": "working set per step far exceeds the 126 MB L2"},
-            "gpu_launches": int(launches),
-            "e2e": None,
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": n / float(dt.item()), "unit": unit, "h2d_bytes_per_step": int(n * 24),
+                    "d2h_bytes_per_step": int(n * 24 + 8 * world), "ms_per_step": float(dt.item()) * 1e3, "steps": k_e2e,
+                    "includes": "per rank: pinned-host -> device copy of owned positions, forward halo, neighbour-list "
+                                "rebuild + preparation, E+F, reverse halo, energy all-reduce, device -> pinned-host copy "
+                                "of owned forces and the energy"},
         }
+        if verify:
+            line["verify"] = verify
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
     return 0

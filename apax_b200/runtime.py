@@ -160,14 +160,15 @@ def energy_forces(params: DeviceParams, R, Z, idx, box, offsets, mode: str = "of
 class PreparedSystem:
     """A neighbour list prepared once (apax_gm_prepare) and evaluated many times (apax_gm_compute)."""
 
-    def __init__(self, params: DeviceParams, Z, idx, n_atoms: Optional[int] = None, n_central: Optional[int] = None):
+    def __init__(self, params: DeviceParams, Z, idx, n_atoms: Optional[int] = None, n_central: Optional[int] = None,
+                 workspace: Optional[Workspace] = None):
         self.params = params
         self.n_central = n_central
         self.Z = to_device(Z, torch.int32)
         self.idx = to_device(idx, torch.int32)
         self.n_atoms = int(self.Z.shape[0]) if n_atoms is None else n_atoms
         self.n_pairs = int(self.idx.shape[1])
-        self.ws = Workspace()
+        self.ws = workspace or Workspace()
         self.wp, self.wb = _gm_ws(self.n_atoms, self.n_pairs, params.n_out, self.ws)
         check(lib().apax_gm_prepare(_stream_ptr(), params.handle, _ptr(self.Z), _ptr(self.idx), self.n_atoms, self.n_pairs,
                                     self.wp, self.wb), "apax_gm_prepare")

@@ -36,7 +36,7 @@ UNIT = "atom-steps/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--molecules", type=int, default=333_334, help="water molecules in the box (default: the 1M-atom box)")
@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="multi-GPU: strong = the same box split into slabs (BASELINE configs[3]); weak = box grows with N")
+    ap.add_argument("--verify", action="store_true", help="multi-GPU: compare against a single-GPU evaluation of the whole box")
     return ap.parse_args()
 
 
@@ -69,7 +70,8 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, window_s: float = 0.0):
+        """Summarise the samples of the last `window_s` seconds (the timed region); 0 = all samples."""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -80,7 +82,10 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         try:
-            for line in open(self.path):
+            lines = open(self.path).read().splitlines()
+            if window_s > 0:
+                lines = lines[-max(2, int(window_s / 0.1) + 1):]
+            for line in lines:
                 parts = [p.strip() for p in line.split(",")]
                 if len(parts) < 9:
                     continue
@@ -236,11 +241,11 @@ def run_ours(args):
     def step():
         return system.compute(frac, box_d, None, "minimage")
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = lib.apax_kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -251,7 +256,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms_total = ev0.elapsed_time(ev1)
     launches = lib.apax_kernel_launch_count() - launches0
-    clocks = sampler.stop()
+    time.sleep(0.15)
+    clocks = sampler.stop(window_s=ms_total * 1e-3 + 0.15)
     ms_per_step = ms_total / args.steps
     value = n * args.steps / (ms_total * 1e-3)
     energy = float(e.cpu().numpy()[0])
