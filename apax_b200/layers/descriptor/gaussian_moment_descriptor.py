@@ -1,0 +1,73 @@
+"""Host mirror of apax/layers/descriptor/gaussian_moment_descriptor.py behind the builder seam
+(apax/nn/builder.py:79-83, 248-260): same constructor fields, same call contract
+`representation(dr_vec [P,3], Z [N], neighbor_idxs [2,P]) -> g [N, 360]`, computed by the fused CUDA
+pair + contraction kernels (apax_gm_descriptor with APAX_DISP_DRVEC)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any
+
+from ... import runtime as rt
+
+
+@dataclass
+class GaussianBasis:
+    """apax/layers/descriptor/basis_functions.py:12-17 (statics only; evaluated inside the pair kernels)."""
+    n_basis: int = 7
+    r_min: float = 0.5
+    r_max: float = 6.0
+    dtype: Any = "fp32"
+    spacing: str = "linear"
+
+
+@dataclass
+class RadialFunction:
+    """apax/layers/descriptor/basis_functions.py:88-95 (statics only)."""
+    n_radial: int = 5
+    basis_fn: GaussianBasis = field(default_factory=GaussianBasis)
+    n_species: int = 119
+    emb_init: str = "uniform"
+    use_embed_norm: bool = True
+    one_sided_dist: bool = False
+    dtype: Any = "fp32"
+
+
+@dataclass
+class GaussianMomentDescriptor:
+    radial_fn: RadialFunction = field(default_factory=RadialFunction)
+    n_contr: int = 8
+    dtype: Any = "fp32"
+    apply_mask: bool = True
+
+    def statics(self) -> dict:
+        b = self.radial_fn.basis_fn
+        if b.spacing != "linear" or self.radial_fn.emb_init != "uniform" or self.dtype not in ("fp32", None) or not self.apply_mask:
+            raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "GaussianMomentDescriptor",
+                                        "kernels cover linear Gaussian basis, embedded radial function, fp32, apply_mask=True")
+        return dict(n_basis=b.n_basis, r_min=b.r_min, r_max=b.r_max, n_radial=self.radial_fn.n_radial,
+                    n_species=self.radial_fn.n_species, use_embed_norm=self.radial_fn.use_embed_norm, n_contr=self.n_contr)
+
+    def apply(self, variables: dict, dr_vec, Z, neighbor_idxs):
+        """variables = {"params": {"radial_fn": {"atomic_type_embedding": [S,S,5,7]}}} as flax would pass it."""
+        emb = variables["params"]["radial_fn"]["atomic_type_embedding"]
+        dp = _descriptor_params(emb, self.statics())
+        return rt.descriptor(dp, dr_vec, Z, neighbor_idxs, mode="drvec")
+
+
+_cache: dict = {}
+
+
+def _descriptor_params(emb, statics):
+    import numpy as np
+
+    key = (id(emb), tuple(sorted(statics.items())))
+    if key not in _cache:
+        zeros = lambda *s: np.zeros(s, dtype=np.float32)  # noqa: E731
+        tree = {"representation": {"radial_fn": {"atomic_type_embedding": emb}},
+                "readout": {"dense_0": {"w": zeros(360, 256), "b": zeros(256)}, "dense_1": {"w": zeros(256, 256), "b": zeros(256)},
+                            "dense_2": {"w": zeros(256, 1), "b": zeros(1)}},
+                "scale_shift": {"scale_per_element": np.ones((statics["n_species"], 1)),
+                                "shift_per_element": np.zeros((statics["n_species"], 1))}}
+        cfg = {k: statics[k] for k in ("n_basis", "r_min", "r_max", "n_radial", "use_embed_norm", "n_contr")}
+        _cache[key] = rt.DeviceParams(tree, cfg)
+    return _cache[key]

@@ -1,0 +1,81 @@
+"""Host mirror of apax/md/ase_calc.py::ASECalculator for the energy+forces properties.  ASE itself
+is not a dependency: `calculate` accepts any object with `.positions`, `.numbers`, `.cell` (3x3 array or
+an object with `.array`) -- an `ase.Atoms` qualifies.  The per-call flow (neighbour path selection
+:501-522, list update, model call, results to NumPy fp64 :392-393) is one apax_ctx_calculate call."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from .. import runtime as rt
+from ..nn.models import device_params
+
+
+@dataclass
+class Atoms:
+    """Minimal stand-in with ase.Atoms' attribute names."""
+    positions: np.ndarray
+    numbers: np.ndarray
+    cell: np.ndarray
+    pbc: bool = True
+
+
+class ASECalculator:
+    implemented_properties = ["energy", "forces"]
+
+    def __init__(self, params: dict, model_config: Optional[dict] = None, dr_threshold: float = 0.5,
+                 padding_factor: float = 1.5, max_pairs_per_atom: int = 160):
+        from ..nn.builder import GMNNBuilder
+
+        self.params = params
+        self.builder = GMNNBuilder(model_config)
+        self.dr_threshold = dr_threshold
+        self.padding_factor = padding_factor
+        self.max_pairs_per_atom = max_pairs_per_atom
+        self.ctx: Optional[rt.HostContext] = None
+        self.results: dict = {}
+
+    def _cell(self, atoms) -> np.ndarray:
+        cell = atoms.cell
+        return np.asarray(getattr(cell, "array", cell), dtype=np.float64)
+
+    def initialize(self, atoms, max_pairs: Optional[int] = None):
+        model = self.builder.build_energy_derivative_model(init_box=self._cell(atoms).T)
+        em = getattr(model, "energy_model", model)
+        self.dp = device_params(self.params, em.statics())
+        n = len(atoms.numbers)
+        self.max_pairs = max_pairs or n * self.max_pairs_per_atom
+        if self.ctx is not None:
+            self.ctx.close()
+        self.ctx = rt.HostContext(self.dp, n, self.max_pairs)
+        self.n_atoms = n
+
+    def calculate(self, atoms, properties=("energy",), system_changes=None):
+        if self.ctx is None or len(atoms.numbers) != self.n_atoms:
+            self.initialize(atoms)
+        cell = self._cell(atoms)
+        try:
+            e, f = self.ctx.calculate(atoms.positions, atoms.numbers, cell, dr_threshold=self.dr_threshold)
+        except rt._lib.ApaxB200Error as err:
+            if err.code != rt._lib.ERR_OVERFLOW:
+                raise
+            # "neighbor list overflowed, reallocating." (ase_calc.py:381-384, 345-347)
+            self.initialize(atoms, max_pairs=int(self.ctx.n_pairs * self.padding_factor) + 1024)
+            e, f = self.ctx.calculate(atoms.positions, atoms.numbers, cell, dr_threshold=self.dr_threshold)
+        if self.dp.n_out == 1:
+            self.results = {"energy": float(e[0]), "forces": f[0]}
+        else:
+            n_ens = self.dp.n_out
+            fm = f.mean(axis=0)
+            self.results = {"energy": float(e.mean()), "energy_ensemble": e, "energy_uncertainty": float(np.sqrt(((e - e.mean()) ** 2).sum() / (n_ens - 1))),
+                            "forces": fm, "forces_uncertainty": np.sqrt(((f - fm) ** 2).sum(axis=0) / (n_ens - 1)),
+                            "forces_ensemble": np.transpose(f, (1, 2, 0))}
+        return self.results
+
+    def get_potential_energy(self, atoms):
+        return self.calculate(atoms)["energy"]
+
+    def get_forces(self, atoms):
+        return self.calculate(atoms)["forces"]
