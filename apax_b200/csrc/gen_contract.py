@@ -227,9 +227,20 @@ def emit_forward(blocks):
     return lines
 
 
-def emit_backward(blocks):
+def emit_backward(blocks, prefetch=2):
+    """Reverse mode, block by block.  The feature adjoints gbar(f) of a block are loaded `prefetch`
+    blocks ahead of their use (function-scope variables g<f>), so the global-load latency overlaps the
+    FMA work of the preceding blocks instead of stalling at the point of use."""
     lines = []
-    for b in blocks:
+
+    def loads(b):
+        return [f"  const float g{t[1]} = gbar({t[1]});" for t, _ in b.stmts if t[0] == "f"]
+
+    for b in blocks[:prefetch]:
+        lines.extend(loads(b))
+    for bi, b in enumerate(blocks):
+        if bi + prefetch < len(blocks):
+            lines.extend(loads(blocks[bi + prefetch]))
         lines.append("  {")
         temps = [t for t, _ in b.stmts if t[0] == "t"]
         for target, terms in b.stmts:
@@ -238,13 +249,8 @@ def emit_backward(blocks):
         for t in temps:
             lines.append(f"    float {t[1]}_b = 0.0f;")
         for target, terms in reversed(b.stmts):
-            if target[0] == "f":
-                lines.append("    {")
-                lines.append(f"      const float gb = gbar({target[1]});")
-                bar = "gb"
-            else:
-                lines.append("    {")
-                bar = f"{target[1]}_b"
+            lines.append("    {")
+            bar = f"g{target[1]}" if target[0] == "f" else f"{target[1]}_b"
             for c, a, bb in terms:
                 scale = bar if c == 1 else f"({cf(c)}*{bar})"
                 for x, y in ((a, bb), (bb, a)):

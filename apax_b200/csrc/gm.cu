@@ -44,6 +44,7 @@ size_t carve_gm_workspace(void* base, int64_t n_atoms, int64_t n_pairs, int32_t 
   w.sp_map = c.take<int32_t>(128);
   w.n_sp = c.take<int32_t>(4);
   w.embc = c.take<float>(int64_t(n_species) * n_species * EMB_STRIDE);
+  w.P = c.take<double4>(N + 1);
   w.G = c.take<float4>(P);
   w.D = c.take<float4>(P);
   w.MT = c.take<float>(NPK * ld);
@@ -290,45 +291,93 @@ __device__ __forceinline__ const float* stage_species_table(const GmWorkspace& w
   return emb;
 }
 
+// ---- per-atom gather record: position + compact species id in one aligned 32-byte word
+__global__ void __launch_bounds__(256) k_atom_pack(GmWorkspace ws, PairGeom geo) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= ws.n_atoms) return;
+  int z = geo.Z[i];
+  z = z < 0 ? 0 : (z >= geo.n_species ? geo.n_species - 1 : z);
+  double4 p;
+  if (geo.mode == APAX_DISP_DRVEC) {
+    p.x = p.y = p.z = 0.0;
+  } else {
+    p.x = geo.R[3 * i + 0]; p.y = geo.R[3 * i + 1]; p.z = geo.R[3 * i + 2];
+  }
+  p.w = __longlong_as_double((long long)ws.sp_map[z]);
+  ws.P[i] = p;
+}
+
 // ---- forward: packed moments of every atom.  LPA lanes cooperate on one atom; each lane walks a
 // strided share of the atom's CSR row with the 100 accumulators in registers; an xor-butterfly over
 // the LPA lanes finishes the segmented sum (no atomics, fixed order => bitwise reproducible).
+// The neighbour gathers are software-pipelined: indices two pairs ahead, atom records one pair ahead.
 template <int LPA>
 __global__ void __launch_bounds__(256) k_pair_fwd(GmWorkspace ws, PairGeom geo, DescConst dc) {
   __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * EMB_STRIDE];
   const float* emb = stage_species_table(ws, s_emb);
   const int n_sp = *ws.n_sp;
+  const int32_t* __restrict__ nbr = ws.nbr;
+  const int32_t* __restrict__ src = ws.src;
+  const double4* __restrict__ P = ws.P;
+  const double* __restrict__ offs = geo.mode == APAX_DISP_DRVEC ? geo.R : geo.offsets;
+  float4* __restrict__ G = ws.G;
   const int64_t gid = int64_t(blockIdx.x) * 256 + threadIdx.x;
   const int64_t atom = gid / LPA;
   const int sub = int(gid % LPA);
   const bool valid = atom < ws.n_central;
+  const bool plain = geo.mode == APAX_DISP_GAS || geo.mode == APAX_DISP_DRVEC;
+  const bool wrap = geo.mode == APAX_DISP_MINIMAGE;
   int beg = 0, end = 0, zc = 0;
   double Ra[3] = {0.0, 0.0, 0.0};
   double box[9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) box[i] = (geo.mode == APAX_DISP_GAS || geo.mode == APAX_DISP_DRVEC) ? 0.0 : geo.box[i];
+  for (int i = 0; i < 9; ++i) box[i] = plain ? ((i % 4 == 0 && geo.mode == APAX_DISP_GAS) ? 1.0 : 0.0) : __ldg(geo.box + i);
   if (valid) {
     beg = ws.rowptr[atom];
     end = ws.rowptr[atom + 1];
-    if (geo.mode != APAX_DISP_DRVEC) {
-      Ra[0] = geo.R[3 * atom + 0]; Ra[1] = geo.R[3 * atom + 1]; Ra[2] = geo.R[3 * atom + 2];
-    }
-    int z = geo.Z[atom];
-    z = z < 0 ? 0 : (z >= geo.n_species ? geo.n_species - 1 : z);
-    zc = ws.sp_map[z];
+    const double4 pa = P[atom];
+    Ra[0] = pa.x; Ra[1] = pa.y; Ra[2] = pa.z;
+    zc = int(__double_as_longlong(pa.w));
   }
   float acc[NPK];
 #pragma unroll
   for (int k = 0; k < NPK; ++k) acc[k] = 0.0f;
 
-  for (int e = beg + sub; e < end; e += LPA) {
-    const int j = ws.nbr[e];
-    float dx, dy, dz;
-    pair_displacement(geo, box, Ra, j, ws.src[e], dx, dy, dz);
-    int zj = geo.Z[j];
-    zj = zj < 0 ? 0 : (zj >= geo.n_species ? geo.n_species - 1 : zj);
-    const int pt = zc * n_sp + ws.sp_map[zj];  // embeddings[Z_central, Z_neighbour] (basis_functions.py:139-141)
-    ws.G[e] = make_float4(dx, dy, dz, __int_as_float(pt));
+  int e = beg + sub;
+  const int safe = valid ? int(atom) : 0;
+  int j_cur = e < end ? __ldg(nbr + e) : safe;
+  int j_nxt = e + LPA < end ? __ldg(nbr + e + LPA) : safe;
+  double4 p_cur = P[j_cur];
+  double o_cur[3] = {0.0, 0.0, 0.0};
+  if (offs && e < end) {
+    const int64_t sp = __ldg(src + e);
+    o_cur[0] = __ldg(offs + 3 * sp); o_cur[1] = __ldg(offs + 3 * sp + 1); o_cur[2] = __ldg(offs + 3 * sp + 2);
+  }
+  for (; e < end; e += LPA) {
+    // ---- issue the gathers of the following pairs before touching this one
+    const int j_nn = e + 2 * LPA < end ? __ldg(nbr + e + 2 * LPA) : safe;
+    const double4 p_nxt = P[j_nxt];
+    double o_nxt[3] = {0.0, 0.0, 0.0};
+    if (offs && e + LPA < end) {
+      const int64_t sp = __ldg(src + e + LPA);
+      o_nxt[0] = __ldg(offs + 3 * sp); o_nxt[1] = __ldg(offs + 3 * sp + 1); o_nxt[2] = __ldg(offs + 3 * sp + 2);
+    }
+    // ---- displacement in fp64 (distances.py:48-67), cast once to fp32 (gaussian_moment_descriptor.py:33)
+    double v0 = Ra[0] - p_cur.x, v1 = Ra[1] - p_cur.y, v2 = Ra[2] - p_cur.z;
+    if (wrap) { v0 = wrap_unit(v0); v1 = wrap_unit(v1); v2 = wrap_unit(v2); }
+    double d0, d1, d2;
+    if (geo.mode == APAX_DISP_GAS) {
+      d0 = v0; d1 = v1; d2 = v2;
+    } else {
+      d0 = box[0] * v0 + box[1] * v1 + box[2] * v2 + o_cur[0];
+      d1 = box[3] * v0 + box[4] * v1 + box[5] * v2 + o_cur[1];
+      d2 = box[6] * v0 + box[7] * v1 + box[8] * v2 + o_cur[2];
+    }
+    const float dx = float(d0), dy = float(d1), dz = float(d2);
+    const int pt = zc * n_sp + int(__double_as_longlong(p_cur.w));  // embeddings[Z_central, Z_neighbour] (basis_functions.py:139-141)
+    G[e] = make_float4(dx, dy, dz, __int_as_float(pt));
+    p_cur = p_nxt; j_cur = j_nxt; j_nxt = j_nn;
+    o_cur[0] = o_nxt[0]; o_cur[1] = o_nxt[1]; o_cur[2] = o_nxt[2];
     const float r2 = dx * dx + dy * dy + dz * dz;
     const float r = r2 > 0.0f ? sqrtf(r2) : 0.0f;  // space.distance + safe_mask (space.py:314-323)
     if (r >= dc.r_max) continue;                   // cosine cutoff is exactly 0 there (basis_functions.py:82-85)
@@ -389,8 +438,12 @@ __global__ void __launch_bounds__(256) k_pair_bwd(GmWorkspace ws, DescConst dc) 
     for (int k = 0; k < NPK; ++k) a[k] = 0.0f;
   }
   double sx = 0.0, sy = 0.0, sz = 0.0;
+  const float4* __restrict__ Gp = ws.G;
+  float4* __restrict__ Dp = ws.D;
+  float4 g_nxt = beg + sub < end ? __ldg(Gp + beg + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int e = beg + sub; e < end; e += LPA) {
-    const float4 g = ws.G[e];
+    const float4 g = g_nxt;
+    if (e + LPA < end) g_nxt = __ldg(Gp + e + LPA);  // next pair's geometry is in flight during this pair's math
     const float dx = g.x, dy = g.y, dz = g.z;
     const int pt = __float_as_int(g.w);
     const float r2 = dx * dx + dy * dy + dz * dz;
@@ -453,7 +506,7 @@ __global__ void __launch_bounds__(256) k_pair_bwd(GmWorkspace ws, DescConst dc) 
       out.z = fmaf(radial, dz, s * nz);
       sx += double(out.x); sy += double(out.y); sz += double(out.z);
     }
-    ws.D[e] = out;
+    Dp[e] = out;
   }
 #pragma unroll
   for (int o = LPA / 2; o > 0; o >>= 1) {
@@ -797,6 +850,7 @@ static int gm_descriptor_impl(cudaStream_t stream, const apax_gm_params_impl* p,
                               const PairGeom& geo) {
   const DescConst dc = make_desc_const(p->cfg);
   const int lpa = pick_lpa(w.n_central);
+  APAX_LAUNCH(k_atom_pack, dim3((unsigned)cdiv(w.n_atoms, 256)), dim3(256), 0, stream, w, geo);
   APAX_DISPATCH_LPA(lpa, launch_pair_fwd, stream, w, geo, dc);
   APAX_LAUNCH(k_contract_fwd, dim3((unsigned)cdiv(w.n_central, 128)), dim3(128), 0, stream, w);
   return APAX_OK;

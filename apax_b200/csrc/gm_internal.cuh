@@ -52,6 +52,8 @@ struct GmWorkspace {
   int32_t* sp_map;      // [128] Z -> compact id
   int32_t* n_sp;        // [1]
   float* embc;          // [n_sp*n_sp][36]
+  // per atom: (x, y, z, compact species id as int bits) -- one aligned 32-byte gather per neighbour
+  double4* P;
   // per pair
   float4* G;  // (dx,dy,dz, pair-table index as int bits)
   float4* D;  // dE/d(dr_vec) per pair

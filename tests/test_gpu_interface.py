@@ -96,7 +96,7 @@ def test_energy_fn_for_md():
     energy_fn = create_energy_fn(model, params, Z, n_models=1)
     e = float(energy_fn(frac, nbrs, box))
     f = energy_fn.force_fn(frac, nbrs, box).cpu().numpy()
-    h = 1e-4
+    h = 5e-3  # fp32 energy noise ~2e-5 eV: the difference quotient is only good to ~1e-2
     inv = np.linalg.inv(cell)
     for a, k in [(0, 0), (17, 2)]:
         dc = np.zeros(3)
@@ -105,4 +105,4 @@ def test_energy_fn_for_md():
         fp[a] += dc @ inv
         fm[a] -= dc @ inv
         fd = -(float(energy_fn(fp, nbrs, box)) - float(energy_fn(fm, nbrs, box))) / (2 * h)
-        assert abs(fd - f[a, k]) < 2e-3 * max(1.0, abs(f[a, k]))     # fp32 energies: coarse central difference
+        assert abs(fd - f[a, k]) < 2e-2 * max(1.0, abs(f[a, k]))
