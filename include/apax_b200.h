@@ -182,6 +182,14 @@ int apax_ctx_calculate(apax_ctx* ctx, const double* positions_host, const int32_
                        const double* cell_host, int64_t n_atoms, double dr_threshold, int32_t rebuild,
                        double* energy_host, double* forces_host, int64_t* n_pairs_host);
 
+/* Readout GEMM building block on the tcgen05 tensor cores, exposed for tests and measurement:
+ * out[nc][ld] = sum_k act[k][atom] * wgt[k][n] with both operands given as exact tf32 (hi, lo) pairs
+ * (3xTF32, fp32-accurate; replaces jnp.dot in apax/layers/ntk_linear.py:40).  act_* f32 [k][ld],
+ * wgt_* f32 [k][nc], nc % 128 == 0, ld % 128 == 0; err_flag i32 [1] is set to 1 on a pipeline time-out. */
+int apax_tc_gemm_test(apax_stream_t stream, const float* act_hi, const float* act_lo, int64_t k, int64_t ld,
+                      int64_t n_atoms, const float* wgt_hi, const float* wgt_lo, int64_t nc, float* out,
+                      int32_t* err_flag);
+
 /* Diagnostics */
 int apax_abi_version(void);
 const char* apax_last_cuda_error(void);
