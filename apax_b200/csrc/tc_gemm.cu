@@ -65,10 +65,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), MN-major, SWIZZLE_128B:
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (stride between 128-byte MN chunks)
 //   [32,46) stride byte offset >> 4 (stride between groups of 8 k-rows)   [46,48) version = 1
-//   [61,64) layout type = 2 (SWIZZLE_128B)
+//   [61,64) layout type = 1 (SWIZZLE_128B_BASE32B): the only shared-memory layout the tensor core accepts for
+//   MN-major 32-bit operands -- 128-byte rows, 32-byte swizzle granules, pattern period 4 k-rows
+//   (cute::UMMA::Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> over 128 B x 4 rows); TMA writes it with
+//   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return uint64_t((addr >> 4) & 0x3fffu) | (uint64_t((lbo_bytes >> 4) & 0x3fffu) << 16) |
-         (uint64_t((sbo_bytes >> 4) & 0x3fffu) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+         (uint64_t((sbo_bytes >> 4) & 0x3fffu) << 32) | (uint64_t(1) << 46) | (uint64_t(1) << 61);
 }
 
 // cute::UMMA::InstrDescriptor: c_format F32 (1) at [4,6), a/b format TF32 (2) at [7,10)/[10,13),
@@ -142,7 +145,12 @@ __global__ void __launch_bounds__(128) k_tc_gemm(const __grid_constant__ CUtenso
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
-    constexpr uint32_t idesc = make_idesc(TC_BM, BN);
+    uint32_t idesc = make_idesc(TC_BM, BN);
+    if (epi.dbg_flags & 1) idesc &= ~((1u << 15) | (1u << 16));
+    // MN chunk (32 atoms / features) stride, and stride between groups of 4 k-rows
+    const uint32_t lbo = (epi.dbg_flags & 2) ? 512u : S::CHUNK_STRIDE;
+    const uint32_t sbo = (epi.dbg_flags & 2) ? S::CHUNK_STRIDE : 512u;
+    const uint64_t desc_mask = (epi.dbg_flags & 4) ? ~(uint64_t(7) << 61) : ~uint64_t(0);
     bool ok = true;
     for (int kb = 0; kb < num_k_blocks && ok; ++kb) {
       const int s = kb % TC_STAGES;
@@ -151,13 +159,22 @@ __global__ void __launch_bounds__(128) k_tc_gemm(const __grid_constant__ CUtenso
       if (!ok) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t stage = smem_base + s * S::STAGE_BYTES;
+      if (epi.dbg && kb == 0) {
+        for (uint32_t i = 0; i < S::STAGE_BYTES / 4 && i < 16384; ++i) {
+          float v;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stage + i * 4));
+          epi.dbg[i] = v;
+        }
+        epi.dbg[16384] = __uint_as_float(tmem_d);
+        epi.dbg[16385] = __uint_as_float(stage);
+      }
 #pragma unroll
       for (int g = 0; g < TC_BK / 8; ++g) {
         const uint32_t koff = g * 1024;  // 8 k-rows x 128 B
-        const uint64_t a_hi = make_smem_desc(stage + koff, S::CHUNK_STRIDE, 1024);
-        const uint64_t a_lo = make_smem_desc(stage + S::A_BYTES + koff, S::CHUNK_STRIDE, 1024);
-        const uint64_t b_hi = make_smem_desc(stage + 2 * S::A_BYTES + koff, S::CHUNK_STRIDE, 1024);
-        const uint64_t b_lo = make_smem_desc(stage + 2 * S::A_BYTES + S::B_BYTES + koff, S::CHUNK_STRIDE, 1024);
+        const uint64_t a_hi = make_smem_desc(stage + koff, lbo, sbo) & desc_mask;
+        const uint64_t a_lo = make_smem_desc(stage + S::A_BYTES + koff, lbo, sbo) & desc_mask;
+        const uint64_t b_hi = make_smem_desc(stage + 2 * S::A_BYTES + koff, lbo, sbo) & desc_mask;
+        const uint64_t b_lo = make_smem_desc(stage + 2 * S::A_BYTES + S::B_BYTES + koff, lbo, sbo) & desc_mask;
         umma_tf32(tmem_d, a_hi, b_hi, idesc, (kb | g) != 0 ? 1u : 0u);
         umma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
         umma_tf32(tmem_d, a_lo, b_hi, idesc, 1u);
@@ -236,7 +253,7 @@ int make_tmap(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, in
   const cuuint32_t box[3] = {32, TC_BK, cuuint32_t(box_chunks)};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? APAX_OK : APAX_ERR_INVALID_ARG;
 }
@@ -276,12 +293,14 @@ int tc_gemm(cudaStream_t stream, const TcOperand& act, const TcOperand& wgt, int
 // Test / measurement entry: out[NC][ld] = act^T . wgt through the tensor-core path (plain store epilogue).
 extern "C" int apax_tc_gemm_test(apax_stream_t stream, const float* act_hi, const float* act_lo, int64_t k, int64_t ld,
                                  int64_t n_atoms, const float* wgt_hi, const float* wgt_lo, int64_t nc, float* out,
-                                 int32_t* err_flag) {
+                                 int32_t* err_flag, float* dbg, int32_t dbg_flags) {
   if (!act_hi || !act_lo || !wgt_hi || !wgt_lo || !out || !err_flag) return APAX_ERR_INVALID_ARG;
   apax::TcOperand a{act_hi, act_lo, k, ld}, w{wgt_hi, wgt_lo, k, nc};
   apax::TcEpilogue e{};
   e.mode = apax::TC_EPI_STORE;
   e.ld = ld;
   e.out_hi = out;
+  e.dbg = dbg;
+  e.dbg_flags = dbg_flags;
   return apax::tc_gemm(stream, a, w, n_atoms, e, err_flag);
 }

@@ -32,6 +32,8 @@ struct TcEpilogue {
   float* out_lo;      // [NC][ld]  ACT / MULD: residual
   float* aux;         // ACT: swish'(y) written here;  MULD: multiplier read from here
   const float* bias;  // ACT: [NC]
+  int dbg_flags;      // debug only: 1 = K-major instruction descriptor, 2 = LBO/SBO swapped, 4 = no swizzle bits
+  float* dbg;         // debug only: first stage of shared memory is dumped here (16384 floats) when non-null
 };
 
 struct TcOperand {   // one feature-major / row-major fp32 matrix [rows][cols], as hi and lo parts

@@ -188,7 +188,7 @@ int apax_ctx_calculate(apax_ctx* ctx, const double* positions_host, const int32_
  * wgt_* f32 [k][nc], nc % 128 == 0, ld % 128 == 0; err_flag i32 [1] is set to 1 on a pipeline time-out. */
 int apax_tc_gemm_test(apax_stream_t stream, const float* act_hi, const float* act_lo, int64_t k, int64_t ld,
                       int64_t n_atoms, const float* wgt_hi, const float* wgt_lo, int64_t nc, float* out,
-                      int32_t* err_flag);
+                      int32_t* err_flag, float* debug_dump /* NULL, or f32 [16386] */, int32_t debug_flags /* 0 */);
 
 /* Diagnostics */
 int apax_abi_version(void);

@@ -28,7 +28,7 @@ def test_tc_gemm_matches_fp64(k, nc, n_atoms):
     out = torch.zeros(nc, ld, device=dev, dtype=torch.float32)
     err = torch.zeros(1, device=dev, dtype=torch.int32)
     rc = rt.lib().apax_tc_gemm_test(rt._stream_ptr(), rt._ptr(a_hi), rt._ptr(a_lo), k, ld, n_atoms, rt._ptr(w_hi), rt._ptr(w_lo),
-                                    nc, rt._ptr(out), rt._ptr(err))
+                                    nc, rt._ptr(out), rt._ptr(err), None, 0)
     assert rc == 0
     torch.cuda.synchronize()
     assert int(err.item()) == 0, "tensor-core pipeline timed out"
