@@ -49,6 +49,7 @@ SIGNATURES = {
     "apax_profile_collect": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "apax_gm_params_create": (C.c_int, [C.POINTER(GmConfig), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     "apax_gm_params_destroy": (None, [_P]),
+    "apax_gm_params_status": (C.c_int, [_P]),
     "apax_gm_workspace_bytes": (C.c_size_t, [_I64, _I64, _I32]),
     "apax_gm_energy_forces": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, C.c_size_t]),
     "apax_gm_prepare": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, C.c_size_t]),

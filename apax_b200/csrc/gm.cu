@@ -13,6 +13,10 @@
 
 #include "contract_gen.cuh"
 #include "gm_internal.cuh"
+#include "tc_gemm.cuh"
+
+#include <stdlib.h>
+#include <string.h>
 
 namespace apax {
 
@@ -54,6 +58,9 @@ size_t carve_gm_workspace(void* base, int64_t n_atoms, int64_t n_pairs, int32_t 
   w.D1T = c.take<float>(NH * ld);
   w.H2T = c.take<float>(NH * ld);
   w.D2T = c.take<float>(NH * ld);
+  w.GLT = c.take<float>(NFP * ld);
+  w.H1LT = c.take<float>(NH * ld);
+  w.H2LT = c.take<float>(NH * ld);
   w.ebar = c.take<float>(ld);
   w.Eatom = c.take<double>(int64_t(n_out) * ld);
   w.partial = c.take<double>(int64_t(n_out) * 256);
@@ -555,6 +562,7 @@ __global__ void __launch_bounds__(256) k_force_gather(GmWorkspace ws, double* __
 // ================================================================================================
 // contractions (thread per atom, generated straight-line code on packed moments)
 // ================================================================================================
+template <bool SPLIT>
 __global__ void __launch_bounds__(128) k_contract_fwd(GmWorkspace ws) {
   const int64_t atom = int64_t(blockIdx.x) * 128 + threadIdx.x;
   if (atom >= ws.n_central) return;
@@ -562,8 +570,18 @@ __global__ void __launch_bounds__(128) k_contract_fwd(GmWorkspace ws) {
 #pragma unroll
   for (int k = 0; k < NPK; ++k) m[k] = ws.MT[int64_t(k) * ws.ld + atom];
   float* gt = ws.GT + atom;
+  float* glt = ws.GLT + atom;
   const int64_t ld = ws.ld;
-  gm_contract_forward(m, [&](int f, float v) { gt[int64_t(f) * ld] = v; });
+  gm_contract_forward(m, [&](int f, float v) {
+    if (SPLIT) {  // tensor-core readout consumes exact (tf32 hi, residual lo) pairs
+      float hi, lo;
+      split_tf32(v, hi, lo);
+      gt[int64_t(f) * ld] = hi;
+      glt[int64_t(f) * ld] = lo;
+    } else {
+      gt[int64_t(f) * ld] = v;
+    }
+  });
 }
 
 __global__ void __launch_bounds__(128) k_contract_bwd(GmWorkspace ws) {
@@ -722,7 +740,7 @@ __global__ void __launch_bounds__(256, 2) k_sgemm(GemmArgs g) {
 // ---- output layer + PerElementScaleShift + mask_by_atom (readout.py:47-50, scaling.py:40-50,
 // models.py:109-112).  Thread per atom; h = H2 . w2 + b2 in fp32, E_i in fp64.
 template <int NOUT>
-__global__ void __launch_bounds__(128) k_head(const float* __restrict__ H2T, int64_t ld, int64_t N,
+__global__ void __launch_bounds__(128) k_head(const float* __restrict__ H2T, const float* __restrict__ H2LT, int64_t ld, int64_t N,
                                               const float* __restrict__ w2, const float* __restrict__ b2, int n_out,
                                               const int32_t* __restrict__ Z, int S, const double* __restrict__ scale,
                                               const double* __restrict__ shift, int mask_atoms,
@@ -738,7 +756,8 @@ __global__ void __launch_bounds__(128) k_head(const float* __restrict__ H2T, int
 #pragma unroll
   for (int k = 0; k < NOUT; ++k) acc[k] = 0.0f;
   for (int n = 0; n < NH; ++n) {
-    const float h = H2T[int64_t(n) * ld + m];
+    float h = H2T[int64_t(n) * ld + m];
+    if (H2LT) h += H2LT[int64_t(n) * ld + m];  // hi + lo is the exact fp32 activation
 #pragma unroll
     for (int k = 0; k < NOUT; ++k)
       if (k < n_out) acc[k] = fmaf(h, w2[n * n_out + k], acc[k]);
@@ -754,6 +773,24 @@ __global__ void __launch_bounds__(128) k_head(const float* __restrict__ H2T, int
 }
 
 __device__ __forceinline__ int64_t cdiv_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- dE/dy2 = ebar * w2[:,head] * swish'(y2) as an exact (tf32 hi, lo) pair: input of the backward tensor-core GEMM
+__global__ void __launch_bounds__(256) k_ybar2(const float* __restrict__ D2T, const float* __restrict__ ebar,
+                                               const float* __restrict__ w2, int n_out, int head, int64_t ld,
+                                               int64_t n_cols, float* __restrict__ out_hi, float* __restrict__ out_lo) {
+  const int64_t m4 = (int64_t(blockIdx.x) * 256 + threadIdx.x) * 4;
+  const int n = blockIdx.y;
+  if (m4 >= n_cols) return;
+  const float w = w2[n * n_out + head];
+  const float4 d = *reinterpret_cast<const float4*>(D2T + int64_t(n) * ld + m4);
+  const float4 e = *reinterpret_cast<const float4*>(ebar + m4);
+  const float v[4] = {e.x * w * d.x, e.y * w * d.y, e.z * w * d.z, e.w * w * d.w};
+  float hi[4], lo[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) split_tf32(v[q], hi[q], lo[q]);
+  *reinterpret_cast<float4*>(out_hi + int64_t(n) * ld + m4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<float4*>(out_lo + int64_t(n) * ld + m4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+}
 
 // ---- fp64 energy sum, two fixed-shape stages => deterministic (apax/utils/math.py:7-12)
 __global__ void __launch_bounds__(256) k_energy_partial(const double* __restrict__ Eatom, int64_t ld, int64_t N,
@@ -847,63 +884,139 @@ static PairGeom make_geom(const apax_gm_params_impl* p, const double* R, const i
 
 // descriptor forward: moments + contractions -> GT
 static int gm_descriptor_impl(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w,
-                              const PairGeom& geo) {
+                              const PairGeom& geo, bool split_features = false) {
   const DescConst dc = make_desc_const(p->cfg);
   const int lpa = pick_lpa(w.n_central);
   APAX_LAUNCH(k_atom_pack, dim3((unsigned)cdiv(w.n_atoms, 256)), dim3(256), 0, stream, w, geo);
   APAX_DISPATCH_LPA(lpa, launch_pair_fwd, stream, w, geo, dc);
-  APAX_LAUNCH(k_contract_fwd, dim3((unsigned)cdiv(w.n_central, 128)), dim3(128), 0, stream, w);
+  if (split_features) {
+    APAX_LAUNCH(k_contract_fwd<true>, dim3((unsigned)cdiv(w.n_central, 128)), dim3(128), 0, stream, w);
+  } else {
+    APAX_LAUNCH(k_contract_fwd<false>, dim3((unsigned)cdiv(w.n_central, 128)), dim3(128), 0, stream, w);
+  }
   return APAX_OK;
 }
 
-static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w,
-                           const PairGeom& geo, double* energy, double* forces) {
-  const int64_t N = w.n_central, ld = w.ld;  // per-central work only; ghosts enter as neighbours
-  const int n_out = p->cfg.n_out;
-  const DescConst dc = make_desc_const(p->cfg);
-  const int lpa = pick_lpa(N);
-  APAX_TRY(gm_descriptor_impl(stream, p, w, geo));
+// Readout implementation switch.  Default: tensor cores (tcgen05, 3xTF32).  APAX_B200_READOUT=simt selects
+// the fp32 CUDA-core GEMMs (kept as the A/B reference for the tensor-core path; same results to fp32 rounding).
+static bool readout_on_tensor_cores() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("APAX_B200_READOUT");
+    mode = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return mode == 1;
+}
 
+static int readout_head_and_energy(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w,
+                                   const PairGeom& geo, const float* h2_lo, double* energy) {
+  const int64_t N = w.n_central, ld = w.ld;
+  const int n_out = p->cfg.n_out;
   const int64_t m_tiles = cdiv(N, 128);
-  const dim3 grid_h((unsigned)m_tiles, NH / 128);
-  {  // layer 0: 360 -> 256
-    GemmArgs a{};
-    a.W = p->w0; a.ldw = NH; a.XT = w.GT; a.YT = w.H1T; a.Y2T = w.D1T; a.bias = p->b0; a.K = NF; a.ld = ld;
-    auto k_sgemm_fwd_l0 = k_sgemm<PRO_NONE, EPI_ACT>;
-    APAX_LAUNCH(k_sgemm_fwd_l0, grid_h, dim3(256), 0, stream, a);
-  }
-  {  // layer 1: 256 -> 256
-    GemmArgs a{};
-    a.W = p->w1; a.ldw = NH; a.XT = w.H1T; a.YT = w.H2T; a.Y2T = w.D2T; a.bias = p->b1; a.K = NH; a.ld = ld;
-    auto k_sgemm_fwd_l1 = k_sgemm<PRO_NONE, EPI_ACT>;
-    APAX_LAUNCH(k_sgemm_fwd_l1, grid_h, dim3(256), 0, stream, a);
-  }
   if (n_out == 1) {
-    APAX_LAUNCH(k_head<1>, dim3((unsigned)m_tiles), dim3(128), 0, stream, w.H2T, ld, N, p->w2, p->b2, n_out,
+    APAX_LAUNCH(k_head<1>, dim3((unsigned)m_tiles), dim3(128), 0, stream, w.H2T, h2_lo, ld, N, p->w2, p->b2, n_out,
                 geo.Z, p->cfg.n_species, p->scale, p->shift, p->cfg.mask_atoms, w.Eatom, w.ebar);
   } else {
-    APAX_LAUNCH(k_head<MAX_OUT>, dim3((unsigned)m_tiles), dim3(128), 0, stream, w.H2T, ld, N, p->w2, p->b2,
+    APAX_LAUNCH(k_head<MAX_OUT>, dim3((unsigned)m_tiles), dim3(128), 0, stream, w.H2T, h2_lo, ld, N, p->w2, p->b2,
                 n_out, geo.Z, p->cfg.n_species, p->scale, p->shift, p->cfg.mask_atoms, w.Eatom, w.ebar);
   }
   const int n_blk = int(N < 256 * 64 ? 1 : (N / (256 * 64) > 256 ? 256 : N / (256 * 64)));
   APAX_LAUNCH(k_energy_partial, dim3(n_blk, n_out), dim3(256), 0, stream, w.Eatom, ld, N, w.partial);
   APAX_LAUNCH(k_energy_final, dim3(n_out), dim3(32), 0, stream, w.partial, n_blk, energy);
-  if (!forces) return APAX_OK;
+  return APAX_OK;
+}
 
+// ---- readout forward + (per head) backward down to dE/dg in GT, on the fp32 CUDA cores
+static int readout_simt(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const PairGeom& geo,
+                        double* energy, int head /* -1: forward only */) {
+  const int64_t N = w.n_central, ld = w.ld;
+  const int n_out = p->cfg.n_out;
+  const int64_t m_tiles = cdiv(N, 128);
+  const dim3 grid_h((unsigned)m_tiles, NH / 128);
+  if (head < 0) {
+    {  // layer 0: 360 -> 256
+      GemmArgs a{};
+      a.W = p->w0; a.ldw = NH; a.XT = w.GT; a.YT = w.H1T; a.Y2T = w.D1T; a.bias = p->b0; a.K = NF; a.ld = ld;
+      auto k_sgemm_fwd_l0 = k_sgemm<PRO_NONE, EPI_ACT>;
+      APAX_LAUNCH(k_sgemm_fwd_l0, grid_h, dim3(256), 0, stream, a);
+    }
+    {  // layer 1: 256 -> 256
+      GemmArgs a{};
+      a.W = p->w1; a.ldw = NH; a.XT = w.H1T; a.YT = w.H2T; a.Y2T = w.D2T; a.bias = p->b1; a.K = NH; a.ld = ld;
+      auto k_sgemm_fwd_l1 = k_sgemm<PRO_NONE, EPI_ACT>;
+      APAX_LAUNCH(k_sgemm_fwd_l1, grid_h, dim3(256), 0, stream, a);
+    }
+    return readout_head_and_energy(stream, p, w, geo, nullptr, energy);
+  }
+  {  // dE/dy1 = (W1 . dE/dy2) * act'(y1),  dE/dy2 = ebar * w2[:,head] * act'(y2) applied on load
+    GemmArgs a{};
+    a.W = p->w1t; a.ldw = NH; a.XT = w.D2T; a.YT = w.H1T; a.Y2T = w.D1T; a.K = NH; a.ld = ld;
+    a.ebar = w.ebar; a.wcol = p->w2 + head; a.wstride = n_out;
+    auto k_sgemm_bwd_l1 = k_sgemm<PRO_HEAD, EPI_MULD>;
+    APAX_LAUNCH(k_sgemm_bwd_l1, grid_h, dim3(256), 0, stream, a);
+  }
+  {  // dE/dg = W0 . dE/dy1   (360 rows padded to 384)
+    GemmArgs a{};
+    a.W = p->w0t; a.ldw = NFP; a.XT = w.H1T; a.YT = w.GT; a.K = NH; a.ld = ld;
+    auto k_sgemm_bwd_l0 = k_sgemm<PRO_NONE, EPI_STORE>;
+    APAX_LAUNCH(k_sgemm_bwd_l0, dim3((unsigned)m_tiles, NFP / 128), dim3(256), 0, stream, a);
+  }
+  return APAX_OK;
+}
+
+// ---- the same on the tensor cores: every activation travels as an exact (tf32 hi, lo) pair
+static int readout_tc(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const PairGeom& geo,
+                      double* energy, int head) {
+  const int64_t N = w.n_central, ld = w.ld;
+  const int n_out = p->cfg.n_out;
+  if (head < 0) {
+    {  // layer 0: 360 -> 256, swish + swish' epilogue
+      TcOperand act{w.GT, w.GLT, NF, ld}, wgt{p->w0_hi, p->w0_lo, NF, NH};
+      TcEpilogue e{};
+      e.mode = TC_EPI_ACT; e.ld = ld; e.out_hi = w.H1T; e.out_lo = w.H1LT; e.aux = w.D1T; e.bias = p->b0;
+      APAX_TRY(tc_gemm(stream, act, wgt, N, e, p->tc_err));
+    }
+    {  // layer 1: 256 -> 256
+      TcOperand act{w.H1T, w.H1LT, NH, ld}, wgt{p->w1_hi, p->w1_lo, NH, NH};
+      TcEpilogue e{};
+      e.mode = TC_EPI_ACT; e.ld = ld; e.out_hi = w.H2T; e.out_lo = w.H2LT; e.aux = w.D2T; e.bias = p->b1;
+      APAX_TRY(tc_gemm(stream, act, wgt, N, e, p->tc_err));
+    }
+    return readout_head_and_energy(stream, p, w, geo, w.H2LT, energy);
+  }
+  const int64_t n_cols = round_up(N, 128);
+  APAX_LAUNCH(k_ybar2, dim3((unsigned)cdiv(n_cols, 1024), NH), dim3(256), 0, stream, w.D2T, w.ebar, p->w2, n_out, head, ld,
+              n_cols, w.H2T, w.H2LT);  // H2 was consumed by the head kernel: its buffers now carry dE/dy2
+  {  // dE/dy1 = (W1 . dE/dy2) * swish'(y1)
+    TcOperand act{w.H2T, w.H2LT, NH, ld}, wgt{p->w1t_hi, p->w1t_lo, NH, NH};
+    TcEpilogue e{};
+    e.mode = TC_EPI_MULD; e.ld = ld; e.out_hi = w.H1T; e.out_lo = w.H1LT; e.aux = w.D1T;
+    APAX_TRY(tc_gemm(stream, act, wgt, N, e, p->tc_err));
+  }
+  {  // dE/dg = W0 . dE/dy1 (384 padded rows)
+    TcOperand act{w.H1T, w.H1LT, NH, ld}, wgt{p->w0t_hi, p->w0t_lo, NH, NFP};
+    TcEpilogue e{};
+    e.mode = TC_EPI_STORE; e.ld = ld; e.out_hi = w.GT;
+    APAX_TRY(tc_gemm(stream, act, wgt, N, e, p->tc_err));
+  }
+  return APAX_OK;
+}
+
+static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w,
+                           const PairGeom& geo, double* energy, double* forces) {
+  const int64_t N = w.n_central;  // per-central work only; ghosts enter as neighbours
+  const int n_out = p->cfg.n_out;
+  const DescConst dc = make_desc_const(p->cfg);
+  const int lpa = pick_lpa(N);
+  const bool tc = readout_on_tensor_cores();
+  APAX_TRY(gm_descriptor_impl(stream, p, w, geo, tc));
+  APAX_TRY(tc ? readout_tc(stream, p, w, geo, energy, -1) : readout_simt(stream, p, w, geo, energy, -1));
+  if (!forces) return APAX_OK;
   for (int head = 0; head < n_out; ++head) {
-    {  // dE/dy1 = (W1 . dE/dy2) * act'(y1),  dE/dy2 = ebar * w2[:,head] * act'(y2) applied on load
-      GemmArgs a{};
-      a.W = p->w1t; a.ldw = NH; a.XT = w.D2T; a.YT = w.H1T; a.Y2T = w.D1T; a.K = NH; a.ld = ld;
-      a.ebar = w.ebar; a.wcol = p->w2 + head; a.wstride = n_out;
-      auto k_sgemm_bwd_l1 = k_sgemm<PRO_HEAD, EPI_MULD>;
-      APAX_LAUNCH(k_sgemm_bwd_l1, grid_h, dim3(256), 0, stream, a);
+    if (tc && head > 0) {
+      // the previous head's backward overwrote H2 (dE/dy2) only; D1/D2/ebar are intact -- nothing to redo
     }
-    {  // dE/dg = W0 . dE/dy1   (360 rows padded to 384)
-      GemmArgs a{};
-      a.W = p->w0t; a.ldw = NFP; a.XT = w.H1T; a.YT = w.GT; a.K = NH; a.ld = ld;
-      auto k_sgemm_bwd_l0 = k_sgemm<PRO_NONE, EPI_STORE>;
-      APAX_LAUNCH(k_sgemm_bwd_l0, dim3((unsigned)m_tiles, NFP / 128), dim3(256), 0, stream, a);
-    }
+    APAX_TRY(tc ? readout_tc(stream, p, w, geo, energy, head) : readout_simt(stream, p, w, geo, energy, head));
     APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(N, 128)), dim3(128), 0, stream, w);
     APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc);
     APAX_DISPATCH_LPA(pick_lpa(w.n_atoms), launch_force_gather, stream, w, forces + int64_t(head) * w.n_atoms * 3);
@@ -1010,6 +1123,28 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
   }
   APAX_TRY(upload(&p->scale, scale, S));
   APAX_TRY(upload(&p->shift, shift, S));
+  {  // exact (tf32 hi, lo) pairs of the (NTK-folded) weights for the tensor-core readout
+    auto split_upload = [&](float** dhi, float** dlo, int rows, int cols, auto get) -> int {
+      const size_t n = size_t(rows) * cols;
+      float* hi = new float[n];
+      float* lo = new float[n];
+      for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) split_tf32(get(r, c), hi[size_t(r) * cols + c], lo[size_t(r) * cols + c]);
+      int st = upload(dhi, hi, n);
+      if (!st) st = upload(dlo, lo, n);
+      delete[] hi;
+      delete[] lo;
+      return st;
+    };
+    const float f0 = wf(NF), f1 = wf(NH);
+    APAX_TRY(split_upload(&p->w0_hi, &p->w0_lo, NF, NH, [&](int k, int n) { return f0 * w0[size_t(k) * NH + n]; }));
+    APAX_TRY(split_upload(&p->w1_hi, &p->w1_lo, NH, NH, [&](int k, int n) { return f1 * w1[size_t(k) * NH + n]; }));
+    APAX_TRY(split_upload(&p->w1t_hi, &p->w1t_lo, NH, NH, [&](int n, int k) { return f1 * w1[size_t(k) * NH + n]; }));
+    APAX_TRY(split_upload(&p->w0t_hi, &p->w0t_lo, NH, NFP,
+                          [&](int n, int k) { return k < NF ? f0 * w0[size_t(k) * NH + n] : 0.0f; }));
+    APAX_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&p->tc_err), sizeof(int32_t)));
+    APAX_CUDA_TRY(cudaMemset(p->tc_err, 0, sizeof(int32_t)));
+  }
   *out = p;
   return APAX_OK;
 }
@@ -1018,7 +1153,17 @@ extern "C" void apax_gm_params_destroy(apax_gm_params* p) {
   if (!p) return;
   cudaFree(p->emb); cudaFree(p->w0); cudaFree(p->w0t); cudaFree(p->b0); cudaFree(p->w1); cudaFree(p->w1t);
   cudaFree(p->b1); cudaFree(p->w2); cudaFree(p->b2); cudaFree(p->scale); cudaFree(p->shift);
+  cudaFree(p->w0_hi); cudaFree(p->w0_lo); cudaFree(p->w1_hi); cudaFree(p->w1_lo); cudaFree(p->w1t_hi);
+  cudaFree(p->w1t_lo); cudaFree(p->w0t_hi); cudaFree(p->w0t_lo); cudaFree(p->tc_err);
   delete p;
+}
+
+extern "C" int apax_gm_params_status(const apax_gm_params* p) {
+  // synchronising query of the tensor-core pipeline's time-out flag (0 = healthy)
+  if (!p) return APAX_ERR_INVALID_ARG;
+  int32_t flag = 0;
+  APAX_CUDA_TRY(cudaMemcpy(&flag, p->tc_err, sizeof(flag), cudaMemcpyDeviceToHost));
+  return flag == 0 ? APAX_OK : APAX_ERR_CUDA;
 }
 
 extern "C" size_t apax_gm_workspace_bytes(int64_t n_atoms, int64_t n_pairs, int32_t n_out) {

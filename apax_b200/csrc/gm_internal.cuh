@@ -28,6 +28,12 @@ struct apax_gm_params_impl {
   float* b2;     // [n_out]
   double* scale; // [S]
   double* shift; // [S]
+  // exact tf32 (hi, lo) pairs of the same weights for the tensor-core readout (tc_gemm.cuh)
+  float *w0_hi, *w0_lo;    // [360][256]
+  float *w1_hi, *w1_lo;    // [256][256]
+  float *w1t_hi, *w1t_lo;  // [256][256]
+  float *w0t_hi, *w0t_lo;  // [256][384]
+  int32_t* tc_err;         // [1] set by the tensor-core pipeline on a barrier time-out
 };
 
 // Everything the compute kernels need, carved out of the caller's workspace.  All feature-major
@@ -65,6 +71,10 @@ struct GmWorkspace {
   float* D1T;  // [256][ld] act'(y1)
   float* H2T;  // [256][ld]
   float* D2T;  // [256][ld]
+  // residual (lo) parts of GT / H1T / H2T when the readout runs on the tensor cores (3xTF32)
+  float* GLT;   // [384][ld]
+  float* H1LT;  // [256][ld]
+  float* H2LT;  // [256][ld]
   float* ebar;     // [ld]   dE/dh per atom (scale*mask) in fp32
   double* Eatom;   // [n_out][ld]
   double* partial; // [n_out][256]

@@ -46,19 +46,24 @@ struct TcOperand {   // one feature-major / row-major fp32 matrix [rows][cols], 
 int tc_gemm(cudaStream_t stream, const TcOperand& act, const TcOperand& wgt, int64_t n_atoms, const TcEpilogue& epi,
             int32_t* err_flag);
 
-// round-to-nearest tf32 split of an fp32 value (device + host)
-__host__ __device__ inline void split_tf32(float x, float& hi, float& lo) {
+// tf32 split of an fp32 value (device + host): hi = rna_tf32(x), lo = rna_tf32(x - hi).  Both parts have
+// zero low mantissa bits, so whatever the tensor core does with bits below tf32 precision is irrelevant;
+// x - (hi + lo) is at most 2^-22 |x|.
+__host__ __device__ inline float round_tf32(float x) {
 #ifdef __CUDA_ARCH__
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  hi = __uint_as_float(u & 0xffffe000u);
+  return __uint_as_float(u & 0xffffe000u);
 #else
   union { float f; uint32_t u; } v;
   v.f = x;
-  v.u = (v.u + 0x1000u) & 0xffffe000u;  // round half away (rna), finite inputs
-  hi = v.f;
+  v.u = (v.u + 0x1000u) & 0xffffe000u;  // round half away from zero (rna), finite inputs
+  return v.f;
 #endif
-  lo = x - hi;
+}
+__host__ __device__ inline void split_tf32(float x, float& hi, float& lo) {
+  hi = round_tf32(x);
+  lo = round_tf32(x - hi);
 }
 
 }  // namespace apax

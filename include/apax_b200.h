@@ -80,6 +80,9 @@ int apax_gm_params_create(const apax_gm_config* cfg, const float* emb_host, cons
                           const float* w2_host, const float* b2_host, const double* scale_host,
                           const double* shift_host, apax_gm_params** out);
 void apax_gm_params_destroy(apax_gm_params* p);
+/* Synchronising health query: 0, or APAX_ERR_CUDA if a tensor-core pipeline barrier ever timed out
+ * while these parameters were in use (results of that call are then invalid). */
+int apax_gm_params_status(const apax_gm_params* p);
 
 /* ------------------------------------------------------------------------------------------------
  * Energy + forces given a neighbour list.  Replaces EnergyDerivativeModel.apply

@@ -8,9 +8,13 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _rna(x: torch.Tensor):
+    return ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def _split(x: torch.Tensor):
-    hi = ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
-    return hi, x - hi
+    hi = _rna(x)
+    return hi, _rna(x - hi)
 
 
 @pytest.mark.parametrize("k,nc,n_atoms", [(16, 256, 128), (256, 256, 1000), (360, 256, 4096), (256, 384, 777)])
@@ -24,7 +28,7 @@ def test_tc_gemm_matches_fp64(k, nc, n_atoms):
     wgt = torch.randn(k, nc, device=dev, dtype=torch.float32) / np.sqrt(k)
     a_hi, a_lo = _split(act)
     w_hi, w_lo = _split(wgt)
-    assert torch.equal(a_hi + a_lo, act) and torch.equal(w_hi + w_lo, wgt)
+    assert (a_hi + a_lo - act).abs().max() <= 2.0 ** -21 * act.abs().max()
     out = torch.zeros(nc, ld, device=dev, dtype=torch.float32)
     err = torch.zeros(1, device=dev, dtype=torch.int32)
     rc = rt.lib().apax_tc_gemm_test(rt._stream_ptr(), rt._ptr(a_hi), rt._ptr(a_lo), k, ld, n_atoms, rt._ptr(w_hi), rt._ptr(w_lo),
@@ -38,4 +42,4 @@ def test_tc_gemm_matches_fp64(k, nc, n_atoms):
     scale = (wgt.double().abs().T @ act.double().abs())[:, :n_tiles]
     rel = ((got - ref[:, :n_tiles]).abs() / scale).max().item()
     print(f"k={k} nc={nc}: max error relative to sum|a||b| = {rel:.2e}")
-    assert rel < 3e-7                               # fp32-accurate (single-pass tf32 would be ~1e-3)
+    assert rel < 4e-7                               # fp32-class accuracy (single-pass tf32 would be ~5e-4)
