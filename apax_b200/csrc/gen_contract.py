@@ -216,7 +216,9 @@ def emit_sum(terms):
 
 def emit_forward(blocks):
     lines = []
-    for b in blocks:
+    for bi, b in enumerate(blocks):
+        if bi % 4 == 0:
+            lines.append("  GM_CONTRACT_SYNC();")
         lines.append("  {")
         for target, terms in b.stmts:
             if target[0] == "t":
@@ -241,6 +243,8 @@ def emit_backward(blocks, prefetch=2):
     for bi, b in enumerate(blocks):
         if bi + prefetch < len(blocks):
             lines.extend(loads(blocks[bi + prefetch]))
+        if bi % 2 == 0:
+            lines.append("  GM_CONTRACT_SYNC();")
         lines.append("  {")
         temps = [t for t, _ in b.stmts if t[0] == "t"]
         for target, terms in b.stmts:
@@ -334,6 +338,12 @@ def main(out_path):
     src.append(f"#define GM_N_FEATURES {n_feat}")
     src.append("#define GM_N_PACKED 100")
     src.append("// m = packed moments of one atom, a = packed adjoint accumulators (caller zero-initialises).")
+    src.append("// The program is ~100-200 KB of straight-line code, far beyond the instruction cache: GM_CONTRACT_SYNC()")
+    src.append("// (a block barrier, defined by the including kernel) keeps the warps of a CTA walking it in step so")
+    src.append("// that one instruction fetch serves all of them.")
+    src.append("#ifndef GM_CONTRACT_SYNC")
+    src.append("#define GM_CONTRACT_SYNC() __syncthreads()")
+    src.append("#endif")
     src.append("template <class Store>")
     src.append("__device__ __forceinline__ void gm_contract_forward(const float (&m)[GM_N_PACKED], Store store) {")
     src.extend(emit_forward(blocks))

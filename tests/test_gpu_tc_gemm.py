@@ -42,4 +42,6 @@ def test_tc_gemm_matches_fp64(k, nc, n_atoms):
     scale = (wgt.double().abs().T @ act.double().abs())[:, :n_tiles]
     rel = ((got - ref[:, :n_tiles]).abs() / scale).max().item()
     print(f"k={k} nc={nc}: max error relative to sum|a||b| = {rel:.2e}")
-    assert rel < 4e-7                               # fp32-class accuracy (single-pass tf32 would be ~5e-4)
+    # single-pass tf32 would be ~5e-4; 3xTF32 removes the operand rounding, what remains is the tensor core's
+    # truncating fp32 accumulator (error grows with the number of accumulation steps, k/8 * 3)
+    assert rel < 2e-6
