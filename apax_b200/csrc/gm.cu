@@ -636,33 +636,47 @@ __global__ void __launch_bounds__(256) k_features_to_rowmajor(const float* __res
 // ================================================================================================
 constexpr float kSwish = 1.6765324703310907f;  // apax/layers/activation.py:8
 
-enum { PRO_NONE = 0, PRO_HEAD = 1 };
 enum { EPI_STORE = 0, EPI_ACT = 1, EPI_MULD = 2 };
 
 struct GemmArgs {
   const float* W;     // [K][ldw]
   int ldw;
   const float* XT;    // [K][ld]
-  float* YT;          // [NC][ld]   (EPI_ACT: H)
-  float* Y2T;         // EPI_ACT: act'(y) ; EPI_MULD: multiplier D (read)
-  const float* bias;  // EPI_ACT
-  const float* ebar;  // PRO_HEAD: [ld]
-  const float* wcol;  // PRO_HEAD: w2[k*wstride]
-  int wstride;
-  int K;
+  float* YT;          // [NC][ld]   (EPI_ACT: swish(y))
+  float* Y2T;         // EPI_ACT: swish'(y) written ; EPI_MULD: multiplier D[n][m] read
+  const float* bias;  // EPI_ACT: [NC]
+  const float* ebar;  // EPI_MULD: per-atom factor [ld]
+  int K;              // multiple of 8
   int64_t ld;
 };
 
-template <int PRO, int EPI>
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(smem))), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int kGemmStages = 4;  // 4 x 8 KB: global->shared copies run three k-tiles ahead of the FMAs
+
+// 128(n) x 128(m) x 8(k) tiles, 256 threads, 8x8 register micro-tile.  Warps tile the block 4(n) x 2(m) and
+// lanes tile a warp 4(n) x 8(m), so every fragment load is one shared-memory wavefront; operands arrive by
+// cp.async (LDGSTS) through a 4-stage ring, i.e. no global-load latency on the FMA critical path.
+template <int EPI>
 __global__ void __launch_bounds__(256, 2) k_sgemm(GemmArgs g) {
-  __shared__ __align__(16) float Ws[2][8][128];
-  __shared__ __align__(16) float Xs[2][8][128];
+  __shared__ __align__(16) float Ws[kGemmStages][8][128];
+  __shared__ __align__(16) float Xs[kGemmStages][8][128];
   const int tid = threadIdx.x;
   const int64_t m0 = int64_t(blockIdx.x) * 128;
   const int n0 = blockIdx.y * 128;
   const int lrow = tid >> 5;         // 0..7
   const int lcol = (tid & 31) * 4;   // 0..124
-  const int tm = tid & 15, tn = tid >> 4;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nb = (warp >> 1) * 32 + (lane >> 3) * 4;  // first n of this thread (second group: +16)
+  const int mb = (warp & 1) * 64 + (lane & 7) * 4;    // first m of this thread (second group: +32)
 
   float acc[8][8];
 #pragma unroll
@@ -670,38 +684,33 @@ __global__ void __launch_bounds__(256, 2) k_sgemm(GemmArgs g) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
 
-  float4 eb4 = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (PRO == PRO_HEAD) eb4 = *reinterpret_cast<const float4*>(g.ebar + m0 + lcol);
-
-  auto load_w = [&](int k0) {
-    return *reinterpret_cast<const float4*>(g.W + int64_t(k0 + lrow) * g.ldw + n0 + lcol);
+  const float* wsrc = g.W + int64_t(lrow) * g.ldw + n0 + lcol;
+  const float* xsrc = g.XT + int64_t(lrow) * g.ld + m0 + lcol;
+  auto issue = [&](int stage, int kt) {
+    cp_async16(&Ws[stage][lrow][lcol], wsrc + int64_t(kt) * 8 * g.ldw);
+    cp_async16(&Xs[stage][lrow][lcol], xsrc + int64_t(kt) * 8 * g.ld);
   };
-  auto load_x = [&](int k0) {
-    float4 v = *reinterpret_cast<const float4*>(g.XT + int64_t(k0 + lrow) * g.ld + m0 + lcol);
-    if (PRO == PRO_HEAD) {
-      const float wk = g.wcol[int64_t(k0 + lrow) * g.wstride];
-      v.x *= eb4.x * wk; v.y *= eb4.y * wk; v.z *= eb4.z * wk; v.w *= eb4.w * wk;
-    }
-    return v;
-  };
-
-  float4 wreg = load_w(0), xreg = load_x(0);
-  *reinterpret_cast<float4*>(&Ws[0][lrow][lcol]) = wreg;
-  *reinterpret_cast<float4*>(&Xs[0][lrow][lcol]) = xreg;
-  __syncthreads();
   const int nk = g.K / 8;
+#pragma unroll
+  for (int s = 0; s < kGemmStages - 1; ++s) {
+    if (s < nk) issue(s, s);
+    cp_async_commit();
+  }
   for (int kt = 0; kt < nk; ++kt) {
-    const int cur = kt & 1;
-    if (kt + 1 < nk) {
-      wreg = load_w((kt + 1) * 8);
-      xreg = load_x((kt + 1) * 8);
+    cp_async_wait<kGemmStages - 2>();
+    __syncthreads();  // tile kt has landed for everyone; everyone is done reading the stage refilled below
+    {
+      const int nxt = kt + kGemmStages - 1;
+      if (nxt < nk) issue(nxt % kGemmStages, nxt);
+      cp_async_commit();
     }
+    const int cur = kt % kGemmStages;
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
-      const float4 wa = *reinterpret_cast<const float4*>(&Ws[cur][kk][tn * 4]);
-      const float4 wb = *reinterpret_cast<const float4*>(&Ws[cur][kk][64 + tn * 4]);
-      const float4 xa = *reinterpret_cast<const float4*>(&Xs[cur][kk][tm * 4]);
-      const float4 xb = *reinterpret_cast<const float4*>(&Xs[cur][kk][64 + tm * 4]);
+      const float4 wa = *reinterpret_cast<const float4*>(&Ws[cur][kk][nb]);
+      const float4 wb = *reinterpret_cast<const float4*>(&Ws[cur][kk][nb + 16]);
+      const float4 xa = *reinterpret_cast<const float4*>(&Xs[cur][kk][mb]);
+      const float4 xb = *reinterpret_cast<const float4*>(&Xs[cur][kk][mb + 32]);
       const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
       const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
@@ -709,19 +718,20 @@ __global__ void __launch_bounds__(256, 2) k_sgemm(GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
     }
-    if (kt + 1 < nk) {
-      *reinterpret_cast<float4*>(&Ws[cur ^ 1][lrow][lcol]) = wreg;
-      *reinterpret_cast<float4*>(&Xs[cur ^ 1][lrow][lcol]) = xreg;
-    }
-    __syncthreads();
   }
+  cp_async_wait<0>();
 
+  float4 eb[2] = {make_float4(1.f, 1.f, 1.f, 1.f), make_float4(1.f, 1.f, 1.f, 1.f)};
+  if (EPI == EPI_MULD) {
+    eb[0] = *reinterpret_cast<const float4*>(g.ebar + m0 + mb);
+    eb[1] = *reinterpret_cast<const float4*>(g.ebar + m0 + mb + 32);
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int n = n0 + (i < 4 ? tn * 4 + i : 64 + tn * 4 + (i - 4));
+    const int n = n0 + nb + (i < 4 ? i : 16 + (i - 4));
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int64_t m = m0 + (h == 0 ? tm * 4 : 64 + tm * 4);
+      const int64_t m = m0 + mb + 32 * h;
       float4 v = make_float4(acc[i][4 * h + 0], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
       const int64_t o = int64_t(n) * g.ld + m;
       if (EPI == EPI_ACT) {
@@ -731,14 +741,15 @@ __global__ void __launch_bounds__(256, 2) k_sgemm(GemmArgs g) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float sg = 1.0f / (1.0f + expf(-y[q]));
-          hh[q] = kSwish * y[q] * sg;                       // variance_preserving_swish
+          hh[q] = kSwish * y[q] * sg;                        // variance_preserving_swish
           dd[q] = kSwish * sg * (1.0f + y[q] * (1.0f - sg)); // its derivative
         }
         *reinterpret_cast<float4*>(g.YT + o) = make_float4(hh[0], hh[1], hh[2], hh[3]);
         *reinterpret_cast<float4*>(g.Y2T + o) = make_float4(dd[0], dd[1], dd[2], dd[3]);
       } else if (EPI == EPI_MULD) {
         const float4 d = *reinterpret_cast<const float4*>(g.Y2T + o);
-        *reinterpret_cast<float4*>(g.YT + o) = make_float4(v.x * d.x, v.y * d.y, v.z * d.z, v.w * d.w);
+        *reinterpret_cast<float4*>(g.YT + o) =
+            make_float4(v.x * d.x * eb[h].x, v.y * d.y * eb[h].y, v.z * d.z * eb[h].z, v.w * d.w * eb[h].w);
       } else {
         *reinterpret_cast<float4*>(g.YT + o) = v;
       }
@@ -950,28 +961,29 @@ static int readout_simt(cudaStream_t stream, const apax_gm_params_impl* p, const
     {  // layer 0: 360 -> 256
       GemmArgs a{};
       a.W = p->w0; a.ldw = NH; a.XT = w.GT; a.YT = w.H1T; a.Y2T = w.D1T; a.bias = p->b0; a.K = NF; a.ld = ld;
-      auto k_sgemm_fwd_l0 = k_sgemm<PRO_NONE, EPI_ACT>;
+      auto k_sgemm_fwd_l0 = k_sgemm<EPI_ACT>;
       APAX_LAUNCH(k_sgemm_fwd_l0, grid_h, dim3(256), 0, stream, a);
     }
     {  // layer 1: 256 -> 256
       GemmArgs a{};
       a.W = p->w1; a.ldw = NH; a.XT = w.H1T; a.YT = w.H2T; a.Y2T = w.D2T; a.bias = p->b1; a.K = NH; a.ld = ld;
-      auto k_sgemm_fwd_l1 = k_sgemm<PRO_NONE, EPI_ACT>;
+      auto k_sgemm_fwd_l1 = k_sgemm<EPI_ACT>;
       APAX_LAUNCH(k_sgemm_fwd_l1, grid_h, dim3(256), 0, stream, a);
     }
     return readout_head_and_energy(stream, p, w, geo, nullptr, energy);
   }
-  {  // dE/dy1 = (W1 . dE/dy2) * act'(y1),  dE/dy2 = ebar * w2[:,head] * act'(y2) applied on load
+  {  // dE/dy1[n][m] = swish'(y1)[n][m] * ebar[m] * sum_k (W1[n][k] w2[k][head]) swish'(y2)[k][m]: the head's output
+     // weights are folded into the transposed layer-1 weights once per parameter set (w1t_head)
     GemmArgs a{};
-    a.W = p->w1t; a.ldw = NH; a.XT = w.D2T; a.YT = w.H1T; a.Y2T = w.D1T; a.K = NH; a.ld = ld;
-    a.ebar = w.ebar; a.wcol = p->w2 + head; a.wstride = n_out;
-    auto k_sgemm_bwd_l1 = k_sgemm<PRO_HEAD, EPI_MULD>;
+    a.W = p->w1t_head + size_t(head) * NH * NH; a.ldw = NH; a.XT = w.D2T; a.YT = w.H1T; a.Y2T = w.D1T; a.K = NH; a.ld = ld;
+    a.ebar = w.ebar;
+    auto k_sgemm_bwd_l1 = k_sgemm<EPI_MULD>;
     APAX_LAUNCH(k_sgemm_bwd_l1, grid_h, dim3(256), 0, stream, a);
   }
   {  // dE/dg = W0 . dE/dy1   (360 rows padded to 384)
     GemmArgs a{};
     a.W = p->w0t; a.ldw = NFP; a.XT = w.H1T; a.YT = w.GT; a.K = NH; a.ld = ld;
-    auto k_sgemm_bwd_l0 = k_sgemm<PRO_NONE, EPI_STORE>;
+    auto k_sgemm_bwd_l0 = k_sgemm<EPI_STORE>;
     APAX_LAUNCH(k_sgemm_bwd_l0, dim3((unsigned)m_tiles, NFP / 128), dim3(256), 0, stream, a);
   }
   return APAX_OK;
@@ -1123,6 +1135,14 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
     float* h = new float[size_t(NH) * n_out];
     for (size_t i = 0; i < size_t(NH) * n_out; ++i) h[i] = wf(NH) * w2[i];
     int st = upload(&p->w2, h, size_t(NH) * n_out);
+    // w1t_head[head][k][n] = W1[n][k] * w2[k][head]  (reduction index k = layer-1 output feature)
+    float* hh = new float[size_t(n_out) * NH * NH];
+    for (int hd = 0; hd < n_out; ++hd)
+      for (int k = 0; k < NH; ++k)
+        for (int n = 0; n < NH; ++n)
+          hh[(size_t(hd) * NH + k) * NH + n] = (wf(NH) * w1[size_t(n) * NH + k]) * h[size_t(k) * n_out + hd];
+    if (!st) st = upload(&p->w1t_head, hh, size_t(n_out) * NH * NH);
+    delete[] hh;
     delete[] h;
     if (st) return st;
   }
@@ -1166,6 +1186,7 @@ extern "C" void apax_gm_params_destroy(apax_gm_params* p) {
   if (!p) return;
   cudaFree(p->emb); cudaFree(p->w0); cudaFree(p->w0t); cudaFree(p->b0); cudaFree(p->w1); cudaFree(p->w1t);
   cudaFree(p->b1); cudaFree(p->w2); cudaFree(p->b2); cudaFree(p->scale); cudaFree(p->shift);
+  cudaFree(p->w1t_head);
   cudaFree(p->w0_hi); cudaFree(p->w0_lo); cudaFree(p->w1_hi); cudaFree(p->w1_lo); cudaFree(p->w1t_hi);
   cudaFree(p->w1t_lo); cudaFree(p->w0t_hi); cudaFree(p->w0t_lo); cudaFree(p->tc_err);
   delete p;

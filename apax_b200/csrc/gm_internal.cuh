@@ -23,6 +23,7 @@ struct apax_gm_params_impl {
   float* b0;     // [256]
   float* w1;     // [256][256]
   float* w1t;    // [256][256]
+  float* w1t_head;  // [n_out][256][256]  W1^T with the head's output weights folded in (backward GEMM)
   float* b1;     // [256]
   float* w2;     // [256][n_out]
   float* b2;     // [n_out]
