@@ -42,7 +42,9 @@ def test_builder_models_and_neighbor_provider(golden):
     out = model.apply(params, d["frac"], d["Z"], nbrs, box, np.zeros((nbrs.idx.shape[1], 3)))
     assert abs(float(out["energy"]) - d["energy"]) <= 1e-6 * abs(d["energy"])
     f = out["forces"].cpu().numpy()
-    assert np.all(np.abs(f - d["forces"]) <= 1e-5 * np.abs(d["forces"]) + 1e-6)
+    from oracle import gmnn_oracle as go
+    ref64 = go.energy_forces(params, d["frac"], d["Z"], d["idx"], box, None, "minimage", go.fp64_config())
+    assert_force_parity(f, d["forces"], ref64["forces"], where="builder model, golden min-image")
     e_only, props = model.energy_model.apply(params, d["frac"], d["Z"], nbrs, box, None)
     assert props == {} and abs(float(e_only) - float(out["energy"])) <= 1e-9 * abs(d["energy"])
 
