@@ -830,6 +830,18 @@ __global__ void __launch_bounds__(256) k_energy_partial(const double* __restrict
   if (threadIdx.x == 0) partial[head * 256 + blockIdx.x] = sm[0];
 }
 
+// per-structure energies of a batch: one warp per (structure, head), fixed summation order
+__global__ void __launch_bounds__(32) k_energy_segments(const double* __restrict__ Eatom, int64_t ld,
+                                                        const int32_t* __restrict__ seg_ptr, int n_out,
+                                                        double* __restrict__ energy) {
+  const int b = blockIdx.x, head = blockIdx.y;
+  double s = 0.0;
+  for (int i = seg_ptr[b] + threadIdx.x; i < seg_ptr[b + 1]; i += 32) s += Eatom[int64_t(head) * ld + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) energy[int64_t(b) * n_out + head] = s;
+}
+
 __global__ void k_energy_final(const double* __restrict__ partial, int n_blocks, double* __restrict__ energy) {
   const int head = blockIdx.x;
   if (threadIdx.x == 0) {
@@ -943,6 +955,10 @@ static int readout_head_and_energy(cudaStream_t stream, const apax_gm_params_imp
   } else {
     APAX_LAUNCH(k_head<MAX_OUT>, dim3((unsigned)m_tiles), dim3(128), 0, stream, w.H2T, h2_lo, ld, N, p->w2, p->b2,
                 n_out, geo.Z, p->cfg.n_species, p->scale, p->shift, p->cfg.mask_atoms, w.Eatom, w.ebar);
+  }
+  if (w.n_seg > 0) {
+    APAX_LAUNCH(k_energy_segments, dim3((unsigned)w.n_seg, n_out), dim3(32), 0, stream, w.Eatom, ld, w.seg_ptr, n_out, energy);
+    return APAX_OK;
   }
   const int n_blk = int(N < 256 * 64 ? 1 : (N / (256 * 64) > 256 ? 256 : N / (256 * 64)));
   APAX_LAUNCH(k_energy_partial, dim3(n_blk, n_out), dim3(256), 0, stream, w.Eatom, ld, N, w.partial);
@@ -1177,6 +1193,8 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
                           [&](int n, int k) { return k < NF ? f0 * w0[size_t(k) * NH + n] : 0.0f; }));
     APAX_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&p->tc_err), sizeof(int32_t)));
     APAX_CUDA_TRY(cudaMemset(p->tc_err, 0, sizeof(int32_t)));
+    const double eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    APAX_TRY(upload(&p->eye, eye, 9));
   }
   *out = p;
   return APAX_OK;
@@ -1187,6 +1205,7 @@ extern "C" void apax_gm_params_destroy(apax_gm_params* p) {
   cudaFree(p->emb); cudaFree(p->w0); cudaFree(p->w0t); cudaFree(p->b0); cudaFree(p->w1); cudaFree(p->w1t);
   cudaFree(p->b1); cudaFree(p->w2); cudaFree(p->b2); cudaFree(p->scale); cudaFree(p->shift);
   cudaFree(p->w1t_head);
+  cudaFree(p->eye);
   cudaFree(p->w0_hi); cudaFree(p->w0_lo); cudaFree(p->w1_hi); cudaFree(p->w1_lo); cudaFree(p->w1t_hi);
   cudaFree(p->w1t_lo); cudaFree(p->w0t_hi); cudaFree(p->w0t_lo); cudaFree(p->tc_err);
   delete p;
@@ -1256,6 +1275,21 @@ extern "C" int apax_gm_energy_forces(apax_stream_t stream, const apax_gm_params*
   APAX_TRY(apax_gm_prepare(stream, params, Z, idx, n_atoms, n_pairs, workspace, workspace_bytes));
   return apax_gm_compute(stream, params, R, Z, box, offsets, n_atoms, n_pairs, disp_mode, energy, forces, workspace,
                          workspace_bytes);
+}
+
+extern "C" int apax_gm_energy_forces_batched(apax_stream_t stream, const apax_gm_params* params, const double* R,
+                                             const int32_t* Z, const int32_t* idx, const double* offsets,
+                                             const int32_t* struct_ptr, int64_t n_structs, int64_t n_atoms,
+                                             int64_t n_pairs, double* energy, double* forces, void* workspace,
+                                             size_t workspace_bytes) {
+  GmWorkspace w;
+  APAX_TRY(get_ws(params, n_atoms, n_pairs, workspace, workspace_bytes, &w));
+  if (!R || !Z || !energy || !struct_ptr || n_structs < 1 || (n_pairs > 0 && !idx)) return APAX_ERR_INVALID_ARG;
+  APAX_TRY(gm_prepare_impl(stream, params, w, Z, idx));
+  w.seg_ptr = struct_ptr;
+  w.n_seg = n_structs;
+  const PairGeom geo = make_geom(params, R, Z, params->eye, offsets, APAX_DISP_OFFSETS);
+  return gm_compute_impl(stream, params, w, geo, energy, forces);
 }
 
 extern "C" int apax_gm_descriptor(apax_stream_t stream, const apax_gm_params* params, const double* R,

@@ -35,6 +35,7 @@ struct apax_gm_params_impl {
   float *w1t_hi, *w1t_lo;  // [256][256]
   float *w0t_hi, *w0t_lo;  // [256][384]
   int32_t* tc_err;         // [1] set by the tensor-core pipeline on a barrier time-out
+  double* eye;             // [3][3] identity (displacement box of Cartesian batched evaluation)
 };
 
 // Everything the compute kernels need, carved out of the caller's workspace.  All feature-major
@@ -42,6 +43,8 @@ struct apax_gm_params_impl {
 struct GmWorkspace {
   int64_t n_atoms, n_pairs, ld;
   int64_t n_central;  // atoms [0, n_central) are evaluated as centrals; the rest only act as neighbours
+  const int32_t* seg_ptr;  // optional [n_seg+1]: atom ranges of independent structures (batched evaluation)
+  int64_t n_seg;           // 0: one structure, energy[n_out]; else energy[n_seg][n_out]
   int32_t n_out;
   // list (CSR by central atom) + transpose
   int32_t* rowptr;   // [N+1]

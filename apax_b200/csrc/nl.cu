@@ -439,6 +439,165 @@ int nl_build_images_csr(cudaStream_t stream, const double* pos, const double* ce
                             overflow);
 }
 
+// ================================================================================================
+// Batched image lists: many small independent periodic cells (BASELINE config 5: 4096 x 128 atoms,
+// apax/md/ase_calc.py:395-481 evaluates them through vesin + padding).  Atoms of all structures are
+// concatenated; every structure is scanned by brute force over its own atoms and image shifts with the
+// same fp64 predicate as the single-structure path.  Rows (central atoms) come out in a fixed
+// enumeration order, so no sort is needed and the CSR can be consumed directly.
+// ================================================================================================
+struct StructGrid {
+  double C[9];     // rows = lattice vectors
+  double Cinv[9];  // frac = pos . Cinv  (row-vector convention)
+  int m[3];        // image range per axis
+  int pad;
+};
+
+namespace {
+
+__global__ void __launch_bounds__(128) k_nlb_setup(const double* __restrict__ pos, const double* __restrict__ cells,
+                                                   const int32_t* __restrict__ struct_ptr, int n_structs, double cutoff,
+                                                   StructGrid* __restrict__ grids, int32_t* __restrict__ sid,
+                                                   int32_t* __restrict__ wrap) {
+  const int b = blockIdx.x;
+  if (b >= n_structs) return;
+  __shared__ StructGrid g;
+  if (threadIdx.x == 0) {
+    double Bm[9], Binv[9];
+    for (int i = 0; i < 9; ++i) g.C[i] = cells[9 * int64_t(b) + i];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Bm[3 * i + j] = g.C[3 * j + i];  // columns = lattice vectors
+    invert3(Bm, Binv);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) g.Cinv[3 * j + i] = Binv[3 * i + j];  // frac_k = sum_j pos_j Cinv[j][k]
+    for (int k = 0; k < 3; ++k) {
+      const double nrm = sqrt(Binv[3 * k] * Binv[3 * k] + Binv[3 * k + 1] * Binv[3 * k + 1] + Binv[3 * k + 2] * Binv[3 * k + 2]);
+      int m = int(ceil(cutoff * nrm));  // cutoff / height
+      g.m[k] = m < 1 ? 1 : (m > 100 ? 100 : m);
+    }
+    g.pad = 0;
+    grids[b] = g;
+  }
+  __syncthreads();
+  for (int a = struct_ptr[b] + threadIdx.x; a < struct_ptr[b + 1]; a += blockDim.x) {
+    sid[a] = b;
+    const double x = pos[3 * int64_t(a)], y = pos[3 * int64_t(a) + 1], z = pos[3 * int64_t(a) + 2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) wrap[3 * int64_t(a) + k] = int(floor(x * g.Cinv[k] + y * g.Cinv[3 + k] + z * g.Cinv[6 + k]));
+  }
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_nlb_scan(const double* __restrict__ pos, int64_t N,
+                                                  const int32_t* __restrict__ struct_ptr,
+                                                  const StructGrid* __restrict__ grids, const int32_t* __restrict__ sid,
+                                                  const int32_t* __restrict__ wrap, double cutoff_sq, int64_t capacity,
+                                                  const int32_t* __restrict__ rowptr, int32_t* __restrict__ rowcnt,
+                                                  int32_t* __restrict__ nbr, int32_t* __restrict__ shift) {
+  const int64_t c = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  if (c >= N) return;
+  const int b = sid[c];
+  const StructGrid g = grids[b];
+  const double cx = pos[3 * c], cy = pos[3 * c + 1], cz = pos[3 * c + 2];
+  const int wc0 = wrap[3 * c], wc1 = wrap[3 * c + 1], wc2 = wrap[3 * c + 2];
+  int count = 0;
+  const int base = FILL ? rowptr[c] : 0;
+  for (int i = struct_ptr[b]; i < struct_ptr[b + 1]; ++i) {
+    const double ix = pos[3 * int64_t(i)], iy = pos[3 * int64_t(i) + 1], iz = pos[3 * int64_t(i) + 2];
+    const int d0 = wrap[3 * int64_t(i)] - wc0, d1 = wrap[3 * int64_t(i) + 1] - wc1, d2 = wrap[3 * int64_t(i) + 2] - wc2;
+    for (int n0 = -g.m[0]; n0 <= g.m[0]; ++n0)
+      for (int n1 = -g.m[1]; n1 <= g.m[1]; ++n1)
+        for (int n2 = -g.m[2]; n2 <= g.m[2]; ++n2) {
+          const int S0 = d0 - n0, S1 = d1 - n1, S2 = d2 - n2;  // D = r_c - r_i + S.cell
+          if (i == c && S0 == 0 && S1 == 0 && S2 == 0) continue;
+          if (S0 < -127 || S0 > 127 || S1 < -127 || S1 > 127 || S2 < -127 || S2 > 127) continue;
+          if (dist_sq_image(g.C, cx, cy, cz, ix, iy, iz, S0, S1, S2) < cutoff_sq) {
+            if (FILL) {
+              const int slot = base + count;
+              if (slot < capacity) {
+                nbr[slot] = i;
+                shift[slot] = pack_shift(S0, S1, S2);
+              }
+            }
+            ++count;
+          }
+        }
+  }
+  if (!FILL) rowcnt[c] = count;
+}
+
+__global__ void __launch_bounds__(256) k_nlb_emit(const int32_t* __restrict__ rowptr_c, int64_t N, int64_t capacity,
+                                                  const int32_t* __restrict__ nbr, const int32_t* __restrict__ shift,
+                                                  const StructGrid* __restrict__ grids, const int32_t* __restrict__ sid,
+                                                  int32_t* __restrict__ idx, int32_t* __restrict__ shifts_out,
+                                                  double* __restrict__ offsets_out) {
+  const int64_t wid = (int64_t(blockIdx.x) * 256 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid < N) {
+    const int b = rowptr_c[wid], e = rowptr_c[wid + 1];
+    const double* C = grids[sid[wid]].C;
+    for (int s = b + lane; s < e; s += 32) {
+      if (idx) { idx[s] = nbr[s]; idx[capacity + s] = int(wid); }
+      int s0, s1, s2;
+      unpack_shift(shift[s], s0, s1, s2);
+      if (shifts_out) { shifts_out[3 * int64_t(s)] = s0; shifts_out[3 * int64_t(s) + 1] = s1; shifts_out[3 * int64_t(s) + 2] = s2; }
+      if (offsets_out) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          offsets_out[3 * int64_t(s) + k] = __dadd_rn(__dadd_rn(__dmul_rn(double(s0), C[k]), __dmul_rn(double(s1), C[3 + k])),
+                                                      __dmul_rn(double(s2), C[6 + k]));
+      }
+    }
+  }
+  const int64_t n_valid = rowptr_c[N];
+  const int64_t tid = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t nthreads = int64_t(gridDim.x) * 256;
+  for (int64_t s = n_valid + tid; s < capacity; s += nthreads) {
+    if (idx) { idx[s] = 0; idx[capacity + s] = 0; }
+    if (shifts_out) { shifts_out[3 * s] = 0; shifts_out[3 * s + 1] = 0; shifts_out[3 * s + 2] = 0; }
+    if (offsets_out) { offsets_out[3 * s] = 0.0; offsets_out[3 * s + 1] = 0.0; offsets_out[3 * s + 2] = 0.0; }
+  }
+}
+
+}  // namespace
+
+size_t carve_nlb_workspace(void* base, int64_t n_atoms, int64_t capacity, int64_t n_structs, NlWorkspace* ws,
+                           StructGrid** grids) {
+  size_t off = carve_nl_workspace(base, n_atoms, capacity, ws);
+  Carver c(base);
+  c.off = off;
+  StructGrid* g = c.take<StructGrid>(n_structs > 0 ? n_structs : 1);
+  if (grids) *grids = g;
+  return c.bytes();
+}
+
+int nl_build_images_batched(cudaStream_t stream, const double* pos, const double* cells, const int32_t* struct_ptr,
+                            int64_t n_structs, int64_t N, double cutoff, int64_t capacity, const NlWorkspace& w,
+                            StructGrid* grids, int32_t* idx, int32_t* shifts, double* offsets, int32_t* n_found,
+                            uint8_t* overflow) {
+  APAX_LAUNCH(k_nlb_setup, dim3((unsigned)n_structs), dim3(128), 0, stream, pos, cells, struct_ptr, int(n_structs), cutoff,
+              grids, w.cell_of, w.wrap);
+  const dim3 grid((unsigned)cdiv(N, 128));
+  {
+    auto k_nlb_count = k_nlb_scan<false>;
+    APAX_LAUNCH(k_nlb_count, grid, dim3(128), 0, stream, pos, N, struct_ptr, grids, w.cell_of, w.wrap, cutoff * cutoff,
+                capacity, w.rowptr, w.rowcnt, w.nbr, w.shift);
+  }
+  APAX_TRY(exclusive_scan_i32(stream, w.rowcnt, w.rowptr, N, w.scan_scratch));
+  APAX_LAUNCH(k_nl_finish_count, dim3((unsigned)cdiv(N + 1, 256)), dim3(256), 0, stream, N, capacity, w.rowptr, w.rowptr_c,
+              n_found, overflow);
+  {
+    auto k_nlb_fill = k_nlb_scan<true>;
+    APAX_LAUNCH(k_nlb_fill, grid, dim3(128), 0, stream, pos, N, struct_ptr, grids, w.cell_of, w.wrap, cutoff * cutoff,
+                capacity, w.rowptr, w.rowcnt, w.nbr, w.shift);
+  }
+  if (idx || shifts || offsets) {
+    APAX_LAUNCH(k_nlb_emit, dim3((unsigned)cdiv(N * 32, 256)), dim3(256), 0, stream, w.rowptr_c, N, capacity, w.nbr,
+                w.shift, grids, w.cell_of, idx, shifts, offsets);
+  }
+  return APAX_OK;
+}
+
 }  // namespace apax
 
 using namespace apax;
@@ -474,6 +633,26 @@ extern "C" int apax_nl_build_images(apax_stream_t stream, const double* pos, con
   if (!pos || !cell || !idx || !n_found || !overflow) return APAX_ERR_INVALID_ARG;
   return nl_build_images_csr(stream, pos, cell, pbc, n_atoms, cutoff, capacity, w, idx, shifts, offsets, n_found,
                              overflow);
+}
+
+extern "C" size_t apax_nl_batched_workspace_bytes(int64_t n_atoms, int64_t capacity, int64_t n_structs) {
+  if (n_atoms < 0 || capacity < 0 || n_structs < 0) return 0;
+  return carve_nlb_workspace(nullptr, n_atoms, capacity, n_structs, nullptr, nullptr);
+}
+
+extern "C" int apax_nl_build_images_batched(apax_stream_t stream, const double* pos, const double* cells,
+                                            const int32_t* struct_ptr, int64_t n_structs, int64_t n_atoms,
+                                            double cutoff, int64_t capacity, int32_t* idx, int32_t* shifts,
+                                            double* offsets, int32_t* n_found, uint8_t* overflow, void* workspace,
+                                            size_t workspace_bytes) {
+  NlWorkspace w;
+  if (n_structs < 1) return APAX_ERR_INVALID_ARG;
+  APAX_TRY(nl_args_ok(n_atoms, capacity, cutoff, workspace, workspace_bytes, &w));
+  StructGrid* grids = nullptr;
+  if (carve_nlb_workspace(workspace, n_atoms, capacity, n_structs, &w, &grids) > workspace_bytes) return APAX_ERR_WORKSPACE;
+  if (!pos || !cells || !struct_ptr || !n_found || !overflow) return APAX_ERR_INVALID_ARG;
+  return nl_build_images_batched(stream, pos, cells, struct_ptr, n_structs, n_atoms, cutoff, capacity, w, grids, idx,
+                                 shifts, offsets, n_found, overflow);
 }
 
 extern "C" int apax_nl_needs_rebuild(apax_stream_t stream, const double* frac, const double* ref, const double* box,

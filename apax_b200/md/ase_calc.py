@@ -74,6 +74,46 @@ class ASECalculator:
                             "forces_ensemble": np.transpose(f, (1, 2, 0))}
         return self.results
 
+    def batch_eval(self, atoms_list, batch_size: int = 64, silent: bool = True):
+        """ASECalculator.batch_eval (apax/md/ase_calc.py:395-481): evaluate many structures, `batch_size` at a
+        time, each batch in ONE neighbour-list call and ONE energy+forces call (atoms concatenated instead of the
+        reference's padding to the largest structure).  Returns a list of result dicts."""
+        import torch
+
+        model = self.builder.build_energy_derivative_model(init_box=self._cell(atoms_list[0]).T)
+        em = getattr(model, "energy_model", model)
+        dp = device_params(self.params, em.statics())
+        r_max = float(dp.config["r_max"])
+        results = []
+        for s in range(0, len(atoms_list), batch_size):
+            chunk = atoms_list[s:s + batch_size]
+            pos = np.concatenate([np.asarray(a.positions, dtype=np.float64) for a in chunk])
+            num = np.concatenate([np.asarray(a.numbers, dtype=np.int32) for a in chunk])
+            cells = np.stack([self._cell(a) for a in chunk])
+            ptr = np.concatenate([[0], np.cumsum([len(a.numbers) for a in chunk])]).astype(np.int32)
+            cap = int(len(num) * self.max_pairs_per_atom)
+            while True:
+                idx, _, offsets, n_found, overflow = rt.nl_build_images_batched(pos, cells, ptr, r_max, cap)
+                nf = int(n_found.item())
+                if not int(overflow.item()):
+                    break
+                cap = int(nf * self.padding_factor) + 1024      # "neighbor list overflowed, extending."
+            e, f = rt.energy_forces_batched(dp, pos, num, idx[:, :nf].contiguous(), offsets[:nf].contiguous(), ptr)
+            torch.cuda.synchronize()
+            e, f = e.cpu().numpy(), f.cpu().numpy()
+            n_ens = dp.n_out
+            for b in range(len(chunk)):
+                fb = f[:, ptr[b]:ptr[b + 1]]
+                if n_ens == 1:
+                    results.append({"energy": float(e[b, 0]), "forces": fb[0]})
+                else:
+                    fm = fb.mean(axis=0)
+                    results.append({"energy": float(e[b].mean()), "energy_ensemble": e[b],
+                                    "energy_uncertainty": float(np.sqrt(((e[b] - e[b].mean()) ** 2).sum() / (n_ens - 1))),
+                                    "forces": fm, "forces_uncertainty": np.sqrt(((fb - fm) ** 2).sum(axis=0) / (n_ens - 1)),
+                                    "forces_ensemble": np.transpose(fb, (1, 2, 0))})
+        return results
+
     def get_potential_energy(self, atoms):
         return self.calculate(atoms)["energy"]
 

@@ -246,6 +246,46 @@ def nl_build_images(positions, cell, cutoff: float, capacity: int, pbc: bool = T
     return idx, shifts, offsets, n_found, overflow
 
 
+def nl_build_images_batched(positions, cells, struct_ptr, cutoff: float, capacity: int):
+    """vesin-style lists for a batch of independent periodic cells (atoms concatenated, global indices)."""
+    dev = _require_cuda()
+    pos = to_device(positions, torch.float64)
+    cells = to_device(cells, torch.float64)
+    sp = to_device(struct_ptr, torch.int32)
+    n, b = int(pos.shape[0]), int(sp.shape[0]) - 1
+    idx = torch.empty((2, capacity), dtype=torch.int32, device=dev)
+    shifts = torch.empty((capacity, 3), dtype=torch.int32, device=dev)
+    offsets = torch.empty((capacity, 3), dtype=torch.float64, device=dev)
+    n_found = torch.zeros(1, dtype=torch.int32, device=dev)
+    overflow = torch.zeros(1, dtype=torch.uint8, device=dev)
+    nbytes = lib().apax_nl_batched_workspace_bytes(n, capacity, b)
+    buf = _nl_ws.get(nbytes)
+    check(lib().apax_nl_build_images_batched(_stream_ptr(), _ptr(pos), _ptr(cells), _ptr(sp), b, n, float(cutoff), capacity,
+                                             _ptr(idx), _ptr(shifts), _ptr(offsets), _ptr(n_found), _ptr(overflow),
+                                             C.c_void_p(Workspace.aligned_ptr(buf)), C.c_size_t(nbytes)),
+          "apax_nl_build_images_batched")
+    return idx, shifts, offsets, n_found, overflow
+
+
+def energy_forces_batched(params: DeviceParams, R, Z, idx, offsets, struct_ptr, forces: bool = True,
+                          workspace: Optional[Workspace] = None):
+    """Many independent structures in one call: energy [B, n_out], forces [n_out, N_total, 3]."""
+    dev = _require_cuda()
+    R = to_device(R, torch.float64)
+    Z = to_device(Z, torch.int32)
+    idx = to_device(idx, torch.int32)
+    sp = to_device(struct_ptr, torch.int32)
+    off_d = None if offsets is None else to_device(offsets, torch.float64)
+    n_atoms, n_pairs, b = int(R.shape[0]), int(idx.shape[1]), int(sp.shape[0]) - 1
+    energy = torch.empty((b, params.n_out), dtype=torch.float64, device=dev)
+    F = torch.empty((params.n_out, n_atoms, 3), dtype=torch.float64, device=dev) if forces else None
+    wp, wb = _gm_ws(n_atoms, n_pairs, params.n_out, workspace)
+    check(lib().apax_gm_energy_forces_batched(_stream_ptr(), params.handle, _ptr(R), _ptr(Z), _ptr(idx), _ptr(off_d), _ptr(sp),
+                                              b, n_atoms, n_pairs, _ptr(energy), _ptr(F), wp, wb),
+          "apax_gm_energy_forces_batched")
+    return energy, F
+
+
 def nl_needs_rebuild(frac, ref, box, dr_threshold: float) -> torch.Tensor:
     dev = _require_cuda()
     frac = to_device(frac, torch.float64)

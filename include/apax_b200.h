@@ -116,6 +116,17 @@ int apax_gm_compute(apax_stream_t stream, const apax_gm_params* params, const do
                     int64_t n_pairs, int32_t disp_mode, double* energy, double* forces,
                     void* workspace, size_t workspace_bytes);
 
+/* Batched evaluation of many independent structures in one call.  Replaces the vmapped model of
+ * ASECalculator.batch_eval (apax/md/ase_calc.py:395-481, jax.vmap over padded structures) and of the training
+ * data path (apax/train/run.py:204).  Atoms of all structures are concatenated (no padding needed):
+ * struct_ptr i32 [n_structs+1] gives each structure's atom range, idx holds GLOBAL atom indices, R is
+ * Cartesian and offsets (f64 [n_pairs][3], Cartesian, NULL = zero) carry the periodic images, i.e.
+ * dr = R[idx[1]] - R[idx[0]] + offsets.  energy f64 [n_structs][n_out]; forces f64 [n_out][n_atoms][3]. */
+int apax_gm_energy_forces_batched(apax_stream_t stream, const apax_gm_params* params, const double* R,
+                                  const int32_t* Z, const int32_t* idx, const double* offsets,
+                                  const int32_t* struct_ptr, int64_t n_structs, int64_t n_atoms, int64_t n_pairs,
+                                  double* energy, double* forces, void* workspace, size_t workspace_bytes);
+
 /* Domain-decomposed evaluation (no counterpart in the reference, which is single-device:
  * apax/md/simulate.py:313-354).  Atoms [0, n_central) are this rank's owned atoms and are the only
  * centrals (rows of the prepared list); atoms [n_central, n_atoms) are ghosts that only act as
@@ -164,6 +175,13 @@ int apax_nl_build_images(apax_stream_t stream, const double* pos, const double* 
                          int64_t n_atoms, double cutoff, int64_t capacity, int32_t* idx,
                          int32_t* shifts, double* offsets, int32_t* n_found, uint8_t* overflow,
                          void* workspace, size_t workspace_bytes);
+/* (2b) the same list for a batch of independent periodic cells (cells f64 [n_structs][3][3], rows = lattice
+ *     vectors; struct_ptr i32 [n_structs+1]); idx holds global atom indices, rows grouped by central atom. */
+size_t apax_nl_batched_workspace_bytes(int64_t n_atoms, int64_t capacity, int64_t n_structs);
+int apax_nl_build_images_batched(apax_stream_t stream, const double* pos, const double* cells,
+                                 const int32_t* struct_ptr, int64_t n_structs, int64_t n_atoms, double cutoff,
+                                 int64_t capacity, int32_t* idx, int32_t* shifts, double* offsets, int32_t* n_found,
+                                 uint8_t* overflow, void* workspace, size_t workspace_bytes);
 int apax_nl_needs_rebuild(apax_stream_t stream, const double* frac, const double* ref,
                           const double* box, int64_t n_atoms, double dr_threshold, int32_t* flag);
 
