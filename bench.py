@@ -310,8 +310,14 @@ def run_ours(args):
             e_h, f_hh = ctx.calculate(pos, Z32, cell, dr_threshold=0.0, rebuild=True)
         dt = (time.perf_counter() - t0) / k_e2e
         assert abs(e_h[0] - energy) <= 1e-9 * abs(energy) + 1e-6, (e_h[0], energy)
+        rec = rt.profile_kernels(lambda: ctx.calculate(pos, Z32, cell, dr_threshold=0.0, rebuild=True))
+        e2e_kernels = {}
+        for name, ms in rec:
+            e2e_kernels[name] = e2e_kernels.get(name, 0.0) + ms
         e2e = {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": int(n * 24 + n * 4 + 36 * 8),
                "d2h_bytes_per_step": int(n * 24 + 8), "ms_per_step": dt * 1e3, "steps": k_e2e,
+               "kernel_ms_per_step": {k: round(v, 3) for k, v in sorted(e2e_kernels.items(), key=lambda kv: -kv[1])},
+               "kernel_ms_total": round(sum(e2e_kernels.values()), 3),
                "includes": "host->device copy of positions/numbers/cell, fractional transform, cell-list neighbour "
                            "build (every step), list preparation, E+F, device->host copy of energy and forces"}
         ctx.close()
