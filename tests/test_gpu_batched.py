@@ -72,6 +72,7 @@ def test_batch_eval_mirror():
     single = ASECalculator(params, model_config={"ensemble": {"kind": "shallow", "n_members": 4, "force_variance": True}})
     for a, r in zip(atoms, out):
         s = single.calculate(a)
-        assert abs(r["energy"] - s["energy"]) <= 1e-9 * abs(s["energy"]) + 1e-9
-        assert np.abs(r["forces"] - s["forces"]).max() < 1e-9
-        assert r["forces_ensemble"].shape == (128, 3, 4) and np.abs(r["forces_uncertainty"] - s["forces_uncertainty"]).max() < 1e-9
+        # same model, different (equally valid) neighbour order inside a row => fp32 summation order differs
+        assert abs(r["energy"] - s["energy"]) <= 1e-6 * abs(s["energy"])
+        assert np.all(np.abs(r["forces"] - s["forces"]) <= 1e-5 * np.abs(s["forces"]) + 2e-6)
+        assert r["forces_ensemble"].shape == (128, 3, 4) and np.abs(r["forces_uncertainty"] - s["forces_uncertainty"]).max() < 1e-5
