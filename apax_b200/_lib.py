@@ -37,6 +37,11 @@ class GmConfig(C.Structure):
     ]
 
 
+class MdNvtConfig(C.Structure):
+    _fields_ = [("chain_length", C.c_int32), ("chain_steps", C.c_int32), ("sy_steps", C.c_int32), ("dt", C.c_double),
+                ("kT", C.c_double), ("tau", C.c_double)]
+
+
 # every exported symbol of include/apax_b200.h with its signature
 _P = C.c_void_p
 _I64 = C.c_int64
@@ -64,6 +69,10 @@ SIGNATURES = {
     "apax_nl_batched_workspace_bytes": (C.c_size_t, [_I64, _I64, _I64]),
     "apax_nl_build_images_batched": (C.c_int, [_P, _P, _P, _P, _I64, _I64, C.c_double, _I64, _P, _P, _P, _P, _P, _P, C.c_size_t]),
     "apax_nl_needs_rebuild": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, _P]),
+    "apax_md_nvt_state_bytes": (C.c_size_t, []),
+    "apax_md_nvt_init": (C.c_int, [_P, C.POINTER(MdNvtConfig), _P, _P, _I64, _P]),
+    "apax_md_nvt_pre_force": (C.c_int, [_P, C.POINTER(MdNvtConfig), _P, _P, _P, _P, _P, _I64, _P]),
+    "apax_md_nvt_post_force": (C.c_int, [_P, C.POINTER(MdNvtConfig), _P, _P, _P, _I64, _P]),
     "apax_ctx_create": (C.c_int, [_P, _I64, _I64, C.POINTER(_P)]),
     "apax_ctx_destroy": (None, [_P]),
     "apax_ctx_calculate": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, _I32, _P, _P, _P]),

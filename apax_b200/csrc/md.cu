@@ -1,0 +1,237 @@
+// NVT Nose-Hoover-chain molecular dynamics around the GMNN force kernels, entirely on the device.
+//
+// Replaces the body of the jitted fori_loop of apax/md/simulate.py:313-354 for the ensemble apax builds at
+// simulate.py:100-119, i.e. jax_md's nvt_nose_hoover (apax/utils/jax_md_reduced/simulate.py:536-639):
+//   chain half step (simulate.py:436-487) -> velocity Verlet (:216-231) with the fractional, wrapped shift of
+//   periodic_general (space.py:284-309) -> kinetic energy -> chain half step.
+// The chain is a handful of scalars: one thread integrates it on the device (no host round trip inside the
+// MD loop -- the reference hops to the host every step through io_callback, simulate.py:343); the O(N) parts
+// are elementwise kernels and a fixed-shape fp64 reduction.  dtypes follow the reference: fp64 state, time
+// steps and chain masses rounded to fp32 where it casts with f32().
+#include <math.h>
+
+#include "common.cuh"
+
+namespace apax {
+
+constexpr int kMaxChain = 16;
+
+struct MdChainState {       // lives in device memory (apax_md_nvt_state_bytes)
+  double xi[kMaxChain];
+  double p_xi[kMaxChain];
+  double Q[kMaxChain];      // fp32-rounded values
+  double KE;
+  double scale;             // momentum scale of the last chain half step
+  double inv_box[9];
+  double partial[256];
+  int dof;
+  int chain_length;
+};
+
+namespace {
+
+__constant__ double kSY3[3] = {0.828981543588751, -0.657963087177502, 0.828981543588751};
+__constant__ double kSY5[5] = {0.2967324292201065, 0.2967324292201065, -0.186929716880426, 0.2967324292201065,
+                               0.2967324292201065};
+__constant__ double kSY7[7] = {0.784513610477560, 0.235573213359357, -1.17767998417887, 1.31518632068391,
+                               -1.17767998417887, 0.235573213359357, 0.784513610477560};
+
+__device__ __forceinline__ double f32r(double x) { return double(float(x)); }
+
+// substep_fn (simulate.py:436-473)
+__device__ double chain_substep(MdChainState& c, double delta, double kT) {
+  const int M = c.chain_length - 1;
+  const double delta_2 = f32r(delta / 2.0), delta_4 = f32r(delta_2 / 2.0), delta_8 = f32r(delta_4 / 2.0);
+  double p_old[kMaxChain];
+  double G = c.p_xi[M - 1] * c.p_xi[M - 1] / c.Q[M - 1] - kT;
+  c.p_xi[M] += delta_4 * G;
+  for (int m = 0; m <= M; ++m) p_old[m] = c.p_xi[m];
+  double carry = c.p_xi[M];
+  for (int m = M - 1; m >= 1; --m) {
+    G = p_old[m - 1] * p_old[m - 1] / c.Q[m - 1] - kT;
+    const double s = exp(-delta_8 * carry / c.Q[m + 1]);
+    carry = s * (s * p_old[m] + delta_4 * G);
+    c.p_xi[m] = carry;
+  }
+  G = 2.0 * c.KE - c.dof * kT;
+  double s = exp(-delta_8 * c.p_xi[1] / c.Q[1]);
+  c.p_xi[0] = s * (s * c.p_xi[0] + delta_4 * G);
+  s = exp(-delta_2 * c.p_xi[0] / c.Q[0]);
+  c.KE *= s * s;
+  const double p_scale = s;
+  for (int m = 0; m <= M; ++m) c.xi[m] += delta_2 * c.p_xi[m] / c.Q[m];
+  G = 2.0 * c.KE - c.dof * kT;
+  for (int m = 0; m <= M; ++m) p_old[m] = c.p_xi[m];
+  for (int m = 0; m < M; ++m) {
+    const double sc = exp(-delta_8 * p_old[m + 1] / c.Q[m + 1]);
+    const double upd = sc * (sc * p_old[m] + delta_4 * G);
+    G = upd * upd / c.Q[m] - kT;
+    c.p_xi[m] = upd;
+  }
+  c.p_xi[M] += delta_4 * G;
+  return p_scale;
+}
+
+// update_chain_mass_fn + half_step_chain_fn (simulate.py:475-495); one thread
+__global__ void k_md_chain_half(MdChainState* st, double dt, double kT, double tau, int chain_steps, int sy_steps,
+                                const double* __restrict__ box) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  MdChainState c = *st;
+  const float q = float(kT) * (float(tau) * float(tau));
+  for (int m = 0; m < c.chain_length; ++m) c.Q[m] = double(m == 0 ? q * float(c.dof) : q);
+  double total = 1.0;
+  if (chain_steps == 1 && sy_steps == 1) {
+    total = chain_substep(c, dt, kT);
+  } else {
+    const double delta = f32r(dt / chain_steps);
+    const double* ws = sy_steps == 3 ? kSY3 : (sy_steps == 5 ? kSY5 : kSY7);
+    for (int i = 0; i < chain_steps * sy_steps; ++i) {
+      const double w = sy_steps == 1 ? 1.0 : ws[i % sy_steps];
+      total *= chain_substep(c, f32r(delta * w), kT);
+    }
+  }
+  c.scale = total;
+  if (box) {  // inverse of the (possibly time-dependent) box for the fractional position update
+    const double* a = box;
+    const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+    const double id = 1.0 / det;
+    c.inv_box[0] = (a[4] * a[8] - a[5] * a[7]) * id; c.inv_box[1] = (a[2] * a[7] - a[1] * a[8]) * id; c.inv_box[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+    c.inv_box[3] = (a[5] * a[6] - a[3] * a[8]) * id; c.inv_box[4] = (a[0] * a[8] - a[2] * a[6]) * id; c.inv_box[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+    c.inv_box[6] = (a[3] * a[7] - a[4] * a[6]) * id; c.inv_box[7] = (a[1] * a[6] - a[0] * a[7]) * id; c.inv_box[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+  }
+  *st = c;
+}
+
+// P <- P*scale + dt/2 F ; R <- mod(R + inv_box.(dt P / m), 1)      (momentum_step, position_step, periodic_shift)
+__global__ void __launch_bounds__(256) k_md_kick_drift(double* __restrict__ R, double* __restrict__ P,
+                                                       const double* __restrict__ F, const double* __restrict__ mass,
+                                                       const MdChainState* __restrict__ st, double dt, double dt_2,
+                                                       int64_t N) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= N) return;
+  const double s = st->scale;
+  double p[3], d[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    p[k] = P[3 * i + k] * s + dt_2 * F[3 * i + k];
+    P[3 * i + k] = p[k];
+    d[k] = dt * p[k] / mass[i];
+  }
+  const double* ib = st->inv_box;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double t = R[3 * i + k] + (ib[3 * k] * d[0] + ib[3 * k + 1] * d[1] + ib[3 * k + 2] * d[2]);
+    double m = fmod(t, 1.0);
+    if (m < 0.0) m += 1.0;   // jnp.mod
+    R[3 * i + k] = m;
+  }
+}
+
+// P <- P + dt/2 F, and the per-block partial sums of 0.5 p^2/m
+__global__ void __launch_bounds__(256) k_md_kick_ke(double* __restrict__ P, const double* __restrict__ F,
+                                                    const double* __restrict__ mass, MdChainState* __restrict__ st,
+                                                    double dt_2, int64_t N, int apply_kick) {
+  __shared__ double sm[256];
+  const int64_t chunk = (N + gridDim.x - 1) / gridDim.x;
+  const int64_t b = int64_t(blockIdx.x) * chunk, e = min(N, b + chunk);
+  double acc = 0.0;
+  for (int64_t i = b + threadIdx.x; i < e; i += 256) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double p = P[3 * i + k];
+      if (apply_kick) {
+        p += dt_2 * F[3 * i + k];
+        P[3 * i + k] = p;
+      }
+      s += p * p;
+    }
+    acc += 0.5 * s / mass[i];
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st->partial[blockIdx.x] = sm[0];
+}
+
+__global__ void k_md_ke_final(MdChainState* st, int n_blocks) {
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n_blocks; ++i) s += st->partial[i];
+    st->KE = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_md_scale(double* __restrict__ P, const MdChainState* __restrict__ st, int64_t n3) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i < n3) P[i] *= st->scale;
+}
+
+__global__ void k_md_chain_init(MdChainState* st, int chain_length, int dof) {
+  if (threadIdx.x != 0) return;
+  for (int m = 0; m < kMaxChain; ++m) { st->xi[m] = 0.0; st->p_xi[m] = 0.0; st->Q[m] = 1.0; }
+  st->chain_length = chain_length;
+  st->dof = dof;
+  st->scale = 1.0;
+}
+
+int ke_blocks(int64_t N) { return int(N < 256 * 16 ? 1 : (N / (256 * 16) > 256 ? 256 : N / (256 * 16))); }
+
+}  // namespace
+}  // namespace apax
+
+using namespace apax;
+
+extern "C" size_t apax_md_nvt_state_bytes(void) { return sizeof(MdChainState); }
+
+static int md_cfg_ok(const apax_md_nvt_config* c) {
+  if (!c || c->chain_length < 2 || c->chain_length > kMaxChain || c->chain_steps < 1) return APAX_ERR_INVALID_ARG;
+  if (c->sy_steps != 1 && c->sy_steps != 3 && c->sy_steps != 5 && c->sy_steps != 7) return APAX_ERR_INVALID_ARG;
+  if (!(c->dt > 0.0) || !(c->kT > 0.0) || !(c->tau > 0.0)) return APAX_ERR_INVALID_ARG;
+  return APAX_OK;
+}
+
+extern "C" int apax_md_nvt_init(apax_stream_t stream, const apax_md_nvt_config* cfg, const double* P, const double* mass,
+                                int64_t n_atoms, void* state) {
+  APAX_TRY(md_cfg_ok(cfg));
+  if (!P || !mass || !state || n_atoms < 1) return APAX_ERR_INVALID_ARG;
+  MdChainState* st = static_cast<MdChainState*>(state);
+  APAX_LAUNCH(k_md_chain_init, dim3(1), dim3(32), 0, stream, st, cfg->chain_length, int(3 * n_atoms));
+  const int nb = ke_blocks(n_atoms);
+  APAX_LAUNCH(k_md_kick_ke, dim3(nb), dim3(256), 0, stream, const_cast<double*>(P), (const double*)nullptr, mass, st, 0.0,
+              n_atoms, 0);
+  APAX_LAUNCH(k_md_ke_final, dim3(1), dim3(32), 0, stream, st, nb);
+  return APAX_OK;
+}
+
+extern "C" int apax_md_nvt_pre_force(apax_stream_t stream, const apax_md_nvt_config* cfg, double* R_frac, double* P,
+                                     const double* F, const double* mass, const double* box, int64_t n_atoms,
+                                     void* state) {
+  APAX_TRY(md_cfg_ok(cfg));
+  if (!R_frac || !P || !F || !mass || !box || !state) return APAX_ERR_INVALID_ARG;
+  MdChainState* st = static_cast<MdChainState*>(state);
+  const double dt = double(float(cfg->dt)), dt_2 = double(float(dt / 2));   // f32(dt), f32(dt / 2) (simulate.py:219-220)
+  APAX_LAUNCH(k_md_chain_half, dim3(1), dim3(32), 0, stream, st, dt, cfg->kT, double(float(cfg->tau)), cfg->chain_steps,
+              cfg->sy_steps, box);
+  APAX_LAUNCH(k_md_kick_drift, dim3((unsigned)cdiv(n_atoms, 256)), dim3(256), 0, stream, R_frac, P, F, mass, st, dt, dt_2,
+              n_atoms);
+  return APAX_OK;
+}
+
+extern "C" int apax_md_nvt_post_force(apax_stream_t stream, const apax_md_nvt_config* cfg, double* P, const double* F,
+                                      const double* mass, int64_t n_atoms, void* state) {
+  APAX_TRY(md_cfg_ok(cfg));
+  if (!P || !F || !mass || !state) return APAX_ERR_INVALID_ARG;
+  MdChainState* st = static_cast<MdChainState*>(state);
+  const double dt = double(float(cfg->dt)), dt_2 = double(float(dt / 2));
+  const int nb = ke_blocks(n_atoms);
+  APAX_LAUNCH(k_md_kick_ke, dim3(nb), dim3(256), 0, stream, P, F, mass, st, dt_2, n_atoms, 1);
+  APAX_LAUNCH(k_md_ke_final, dim3(1), dim3(32), 0, stream, st, nb);
+  APAX_LAUNCH(k_md_chain_half, dim3(1), dim3(32), 0, stream, st, dt, cfg->kT, double(float(cfg->tau)), cfg->chain_steps,
+              cfg->sy_steps, (const double*)nullptr);
+  APAX_LAUNCH(k_md_scale, dim3((unsigned)cdiv(3 * n_atoms, 256)), dim3(256), 0, stream, P, st, 3 * n_atoms);
+  return APAX_OK;
+}

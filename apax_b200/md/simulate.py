@@ -30,3 +30,71 @@ def create_energy_fn(model: EnergyModel, params, numbers, n_models: int = 1, sha
 
     energy_fn.force_fn = force_fn
     return energy_fn
+
+
+def run_nvt(params, atoms, model_config=None, *, dt: float, kT: float, n_steps: int, dr_threshold: float = 0.5,
+            rebuild_every: int | None = None, masses=None, momentum=None, seed: int = 0, chain_length: int = 5,
+            chain_steps: int = 2, sy_steps: int = 3, tau=None, on_step=None):
+    """The MD driver of apax/md/simulate.py (md_setup :440-561 + run_sim :218-437) for the NVT Nose-Hoover
+    ensemble, with everything inside the step loop on the GPU: fractional positions, min-image list with skin
+    (rebuilt on the reference's skin criterion, partition.py:771-779, or every `rebuild_every` steps as
+    BASELINE config 3 words it), GMNN energy+forces, integrator.  Units are the caller's (ASE: eV, A, amu =>
+    time in A sqrt(amu/eV)).  Returns the final NVTNoseHooverState and a dict of counters."""
+    import numpy as np
+
+    from ..nn.builder import GMNNBuilder
+    from ..utils.jax_md_reduced import partition
+    from ..utils.jax_md_reduced.simulate import nvt_nose_hoover
+
+    cell = np.asarray(getattr(atoms.cell, "array", atoms.cell), dtype=np.float64)
+    box = cell.T.copy()                                                   # sim_utils.py:18-38
+    frac = np.asarray(atoms.positions, dtype=np.float64) @ np.linalg.inv(cell)
+    frac = frac - np.floor(frac)
+    builder = GMNNBuilder(model_config)
+    model = builder.build_energy_model(init_box=box, inference_disp_fn=object())
+    r_max = float(builder.config["basis"]["r_max"])
+    neighbor_fn = partition.neighbor_list(None, box, r_max, dr_threshold, fractional_coordinates=True,
+                                          disable_cell_list=True, format=partition.Sparse)
+    energy_fn = create_energy_fn(model, params, atoms.numbers, n_models=1)
+    box_d = rt.to_device(box, torch.float64)
+    nbrs = neighbor_fn.allocate(frac, box=box_d)
+    counters = {"rebuilds": 0, "steps": 0}
+    dp = device_params(params, model.statics())
+    Z = rt.to_device(atoms.numbers, torch.int32)
+    system = {"prepared": rt.PreparedSystem(dp, Z, nbrs.idx), "nbrs": nbrs}
+
+    def force_fn(R, box=None, **kw):
+        _, f = system["prepared"].compute(R, box_d, None, "minimage")
+        return f[0]
+
+    init_fn, apply_fn = nvt_nose_hoover(force_fn, None, dt, kT, chain_length, chain_steps, sy_steps, tau)
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    state = init_fn(gen, frac, mass=np.ones(len(atoms.numbers)) if masses is None else masses, momentum=momentum)
+
+    def maybe_rebuild(step):
+        if rebuild_every is not None:
+            need = step % rebuild_every == 0 and step > 0
+            new = neighbor_fn.allocate(state.position, box=box_d) if need else system["nbrs"]
+        else:
+            new = system["nbrs"].update(state.position, box=box_d)
+            need = new is not system["nbrs"]
+            if need and new.did_buffer_overflow:                           # simulate.py:388-394
+                new = neighbor_fn.allocate(state.position, box=box_d)
+        if need:
+            system["nbrs"] = new
+            system["prepared"] = rt.PreparedSystem(dp, Z, new.idx, workspace=system["prepared"].ws)
+            counters["rebuilds"] += 1
+
+    orig_force = force_fn
+
+    def stepping_force(R, box=None, **kw):
+        maybe_rebuild(counters["steps"])
+        return orig_force(R)
+
+    init_fn2, apply_fn = nvt_nose_hoover(stepping_force, None, dt, kT, chain_length, chain_steps, sy_steps, tau)
+    for _ in range(n_steps):
+        counters["steps"] += 1
+        state = apply_fn(state, box=box_d)
+        if on_step is not None:
+            on_step(counters["steps"], state)
+    return state, counters

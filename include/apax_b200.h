@@ -186,6 +186,32 @@ int apax_nl_needs_rebuild(apax_stream_t stream, const double* frac, const double
                           const double* box, int64_t n_atoms, double dr_threshold, int32_t* flag);
 
 /* ------------------------------------------------------------------------------------------------
+ * NVT Nose-Hoover-chain integrator, on the device.  Replaces the per-step body of apax's MD loop
+ * (apax/md/simulate.py:313-354) for the ensemble built at simulate.py:100-119, i.e. jax_md's
+ * nvt_nose_hoover.apply_fn (apax/utils/jax_md_reduced/simulate.py:611-637):
+ *   apax_md_nvt_pre_force : chain half step (:436-487), P += dt/2 F, R_frac = mod(R_frac + inv(box).(dt P/m), 1)
+ *   -- caller evaluates F(R_frac) with apax_gm_compute --
+ *   apax_md_nvt_post_force: P += dt/2 F, kinetic energy, chain half step, momentum rescale
+ * R_frac, P, F f64 [n][3]; mass f64 [n]; box f64 [3][3] (columns = lattice vectors); state: device buffer of
+ * apax_md_nvt_state_bytes() bytes initialised by apax_md_nvt_init (chain at rest, KE from P).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t chain_length; /* 5 (simulate.py:541) */
+  int32_t chain_steps;  /* 2 */
+  int32_t sy_steps;     /* 3 (1, 3, 5 or 7) */
+  double dt;            /* time step (rounded to fp32 like the reference's f32(dt)) */
+  double kT;
+  double tau;           /* thermostat period; the reference default is 100 dt */
+} apax_md_nvt_config;
+size_t apax_md_nvt_state_bytes(void);
+int apax_md_nvt_init(apax_stream_t stream, const apax_md_nvt_config* cfg, const double* P, const double* mass,
+                     int64_t n_atoms, void* state);
+int apax_md_nvt_pre_force(apax_stream_t stream, const apax_md_nvt_config* cfg, double* R_frac, double* P,
+                          const double* F, const double* mass, const double* box, int64_t n_atoms, void* state);
+int apax_md_nvt_post_force(apax_stream_t stream, const apax_md_nvt_config* cfg, double* P, const double* F,
+                           const double* mass, int64_t n_atoms, void* state);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-buffer convenience context: what ASECalculator.calculate does per call
  * (apax/md/ase_calc.py:357-393): positions/cell on the HOST in, neighbour list (min-image when
  * min cell height / 2 > r_max, image list otherwise, :501-522), E+F, results on the HOST out.

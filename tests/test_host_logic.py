@@ -67,7 +67,7 @@ def test_generated_header_is_current():
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "apax_b200.h")).read()
     declared = set(re.findall(r"\b(apax_[a-z0-9_]+)\s*\(", header))
-    declared -= {"apax_gm_params", "apax_ctx"}
+    declared -= {"apax_gm_params", "apax_ctx", "apax_md_nvt_config", "apax_gm_config"}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     if not os.path.exists(_lib.LIB_PATH):
         pytest.skip("libapax_b200.so not built in this checkout (python -m apax_b200.build)")
