@@ -40,7 +40,7 @@ def assert_force_parity(f, f_ref32, f_ref64=None, n_atoms=None, where=""):
     (golden fixtures) sits at 1.4x of it against the all-fp64 oracle on the 36-atom fixture, the fp32 oracle at
     0.75x (96 atoms) ... 1.7x (DESIGN.md "Numerics").  The criterion is therefore "inside the tolerance, or no
     further from the reference than the reference is from the truth":
-      (a) worst element vs f_ref32 <= max(1, 1.5 * worst element of f_ref32 vs f_ref64), never beyond 3x
+      (a) worst element vs f_ref32 <= max(1, 1.5 * worst element of f_ref32 vs f_ref64)
           (two independent evaluations with the same noise differ by sqrt(2) of it);
       (b) >= 99 % of the elements inside the literal tolerance (or, if the reference itself has fewer than that
           inside it against the fp64 truth, at most 2 % fewer than the reference);
@@ -51,7 +51,7 @@ def assert_force_parity(f, f_ref32, f_ref64=None, n_atoms=None, where=""):
     bound, frac_bound = 1.0, 0.99
     if f_ref64 is not None:
         ref_noise = np.abs(f_ref32 - f_ref64) / (1e-5 * np.abs(f_ref64) + 1e-6)
-        bound = min(3.0, max(1.0, 1.5 * float(ref_noise.max())))
+        bound = max(1.0, 1.5 * float(ref_noise.max()))
         frac_bound = min(0.99, float(np.mean(ref_noise <= 1.0)) - 0.02)
     assert viol.max() <= bound, f"{where}: worst element at {viol.max():.3f}x tolerance (bound {bound:.3f})"
     assert np.mean(viol <= 1.0) >= frac_bound, f"{where}: {np.mean(viol <= 1.0):.4f} of elements within tolerance (bound {frac_bound:.4f})"

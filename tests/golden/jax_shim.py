@@ -38,14 +38,29 @@ class _AtSetter:
     def __init__(self, t, index):
         self.t, self.index = t, index
 
-    def set(self, values):
-        out = self.t.clone()
+    def _idx(self):
         idx = self.index
         if isinstance(idx, tuple):
             idx = tuple(i.long() if isinstance(i, _T) and not i.dtype == torch.bool else i for i in idx)
         elif isinstance(idx, _T) and idx.dtype != torch.bool:
             idx = idx.long()
-        out[idx] = values if not isinstance(values, _T) else values.to(out.dtype)
+        return idx
+
+    def set(self, values):
+        out = self.t.clone()
+        out[self._idx()] = values if not isinstance(values, _T) else values.to(out.dtype)
+        return out
+
+    def add(self, values):
+        out = self.t.clone()
+        idx = self._idx()
+        out[idx] = out[idx] + (values if not isinstance(values, _T) else values.to(out.dtype))
+        return out
+
+    def multiply(self, values):
+        out = self.t.clone()
+        idx = self._idx()
+        out[idx] = out[idx] * (values if not isinstance(values, _T) else values.to(out.dtype))
         return out
 
 
@@ -193,6 +208,21 @@ def _where(c, a, b):
 
 
 jnp.where = _where
+jnp.integer = "integer"
+jnp.complexfloating = "complexfloating"
+jnp.floating = "floating"
+
+
+def _issubdtype(dt, kind):
+    tdt = _to_torch_dtype(dt)
+    if kind == "integer":
+        return tdt in (torch.int8, torch.int16, torch.int32, torch.int64, torch.uint8)
+    if kind == "complexfloating":
+        return tdt in (torch.complex64, torch.complex128)
+    return tdt in (torch.float16, torch.float32, torch.float64)
+
+
+jnp.issubdtype = _issubdtype
 
 
 def _clip(x, min=None, max=None):
@@ -319,6 +349,16 @@ class _Lax(types.ModuleType):
         return x.detach() if isinstance(x, _T) else x
 
     @staticmethod
+    def scan(f, init, xs, length=None, unroll=1):
+        carry, ys = init, []
+        for i in range(len(xs)):
+            carry, y = f(carry, xs[i])
+            ys.append(y)
+        if ys and isinstance(ys[0], _T):
+            ys = torch.stack(ys)
+        return carry, ys
+
+    @staticmethod
     def cond(pred, *args):
         # lax.cond(pred, operand_true..., true_fn, operand_false, false_fn) legacy 5-arg form
         if len(args) == 4:
@@ -337,11 +377,38 @@ def install(reference_root="/root/reference"):
     jax.value_and_grad, jax.grad, jax.jacrev = value_and_grad, grad, jacrev
     jax.eval_shape = eval_shape
     jax.Array = _T
+
+    class ShapeDtypeStruct:  # eval_shape returns concrete tensors in this shim
+        pass
+
+    jax.ShapeDtypeStruct = ShapeDtypeStruct
+    jscipy = types.ModuleType("jax.scipy")
+    jspecial = types.ModuleType("jax.scipy.special")
+    jspecial.gammaln = torch.lgamma
+    jscipy.special = jspecial
+    jax.scipy = jscipy
     jax.lax = _Lax("jax.lax")
     jax.ensure_compile_time_eval = lambda: __import__("contextlib").nullcontext()
     tree_util = types.ModuleType("jax.tree_util")
     tree_util.register_pytree_node = lambda *a, **k: None
-    tree_util.tree_map = lambda f, t: {k: f(v) for k, v in t.items()}
+    def _tree_map(f, t, *rest):
+        if isinstance(t, dict):
+            return {k: _tree_map(f, v, *[r[k] for r in rest]) for k, v in t.items()}
+        if isinstance(t, (list, tuple)):
+            return type(t)(_tree_map(f, v, *[r[i] for r in rest]) for i, v in enumerate(t))
+        return f(t, *rest)
+
+    def _tree_leaves(t):
+        if isinstance(t, dict):
+            return [l for v in t.values() for l in _tree_leaves(v)]
+        if isinstance(t, (list, tuple)):
+            return [l for v in t for l in _tree_leaves(v)]
+        return [t]
+
+    tree_util.tree_map = _tree_map
+    tree_util.tree_reduce = lambda f, t, init: functools.reduce(f, _tree_leaves(t), init)
+    tree_util.tree_flatten = lambda t: (_tree_leaves(t), None)
+    tree_util.tree_unflatten = lambda treedef, leaves: leaves[0]
     jax.tree_util = tree_util
     ops = types.ModuleType("jax.ops")
     ops.segment_sum = _segment_sum
@@ -364,7 +431,8 @@ def install(reference_root="/root/reference"):
     jax._src = jsrc
     mods = {"jax": jax, "jax.numpy": jnp, "jax.numpy.linalg": _linalg, "jax.lax": jax.lax,
             "jax.tree_util": tree_util, "jax.ops": ops, "jax.nn": jnn, "jax.nn.initializers": inits,
-            "jax.random": jrandom, "jax.core": jcore, "jax._src": jsrc, "jax._src.dtypes": jsrc_dtypes}
+            "jax.random": jrandom, "jax.core": jcore, "jax._src": jsrc, "jax._src.dtypes": jsrc_dtypes,
+            "jax.scipy": jscipy, "jax.scipy.special": jspecial}
 
     # ---- flax.linen
     flax = types.ModuleType("flax")
@@ -402,7 +470,10 @@ def install(reference_root="/root/reference"):
 
     # apax.utils.jax_md_reduced's __init__ would import simulate/smap/quantity; expose what is used
     jm = sys.modules["apax.utils.jax_md_reduced"]
-    for sub in ("util", "dataclasses", "space", "partition"):
+    smap = types.ModuleType("apax.utils.jax_md_reduced.smap")  # pair-potential mappers: unused by GMNN
+    sys.modules["apax.utils.jax_md_reduced.smap"] = smap
+    jm.smap = smap
+    for sub in ("util", "dataclasses", "space", "partition", "quantity", "simulate"):
         setattr(jm, sub, importlib.import_module(f"apax.utils.jax_md_reduced.{sub}"))
     return jax
 

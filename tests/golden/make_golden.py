@@ -176,6 +176,48 @@ def case_ensemble(n_mol=10, seed=9, n_ens=4):
              box=box, param_seed=77, n_ens=n_ens, **res)
 
 
+def case_md_nvt(n=24, seed=2):
+    """jax_md's nvt_nose_hoover.apply_fn (apax/utils/jax_md_reduced/simulate.py:611-637) as apax runs it
+    (apax/md/simulate.py:100-119), driven by a harmonic tether force so that only the integrator is exercised."""
+    from apax.utils.jax_md_reduced import simulate
+
+    rng = np.random.default_rng(seed)
+    cell = np.array([[9.0, 0.0, 0.0], [1.0, 8.0, 0.0], [0.5, -0.7, 10.0]])
+    box = torch.as_tensor(cell.T.copy())
+    frac0 = rng.uniform(size=(n, 3))
+    anchor = torch.as_tensor(frac0.copy())
+    mass = rng.uniform(1.0, 16.0, size=n)
+    kT, dt = 0.3, 0.02
+    p0 = rng.normal(size=(n, 3)) * np.sqrt(mass * kT)[:, None]
+    p0 -= p0.mean(0)
+    kspring = 0.7
+
+    def force_fn(R, **kwargs):
+        d = R - anchor
+        d = d - torch.round(d)
+        return -kspring * (d @ box.T)            # Cartesian restoring force
+
+    _, shift_fn = space.periodic_general(box, fractional_coordinates=True)
+    init_fn, apply_fn = simulate.nvt_nose_hoover(force_fn, shift_fn, dt, kT)   # defaults: chain 5 / 2 / 3, tau = 100 dt
+    R = torch.as_tensor(frac0.copy())
+    thermostat = simulate.nose_hoover_chain(simulate.f32(dt), 5, 2, 3, simulate.f32(simulate.f32(dt) * 100))
+    state = simulate.NVTNoseHooverState(R, torch.as_tensor(p0.copy()), force_fn(R), torch.as_tensor(mass.copy())[:, None], None)
+    KE = simulate.kinetic_energy(state)
+    state = state.set(chain=thermostat.initialize(3 * n, KE, kT))
+    snaps = {}
+    for step in range(1, 8):
+        state = apply_fn(state)
+        if step in (1, 7):
+            snaps[f"position_{step}"] = state.position.numpy().copy()
+            snaps[f"momentum_{step}"] = state.momentum.numpy().copy()
+            snaps[f"xi_{step}"] = state.chain.position.numpy().copy()
+            snaps[f"p_xi_{step}"] = state.chain.momentum.numpy().copy()
+            snaps[f"Q_{step}"] = state.chain.mass.numpy().astype(np.float64)
+            snaps[f"KE_{step}"] = float(state.chain.kinetic_energy)
+    np.savez(os.path.join(HERE, "md_nvt.npz"), cell=cell, frac0=frac0, mass=mass, p0=p0, kT=kT, dt=dt, kspring=kspring,
+             KE0=float(KE), **snaps)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     case_descriptor_unit()
@@ -188,3 +230,5 @@ if __name__ == "__main__":
     print("min_image ok")
     case_ensemble()
     print("ensemble ok")
+    case_md_nvt()
+    print("md_nvt ok")

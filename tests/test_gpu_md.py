@@ -77,7 +77,7 @@ def test_run_nvt_conserves_extended_energy_and_rebuilds():
 
     state, counters = run_nvt(params, Atoms(pos, Z, cell), dt=dt, kT=kT, n_steps=100, masses=mass, rebuild_every=10,
                               on_step=on_step)
-    assert counters["steps"] == 100 and counters["rebuilds"] == 9
+    assert counters["steps"] == 100 and counters["rebuilds"] == 10   # steps 10, 20, ..., 100
     p = state.momentum.cpu().numpy()
     assert np.isfinite(p).all() and np.isfinite(state.position.cpu().numpy()).all()
     assert np.abs(p.sum(0)).max() < 1e-6 * np.abs(p).sum()           # total momentum stays zero
@@ -85,3 +85,34 @@ def test_run_nvt_conserves_extended_energy_and_rebuilds():
     assert all(k > 0 for k in log)
     state2, counters2 = run_nvt(params, Atoms(pos, Z, cell), dt=dt, kT=kT, n_steps=30, masses=mass, dr_threshold=0.5)
     assert counters2["rebuilds"] >= 0 and np.isfinite(state2.momentum.cpu().numpy()).all()
+
+
+def test_nvt_kernels_against_reference_fixture(golden):
+    """The device integrator alone (analytic tether force computed with torch on the GPU) against the fixture
+    produced by the reference's own simulate.py: positions/momenta/chain after 1 and 7 steps."""
+    from apax_b200 import runtime as rt
+    from apax_b200.utils.jax_md_reduced.simulate import nvt_nose_hoover
+
+    d = golden("md_nvt")
+    box = rt.to_device(d["cell"].T.copy(), torch.float64)
+    anchor = rt.to_device(d["frac0"], torch.float64)
+    k = float(d["kspring"])
+
+    def force(R, box=None, **kw):
+        dd = R - anchor
+        dd = dd - torch.round(dd)
+        return -k * (dd @ rt.to_device(d["cell"].T.copy(), torch.float64).T)
+
+    init_fn, apply_fn = nvt_nose_hoover(force, None, float(d["dt"]), float(d["kT"]))
+    st = init_fn(None, d["frac0"], mass=d["mass"], momentum=d["p0"])
+    assert abs(st.chain_numbers()["KE"] - float(d["KE0"])) < 1e-12
+    for step in range(1, 8):
+        st = apply_fn(st, box=box)
+        if step in (1, 7):
+            ch = st.chain_numbers()
+            assert np.abs(st.position.cpu().numpy() - d[f"position_{step}"]).max() < 1e-13
+            assert np.abs(st.momentum.cpu().numpy() - d[f"momentum_{step}"]).max() < 1e-12
+            assert np.abs(ch["xi"][:5] - d[f"xi_{step}"]).max() < 1e-13
+            assert np.abs(ch["p_xi"][:5] - d[f"p_xi_{step}"]).max() < 1e-11
+            assert np.array_equal(ch["Q"][:5], d[f"Q_{step}"])
+            assert abs(ch["KE"] - float(d[f"KE_{step}"])) < 1e-11

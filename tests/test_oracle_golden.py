@@ -65,3 +65,30 @@ def test_shallow_ensemble(golden):
         assert np.allclose(r[k], d[k], rtol=2e-6, atol=1e-6), k
     for k in ("forces", "forces_uncertainty", "forces_ensemble"):
         assert np.all(np.abs(r[k] - d[k]) <= 1e-5 * np.abs(d[k]) + 2e-6), k
+
+
+def test_md_integrator_against_reference_source(golden):
+    """oracle/md_oracle.py vs jax_md's nvt_nose_hoover executed from the reference's own simulate.py
+    (tests/golden/make_golden.py::case_md_nvt): 7 steps, triclinic box, unequal masses."""
+    from oracle import md_oracle as mo
+
+    d = golden("md_nvt")
+    box = d["cell"].T.copy()
+    anchor, k = d["frac0"].copy(), float(d["kspring"])
+
+    def force(R):
+        dd = R - anchor
+        dd = dd - np.round(dd)
+        return -k * (dd @ box.T)
+
+    st = mo.nvt_init(d["frac0"], d["p0"], d["mass"], force, float(d["kT"]), float(d["dt"]))
+    assert st.chain.KE == float(d["KE0"])
+    for step in range(1, 8):
+        st = mo.nvt_step(st, force, box, float(d["kT"]), float(d["dt"]))
+        if step in (1, 7):
+            assert np.abs(st.position - d[f"position_{step}"]).max() < 1e-14
+            assert np.abs(st.momentum - d[f"momentum_{step}"]).max() < 1e-13
+            assert np.abs(st.chain.xi - d[f"xi_{step}"]).max() < 1e-15
+            assert np.abs(st.chain.p_xi - d[f"p_xi_{step}"]).max() < 1e-13
+            assert np.array_equal(st.chain.Q, d[f"Q_{step}"])
+            assert abs(st.chain.KE - float(d[f"KE_{step}"])) < 1e-12
