@@ -142,17 +142,25 @@ extern "C" int apax_ctx_calculate(apax_ctx* c, const double* positions_host, con
                cell_host[2] * (cell_host[3] * cell_host[7] - cell_host[4] * cell_host[6]);
   if (!(fabs(det) > 1e-12)) return APAX_ERR_UNSUPPORTED;  // gas phase: use apax_gm_energy_forces with a list
 
-  // ---- H2D: positions, numbers, cell / box / inverse / identity
-  memcpy(c->h_pos, positions_host, sizeof(double) * 3 * N);
-  memcpy(c->h_Z, numbers_host, sizeof(int32_t) * N);
+  // ---- H2D: positions, numbers, cell / box / inverse / identity.  Page-locked caller buffers are copied from
+  // directly; pageable ones go through the context's pinned staging area.
+  auto is_pinned = [](const void* ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  const bool pos_pinned = is_pinned(positions_host), z_pinned = is_pinned(numbers_host);
+  if (!pos_pinned) memcpy(c->h_pos, positions_host, sizeof(double) * 3 * N);
+  if (!z_pinned) memcpy(c->h_Z, numbers_host, sizeof(int32_t) * N);
   double* m = c->h_mats;
   for (int i = 0; i < 9; ++i) m[i] = cell_host[i];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) m[9 + 3 * i + j] = cell_host[3 * j + i];  // box = cell.T (ase_calc.py:42-43)
   host_invert3(m + 9, m + 18);
   for (int i = 0; i < 9; ++i) m[27 + i] = (i % 4 == 0) ? 1.0 : 0.0;
-  APAX_CUDA_TRY(cudaMemcpyAsync(c->pos, c->h_pos, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, s));
-  APAX_CUDA_TRY(cudaMemcpyAsync(c->Z, c->h_Z, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s));
+  APAX_CUDA_TRY(cudaMemcpyAsync(c->pos, pos_pinned ? positions_host : c->h_pos, sizeof(double) * 3 * N,
+                                cudaMemcpyHostToDevice, s));
+  APAX_CUDA_TRY(cudaMemcpyAsync(c->Z, z_pinned ? numbers_host : c->h_Z, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s));
   APAX_CUDA_TRY(cudaMemcpyAsync(c->mats, c->h_mats, sizeof(double) * 36, cudaMemcpyHostToDevice, s));
   const double* d_cell = c->mats;
   const double* d_box = c->mats + 9;
@@ -199,7 +207,7 @@ extern "C" int apax_ctx_calculate(apax_ctx* c, const double* positions_host, con
     if (!minimage) {
       APAX_TRY(nl_emit_offsets(s, nw, N, c->offsets));
     }
-    APAX_TRY(gm_prepare_from_csr(s, p, gw, c->Z, nw.rowptr_c, nw.nbr));
+    APAX_TRY(gm_prepare_from_csr(s, p, gw, c->Z, nw.rowptr_c, nw.nbr, /*symmetric_sorted=*/minimage));
     c->list_atoms = N;
     c->list_minimage = int(minimage);
     c->list_cutoff = cutoff;
@@ -216,11 +224,13 @@ extern "C" int apax_ctx_calculate(apax_ctx* c, const double* positions_host, con
   }
   // ---- D2H
   APAX_CUDA_TRY(cudaMemcpyAsync(c->h_out, c->energy, sizeof(double) * n_out, cudaMemcpyDeviceToHost, s));
+  const bool f_pinned = forces_host && is_pinned(forces_host);
   if (forces_host)
-    APAX_CUDA_TRY(cudaMemcpyAsync(c->h_out + n_out, c->forces, sizeof(double) * 3 * N * n_out, cudaMemcpyDeviceToHost, s));
+    APAX_CUDA_TRY(cudaMemcpyAsync(f_pinned ? forces_host : c->h_out + n_out, c->forces, sizeof(double) * 3 * N * n_out,
+                                  cudaMemcpyDeviceToHost, s));
   APAX_CUDA_TRY(cudaStreamSynchronize(s));
   memcpy(energy_host, c->h_out, sizeof(double) * n_out);
-  if (forces_host) memcpy(forces_host, c->h_out + n_out, sizeof(double) * 3 * N * n_out);
+  if (forces_host && !f_pinned) memcpy(forces_host, c->h_out + n_out, sizeof(double) * 3 * N * n_out);
   if (n_pairs_host) *n_pairs_host = c->n_pairs;
   return APAX_OK;
 }

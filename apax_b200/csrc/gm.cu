@@ -165,6 +165,33 @@ __global__ void __launch_bounds__(256) k_csr_import(const int32_t* __restrict__ 
 }
 }  // namespace
 
+// Transpose map of a SYMMETRIC list whose rows are sorted by neighbour index (what nl.cu's min-image builder
+// produces): the reverse of slot s = (j in row a) is the slot of a in row j, found by binary search -- no
+// atomics, no sort.  A slot without a partner (a pair exactly at the cutoff that rounding kept on one side only;
+// its force contribution is exactly zero there) maps onto itself with zero weight via tpos = -1.
+__global__ void __launch_bounds__(256) k_transpose_symmetric(const int32_t* __restrict__ rowptr, int64_t N,
+                                                             const int32_t* __restrict__ nbr, int32_t* __restrict__ trowptr,
+                                                             int32_t* __restrict__ tpos) {
+  const int64_t s = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (s <= N) trowptr[s] = rowptr[s];
+  if (s >= rowptr[N]) return;
+  // row of slot s: binary search over rowptr
+  int lo = 0, hi = int(N);
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (rowptr[mid] <= s) lo = mid; else hi = mid;
+  }
+  const int a = lo, j = nbr[s];
+  int b = rowptr[j], e = rowptr[j + 1] - 1, found = -1;
+  while (b <= e) {
+    const int mid = (b + e) >> 1;
+    const int v = nbr[mid];
+    if (v == a) { found = mid; break; }
+    if (v < a) b = mid + 1; else e = mid - 1;
+  }
+  tpos[s] = found;   // transpose row of a, entry k  <->  row a's own slot order
+}
+
 // transpose map + compact species table; expects w.rowptr / w.nbr final and w.tcnt = counts by neighbour
 static int gm_prepare_tail(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const int32_t* Z) {
   const int64_t N = w.n_atoms, P = w.n_pairs;
@@ -199,15 +226,23 @@ static int gm_prepare_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
   return gm_prepare_tail(stream, p, w, Z);
 }
 
-// list already in CSR form (rows = central atoms, e.g. straight from nl.cu): no COO pass, no row sort
+// list already in CSR form (rows = central atoms, e.g. straight from nl.cu): no COO pass, no row sort.
+// symmetric_sorted: every pair appears in both directions and rows are sorted by neighbour (min-image builder).
 int gm_prepare_from_csr(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const int32_t* Z,
-                        const int32_t* rowptr_in, const int32_t* nbr_in) {
+                        const int32_t* rowptr_in, const int32_t* nbr_in, bool symmetric_sorted) {
   const int64_t N = w.n_atoms, P = w.n_pairs;
   APAX_CUDA_TRY(cudaMemsetAsync(w.tcnt, 0, sizeof(int32_t) * (N + 1), stream));
   const int64_t n = (P > N + 1 ? P : N + 1);
   APAX_LAUNCH(k_csr_import, dim3((unsigned)cdiv(n, 256)), dim3(256), 0, stream, rowptr_in, nbr_in, N, P, w.rowptr, w.nbr,
               w.src, w.tcnt);
-  return gm_prepare_tail(stream, p, w, Z);
+  if (!symmetric_sorted) return gm_prepare_tail(stream, p, w, Z);
+  APAX_LAUNCH(k_transpose_symmetric, dim3((unsigned)cdiv(n, 256)), dim3(256), 0, stream, w.rowptr, N, w.nbr, w.trowptr,
+              w.tpos);
+  const int S = p->cfg.n_species;
+  APAX_CUDA_TRY(cudaMemsetAsync(w.sp_present, 0, sizeof(int32_t) * 128, stream));
+  APAX_LAUNCH(k_species_mark, dim3((unsigned)cdiv(N, 128)), dim3(128), 0, stream, Z, N, S, w.sp_present);
+  APAX_LAUNCH(k_species_build, dim3(1), dim3(256), 0, stream, w.sp_present, S, p->emb, w.sp_map, w.n_sp, w.embc);
+  return APAX_OK;
 }
 
 // ================================================================================================
@@ -542,7 +577,9 @@ __global__ void __launch_bounds__(256) k_force_gather(GmWorkspace ws, double* __
   }
   double tx = 0.0, ty = 0.0, tz = 0.0;
   for (int k = beg + sub; k < end; k += LPA) {
-    const float4 d = ws.D[ws.tpos[k]];
+    const int t = ws.tpos[k];
+    if (t < 0) continue;  // unmatched boundary pair of a symmetric list: zero contribution
+    const float4 d = ws.D[t];
     tx += double(d.x); ty += double(d.y); tz += double(d.z);
   }
 #pragma unroll

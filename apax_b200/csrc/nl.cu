@@ -25,6 +25,7 @@ size_t carve_nl_workspace(void* base, int64_t n_atoms, int64_t capacity, NlWorks
   w.cellptr = c.take<int32_t>(N + 1);
   w.cell_tmp = c.take<int32_t>(N);
   w.cell_atoms = c.take<int32_t>(N);
+  w.cell_pos = c.take<float4>(N);
   w.rowcnt = c.take<int32_t>(N + 1);
   w.rowptr = c.take<int32_t>(N + 1);
   w.rowptr_c = c.take<int32_t>(N + 1);
@@ -196,6 +197,16 @@ __device__ __forceinline__ void unpack_shift(int p, int& s0, int& s1, int& s2) {
   s0 = ((p >> 16) & 255) - 128; s1 = ((p >> 8) & 255) - 128; s2 = (p & 255) - 128;
 }
 
+// cell-ordered fp32 copy of the wrapped fractional positions: the candidate stream of the pre-filter below
+__global__ void __launch_bounds__(256) k_cell_pack(const double* __restrict__ pos, int64_t N,
+                                                   const int32_t* __restrict__ cell_atoms, float4* __restrict__ cell_pos) {
+  const int64_t t = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (t >= N) return;
+  const int j = cell_atoms[t];
+  const double x = pos[3 * int64_t(j)], y = pos[3 * int64_t(j) + 1], z = pos[3 * int64_t(j) + 2];
+  cell_pos[t] = make_float4(float(x - floor(x)), float(y - floor(y)), float(z - floor(z)), __int_as_float(j));
+}
+
 // Candidate scan of one atom by LG lanes.  FILL = false: count accepted pairs; FILL = true: append
 // them (order irrelevant, rows are sorted afterwards).
 template <int MODE, bool FILL>
@@ -217,6 +228,19 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
   }
   int wa[3] = {0, 0, 0};
   if (MODE == 1) { wa[0] = w.wrap[3 * atom]; wa[1] = w.wrap[3 * atom + 1]; wa[2] = w.wrap[3 * atom + 2]; }
+  // fp32 pre-filter (min-image mode): candidates whose approximate distance is outside cutoff +- delta are decided
+  // in fp32, only the thin shell around the cutoff pays for the exact fp64 predicate -- the pair set is unchanged.
+  float fa[3] = {0.f, 0.f, 0.f}, Bf[9], c2_lo = 0.f, c2_hi = 0.f;
+  if (MODE == 0) {
+    fa[0] = float(ax - floor(ax)); fa[1] = float(ay - floor(ay)); fa[2] = float(az - floor(az));
+    float bmax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { Bf[i] = float(g.B[i]); bmax = fmaxf(bmax, fabsf(Bf[i])); }
+    const float cut = sqrtf(float(g.cutoff_sq));
+    const float delta = 1e-3f + 4e-6f * bmax;   // >> fp32 error of wrapped fractional differences times |box|
+    c2_lo = (cut - delta) * (cut - delta);
+    c2_hi = (cut + delta) * (cut + delta);
+  }
   const int base = FILL ? w.rowptr[atom] : 0;
   int count = 0;
   const int m0 = valid ? g.m[0] : -1;
@@ -235,13 +259,29 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
         const int cid = (k0 * g.nc[1] + k1) * g.nc[2] + k2;
         const int cb = w.cellptr[cid], ce = w.cellptr[cid + 1];
         for (int t = cb + sub; t < ce; t += LG) {
-          const int j = w.cell_atoms[t];
-          const double bx = pos[3 * int64_t(j)], by = pos[3 * int64_t(j) + 1], bz = pos[3 * int64_t(j) + 2];
+          int j;
           bool keep;
           int packed = 0;
           if (MODE == 0) {
-            keep = (j != atom) && metric_sq_minimage(g.B, ax, ay, az, bx, by, bz) < g.cutoff_sq;
+            const float4 q = w.cell_pos[t];
+            j = __float_as_int(q.w);
+            float u0 = fa[0] - q.x, u1 = fa[1] - q.y, u2 = fa[2] - q.z;
+            u0 -= rintf(u0); u1 -= rintf(u1); u2 -= rintf(u2);
+            const float e0 = Bf[0] * u0 + Bf[1] * u1 + Bf[2] * u2;
+            const float e1 = Bf[3] * u0 + Bf[4] * u1 + Bf[5] * u2;
+            const float e2 = Bf[6] * u0 + Bf[7] * u1 + Bf[8] * u2;
+            const float d2f = e0 * e0 + e1 * e1 + e2 * e2;
+            if (d2f > c2_hi || j == atom) {
+              keep = false;
+            } else if (d2f < c2_lo) {
+              keep = true;
+            } else {
+              const double bx = pos[3 * int64_t(j)], by = pos[3 * int64_t(j) + 1], bz = pos[3 * int64_t(j) + 2];
+              keep = metric_sq_minimage(g.B, ax, ay, az, bx, by, bz) < g.cutoff_sq;
+            }
           } else {
+            j = w.cell_atoms[t];
+            const double bx = pos[3 * int64_t(j)], by = pos[3 * int64_t(j) + 1], bz = pos[3 * int64_t(j) + 2];
             // S such that D = r_c - r_i + S.cell for the image reached through box shift (s0,s1,s2)
             const int S0 = w.wrap[3 * int64_t(j)] - wa[0] - s0;
             const int S1 = w.wrap[3 * int64_t(j) + 1] - wa[1] - s1;
@@ -396,6 +436,7 @@ static int nl_build_common(cudaStream_t stream, const double* pos, const double*
   APAX_LAUNCH(k_cell_fill, dim3((unsigned)cdiv(N, 256)), dim3(256), 0, stream, N, w.cell_of, w.cellptr, w.cell_cnt,
               w.cell_tmp);
   APAX_TRY(rowsort_i32(stream, w.cellptr, N, w.cell_tmp, nullptr, w.cell_atoms, nullptr));
+  if (MODE == 0) APAX_LAUNCH(k_cell_pack, dim3((unsigned)cdiv(N, 256)), dim3(256), 0, stream, pos, N, w.cell_atoms, w.cell_pos);
   const dim3 grid_scan((unsigned)cdiv(N * LG, 256));
   APAX_CUDA_TRY(cudaMemsetAsync(w.rowcnt, 0, sizeof(int32_t) * (N + 1), stream));
   {

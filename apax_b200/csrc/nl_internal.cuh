@@ -25,6 +25,7 @@ struct NlWorkspace {
   int32_t* cellptr;     // [N+1]
   int32_t* cell_tmp;    // [N]
   int32_t* cell_atoms;  // [N] atoms of each cell, ascending
+  float4* cell_pos;     // [N] per cell slot: wrapped fractional position in fp32 + atom index (pre-filter stream)
   int32_t* rowcnt;      // [N+1]
   int32_t* rowptr;      // [N+1] (unclamped occupancy prefix)
   int32_t* rowptr_c;    // [N+1] clamped to capacity

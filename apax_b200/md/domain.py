@@ -207,6 +207,7 @@ def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: 
 
     torch.cuda.set_device(local)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ["NCCL_DEBUG"] = "WARN"   # NCCL otherwise prints its version banner on stdout, next to the JSON line
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_mol = args.molecules * (world if args.scaling == "weak" else 1)
     pos, Z, cell = syn.water_box(n_mol, 0)

@@ -307,13 +307,17 @@ class HostContext:
         check(lib().apax_ctx_create(params.handle, max_atoms, max_pairs, C.byref(self.handle)), "apax_ctx_create")
 
     def calculate(self, positions: np.ndarray, numbers: np.ndarray, cell: np.ndarray, dr_threshold: float = 0.0,
-                  rebuild: bool = False, forces: bool = True):
+                  rebuild: bool = False, forces: bool = True, out_forces: Optional[np.ndarray] = None):
+        """positions / numbers / out_forces may be views of page-locked memory (e.g. `torch.empty(...).pin_memory().numpy()`),
+        in which case the library copies from / into them directly without its staging buffer."""
         pos = np.ascontiguousarray(positions, dtype=np.float64)
         num = np.ascontiguousarray(numbers, dtype=np.int32)
         cel = np.ascontiguousarray(cell, dtype=np.float64)
         n = pos.shape[0]
         e = np.empty(self.params.n_out, dtype=np.float64)
-        f = np.empty((self.params.n_out, n, 3), dtype=np.float64) if forces else None
+        if out_forces is not None:
+            assert out_forces.dtype == np.float64 and out_forces.shape == (self.params.n_out, n, 3) and out_forces.flags.c_contiguous
+        f = (out_forces if out_forces is not None else np.empty((self.params.n_out, n, 3), dtype=np.float64)) if forces else None
         npairs = C.c_int64(0)
         code = lib().apax_ctx_calculate(self.handle, pos.ctypes.data_as(C.c_void_p), num.ctypes.data_as(C.c_void_p),
                                         cel.ctypes.data_as(C.c_void_p), n, float(dr_threshold), int(rebuild),
