@@ -172,24 +172,24 @@ __global__ void __launch_bounds__(256) k_csr_import(const int32_t* __restrict__ 
 __global__ void __launch_bounds__(256) k_transpose_symmetric(const int32_t* __restrict__ rowptr, int64_t N,
                                                              const int32_t* __restrict__ nbr, int32_t* __restrict__ trowptr,
                                                              int32_t* __restrict__ tpos) {
-  const int64_t s = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  if (s <= N) trowptr[s] = rowptr[s];
-  if (s >= rowptr[N]) return;
-  // row of slot s: binary search over rowptr
-  int lo = 0, hi = int(N);
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (rowptr[mid] <= s) lo = mid; else hi = mid;
+  // warp per row a: lanes take the row's slots; each looks its own atom up in the (sorted) row of the neighbour
+  const int64_t a = (int64_t(blockIdx.x) * 256 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a > N) return;
+  if (lane == 0) trowptr[a] = rowptr[a];
+  if (a == N) return;
+  const int rb = rowptr[a], re = rowptr[a + 1];
+  for (int s = rb + lane; s < re; s += 32) {
+    const int j = nbr[s];
+    int b = __ldg(rowptr + j), e = __ldg(rowptr + j + 1) - 1, found = -1;
+    while (b <= e) {
+      const int mid = (b + e) >> 1;
+      const int v = __ldg(nbr + mid);
+      if (v == int(a)) { found = mid; break; }
+      if (v < int(a)) b = mid + 1; else e = mid - 1;
+    }
+    tpos[s] = found;
   }
-  const int a = lo, j = nbr[s];
-  int b = rowptr[j], e = rowptr[j + 1] - 1, found = -1;
-  while (b <= e) {
-    const int mid = (b + e) >> 1;
-    const int v = nbr[mid];
-    if (v == a) { found = mid; break; }
-    if (v < a) b = mid + 1; else e = mid - 1;
-  }
-  tpos[s] = found;   // transpose row of a, entry k  <->  row a's own slot order
 }
 
 // transpose map + compact species table; expects w.rowptr / w.nbr final and w.tcnt = counts by neighbour
@@ -236,8 +236,8 @@ int gm_prepare_from_csr(cudaStream_t stream, const apax_gm_params_impl* p, const
   APAX_LAUNCH(k_csr_import, dim3((unsigned)cdiv(n, 256)), dim3(256), 0, stream, rowptr_in, nbr_in, N, P, w.rowptr, w.nbr,
               w.src, w.tcnt);
   if (!symmetric_sorted) return gm_prepare_tail(stream, p, w, Z);
-  APAX_LAUNCH(k_transpose_symmetric, dim3((unsigned)cdiv(n, 256)), dim3(256), 0, stream, w.rowptr, N, w.nbr, w.trowptr,
-              w.tpos);
+  APAX_LAUNCH(k_transpose_symmetric, dim3((unsigned)cdiv((N + 1) * 32, 256)), dim3(256), 0, stream, w.rowptr, N, w.nbr,
+              w.trowptr, w.tpos);
   const int S = p->cfg.n_species;
   APAX_CUDA_TRY(cudaMemsetAsync(w.sp_present, 0, sizeof(int32_t) * 128, stream));
   APAX_LAUNCH(k_species_mark, dim3((unsigned)cdiv(N, 128)), dim3(128), 0, stream, Z, N, S, w.sp_present);

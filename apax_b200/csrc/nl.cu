@@ -258,11 +258,15 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
         const int k2 = q2 - s2 * g.nc[2];
         const int cid = (k0 * g.nc[1] + k1) * g.nc[2] + k2;
         const int cb = w.cellptr[cid], ce = w.cellptr[cid + 1];
-        for (int t = cb + sub; t < ce; t += LG) {
-          int j;
-          bool keep;
+        for (int t0 = cb; t0 < ce; t0 += LG) {   // uniform trip count inside the lane group (ballot below)
+          const int t = t0 + sub;
+          const bool in_range = t < ce;
+          int j = 0;
+          bool keep = false;
           int packed = 0;
-          if (MODE == 0) {
+          if (!in_range) {
+            // nothing to test; still take part in the group ballot
+          } else if (MODE == 0) {
             const float4 q = w.cell_pos[t];
             j = __float_as_int(q.w);
             float u0 = fa[0] - q.x, u1 = fa[1] - q.y, u2 = fa[2] - q.z;
@@ -297,16 +301,20 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
                    S0 >= -127 && S0 <= 127 && S1 >= -127 && S1 <= 127 && S2 >= -127 && S2 <= 127;
             packed = pack_shift(S0, S1, S2);
           }
-          if (keep) {
-            if (FILL) {
-              const int slot = base + atomicAdd(&w.rowcnt[atom], 1);
+          if (FILL) {
+            // slot = running count of the lane group + rank of this lane among the accepting lanes: no atomics
+            const unsigned gmask = 0xffu << ((threadIdx.x & 31) / LG * LG);
+            const unsigned acc = (__ballot_sync(gmask, keep) >> ((threadIdx.x & 31) / LG * LG)) & 0xffu;
+            if (keep) {
+              const int slot = base + count + __popc(acc & ((1u << sub) - 1u));
               if (slot < w.capacity) {
                 w.nbr_tmp[slot] = j;
                 if (MODE == 1) w.shift_tmp[slot] = packed;
               }
-            } else {
-              ++count;
             }
+            count += __popc(acc);
+          } else if (keep) {
+            ++count;
           }
         }
       }
@@ -446,7 +454,6 @@ static int nl_build_common(cudaStream_t stream, const double* pos, const double*
   APAX_TRY(exclusive_scan_i32(stream, w.rowcnt, w.rowptr, N, w.scan_scratch));
   APAX_LAUNCH(k_nl_finish_count, dim3((unsigned)cdiv(N + 1, 256)), dim3(256), 0, stream, N, capacity, w.rowptr,
               w.rowptr_c, n_found, overflow);
-  APAX_CUDA_TRY(cudaMemsetAsync(w.rowcnt, 0, sizeof(int32_t) * (N + 1), stream));
   {
     auto k_nl_scan_fill = k_nl_scan<MODE, true>;
     APAX_LAUNCH(k_nl_scan_fill, grid_scan, dim3(256), 0, stream, pos, N, w.grid, w);

@@ -229,6 +229,13 @@ int apax_ctx_calculate(apax_ctx* ctx, const double* positions_host, const int32_
                        const double* cell_host, int64_t n_atoms, double dr_threshold, int32_t rebuild,
                        double* energy_host, double* forces_host, int64_t* n_pairs_host);
 
+/* Test entry of the exact integer tensor-core readout GEMM (tcgen05.mma kind::i8, four base-256 digit planes per
+ * operand, int32 accumulators): out[nc][ld] = act^T . wgt with act a device fp32 [k][ld] feature-major matrix and
+ * wgt a device fp32 [k][nc] matrix.  Replaces the fp32 matmuls of apax/layers/ntk_linear.py:40 inside the
+ * readout; allocates its own scratch, so it is for tests and measurements only. */
+int apax_i8_gemm_test(apax_stream_t stream, const float* act, int64_t k, int64_t ld, int64_t n_atoms, const float* wgt,
+                      int64_t nc, float* out, int32_t* err_flag);
+
 /* Readout GEMM building block on the tcgen05 tensor cores, exposed for tests and measurement:
  * out[nc][ld] = sum_k act[k][atom] * wgt[k][n] with both operands given as exact tf32 (hi, lo) pairs
  * (3xTF32, fp32-accurate; replaces jnp.dot in apax/layers/ntk_linear.py:40).  act_* f32 [k][ld],
