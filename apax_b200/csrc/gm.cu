@@ -13,10 +13,13 @@
 
 #include "contract_gen.cuh"
 #include "gm_internal.cuh"
+#include "i8_gemm.cuh"
 #include "tc_gemm.cuh"
 
 #include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 namespace apax {
 
@@ -829,6 +832,31 @@ __global__ void __launch_bounds__(128) k_head(const float* __restrict__ H2T, con
   ebar[m] = float(sc * msk);  // cotangent of h after the fp64->fp32 cast
 }
 
+// ---- the same tail when the output layer was already contracted in the GEMM epilogue (integer tensor-core
+// readout): h[k][m] = sum_n swish(y2)[n][m] w2[n][k]
+template <int NOUT>
+__global__ void __launch_bounds__(128) k_head_scale_shift(const float* __restrict__ hT, int64_t ld, int64_t N,
+                                                          const float* __restrict__ b2, int n_out,
+                                                          const int32_t* __restrict__ Z, int S,
+                                                          const double* __restrict__ scale, const double* __restrict__ shift,
+                                                          int mask_atoms, double* __restrict__ Eatom, float* __restrict__ ebar) {
+  const int64_t m = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  if (m >= ld) return;
+  if (m >= N) {
+    ebar[m] = 0.0f;
+    for (int k = 0; k < n_out; ++k) Eatom[int64_t(k) * ld + m] = 0.0;
+    return;
+  }
+  int z = Z[m];
+  const double msk = (mask_atoms && z == 0) ? 0.0 : 1.0;
+  z = z < 0 ? 0 : (z >= S ? S - 1 : z);
+  const double sc = scale[z], sh = shift[z];
+#pragma unroll
+  for (int k = 0; k < NOUT; ++k)
+    if (k < n_out) Eatom[int64_t(k) * ld + m] = (sc * double(hT[int64_t(k) * ld + m] + b2[k]) + sh) * msk;
+  ebar[m] = float(sc * msk);
+}
+
 __device__ __forceinline__ int64_t cdiv_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- dE/dy2 = ebar * w2[:,head] * swish'(y2) as an exact (tf32 hi, lo) pair: input of the backward tensor-core GEMM
@@ -972,13 +1000,26 @@ static int gm_descriptor_impl(cudaStream_t stream, const apax_gm_params_impl* p,
 // 1e-6 energy tolerance.  APAX_B200_READOUT=tc selects the tcgen05 3xTF32 tensor-core GEMMs: measured on B200
 // they are ~1e-6 accurate per output but BIASED (the tensor core's fp32 accumulator truncates instead of
 // rounding), which adds up coherently to ~8e-6 relative on total energies.
-static bool readout_on_tensor_cores() {
+enum { READOUT_SIMT = 0, READOUT_TC = 1, READOUT_I8 = 2 };
+static int readout_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("APAX_B200_READOUT");
-    mode = (e && strcmp(e, "tc") == 0) ? 1 : 0;
+    mode = (e && strcmp(e, "tc") == 0) ? READOUT_TC : (e && strcmp(e, "i8") == 0) ? READOUT_I8 : READOUT_SIMT;
   }
-  return mode == 1;
+  return mode;
+}
+
+static int energy_sums(cudaStream_t stream, const GmWorkspace& w, int n_out, double* energy) {
+  const int64_t N = w.n_central, ld = w.ld;
+  if (w.n_seg > 0) {
+    APAX_LAUNCH(k_energy_segments, dim3((unsigned)w.n_seg, n_out), dim3(32), 0, stream, w.Eatom, ld, w.seg_ptr, n_out, energy);
+    return APAX_OK;
+  }
+  const int n_blk = int(N < 256 * 64 ? 1 : (N / (256 * 64) > 256 ? 256 : N / (256 * 64)));
+  APAX_LAUNCH(k_energy_partial, dim3(n_blk, n_out), dim3(256), 0, stream, w.Eatom, ld, N, w.partial);
+  APAX_LAUNCH(k_energy_final, dim3(n_out), dim3(32), 0, stream, w.partial, n_blk, energy);
+  return APAX_OK;
 }
 
 static int readout_head_and_energy(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w,
@@ -993,14 +1034,7 @@ static int readout_head_and_energy(cudaStream_t stream, const apax_gm_params_imp
     APAX_LAUNCH(k_head<MAX_OUT>, dim3((unsigned)m_tiles), dim3(128), 0, stream, w.H2T, h2_lo, ld, N, p->w2, p->b2,
                 n_out, geo.Z, p->cfg.n_species, p->scale, p->shift, p->cfg.mask_atoms, w.Eatom, w.ebar);
   }
-  if (w.n_seg > 0) {
-    APAX_LAUNCH(k_energy_segments, dim3((unsigned)w.n_seg, n_out), dim3(32), 0, stream, w.Eatom, ld, w.seg_ptr, n_out, energy);
-    return APAX_OK;
-  }
-  const int n_blk = int(N < 256 * 64 ? 1 : (N / (256 * 64) > 256 ? 256 : N / (256 * 64)));
-  APAX_LAUNCH(k_energy_partial, dim3(n_blk, n_out), dim3(256), 0, stream, w.Eatom, ld, N, w.partial);
-  APAX_LAUNCH(k_energy_final, dim3(n_out), dim3(32), 0, stream, w.partial, n_blk, energy);
-  return APAX_OK;
+  return energy_sums(stream, w, n_out, energy);
 }
 
 // ---- readout forward + (per head) backward down to dE/dg in GT, on the fp32 CUDA cores
@@ -1080,21 +1114,89 @@ static int readout_tc(cudaStream_t stream, const apax_gm_params_impl* p, const G
   return APAX_OK;
 }
 
+// ---- the same on the integer tensor cores (i8_gemm.cuh): activations travel between the four GEMMs as base-256
+// digit planes written by the epilogues; fp32 copies exist only of swish'(y1) (D1T) and of dE/dg (GT).
+// Buffer reuse: descriptor planes in GLT, swish(y1) / dE/dy1 planes in H1LT, swish'(y2) planes in H2LT, the epilogue
+// staging in H2T, and head sums + row exponents in the first rows of H1T (none of these hold fp32 data here).
+static int readout_i8(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const PairGeom& geo,
+                      double* energy, int head) {
+  const int64_t N = w.n_central, ld = w.ld;
+  const int n_out = p->cfg.n_out;
+  int8_t* gq = reinterpret_cast<int8_t*>(w.GLT);
+  int8_t* h1q = reinterpret_cast<int8_t*>(w.H1LT);
+  int8_t* d2q = reinterpret_cast<int8_t*>(w.H2LT);
+  float* h_out = w.H1T;                                                   // [n_out <= 16][ld]
+  int32_t* e_g = reinterpret_cast<int32_t*>(w.H1T + int64_t(MAX_OUT) * ld);
+  int32_t* e_h1 = e_g + ld;
+  int32_t* e_x1 = e_h1 + ld;
+  int32_t* rowmax = e_x1 + ld;
+  const I8Planes w0{p->q_w0, NH, NFP, int64_t(NH) * NFP, 4}, w1{p->q_w1, NH, NH, int64_t(NH) * NH, 4};
+  if (head < 0) {
+    APAX_TRY(i8_quantize_rows(stream, w.GT, ld, N, NF, NFP, 3, p->cs_g, gq, e_g, rowmax));
+    {  // layer 0: 360 -> 256; swish' kept in fp32 for the backward pass, swish goes on as digit planes
+      const I8Planes act{gq, ld, NFP, ld * int64_t(NFP), 3};
+      I8Epilogue e{};
+      e.mode = I8_EPI_ACT_Q; e.ld = ld; e.n_valid = NH; e.row_exp = e_g; e.bias = p->b0; e.aux = w.D1T;
+      e.q_planes = h1q; e.q_kp = NH; e.q_plane_stride = ld * int64_t(NH); e.q_col_scale = p->cs_h1; e.q_row_exp = e_h1;
+      e.scratch = w.H2T;
+      APAX_TRY(i8_gemm(stream, act, w0, e, p->tc_err));
+    }
+    {  // layer 1: 256 -> 256, output layer contracted in the epilogue; swish' goes on as fixed-scale digit planes
+      const I8Planes act{h1q, ld, NH, ld * int64_t(NH), 4};
+      I8Epilogue e{};
+      e.mode = I8_EPI_ACT_HEAD; e.ld = ld; e.n_valid = NH; e.row_exp = e_h1; e.bias = p->b1;
+      e.q_planes = d2q; e.q_kp = NH; e.q_plane_stride = ld * int64_t(NH); e.q_col_scale = p->cs_d2; e.q_fixed_exp = p->d2_exp;
+      e.w_head = p->w2; e.n_out = n_out; e.h_out = h_out;
+      APAX_TRY(i8_gemm(stream, act, w1, e, p->tc_err));
+    }
+    const int64_t m_tiles = cdiv(N, 128);
+    if (n_out == 1) {
+      APAX_LAUNCH(k_head_scale_shift<1>, dim3((unsigned)m_tiles), dim3(128), 0, stream, h_out, ld, N, p->b2, n_out, geo.Z,
+                  p->cfg.n_species, p->scale, p->shift, p->cfg.mask_atoms, w.Eatom, w.ebar);
+    } else {
+      APAX_LAUNCH(k_head_scale_shift<MAX_OUT>, dim3((unsigned)m_tiles), dim3(128), 0, stream, h_out, ld, N, p->b2, n_out,
+                  geo.Z, p->cfg.n_species, p->scale, p->shift, p->cfg.mask_atoms, w.Eatom, w.ebar);
+    }
+    return energy_sums(stream, w, n_out, energy);
+  }
+  {  // dE/dy1 = swish'(y1) * ebar * (W1 w2[head]) . swish'(y2)  -> digit planes
+    const I8Planes act{d2q, ld, NH, ld * int64_t(NH), 4};
+    const I8Planes wth{p->q_w1th + size_t(head) * 4 * NH * NH, NH, NH, int64_t(NH) * NH, 4};
+    I8Epilogue e{};
+    e.mode = I8_EPI_MULD_Q; e.ld = ld; e.n_valid = NH; e.row_exp = nullptr; e.fixed_exp = p->d2_exp; e.aux = w.D1T;
+    e.row_mul = w.ebar;
+    e.q_planes = h1q; e.q_kp = NH; e.q_plane_stride = ld * int64_t(NH); e.q_col_scale = p->cs_x1; e.q_row_exp = e_x1;
+    e.scratch = w.H2T;
+    APAX_TRY(i8_gemm(stream, act, wth, e, p->tc_err));
+  }
+  {  // dE/dg = W0 . dE/dy1 (384 padded rows, fp32 for the contraction backward)
+    const I8Planes act{h1q, ld, NH, ld * int64_t(NH), 4};
+    const I8Planes w0t{p->q_w0t, NFP, NH, int64_t(NFP) * NH, 4};
+    I8Epilogue e{};
+    e.mode = I8_EPI_STORE; e.ld = ld; e.n_valid = NFP; e.row_exp = e_x1; e.out = w.GT;
+    APAX_TRY(i8_gemm(stream, act, w0t, e, p->tc_err));
+  }
+  return APAX_OK;
+}
+
 static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w,
                            const PairGeom& geo, double* energy, double* forces) {
   const int64_t N = w.n_central;  // per-central work only; ghosts enter as neighbours
   const int n_out = p->cfg.n_out;
   const DescConst dc = make_desc_const(p->cfg);
   const int lpa = pick_lpa(N);
-  const bool tc = readout_on_tensor_cores();
-  APAX_TRY(gm_descriptor_impl(stream, p, w, geo, tc));
-  APAX_TRY(tc ? readout_tc(stream, p, w, geo, energy, -1) : readout_simt(stream, p, w, geo, energy, -1));
+  const int mode = readout_mode();
+  auto readout = [&](int head) {
+    return mode == READOUT_I8   ? readout_i8(stream, p, w, geo, energy, head)
+           : mode == READOUT_TC ? readout_tc(stream, p, w, geo, energy, head)
+                                : readout_simt(stream, p, w, geo, energy, head);
+  };
+  APAX_TRY(gm_descriptor_impl(stream, p, w, geo, mode == READOUT_TC));
+  APAX_TRY(readout(-1));
   if (!forces) return APAX_OK;
   for (int head = 0; head < n_out; ++head) {
-    if (tc && head > 0) {
-      // the previous head's backward overwrote H2 (dE/dy2) only; D1/D2/ebar are intact -- nothing to redo
-    }
-    APAX_TRY(tc ? readout_tc(stream, p, w, geo, energy, head) : readout_simt(stream, p, w, geo, energy, head));
+    // every backward pass reads only what the forward pass left behind (D1, D2 / its planes, ebar): nothing to redo
+    APAX_TRY(readout(head));
     APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(N, kContractThreads)), dim3(kContractThreads), 0, stream, w);
     APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc);
     APAX_DISPATCH_LPA(pick_lpa(w.n_atoms), launch_force_gather, stream, w, forces + int64_t(head) * w.n_atoms * 3);
@@ -1228,6 +1330,46 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
     APAX_TRY(split_upload(&p->w1t_hi, &p->w1t_lo, NH, NH, [&](int n, int k) { return f1 * w1[size_t(k) * NH + n]; }));
     APAX_TRY(split_upload(&p->w0t_hi, &p->w0t_lo, NH, NFP,
                           [&](int n, int k) { return k < NF ? f0 * w0[size_t(k) * NH + n] : 0.0f; }));
+    {  // digit planes of the same weights for the integer tensor-core readout
+      std::vector<float> W;
+      std::vector<int8_t> planes;
+      std::vector<float> cs;
+      W.assign(size_t(NF) * NH, 0.0f);
+      for (int k = 0; k < NF; ++k)
+        for (int n = 0; n < NH; ++n) W[size_t(k) * NH + n] = f0 * w0[size_t(k) * NH + n];
+      i8_quantize_weights(W.data(), NF, NH, NH, NFP, NH, planes, cs);
+      APAX_TRY(upload(&p->q_w0, planes.data(), planes.size()));
+      APAX_TRY(upload(&p->cs_g, cs.data(), cs.size()));
+      W.assign(size_t(NH) * NH, 0.0f);
+      for (int k = 0; k < NH; ++k)
+        for (int n = 0; n < NH; ++n) W[size_t(k) * NH + n] = f1 * w1[size_t(k) * NH + n];
+      i8_quantize_weights(W.data(), NH, NH, NH, NH, NH, planes, cs);
+      APAX_TRY(upload(&p->q_w1, planes.data(), planes.size()));
+      APAX_TRY(upload(&p->cs_h1, cs.data(), cs.size()));
+      // backward layer 1: one weight matrix per head, one scale vector for all of them
+      std::vector<float> Wh(size_t(n_out) * NH * NH);
+      for (int hd = 0; hd < n_out; ++hd)
+        for (int k = 0; k < NH; ++k)
+          for (int n = 0; n < NH; ++n)
+            Wh[(size_t(hd) * NH + k) * NH + n] = (f1 * w1[size_t(n) * NH + k]) * (f1 * w2[size_t(k) * n_out + hd]);
+      for (int hd = 0; hd < n_out; ++hd) i8_weight_scales(Wh.data() + size_t(hd) * NH * NH, NH, NH, NH, NH, cs, hd > 0);
+      std::vector<int8_t> all;
+      for (int hd = 0; hd < n_out; ++hd) {
+        i8_quantize_weights(Wh.data() + size_t(hd) * NH * NH, NH, NH, NH, NH, NH, planes, cs, true);
+        all.insert(all.end(), planes.begin(), planes.end());
+      }
+      APAX_TRY(upload(&p->q_w1th, all.data(), all.size()));
+      APAX_TRY(upload(&p->cs_d2, cs.data(), cs.size()));
+      float cmax = 0.0f;
+      for (int k = 0; k < NH; ++k) cmax = fmaxf(cmax, cs[k]);
+      p->d2_exp = int(ceil(log2(1.85 * double(cmax) / 63.0)));   // |swish'| <= 1.845: every scaled value stays below 64
+      W.assign(size_t(NH) * NFP, 0.0f);
+      for (int n = 0; n < NH; ++n)
+        for (int k = 0; k < NF; ++k) W[size_t(n) * NFP + k] = f0 * w0[size_t(k) * NH + n];
+      i8_quantize_weights(W.data(), NH, NFP, NFP, NH, NFP, planes, cs);
+      APAX_TRY(upload(&p->q_w0t, planes.data(), planes.size()));
+      APAX_TRY(upload(&p->cs_x1, cs.data(), cs.size()));
+    }
     APAX_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&p->tc_err), sizeof(int32_t)));
     APAX_CUDA_TRY(cudaMemset(p->tc_err, 0, sizeof(int32_t)));
     const double eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -1245,6 +1387,8 @@ extern "C" void apax_gm_params_destroy(apax_gm_params* p) {
   cudaFree(p->eye);
   cudaFree(p->w0_hi); cudaFree(p->w0_lo); cudaFree(p->w1_hi); cudaFree(p->w1_lo); cudaFree(p->w1t_hi);
   cudaFree(p->w1t_lo); cudaFree(p->w0t_hi); cudaFree(p->w0t_lo); cudaFree(p->tc_err);
+  cudaFree(p->q_w0); cudaFree(p->q_w1); cudaFree(p->q_w1th); cudaFree(p->q_w0t);
+  cudaFree(p->cs_g); cudaFree(p->cs_h1); cudaFree(p->cs_d2); cudaFree(p->cs_x1);
   delete p;
 }
 

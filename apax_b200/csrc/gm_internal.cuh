@@ -35,6 +35,16 @@ struct apax_gm_params_impl {
   float *w1t_hi, *w1t_lo;  // [256][256]
   float *w0t_hi, *w0t_lo;  // [256][384]
   int32_t* tc_err;         // [1] set by the tensor-core pipeline on a barrier time-out
+  // integer tensor-core readout (i8_gemm.cuh): weight digit planes [4][outputs][k] and per-feature scales
+  int8_t* q_w0;     // [4][256][384]          layer 0
+  int8_t* q_w1;     // [4][256][256]          layer 1
+  int8_t* q_w1th;   // [n_out][4][256][256]   backward through layer 1, head weights folded in
+  int8_t* q_w0t;    // [4][384][256]          backward through layer 0
+  float* cs_g;      // [384] scales of the descriptor features (layer 0 reduction)
+  float* cs_h1;     // [256] scales of swish(y1)          (layer 1 reduction)
+  float* cs_d2;     // [256] scales of swish'(y2)         (backward layer 1 reduction), shared by all heads
+  float* cs_x1;     // [256] scales of dE/dy1             (backward layer 0 reduction)
+  int d2_exp;       // exponent shared by every row of the swish'(y2) planes (|swish'| <= 1.85)
   double* eye;             // [3][3] identity (displacement box of Cartesian batched evaluation)
 };
 

@@ -11,13 +11,17 @@ namespace {
 
 using namespace tcptx;
 
-constexpr uint32_t I8_PLANE_TILE = I8_BM * I8_KC;                       // 8 KB: 128 rows x 64 bytes
-constexpr uint32_t I8_STAGE_BYTES = 2 * I8_DIGITS * I8_PLANE_TILE;       // 4 A planes + 4 B planes = 64 KB
-constexpr uint32_t I8_SMEM_BYTES = I8_STAGES * I8_STAGE_BYTES + 1024;   // + slack for 1024-byte alignment
-constexpr uint32_t I8_TMEM_COLS = I8_DIGITS * I8_BN;                     // 512
-constexpr float kSwishI8 = 1.6765324703310907f;                          // apax/layers/activation.py:8
-
-static_assert(I8_BM == I8_BN, "A and B plane tiles share one size");
+constexpr uint32_t I8_A_TILE = I8_BM * I8_KC;                  // 8 KB: 128 atoms x 64 bytes of one plane
+constexpr uint32_t I8_B_TILE = I8_BN * I8_KC;                  // 4 KB: 64 outputs x 64 bytes of one plane
+constexpr uint32_t I8_B_STAGE = I8_DIGITS * I8_B_TILE;         // 16 KB: one k-block of the four weight planes
+constexpr uint32_t I8_ACC_COLS = I8_DIGITS * I8_BN;            // 256 columns: one accumulator set (orders 0..3)
+constexpr uint32_t I8_TMEM_COLS = 2 * I8_ACC_COLS;             // two sets = the SM's whole tensor memory
+constexpr int I8_MAX_B_STAGES = 8;
+constexpr int I8_EPI_WARPS = 8;                                // two warps per TMEM lane quarter
+constexpr int I8_EPI_THREADS = 32 * I8_EPI_WARPS;
+constexpr int I8_THREADS = 64 + I8_EPI_THREADS;                // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr uint32_t I8_SMEM_LIMIT = 232448;                     // 227 KB per CTA
+constexpr float kSwishI8 = 1.6765324703310907f;                // apax/layers/activation.py:8
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_64B (cute::UMMA::LayoutType::SWIZZLE_64B = 4): rows of 64
 // bytes, 8-row atoms 512 bytes apart (stride byte offset); the leading byte offset is unused for swizzled
@@ -38,26 +42,130 @@ __device__ __forceinline__ float exp2_int(int e) {
   return ldexpf(1.0f, e);
 }
 
-__global__ void __launch_bounds__(128) k_i8_gemm(const __grid_constant__ CUtensorMap tm_a,
-                                                 const __grid_constant__ CUtensorMap tm_b, int num_k_blocks,
-                                                 I8Epilogue epi, int32_t* err) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// one elected lane of a fully converged warp (the MMA / TMA warps run warp-uniform code so that descriptors and
+// loop state stay in uniform registers; only the issuing instructions are predicated on the elected lane)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// whole-warp wait with a warp-uniform result
+__device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity, int32_t* err) {
+  return __all_sync(0xffffffffu, mbar_wait(bar, parity, err));
+}
+__device__ __forceinline__ void epi_bar_sync() {   // named barrier 1: the 256 epilogue threads only
+  asm volatile("bar.sync 1, %0;" ::"n"(I8_EPI_THREADS) : "memory");
+}
+
+// ---- digits.  Balanced base-256 digits of I = rn(v), all at once: adding 128 to each low byte (with the
+// carries that produces) turns the balanced digits into offset-binary bytes, flipping their top bits back gives
+// two's complement.  P digits: byte P-1 = leading digit d0 ... byte 0 = d_{P-1}.
+template <int P>
+__device__ __forceinline__ uint32_t i8_digit_word(float v) {
+  constexpr uint32_t kOff = P == 4 ? 0x00808080u : 0x00008080u;
+  return (uint32_t(__float2int_rn(v)) + kOff) ^ kOff;   // |I| < 2^(8 P - 2)
+}
+// 4 x 4 byte transpose: words e[j] of elements j = 0..3  ->  tb[b] = byte b of the four elements (element 0 lowest)
+__device__ __forceinline__ void i8_transpose4(const uint32_t (&e)[4], uint32_t (&tb)[4]) {
+  const uint32_t t0 = __byte_perm(e[0], e[1], 0x5140);  // e0.b0 e1.b0 e0.b1 e1.b1
+  const uint32_t t1 = __byte_perm(e[2], e[3], 0x5140);
+  const uint32_t t2 = __byte_perm(e[0], e[1], 0x7362);  // e0.b2 e1.b2 e0.b3 e1.b3
+  const uint32_t t3 = __byte_perm(e[2], e[3], 0x7362);
+  tb[0] = __byte_perm(t0, t1, 0x5410);
+  tb[1] = __byte_perm(t0, t1, 0x7632);
+  tb[2] = __byte_perm(t2, t3, 0x5410);
+  tb[3] = __byte_perm(t2, t3, 0x7632);
+}
+
+// exponent e (row maximum 2^-e in [32, 64)) and two in-range powers of two whose product is 2^(8 (P - 1) - e)
+__device__ __forceinline__ void i8_row_scale(float mx, int P, int& e, float& sc, float& sc2) {
+  e = 0;
+  sc = 0.0f;
+  sc2 = 0.0f;                         // zero / padding / non-finite rows quantise to all-zero digits
+  if (mx > 0.0f && mx < 3.0e38f) {
+    int ex;
+    frexpf(mx, &ex);                  // mx = f 2^ex, f in [0.5, 1)
+    e = ex - 6;
+    const int tot = 8 * (P - 1) - e, h = tot / 2;
+    sc = exp2_int(h);
+    sc2 = exp2_int(tot - h);
+  }
+}
+
+// sixteen values (already multiplied by their column scales) -> four 16-byte plane pieces at planes + p * stride
+__device__ __forceinline__ void i8_emit16(const float (&v)[16], float sc, float sc2, int8_t* dst, int64_t plane_stride) {
+  uint32_t w[I8_DIGITS][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t ew[4], tb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ew[j] = i8_digit_word<4>((v[4 * q + j] * sc) * sc2);
+    i8_transpose4(ew, tb);
+#pragma unroll
+    for (int d = 0; d < I8_DIGITS; ++d) w[d][q] = tb[3 - d];
+  }
+#pragma unroll
+  for (int d = 0; d < I8_DIGITS; ++d)
+    *reinterpret_cast<uint4*>(dst + d * plane_stride) = make_uint4(w[d][0], w[d][1], w[d][2], w[d][3]);
+}
+
+// int32 accumulators of the four orders -> fp32.  Order 0 (|.| < 2^22) and the rounded-down tails of orders 2 and 3
+// go through the exact magic-number conversion on the ALU pipes, order 1 through I2F; the shifts drop at most
+// 2^-15 of an order-0 unit, far below the fp32 rounding of the result.
+__device__ __forceinline__ float i8_combine(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23
+  const float f0 = __int_as_float(int(r0) + 0x4B400000) - kMagic;
+  const float f1 = float(int(r1));
+  const float f2 = __int_as_float(((int(r2) + 2) >> 2) + 0x4B400000) - kMagic;   // units of 4
+  const float f3 = __int_as_float(((int(r3) + 8) >> 4) + 0x4B400000) - kMagic;   // units of 16
+  float t = fmaf(f3, 16.0f / 256.0f / 4.0f, f2);   // in units of 4 * 256^-2
+  t = fmaf(t, 4.0f / 256.0f, f1);                   // in units of 256^-1
+  return fmaf(t, 1.0f / 256.0f, f0);
+}
+
+// ================================================================================================
+// The GEMM.  MODE: epilogue (I8_EPI_*), NOUT: heads accumulated by I8_EPI_ACT_HEAD (1 or I8_MAX_HEADS).
+// ================================================================================================
+template <int MODE, int NOUT>
+__global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant__ CUtensorMap tm_a,
+                                                           const __grid_constant__ CUtensorMap tm_b, int num_kb,
+                                                           int a_planes, int num_m_tiles, int num_n_sub, int b_stages,
+                                                           I8Epilogue epi, int32_t* err) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[I8_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[I8_STAGES];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t a_full[I8_MAX_KB];
+  __shared__ __align__(8) uint64_t a_empty[I8_MAX_KB];
+  __shared__ __align__(8) uint64_t b_full[I8_MAX_B_STAGES];
+  __shared__ __align__(8) uint64_t b_empty[I8_MAX_B_STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float xmax[2][I8_BM];            // row-maximum exchange between the two column halves
+  __shared__ float xhead[I8_BM * NOUT];       // head partial sums of the second column half
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int m0 = blockIdx.x * I8_BM;
-  const int n0 = blockIdx.y * I8_BN;
+  const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_b = smem_a + uint32_t(num_kb * a_planes) * I8_A_TILE;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < I8_STAGES; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+    for (int i = 0; i < I8_MAX_KB; ++i) {
+      mbar_init(smem_u32(&a_full[i]), 1);
+      mbar_init(smem_u32(&a_empty[i]), 1);
     }
-    mbar_init(smem_u32(&accum_bar), 1);
+    for (int i = 0; i < I8_MAX_B_STAGES; ++i) {
+      mbar_init(smem_u32(&b_full[i]), 1);
+      mbar_init(smem_u32(&b_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&acc_full[i]), 1);
+      mbar_init(smem_u32(&acc_empty[i]), I8_EPI_THREADS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -70,95 +178,225 @@ __global__ void __launch_bounds__(128) k_i8_gemm(const __grid_constant__ CUtenso
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_slot;
+  const int my_m_tiles = (num_m_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    for (int kb = 0; kb < num_k_blocks; ++kb) {
-      const int s = kb % I8_STAGES;
-      const uint32_t phase = (kb / I8_STAGES) & 1;
-      if (!mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1, err)) break;
-      const uint32_t stage = smem_base + s * I8_STAGE_BYTES;
-      const uint32_t bar = smem_u32(&full_bar[s]);
-      mbar_expect_tx(bar, I8_STAGE_BYTES);
-      const int k0 = kb * I8_KC;
-#pragma unroll
-      for (int d = 0; d < I8_DIGITS; ++d) {
-        tma_load_3d(stage + d * I8_PLANE_TILE, &tm_a, bar, k0, m0, d);
-        tma_load_3d(stage + (I8_DIGITS + d) * I8_PLANE_TILE, &tm_b, bar, k0, n0, d);
-      }
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    constexpr uint32_t idesc = make_idesc_i8(I8_BM, I8_BN);
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (warp-uniform, elected lane issues)
+    uint32_t bit = 0;
     bool ok = true;
-    for (int kb = 0; kb < num_k_blocks && ok; ++kb) {
-      const int s = kb % I8_STAGES;
-      const uint32_t phase = (kb / I8_STAGES) & 1;
-      ok = mbar_wait(smem_u32(&full_bar[s]), phase, err);
-      if (!ok) break;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t stage = smem_base + s * I8_STAGE_BYTES;
+    for (int mt = 0; mt < my_m_tiles && ok; ++mt) {
+      const int m0 = (int(blockIdx.x) + mt * int(gridDim.x)) * I8_BM;
+      for (int j = 0; j < num_n_sub && ok; ++j) {
+        for (int kb = 0; kb < num_kb; ++kb, ++bit) {
+          if (j == 0) {   // the atom tile's planes of this k-block: resident for the whole output sweep
+            ok = mbar_wait_warp(smem_u32(&a_empty[kb]), (uint32_t(mt) & 1) ^ 1, err);
+            if (!ok) break;
+            if (elect_one()) {
+              const uint32_t bar = smem_u32(&a_full[kb]);
+              mbar_expect_tx(bar, uint32_t(a_planes) * I8_A_TILE);
+              for (int d = 0; d < a_planes; ++d)
+                tma_load_3d(smem_a + uint32_t(kb * a_planes + d) * I8_A_TILE, &tm_a, bar, kb * I8_KC, m0, d);
+            }
+            __syncwarp();
+          }
+          const uint32_t s = bit % uint32_t(b_stages), phase = (bit / uint32_t(b_stages)) & 1;
+          ok = mbar_wait_warp(smem_u32(&b_empty[s]), phase ^ 1, err);
+          if (!ok) break;
+          if (elect_one()) {
+            const uint32_t bar = smem_u32(&b_full[s]);
+            mbar_expect_tx(bar, I8_B_STAGE);
 #pragma unroll
-      for (int kk = 0; kk < I8_KC / 32; ++kk) {
-        uint64_t a[I8_DIGITS], b[I8_DIGITS];
-#pragma unroll
-        for (int d = 0; d < I8_DIGITS; ++d) {
-          a[d] = make_desc_k_sw64(stage + d * I8_PLANE_TILE + kk * 32);
-          b[d] = make_desc_k_sw64(stage + (I8_DIGITS + d) * I8_PLANE_TILE + kk * 32);
-        }
-        const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-        // digit pair (s, t) contributes to order o = s + t; orders above 3 are below 2^-32 and dropped
-#pragma unroll
-        for (int o = 0; o < I8_DIGITS; ++o) {
-#pragma unroll
-          for (int sa = 0; sa <= o; ++sa) umma_i8(tmem_d + o * I8_BN, a[sa], b[o - sa], idesc, sa == 0 ? acc : 1u);
+            for (int d = 0; d < I8_DIGITS; ++d)
+              tma_load_3d(smem_b + s * I8_B_STAGE + d * I8_B_TILE, &tm_b, bar, kb * I8_KC, j * I8_BN, d);
+          }
+          __syncwarp();
         }
       }
-      umma_commit(smem_u32(&empty_bar[s]));  // frees the stage when the MMAs above have read it
     }
-    umma_commit(smem_u32(&accum_bar));
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform, elected lane issues)
+    constexpr uint32_t idesc = make_idesc_i8(I8_BM, I8_BN);
+    uint32_t bit = 0, tile = 0;
+    bool ok = true;
+    long long w_acc = 0, w_a = 0, w_b = 0, t_begin = clock64();
+    for (int mt = 0; mt < my_m_tiles && ok; ++mt) {
+      for (int j = 0; j < num_n_sub && ok; ++j, ++tile) {
+        const uint32_t buf = tile & 1, use = tile >> 1;
+        long long c0 = clock64();
+        ok = mbar_wait_warp(smem_u32(&acc_empty[buf]), (use & 1) ^ 1, err);   // epilogue has drained this set
+        w_acc += clock64() - c0;
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc_base = tmem_d + buf * I8_ACC_COLS;
+        for (int kb = 0; kb < num_kb; ++kb, ++bit) {
+          if (j == 0) {
+            c0 = clock64();
+            ok = mbar_wait_warp(smem_u32(&a_full[kb]), uint32_t(mt) & 1, err);
+            w_a += clock64() - c0;
+            if (!ok) break;
+          }
+          const uint32_t s = bit % uint32_t(b_stages), phase = (bit / uint32_t(b_stages)) & 1;
+          c0 = clock64();
+          ok = mbar_wait_warp(smem_u32(&b_full[s]), phase, err);
+          w_b += clock64() - c0;
+          if (!ok) break;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          // descriptors of plane d / k-slice kk differ from the first one only in the 16-byte-unit start address
+          const uint64_t a0 = make_desc_k_sw64(smem_a + uint32_t(kb * a_planes) * I8_A_TILE);
+          const uint64_t b0 = make_desc_k_sw64(smem_b + s * I8_B_STAGE);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < I8_KC / 32; ++kk) {
+              const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
+              // digit pair (s, t) contributes to order o = s + t; orders above 3 are below 2^-32 and dropped
+#pragma unroll
+              for (int o = 0; o < I8_DIGITS; ++o) {
+#pragma unroll
+                for (int sa = 0; sa <= o; ++sa)
+                  if (sa < a_planes)
+                    umma_i8(acc_base + o * I8_BN, a0 + uint64_t((sa * I8_A_TILE + kk * 32) >> 4),
+                            b0 + uint64_t(((o - sa) * I8_B_TILE + kk * 32) >> 4), idesc, sa == 0 ? acc : 1u);
+              }
+            }
+            umma_commit(smem_u32(&b_empty[s]));                          // weight stage free once these MMAs have read it
+            if (j == num_n_sub - 1) umma_commit(smem_u32(&a_empty[kb]));  // last sweep over this atom k-block
+            if (kb == num_kb - 1) umma_commit(smem_u32(&acc_full[buf]));
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (epi.dbg && lane == 0) {
+      epi.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
+      epi.dbg[blockIdx.x * 8 + 1] = w_acc;
+      epi.dbg[blockIdx.x * 8 + 2] = w_b;
+      epi.dbg[blockIdx.x * 8 + 3] = w_a;
+    }
+  } else {
+    // -------------------------------------------------------------------- epilogue warps: lane == atom
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;          // the two warps of a quarter split the 64 columns
+    const int row = q * 32 + lane;
+    float* scratch = (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_MULD_Q)
+                         ? epi.scratch + int64_t(blockIdx.x) * num_n_sub * I8_BN * I8_BM + row
+                         : nullptr;
+    uint32_t tile = 0;
+    bool ok = true;
+    long long w_wait = 0, t_begin = clock64();
+    for (int mt = 0; mt < my_m_tiles && ok; ++mt) {
+      const int64_t m = int64_t(int(blockIdx.x) + mt * int(gridDim.x)) * I8_BM + row;
+      const float scale = exp2_int(epi.row_exp ? epi.row_exp[m] : epi.fixed_exp);
+      const float rmul = (MODE == I8_EPI_MULD_Q && epi.row_mul) ? epi.row_mul[m] : 1.0f;
+      float mx = 0.0f;
+      float hacc[NOUT];
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) hacc[k] = 0.0f;
+      float qsc = 0.0f, qsc2 = 0.0f;
+      if (MODE == I8_EPI_ACT_HEAD) {   // v 2^24 = d c 2^(24 - e) with the shared exponent
+        const int tot = 24 - epi.q_fixed_exp, h = tot / 2;
+        qsc = exp2_int(h);
+        qsc2 = exp2_int(tot - h);
+      }
+      for (int j = 0; j < num_n_sub && ok; ++j, ++tile) {
+        const uint32_t buf = tile & 1, use = tile >> 1;
+        const long long c0 = clock64();
+        ok = mbar_wait(smem_u32(&acc_full[buf]), use & 1, err);
+        w_wait += clock64() - c0;
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_d + buf * I8_ACC_COLS + (uint32_t(q * 32) << 16);
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = half * 32 + cc * 16;
+          uint32_t r0[16], r1[16], r2[16], r3[16];
+          tmem_ld16_u32(taddr + c, r0);
+          tmem_ld16_u32(taddr + I8_BN + c, r1);
+          tmem_ld16_u32(taddr + 2 * I8_BN + c, r2);
+          tmem_ld16_u32(taddr + 3 * I8_BN + c, r3);
+          tmem_ld_wait();
+          if (cc == 1) {  // everything is in registers: hand the accumulator set back before the math
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(smem_u32(&acc_empty[buf]));
+          }
+          const int nb = j * I8_BN + c;   // first output of this chunk
+          float dq[16];                   // ACT_HEAD: swish' values to be quantised
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = nb + i;
+            const float y = i8_combine(r0[i], r1[i], r2[i], r3[i]) * scale;
+            const int64_t o = int64_t(n) * epi.ld + m;
+            if (MODE == I8_EPI_STORE) {
+              if (n < epi.n_valid) epi.out[o] = y;
+            } else if (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_ACT_HEAD) {
+              const float z = y + __ldg(epi.bias + n);
+              const float sg = 1.0f / (1.0f + expf(-z));
+              const float h = kSwishI8 * z * sg;                           // variance_preserving_swish (activation.py:7-9)
+              const float d = kSwishI8 * sg * (1.0f + z * (1.0f - sg));    // its derivative, for the backward pass
+              if (MODE == I8_EPI_ACT_Q) {
+                epi.aux[o] = d;
+                scratch[int64_t(n) * I8_BM] = h;
+                mx = fmaxf(mx, fabsf(h * __ldg(epi.q_col_scale + n)));
+                if (epi.out) epi.out[o] = h;
+              } else {
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k)
+                  if (k < epi.n_out) hacc[k] = fmaf(h, __ldg(epi.w_head + n * epi.n_out + k), hacc[k]);
+                dq[i] = d * __ldg(epi.q_col_scale + n);
+                if (epi.out) epi.out[o] = d;
+              }
+            } else {
+              const float t = y * epi.aux[o] * rmul;
+              scratch[int64_t(n) * I8_BM] = t;
+              mx = fmaxf(mx, fabsf(t * __ldg(epi.q_col_scale + n)));
+              if (epi.out) epi.out[o] = t;
+            }
+          }
+          if (MODE == I8_EPI_ACT_HEAD)
+            i8_emit16(dq, qsc, qsc2, epi.q_planes + m * epi.q_kp + nb, epi.q_plane_stride);
+        }
+      }
+      if (!ok) break;
+      // ---- end of the output sweep of this atom tile
+      if (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_MULD_Q) {
+        xmax[half][row] = mx;
+        epi_bar_sync();
+        mx = fmaxf(xmax[0][row], xmax[1][row]);
+        epi_bar_sync();
+        int e;
+        float sc, sc2;
+        i8_row_scale(mx, 4, e, sc, sc2);
+        if (half == 0) epi.q_row_exp[m] = e;
+        // this thread staged the columns [j*64 + half*32, +32) of every sub-tile itself: re-read and emit digits
+        for (int j = 0; j < num_n_sub; ++j) {
+#pragma unroll 1
+          for (int cc = 0; cc < 2; ++cc) {
+            const int nb = j * I8_BN + half * 32 + cc * 16;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = scratch[int64_t(nb + i) * I8_BM] * __ldg(epi.q_col_scale + nb + i);
+            i8_emit16(v, sc, sc2, epi.q_planes + m * epi.q_kp + nb, epi.q_plane_stride);
+          }
+        }
+      } else if (MODE == I8_EPI_ACT_HEAD) {
+        if (half == 1) {
+#pragma unroll
+          for (int k = 0; k < NOUT; ++k) xhead[row * NOUT + k] = hacc[k];
+        }
+        epi_bar_sync();
+        if (half == 0) {
+#pragma unroll
+          for (int k = 0; k < NOUT; ++k)
+            if (k < epi.n_out) epi.h_out[int64_t(k) * epi.ld + m] = hacc[k] + xhead[row * NOUT + k];
+        }
+        epi_bar_sync();
+      }
+    }
+    if (epi.dbg && threadIdx.x == 64) {
+      epi.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin;
+      epi.dbg[blockIdx.x * 8 + 5] = w_wait;
+    }
   }
   __syncwarp();
-
-  // ---------------------------------------------------------------------- epilogue: lane == atom
-  const bool have = mbar_wait(smem_u32(&accum_bar), 0, err);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (have) {
-    const int64_t m = int64_t(m0) + threadIdx.x;
-    const float scale = exp2_int(epi.row_exp[m]);
-    const float rmul = (epi.mode == I8_EPI_MULD && epi.row_mul) ? epi.row_mul[m] : 1.0f;
-    const uint32_t taddr = tmem_d + (uint32_t(warp * 32) << 16);
-    constexpr float kInv256 = 1.0f / 256.0f;
-#pragma unroll 1
-    for (int c = 0; c < I8_BN; c += 16) {
-      uint32_t r0[16], r1[16], r2[16], r3[16];
-      tmem_ld16_u32(taddr + c, r0);
-      tmem_ld16_u32(taddr + I8_BN + c, r1);
-      tmem_ld16_u32(taddr + 2 * I8_BN + c, r2);
-      tmem_ld16_u32(taddr + 3 * I8_BN + c, r3);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int n = n0 + c + i;
-        if (n >= epi.n_valid) break;
-        float t = fmaf(float(int(r3[i])), kInv256, float(int(r2[i])));
-        t = fmaf(t, kInv256, float(int(r1[i])));
-        t = fmaf(t, kInv256, float(int(r0[i])));
-        const float v = t * scale;
-        const int64_t o = int64_t(n) * epi.ld + m;
-        if (epi.mode == I8_EPI_STORE) {
-          epi.out[o] = v;
-        } else if (epi.mode == I8_EPI_ACT) {
-          const float y = v + __ldg(epi.bias + n);
-          const float sg = 1.0f / (1.0f + expf(-y));
-          epi.out[o] = kSwishI8 * y * sg;                            // variance_preserving_swish (activation.py:7-9)
-          epi.aux[o] = kSwishI8 * sg * (1.0f + y * (1.0f - sg));     // its derivative, for the backward pass
-        } else {
-          epi.out[o] = v * epi.aux[o] * rmul;
-        }
-      }
-    }
-  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
@@ -166,66 +404,88 @@ __global__ void __launch_bounds__(128) k_i8_gemm(const __grid_constant__ CUtenso
   }
 }
 
-// ---- activations -> digit planes.  Thread == atom (coalesced feature-major reads); two passes over the
-// atom's features: scaled row maximum, then fixed-point conversion and balanced base-256 digit extraction.
-__global__ void __launch_bounds__(128) k_i8_quantize_rows(const float* __restrict__ xt, int64_t ld, int64_t n_valid_rows,
-                                                          int K, int kp, const float* __restrict__ col_scale,
-                                                          int8_t* __restrict__ planes, int32_t* __restrict__ row_exp) {
+// ---- activations -> digit planes, two tile-parallel kernels (grid: 128-atom tiles x 64-feature chunks).
+// Thread == atom, so the feature-major reads are coalesced.
+//   k_i8_rowmax:   scaled row maxima, combined across chunks with an integer atomicMax on the float bits
+//   k_i8_quantize: fixed-point conversion + balanced base-256 digits; the 128 x 64-byte tile of each plane is
+//                  staged in shared memory and written out as full 64-byte row segments.
+__global__ void __launch_bounds__(128) k_i8_rowmax(const float* __restrict__ xt, int64_t ld, int64_t n_valid_rows, int K,
+                                                   const float* __restrict__ col_scale, int32_t* __restrict__ rowmax_bits) {
   const int64_t m = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  if (m >= n_valid_rows) return;
+  const int k0 = blockIdx.y * 64, k1 = min(K, k0 + 64);
   const float* x = xt + m;
   float mx = 0.0f;
-  if (m < n_valid_rows) {
 #pragma unroll 8
-    for (int k = 0; k < K; ++k) mx = fmaxf(mx, fabsf(x[int64_t(k) * ld] * __ldg(col_scale + k)));
-  }
-  int e = 0;
-  float sc = 0.0f;  // zero / padding / non-finite rows quantise to all-zero digits
-  if (mx > 0.0f && mx < 3.0e38f) {
-    int ex;
-    frexpf(mx, &ex);        // mx = f 2^ex, f in [0.5, 1)  =>  mx 2^-(ex-6) in [32, 64)
-    e = ex - 6;
-    sc = exp2_int(24 - e);  // v 2^24 with v = x c 2^-e
-  }
-  row_exp[m] = e;
-  const int64_t plane_stride = ld * int64_t(kp);
-  int8_t* dst = planes + m * int64_t(kp);
-  for (int k0 = 0; k0 < kp; k0 += 16) {
-    uint32_t w[I8_DIGITS][4];
+  for (int k = k0; k < k1; ++k) mx = fmaxf(mx, fabsf(x[int64_t(k) * ld] * __ldg(col_scale + k)));
+  if (!(mx < 3.0e38f)) mx = 3.4e38f;   // NaN / inf rows are flagged by a huge maximum and quantise to zero
+  atomicMax(rowmax_bits + m, __float_as_int(mx));
+}
+
+template <int P>
+__global__ void __launch_bounds__(128, 7) k_i8_quantize(const float* __restrict__ xt, int64_t ld, int K, int kp,
+                                                        const float* __restrict__ col_scale,
+                                                        const int32_t* __restrict__ rowmax_bits,
+                                                        int8_t* __restrict__ planes, int32_t* __restrict__ row_exp) {
+  __shared__ __align__(16) uint8_t tile[P][128 * 64];
+  const int tid = threadIdx.x;
+  const int64_t m0 = int64_t(blockIdx.x) * 128, m = m0 + tid;
+  const int kc = blockIdx.y * 64;
+  int e;
+  float sc, sc2;
+  i8_row_scale(__int_as_float(rowmax_bits[m]), P, e, sc, sc2);
+  if (blockIdx.y == 0) row_exp[m] = e;
+  const float* x = xt + m;
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+    const int k0 = kc + g * 16;
+    float v[16];
+    if (k0 + 16 <= K) {
 #pragma unroll
-    for (int d = 0; d < I8_DIGITS; ++d)
+      for (int j = 0; j < 16; ++j) v[j] = x[int64_t(k0 + j) * ld];
+    } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) w[d][q] = 0u;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int k = k0 + j;
-      float v = 0.0f;
-      if (k < K && sc != 0.0f) v = (x[int64_t(k) * ld] * __ldg(col_scale + k)) * sc;
-      int I = __float2int_rn(v);        // |I| <= 2^30
-      const int d3 = (I << 24) >> 24;   // balanced digit: sign-extended low byte
-      I = (I - d3) >> 8;
-      const int d2 = (I << 24) >> 24;
-      I = (I - d2) >> 8;
-      const int d1 = (I << 24) >> 24;
-      I = (I - d1) >> 8;                // leading digit, |I| <= 65
-      const int sh = (j & 3) * 8;
-      w[0][j >> 2] |= uint32_t(I & 0xff) << sh;
-      w[1][j >> 2] |= uint32_t(d1 & 0xff) << sh;
-      w[2][j >> 2] |= uint32_t(d2 & 0xff) << sh;
-      w[3][j >> 2] |= uint32_t(d3 & 0xff) << sh;
+      for (int j = 0; j < 16; ++j) v[j] = (k0 + j < K) ? x[int64_t(k0 + j) * ld] : 0.0f;
     }
+    uint32_t w[P][4];
 #pragma unroll
-    for (int d = 0; d < I8_DIGITS; ++d)
-      *reinterpret_cast<uint4*>(dst + d * plane_stride + k0) = make_uint4(w[d][0], w[d][1], w[d][2], w[d][3]);
+    for (int q = 0; q < 4; ++q) {
+      uint32_t ew[4], tb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + 4 * q + j;
+        const float c = (k < K) ? __ldg(col_scale + k) : 0.0f;
+        ew[j] = i8_digit_word<P>(sc != 0.0f ? ((v[4 * q + j] * c) * sc) * sc2 : 0.0f);
+      }
+      i8_transpose4(ew, tb);
+#pragma unroll
+      for (int d = 0; d < P; ++d) w[d][q] = tb[P - 1 - d];
+    }
+    const int piece = g ^ ((tid >> 1) & 3);   // 16-byte pieces of a row are xor-swizzled: conflict-free both ways
+#pragma unroll
+    for (int d = 0; d < P; ++d)
+      *reinterpret_cast<uint4*>(&tile[d][tid * 64 + piece * 16]) = make_uint4(w[d][0], w[d][1], w[d][2], w[d][3]);
+  }
+  __syncthreads();
+  const int64_t plane_stride = ld * int64_t(kp);
+#pragma unroll
+  for (int d = 0; d < P; ++d) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = tid + 128 * j, r = idx >> 2, p = idx & 3;
+      const uint4 val = *reinterpret_cast<const uint4*>(&tile[d][r * 64 + (p ^ ((r >> 1) & 3)) * 16]);
+      *reinterpret_cast<uint4*>(planes + d * plane_stride + (m0 + r) * int64_t(kp) + kc + p * 16) = val;
+    }
   }
 }
 
-// planes [4][rows][kp] int8 as a 3-d tensor {kp, rows, 4}; box {64 bytes, 128 rows, 1 plane}, SWIZZLE_64B
-int make_plane_tmap(CUtensorMap* tm, const I8Planes& p) {
+// planes [n][rows][kp] int8 as a 3-d tensor {kp, rows, n}; box {64 bytes, box_rows, 1 plane}, SWIZZLE_64B
+int make_plane_tmap(CUtensorMap* tm, const I8Planes& p, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return APAX_ERR_CUDA;
-  const cuuint64_t dims[3] = {cuuint64_t(p.kp), cuuint64_t(p.rows), cuuint64_t(I8_DIGITS)};
+  const cuuint64_t dims[3] = {cuuint64_t(p.kp), cuuint64_t(p.rows), cuuint64_t(p.n_planes)};
   const cuuint64_t strides[2] = {cuuint64_t(p.kp), cuuint64_t(p.plane_stride)};
-  const cuuint32_t box[3] = {I8_KC, I8_BM, 1};
+  const cuuint32_t box[3] = {I8_KC, cuuint32_t(box_rows), 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(p.base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -233,29 +493,73 @@ int make_plane_tmap(CUtensorMap* tm, const I8Planes& p) {
   return r == CUDA_SUCCESS ? APAX_OK : APAX_ERR_INVALID_ARG;
 }
 
-}  // namespace
+struct I8Launch {
+  CUtensorMap ta, tb;
+  int num_kb, a_planes, num_m_tiles, num_n_sub, b_stages, grid;
+  uint32_t smem;
+};
 
-int i8_quantize_rows(cudaStream_t stream, const float* xt, int64_t ld, int64_t n_valid_rows, int K, int kp,
-                     const float* col_scale, int8_t* planes, int32_t* row_exp) {
-  if (ld % 128 != 0 || kp % 64 != 0 || K > kp) return APAX_ERR_INVALID_ARG;
-  APAX_LAUNCH(k_i8_quantize_rows, dim3((unsigned)(ld / 128)), dim3(128), 0, stream, xt, ld, n_valid_rows, K, kp, col_scale,
-              planes, row_exp);
+template <class Kern>
+int prepare_i8(Kern kern) {
+  cudaFuncAttributes fa;
+  APAX_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+  APAX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(I8_SMEM_LIMIT - fa.sharedSizeBytes)));
   return APAX_OK;
 }
 
-void i8_quantize_weights(const float* W, int K, int NC, int ldw, int kp, int ncp, std::vector<int8_t>& planes,
-                         std::vector<float>& col_scale) {
-  planes.assign(size_t(I8_DIGITS) * ncp * kp, 0);
-  col_scale.assign(size_t(kp), 1.0f);
-  const size_t plane_stride = size_t(ncp) * kp;
+// one named launch per epilogue so that launch lists and the per-kernel profile tell the four GEMMs apart
+#define I8_LAUNCH(name, MODE, NOUT)                                                                                  \
+  do {                                                                                                               \
+    auto name = k_i8_gemm<MODE, NOUT>;                                                                               \
+    static bool prepared = false;                                                                                    \
+    if (!prepared) {                                                                                                 \
+      APAX_TRY(prepare_i8(name));                                                                                    \
+      prepared = true;                                                                                               \
+    }                                                                                                                \
+    APAX_LAUNCH(name, dim3((unsigned)L.grid), dim3(I8_THREADS), L.smem, stream, L.ta, L.tb, L.num_kb, L.a_planes,    \
+                L.num_m_tiles, L.num_n_sub, L.b_stages, epi, err_flag);                                              \
+    return APAX_OK;                                                                                                  \
+  } while (0)
+
+}  // namespace
+
+int i8_quantize_rows(cudaStream_t stream, const float* xt, int64_t ld, int64_t n_valid_rows, int K, int kp, int n_planes,
+                     const float* col_scale, int8_t* planes, int32_t* row_exp, int32_t* rowmax_bits) {
+  if (ld % 128 != 0 || kp % 64 != 0 || K > kp || (n_planes != 3 && n_planes != 4)) return APAX_ERR_INVALID_ARG;
+  const dim3 grid((unsigned)(ld / 128), (unsigned)(kp / 64));
+  APAX_CUDA_TRY(cudaMemsetAsync(rowmax_bits, 0, sizeof(int32_t) * ld, stream));
+  APAX_LAUNCH(k_i8_rowmax, grid, dim3(128), 0, stream, xt, ld, n_valid_rows, K, col_scale, rowmax_bits);
+  if (n_planes == 3) {
+    APAX_LAUNCH(k_i8_quantize<3>, grid, dim3(128), 0, stream, xt, ld, K, kp, col_scale, rowmax_bits, planes, row_exp);
+  } else {
+    APAX_LAUNCH(k_i8_quantize<4>, grid, dim3(128), 0, stream, xt, ld, K, kp, col_scale, rowmax_bits, planes, row_exp);
+  }
+  return APAX_OK;
+}
+
+void i8_weight_scales(const float* W, int K, int NC, int ldw, int kp, std::vector<float>& col_scale, bool merge) {
+  if (!merge) col_scale.assign(size_t(kp), 0.0f);
   for (int k = 0; k < K; ++k) {
     double mx = 0.0;
     for (int n = 0; n < NC; ++n) mx = std::fmax(mx, std::fabs(double(W[size_t(k) * ldw + n])));
     if (!(mx > 0.0) || !std::isfinite(mx)) continue;
     int ex;
-    std::frexp(mx, &ex);                       // mx / 2^(ex-6) in [32, 64)
-    const double c = std::ldexp(1.0, ex - 6);
-    col_scale[k] = float(c);                   // power of two: exact in fp32, exact to multiply by
+    std::frexp(mx, &ex);                                   // mx / 2^(ex-6) in [32, 64)
+    col_scale[k] = std::fmax(col_scale[k], float(std::ldexp(1.0, ex - 6)));   // power of two: exact in fp32
+  }
+}
+
+void i8_quantize_weights(const float* W, int K, int NC, int ldw, int kp, int ncp, std::vector<int8_t>& planes,
+                         std::vector<float>& col_scale, bool given_scale) {
+  planes.assign(size_t(I8_DIGITS) * ncp * kp, 0);
+  if (!given_scale) i8_weight_scales(W, K, NC, ldw, kp, col_scale, false);
+  const size_t plane_stride = size_t(ncp) * kp;
+  for (int k = 0; k < K; ++k) {
+    if (!(col_scale[k] > 0.0f)) {
+      col_scale[k] = 1.0f;   // all-zero weight row: any scale will do, the digits stay zero
+      continue;
+    }
+    const double c = double(col_scale[k]);
     for (int n = 0; n < NC; ++n) {
       long long I = std::llrint(double(W[size_t(k) * ldw + n]) / c * 16777216.0);
       int d[I8_DIGITS];
@@ -268,22 +572,43 @@ void i8_quantize_weights(const float* W, int K, int NC, int ldw, int kp, int ncp
       for (int s = 0; s < I8_DIGITS; ++s) planes[s * plane_stride + size_t(n) * kp + k] = int8_t(d[s]);
     }
   }
+  for (int k = K; k < kp; ++k) col_scale[k] = 1.0f;
 }
 
 int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const I8Epilogue& epi, int32_t* err_flag) {
-  if (act.kp != wgt.kp || act.kp % I8_KC != 0 || act.rows % I8_BM != 0 || wgt.rows % I8_BN != 0) return APAX_ERR_INVALID_ARG;
-  CUtensorMap ta, tb;
-  APAX_TRY(make_plane_tmap(&ta, act));
-  APAX_TRY(make_plane_tmap(&tb, wgt));
-  static bool attr_set = false;
-  if (!attr_set) {
-    APAX_CUDA_TRY(cudaFuncSetAttribute(k_i8_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, int(I8_SMEM_BYTES)));
-    attr_set = true;
+  if (act.kp != wgt.kp || act.kp % I8_KC != 0 || act.kp / I8_KC > I8_MAX_KB || act.rows % I8_BM != 0 ||
+      wgt.rows % I8_BN != 0 || wgt.n_planes != I8_DIGITS || (act.n_planes != 3 && act.n_planes != 4))
+    return APAX_ERR_INVALID_ARG;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    APAX_CUDA_TRY(cudaGetDevice(&dev));
+    APAX_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int num_k_blocks = int(act.kp / I8_KC);
-  const dim3 grid((unsigned)(act.rows / I8_BM), (unsigned)(wgt.rows / I8_BN));
-  APAX_LAUNCH(k_i8_gemm, grid, dim3(128), I8_SMEM_BYTES, stream, ta, tb, num_k_blocks, epi, err_flag);
-  return APAX_OK;
+  I8Launch L;
+  APAX_TRY(make_plane_tmap(&L.ta, act, I8_BM));
+  APAX_TRY(make_plane_tmap(&L.tb, wgt, I8_BN));
+  L.num_kb = int(act.kp / I8_KC);
+  L.a_planes = act.n_planes;
+  L.num_m_tiles = int(act.rows / I8_BM);
+  L.num_n_sub = int(wgt.rows / I8_BN);
+  L.grid = L.num_m_tiles < n_sm ? L.num_m_tiles : n_sm;   // one persistent CTA per SM (it owns the SM's whole TMEM)
+  const uint32_t a_bytes = uint32_t(L.num_kb * L.a_planes) * I8_A_TILE;
+  if (a_bytes + 2 * I8_B_STAGE + 10240 > I8_SMEM_LIMIT) return APAX_ERR_INVALID_ARG;
+  const uint32_t budget = I8_SMEM_LIMIT - 10240 /* static + alignment */ - a_bytes;
+  L.b_stages = int(budget / I8_B_STAGE);
+  if (L.b_stages > I8_MAX_B_STAGES) L.b_stages = I8_MAX_B_STAGES;
+  L.smem = a_bytes + uint32_t(L.b_stages) * I8_B_STAGE + 1024;
+  switch (epi.mode) {
+    case I8_EPI_STORE: I8_LAUNCH(k_i8_gemm_store, I8_EPI_STORE, 1);
+    case I8_EPI_ACT_Q: I8_LAUNCH(k_i8_gemm_act_q, I8_EPI_ACT_Q, 1);
+    case I8_EPI_MULD_Q: I8_LAUNCH(k_i8_gemm_muld_q, I8_EPI_MULD_Q, 1);
+    case I8_EPI_ACT_HEAD:
+      if (epi.n_out == 1) I8_LAUNCH(k_i8_gemm_act_head, I8_EPI_ACT_HEAD, 1);
+      if (epi.n_out <= I8_MAX_HEADS) I8_LAUNCH(k_i8_gemm_act_heads, I8_EPI_ACT_HEAD, I8_MAX_HEADS);
+      return APAX_ERR_INVALID_ARG;
+    default: return APAX_ERR_INVALID_ARG;
+  }
 }
 
 }  // namespace apax
@@ -291,10 +616,11 @@ int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const
 // Test / measurement entry: out[nc][ld] = act^T . wgt through the integer tensor-core path (plain store
 // epilogue).  act: device fp32 [k][ld]; wgt: device fp32 [k][nc].  Allocates its own scratch (test only).
 extern "C" int apax_i8_gemm_test(apax_stream_t stream_, const float* act, int64_t k, int64_t ld, int64_t n_atoms,
-                                 const float* wgt, int64_t nc, float* out, int32_t* err_flag) {
+                                 const float* wgt, int64_t nc, float* out, int32_t* err_flag, int64_t* dbg,
+                                 int32_t act_planes) {
   if (!act || !wgt || !out || !err_flag || k <= 0 || nc <= 0 || ld % 128 != 0) return APAX_ERR_INVALID_ARG;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const int kp = int((k + 63) / 64 * 64), ncp = int((nc + 127) / 128 * 128);
+  const int kp = int((k + 63) / 64 * 64), ncp = int((nc + 63) / 64 * 64);
   std::vector<float> hw(size_t(k) * nc);
   APAX_CUDA_TRY(cudaStreamSynchronize(stream));
   APAX_CUDA_TRY(cudaMemcpy(hw.data(), wgt, hw.size() * sizeof(float), cudaMemcpyDeviceToHost));
@@ -303,24 +629,26 @@ extern "C" int apax_i8_gemm_test(apax_stream_t stream_, const float* act, int64_
   apax::i8_quantize_weights(hw.data(), int(k), int(nc), int(nc), kp, ncp, wp, cs);
   int8_t *d_wp = nullptr, *d_ap = nullptr;
   float* d_cs = nullptr;
-  int32_t* d_e = nullptr;
+  int32_t *d_e = nullptr, *d_mx = nullptr;
   int rc = APAX_OK;
   if (cudaMalloc(&d_wp, wp.size()) != cudaSuccess || cudaMalloc(&d_ap, size_t(4) * ld * kp) != cudaSuccess ||
-      cudaMalloc(&d_cs, cs.size() * sizeof(float)) != cudaSuccess || cudaMalloc(&d_e, ld * sizeof(int32_t)) != cudaSuccess)
+      cudaMalloc(&d_cs, cs.size() * sizeof(float)) != cudaSuccess || cudaMalloc(&d_e, ld * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&d_mx, ld * sizeof(int32_t)) != cudaSuccess)
     rc = APAX_ERR_CUDA;
   if (rc == APAX_OK) {
     cudaMemcpy(d_wp, wp.data(), wp.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(d_cs, cs.data(), cs.size() * sizeof(float), cudaMemcpyHostToDevice);
-    rc = apax::i8_quantize_rows(stream, act, ld, n_atoms, int(k), kp, d_cs, d_ap, d_e);
+    rc = apax::i8_quantize_rows(stream, act, ld, n_atoms, int(k), kp, act_planes, d_cs, d_ap, d_e, d_mx);
   }
   if (rc == APAX_OK) {
-    apax::I8Planes a{d_ap, ld, kp, ld * int64_t(kp)}, w{d_wp, ncp, kp, int64_t(ncp) * kp};
+    apax::I8Planes a{d_ap, ld, kp, ld * int64_t(kp), act_planes}, w{d_wp, ncp, kp, int64_t(ncp) * kp, 4};
     apax::I8Epilogue e{};
     e.mode = apax::I8_EPI_STORE;
     e.ld = ld;
     e.n_valid = int(nc);
     e.row_exp = d_e;
     e.out = out;
+    e.dbg = reinterpret_cast<long long*>(dbg);
     rc = apax::i8_gemm(stream, a, w, e, err_flag);
   }
   if (cudaStreamSynchronize(stream) != cudaSuccess && rc == APAX_OK) rc = APAX_ERR_CUDA;
@@ -328,5 +656,6 @@ extern "C" int apax_i8_gemm_test(apax_stream_t stream_, const float* act, int64_
   cudaFree(d_ap);
   cudaFree(d_cs);
   cudaFree(d_e);
+  cudaFree(d_mx);
   return rc;
 }

@@ -8,18 +8,26 @@
 //
 // Scheme (Ozaki-style slicing, fixed 8-bit slices):
 //   * every activation row (one atom) is scaled by a power of two 2^-e[m] and a per-feature power of two c[k]
-//     such that |x[m][k] c[k] 2^-e[m]| < 64, then written as a 32-bit fixed-point number I = rn(v 2^24) and
-//     split into four balanced base-256 digits d0..d3 in [-128,127]:  v = sum_s d_s 256^-s;
-//   * the weights get the reciprocal per-feature scale (w[k][n] / c[k], row maximum in [32,64)) and the
-//     same four digits, once per parameter set;
-//   * D_o[m][n] = sum_{s+t=o} sum_k a_s[m][k] b_t[k][n] for o = 0..3 -- ten int8 MMAs per 32-wide k-step into
-//     four int32 accumulators of 128 TMEM columns each (all 512 columns of the SM);
-//   * epilogue: y[m][n] = 2^e[m] (D_0 + D_1/256 + D_2/256^2 + D_3/256^3), then bias / swish / multipliers.
+//     such that |x[m][k] c[k] 2^-e[m]| < 64, then written as a fixed-point number and split into balanced
+//     base-256 digits d0, d1, ... in [-128,127]:  v = sum_s d_s 256^-s  (4 digits, or 3 for the 360-feature
+//     descriptor whose 24-bit slices equal fp32's own significand);
+//   * the weights get the reciprocal per-feature scale (w[k][n] / c[k], row maximum in [32,64)) and four
+//     digits, once per parameter set;
+//   * D_o[m][n] = sum_{s+t=o} sum_k a_s[m][k] b_t[k][n] for o = 0..3 -- ten (nine) int8 MMAs per 32-wide k-step
+//     into four int32 accumulators;
+//   * epilogue: y[m][n] = 2^e[m] (D_0 + D_1/256 + D_2/256^2 + D_3/256^3), then the layer's fused tail.
 //
-// Data path: digit planes are K-major int8 matrices [row][Kp]; TMA loads {64 bytes of k, 128 rows} boxes with
-// SWIZZLE_64B (the canonical UMMA K-major SW64 layout: 8-row x 64-byte atoms, 512 bytes apart), three
-// pipeline stages of 8 planes x 8 KB.  One CTA (128 threads: TMA thread, MMA thread, 4 epilogue warps) per
-// 128 atoms x 128 outputs tile; TMEM lane == atom, so epilogue stores are coalesced along atoms.
+// Kernel shape (one persistent CTA per SM; TMA warp, MMA warp, eight epilogue warps):
+//   * activation-stationary: the 128-atom tile's digit planes for the whole reduction (<= 144 KB) sit in shared
+//     memory while the CTA sweeps the layer's outputs in 64-wide sub-tiles, streaming only weight planes
+//     (16 KB per 64-byte k-block) from L2 through a ring -- the L2 -> SM stream is what bounded the first version;
+//   * two TMEM accumulator sets (2 x 4 x 64 columns = all 512): the epilogue of sub-tile j overlaps the MMAs of
+//     j + 1; draining tensor memory (64 B/clk/SM) is the epilogue's floor;
+//   * digit planes are K-major [row][kp] int8; TMA boxes {64 bytes of k, rows} with SWIZZLE_64B land in the
+//     canonical UMMA K-major SW64 layout (8-row x 64-byte atoms, 512 bytes apart);
+//   * TMEM lane == atom: fp32 stores are coalesced along atoms, and one thread sees a whole output row of its
+//     atom over the sweep, so row maxima, the energy head and the next layer's digit planes come out of the
+//     epilogue directly (fused modes below) -- activations never exist in fp32 in HBM.
 #pragma once
 #include <cuda.h>
 
@@ -29,40 +37,70 @@
 
 namespace apax {
 
-constexpr int I8_BM = 128;      // atoms per CTA (UMMA M)
-constexpr int I8_BN = 128;      // outputs per CTA (UMMA N); 4 accumulators x 128 columns = whole TMEM
-constexpr int I8_KC = 64;       // k bytes per pipeline stage (two K = 32 MMAs per digit pair)
-constexpr int I8_STAGES = 3;
+constexpr int I8_BM = 128;      // atoms per CTA tile (UMMA M)
+constexpr int I8_BN = 64;       // outputs per sub-tile (UMMA N)
+constexpr int I8_KC = 64;       // k bytes per k-block (two K = 32 MMAs per digit pair)
 constexpr int I8_DIGITS = 4;
+constexpr int I8_MAX_KB = 6;    // reduction length <= 384
+constexpr int I8_MAX_HEADS = 16;
 
-enum { I8_EPI_STORE = 0, I8_EPI_ACT = 1, I8_EPI_MULD = 2 };
+enum {
+  I8_EPI_STORE = 0,     // out[n][m] = y
+  I8_EPI_ACT_Q = 1,     // h = swish(y + bias): aux[n][m] = swish'(.), h -> digit planes of the next layer (row-max scaled)
+  I8_EPI_ACT_HEAD = 2,  // h = swish(y + bias): h_out[k][m] = sum_n h w_head[n][k]; swish'(.) -> digit planes (fixed scale)
+  I8_EPI_MULD_Q = 3     // t = y * aux[n][m] * row_mul[m] -> digit planes of the next layer (row-max scaled)
+};
 
-struct I8Planes {        // four digit planes of a [rows][kp] matrix, plane p at base + p * plane_stride
+struct I8Planes {        // digit planes of a [rows][kp] matrix, plane p at base + p * plane_stride
   const int8_t* base;
-  int64_t rows;          // multiple of 128
+  int64_t rows;          // activations: multiple of 128; weights: multiple of 64
   int64_t kp;            // padded reduction length in bytes, multiple of 64
   int64_t plane_stride;  // bytes between planes
+  int n_planes;          // 3 or 4 (weights: 4)
 };
 
 struct I8Epilogue {
   int mode;
-  int64_t ld;            // atom stride of the feature-major fp32 outputs
-  int n_valid;           // outputs >= n_valid are not stored
-  const int32_t* row_exp;  // [rows of A] e[m]
-  float* out;            // [n][ld]  STORE: y;  ACT: swish(y + bias);  MULD: y * aux * row_mul
-  float* aux;            // ACT: swish'(y + bias) written;  MULD: multiplier read
-  const float* bias;     // ACT: [n]
-  const float* row_mul;  // MULD: per-atom factor [ld] (may be null)
+  int64_t ld;              // atom stride of the feature-major fp32 matrices
+  int n_valid;             // outputs >= n_valid are ignored
+  const int32_t* row_exp;  // [rows] exponents e[m] of the activation planes; null: fixed_exp for every row
+  int fixed_exp;
+  float* out;              // STORE: [n][ld].  Fused modes: optional fp32 copy of the quantised quantity (debug), may be null
+  const float* bias;       // ACT_*: [n]
+  float* aux;              // ACT_Q: swish' written [n][ld];  MULD_Q: multiplier read
+  const float* row_mul;    // MULD_Q: per-atom factor [ld] (may be null)
+  // digit planes produced for the next GEMM (always four planes of a [rows][q_kp] matrix)
+  int8_t* q_planes;
+  int64_t q_kp, q_plane_stride;
+  const float* q_col_scale;  // [n] per-feature powers of two of the consuming layer
+  int32_t* q_row_exp;        // [rows] written by ACT_Q / MULD_Q
+  int q_fixed_exp;           // ACT_HEAD: exponent shared by all rows
+  float* scratch;            // ACT_Q / MULD_Q: [grid][n_outputs][128] fp32 staging (stays in L2)
+  // energy head (ACT_HEAD)
+  const float* w_head;       // [n][n_out]
+  int n_out;
+  float* h_out;              // [n_out][ld]
+  long long* dbg;            // optional [grid][8] cycle counters
 };
 
-// activations: feature-major fp32 [K][ld] -> digit planes [4][ld][kp] + per-atom exponents
-int i8_quantize_rows(cudaStream_t stream, const float* xt, int64_t ld, int64_t n_valid_rows, int K, int kp,
-                     const float* col_scale /* [kp] powers of two */, int8_t* planes, int32_t* row_exp);
+// activations: feature-major fp32 [K][ld] -> digit planes [n_planes][ld][kp] + per-atom exponents
+int i8_quantize_rows(cudaStream_t stream, const float* xt, int64_t ld, int64_t n_valid_rows, int K, int kp, int n_planes,
+                     const float* col_scale /* [kp] powers of two */, int8_t* planes, int32_t* row_exp,
+                     int32_t* rowmax_scratch /* [ld] */);
 
-// weights (host): W[k][n] (row stride ldw) -> planes [4][ncp][kp] of W[k][n] / c[k] and the per-k scales c[k]
+// weights (host): W[k][n] (row stride ldw) -> planes [4][ncp][kp] of W[k][n] / c[k].  col_scale: computed here from
+// the row maxima of W (given_scale = false), or taken as given (shared between several weight matrices).
 void i8_quantize_weights(const float* W, int K, int NC, int ldw, int kp, int ncp, std::vector<int8_t>& planes,
-                         std::vector<float>& col_scale);
+                         std::vector<float>& col_scale, bool given_scale = false);
+// per-k scale c[k] = 2^(exponent of max_n |W[k][n]| - 6); merges into an existing scale vector by maximum
+void i8_weight_scales(const float* W, int K, int NC, int ldw, int kp, std::vector<float>& col_scale, bool merge);
 
 int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const I8Epilogue& epi, int32_t* err_flag);
+
+// per-CTA staging floats needed by the fused modes for n_outputs outputs and the given number of atom rows
+inline int64_t i8_scratch_floats(int64_t rows, int n_sm, int n_outputs) {
+  const int64_t tiles = rows / I8_BM;
+  return (tiles < n_sm ? tiles : n_sm) * int64_t(n_outputs) * I8_BM;
+}
 
 }  // namespace apax

@@ -234,7 +234,8 @@ int apax_ctx_calculate(apax_ctx* ctx, const double* positions_host, const int32_
  * wgt a device fp32 [k][nc] matrix.  Replaces the fp32 matmuls of apax/layers/ntk_linear.py:40 inside the
  * readout; allocates its own scratch, so it is for tests and measurements only. */
 int apax_i8_gemm_test(apax_stream_t stream, const float* act, int64_t k, int64_t ld, int64_t n_atoms, const float* wgt,
-                      int64_t nc, float* out, int32_t* err_flag);
+                      int64_t nc, float* out, int32_t* err_flag, int64_t* dbg_cycles /* nullable, [n_sm][8] */,
+                      int32_t act_planes /* 3 or 4 digit planes for the activations */);
 
 /* Readout GEMM building block on the tcgen05 tensor cores, exposed for tests and measurement:
  * out[nc][ld] = sum_k act[k][atom] * wgt[k][n] with both operands given as exact tf32 (hi, lo) pairs

@@ -1,5 +1,7 @@
 """Time the integer tensor-core GEMM pieces at readout sizes (quantise + GEMM), via the library's per-launch profile."""
+import os
 import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from apax_b200 import runtime as rt
@@ -12,9 +14,10 @@ for k, nc in [(360, 256), (256, 256), (256, 360)]:
     wgt = torch.randn(k, nc, device=dev) / np.sqrt(k)
     out = torch.zeros(nc, ld, device=dev)
     err = torch.zeros(1, device=dev, dtype=torch.int32)
+    dbg = torch.zeros(148 * 8, device=dev, dtype=torch.int64)
 
     def go():
-        rc = rt.lib().apax_i8_gemm_test(rt._stream_ptr(), rt._ptr(act), k, ld, n_atoms, rt._ptr(wgt), nc, rt._ptr(out), rt._ptr(err))
+        rc = rt.lib().apax_i8_gemm_test(rt._stream_ptr(), rt._ptr(act), k, ld, n_atoms, rt._ptr(wgt), nc, rt._ptr(out), rt._ptr(err), rt._ptr(dbg), 3 if k > 256 else 4)
         assert rc == 0
 
     go(); go()
@@ -22,4 +25,6 @@ for k, nc in [(360, 256), (256, 256), (256, 360)]:
     flops = 2.0 * n_atoms * k * nc
     print(k, nc, [(n, round(ms, 3)) for n, ms in rec], "err", int(err.item()),
           "fp32-equivalent TFLOP/s of GEMM:", round(flops / (rec[-1][1] * 1e-3) / 1e12, 1))
+    d = dbg.view(148, 8).double().mean(0).tolist()
+    print('   cycles/CTA: mma total %.0f wait_acc %.0f wait_b %.0f wait_a %.0f | epi total %.0f wait %.0f' % tuple(d[:6]))
     del act, out
