@@ -1132,9 +1132,9 @@ static int readout_i8(cudaStream_t stream, const apax_gm_params_impl* p, const G
   int32_t* rowmax = e_x1 + ld;
   const I8Planes w0{p->q_w0, NH, NFP, int64_t(NH) * NFP, 4}, w1{p->q_w1, NH, NH, int64_t(NH) * NH, 4};
   if (head < 0) {
-    APAX_TRY(i8_quantize_rows(stream, w.GT, ld, N, NF, NFP, 3, p->cs_g, gq, e_g, rowmax));
+    APAX_TRY(i8_quantize_rows(stream, w.GT, ld, N, NF, NFP, 4, p->cs_g, gq, e_g, rowmax));
     {  // layer 0: 360 -> 256; swish' kept in fp32 for the backward pass, swish goes on as digit planes
-      const I8Planes act{gq, ld, NFP, ld * int64_t(NFP), 3};
+      const I8Planes act{gq, ld, NFP, ld * int64_t(NFP), 4};
       I8Epilogue e{};
       e.mode = I8_EPI_ACT_Q; e.ld = ld; e.n_valid = NH; e.row_exp = e_g; e.bias = p->b0; e.aux = w.D1T;
       e.q_planes = h1q; e.q_kp = NH; e.q_plane_stride = ld * int64_t(NH); e.q_col_scale = p->cs_h1; e.q_row_exp = e_h1;

@@ -136,8 +136,8 @@ __device__ __forceinline__ float i8_combine(uint32_t r0, uint32_t r1, uint32_t r
 template <int MODE, int NOUT>
 __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant__ CUtensorMap tm_a,
                                                            const __grid_constant__ CUtensorMap tm_b, int num_kb,
-                                                           int a_planes, int num_m_tiles, int num_n_sub, int b_stages,
-                                                           I8Epilogue epi, int32_t* err) {
+                                                           int a_planes, int a_res, int num_m_tiles, int num_n_sub,
+                                                           int b_stages, I8Epilogue epi, int32_t* err) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[I8_MAX_KB];
   __shared__ __align__(8) uint64_t a_empty[I8_MAX_KB];
@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_b = smem_a + uint32_t(num_kb * a_planes) * I8_A_TILE;
+  // a_res planes of the atom tile are resident; the others travel with the weight stages (they are used least)
+  const uint32_t smem_b = smem_a + uint32_t(num_kb * a_res) * I8_A_TILE;
+  const uint32_t stage_bytes = I8_B_STAGE + uint32_t(a_planes - a_res) * I8_A_TILE;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < I8_MAX_KB; ++i) {
@@ -193,9 +195,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
             if (!ok) break;
             if (elect_one()) {
               const uint32_t bar = smem_u32(&a_full[kb]);
-              mbar_expect_tx(bar, uint32_t(a_planes) * I8_A_TILE);
-              for (int d = 0; d < a_planes; ++d)
-                tma_load_3d(smem_a + uint32_t(kb * a_planes + d) * I8_A_TILE, &tm_a, bar, kb * I8_KC, m0, d);
+              mbar_expect_tx(bar, uint32_t(a_res) * I8_A_TILE);
+              for (int d = 0; d < a_res; ++d)
+                tma_load_3d(smem_a + uint32_t(kb * a_res + d) * I8_A_TILE, &tm_a, bar, kb * I8_KC, m0, d);
             }
             __syncwarp();
           }
@@ -204,10 +206,12 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
           if (!ok) break;
           if (elect_one()) {
             const uint32_t bar = smem_u32(&b_full[s]);
-            mbar_expect_tx(bar, I8_B_STAGE);
+            mbar_expect_tx(bar, stage_bytes);
 #pragma unroll
             for (int d = 0; d < I8_DIGITS; ++d)
-              tma_load_3d(smem_b + s * I8_B_STAGE + d * I8_B_TILE, &tm_b, bar, kb * I8_KC, j * I8_BN, d);
+              tma_load_3d(smem_b + s * stage_bytes + d * I8_B_TILE, &tm_b, bar, kb * I8_KC, j * I8_BN, d);
+            for (int d = a_res; d < a_planes; ++d)
+              tma_load_3d(smem_b + s * stage_bytes + I8_B_STAGE + uint32_t(d - a_res) * I8_A_TILE, &tm_a, bar, kb * I8_KC, m0, d);
           }
           __syncwarp();
         }
@@ -215,7 +219,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform, elected lane issues)
-    constexpr uint32_t idesc = make_idesc_i8(I8_BM, I8_BN);
     uint32_t bit = 0, tile = 0;
     bool ok = true;
     long long w_acc = 0, w_a = 0, w_b = 0, t_begin = clock64();
@@ -242,20 +245,26 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
           if (!ok) break;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           // descriptors of plane d / k-slice kk differ from the first one only in the 16-byte-unit start address
-          const uint64_t a0 = make_desc_k_sw64(smem_a + uint32_t(kb * a_planes) * I8_A_TILE);
-          const uint64_t b0 = make_desc_k_sw64(smem_b + s * I8_B_STAGE);
+          const uint64_t a0 = make_desc_k_sw64(smem_a + uint32_t(kb * a_res) * I8_A_TILE);
+          const uint64_t b0 = make_desc_k_sw64(smem_b + s * stage_bytes);
+          const uint64_t as0 = b0 + uint64_t(I8_B_STAGE >> 4);   // streamed activation planes follow the weight planes
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < I8_KC / 32; ++kk) {
               const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-              // digit pair (s, t) contributes to order o = s + t; orders above 3 are below 2^-32 and dropped
+              // Activation digit s meets the weight digits 0 .. 3-s in ONE MMA: the four weight planes of a stage are
+              // contiguous 64-row blocks of one K-major tile, so N = 64 (4 - s) output columns are the products
+              // a_s b_0 | a_s b_1 | ... and land on the accumulators of orders s, s+1, ..., 3.  Products of order
+              // above 3 (below 2^-32) are never formed.  Wide MMAs run at the tensor rate; N = 64 ones are bound by
+              // the shared-memory reads of the activation tile.
 #pragma unroll
-              for (int o = 0; o < I8_DIGITS; ++o) {
-#pragma unroll
-                for (int sa = 0; sa <= o; ++sa)
-                  if (sa < a_planes)
-                    umma_i8(acc_base + o * I8_BN, a0 + uint64_t((sa * I8_A_TILE + kk * 32) >> 4),
-                            b0 + uint64_t(((o - sa) * I8_B_TILE + kk * 32) >> 4), idesc, sa == 0 ? acc : 1u);
+              for (int sa = 0; sa < I8_DIGITS; ++sa) {
+                if (sa < a_planes) {
+                  const uint64_t ad = (sa < a_res ? a0 + uint64_t((sa * I8_A_TILE) >> 4) : as0 + uint64_t(((sa - a_res) * I8_A_TILE) >> 4)) +
+                                      uint64_t((kk * 32) >> 4);
+                  umma_i8(acc_base + sa * I8_BN, ad, b0 + uint64_t((kk * 32) >> 4), make_idesc_i8(I8_BM, (I8_DIGITS - sa) * I8_BN),
+                          sa == 0 ? acc : 1u);
+                }
               }
             }
             umma_commit(smem_u32(&b_empty[s]));                          // weight stage free once these MMAs have read it
@@ -305,25 +314,26 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
         if (!ok) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_d + buf * I8_ACC_COLS + (uint32_t(q * 32) << 16);
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = half * 32 + cc * 16;
-          uint32_t r0[16], r1[16], r2[16], r3[16];
-          tmem_ld16_u32(taddr + c, r0);
-          tmem_ld16_u32(taddr + I8_BN + c, r1);
-          tmem_ld16_u32(taddr + 2 * I8_BN + c, r2);
-          tmem_ld16_u32(taddr + 3 * I8_BN + c, r3);
+        uint32_t r0[32], r1[32], r2[32], r3[32];   // this thread's 32 columns of the four orders
+        {
+          const int c = half * 32;
+          tmem_ld32_u32(taddr + c, r0);
+          tmem_ld32_u32(taddr + I8_BN + c, r1);
+          tmem_ld32_u32(taddr + 2 * I8_BN + c, r2);
+          tmem_ld32_u32(taddr + 3 * I8_BN + c, r3);
           tmem_ld_wait();
-          if (cc == 1) {  // everything is in registers: hand the accumulator set back before the math
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(smem_u32(&acc_empty[buf]));
-          }
-          const int nb = j * I8_BN + c;   // first output of this chunk
-          float dq[16];                   // ACT_HEAD: swish' values to be quantised
+          // everything is in registers: hand the accumulator set back before the math
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(smem_u32(&acc_empty[buf]));
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int nb = j * I8_BN + half * 32 + cc * 16;   // first output of this chunk
+          float dq[16];                                     // ACT_HEAD: swish' values to be quantised
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int n = nb + i;
-            const float y = i8_combine(r0[i], r1[i], r2[i], r3[i]) * scale;
+            const int n = nb + i, ri = cc * 16 + i;
+            const float y = i8_combine(r0[ri], r1[ri], r2[ri], r3[ri]) * scale;
             const int64_t o = int64_t(n) * epi.ld + m;
             if (MODE == I8_EPI_STORE) {
               if (n < epi.n_valid) epi.out[o] = y;
@@ -495,7 +505,7 @@ int make_plane_tmap(CUtensorMap* tm, const I8Planes& p, int box_rows) {
 
 struct I8Launch {
   CUtensorMap ta, tb;
-  int num_kb, a_planes, num_m_tiles, num_n_sub, b_stages, grid;
+  int num_kb, a_planes, a_res, num_m_tiles, num_n_sub, b_stages, grid;
   uint32_t smem;
 };
 
@@ -517,7 +527,7 @@ int prepare_i8(Kern kern) {
       prepared = true;                                                                                               \
     }                                                                                                                \
     APAX_LAUNCH(name, dim3((unsigned)L.grid), dim3(I8_THREADS), L.smem, stream, L.ta, L.tb, L.num_kb, L.a_planes,    \
-                L.num_m_tiles, L.num_n_sub, L.b_stages, epi, err_flag);                                              \
+                L.a_res, L.num_m_tiles, L.num_n_sub, L.b_stages, epi, err_flag);                                     \
     return APAX_OK;                                                                                                  \
   } while (0)
 
@@ -593,12 +603,20 @@ int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const
   L.num_m_tiles = int(act.rows / I8_BM);
   L.num_n_sub = int(wgt.rows / I8_BN);
   L.grid = L.num_m_tiles < n_sm ? L.num_m_tiles : n_sm;   // one persistent CTA per SM (it owns the SM's whole TMEM)
-  const uint32_t a_bytes = uint32_t(L.num_kb * L.a_planes) * I8_A_TILE;
-  if (a_bytes + 2 * I8_B_STAGE + 10240 > I8_SMEM_LIMIT) return APAX_ERR_INVALID_ARG;
-  const uint32_t budget = I8_SMEM_LIMIT - 10240 /* static + alignment */ - a_bytes;
-  L.b_stages = int(budget / I8_B_STAGE);
+  // as many activation planes as fit stay resident next to a ring of at least three weight stages; the least
+  // significant planes (used by the fewest MMAs) travel with the stages otherwise
+  const uint32_t budget = I8_SMEM_LIMIT - 10240 /* static + alignment */;
+  L.a_res = L.a_planes;
+  uint32_t a_bytes, stage_bytes;
+  for (;; --L.a_res) {
+    a_bytes = uint32_t(L.num_kb * L.a_res) * I8_A_TILE;
+    stage_bytes = I8_B_STAGE + uint32_t(L.a_planes - L.a_res) * I8_A_TILE;
+    if (a_bytes + 3 * stage_bytes <= budget) break;
+    if (L.a_res == 0) return APAX_ERR_INVALID_ARG;
+  }
+  L.b_stages = int((budget - a_bytes) / stage_bytes);
   if (L.b_stages > I8_MAX_B_STAGES) L.b_stages = I8_MAX_B_STAGES;
-  L.smem = a_bytes + uint32_t(L.b_stages) * I8_B_STAGE + 1024;
+  L.smem = a_bytes + uint32_t(L.b_stages) * stage_bytes + 1024;
   switch (epi.mode) {
     case I8_EPI_STORE: I8_LAUNCH(k_i8_gemm_store, I8_EPI_STORE, 1);
     case I8_EPI_ACT_Q: I8_LAUNCH(k_i8_gemm_act_q, I8_EPI_ACT_Q, 1);
@@ -658,4 +676,92 @@ extern "C" int apax_i8_gemm_test(apax_stream_t stream_, const float* act, int64_
   cudaFree(d_e);
   cudaFree(d_mx);
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MMA issue-rate probe (measurement only): one CTA per SM issues `iters` rounds of tcgen05.mma kind::i8 on whatever
+// shared memory holds and reports elapsed SM cycles.  pattern 0: one accumulator, fixed descriptors; 1: four
+// accumulators in rotation, fixed descriptors; 2: the GEMM's ten digit-pair MMAs (four A tiles, four B tiles).
+// ------------------------------------------------------------------------------------------------
+namespace apax {
+namespace {
+using namespace tcptx;
+template <int N>
+__global__ void __launch_bounds__(128, 1) k_i8_mma_probe(int pattern, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  for (uint32_t i = threadIdx.x; i < 96 * 1024 / 4; i += 128)
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + i * 4), "r"(0x01010101u) : "memory");
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&done_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_slot;
+  if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_i8(128, N);
+    constexpr uint32_t B_TILE = N * 64;
+    const uint64_t a0 = make_desc_k_sw64(base), b0 = make_desc_k_sw64(base + 4 * I8_A_TILE);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one()) {
+        if (pattern == 0) {
+#pragma unroll
+          for (int i = 0; i < 10; ++i) umma_i8(tmem_d, a0, b0, idesc, 1u);
+        } else if (pattern == 1) {
+#pragma unroll
+          for (int i = 0; i < 10; ++i) umma_i8(tmem_d + (N > 128 ? (i & 1) * 256 : (i & 3) * N), a0, b0, idesc, 1u);
+        } else {
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int sa = 0; sa <= o; ++sa)
+              umma_i8(tmem_d + (N > 128 ? (o & 1) * 256 : o * N), a0 + uint64_t((sa * I8_A_TILE + (it & 1) * 32) >> 4),
+                      b0 + uint64_t(((o - sa) * B_TILE + (it & 1) * 32) >> 4), idesc, 1u);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(smem_u32(&done_bar));
+    __syncwarp();
+    int32_t dummy = 0;
+    mbar_wait_warp(smem_u32(&done_bar), 0, &dummy);
+    if (threadIdx.x == 32) out[blockIdx.x] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
+}
+}  // namespace
+}  // namespace apax
+
+extern "C" int apax_i8_mma_probe(apax_stream_t stream_, int32_t n, int32_t pattern, int32_t iters, int64_t* out_cycles) {
+  using namespace apax;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int smem = 100 * 1024;
+  if (n == 64) {
+    APAX_CUDA_TRY(cudaFuncSetAttribute(k_i8_mma_probe<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_i8_mma_probe<64><<<148, 128, smem, stream>>>(pattern, iters, reinterpret_cast<long long*>(out_cycles));
+  } else if (n == 128) {
+    APAX_CUDA_TRY(cudaFuncSetAttribute(k_i8_mma_probe<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_i8_mma_probe<128><<<148, 128, smem, stream>>>(pattern, iters, reinterpret_cast<long long*>(out_cycles));
+  } else if (n == 256) {
+    APAX_CUDA_TRY(cudaFuncSetAttribute(k_i8_mma_probe<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_i8_mma_probe<256><<<148, 128, smem, stream>>>(pattern, iters, reinterpret_cast<long long*>(out_cycles));
+  } else {
+    return APAX_ERR_INVALID_ARG;
+  }
+  APAX_CUDA_TRY(cudaGetLastError());
+  return APAX_OK;
 }

@@ -8,7 +8,7 @@ from apax_b200 import runtime as rt
 
 n_atoms = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_064
 dev = torch.device("cuda")
-for k, nc in [(360, 256), (256, 256), (256, 360)]:
+for k, nc, planes in [(360, 256, 4), (360, 256, 3), (256, 256, 4), (256, 360, 4)]:
     ld = (n_atoms + 127) // 128 * 128
     act = torch.randn(k, ld, device=dev)
     wgt = torch.randn(k, nc, device=dev) / np.sqrt(k)
@@ -17,7 +17,7 @@ for k, nc in [(360, 256), (256, 256), (256, 360)]:
     dbg = torch.zeros(148 * 8, device=dev, dtype=torch.int64)
 
     def go():
-        rc = rt.lib().apax_i8_gemm_test(rt._stream_ptr(), rt._ptr(act), k, ld, n_atoms, rt._ptr(wgt), nc, rt._ptr(out), rt._ptr(err), rt._ptr(dbg), 3 if k > 256 else 4)
+        rc = rt.lib().apax_i8_gemm_test(rt._stream_ptr(), rt._ptr(act), k, ld, n_atoms, rt._ptr(wgt), nc, rt._ptr(out), rt._ptr(err), rt._ptr(dbg), planes)
         assert rc == 0
 
     go(); go()
