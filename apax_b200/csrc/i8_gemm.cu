@@ -2,6 +2,7 @@
 #include "i8_gemm.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 #include "tc_ptx.cuh"
 
@@ -60,8 +61,83 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity, int32_t* err) {
   return __all_sync(0xffffffffu, mbar_wait(bar, parity, err));
 }
+// Bounded wait that never changes control flow: the TMA and MMA warps must stay provably warp-uniform (descriptors
+// in uniform registers, no per-MMA register -> uniform-register moves), so a time-out only raises the error flag
+// and marks the CTA dead, after which every later wait returns at once and the kernel drains quickly.
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_soft(uint32_t bar, uint32_t parity, int32_t* err, volatile int* dead) {
+  if (*dead) return;
+  // non-blocking polls: the pipeline hand-offs are on the critical path, a suspended try_wait wakes up too late
+  for (uint32_t it = 0; it < (kSpinLimit << 4); ++it)
+    if (mbar_test_wait(bar, parity)) return;
+  atomicExch(err, 1);
+  *dead = 1;
+}
 __device__ __forceinline__ void epi_bar_sync() {   // named barrier 1: the 256 epilogue threads only
   asm volatile("bar.sync 1, %0;" ::"n"(I8_EPI_THREADS) : "memory");
+}
+
+// All MMAs of up to two 64-byte k-blocks as ONE instruction burst.  The tensor pipe queues only an MMA or two, so
+// whatever the issuing warp does between MMAs (barrier polls, descriptor arithmetic, commits) is time the pipe
+// idles: every operand is therefore an input of a single asm statement (descriptors sit in uniform registers before
+// the burst starts), two k-blocks share one hand-shake, and the burst ends with its widest MMAs (N = 256, 128
+// cycles each) so that the pipe still has work while the warp goes through the next hand-shake.
+//   activation digit s (descriptor a_s) x weight planes 0 .. 3-s (descriptor b, N = 64 (4 - s)) -> accumulators s..3
+//   order: a0 of the first k-slice (it may zero-initialise all four accumulators), then digits 3, 2, 1, then the rest of a0
+__device__ __forceinline__ void umma_i8_burst(uint32_t tm0, uint32_t tm1, uint32_t tm2, uint32_t tm3, uint64_t a00,
+                                              uint64_t a01, uint64_t a02, uint64_t a03, uint64_t a10, uint64_t a11,
+                                              uint64_t a12, uint64_t a13, uint64_t b0, uint64_t b1, uint32_t id256,
+                                              uint32_t id192, uint32_t id128, uint32_t id64, uint32_t acc_first,
+                                              uint32_t have3, uint32_t have_kb1) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, p3, p1, p31, pt;\n\t"
+      ".reg .b64 a0b, a1b, a2b, a3b, a0c, a1c, a2c, a3c, a0d, a1d, a2d, a3d, b0b, b1b;\n\t"
+      "setp.ne.b32 pacc, %18, 0;\n\t"
+      "setp.ne.b32 p3, %19, 0;\n\t"
+      "setp.ne.b32 p1, %20, 0;\n\t"
+      "and.pred p31, p3, p1;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "add.s64 a0b, %4, 2;\n\t"
+      "add.s64 a1b, %5, 2;\n\t"
+      "add.s64 a2b, %6, 2;\n\t"
+      "add.s64 a3b, %7, 2;\n\t"
+      "add.s64 a0d, %8, 2;\n\t"
+      "add.s64 a1d, %9, 2;\n\t"
+      "add.s64 a2d, %10, 2;\n\t"
+      "add.s64 a3d, %11, 2;\n\t"
+      "add.s64 b0b, %12, 2;\n\t"
+      "add.s64 b1b, %13, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %4, %12, %14, pacc;\n\t"
+      "@p3 tcgen05.mma.cta_group::1.kind::i8 [%3], %7, %12, %17, pt;\n\t"
+      "@p3 tcgen05.mma.cta_group::1.kind::i8 [%3], a3b, b0b, %17, pt;\n\t"
+      "@p31 tcgen05.mma.cta_group::1.kind::i8 [%3], %11, %13, %17, pt;\n\t"
+      "@p31 tcgen05.mma.cta_group::1.kind::i8 [%3], a3d, b1b, %17, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%2], %6, %12, %16, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%2], a2b, b0b, %16, pt;\n\t"
+      "@p1 tcgen05.mma.cta_group::1.kind::i8 [%2], %10, %13, %16, pt;\n\t"
+      "@p1 tcgen05.mma.cta_group::1.kind::i8 [%2], a2d, b1b, %16, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], %5, %12, %15, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%1], a1b, b0b, %15, pt;\n\t"
+      "@p1 tcgen05.mma.cta_group::1.kind::i8 [%1], %9, %13, %15, pt;\n\t"
+      "@p1 tcgen05.mma.cta_group::1.kind::i8 [%1], a1d, b1b, %15, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], a0b, b0b, %14, pt;\n\t"
+      "@p1 tcgen05.mma.cta_group::1.kind::i8 [%0], %8, %13, %14, pt;\n\t"
+      "@p1 tcgen05.mma.cta_group::1.kind::i8 [%0], a0d, b1b, %14, pt;\n\t"
+      "}"
+      ::"r"(tm0), "r"(tm1), "r"(tm2), "r"(tm3), "l"(a00), "l"(a01), "l"(a02), "l"(a03), "l"(a10), "l"(a11), "l"(a12),
+      "l"(a13), "l"(b0), "l"(b1), "r"(id256), "r"(id192), "r"(id128), "r"(id64), "r"(acc_first), "r"(have3), "r"(have_kb1)
+      : "memory");
 }
 
 // ---- digits.  Balanced base-256 digits of I = rn(v), all at once: adding 128 to each low byte (with the
@@ -146,6 +222,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ int cta_dead;
   __shared__ float xmax[2][I8_BM];            // row-maximum exchange between the two column halves
   __shared__ float xhead[I8_BM * NOUT];       // head partial sums of the second column half
 
@@ -156,6 +233,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
   const uint32_t stage_bytes = I8_B_STAGE + uint32_t(a_planes - a_res) * I8_A_TILE;
 
   if (threadIdx.x == 0) {
+    cta_dead = 0;
     for (int i = 0; i < I8_MAX_KB; ++i) {
       mbar_init(smem_u32(&a_full[i]), 1);
       mbar_init(smem_u32(&a_empty[i]), 1);
@@ -185,15 +263,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (warp-uniform, elected lane issues)
     uint32_t bit = 0;
-    bool ok = true;
-    for (int mt = 0; mt < my_m_tiles && ok; ++mt) {
+    for (int mt = 0; mt < my_m_tiles; ++mt) {
       const int m0 = (int(blockIdx.x) + mt * int(gridDim.x)) * I8_BM;
-      for (int j = 0; j < num_n_sub && ok; ++j) {
+      for (int j = 0; j < num_n_sub; ++j) {
         for (int kb = 0; kb < num_kb; ++kb, ++bit) {
           if (j == 0) {   // the atom tile's planes of this k-block: resident for the whole output sweep
-            ok = mbar_wait_warp(smem_u32(&a_empty[kb]), (uint32_t(mt) & 1) ^ 1, err);
-            if (!ok) break;
-            if (elect_one()) {
+            mbar_wait_soft(smem_u32(&a_empty[kb]), (uint32_t(mt) & 1) ^ 1, err, &cta_dead);
+            if (epi.dbg_flags & 2) {
+              if (elect_one()) mbar_arrive(smem_u32(&a_full[kb]));
+            } else if (elect_one()) {
               const uint32_t bar = smem_u32(&a_full[kb]);
               mbar_expect_tx(bar, uint32_t(a_res) * I8_A_TILE);
               for (int d = 0; d < a_res; ++d)
@@ -202,9 +280,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
             __syncwarp();
           }
           const uint32_t s = bit % uint32_t(b_stages), phase = (bit / uint32_t(b_stages)) & 1;
-          ok = mbar_wait_warp(smem_u32(&b_empty[s]), phase ^ 1, err);
-          if (!ok) break;
-          if (elect_one()) {
+          mbar_wait_soft(smem_u32(&b_empty[s]), phase ^ 1, err, &cta_dead);
+          if (epi.dbg_flags & 2) {
+            if (elect_one()) mbar_arrive(smem_u32(&b_full[s]));
+          } else if (elect_one()) {
             const uint32_t bar = smem_u32(&b_full[s]);
             mbar_expect_tx(bar, stage_bytes);
 #pragma unroll
@@ -220,67 +299,63 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform, elected lane issues)
     uint32_t bit = 0, tile = 0;
-    bool ok = true;
-    long long w_acc = 0, w_a = 0, w_b = 0, t_begin = clock64();
-    for (int mt = 0; mt < my_m_tiles && ok; ++mt) {
-      for (int j = 0; j < num_n_sub && ok; ++j, ++tile) {
+    const long long t_begin = clock64();
+    // 16-byte-unit offsets of the four activation planes: resident ones relative to the k-block's resident slot,
+    // streamed ones relative to the weight stage
+    uint32_t a_off[I8_DIGITS];
+#pragma unroll
+    for (int sa = 0; sa < I8_DIGITS; ++sa)
+      a_off[sa] = sa < a_res ? uint32_t(sa) * (I8_A_TILE >> 4) : (I8_B_STAGE >> 4) + uint32_t(sa - a_res) * (I8_A_TILE >> 4);
+    for (int mt = 0; mt < my_m_tiles; ++mt) {
+      for (int j = 0; j < num_n_sub; ++j, ++tile) {
         const uint32_t buf = tile & 1, use = tile >> 1;
-        long long c0 = clock64();
-        ok = mbar_wait_warp(smem_u32(&acc_empty[buf]), (use & 1) ^ 1, err);   // epilogue has drained this set
-        w_acc += clock64() - c0;
-        if (!ok) break;
+        mbar_wait_soft(smem_u32(&acc_empty[buf]), (use & 1) ^ 1, err, &cta_dead);   // epilogue has drained this set
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc_base = tmem_d + buf * I8_ACC_COLS;
-        for (int kb = 0; kb < num_kb; ++kb, ++bit) {
+        for (int kb = 0; kb < num_kb; kb += 2, bit += 2) {
+          const bool two = kb + 1 < num_kb;   // k-blocks are issued in pairs (one hand-shake per sixteen MMAs)
+          const uint32_t s0 = bit % uint32_t(b_stages), ph0 = (bit / uint32_t(b_stages)) & 1;
+          const uint32_t s1 = (bit + 1) % uint32_t(b_stages), ph1 = ((bit + 1) / uint32_t(b_stages)) & 1;
           if (j == 0) {
-            c0 = clock64();
-            ok = mbar_wait_warp(smem_u32(&a_full[kb]), uint32_t(mt) & 1, err);
-            w_a += clock64() - c0;
-            if (!ok) break;
+            mbar_wait_soft(smem_u32(&a_full[kb]), uint32_t(mt) & 1, err, &cta_dead);
+            if (two) mbar_wait_soft(smem_u32(&a_full[kb + 1]), uint32_t(mt) & 1, err, &cta_dead);
           }
-          const uint32_t s = bit % uint32_t(b_stages), phase = (bit / uint32_t(b_stages)) & 1;
-          c0 = clock64();
-          ok = mbar_wait_warp(smem_u32(&b_full[s]), phase, err);
-          w_b += clock64() - c0;
-          if (!ok) break;
+          mbar_wait_soft(smem_u32(&b_full[s0]), ph0, err, &cta_dead);
+          if (two) mbar_wait_soft(smem_u32(&b_full[s1]), ph1, err, &cta_dead);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          // descriptors of plane d / k-slice kk differ from the first one only in the 16-byte-unit start address
-          const uint64_t a0 = make_desc_k_sw64(smem_a + uint32_t(kb * a_res) * I8_A_TILE);
-          const uint64_t b0 = make_desc_k_sw64(smem_b + s * stage_bytes);
-          const uint64_t as0 = b0 + uint64_t(I8_B_STAGE >> 4);   // streamed activation planes follow the weight planes
+          // Activation digit s meets the weight digits 0 .. 3-s in ONE MMA: the four weight planes of a stage are
+          // contiguous 64-row blocks of one K-major tile, so N = 64 (4 - s) output columns are the products
+          // a_s b_0 | a_s b_1 | ... and land on the accumulators of orders s, s+1, ..., 3.  Products of order above 3
+          // (below 2^-32) are never formed.
+          const uint64_t ar0 = make_desc_k_sw64(smem_a + uint32_t(kb * a_res) * I8_A_TILE);
+          const uint64_t ar1 = ar0 + uint64_t((uint32_t(a_res) * I8_A_TILE) >> 4);
+          const uint64_t b0 = make_desc_k_sw64(smem_b + s0 * stage_bytes);
+          const uint64_t b1 = make_desc_k_sw64(smem_b + s1 * stage_bytes);
+          uint64_t ad0[I8_DIGITS], ad1[I8_DIGITS];
+#pragma unroll
+          for (int sa = 0; sa < I8_DIGITS; ++sa) {
+            ad0[sa] = (sa < a_res ? ar0 : b0) + uint64_t(a_off[sa]);
+            ad1[sa] = (sa < a_res ? ar1 : b1) + uint64_t(a_off[sa]);
+          }
           if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < I8_KC / 32; ++kk) {
-              const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-              // Activation digit s meets the weight digits 0 .. 3-s in ONE MMA: the four weight planes of a stage are
-              // contiguous 64-row blocks of one K-major tile, so N = 64 (4 - s) output columns are the products
-              // a_s b_0 | a_s b_1 | ... and land on the accumulators of orders s, s+1, ..., 3.  Products of order
-              // above 3 (below 2^-32) are never formed.  Wide MMAs run at the tensor rate; N = 64 ones are bound by
-              // the shared-memory reads of the activation tile.
-#pragma unroll
-              for (int sa = 0; sa < I8_DIGITS; ++sa) {
-                if (sa < a_planes) {
-                  const uint64_t ad = (sa < a_res ? a0 + uint64_t((sa * I8_A_TILE) >> 4) : as0 + uint64_t(((sa - a_res) * I8_A_TILE) >> 4)) +
-                                      uint64_t((kk * 32) >> 4);
-                  umma_i8(acc_base + sa * I8_BN, ad, b0 + uint64_t((kk * 32) >> 4), make_idesc_i8(I8_BM, (I8_DIGITS - sa) * I8_BN),
-                          sa == 0 ? acc : 1u);
-                }
-              }
+            umma_i8_burst(acc_base, acc_base + I8_BN, acc_base + 2 * I8_BN, acc_base + 3 * I8_BN, ad0[0], ad0[1], ad0[2], ad0[3],
+                          ad1[0], ad1[1], ad1[2], ad1[3], b0, b1, make_idesc_i8(I8_BM, 4 * I8_BN),
+                          make_idesc_i8(I8_BM, 3 * I8_BN), make_idesc_i8(I8_BM, 2 * I8_BN), make_idesc_i8(I8_BM, I8_BN),
+                          kb != 0 ? 1u : 0u, a_planes > 3 ? 1u : 0u, two ? 1u : 0u);
+            umma_commit(smem_u32(&b_empty[s0]));                 // weight stages free once these MMAs have read them
+            if (two) umma_commit(smem_u32(&b_empty[s1]));
+            if (j == num_n_sub - 1) {                            // last sweep over these atom k-blocks
+              umma_commit(smem_u32(&a_empty[kb]));
+              if (two) umma_commit(smem_u32(&a_empty[kb + 1]));
             }
-            umma_commit(smem_u32(&b_empty[s]));                          // weight stage free once these MMAs have read it
-            if (j == num_n_sub - 1) umma_commit(smem_u32(&a_empty[kb]));  // last sweep over this atom k-block
-            if (kb == num_kb - 1) umma_commit(smem_u32(&acc_full[buf]));
+            if (kb + 2 >= num_kb) umma_commit(smem_u32(&acc_full[buf]));
           }
           __syncwarp();
+          if (!two) --bit;   // an odd last k-block advanced the ring by one stage only
         }
       }
     }
-    if (epi.dbg && lane == 0) {
-      epi.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
-      epi.dbg[blockIdx.x * 8 + 1] = w_acc;
-      epi.dbg[blockIdx.x * 8 + 2] = w_b;
-      epi.dbg[blockIdx.x * 8 + 3] = w_a;
-    }
+    if (epi.dbg && lane == 0) epi.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
   } else {
     // -------------------------------------------------------------------- epilogue warps: lane == atom
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
@@ -315,6 +390,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_d + buf * I8_ACC_COLS + (uint32_t(q * 32) << 16);
         uint32_t r0[32], r1[32], r2[32], r3[32];   // this thread's 32 columns of the four orders
+        if (epi.dbg_flags & 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(smem_u32(&acc_empty[buf]));
+          continue;
+        }
         {
           const int c = half * 32;
           tmem_ld32_u32(taddr + c, r0);
@@ -585,7 +665,9 @@ void i8_quantize_weights(const float* W, int K, int NC, int ldw, int kp, int ncp
   for (int k = K; k < kp; ++k) col_scale[k] = 1.0f;
 }
 
-int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const I8Epilogue& epi, int32_t* err_flag) {
+int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const I8Epilogue& epi_in, int32_t* err_flag) {
+  const I8Epilogue& epi0 = epi_in;
+  (void)epi0;
   if (act.kp != wgt.kp || act.kp % I8_KC != 0 || act.kp / I8_KC > I8_MAX_KB || act.rows % I8_BM != 0 ||
       wgt.rows % I8_BN != 0 || wgt.n_planes != I8_DIGITS || (act.n_planes != 3 && act.n_planes != 4))
     return APAX_ERR_INVALID_ARG;
@@ -595,6 +677,8 @@ int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const
     APAX_CUDA_TRY(cudaGetDevice(&dev));
     APAX_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
+  I8Epilogue epi = epi_in;
+  if (const char* f = getenv("APAX_I8_DBG")) epi.dbg_flags = atoi(f);
   I8Launch L;
   APAX_TRY(make_plane_tmap(&L.ta, act, I8_BM));
   APAX_TRY(make_plane_tmap(&L.tb, wgt, I8_BN));
@@ -679,24 +763,38 @@ extern "C" int apax_i8_gemm_test(apax_stream_t stream_, const float* act, int64_
 }
 
 // ------------------------------------------------------------------------------------------------
-// MMA issue-rate probe (measurement only): one CTA per SM issues `iters` rounds of tcgen05.mma kind::i8 on whatever
-// shared memory holds and reports elapsed SM cycles.  pattern 0: one accumulator, fixed descriptors; 1: four
-// accumulators in rotation, fixed descriptors; 2: the GEMM's ten digit-pair MMAs (four A tiles, four B tiles).
+// Tensor-pipe / tensor-memory probe (measurement only): one CTA per SM.  Warp 4 issues `iters` rounds of ten
+// tcgen05.mma kind::i8 (pattern 0: one accumulator; 1: four accumulators; 2: the GEMM's digit-pair schedule;
+// < 0: none) on whatever shared memory holds; warps 0-3 meanwhile drain all 512 TMEM columns `reads` times with
+// tcgen05.ld.32x32b.x32.  out[cta][0] = MMA cycles, out[cta][1] = drain cycles of warp 0.
 // ------------------------------------------------------------------------------------------------
 namespace apax {
 namespace {
 using namespace tcptx;
 template <int N>
-__global__ void __launch_bounds__(128, 1) k_i8_mma_probe(int pattern, int iters, long long* out) {
+__global__ void __launch_bounds__(160, 1) k_i8_mma_probe(int pattern, int iters, int reads, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t done_bar;
+  __shared__ __align__(8) uint64_t side_bar;
+  __shared__ __align__(8) uint64_t ready_bar;
   __shared__ uint32_t tmem_base_slot;
   const int warp = threadIdx.x >> 5;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  for (uint32_t i = threadIdx.x; i < 96 * 1024 / 4; i += 128)
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + i * 4), "r"(0x01010101u) : "memory");
+  const bool random_data = (pattern & 16) != 0;   // constant operands toggle few wires; random ones load the data paths
+  if (pattern >= 0) pattern &= 15;
+  for (uint32_t i = threadIdx.x; i < 96 * 1024 / 4; i += 160) {
+    uint32_t v = 0x01010101u;
+    if (random_data) {
+      v = (i + blockIdx.x * 7919u) * 2654435761u;
+      v ^= v >> 15; v *= 2246822519u; v ^= v >> 13;
+    }
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + i * 4), "r"(v) : "memory");
+  }
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&done_bar), 1);
+    mbar_init(smem_u32(&side_bar), 1);
+    mbar_init(smem_u32(&ready_bar), 1);
+    mbar_arrive(smem_u32(&ready_bar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -709,35 +807,71 @@ __global__ void __launch_bounds__(128, 1) k_i8_mma_probe(int pattern, int iters,
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_slot;
-  if (warp == 1) {
+  if (warp == 4) {
     constexpr uint32_t idesc = make_idesc_i8(128, N);
     constexpr uint32_t B_TILE = N * 64;
     const uint64_t a0 = make_desc_k_sw64(base), b0 = make_desc_k_sw64(base + 4 * I8_A_TILE);
     const long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
-      if (elect_one()) {
-        if (pattern == 0) {
+    if (pattern >= 0) {
+      for (int it = 0; it < iters; ++it) {
+        if (elect_one()) {
+          if (pattern == 0) {
 #pragma unroll
-          for (int i = 0; i < 10; ++i) umma_i8(tmem_d, a0, b0, idesc, 1u);
-        } else if (pattern == 1) {
+            for (int i = 0; i < 10; ++i) umma_i8(tmem_d, a0, b0, idesc, 1u);
+          } else if (pattern == 1) {
 #pragma unroll
-          for (int i = 0; i < 10; ++i) umma_i8(tmem_d + (N > 128 ? (i & 1) * 256 : (i & 3) * N), a0, b0, idesc, 1u);
-        } else {
+            for (int i = 0; i < 10; ++i) umma_i8(tmem_d + (N > 128 ? (i & 1) * 256 : (i & 3) * N), a0, b0, idesc, 1u);
+          } else if (pattern == 2) {
 #pragma unroll
-          for (int o = 0; o < 4; ++o)
+            for (int o = 0; o < 4; ++o)
 #pragma unroll
-            for (int sa = 0; sa <= o; ++sa)
-              umma_i8(tmem_d + (N > 128 ? (o & 1) * 256 : o * N), a0 + uint64_t((sa * I8_A_TILE + (it & 1) * 32) >> 4),
-                      b0 + uint64_t(((o - sa) * B_TILE + (it & 1) * 32) >> 4), idesc, 1u);
+              for (int sa = 0; sa <= o; ++sa)
+                umma_i8(tmem_d + (N > 128 ? (o & 1) * 256 : o * N), a0 + uint64_t((sa * I8_A_TILE + (it & 1) * 32) >> 4),
+                        b0 + uint64_t(((o - sa) * B_TILE + (it & 1) * 32) >> 4), idesc, 1u);
+          } else {   // the GEMM's merged schedule: digit s of the activations against 4 - s weight planes (ten products)
+#pragma unroll
+            for (int sa = 0; sa < 4; ++sa)
+              umma_i8(tmem_d + sa * 64, a0 + uint64_t((sa * I8_A_TILE + (it & 1) * 32) >> 4), b0 + uint64_t(((it & 1) * 32) >> 4),
+                      make_idesc_i8(128, (4 - sa) * 64), 1u);
+            if (pattern >= 4 && (it & 1)) umma_commit(smem_u32(&side_bar));   // one commit per "k-block" of 8 MMAs
+          }
+        }
+        __syncwarp();
+        if (pattern >= 5 && (it & 1)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (pattern >= 6 && (it & 1)) {
+          int32_t dummy = 0;
+          mbar_wait(smem_u32(&ready_bar), 0, &dummy);   // long since complete
+        }
+        if (pattern >= 7 && (it & 1)) {
+          int32_t dummy = 0;
+          mbar_wait(smem_u32(&side_bar), (uint32_t(it >> 1) & 1), &dummy);   // wait for this k-block's own commit
         }
       }
+      if (elect_one()) umma_commit(smem_u32(&done_bar));
       __syncwarp();
+      int32_t dummy = 0;
+      mbar_wait_warp(smem_u32(&done_bar), 0, &dummy);
     }
-    if (elect_one()) umma_commit(smem_u32(&done_bar));
-    __syncwarp();
-    int32_t dummy = 0;
-    mbar_wait_warp(smem_u32(&done_bar), 0, &dummy);
-    if (threadIdx.x == 32) out[blockIdx.x] = clock64() - t0;
+    if (threadIdx.x == 128) out[blockIdx.x * 2] = clock64() - t0;
+  } else if (reads > 0) {
+    const uint32_t taddr = tmem_d + (uint32_t(warp * 32) << 16);
+    uint32_t sink = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < reads; ++it) {
+#pragma unroll 1
+      for (int c = 0; c < 512; c += 128) {
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        tmem_ld32_u32(taddr + c, r0);
+        tmem_ld32_u32(taddr + c + 32, r1);
+        tmem_ld32_u32(taddr + c + 64, r2);
+        tmem_ld32_u32(taddr + c + 96, r3);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sink ^= r0[i] ^ r1[i] ^ r2[i] ^ r3[i];
+      }
+    }
+    if (threadIdx.x == 0) out[blockIdx.x * 2 + 1] = clock64() - t0;
+    if (sink == 0x12345678u) out[blockIdx.x * 2 + 1] = 0;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -746,19 +880,21 @@ __global__ void __launch_bounds__(128, 1) k_i8_mma_probe(int pattern, int iters,
 }  // namespace
 }  // namespace apax
 
-extern "C" int apax_i8_mma_probe(apax_stream_t stream_, int32_t n, int32_t pattern, int32_t iters, int64_t* out_cycles) {
+extern "C" int apax_i8_mma_probe(apax_stream_t stream_, int32_t n, int32_t pattern, int32_t iters, int32_t reads,
+                                 int64_t* out_cycles) {
   using namespace apax;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int smem = 100 * 1024;
+  long long* out = reinterpret_cast<long long*>(out_cycles);
   if (n == 64) {
     APAX_CUDA_TRY(cudaFuncSetAttribute(k_i8_mma_probe<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_i8_mma_probe<64><<<148, 128, smem, stream>>>(pattern, iters, reinterpret_cast<long long*>(out_cycles));
+    k_i8_mma_probe<64><<<148, 160, smem, stream>>>(pattern, iters, reads, out);
   } else if (n == 128) {
     APAX_CUDA_TRY(cudaFuncSetAttribute(k_i8_mma_probe<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_i8_mma_probe<128><<<148, 128, smem, stream>>>(pattern, iters, reinterpret_cast<long long*>(out_cycles));
+    k_i8_mma_probe<128><<<148, 160, smem, stream>>>(pattern, iters, reads, out);
   } else if (n == 256) {
     APAX_CUDA_TRY(cudaFuncSetAttribute(k_i8_mma_probe<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_i8_mma_probe<256><<<148, 128, smem, stream>>>(pattern, iters, reinterpret_cast<long long*>(out_cycles));
+    k_i8_mma_probe<256><<<148, 160, smem, stream>>>(pattern, iters, reads, out);
   } else {
     return APAX_ERR_INVALID_ARG;
   }

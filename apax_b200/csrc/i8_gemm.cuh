@@ -81,6 +81,7 @@ struct I8Epilogue {
   int n_out;
   float* h_out;              // [n_out][ld]
   long long* dbg;            // optional [grid][8] cycle counters
+  int dbg_flags;             // measurement only: 1 = epilogue skips the drain, 2 = producer signals without loading
 };
 
 // activations: feature-major fp32 [K][ld] -> digit planes [n_planes][ld][kp] + per-atom exponents

@@ -237,10 +237,11 @@ int apax_i8_gemm_test(apax_stream_t stream, const float* act, int64_t k, int64_t
                       int64_t nc, float* out, int32_t* err_flag, int64_t* dbg_cycles /* nullable, [n_sm][8] */,
                       int32_t act_planes /* 3 or 4 digit planes for the activations */);
 
-/* Measurement only: issue rate of tcgen05.mma kind::i8 (M = 128, N = n) on one CTA per SM; writes elapsed SM
- * cycles per CTA for `iters` rounds of ten MMAs.  pattern 0 / 1 / 2: one accumulator / four accumulators /
- * the readout GEMM's digit-pair schedule. */
-int apax_i8_mma_probe(apax_stream_t stream, int32_t n, int32_t pattern, int32_t iters, int64_t* out_cycles);
+/* Measurement only: tcgen05.mma kind::i8 issue rate (M = 128, N = n; `iters` rounds of ten MMAs; pattern 0 / 1 / 2:
+ * one accumulator / four accumulators / the readout GEMM's digit-pair schedule; negative: none) and tensor-memory
+ * drain rate (`reads` passes of tcgen05.ld over all 512 columns by four warps), alone or concurrently, one CTA per
+ * SM.  out_cycles[cta][0] = MMA cycles, [cta][1] = drain cycles. */
+int apax_i8_mma_probe(apax_stream_t stream, int32_t n, int32_t pattern, int32_t iters, int32_t reads, int64_t* out_cycles);
 
 /* Readout GEMM building block on the tcgen05 tensor cores, exposed for tests and measurement:
  * out[nc][ld] = sum_k act[k][atom] * wgt[k][n] with both operands given as exact tf32 (hi, lo) pairs
