@@ -2,6 +2,7 @@
 #include "i8_gemm.cuh"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 #include "tc_ptx.cuh"
@@ -192,6 +193,28 @@ __device__ __forceinline__ void i8_emit16(const float (&v)[16], float sc, float 
     *reinterpret_cast<uint4*>(dst + d * plane_stride) = make_uint4(w[d][0], w[d][1], w[d][2], w[d][3]);
 }
 
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+// thirty-two values (already multiplied by their column scales) -> one full 32-byte sector per plane (256-bit stores:
+// a thread owns 32 consecutive outputs of its atom, i.e. exactly one sector of each plane's row)
+__device__ __forceinline__ void i8_emit32(const float (&v)[32], float sc, float sc2, int8_t* dst, int64_t plane_stride) {
+  uint32_t w[I8_DIGITS][8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint32_t ew[4], tb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ew[j] = i8_digit_word<4>((v[4 * q + j] * sc) * sc2);
+    i8_transpose4(ew, tb);
+#pragma unroll
+    for (int d = 0; d < I8_DIGITS; ++d) w[d][q] = tb[3 - d];
+  }
+#pragma unroll
+  for (int d = 0; d < I8_DIGITS; ++d) st_global_v8(dst + d * plane_stride, w[d]);
+}
+
 // int32 accumulators of the four orders -> fp32.  Order 0 (|.| < 2^22) and the rounded-down tails of orders 2 and 3
 // go through the exact magic-number conversion on the ALU pipes, order 1 through I2F; the shifts drop at most
 // 2^-15 of an order-0 unit, far below the fp32 rounding of the result.
@@ -366,7 +389,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
                          : nullptr;
     uint32_t tile = 0;
     bool ok = true;
-    long long w_wait = 0, t_begin = clock64();
+    long long w_wait = 0, w_phase2 = 0, t_begin = clock64();
     for (int mt = 0; mt < my_m_tiles && ok; ++mt) {
       const int64_t m = int64_t(int(blockIdx.x) + mt * int(gridDim.x)) * I8_BM + row;
       const float scale = exp2_int(epi.row_exp ? epi.row_exp[m] : epi.fixed_exp);
@@ -383,45 +406,53 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
       }
       for (int j = 0; j < num_n_sub && ok; ++j, ++tile) {
         const uint32_t buf = tile & 1, use = tile >> 1;
+        float auxv[32];   // MULD_Q: the multipliers of this sub-tile, requested before the wait so that their latency hides
+        if (MODE == I8_EPI_MULD_Q) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) auxv[i] = epi.aux[int64_t(j * I8_BN + half * 32 + i) * epi.ld + m];
+        }
         const long long c0 = clock64();
         ok = mbar_wait(smem_u32(&acc_full[buf]), use & 1, err);
         w_wait += clock64() - c0;
         if (!ok) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_d + buf * I8_ACC_COLS + (uint32_t(q * 32) << 16);
-        uint32_t r0[32], r1[32], r2[32], r3[32];   // this thread's 32 columns of the four orders
         if (epi.dbg_flags & 1) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(smem_u32(&acc_empty[buf]));
           continue;
         }
-        {
-          const int c = half * 32;
-          tmem_ld32_u32(taddr + c, r0);
-          tmem_ld32_u32(taddr + I8_BN + c, r1);
-          tmem_ld32_u32(taddr + 2 * I8_BN + c, r2);
-          tmem_ld32_u32(taddr + 3 * I8_BN + c, r3);
-          tmem_ld_wait();
-          // everything is in registers: hand the accumulator set back before the math
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(smem_u32(&acc_empty[buf]));
-        }
+        float dq[32];                                       // ACT_HEAD: swish' values to be quantised
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
-          const int nb = j * I8_BN + half * 32 + cc * 16;   // first output of this chunk
-          float dq[16];                                     // ACT_HEAD: swish' values to be quantised
+          const int c = half * 32 + cc * 16;
+          uint32_t r0[16], r1[16], r2[16], r3[16];          // sixteen columns of the four orders
+          tmem_ld16_u32(taddr + c, r0);
+          tmem_ld16_u32(taddr + I8_BN + c, r1);
+          tmem_ld16_u32(taddr + 2 * I8_BN + c, r2);
+          tmem_ld16_u32(taddr + 3 * I8_BN + c, r3);
+          tmem_ld_wait();
+          if (cc == 1) {  // everything is in registers: hand the accumulator set back before the math
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(smem_u32(&acc_empty[buf]));
+          }
+          const int nb = j * I8_BN + c;                     // first output of this chunk
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int n = nb + i, ri = cc * 16 + i;
-            const float y = i8_combine(r0[ri], r1[ri], r2[ri], r3[ri]) * scale;
+            const float y = i8_combine(r0[i], r1[i], r2[i], r3[i]) * scale;
             const int64_t o = int64_t(n) * epi.ld + m;
             if (MODE == I8_EPI_STORE) {
               if (n < epi.n_valid) epi.out[o] = y;
             } else if (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_ACT_HEAD) {
+              // variance_preserving_swish (activation.py:7-9) and its derivative.  The sigmoid goes through the two
+              // SFU approximations (ex2, rcp: ~1e-7 relative, unbiased) -- the epilogue is bound by instruction issue,
+              // and the libm expf + IEEE division cost four times as many instructions.
               const float z = y + __ldg(epi.bias + n);
-              const float sg = 1.0f / (1.0f + expf(-z));
-              const float h = kSwishI8 * z * sg;                           // variance_preserving_swish (activation.py:7-9)
-              const float d = kSwishI8 * sg * (1.0f + z * (1.0f - sg));    // its derivative, for the backward pass
+              const float sg = __fdividef(1.0f, 1.0f + __expf(-z));
+              const float cs = kSwishI8 * sg;
+              const float h = cs * z;
+              const float d = cs * fmaf(z, 1.0f - sg, 1.0f);
               if (MODE == I8_EPI_ACT_Q) {
                 epi.aux[o] = d;
                 scratch[int64_t(n) * I8_BM] = h;
@@ -431,23 +462,30 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
 #pragma unroll
                 for (int k = 0; k < NOUT; ++k)
                   if (k < epi.n_out) hacc[k] = fmaf(h, __ldg(epi.w_head + n * epi.n_out + k), hacc[k]);
-                dq[i] = d * __ldg(epi.q_col_scale + n);
+                dq[ri] = d * __ldg(epi.q_col_scale + n);
                 if (epi.out) epi.out[o] = d;
               }
             } else {
-              const float t = y * epi.aux[o] * rmul;
+              const float t = y * auxv[ri] * rmul;
               scratch[int64_t(n) * I8_BM] = t;
               mx = fmaxf(mx, fabsf(t * __ldg(epi.q_col_scale + n)));
               if (epi.out) epi.out[o] = t;
             }
           }
-          if (MODE == I8_EPI_ACT_HEAD)
-            i8_emit16(dq, qsc, qsc2, epi.q_planes + m * epi.q_kp + nb, epi.q_plane_stride);
         }
+        if (MODE == I8_EPI_ACT_HEAD)
+          i8_emit32(dq, qsc, qsc2, epi.q_planes + m * epi.q_kp + j * I8_BN + half * 32, epi.q_plane_stride);
       }
       if (!ok) break;
       // ---- end of the output sweep of this atom tile
       if (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_MULD_Q) {
+        // This thread staged the columns [j*64 + half*32, +32) of every sub-tile itself: re-read them (L2) and emit
+        // digits, one 32-byte sector per plane and sub-tile.  The loads do not depend on the row maximum, so the first
+        // batch is requested before the exchange.
+        const long long p0 = clock64();
+        float cur[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cur[i] = scratch[int64_t(half * 32 + i) * I8_BM];
         xmax[half][row] = mx;
         epi_bar_sync();
         mx = fmaxf(xmax[0][row], xmax[1][row]);
@@ -456,17 +494,18 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
         float sc, sc2;
         i8_row_scale(mx, 4, e, sc, sc2);
         if (half == 0) epi.q_row_exp[m] = e;
-        // this thread staged the columns [j*64 + half*32, +32) of every sub-tile itself: re-read and emit digits
-        for (int j = 0; j < num_n_sub; ++j) {
 #pragma unroll 1
-          for (int cc = 0; cc < 2; ++cc) {
-            const int nb = j * I8_BN + half * 32 + cc * 16;
-            float v[16];
+        for (int j = 0; j < num_n_sub; ++j) {
+          const int nb = j * I8_BN + half * 32;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = scratch[int64_t(nb + i) * I8_BM] * __ldg(epi.q_col_scale + nb + i);
-            i8_emit16(v, sc, sc2, epi.q_planes + m * epi.q_kp + nb, epi.q_plane_stride);
+          for (int i = 0; i < 32; ++i) cur[i] *= __ldg(epi.q_col_scale + nb + i);
+          i8_emit32(cur, sc, sc2, epi.q_planes + m * epi.q_kp + nb, epi.q_plane_stride);
+          if (j + 1 < num_n_sub) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) cur[i] = scratch[int64_t(nb + I8_BN + i) * I8_BM];
           }
         }
+        w_phase2 += clock64() - p0;
       } else if (MODE == I8_EPI_ACT_HEAD) {
         if (half == 1) {
 #pragma unroll
@@ -484,6 +523,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
     if (epi.dbg && threadIdx.x == 64) {
       epi.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin;
       epi.dbg[blockIdx.x * 8 + 5] = w_wait;
+      epi.dbg[blockIdx.x * 8 + 6] = w_phase2;
     }
   }
   __syncwarp();
@@ -679,6 +719,29 @@ int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const
   }
   I8Epilogue epi = epi_in;
   if (const char* f = getenv("APAX_I8_DBG")) epi.dbg_flags = atoi(f);
+  static const bool trace = getenv("APAX_I8_TRACE") != nullptr;   // measurement only: per-launch cycle counters to stderr
+  static long long* trace_buf = nullptr;
+  if (trace) {
+    if (!trace_buf) APAX_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&trace_buf), 256 * 8 * sizeof(long long)));
+    APAX_CUDA_TRY(cudaMemsetAsync(trace_buf, 0, 256 * 8 * sizeof(long long), stream));
+    epi.dbg = trace_buf;
+  }
+  struct TraceDump {
+    bool on; cudaStream_t st; long long* buf; int mode; int* grid;
+    ~TraceDump() {
+      if (!on) return;
+      std::vector<long long> h(256 * 8);
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h.data(), buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      double m[8] = {0};
+      for (int c = 0; c < *grid; ++c)
+        for (int i = 0; i < 8; ++i) m[i] += double(h[c * 8 + i]) / *grid;
+      fprintf(stderr, "[i8 trace] mode %d grid %d: mma warp %.0f clk | epilogue total %.0f wait %.0f phase2 %.0f\n", mode, *grid,
+              m[0], m[4], m[5], m[6]);
+    }
+  };
+  int trace_grid = 0;
+  TraceDump trace_dump{trace, stream, trace_buf, epi.mode, &trace_grid};
   I8Launch L;
   APAX_TRY(make_plane_tmap(&L.ta, act, I8_BM));
   APAX_TRY(make_plane_tmap(&L.tb, wgt, I8_BN));
@@ -687,6 +750,7 @@ int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const
   L.num_m_tiles = int(act.rows / I8_BM);
   L.num_n_sub = int(wgt.rows / I8_BN);
   L.grid = L.num_m_tiles < n_sm ? L.num_m_tiles : n_sm;   // one persistent CTA per SM (it owns the SM's whole TMEM)
+  trace_grid = L.grid;
   // as many activation planes as fit stay resident next to a ring of at least three weight stages; the least
   // significant planes (used by the fewest MMAs) travel with the stages otherwise
   const uint32_t budget = I8_SMEM_LIMIT - 10240 /* static + alignment */;
