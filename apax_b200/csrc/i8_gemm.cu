@@ -44,6 +44,12 @@ __device__ __forceinline__ float exp2_int(int e) {
   return ldexpf(1.0f, e);
 }
 
+// 1 / x for finite x >= 1: SFU approximation (1 ulp) + one Newton step
+__device__ __forceinline__ float rcp_newton(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -446,10 +452,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
               if (n < epi.n_valid) epi.out[o] = y;
             } else if (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_ACT_HEAD) {
               // variance_preserving_swish (activation.py:7-9) and its derivative.  The sigmoid goes through the two
-              // SFU approximations (ex2, rcp: ~1e-7 relative, unbiased) -- the epilogue is bound by instruction issue,
-              // and the libm expf + IEEE division cost four times as many instructions.
+              // SFU exponential (ex2.approx, 2 ulp like libm's expf) and an SFU reciprocal refined by one Newton step
+              // (< 1 ulp) -- the epilogue is bound by instruction issue, and libm expf + IEEE division cost three times
+              // as many instructions.
               const float z = y + __ldg(epi.bias + n);
-              const float sg = __fdividef(1.0f, 1.0f + __expf(-z));
+              const float sg = rcp_newton(1.0f + __expf(fminf(-z, 80.0f)));
               const float cs = kSwishI8 * sg;
               const float h = cs * z;
               const float d = cs * fmaf(z, 1.0f - sg, 1.0f);
