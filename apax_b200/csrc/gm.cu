@@ -606,7 +606,9 @@ __global__ void __launch_bounds__(256) k_force_gather(GmWorkspace ws, double* __
 // out-of-range threads stay alive on a clamped atom index and only their stores are suppressed.
 constexpr int kContractThreads = 256;
 
-template <bool SPLIT>
+// MODE 0: features -> GT.  1: exact (tf32 hi, residual lo) pairs for the floating-point tensor-core readout.
+// 2: GT plus each atom's maximum of |g[k] c[k]| -- the row scale of the integer tensor-core readout's digit planes.
+template <int MODE>
 __global__ void __launch_bounds__(kContractThreads, 1) k_contract_fwd(GmWorkspace ws) {
   const int64_t atom_raw = int64_t(blockIdx.x) * kContractThreads + threadIdx.x;
   const bool live = atom_raw < ws.n_central;
@@ -617,9 +619,11 @@ __global__ void __launch_bounds__(kContractThreads, 1) k_contract_fwd(GmWorkspac
   float* gt = ws.GT + atom;
   float* glt = ws.GLT + atom;
   const int64_t ld = ws.ld;
+  float mx = 0.0f;
   gm_contract_forward(m, [&](int f, float v) {
+    if (MODE == 2) mx = fmaxf(mx, fabsf(v * __ldg(ws.q_cs + f)));
     if (!live) return;
-    if (SPLIT) {  // tensor-core readout consumes exact (tf32 hi, residual lo) pairs
+    if (MODE == 1) {
       float hi, lo;
       split_tf32(v, hi, lo);
       gt[int64_t(f) * ld] = hi;
@@ -628,6 +632,7 @@ __global__ void __launch_bounds__(kContractThreads, 1) k_contract_fwd(GmWorkspac
       gt[int64_t(f) * ld] = v;
     }
   });
+  if (MODE == 2 && live) ws.q_rowmax[atom] = __float_as_int(mx < 3.0e38f ? mx : 3.4e38f);   // NaN / inf rows quantise to zero
 }
 
 __global__ void __launch_bounds__(kContractThreads, 1) k_contract_bwd(GmWorkspace ws) {
@@ -981,17 +986,18 @@ static PairGeom make_geom(const apax_gm_params_impl* p, const double* R, const i
 
 // descriptor forward: moments + contractions -> GT
 static int gm_descriptor_impl(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w,
-                              const PairGeom& geo, bool split_features = false) {
+                              const PairGeom& geo, int feature_mode = 0) {
   const DescConst dc = make_desc_const(p->cfg);
   const int lpa = pick_lpa(w.n_central);
   APAX_LAUNCH(k_atom_pack, dim3((unsigned)cdiv(w.n_atoms, 256)), dim3(256), 0, stream, w, geo);
   APAX_DISPATCH_LPA(lpa, launch_pair_fwd, stream, w, geo, dc);
-  if (split_features) {
-    APAX_LAUNCH(k_contract_fwd<true>, dim3((unsigned)cdiv(w.n_central, kContractThreads)), dim3(kContractThreads), 0,
-                stream, w);
+  const dim3 grid_c((unsigned)cdiv(w.n_central, kContractThreads));
+  if (feature_mode == 1) {
+    APAX_LAUNCH(k_contract_fwd<1>, grid_c, dim3(kContractThreads), 0, stream, w);
+  } else if (feature_mode == 2) {
+    APAX_LAUNCH(k_contract_fwd<2>, grid_c, dim3(kContractThreads), 0, stream, w);
   } else {
-    APAX_LAUNCH(k_contract_fwd<false>, dim3((unsigned)cdiv(w.n_central, kContractThreads)), dim3(kContractThreads), 0,
-                stream, w);
+    APAX_LAUNCH(k_contract_fwd<0>, grid_c, dim3(kContractThreads), 0, stream, w);
   }
   return APAX_OK;
 }
@@ -1120,6 +1126,10 @@ static int readout_tc(cudaStream_t stream, const apax_gm_params_impl* p, const G
 // digit planes written by the epilogues; fp32 copies exist only of swish'(y1) (D1T) and of dE/dg (GT).
 // Buffer reuse: descriptor planes in GLT, swish(y1) / dE/dy1 planes in H1LT, swish'(y2) planes in H2LT, the epilogue
 // staging in H2T, and head sums + row exponents in the first rows of H1T (none of these hold fp32 data here).
+static int32_t* i8_rowmax_buffer(const GmWorkspace& w) {
+  return reinterpret_cast<int32_t*>(w.H1T + int64_t(MAX_OUT) * w.ld) + 3 * w.ld;
+}
+
 static int readout_i8(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const PairGeom& geo,
                       double* energy, int head) {
   const int64_t N = w.n_central, ld = w.ld;
@@ -1131,10 +1141,10 @@ static int readout_i8(cudaStream_t stream, const apax_gm_params_impl* p, const G
   int32_t* e_g = reinterpret_cast<int32_t*>(w.H1T + int64_t(MAX_OUT) * ld);
   int32_t* e_h1 = e_g + ld;
   int32_t* e_x1 = e_h1 + ld;
-  int32_t* rowmax = e_x1 + ld;
+  int32_t* rowmax = i8_rowmax_buffer(w);   // filled by k_contract_fwd<2>
   const I8Planes w0{p->q_w0, NH, NFP, int64_t(NH) * NFP, 4}, w1{p->q_w1, NH, NH, int64_t(NH) * NH, 4};
   if (head < 0) {
-    APAX_TRY(i8_quantize_rows(stream, w.GT, ld, N, NF, NFP, 4, p->cs_g, gq, e_g, rowmax));
+    APAX_TRY(i8_quantize_rows(stream, w.GT, ld, N, NF, NFP, 4, p->cs_g, gq, e_g, rowmax, /*have_rowmax=*/true));
     {  // layer 0: 360 -> 256; swish' kept in fp32 for the backward pass, swish goes on as digit planes
       const I8Planes act{gq, ld, NFP, ld * int64_t(NFP), 4};
       I8Epilogue e{};
@@ -1193,7 +1203,14 @@ static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
            : mode == READOUT_TC ? readout_tc(stream, p, w, geo, energy, head)
                                 : readout_simt(stream, p, w, geo, energy, head);
   };
-  APAX_TRY(gm_descriptor_impl(stream, p, w, geo, mode == READOUT_TC));
+  if (mode == READOUT_I8) {
+    GmWorkspace wq = w;   // the contraction kernel leaves the row maxima of the scaled features for the quantiser
+    wq.q_cs = p->cs_g;
+    wq.q_rowmax = i8_rowmax_buffer(w);
+    APAX_TRY(gm_descriptor_impl(stream, p, wq, geo, 2));
+  } else {
+    APAX_TRY(gm_descriptor_impl(stream, p, w, geo, mode == READOUT_TC ? 1 : 0));
+  }
   APAX_TRY(readout(-1));
   if (!forces) return APAX_OK;
   for (int head = 0; head < n_out; ++head) {

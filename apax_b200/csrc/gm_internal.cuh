@@ -93,6 +93,9 @@ struct GmWorkspace {
   double* Eatom;   // [n_out][ld]
   double* partial; // [n_out][256]
   double* Frow;    // [N][3] sum of dbar over the rows of the central atom
+  // integer tensor-core readout: the contraction kernel also leaves each atom's scaled feature maximum (set per call)
+  const float* q_cs;   // [384] per-feature scales of layer 0, or null
+  int32_t* q_rowmax;   // [ld] float bits of max_k |g[k] c[k]|
 };
 
 size_t carve_gm_workspace(void* base, int64_t n_atoms, int64_t n_pairs, int32_t n_out, int32_t n_species,

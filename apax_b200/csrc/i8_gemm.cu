@@ -254,6 +254,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
   __shared__ int cta_dead;
   __shared__ float xmax[2][I8_BM];            // row-maximum exchange between the two column halves
   __shared__ float xhead[I8_BM * NOUT];       // head partial sums of the second column half
+  // per-output constants of the epilogue (bias, next layer's feature scales, head weights for one head): broadcast
+  // shared-memory reads instead of global loads inside the element loop
+  __shared__ float s_bias[I8_MAX_KB * I8_KC], s_qcs[I8_MAX_KB * I8_KC], s_whead[I8_MAX_KB * I8_KC];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -261,6 +264,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
   const uint32_t smem_b = smem_a + uint32_t(num_kb * a_res) * I8_A_TILE;
   const uint32_t stage_bytes = I8_B_STAGE + uint32_t(a_planes - a_res) * I8_A_TILE;
 
+  for (int n = threadIdx.x; n < num_n_sub * I8_BN; n += I8_THREADS) {
+    s_bias[n] = (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_ACT_HEAD) ? epi.bias[n] : 0.0f;
+    s_qcs[n] = MODE != I8_EPI_STORE ? epi.q_col_scale[n] : 0.0f;
+    s_whead[n] = (MODE == I8_EPI_ACT_HEAD && NOUT == 1) ? epi.w_head[n] : 0.0f;
+  }
   if (threadIdx.x == 0) {
     cta_dead = 0;
     for (int i = 0; i < I8_MAX_KB; ++i) {
@@ -443,41 +451,43 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
             mbar_arrive(smem_u32(&acc_empty[buf]));
           }
           const int nb = j * I8_BN + c;                     // first output of this chunk
+          float* gp = (MODE == I8_EPI_STORE ? epi.out : epi.aux) + int64_t(nb) * epi.ld + m;   // walks down the feature rows
+          const bool all_valid = MODE != I8_EPI_STORE || nb + 16 <= epi.n_valid;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int n = nb + i, ri = cc * 16 + i;
             const float y = i8_combine(r0[i], r1[i], r2[i], r3[i]) * scale;
-            const int64_t o = int64_t(n) * epi.ld + m;
             if (MODE == I8_EPI_STORE) {
-              if (n < epi.n_valid) epi.out[o] = y;
+              if (all_valid || n < epi.n_valid) *gp = y;
             } else if (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_ACT_HEAD) {
-              // variance_preserving_swish (activation.py:7-9) and its derivative.  The sigmoid goes through the two
-              // SFU exponential (ex2.approx, 2 ulp like libm's expf) and an SFU reciprocal refined by one Newton step
-              // (< 1 ulp) -- the epilogue is bound by instruction issue, and libm expf + IEEE division cost three times
-              // as many instructions.
-              const float z = y + __ldg(epi.bias + n);
+              // variance_preserving_swish (activation.py:7-9) and its derivative: SFU exponential (ex2.approx, 2 ulp
+              // like libm's expf) and an SFU reciprocal refined by one Newton step (< 1 ulp) -- the epilogue is bound by
+              // instruction issue, and libm expf + IEEE division cost three times as many instructions.
+              const float z = y + s_bias[n];
               const float sg = rcp_newton(1.0f + __expf(fminf(-z, 80.0f)));
               const float cs = kSwishI8 * sg;
               const float h = cs * z;
               const float d = cs * fmaf(z, 1.0f - sg, 1.0f);
               if (MODE == I8_EPI_ACT_Q) {
-                epi.aux[o] = d;
-                scratch[int64_t(n) * I8_BM] = h;
-                mx = fmaxf(mx, fabsf(h * __ldg(epi.q_col_scale + n)));
-                if (epi.out) epi.out[o] = h;
+                *gp = d;
+                scratch[(nb + i) * I8_BM] = h;
+                mx = fmaxf(mx, fabsf(h * s_qcs[n]));
               } else {
+                if (NOUT == 1) {
+                  hacc[0] = fmaf(h, s_whead[n], hacc[0]);
+                } else {
 #pragma unroll
-                for (int k = 0; k < NOUT; ++k)
-                  if (k < epi.n_out) hacc[k] = fmaf(h, __ldg(epi.w_head + n * epi.n_out + k), hacc[k]);
-                dq[ri] = d * __ldg(epi.q_col_scale + n);
-                if (epi.out) epi.out[o] = d;
+                  for (int k = 0; k < NOUT; ++k)
+                    if (k < epi.n_out) hacc[k] = fmaf(h, __ldg(epi.w_head + n * epi.n_out + k), hacc[k]);
+                }
+                dq[ri] = d * s_qcs[n];
               }
             } else {
               const float t = y * auxv[ri] * rmul;
-              scratch[int64_t(n) * I8_BM] = t;
-              mx = fmaxf(mx, fabsf(t * __ldg(epi.q_col_scale + n)));
-              if (epi.out) epi.out[o] = t;
+              scratch[(nb + i) * I8_BM] = t;
+              mx = fmaxf(mx, fabsf(t * s_qcs[n]));
             }
+            gp += epi.ld;
           }
         }
         if (MODE == I8_EPI_ACT_HEAD)
@@ -492,7 +502,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
         const long long p0 = clock64();
         float cur[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) cur[i] = scratch[int64_t(half * 32 + i) * I8_BM];
+        for (int i = 0; i < 32; ++i) cur[i] = scratch[(half * 32 + i) * I8_BM];
         xmax[half][row] = mx;
         epi_bar_sync();
         mx = fmaxf(xmax[0][row], xmax[1][row]);
@@ -505,11 +515,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
         for (int j = 0; j < num_n_sub; ++j) {
           const int nb = j * I8_BN + half * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) cur[i] *= __ldg(epi.q_col_scale + nb + i);
+          for (int i = 0; i < 32; ++i) cur[i] *= s_qcs[nb + i];
           i8_emit32(cur, sc, sc2, epi.q_planes + m * epi.q_kp + nb, epi.q_plane_stride);
           if (j + 1 < num_n_sub) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) cur[i] = scratch[int64_t(nb + I8_BN + i) * I8_BM];
+            for (int i = 0; i < 32; ++i) cur[i] = scratch[(nb + I8_BN + i) * I8_BM];
           }
         }
         w_phase2 += clock64() - p0;
@@ -560,7 +570,7 @@ __global__ void __launch_bounds__(128) k_i8_rowmax(const float* __restrict__ xt,
 }
 
 template <int P>
-__global__ void __launch_bounds__(128, 7) k_i8_quantize(const float* __restrict__ xt, int64_t ld, int K, int kp,
+__global__ void __launch_bounds__(128, 7) k_i8_quantize(const float* __restrict__ xt, int64_t ld, int64_t n_valid_rows, int K, int kp,
                                                         const float* __restrict__ col_scale,
                                                         const int32_t* __restrict__ rowmax_bits,
                                                         int8_t* __restrict__ planes, int32_t* __restrict__ row_exp) {
@@ -570,7 +580,7 @@ __global__ void __launch_bounds__(128, 7) k_i8_quantize(const float* __restrict_
   const int kc = blockIdx.y * 64;
   int e;
   float sc, sc2;
-  i8_row_scale(__int_as_float(rowmax_bits[m]), P, e, sc, sc2);
+  i8_row_scale(m < n_valid_rows ? __int_as_float(rowmax_bits[m]) : 0.0f, P, e, sc, sc2);   // padding rows: zero digits
   if (blockIdx.y == 0) row_exp[m] = e;
   const float* x = xt + m;
 #pragma unroll 1
@@ -661,15 +671,17 @@ int prepare_i8(Kern kern) {
 }  // namespace
 
 int i8_quantize_rows(cudaStream_t stream, const float* xt, int64_t ld, int64_t n_valid_rows, int K, int kp, int n_planes,
-                     const float* col_scale, int8_t* planes, int32_t* row_exp, int32_t* rowmax_bits) {
+                     const float* col_scale, int8_t* planes, int32_t* row_exp, int32_t* rowmax_bits, bool have_rowmax) {
   if (ld % 128 != 0 || kp % 64 != 0 || K > kp || (n_planes != 3 && n_planes != 4)) return APAX_ERR_INVALID_ARG;
   const dim3 grid((unsigned)(ld / 128), (unsigned)(kp / 64));
-  APAX_CUDA_TRY(cudaMemsetAsync(rowmax_bits, 0, sizeof(int32_t) * ld, stream));
-  APAX_LAUNCH(k_i8_rowmax, grid, dim3(128), 0, stream, xt, ld, n_valid_rows, K, col_scale, rowmax_bits);
+  if (!have_rowmax) {   // otherwise the producer of xt already left the maxima of the first n_valid_rows rows
+    APAX_CUDA_TRY(cudaMemsetAsync(rowmax_bits, 0, sizeof(int32_t) * ld, stream));
+    APAX_LAUNCH(k_i8_rowmax, grid, dim3(128), 0, stream, xt, ld, n_valid_rows, K, col_scale, rowmax_bits);
+  }
   if (n_planes == 3) {
-    APAX_LAUNCH(k_i8_quantize<3>, grid, dim3(128), 0, stream, xt, ld, K, kp, col_scale, rowmax_bits, planes, row_exp);
+    APAX_LAUNCH(k_i8_quantize<3>, grid, dim3(128), 0, stream, xt, ld, n_valid_rows, K, kp, col_scale, rowmax_bits, planes, row_exp);
   } else {
-    APAX_LAUNCH(k_i8_quantize<4>, grid, dim3(128), 0, stream, xt, ld, K, kp, col_scale, rowmax_bits, planes, row_exp);
+    APAX_LAUNCH(k_i8_quantize<4>, grid, dim3(128), 0, stream, xt, ld, n_valid_rows, K, kp, col_scale, rowmax_bits, planes, row_exp);
   }
   return APAX_OK;
 }

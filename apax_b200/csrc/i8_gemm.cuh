@@ -65,7 +65,7 @@ struct I8Epilogue {
   int n_valid;             // outputs >= n_valid are ignored
   const int32_t* row_exp;  // [rows] exponents e[m] of the activation planes; null: fixed_exp for every row
   int fixed_exp;
-  float* out;              // STORE: [n][ld].  Fused modes: optional fp32 copy of the quantised quantity (debug), may be null
+  float* out;              // STORE: [n][ld]
   const float* bias;       // ACT_*: [n]
   float* aux;              // ACT_Q: swish' written [n][ld];  MULD_Q: multiplier read
   const float* row_mul;    // MULD_Q: per-atom factor [ld] (may be null)
@@ -87,7 +87,7 @@ struct I8Epilogue {
 // activations: feature-major fp32 [K][ld] -> digit planes [n_planes][ld][kp] + per-atom exponents
 int i8_quantize_rows(cudaStream_t stream, const float* xt, int64_t ld, int64_t n_valid_rows, int K, int kp, int n_planes,
                      const float* col_scale /* [kp] powers of two */, int8_t* planes, int32_t* row_exp,
-                     int32_t* rowmax_scratch /* [ld] */);
+                     int32_t* rowmax /* [ld] float bits of the scaled row maxima */, bool have_rowmax = false);
 
 // weights (host): W[k][n] (row stride ldw) -> planes [4][ncp][kp] of W[k][n] / c[k].  col_scale: computed here from
 // the row maxima of W (given_scale = false), or taken as given (shared between several weight matrices).
