@@ -207,13 +207,21 @@ __global__ void __launch_bounds__(256) k_cell_pack(const double* __restrict__ po
   cell_pos[t] = make_float4(float(x - floor(x)), float(y - floor(y)), float(z - floor(z)), __int_as_float(j));
 }
 
-// Candidate scan of one atom by LG lanes.  FILL = false: count accepted pairs; FILL = true: append
-// them (order irrelevant, rows are sorted afterwards).
-template <int MODE, bool FILL>
+// Candidate scan of one atom by LG lanes (order of the accepted pairs is irrelevant, rows are sorted afterwards).
+//   PASS 0: count accepted pairs.
+//   PASS 1: append them at rowptr[atom] (second pass of the two-pass build; rows whose count is <= stride were
+//           already captured by a PASS 2 scan and are skipped).
+//   PASS 2: count AND park the first `stride` accepted neighbours of every atom in a fixed-stride scratch row, so
+//           that one scan suffices whenever no row exceeds the stride.
+template <int MODE, int PASS>
 __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos, int64_t N,
-                                                 const NlGrid* __restrict__ gridp, NlWorkspace w) {
+                                                 const NlGrid* __restrict__ gridp, NlWorkspace w, int stride,
+                                                 int32_t* __restrict__ scratch) {
+  constexpr bool FILL = PASS != 0;
   __shared__ NlGrid g;
+  __shared__ int s_cnt[256 / LG];   // PASS 1 / 2: running slot counter of each lane group
   if (threadIdx.x == 0) g = *gridp;
+  if (threadIdx.x < 256 / LG) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const int64_t gid = int64_t(blockIdx.x) * 256 + threadIdx.x;
   const bool valid = gid / LG < N;
@@ -241,9 +249,10 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
     c2_lo = (cut - delta) * (cut - delta);
     c2_hi = (cut + delta) * (cut + delta);
   }
-  const int base = FILL ? w.rowptr[atom] : 0;
+  const int grp = threadIdx.x / LG;
+  const int64_t base = PASS == 1 ? int64_t(w.rowptr[atom]) : PASS == 2 ? atom * int64_t(stride) : 0;
   int count = 0;
-  const int m0 = valid ? g.m[0] : -1;
+  const int m0 = (valid && !(PASS == 1 && w.rowcnt[atom] <= stride)) ? g.m[0] : -1;
   for (int d0 = -m0; d0 <= m0; ++d0) {
     const int q0 = c[0] + d0;
     const int s0 = q0 >= 0 ? q0 / g.nc[0] : -((-q0 + g.nc[0] - 1) / g.nc[0]);
@@ -258,15 +267,11 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
         const int k2 = q2 - s2 * g.nc[2];
         const int cid = (k0 * g.nc[1] + k1) * g.nc[2] + k2;
         const int cb = w.cellptr[cid], ce = w.cellptr[cid + 1];
-        for (int t0 = cb; t0 < ce; t0 += LG) {   // uniform trip count inside the lane group (ballot below)
-          const int t = t0 + sub;
-          const bool in_range = t < ce;
+        for (int t = cb + sub; t < ce; t += LG) {
           int j = 0;
           bool keep = false;
           int packed = 0;
-          if (!in_range) {
-            // nothing to test; still take part in the group ballot
-          } else if (MODE == 0) {
+          if (MODE == 0) {
             const float4 q = w.cell_pos[t];
             j = __float_as_int(q.w);
             float u0 = fa[0] - q.x, u1 = fa[1] - q.y, u2 = fa[2] - q.z;
@@ -301,29 +306,30 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
                    S0 >= -127 && S0 <= 127 && S1 >= -127 && S1 <= 127 && S2 >= -127 && S2 <= 127;
             packed = pack_shift(S0, S1, S2);
           }
-          if (FILL) {
-            // slot = running count of the lane group + rank of this lane among the accepting lanes: no atomics
-            const unsigned gmask = 0xffu << ((threadIdx.x & 31) / LG * LG);
-            const unsigned acc = (__ballot_sync(gmask, keep) >> ((threadIdx.x & 31) / LG * LG)) & 0xffu;
-            if (keep) {
-              const int slot = base + count + __popc(acc & ((1u << sub) - 1u));
-              if (slot < w.capacity) {
-                w.nbr_tmp[slot] = j;
-                if (MODE == 1) w.shift_tmp[slot] = packed;
+          if (keep) {
+            if (FILL) {
+              const int slot = atomicAdd(&s_cnt[grp], 1);   // shared-memory counter of the lane group
+              if (PASS == 2) {
+                if (slot < stride) scratch[base + slot] = j;
+              } else if (base + slot < w.capacity) {
+                w.nbr_tmp[base + slot] = j;
+                if (MODE == 1) w.shift_tmp[base + slot] = packed;
               }
+            } else {
+              ++count;
             }
-            count += __popc(acc);
-          } else if (keep) {
-            ++count;
           }
         }
       }
     }
   }
-  if (!FILL) {
+  if (PASS == 0) {
 #pragma unroll
     for (int o = LG / 2; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
     if (valid && sub == 0) w.rowcnt[atom] = count;
+  } else if (PASS == 2) {
+    __syncwarp();
+    if (valid && sub == 0) w.rowcnt[atom] = s_cnt[grp];
   }
 }
 
@@ -358,6 +364,53 @@ __global__ void __launch_bounds__(256) k_nl_rowsort(const int32_t* __restrict__ 
     }
     nbr_out[b + rank] = nbr_in[i];
     if (shift_in) shift_out[b + rank] = shift_in[i];
+  }
+}
+
+// Rank sort from the single-scan scratch (min-image lists): the row is staged in shared memory, every element's
+// rank is its number of smaller row mates, and only ranks below the capacity-clamped row length are written --
+// i.e. a truncated list keeps the FIRST pairs in the reference's order (partition.py:656-664).
+constexpr int kRowSortMax = 256;
+__global__ void __launch_bounds__(256) k_nl_rowsort_strided(const int32_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ rowptr_c,
+                                                            const int32_t* __restrict__ rowcnt, int64_t N,
+                                                            const int32_t* __restrict__ scratch, int stride,
+                                                            const int32_t* __restrict__ nbr_tmp,
+                                                            int32_t* __restrict__ nbr_out) {
+  __shared__ int32_t s_row[8][kRowSortMax];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * 8 + wib;
+  if (row >= N) return;
+  const int cnt = rowcnt[row];
+  const int b = rowptr_c[row], len_c = rowptr_c[row + 1] - b;
+  const int32_t* src = cnt <= stride ? scratch + row * int64_t(stride) : nbr_tmp + rowptr[row];
+  if (cnt <= kRowSortMax) {
+    for (int i = lane; i < cnt; i += 32) s_row[wib][i] = src[i];
+    __syncwarp();
+    for (int i0 = 0; i0 < cnt; i0 += 128) {   // four keys per lane share every broadcast read
+      int key[4], rank[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * 32 + lane;
+        key[q] = i < cnt ? s_row[wib][i] : 0x7fffffff;
+        rank[q] = 0;
+      }
+      for (int j = 0; j < cnt; ++j) {
+        const int v = s_row[wib][j];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rank[q] += (v < key[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (i0 + q * 32 + lane < cnt && rank[q] < len_c) nbr_out[b + rank[q]] = key[q];
+    }
+  } else {   // very long rows: rank straight from global memory
+    for (int i = lane; i < cnt; i += 32) {
+      const int key = src[i];
+      int rank = 0;
+      for (int j = 0; j < cnt; ++j) rank += (src[j] < key);
+      if (rank < len_c) nbr_out[b + rank] = key;
+    }
   }
 }
 
@@ -446,20 +499,41 @@ static int nl_build_common(cudaStream_t stream, const double* pos, const double*
   APAX_TRY(rowsort_i32(stream, w.cellptr, N, w.cell_tmp, nullptr, w.cell_atoms, nullptr));
   if (MODE == 0) APAX_LAUNCH(k_cell_pack, dim3((unsigned)cdiv(N, 256)), dim3(256), 0, stream, pos, N, w.cell_atoms, w.cell_pos);
   const dim3 grid_scan((unsigned)cdiv(N * LG, 256));
-  APAX_CUDA_TRY(cudaMemsetAsync(w.rowcnt, 0, sizeof(int32_t) * (N + 1), stream));
-  {
-    auto k_nl_scan_count = k_nl_scan<MODE, false>;
-    APAX_LAUNCH(k_nl_scan_count, grid_scan, dim3(256), 0, stream, pos, N, w.grid, w);
+  // Min-image lists carry no shifts, so the two shift buffers (2 x capacity ints, contiguous up to alignment padding)
+  // serve as fixed-stride scratch rows and ONE candidate scan both counts and captures the neighbours; only rows
+  // longer than the stride (none for ordinary densities: the stride is ~twice the mean row) are re-scanned.
+  int stride = 0;
+  int32_t* scratch = nullptr;
+  if (MODE == 0) {
+    const int64_t span = (reinterpret_cast<char*>(w.shift) - reinterpret_cast<char*>(w.shift_tmp)) / int64_t(sizeof(int32_t)) + capacity;
+    const int64_t per_row = span / N;
+    if (per_row >= 32) {
+      stride = int(per_row < kRowSortMax ? per_row : kRowSortMax);
+      scratch = w.shift_tmp;
+    }
+  }
+  if (stride > 0) {
+    auto k_nl_scan_single = k_nl_scan<MODE, 2>;
+    APAX_LAUNCH(k_nl_scan_single, grid_scan, dim3(256), 0, stream, pos, N, w.grid, w, stride, scratch);
+  } else {
+    APAX_CUDA_TRY(cudaMemsetAsync(w.rowcnt, 0, sizeof(int32_t) * (N + 1), stream));
+    auto k_nl_scan_count = k_nl_scan<MODE, 0>;
+    APAX_LAUNCH(k_nl_scan_count, grid_scan, dim3(256), 0, stream, pos, N, w.grid, w, 0, scratch);
   }
   APAX_TRY(exclusive_scan_i32(stream, w.rowcnt, w.rowptr, N, w.scan_scratch));
   APAX_LAUNCH(k_nl_finish_count, dim3((unsigned)cdiv(N + 1, 256)), dim3(256), 0, stream, N, capacity, w.rowptr,
               w.rowptr_c, n_found, overflow);
   {
-    auto k_nl_scan_fill = k_nl_scan<MODE, true>;
-    APAX_LAUNCH(k_nl_scan_fill, grid_scan, dim3(256), 0, stream, pos, N, w.grid, w);
+    auto k_nl_scan_fill = k_nl_scan<MODE, 1>;   // with a stride: only the rows the single scan could not hold
+    APAX_LAUNCH(k_nl_scan_fill, grid_scan, dim3(256), 0, stream, pos, N, w.grid, w, stride > 0 ? stride : -1, scratch);
   }
-  APAX_LAUNCH(k_nl_rowsort, dim3((unsigned)cdiv(N * 32, 256)), dim3(256), 0, stream, w.rowptr_c, N, w.nbr_tmp,
-              MODE == 1 ? w.shift_tmp : nullptr, w.nbr, MODE == 1 ? w.shift : nullptr);
+  if (stride > 0) {
+    APAX_LAUNCH(k_nl_rowsort_strided, dim3((unsigned)cdiv(N, 8)), dim3(256), 0, stream, w.rowptr, w.rowptr_c, w.rowcnt, N,
+                scratch, stride, w.nbr_tmp, w.nbr);
+  } else {
+    APAX_LAUNCH(k_nl_rowsort, dim3((unsigned)cdiv(N * 32, 256)), dim3(256), 0, stream, w.rowptr_c, N, w.nbr_tmp,
+                MODE == 1 ? w.shift_tmp : nullptr, w.nbr, MODE == 1 ? w.shift : nullptr);
+  }
   if (idx) {
     const int64_t blocks = cdiv(N * 32, 256);
     APAX_LAUNCH(k_nl_emit, dim3((unsigned)blocks), dim3(256), 0, stream, w.rowptr_c, N, capacity, w.nbr,
