@@ -647,7 +647,10 @@ __global__ void __launch_bounds__(kContractThreads, 1) k_contract_bwd(GmWorkspac
   }
   const float* gt = ws.GT + atom;
   const int64_t ld = ws.ld;
-  gm_contract_backward(m, a, [&](int f) { return gt[int64_t(f) * ld]; });
+  // looped form of the reverse program: one generic block per contraction type (~15 KB of code instead of ~200 KB of
+  // straight-line code that ran at 12 % issue utilisation behind instruction-fetch stalls)
+  __shared__ float s_ring[GM_RING_FLOATS_PER_THREAD * kContractThreads];   // feature adjoints in flight (cp.async)
+  gm_contract_backward_looped(m, a, gt, ld, s_ring + threadIdx.x, kContractThreads);
   if (live) {
 #pragma unroll
     for (int k = 0; k < NPK; ++k) ws.AT[int64_t(k) * ws.ld + atom] = a[k];

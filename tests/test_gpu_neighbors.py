@@ -56,6 +56,34 @@ def test_min_image_list_vs_oracle(rt, no, n_mol, seed, cutoff):
     assert np.all(idx[:, nf:].cpu().numpy() == len(Z))
 
 
+def test_min_image_rows_longer_than_the_scratch_stride(rt, no):
+    """Inhomogeneous density: a compact cluster inside a dilute box.  The single-scan build parks at most
+    2*capacity/N neighbours per atom; the cluster's rows are several times longer and take the re-scan path, the
+    dilute atoms stay on the fast path -- the list must still equal the oracle's, order included."""
+    rng = np.random.default_rng(11)
+    L = 40.0
+    cell = np.diag([L, L, L])
+    cluster = 20.0 + rng.uniform(-3.0, 3.0, size=(300, 3))        # ~300 mutual neighbours within 6.5 A
+    dilute = rng.uniform(0.0, L, size=(2700, 3))
+    pos = np.concatenate([cluster, dilute])[rng.permutation(3000)]
+    frac = pos @ np.linalg.inv(cell)
+    ref = no.jaxmd_sparse_pairs(frac, cell.T, 6.5)
+    rows = np.bincount(ref[0], minlength=3000)
+    cap = int(ref.shape[1] * 1.1)
+    assert rows.max() > 2 * cap // 3000 + 32 and np.median(rows) < cap // 3000   # both paths are exercised
+    idx, n_found, ov = rt.nl_build_minimage(frac, cell.T, 6.5, cap)
+    nf = int(n_found.item())
+    assert nf == ref.shape[1] and not int(ov.item())
+    assert np.array_equal(idx[:, :nf].cpu().numpy(), ref)
+    # a too-small capacity raises the overflow flag and reports the size needed (partition.py:759-768: the caller
+    # must re-allocate); every row that fits entirely is still the reference's
+    cap2 = ref.shape[1] - 1234
+    idx2, n2, ov2 = rt.nl_build_minimage(frac, cell.T, 6.5, cap2)
+    assert int(ov2.item()) == 1 and int(n2.item()) == ref.shape[1]
+    whole = int(np.searchsorted(ref[1], ref[1, cap2 - 1]))   # first slot of the row cut by the capacity
+    assert np.array_equal(idx2.cpu().numpy()[:, :whole], ref[:, :whole])
+
+
 def test_min_image_triclinic_and_unwrapped_positions(rt, no):
     rng = np.random.default_rng(5)
     cell = np.array([[26.0, 0.0, 0.0], [3.0, 25.0, 0.0], [-2.0, 4.0, 27.0]])
