@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import json
 import os
+import sys
 import time
 from dataclasses import dataclass
 from typing import Callable, List, Optional
@@ -207,7 +208,11 @@ def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: 
 
     torch.cuda.set_device(local)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ["NCCL_DEBUG"] = "WARN"   # NCCL otherwise prints its version banner on stdout, next to the JSON line
+    # stdout must carry exactly one JSON line: NCCL writes its version banner to file descriptor 1, so everything any
+    # library prints there is sent to stderr, and the result line goes out through a saved copy of the descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_mol = args.molecules * (world if args.scaling == "weak" else 1)
     pos, Z, cell = syn.water_box(n_mol, 0)
@@ -317,6 +322,7 @@ def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: 
         }
         if verify:
             line["verify"] = verify
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     dist.destroy_process_group()
     return 0
