@@ -21,7 +21,8 @@ constexpr uint32_t I8_TMEM_COLS = 2 * I8_ACC_COLS;             // two sets = the
 constexpr int I8_MAX_B_STAGES = 8;
 constexpr int I8_EPI_WARPS = 8;                                // two warps per TMEM lane quarter
 constexpr int I8_EPI_THREADS = 32 * I8_EPI_WARPS;
-constexpr int I8_THREADS = 64 + I8_EPI_THREADS;                // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int I8_MMA_WARP2 = 2 + I8_EPI_WARPS;                 // second MMA-issuing warp (odd tiles)
+constexpr int I8_THREADS = 96 + I8_EPI_THREADS;                // warp 0 TMA, warps 1 and 10 MMA, warps 2-9 epilogue
 constexpr uint32_t I8_SMEM_LIMIT = 232448;                     // 227 KB per CTA
 constexpr float kSwishI8 = 1.6765324703310907f;                // apax/layers/activation.py:8
 
@@ -259,6 +260,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
   __shared__ float s_bias[I8_MAX_KB * I8_KC], s_qcs[I8_MAX_KB * I8_KC], s_whead[I8_MAX_KB * I8_KC];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Two MMA-issuing warps (even / odd tiles) when the weight ring can be split into two private rings of at least two
+  // stages: a ring must have ONE consumer walking it in order, or a parity wait could alias a phase that is a whole
+  // revolution away.
+  const bool dual = b_stages >= 4 && num_n_sub >= 2;
+  const uint32_t ring_size = dual ? uint32_t(b_stages) / 2 : uint32_t(b_stages);
   const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // a_res planes of the atom tile are resident; the others travel with the weight stages (they are used least)
   const uint32_t smem_b = smem_a + uint32_t(num_kb * a_res) * I8_A_TILE;
@@ -273,7 +279,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
     cta_dead = 0;
     for (int i = 0; i < I8_MAX_KB; ++i) {
       mbar_init(smem_u32(&a_full[i]), 1);
-      mbar_init(smem_u32(&a_empty[i]), 1);
+      mbar_init(smem_u32(&a_empty[i]), dual ? 2 : 1);   // with two MMA warps both sweep every atom tile
     }
     for (int i = 0; i < I8_MAX_B_STAGES; ++i) {
       mbar_init(smem_u32(&b_full[i]), 1);
@@ -299,11 +305,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (warp-uniform, elected lane issues)
-    uint32_t bit = 0;
+    uint32_t cnt[2] = {0, 0};   // k-blocks sent into each ring
     for (int mt = 0; mt < my_m_tiles; ++mt) {
       const int m0 = (int(blockIdx.x) + mt * int(gridDim.x)) * I8_BM;
       for (int j = 0; j < num_n_sub; ++j) {
-        for (int kb = 0; kb < num_kb; ++kb, ++bit) {
+        const uint32_t w = dual ? uint32_t(mt * num_n_sub + j) & 1u : 0u;   // the ring of the warp that owns this tile
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const uint32_t bit = w == 0 ? cnt[0]++ : cnt[1]++;
           if (j == 0) {   // the atom tile's planes of this k-block: resident for the whole output sweep
             mbar_wait_soft(smem_u32(&a_empty[kb]), (uint32_t(mt) & 1) ^ 1, err, &cta_dead);
             if (epi.dbg_flags & 2) {
@@ -316,7 +324,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
             }
             __syncwarp();
           }
-          const uint32_t s = bit % uint32_t(b_stages), phase = (bit / uint32_t(b_stages)) & 1;
+          const uint32_t s = w * ring_size + bit % ring_size, phase = (bit / ring_size) & 1;
           mbar_wait_soft(smem_u32(&b_empty[s]), phase ^ 1, err, &cta_dead);
           if (epi.dbg_flags & 2) {
             if (elect_one()) mbar_arrive(smem_u32(&b_full[s]));
@@ -333,9 +341,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform, elected lane issues)
-    uint32_t bit = 0, tile = 0;
+  } else if (warp == 1 || warp == I8_MMA_WARP2) {
+    // ------------------------------------------------------------------ MMA issuers (warp-uniform, elected lane issues)
+    // Two warps: one owns the even tiles (accumulator set 0), the other the odd ones (set 1).  The tensor pipe queues
+    // only an MMA or two, so a single issuer leaves it idle during every hand-shake (barrier polls, descriptors,
+    // commits); with two, one warp's burst executes while the other goes through its hand-shake.  Each warp's MMAs
+    // touch only its own accumulator set and tcgen05.commit tracks the issuing thread's MMAs, so no ordering between
+    // the two is needed; the atom tile's slots are released when both have committed (barrier count 2).
+    const uint32_t mma_id = warp == 1 ? 0u : 1u;
+    const uint32_t total_tiles = (dual || mma_id == 0) ? uint32_t(my_m_tiles) * uint32_t(num_n_sub) : 0u;   // single mode: warp 1 only
+    const uint32_t tile_step = dual ? 2u : 1u;
+    uint32_t bit = 0;   // k-blocks this warp has taken from its ring
     const long long t_begin = clock64();
     // 16-byte-unit offsets of the four activation planes: resident ones relative to the k-block's resident slot,
     // streamed ones relative to the weight stage
@@ -343,17 +359,21 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
 #pragma unroll
     for (int sa = 0; sa < I8_DIGITS; ++sa)
       a_off[sa] = sa < a_res ? uint32_t(sa) * (I8_A_TILE >> 4) : (I8_B_STAGE >> 4) + uint32_t(sa - a_res) * (I8_A_TILE >> 4);
-    for (int mt = 0; mt < my_m_tiles; ++mt) {
-      for (int j = 0; j < num_n_sub; ++j, ++tile) {
+    for (uint32_t tile = mma_id; tile < total_tiles; tile += tile_step) {
+      {
+        const int mt = int(tile / uint32_t(num_n_sub));
+        const bool first_in_mt = tile < tile_step || int((tile - tile_step) / uint32_t(num_n_sub)) != mt;   // this warp's first sweep of the atom tile
+        const bool last_in_mt = int((tile + tile_step) / uint32_t(num_n_sub)) != mt;                        // ... and its last
         const uint32_t buf = tile & 1, use = tile >> 1;
         mbar_wait_soft(smem_u32(&acc_empty[buf]), (use & 1) ^ 1, err, &cta_dead);   // epilogue has drained this set
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc_base = tmem_d + buf * I8_ACC_COLS;
         for (int kb = 0; kb < num_kb; kb += 2, bit += 2) {
           const bool two = kb + 1 < num_kb;   // k-blocks are issued in pairs (one hand-shake per sixteen MMAs)
-          const uint32_t s0 = bit % uint32_t(b_stages), ph0 = (bit / uint32_t(b_stages)) & 1;
-          const uint32_t s1 = (bit + 1) % uint32_t(b_stages), ph1 = ((bit + 1) / uint32_t(b_stages)) & 1;
-          if (j == 0) {
+          const uint32_t ring0 = dual ? mma_id * ring_size : 0u;
+          const uint32_t s0 = ring0 + bit % ring_size, ph0 = (bit / ring_size) & 1;
+          const uint32_t s1 = ring0 + (bit + 1) % ring_size, ph1 = ((bit + 1) / ring_size) & 1;
+          if (first_in_mt) {
             mbar_wait_soft(smem_u32(&a_full[kb]), uint32_t(mt) & 1, err, &cta_dead);
             if (two) mbar_wait_soft(smem_u32(&a_full[kb + 1]), uint32_t(mt) & 1, err, &cta_dead);
           }
@@ -381,7 +401,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
                           kb != 0 ? 1u : 0u, a_planes > 3 ? 1u : 0u, two ? 1u : 0u);
             umma_commit(smem_u32(&b_empty[s0]));                 // weight stages free once these MMAs have read them
             if (two) umma_commit(smem_u32(&b_empty[s1]));
-            if (j == num_n_sub - 1) {                            // last sweep over these atom k-blocks
+            if (last_in_mt) {                                    // this warp's last sweep over these atom k-blocks
               umma_commit(smem_u32(&a_empty[kb]));
               if (two) umma_commit(smem_u32(&a_empty[kb + 1]));
             }
@@ -392,8 +412,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
         }
       }
     }
-    if (epi.dbg && lane == 0) epi.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
-  } else {
+    if (epi.dbg && lane == 0 && mma_id == 0) epi.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
+  } else if (warp < I8_MMA_WARP2) {
     // -------------------------------------------------------------------- epilogue warps: lane == atom
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;          // the two warps of a quarter split the 64 columns
