@@ -37,6 +37,17 @@ class GmConfig(C.Structure):
     ]
 
 
+class TrainLossConfig(C.Structure):
+    _fields_ = [("energy_weight", C.c_double), ("energy_atoms_exponent", C.c_double), ("forces_weight", C.c_double),
+                ("forces_atoms_exponent", C.c_double)]
+
+
+class TrainOptConfig(C.Structure):
+    _fields_ = [("emb_lr", C.c_double), ("nn_lr", C.c_double), ("scale_lr", C.c_double), ("shift_lr", C.c_double),
+                ("gradient_clipping", C.c_double), ("end_value", C.c_double), ("transition_steps", C.c_int64),
+                ("transition_begin", C.c_int64), ("b1", C.c_double), ("b2", C.c_double), ("eps", C.c_double)]
+
+
 class MdNvtConfig(C.Structure):
     _fields_ = [("chain_length", C.c_int32), ("chain_steps", C.c_int32), ("sy_steps", C.c_int32), ("dt", C.c_double),
                 ("kT", C.c_double), ("tau", C.c_double)]
@@ -75,6 +86,13 @@ SIGNATURES = {
     "apax_md_nvt_init": (C.c_int, [_P, C.POINTER(MdNvtConfig), _P, _P, _I64, _P]),
     "apax_md_nvt_pre_force": (C.c_int, [_P, C.POINTER(MdNvtConfig), _P, _P, _P, _P, _P, _I64, _P]),
     "apax_md_nvt_post_force": (C.c_int, [_P, C.POINTER(MdNvtConfig), _P, _P, _P, _I64, _P]),
+    "apax_train_plan_create": (C.c_int, [C.POINTER(GmConfig), C.POINTER(_P)]),
+    "apax_train_plan_destroy": (None, [_P]),
+    "apax_train_param_layout": (C.c_int, [_P, _P, _P]),
+    "apax_train_workspace_bytes": (C.c_size_t, [_P, _I64, _I64, _I64]),
+    "apax_train_loss_and_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P,
+                                           C.POINTER(TrainLossConfig), C.c_double, _P, _P, _P, _P, _P, _P, C.c_size_t]),
+    "apax_train_adam_step": (C.c_int, [_P, _P, C.POINTER(TrainOptConfig), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "apax_ctx_create": (C.c_int, [_P, _I64, _I64, C.POINTER(_P)]),
     "apax_ctx_destroy": (None, [_P]),
     "apax_ctx_calculate": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, _I32, _P, _P, _P]),

@@ -1,0 +1,1082 @@
+// Training step of the GMNN path (BASELINE configs[1]; SURVEY.md s8e "Training", s8f rank 1): the loss of a batch of
+// independent structures and its gradient w.r.t. every parameter, and the optax-Adam update -- hand-derived, no autodiff.
+//
+// Replaces, for the GMNN model with an energy + force MSE loss:
+//   calc_loss + jax.value_and_grad(params)      apax/train/trainer.py:253-263, 332-336
+//   jax.vmap(model.apply) over structures       apax/train/run.py:204
+//   Loss.__call__ (mse, atoms_exponent)         apax/train/loss.py:12-23, 199-244
+//   get_opt (clip -> adam(linear schedule) -> zero_nans per parameter group)   apax/optimizer/get_optimizer.py:62-176
+//
+// The force loss differentiates F = -dE/dR w.r.t. the weights.  With u = dL/dF (a fixed vector once E and F of the batch are
+// known) and alpha_s = dL/dE_s,   grad_theta L = grad_theta [ sum_s alpha_s E_s  -  d/d(eps) E(R + eps u) ],
+// so one FORWARD-mode (tangent) sweep of the energy along u followed by one reverse sweep of the dual program gives every
+// gradient; the adjoint of the tangent quantities is minus the adjoint chain that produced the forces, so it is reused.
+//
+// Workload shape: hundreds of atoms per step (32 x 9-atom molecules per GPU), i.e. launch-latency bound.  All kernels are
+// plain fp32 CUDA-core code in atom-major layout, deterministic (no floating-point atomics), never allocate and never
+// synchronise, so a whole step (loss+grad, all-reduce, Adam) can be captured in a CUDA graph; the learning-rate schedule is
+// evaluated on the device from a device-resident step counter for the same reason.
+#include <math.h>
+
+#include <algorithm>
+#include <array>
+#include <map>
+#include <vector>
+
+#include "common.cuh"
+#include "gm_internal.cuh"
+
+namespace apax {
+namespace {
+
+constexpr int ONE_SLOT = NPK;           // pseudo-moment that is identically 1 (tangent 0)
+constexpr float kSwish = 1.6765324703310907f;   // apax/layers/activation.py:8
+constexpr int TR_CH = 32;               // pairs staged per chunk in the moment kernels
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Contraction program as a flat table of monomials in the packed moments (built on the host, once per plan).
+// feature f = sum_t coef_t * M[a_t] * M[b_t] * M[c_t]   (slot 100 == 1 for lower degrees)
+// Reference: apax/layers/descriptor/gaussian_moment_descriptor.py:56-101, triangular_indices.py:28-49.
+// ---------------------------------------------------------------------------------------------------------------------
+struct Term {
+  int f;
+  float coef;
+  uint8_t a, b, c;
+};
+
+int pack2(int i, int j) {
+  if (i > j) std::swap(i, j);
+  static const int t[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+  return t[i][j];
+}
+int pack3(int i, int j, int k) {
+  int v[3] = {i, j, k};
+  std::sort(v, v + 3);
+  static const int order[10][3] = {{0, 0, 0}, {0, 0, 1}, {0, 0, 2}, {0, 1, 1}, {0, 1, 2},
+                                   {0, 2, 2}, {1, 1, 1}, {1, 1, 2}, {1, 2, 2}, {2, 2, 2}};
+  for (int q = 0; q < 10; ++q)
+    if (order[q][0] == v[0] && order[q][1] == v[1] && order[q][2] == v[2]) return q;
+  return -1;
+}
+int s0(int r) { return r * 20; }
+int s1(int r, int i) { return r * 20 + 1 + i; }
+int s2(int r, int i, int j) { return r * 20 + 4 + pack2(i, j); }
+int s3(int r, int i, int j, int k) { return r * 20 + 10 + pack3(i, j, k); }
+
+std::vector<Term> build_terms() {
+  std::vector<std::array<int, 2>> t2;
+  std::vector<std::array<int, 3>> t3;
+  for (int i = 0; i < NR; ++i) {
+    t2.push_back({i, i});
+    for (int j = i + 1; j < NR; ++j) t2.push_back({i, j});
+  }
+  for (int i = 0; i < NR; ++i) {
+    t3.push_back({i, i, i});
+    for (int j = 0; j < NR; ++j)
+      if (j != i) t3.push_back({i, j, j});
+    for (int j = i + 1; j < NR; ++j)
+      for (int k = j + 1; k < NR; ++k) t3.push_back({i, j, k});
+  }
+  std::map<std::array<int, 4>, int> acc;   // (feature, sorted slots) -> multiplicity
+  auto add = [&](int f, int a, int b, int c) {
+    int v[3] = {a, b, c};
+    std::sort(v, v + 3);
+    acc[{f, v[0], v[1], v[2]}] += 1;
+  };
+  int off = 0;
+  for (int r = 0; r < NR; ++r) add(off + r, s0(r), ONE_SLOT, ONE_SLOT);   // c0
+  off += NR;
+  const int nt2 = int(t2.size()), nt3 = int(t3.size());
+  for (int q = 0; q < nt2; ++q)   // c1 = ari,asi->ars
+    for (int i = 0; i < 3; ++i) add(off + q, s1(t2[q][0], i), s1(t2[q][1], i), ONE_SLOT);
+  off += nt2;
+  for (int q = 0; q < nt2; ++q)   // c2 = arij,asij->ars
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) add(off + q, s2(t2[q][0], i, j), s2(t2[q][1], i, j), ONE_SLOT);
+  off += nt2;
+  for (int q = 0; q < nt2; ++q)   // c3 = arijk,asijk->ars
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        for (int k = 0; k < 3; ++k) add(off + q, s3(t2[q][0], i, j, k), s3(t2[q][1], i, j, k), ONE_SLOT);
+  off += nt2;
+  for (int q = 0; q < nt3; ++q)   // c4 = arij,asik,atjk->arst
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        for (int k = 0; k < 3; ++k) add(off + q, s2(t3[q][0], i, j), s2(t3[q][1], i, k), s2(t3[q][2], j, k));
+  off += nt3;
+  for (int q = 0; q < nt2; ++q)   // c5 = ari,asj,atij->arst at the (r,s) pairs, all t
+    for (int t = 0; t < NR; ++t)
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) add(off + q * NR + t, s1(t2[q][0], i), s1(t2[q][1], j), s2(t, i, j));
+  off += nt2 * NR;
+  for (int q = 0; q < nt2; ++q)   // c6 = arijk,asijl,atkl->arst at the (r,s) pairs, all t
+    for (int t = 0; t < NR; ++t)
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+          for (int k = 0; k < 3; ++k)
+            for (int l = 0; l < 3; ++l) add(off + q * NR + t, s3(t2[q][0], i, j, k), s3(t2[q][1], i, j, l), s2(t, k, l));
+  off += nt2 * NR;
+  for (int r = 0; r < NR; ++r)    // c7 = arijk,asij,atk->arst, all (r,s,t)
+    for (int s = 0; s < NR; ++s)
+      for (int t = 0; t < NR; ++t)
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j)
+            for (int k = 0; k < 3; ++k) add(off + (r * NR + s) * NR + t, s3(r, i, j, k), s2(s, i, j), s1(t, k));
+  off += NR * NR * NR;
+  std::vector<Term> out;
+  if (off != NF) return out;
+  for (auto& kv : acc) out.push_back({kv.first[0], float(kv.second), uint8_t(kv.first[1]), uint8_t(kv.first[2]), uint8_t(kv.first[3])});
+  return out;   // std::map order: by feature first
+}
+
+// device tables
+struct Tables {
+  // by feature
+  const int32_t* f_ptr;     // [NF+1]
+  const float* f_coef;
+  const uchar4* f_slots;    // (a, b, c, -)
+  // by moment slot: every occurrence of slot i in a term: d term / d M_i = coef * M[o1] * M[o2]
+  const int32_t* o_ptr;     // [NPK+1]
+  const float* o_coef;
+  const int32_t* o_pack;    // f | o1 << 16 | o2 << 24
+};
+
+struct DescConstT {
+  float r_max, beta, norm, two_beta, pi_f, inv_sqrt_nb;
+  float mu[NB];
+};
+
+}  // namespace
+}  // namespace apax
+
+struct apax_train_plan {
+  apax_gm_config cfg;
+  apax::Tables tab;
+  apax::DescConstT dc;
+  void* dev_block;          // one allocation holding all tables
+  int64_t off32[8];         // emb, w0, b0, w1, b1, w2, b2, total
+  int64_t off64[3];         // scale, shift, total
+};
+
+namespace apax {
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------------------------------
+struct TrWs {
+  int64_t n, P, B;
+  int32_t *rs, *re, *ts, *te;     // [n] row / transpose-row ranges into rowp / trowp
+  int32_t *rowp, *trowp;          // [P] COO positions grouped by central atom / by neighbour atom
+  float4* geo;                    // [P] (dx,dy,dz, species-pair key as int bits); w < 0: dropped entry
+  float4* Q;                      // [P] per-pair force contribution
+  float* cbar;                    // [P][35] per-pair embedding-gradient contributions
+  int32_t* present;               // [128] species present
+  float *M, *Md, *Mdb, *Mb2;      // [n][100]
+  float *GS, *GB;                 // [2n][360]
+  float *Y1, *H1, *Y2, *H2, *YB2, *HB1, *YB1;   // [2n][256]
+  float* e_atom;                  // [2n]: readout output e_a, then its tangent
+  double* Es;                     // [B]
+  double* alpha;                  // [B]   dL/dE_s
+  double* cF;                     // [B]   force-loss coefficient of the structure
+  double* u;                      // [n][3] dL/dF
+  double* loss_s;                 // [B]
+};
+
+size_t carve_tr(void* base, int64_t n, int64_t P, int64_t B, TrWs* w) {
+  Carver c(base);
+  TrWs t{};
+  t.n = n; t.P = P; t.B = B;
+  t.rs = c.take<int32_t>(n); t.re = c.take<int32_t>(n); t.ts = c.take<int32_t>(n); t.te = c.take<int32_t>(n);
+  t.rowp = c.take<int32_t>(P); t.trowp = c.take<int32_t>(P);
+  t.geo = c.take<float4>(P); t.Q = c.take<float4>(P);
+  t.cbar = c.take<float>(P * 35);
+  t.present = c.take<int32_t>(128);
+  t.M = c.take<float>(n * NPK); t.Md = c.take<float>(n * NPK); t.Mdb = c.take<float>(n * NPK); t.Mb2 = c.take<float>(n * NPK);
+  t.GS = c.take<float>(2 * n * NF); t.GB = c.take<float>(2 * n * NF);
+  t.Y1 = c.take<float>(2 * n * NH); t.H1 = c.take<float>(2 * n * NH); t.Y2 = c.take<float>(2 * n * NH);
+  t.H2 = c.take<float>(2 * n * NH); t.YB2 = c.take<float>(2 * n * NH); t.HB1 = c.take<float>(2 * n * NH);
+  t.YB1 = c.take<float>(2 * n * NH);
+  t.e_atom = c.take<float>(2 * n);
+  t.Es = c.take<double>(B); t.alpha = c.take<double>(B); t.cF = c.take<double>(B); t.u = c.take<double>(3 * n);
+  t.loss_s = c.take<double>(B);
+  if (w) *w = t;
+  return c.bytes();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// list grouping: one block per structure.  Every thread owns atoms of the structure and scans the structure's COO range:
+// row (central == a) and transpose row (neighbour == a) in COO order, so all later sums have a fixed order.
+// Dropped: entries with idx[0]==idx[1] (the (0,0) padding, apax/layers/masking.py:10-16) or an index outside the structure.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_tr_group(const int32_t* __restrict__ idx, int64_t P, const int32_t* __restrict__ struct_ptr,
+                                                  const int32_t* __restrict__ pair_ptr, TrWs w) {
+  const int s = blockIdx.x;
+  const int a0 = struct_ptr[s], a1 = struct_ptr[s + 1];
+  const int p0 = pair_ptr[s], p1 = pair_ptr[s + 1];
+  const int32_t* i0 = idx;        // neighbour
+  const int32_t* i1 = idx + P;    // central
+  for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+    int nc = 0, nt = 0;
+    for (int p = p0; p < p1; ++p) {
+      const int j = i0[p], c = i1[p];
+      const bool ok = j != c && j >= a0 && j < a1 && c >= a0 && c < a1;
+      nc += ok && c == a;
+      nt += ok && j == a;
+    }
+    w.rs[a] = nc;
+    w.ts[a] = nt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {   // serial prefix over the structure's atoms (tens to hundreds)
+    int rc = p0, tc = p0;
+    for (int a = a0; a < a1; ++a) {
+      const int nc = w.rs[a], nt = w.ts[a];
+      w.rs[a] = rc; w.re[a] = rc + nc; rc += nc;
+      w.ts[a] = tc; w.te[a] = tc + nt; tc += nt;
+    }
+  }
+  __syncthreads();
+  for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+    int rc = w.rs[a], tc = w.ts[a];
+    for (int p = p0; p < p1; ++p) {
+      const int j = i0[p], c = i1[p];
+      const bool ok = j != c && j >= a0 && j < a1 && c >= a0 && c < a1;
+      if (ok && c == a) w.rowp[rc++] = p;
+      if (ok && j == a) w.trowp[tc++] = p;
+    }
+  }
+}
+
+// per COO entry: fp64 displacement R[i1] - R[i0] (+ offsets) cast to fp32 (apax/layers/distances.py:48-67,
+// gaussian_moment_descriptor.py:33) and the embedding block of the pair: central species first (basis_functions.py:139-141)
+__global__ void __launch_bounds__(256) k_tr_geom(const double* __restrict__ R, const int32_t* __restrict__ Z,
+                                                 const int32_t* __restrict__ idx, const double* __restrict__ offsets, int S,
+                                                 const int32_t* __restrict__ atom_struct, const int32_t* __restrict__ pair_ptr,
+                                                 TrWs w) {
+  const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= w.P) return;
+  const int j = idx[p], c = idx[w.P + p];
+  float4 g = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+  bool ok = j != c && j >= 0 && c >= 0 && j < w.n && c < w.n;
+  if (ok) {   // same rule as k_tr_group: both atoms in the structure whose COO range holds p
+    const int s = atom_struct[c];
+    ok = atom_struct[j] == s && p >= pair_ptr[s] && p < pair_ptr[s + 1];
+  }
+  if (ok) {
+    double d0 = R[3 * int64_t(c) + 0] - R[3 * int64_t(j) + 0];
+    double d1 = R[3 * int64_t(c) + 1] - R[3 * int64_t(j) + 1];
+    double d2 = R[3 * int64_t(c) + 2] - R[3 * int64_t(j) + 2];
+    if (offsets) { d0 += offsets[3 * p + 0]; d1 += offsets[3 * p + 1]; d2 += offsets[3 * p + 2]; }
+    g = make_float4(float(d0), float(d1), float(d2), __int_as_float(Z[c] * S + Z[j]));
+  }
+  w.geo[p] = g;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// per-pair scalar pieces
+// ---------------------------------------------------------------------------------------------------------------------
+struct PairT {
+  float r, inv_re;        // |d|, 1/(r + 1e-5)
+  float n[3];             // d / (r + 1e-5)     (gaussian_moment_descriptor.py:46-48)
+  float G[NB], dG[NB];    // Gaussian basis and d/dr (basis_functions.py:19-56)
+  float fc, dfc;          // cosine cutoff and d/dr (basis_functions.py:82-85; zero slope beyond r_max)
+};
+
+__device__ __forceinline__ void pair_terms(const float4 g, const DescConstT& dc, PairT& t) {
+  const float r2 = g.x * g.x + g.y * g.y + g.z * g.z;
+  t.r = r2 > 0.f ? sqrtf(r2) : 0.f;                      // space.distance / safe_mask (space.py:314-323)
+  t.inv_re = 1.0f / (t.r + 1e-5f);
+  t.n[0] = g.x * t.inv_re; t.n[1] = g.y * t.inv_re; t.n[2] = g.z * t.inv_re;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const float dm = dc.mu[b] - t.r;
+    t.G[b] = dc.norm * expf(-dc.beta * (dm * dm));
+    t.dG[b] = t.G[b] * dc.two_beta * dm;
+  }
+  if (t.r < dc.r_max) {
+    float sn, cs;
+    sincosf(dc.pi_f * t.r / dc.r_max, &sn, &cs);
+    t.fc = 0.5f * (cs + 1.0f);
+    t.dfc = -0.5f * (dc.pi_f / dc.r_max) * sn;
+  } else {
+    t.fc = 0.f;
+    t.dfc = 0.f;
+  }
+}
+
+__device__ __forceinline__ void monomials20(const float (&n)[3], float (&m)[20]) {
+  const float x = n[0], y = n[1], z = n[2];
+  m[0] = 1.0f; m[1] = x; m[2] = y; m[3] = z;
+  const float xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
+  m[4] = xx; m[5] = xy; m[6] = xz; m[7] = yy; m[8] = yz; m[9] = zz;
+  m[10] = xx * x; m[11] = xx * y; m[12] = xx * z; m[13] = xy * y; m[14] = xy * z;
+  m[15] = xz * z; m[16] = yy * y; m[17] = yy * z; m[18] = yz * z; m[19] = zz * z;
+}
+
+// d mono_k / d n_i  (k as in monomials20)
+__device__ __forceinline__ void monomial_grads(const float (&n)[3], float (&gx)[20], float (&gy)[20], float (&gz)[20]) {
+  const float x = n[0], y = n[1], z = n[2];
+  const float xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
+  //        1     x     y     z     xx      xy    xz    yy      yz    zz
+  gx[0] = 0; gx[1] = 1; gx[2] = 0; gx[3] = 0; gx[4] = 2 * x; gx[5] = y; gx[6] = z; gx[7] = 0; gx[8] = 0; gx[9] = 0;
+  gy[0] = 0; gy[1] = 0; gy[2] = 1; gy[3] = 0; gy[4] = 0; gy[5] = x; gy[6] = 0; gy[7] = 2 * y; gy[8] = z; gy[9] = 0;
+  gz[0] = 0; gz[1] = 0; gz[2] = 0; gz[3] = 1; gz[4] = 0; gz[5] = 0; gz[6] = x; gz[7] = 0; gz[8] = y; gz[9] = 2 * z;
+  //         xxx        xxy        xxz        xyy        xyz       xzz        yyy        yyz        yzz        zzz
+  gx[10] = 3 * xx; gx[11] = 2 * xy; gx[12] = 2 * xz; gx[13] = yy; gx[14] = yz; gx[15] = zz; gx[16] = 0; gx[17] = 0; gx[18] = 0; gx[19] = 0;
+  gy[10] = 0; gy[11] = xx; gy[12] = 0; gy[13] = 2 * xy; gy[14] = xz; gy[15] = 0; gy[16] = 3 * yy; gy[17] = 2 * yz; gy[18] = zz; gy[19] = 0;
+  gz[10] = 0; gz[11] = 0; gz[12] = xx; gz[13] = 0; gz[14] = xy; gz[15] = 2 * xz; gz[16] = 0; gz[17] = yy; gz[18] = 2 * yz; gz[19] = 3 * zz;
+}
+
+// radial channels: rho_r = (sum_b c_rb G_b) * fc,  drho_r/dr;  c = (1/sqrt(n_basis)) * W[Z_central, Z_neighbour]
+__device__ __forceinline__ void radial(const float* __restrict__ emb, int key, const DescConstT& dc, const PairT& t,
+                                       float (&rho)[NR], float (&drho)[NR]) {
+  const float* c = emb + int64_t(key) * (NR * NB);
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    float s = 0.f, ds = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const float cb = dc.inv_sqrt_nb * c[r * NB + b];
+      s += cb * t.G[b];
+      ds += cb * t.dG[b];
+    }
+    rho[r] = s * t.fc;
+    drho[r] = ds * t.fc + s * t.dfc;
+  }
+}
+
+// tangent of the pair geometry along ddot = u[central] - u[neighbour]
+__device__ __forceinline__ void pair_tangent(const float4 g, const PairT& t, const double* __restrict__ u, int c, int j,
+                                             float& rdot, float (&ndot)[3]) {
+  const float e0 = float(u[3 * c + 0] - u[3 * j + 0]);
+  const float e1 = float(u[3 * c + 1] - u[3 * j + 1]);
+  const float e2 = float(u[3 * c + 2] - u[3 * j + 2]);
+  rdot = t.r > 0.f ? (g.x * e0 + g.y * e1 + g.z * e2) / t.r : 0.f;
+  const float k = rdot * t.inv_re * t.inv_re;
+  ndot[0] = e0 * t.inv_re - g.x * k;
+  ndot[1] = e1 * t.inv_re - g.y * k;
+  ndot[2] = e2 * t.inv_re - g.z * k;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// moments (moments.py:5-29) and their tangent: block per atom; pairs are staged chunk-wise (thread per pair), then
+// thread (r, k) sums its slot over the chunk in list order.
+//   TANGENT = 0:  M[a][r][k]  = sum_p rho_r mono_k
+//   TANGENT = 1:  Md[a][r][k] = sum_p rhodot_r mono_k + rho_r monodot_k
+// ---------------------------------------------------------------------------------------------------------------------
+template <int TANGENT>
+__global__ void __launch_bounds__(128) k_tr_moments(TrWs w, const float* __restrict__ emb, const int32_t* __restrict__ idx,
+                                                    DescConstT dc, float* __restrict__ out) {
+  __shared__ float s_rho[TR_CH][NR], s_mono[TR_CH][20];
+  __shared__ float s_rhod[TANGENT ? TR_CH : 1][NR], s_monod[TANGENT ? TR_CH : 1][20];
+  const int a = blockIdx.x;
+  const int b0 = w.rs[a], b1 = w.re[a];
+  const int t = threadIdx.x, r = t / 20, k = t % 20;
+  float acc = 0.f;
+  for (int base = b0; base < b1; base += TR_CH) {
+    const int cnt = min(TR_CH, b1 - base);
+    if (t < cnt) {
+      const int p = w.rowp[base + t];
+      const float4 g = w.geo[p];
+      PairT pt;
+      pair_terms(g, dc, pt);
+      float rho[NR], drho[NR], mono[20];
+      radial(emb, __float_as_int(g.w), dc, pt, rho, drho);
+      monomials20(pt.n, mono);
+#pragma unroll
+      for (int q = 0; q < NR; ++q) s_rho[t][q] = rho[q];
+#pragma unroll
+      for (int q = 0; q < 20; ++q) s_mono[t][q] = mono[q];
+      if (TANGENT) {
+        float rdot, nd[3], gx[20], gy[20], gz[20];
+        pair_tangent(g, pt, w.u, a, idx[p], rdot, nd);
+        monomial_grads(pt.n, gx, gy, gz);
+#pragma unroll
+        for (int q = 0; q < NR; ++q) s_rhod[t][q] = drho[q] * rdot;
+#pragma unroll
+        for (int q = 0; q < 20; ++q) s_monod[t][q] = gx[q] * nd[0] + gy[q] * nd[1] + gz[q] * nd[2];
+      }
+    }
+    __syncthreads();
+    if (t < NPK) {
+      for (int q = 0; q < cnt; ++q) {
+        if (TANGENT) acc += s_rhod[q][r] * s_mono[q][k] + s_rho[q][r] * s_monod[q][k];
+        else acc += s_rho[q][r] * s_mono[q][k];
+      }
+    }
+    __syncthreads();
+  }
+  if (t < NPK) out[int64_t(a) * NPK + t] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// contractions: block per atom
+//   fwd      g[f]  = sum_t coef M_a M_b M_c
+//   tangent  gd[f] = sum_t coef (Md_a M_b M_c + M_a Md_b M_c + M_a M_b Md_c)
+// ---------------------------------------------------------------------------------------------------------------------
+template <int TANGENT>
+__global__ void __launch_bounds__(384) k_tr_contract(Tables tab, const float* __restrict__ M, const float* __restrict__ Md,
+                                                     float* __restrict__ out) {
+  __shared__ float m[NPK + 1], md[NPK + 1];
+  const int a = blockIdx.x, t = threadIdx.x;
+  if (t < NPK) {
+    m[t] = M[int64_t(a) * NPK + t];
+    md[t] = TANGENT ? Md[int64_t(a) * NPK + t] : 0.f;
+  }
+  if (t == NPK) { m[NPK] = 1.f; md[NPK] = 0.f; }
+  __syncthreads();
+  if (t >= NF) return;
+  float acc = 0.f;
+  for (int q = tab.f_ptr[t]; q < tab.f_ptr[t + 1]; ++q) {
+    const uchar4 s = tab.f_slots[q];
+    const float c = tab.f_coef[q];
+    if (TANGENT) acc += c * (md[s.x] * m[s.y] * m[s.z] + m[s.x] * (md[s.y] * m[s.z] + m[s.y] * md[s.z]));
+    else acc += c * (m[s.x] * m[s.y] * m[s.z]);
+  }
+  out[int64_t(a) * NF + t] = acc;
+}
+
+// reverse:  out[i] = sum_occ coef * ( gb1[f] * M[o1] M[o2]  +  gb2[f] * (Md[o1] M[o2] + M[o1] Md[o2]) )
+// gb2 == nullptr: plain transpose-Jacobian product J(M)^T gb1.  With gb2 = adjoint of the tangent features this adds the
+// second-order term d/d(eps) J(M + eps Md)^T gb2.
+__global__ void __launch_bounds__(128) k_tr_contract_bwd(Tables tab, const float* __restrict__ M, const float* __restrict__ Md,
+                                                         const float* __restrict__ gb1, const float* __restrict__ gb2,
+                                                         float* __restrict__ out) {
+  __shared__ float m[NPK + 1], md[NPK + 1], g1[NF], g2[NF];
+  const int a = blockIdx.x, t = threadIdx.x;
+  for (int i = t; i < NF; i += blockDim.x) {
+    g1[i] = gb1[int64_t(a) * NF + i];
+    g2[i] = gb2 ? gb2[int64_t(a) * NF + i] : 0.f;
+  }
+  if (t < NPK) {
+    m[t] = M[int64_t(a) * NPK + t];
+    md[t] = gb2 ? Md[int64_t(a) * NPK + t] : 0.f;
+  }
+  if (t == NPK) { m[NPK] = 1.f; md[NPK] = 0.f; }
+  __syncthreads();
+  if (t >= NPK) return;
+  float acc = 0.f;
+  const bool second = gb2 != nullptr;
+  for (int q = tab.o_ptr[t]; q < tab.o_ptr[t + 1]; ++q) {
+    const int pk = tab.o_pack[q];
+    const int f = pk & 0xffff, o1 = (pk >> 16) & 0xff, o2 = (pk >> 24) & 0xff;
+    float v = g1[f] * (m[o1] * m[o2]);
+    if (second) v += g2[f] * (md[o1] * m[o2] + m[o1] * md[o2]);
+    acc += tab.o_coef[q] * v;
+  }
+  out[int64_t(a) * NPK + t] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// small fp32 GEMM with strided operands:  C[i][j] = sum_k A(i,k) B(k,j)  (+ bias[j]), 32x32 tile, 2x2 per thread
+// ---------------------------------------------------------------------------------------------------------------------
+enum { EPI_NONE = 0, EPI_ACT = 1, EPI_TAN = 2, EPI_MULD = 3, EPI_SECOND = 4 };
+
+__device__ __forceinline__ float sigm(float y) { return 1.0f / (1.0f + expf(-y)); }
+__device__ __forceinline__ float swish(float y) { return kSwish * y * sigm(y); }                       // activation.py:7-9
+__device__ __forceinline__ float dswish(float y) { const float s = sigm(y); return kSwish * (s + y * s * (1.f - s)); }
+__device__ __forceinline__ float d2swish(float y) {
+  const float s = sigm(y), q = s * (1.f - s);
+  return kSwish * (2.f * q + y * q * (1.f - 2.f * s));
+}
+
+struct GemmT {
+  const float* A; int64_t a_rs, a_cs;
+  const float* B; int64_t b_rs, b_cs;
+  float* C; int64_t ldc;
+  int M, N, K;
+  const float* bias;
+  int epi;
+  float* C2;          // second output, same shape/ld as C
+  const float* X1;    // [M][ldc] pre-activations of the primal rows
+  const float* X2;    // EPI_SECOND: adjoint of the tangent activations
+  const float* X3;    // EPI_SECOND: tangent pre-activations
+};
+
+__global__ void __launch_bounds__(256) k_tr_gemm(GemmT g) {
+  __shared__ float As[32][33], Bs[32][33];
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < g.K; k0 += 32) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = t + 256 * q;
+      int ii, kk;
+      if (g.a_cs == 1) { ii = e >> 5; kk = e & 31; } else { kk = e >> 5; ii = e & 31; }
+      const int gi = i0 + ii, gk = k0 + kk;
+      As[ii][kk] = (gi < g.M && gk < g.K) ? g.A[gi * g.a_rs + gk * g.a_cs] : 0.f;
+      int jj;
+      if (g.b_cs == 1) { kk = e >> 5; jj = e & 31; } else { jj = e >> 5; kk = e & 31; }
+      const int gj = j0 + jj;
+      const int gk2 = k0 + kk;
+      Bs[kk][jj] = (gj < g.N && gk2 < g.K) ? g.B[gk2 * g.b_rs + gj * g.b_cs] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      const float a0 = As[2 * ty][kk], a1 = As[2 * ty + 1][kk];
+      const float b0 = Bs[kk][2 * tx], b1 = Bs[kk][2 * tx + 1];
+      acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int di = 0; di < 2; ++di)
+#pragma unroll
+    for (int dj = 0; dj < 2; ++dj) {
+      const int i = i0 + 2 * ty + di, j = j0 + 2 * tx + dj;
+      if (i >= g.M || j >= g.N) continue;
+      float v = acc[di][dj];
+      if (g.bias) v += g.bias[j];
+      const int64_t o = int64_t(i) * g.ldc + j;
+      g.C[o] = v;
+      switch (g.epi) {
+        case EPI_ACT: g.C2[o] = swish(v); break;
+        case EPI_TAN: g.C2[o] = dswish(g.X1[o]) * v; break;
+        case EPI_MULD: g.C2[o] = dswish(g.X1[o]) * v; break;
+        case EPI_SECOND: g.C2[o] = dswish(g.X1[o]) * v + g.X2[o] * d2swish(g.X1[o]) * g.X3[o]; break;
+        default: break;
+      }
+    }
+}
+
+int gemm(cudaStream_t s, const GemmT& g) {
+  dim3 grid((unsigned)cdiv(g.N, 32), (unsigned)cdiv(g.M, 32));
+  APAX_LAUNCH(k_tr_gemm, grid, dim3(256), 0, s, g);
+  return APAX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// head, energies, first adjoint row block
+// ---------------------------------------------------------------------------------------------------------------------
+// warp per atom: e_a = h2[a] . w2 + b2;  YB2[n + a][k] = -s~_a w2[k] swish'(y2[a][k])  (adjoint of the tangent pre-activation)
+__global__ void __launch_bounds__(256) k_tr_head(TrWs w, const float* __restrict__ w2, const float* __restrict__ b2,
+                                                 const int32_t* __restrict__ Z, const double* __restrict__ scale, int mask_atoms) {
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (a >= w.n) return;
+  const int z = Z[a];
+  const float st = float((mask_atoms && z == 0) ? 0.0 : scale[z]);
+  float acc = 0.f;
+  for (int k = lane; k < NH; k += 32) {
+    const int64_t o = int64_t(a) * NH + k;
+    acc += w.H2[o] * w2[k];
+    w.YB2[int64_t(w.n) * NH + o] = -st * w2[k] * dswish(w.Y2[o]);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) w.e_atom[a] = acc + b2[0];
+}
+
+// block per structure: E_s = sum_a mask (scale[Z] e_a + shift[Z]) in fp64 (scaling.py:40-50, models.py:109-122)
+__global__ void __launch_bounds__(128) k_tr_energy(TrWs w, const int32_t* __restrict__ struct_ptr, const int32_t* __restrict__ Z,
+                                                   const double* __restrict__ scale, const double* __restrict__ shift,
+                                                   int mask_atoms, double* __restrict__ energy_out) {
+  __shared__ double red[128];
+  const int s = blockIdx.x;
+  double acc = 0.0;
+  for (int a = struct_ptr[s] + threadIdx.x; a < struct_ptr[s + 1]; a += blockDim.x) {
+    const int z = Z[a];
+    if (!(mask_atoms && z == 0)) acc += scale[z] * double(w.e_atom[a]) + shift[z];
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 64; o; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { w.Es[s] = red[0]; energy_out[s] = red[0]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// per-pair reverse of the moments: q = d(-E)/d(dr) given Mdb = -dE/dM.  Thread per pair, block per atom.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_tr_pair_bwd(TrWs w, const float* __restrict__ emb, DescConstT dc) {
+  __shared__ float A[NPK];
+  const int a = blockIdx.x;
+  for (int i = threadIdx.x; i < NPK; i += blockDim.x) A[i] = w.Mdb[int64_t(a) * NPK + i];
+  __syncthreads();
+  for (int s = w.rs[a] + threadIdx.x; s < w.re[a]; s += blockDim.x) {
+    const int p = w.rowp[s];
+    const float4 g = w.geo[p];
+    PairT pt;
+    pair_terms(g, dc, pt);
+    float rho[NR], drho[NR], mono[20], gx[20], gy[20], gz[20];
+    radial(emb, __float_as_int(g.w), dc, pt, rho, drho);
+    monomials20(pt.n, mono);
+    monomial_grads(pt.n, gx, gy, gz);
+    float rbar = 0.f, nb0 = 0.f, nb1 = 0.f, nb2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      float rb = 0.f, x0 = 0.f, x1 = 0.f, x2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 20; ++k) {
+        const float av = A[r * 20 + k];
+        rb += av * mono[k];
+        x0 += av * gx[k]; x1 += av * gy[k]; x2 += av * gz[k];
+      }
+      rbar += rb * drho[r];
+      nb0 += rho[r] * x0; nb1 += rho[r] * x1; nb2 += rho[r] * x2;
+    }
+    // dn/dd^T nbar = nbar/(r+eps) - d (d.nbar) / (r (r+eps)^2);  dr/dd = d/r (0 at r = 0)
+    float q0 = nb0 * pt.inv_re, q1 = nb1 * pt.inv_re, q2 = nb2 * pt.inv_re;
+    if (pt.r > 0.f) {
+      const float dn = g.x * nb0 + g.y * nb1 + g.z * nb2;
+      const float k = rbar / pt.r - dn * pt.inv_re * pt.inv_re / pt.r;
+      q0 += g.x * k; q1 += g.y * k; q2 += g.z * k;
+    }
+    w.Q[p] = make_float4(q0, q1, q2, 0.f);
+  }
+}
+
+// block per structure: forces (fp64), u = dL/dF, alpha = dL/dE, loss of the structure (loss.py:231-243)
+struct LossArgs {
+  double wE, expE, wF, expF, batch_divisor;
+};
+__global__ void __launch_bounds__(128) k_tr_forces_loss(TrWs w, const int32_t* __restrict__ struct_ptr,
+                                                        const int32_t* __restrict__ n_real, const double* __restrict__ E_lab,
+                                                        const double* __restrict__ F_lab, LossArgs la, double* __restrict__ F_out) {
+  __shared__ double red[128];
+  const int s = blockIdx.x;
+  const double na = double(n_real[s]);
+  const double cE = la.wE / (pow(na, la.expE) * la.batch_divisor);
+  const double cF = la.wF / (pow(na, la.expF) * la.batch_divisor);
+  double acc = 0.0;
+  for (int a = struct_ptr[s] + threadIdx.x; a < struct_ptr[s + 1]; a += blockDim.x) {
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    for (int q = w.rs[a]; q < w.re[a]; ++q) {
+      const float4 v = w.Q[w.rowp[q]];
+      f0 += double(v.x); f1 += double(v.y); f2 += double(v.z);
+    }
+    for (int q = w.ts[a]; q < w.te[a]; ++q) {
+      const float4 v = w.Q[w.trowp[q]];
+      f0 -= double(v.x); f1 -= double(v.y); f2 -= double(v.z);
+    }
+    F_out[3 * int64_t(a) + 0] = f0; F_out[3 * int64_t(a) + 1] = f1; F_out[3 * int64_t(a) + 2] = f2;
+    const double e0 = f0 - F_lab[3 * int64_t(a) + 0], e1 = f1 - F_lab[3 * int64_t(a) + 1], e2 = f2 - F_lab[3 * int64_t(a) + 2];
+    w.u[3 * int64_t(a) + 0] = 2.0 * cF * e0; w.u[3 * int64_t(a) + 1] = 2.0 * cF * e1; w.u[3 * int64_t(a) + 2] = 2.0 * cF * e2;
+    acc += cF * (e0 * e0 + e1 * e1 + e2 * e2);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 64; o; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double dE = w.Es[s] - E_lab[s];
+    w.alpha[s] = 2.0 * cE * dE;
+    w.cF[s] = cF;
+    w.loss_s[s] = red[0] + cE * dE * dE;
+  }
+}
+
+__global__ void __launch_bounds__(32) k_tr_loss_sum(TrWs w, double* __restrict__ loss) {
+  if (threadIdx.x == 0) {
+    double acc = 0.0;
+    for (int64_t s = 0; s < w.B; ++s) acc += w.loss_s[s];
+    loss[0] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// second half of the head: tangent output, first row block of the reverse sweep
+// warp per atom: edot_a = hdot2[a] . w2;  YB2[a][k] = alpha s~ w2[k] swish'(y2) - s~ w2[k] swish''(y2) ydot2
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tr_head2(TrWs w, const float* __restrict__ w2, const int32_t* __restrict__ Z,
+                                                  const int32_t* __restrict__ atom_struct, const double* __restrict__ scale,
+                                                  int mask_atoms) {
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (a >= w.n) return;
+  const int z = Z[a];
+  const float st = float((mask_atoms && z == 0) ? 0.0 : scale[z]);
+  const float al = float(w.alpha[atom_struct[a]]);
+  float acc = 0.f;
+  for (int k = lane; k < NH; k += 32) {
+    const int64_t o = int64_t(a) * NH + k, od = int64_t(w.n) * NH + o;
+    acc += w.H2[od] * w2[k];
+    const float y = w.Y2[o];
+    w.YB2[o] = st * w2[k] * (al * dswish(y) - d2swish(y) * w.Y2[od]);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) w.e_atom[w.n + a] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_tr_atom_struct(const int32_t* __restrict__ struct_ptr, int64_t B, int32_t* __restrict__ atom_struct) {
+  const int s = blockIdx.x;
+  for (int a = struct_ptr[s] + threadIdx.x; a < struct_ptr[s + 1]; a += blockDim.x) atom_struct[a] = s;
+}
+
+// gradients of the output layer and of scale / shift.  grid: 1 + ceil(S / 4) blocks of 256 threads.
+//   block 0: thread k: w2bar[k] = sum_a s~_a (alpha h2[a][k] - hdot2[a][k]);  thread 0 also b2bar = sum_a alpha s~_a
+//   other blocks: warp per species z: scalebar[z] = sum_{a: Z_a = z} mask (alpha e_a - edot_a), shiftbar[z] = sum alpha mask
+__global__ void __launch_bounds__(256) k_tr_head_grads(TrWs w, const int32_t* __restrict__ Z, const int32_t* __restrict__ atom_struct,
+                                                       const double* __restrict__ scale, int mask_atoms, int S,
+                                                       float* __restrict__ w2bar, float* __restrict__ b2bar,
+                                                       double* __restrict__ scalebar, double* __restrict__ shiftbar) {
+  if (blockIdx.x == 0) {
+    const int k = threadIdx.x;
+    float acc = 0.f, accb = 0.f;
+    for (int64_t a = 0; a < w.n; ++a) {
+      const int z = Z[a];
+      const float st = float((mask_atoms && z == 0) ? 0.0 : scale[z]);
+      const float al = float(w.alpha[atom_struct[a]]);
+      acc += st * (al * w.H2[a * NH + k] - w.H2[(w.n + a) * NH + k]);
+      accb += al * st;
+    }
+    w2bar[k] = acc;
+    if (k == 0) b2bar[0] = accb;
+    return;
+  }
+  const int z = (blockIdx.x - 1) * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (z >= S) return;
+  double sc = 0.0, sh = 0.0;
+  if (!(mask_atoms && z == 0)) {
+    for (int64_t a = lane; a < w.n; a += 32) {
+      if (Z[a] != z) continue;
+      const double al = w.alpha[atom_struct[a]];
+      sc += al * double(w.e_atom[a]) - double(w.e_atom[w.n + a]);
+      sh += al;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    sc += __shfl_xor_sync(0xffffffffu, sc, o);
+    sh += __shfl_xor_sync(0xffffffffu, sh, o);
+  }
+  if (lane == 0) { scalebar[z] = sc; shiftbar[z] = sh; }
+}
+
+// bias gradients: column sums of the first n rows of the pre-activation adjoints.  thread per column.
+__global__ void __launch_bounds__(256) k_tr_colsum(const float* __restrict__ X, int64_t n, int ld, float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ld) return;
+  float acc = 0.f;
+  for (int64_t a = 0; a < n; ++a) acc += X[a * ld + k];
+  out[k] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// embedding gradient.  Per pair:  cbar[r][b] = rhobar_r fc G_b + rhodotbar_r rdot (fc G'_b + fc' G_b)
+//   rhobar_r    = sum_k Mb2[r][k] mono_k + Mdb[r][k] monodot_k       rhodotbar_r = sum_k Mdb[r][k] mono_k
+// then a fixed-order reduction per species pair into the [S][S][5][7] table.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_tr_emb_pair(TrWs w, const int32_t* __restrict__ idx, DescConstT dc) {
+  __shared__ float A1[NPK], A2[NPK];
+  const int a = blockIdx.x;
+  for (int i = threadIdx.x; i < NPK; i += blockDim.x) {
+    A1[i] = w.Mb2[int64_t(a) * NPK + i];
+    A2[i] = w.Mdb[int64_t(a) * NPK + i];
+  }
+  __syncthreads();
+  for (int s = w.rs[a] + threadIdx.x; s < w.re[a]; s += blockDim.x) {
+    const int p = w.rowp[s];
+    const float4 g = w.geo[p];
+    PairT pt;
+    pair_terms(g, dc, pt);
+    float mono[20], gx[20], gy[20], gz[20], rdot, nd[3];
+    monomials20(pt.n, mono);
+    monomial_grads(pt.n, gx, gy, gz);
+    pair_tangent(g, pt, w.u, a, idx[p], rdot, nd);
+    float* out = w.cbar + int64_t(p) * 35;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      float rb = 0.f, rdb = 0.f;
+#pragma unroll
+      for (int k = 0; k < 20; ++k) {
+        const float md = gx[k] * nd[0] + gy[k] * nd[1] + gz[k] * nd[2];
+        rb += A1[r * 20 + k] * mono[k] + A2[r * 20 + k] * md;
+        rdb += A2[r * 20 + k] * mono[k];
+      }
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+        out[r * NB + b] = dc.inv_sqrt_nb * (rb * pt.fc * pt.G[b] + rdb * rdot * (pt.fc * pt.dG[b] + pt.dfc * pt.G[b]));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_tr_species_mark(const int32_t* __restrict__ Z, int64_t n, int32_t* __restrict__ present) {
+  const int64_t a = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (a < n) present[Z[a] & 127] = 1;   // benign race: every writer stores 1
+}
+
+// grid (S, S): block (zc, zn) returns at once unless both species are present; else sums the cbar rows whose key matches,
+// thread-strided partial sums then a fixed tree.
+__global__ void __launch_bounds__(128) k_tr_emb_reduce(TrWs w, int S, float* __restrict__ embbar) {
+  const int zc = blockIdx.y, zn = blockIdx.x;
+  if (!w.present[zc] || !w.present[zn]) return;
+  __shared__ float red[128][36];
+  const int key = zc * S + zn;
+  float acc[35];
+#pragma unroll
+  for (int q = 0; q < 35; ++q) acc[q] = 0.f;
+  for (int64_t p = threadIdx.x; p < w.P; p += blockDim.x) {
+    if (__float_as_int(w.geo[p].w) != key) continue;
+    const float* c = w.cbar + p * 35;
+#pragma unroll
+    for (int q = 0; q < 35; ++q) acc[q] += c[q];
+  }
+#pragma unroll
+  for (int q = 0; q < 35; ++q) red[threadIdx.x][q] = acc[q];
+  __syncthreads();
+  for (int o = 64; o; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int q = 0; q < 35; ++q) red[threadIdx.x][q] += red[threadIdx.x + o][q];
+    __syncthreads();
+  }
+  if (threadIdx.x < 35) embbar[int64_t(key) * 35 + threadIdx.x] = red[0][threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// optimizer: optax.chain(clip(c), adam(linear_schedule), zero_nans()) per group (get_optimizer.py:73-85)
+// ---------------------------------------------------------------------------------------------------------------------
+struct AdamArgs {
+  double lr_emb, lr_nn, lr_scale, lr_shift, clip, end_value, b1, b2, eps;
+  int64_t transition_steps, transition_begin;
+  int64_t emb_count;    // elements [0, emb_count) of the fp32 block are the embedding group
+  int64_t n32, n64, S;
+};
+
+__device__ __forceinline__ double sched(double init, int64_t count, const AdamArgs& a) {
+  // optax.linear_schedule == polynomial_schedule(power = 1)
+  int64_t c = count - a.transition_begin;
+  c = c < 0 ? 0 : (c > a.transition_steps ? a.transition_steps : c);
+  const double frac = 1.0 - double(c) / double(a.transition_steps);
+  return (init - a.end_value) * frac + a.end_value;
+}
+
+template <class T>
+__device__ __forceinline__ void adam_one(T& p, T g, T& m, T& v, double lr0, int64_t count, const AdamArgs& a) {
+  if (lr0 <= 1e-7) return;   // optax.set_to_zero (get_optimizer.py:74-75)
+  const T c = T(a.clip);
+  g = g < -c ? -c : (g > c ? c : g);
+  m = T(a.b1) * m + T(1.0 - a.b1) * g;
+  v = T(a.b2) * v + T(1.0 - a.b2) * g * g;
+  const double t = double(count + 1);
+  const T mh = m / T(1.0 - pow(a.b1, t));
+  const T vh = v / T(1.0 - pow(a.b2, t));
+  T upd = T(-sched(lr0, count, a)) * (mh / (sqrt(vh) + T(a.eps)));
+  if (upd != upd) upd = T(0);
+  p += upd;
+}
+
+__global__ void __launch_bounds__(256) k_tr_adam(AdamArgs a, float* __restrict__ th32, const float* __restrict__ g32,
+                                                 float* __restrict__ m32, float* __restrict__ v32, double* __restrict__ th64,
+                                                 const double* __restrict__ g64, double* __restrict__ m64,
+                                                 double* __restrict__ v64, const int64_t* __restrict__ count_dev) {
+  const int64_t count = *count_dev;
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < a.n32) {
+    float p = th32[i], m = m32[i], v = v32[i];
+    adam_one<float>(p, g32[i], m, v, i < a.emb_count ? a.lr_emb : a.lr_nn, count, a);
+    th32[i] = p; m32[i] = m; v32[i] = v;
+  }
+  if (i < a.n64) {
+    double p = th64[i], m = m64[i], v = v64[i];
+    adam_one<double>(p, g64[i], m, v, i < a.S ? a.lr_scale : a.lr_shift, count, a);
+    th64[i] = p; m64[i] = m; v64[i] = v;
+  }
+}
+
+__global__ void k_tr_count_inc(int64_t* count_dev) { *count_dev += 1; }
+
+}  // namespace
+}  // namespace apax
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+using namespace apax;
+
+extern "C" int apax_train_plan_create(const apax_gm_config* cfg, apax_train_plan** out) {
+  if (!cfg || !out) return APAX_ERR_INVALID_ARG;
+  if (cfg->n_radial != NR || cfg->n_basis != NB || cfg->n_contr != 8 || cfg->n_hidden1 != NH || cfg->n_hidden2 != NH ||
+      cfg->n_out != 1 || cfg->use_ntk != 0 || cfg->n_species < 1 || cfg->n_species > 128)
+    return APAX_ERR_UNSUPPORTED;
+  std::vector<Term> terms = build_terms();
+  if (terms.empty()) return APAX_ERR_INVALID_ARG;
+  const int nt = int(terms.size());
+  std::vector<int32_t> f_ptr(NF + 1, 0), o_ptr(NPK + 1, 0);
+  std::vector<float> f_coef(nt);
+  std::vector<uchar4> f_slots(nt);
+  for (int q = 0; q < nt; ++q) {
+    f_ptr[terms[q].f + 1] += 1;
+    f_coef[q] = terms[q].coef;
+    f_slots[q] = make_uchar4(terms[q].a, terms[q].b, terms[q].c, 0);
+  }
+  for (int f = 0; f < NF; ++f) f_ptr[f + 1] += f_ptr[f];
+  // occurrences by slot (the constant slot has none)
+  std::vector<std::vector<std::pair<float, int32_t>>> occ(NPK);
+  for (int q = 0; q < nt; ++q) {
+    const int sl[3] = {terms[q].a, terms[q].b, terms[q].c};
+    for (int w = 0; w < 3; ++w) {
+      if (sl[w] == ONE_SLOT) continue;
+      const int o1 = sl[(w + 1) % 3], o2 = sl[(w + 2) % 3];
+      occ[sl[w]].push_back({terms[q].coef, int32_t(terms[q].f | (o1 << 16) | (o2 << 24))});
+    }
+  }
+  std::vector<float> o_coef;
+  std::vector<int32_t> o_pack;
+  for (int i = 0; i < NPK; ++i) {
+    o_ptr[i] = int32_t(o_coef.size());
+    for (auto& e : occ[i]) { o_coef.push_back(e.first); o_pack.push_back(e.second); }
+  }
+  o_ptr[NPK] = int32_t(o_coef.size());
+  const int no = int(o_coef.size());
+
+  apax_train_plan* p = new apax_train_plan();
+  p->cfg = *cfg;
+  Carver c(nullptr);
+  c.take<int32_t>(NF + 1); c.take<float>(nt); c.take<uchar4>(nt); c.take<int32_t>(NPK + 1); c.take<float>(no); c.take<int32_t>(no);
+  const size_t bytes = c.bytes();
+  if (cudaMalloc(&p->dev_block, bytes) != cudaSuccess) { delete p; return APAX_ERR_CUDA; }
+  Carver d(p->dev_block);
+  int32_t* d_fptr = d.take<int32_t>(NF + 1); float* d_fcoef = d.take<float>(nt); uchar4* d_fslots = d.take<uchar4>(nt);
+  int32_t* d_optr = d.take<int32_t>(NPK + 1); float* d_ocoef = d.take<float>(no); int32_t* d_opack = d.take<int32_t>(no);
+  bool ok = true;
+  ok &= cudaMemcpy(d_fptr, f_ptr.data(), sizeof(int32_t) * (NF + 1), cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(d_fcoef, f_coef.data(), sizeof(float) * nt, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(d_fslots, f_slots.data(), sizeof(uchar4) * nt, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(d_optr, o_ptr.data(), sizeof(int32_t) * (NPK + 1), cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(d_ocoef, o_coef.data(), sizeof(float) * no, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(d_opack, o_pack.data(), sizeof(int32_t) * no, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok) { cudaFree(p->dev_block); delete p; return APAX_ERR_CUDA; }
+  p->tab = Tables{d_fptr, d_fcoef, d_fslots, d_optr, d_ocoef, d_opack};
+  const double beta = double(cfg->n_basis) * cfg->n_basis / (double(cfg->r_max) * cfg->r_max);
+  p->dc.r_max = cfg->r_max;
+  p->dc.beta = float(beta);
+  p->dc.two_beta = float(2.0 * beta);
+  p->dc.norm = float(pow(2.0 * beta / M_PI, 0.25));
+  p->dc.pi_f = float(M_PI);
+  p->dc.inv_sqrt_nb = cfg->use_embed_norm ? float(1.0 / sqrt(double(cfg->n_basis))) : 1.0f;
+  for (int b = 0; b < NB; ++b)
+    p->dc.mu[b] = float(double(cfg->r_min) + (double(cfg->r_max) - double(cfg->r_min)) / cfg->n_basis * b);
+  // parameter block layout: every array starts on a 64-element boundary
+  const int64_t S = cfg->n_species;
+  const int64_t sizes[7] = {S * S * NR * NB, int64_t(NF) * NH, NH, int64_t(NH) * NH, NH, NH, 1};
+  int64_t off = 0;
+  for (int i = 0; i < 7; ++i) { p->off32[i] = off; off = round_up(off + sizes[i], 64); }
+  p->off32[7] = off;
+  p->off64[0] = 0; p->off64[1] = S; p->off64[2] = 2 * S;
+  *out = p;
+  return APAX_OK;
+}
+
+extern "C" void apax_train_plan_destroy(apax_train_plan* p) {
+  if (!p) return;
+  cudaFree(p->dev_block);
+  delete p;
+}
+
+extern "C" int apax_train_param_layout(const apax_train_plan* p, int64_t* offsets32, int64_t* offsets64) {
+  if (!p) return APAX_ERR_INVALID_ARG;
+  if (offsets32) for (int i = 0; i < 8; ++i) offsets32[i] = p->off32[i];
+  if (offsets64) for (int i = 0; i < 3; ++i) offsets64[i] = p->off64[i];
+  return APAX_OK;
+}
+
+extern "C" size_t apax_train_workspace_bytes(const apax_train_plan* p, int64_t n_atoms, int64_t n_pairs, int64_t n_structs) {
+  (void)p;
+  size_t b = carve_tr(nullptr, n_atoms, n_pairs, n_structs, nullptr);
+  return b + size_t(round_up(n_atoms, 64)) * sizeof(int32_t) + 256;   // + atom -> structure map
+}
+
+extern "C" int apax_train_loss_and_grad(apax_stream_t stream_, const apax_train_plan* p, const float* theta32,
+                                        const double* theta64, const double* R, const int32_t* Z, const int32_t* idx,
+                                        const double* offsets, const int32_t* struct_ptr, const int32_t* pair_ptr,
+                                        const int32_t* n_real, int64_t n_structs, int64_t n_atoms, int64_t n_pairs,
+                                        const double* E_label, const double* F_label, const apax_train_loss_config* lc,
+                                        double batch_divisor, double* loss, double* energy, double* forces, float* grad32,
+                                        double* grad64, void* workspace, size_t workspace_bytes) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  if (!p || !theta32 || !theta64 || !R || !Z || !idx || !struct_ptr || !pair_ptr || !n_real || !E_label || !F_label || !lc ||
+      !loss || !energy || !forces || !grad32 || !grad64 || !workspace)
+    return APAX_ERR_INVALID_ARG;
+  if (n_structs < 1 || n_atoms < 1 || n_pairs < 1 || n_atoms > (int64_t(1) << 24) || n_pairs > (int64_t(1) << 30)) return APAX_ERR_INVALID_ARG;
+  if (workspace_bytes < apax_train_workspace_bytes(p, n_atoms, n_pairs, n_structs)) return APAX_ERR_WORKSPACE;
+  TrWs w;
+  const size_t used = carve_tr(workspace, n_atoms, n_pairs, n_structs, &w);
+  int32_t* atom_struct = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + used);
+  const int64_t n = n_atoms, P = n_pairs, B = n_structs;
+  const int S = p->cfg.n_species, mask = p->cfg.mask_atoms;
+  const float* emb = theta32 + p->off32[0];
+  const float *w0 = theta32 + p->off32[1], *b0 = theta32 + p->off32[2], *w1 = theta32 + p->off32[3], *b1 = theta32 + p->off32[4],
+              *w2 = theta32 + p->off32[5], *b2 = theta32 + p->off32[6];
+  const double *scale = theta64 + p->off64[0], *shift = theta64 + p->off64[1];
+  float *g_emb = grad32 + p->off32[0], *g_w0 = grad32 + p->off32[1], *g_b0 = grad32 + p->off32[2], *g_w1 = grad32 + p->off32[3],
+        *g_b1 = grad32 + p->off32[4], *g_w2 = grad32 + p->off32[5], *g_b2 = grad32 + p->off32[6];
+  const Tables& tab = p->tab;
+  const DescConstT& dc = p->dc;
+
+  APAX_CUDA_TRY(cudaMemsetAsync(grad32, 0, sizeof(float) * size_t(p->off32[7]), s));
+  APAX_CUDA_TRY(cudaMemsetAsync(w.present, 0, sizeof(int32_t) * 128, s));
+  // lists and geometry
+  APAX_LAUNCH(k_tr_group, dim3((unsigned)B), dim3(128), 0, s, idx, P, struct_ptr, pair_ptr, w);
+  APAX_LAUNCH(k_tr_atom_struct, dim3((unsigned)B), dim3(256), 0, s, struct_ptr, B, atom_struct);
+  APAX_LAUNCH(k_tr_geom, dim3((unsigned)cdiv(P, 256)), dim3(256), 0, s, R, Z, idx, offsets, S, atom_struct, pair_ptr, w);
+  APAX_LAUNCH(k_tr_species_mark, dim3((unsigned)cdiv(n, 128)), dim3(128), 0, s, Z, n, w.present);
+  // ---- energy
+  APAX_LAUNCH(k_tr_moments<0>, dim3((unsigned)n), dim3(128), 0, s, w, emb, idx, dc, w.M);
+  APAX_LAUNCH(k_tr_contract<0>, dim3((unsigned)n), dim3(384), 0, s, tab, w.M, nullptr, w.GS);
+  GemmT g{};
+  g = GemmT{w.GS, NF, 1, w0, NH, 1, w.Y1, NH, int(n), NH, NF, b0, EPI_ACT, w.H1, nullptr, nullptr, nullptr};
+  APAX_TRY(gemm(s, g));
+  g = GemmT{w.H1, NH, 1, w1, NH, 1, w.Y2, NH, int(n), NH, NH, b1, EPI_ACT, w.H2, nullptr, nullptr, nullptr};
+  APAX_TRY(gemm(s, g));
+  APAX_LAUNCH(k_tr_head, dim3((unsigned)cdiv(n * 32, 256)), dim3(256), 0, s, w, w2, b2, Z, scale, mask);
+  APAX_LAUNCH(k_tr_energy, dim3((unsigned)B), dim3(128), 0, s, w, struct_ptr, Z, scale, shift, mask, energy);
+  // ---- forces: adjoint chain of the TANGENT quantities (= minus the energy-gradient chain), rows [n, 2n)
+  g = GemmT{w.YB2 + n * NH, NH, 1, w1, 1, NH, w.HB1 + n * NH, NH, int(n), NH, NH, nullptr, EPI_MULD, w.YB1 + n * NH, w.Y1, nullptr, nullptr};
+  APAX_TRY(gemm(s, g));
+  g = GemmT{w.YB1 + n * NH, NH, 1, w0, 1, NH, w.GB + n * NF, NF, int(n), NF, NH, nullptr, EPI_NONE, nullptr, nullptr, nullptr, nullptr};
+  APAX_TRY(gemm(s, g));
+  APAX_LAUNCH(k_tr_contract_bwd, dim3((unsigned)n), dim3(128), 0, s, tab, w.M, nullptr, w.GB + n * NF, nullptr, w.Mdb);
+  APAX_LAUNCH(k_tr_pair_bwd, dim3((unsigned)n), dim3(64), 0, s, w, emb, dc);
+  LossArgs la{lc->energy_weight, lc->energy_atoms_exponent, lc->forces_weight, lc->forces_atoms_exponent, batch_divisor};
+  APAX_LAUNCH(k_tr_forces_loss, dim3((unsigned)B), dim3(128), 0, s, w, struct_ptr, n_real, E_label, F_label, la, forces);
+  APAX_LAUNCH(k_tr_loss_sum, dim3(1), dim3(32), 0, s, w, loss);
+  // ---- tangent sweep along u = dL/dF, rows [n, 2n)
+  APAX_LAUNCH(k_tr_moments<1>, dim3((unsigned)n), dim3(128), 0, s, w, emb, idx, dc, w.Md);
+  APAX_LAUNCH(k_tr_contract<1>, dim3((unsigned)n), dim3(384), 0, s, tab, w.M, w.Md, w.GS + n * NF);
+  g = GemmT{w.GS + n * NF, NF, 1, w0, NH, 1, w.Y1 + n * NH, NH, int(n), NH, NF, nullptr, EPI_TAN, w.H1 + n * NH, w.Y1, nullptr, nullptr};
+  APAX_TRY(gemm(s, g));
+  g = GemmT{w.H1 + n * NH, NH, 1, w1, NH, 1, w.Y2 + n * NH, NH, int(n), NH, NH, nullptr, EPI_TAN, w.H2 + n * NH, w.Y2, nullptr, nullptr};
+  APAX_TRY(gemm(s, g));
+  // ---- reverse sweep of  sum_s alpha_s E_s - Edot, rows [0, n)
+  APAX_LAUNCH(k_tr_head2, dim3((unsigned)cdiv(n * 32, 256)), dim3(256), 0, s, w, w2, Z, atom_struct, scale, mask);
+  APAX_LAUNCH(k_tr_head_grads, dim3((unsigned)(1 + cdiv(S, 8))), dim3(256), 0, s, w, Z, atom_struct, scale, mask, S, g_w2, g_b2,
+              grad64 + p->off64[0], grad64 + p->off64[1]);
+  g = GemmT{w.YB2, NH, 1, w1, 1, NH, w.HB1, NH, int(n), NH, NH, nullptr, EPI_SECOND, w.YB1, w.Y1, w.HB1 + n * NH, w.Y1 + n * NH};
+  APAX_TRY(gemm(s, g));
+  g = GemmT{w.YB1, NH, 1, w0, 1, NH, w.GB, NF, int(n), NF, NH, nullptr, EPI_NONE, nullptr, nullptr, nullptr, nullptr};
+  APAX_TRY(gemm(s, g));
+  // weight gradients: [x ; xdot]^T [ybar ; ydotbar] over all 2n rows
+  g = GemmT{w.H1, 1, NH, w.YB2, NH, 1, g_w1, NH, NH, NH, int(2 * n), nullptr, EPI_NONE, nullptr, nullptr, nullptr, nullptr};
+  APAX_TRY(gemm(s, g));
+  g = GemmT{w.GS, 1, NF, w.YB1, NH, 1, g_w0, NH, NF, NH, int(2 * n), nullptr, EPI_NONE, nullptr, nullptr, nullptr, nullptr};
+  APAX_TRY(gemm(s, g));
+  APAX_LAUNCH(k_tr_colsum, dim3(1), dim3(256), 0, s, w.YB2, n, NH, g_b1);
+  APAX_LAUNCH(k_tr_colsum, dim3(1), dim3(256), 0, s, w.YB1, n, NH, g_b0);
+  // moments' adjoint incl. the second-order term, then the embedding gradient
+  APAX_LAUNCH(k_tr_contract_bwd, dim3((unsigned)n), dim3(128), 0, s, tab, w.M, w.Md, w.GB, w.GB + n * NF, w.Mb2);
+  APAX_LAUNCH(k_tr_emb_pair, dim3((unsigned)n), dim3(64), 0, s, w, idx, dc);
+  APAX_LAUNCH(k_tr_emb_reduce, dim3((unsigned)S, (unsigned)S), dim3(128), 0, s, w, S, g_emb);
+  return APAX_OK;
+}
+
+extern "C" int apax_train_adam_step(apax_stream_t stream_, const apax_train_plan* p, const apax_train_opt_config* oc,
+                                    float* theta32, double* theta64, const float* grad32, const double* grad64, float* m32,
+                                    float* v32, double* m64, double* v64, int64_t* count_device) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  if (!p || !oc || !theta32 || !theta64 || !grad32 || !grad64 || !m32 || !v32 || !m64 || !v64 || !count_device)
+    return APAX_ERR_INVALID_ARG;
+  if (oc->transition_steps < 1) return APAX_ERR_INVALID_ARG;
+  AdamArgs a{oc->emb_lr, oc->nn_lr, oc->scale_lr, oc->shift_lr, oc->gradient_clipping, oc->end_value, oc->b1, oc->b2, oc->eps,
+             oc->transition_steps, oc->transition_begin, p->off32[1], p->off32[7], p->off64[2], p->cfg.n_species};
+  APAX_LAUNCH(k_tr_adam, dim3((unsigned)cdiv(std::max(a.n32, a.n64), 256)), dim3(256), 0, s, a, theta32, grad32, m32, v32, theta64,
+              grad64, m64, v64, count_device);
+  APAX_LAUNCH(k_tr_count_inc, dim3(1), dim3(1), 0, s, count_device);
+  return APAX_OK;
+}

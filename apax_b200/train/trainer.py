@@ -1,0 +1,272 @@
+"""Mirror of the training step of apax/train/trainer.py (`make_step_fns`, :296-372; `calc_loss`, :253-263) and of the
+train state it updates (flax TrainState created at apax/train/checkpoints.py:32-45), for the GMNN model.
+
+Everything numerical happens in libapax_b200.so (`apax_train_loss_and_grad`, `apax_train_adam_step`, csrc/train.cu);
+this file owns device buffers (torch = plumbing), flattens the reference's padded batch
+(apax/data/input_pipeline.py:423-470) into the concatenated layout of the C ABI, and, when torch.distributed is
+initialised, sums the gradient blocks over ranks (the reference shards the batch over a device mesh and lets XLA
+insert the all-reduce, trainer.py:101-106, input_pipeline.py:296-300).  No oracle, no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import check, lib
+from ..optimizer.get_optimizer import AdamLinear
+from ..runtime import Workspace, _ptr, _require_cuda, _stream_ptr, default_config
+from .loss import LossCollection
+
+_NAMES32 = ("emb", "w0", "b0", "w1", "b1", "w2", "b2")
+
+
+class TrainState:
+    """params + optimizer state on the device (flax.training.train_state.TrainState: step, params, tx, opt_state)."""
+
+    def __init__(self, params: dict, tx: AdamLinear, config: Optional[dict] = None):
+        dev = _require_cuda()
+        tree = params.get("params", params)
+        tree = tree.get("energy_model", tree)
+        emb = np.asarray(tree["representation"]["radial_fn"]["atomic_type_embedding"], dtype=np.float32)
+        ro = tree["readout"]
+        if len(ro) != 3:
+            raise _lib.ApaxB200Error(_lib.ERR_UNSUPPORTED, "TrainState", "readout must be [256, 256] + output layer")
+        cfg = default_config(n_out=1)
+        if config:
+            cfg.update(config)
+        cfg["n_species"] = int(emb.shape[0])
+        self.config = cfg
+        c = _lib.GmConfig(n_species=cfg["n_species"], n_radial=cfg["n_radial"], n_basis=cfg["n_basis"], n_contr=cfg["n_contr"],
+                          n_hidden1=cfg["nn"][0], n_hidden2=cfg["nn"][1], n_out=1, use_ntk=int(cfg["use_ntk"]),
+                          use_embed_norm=int(cfg["use_embed_norm"]), mask_atoms=int(cfg["mask_atoms"]), r_min=cfg["r_min"],
+                          r_max=cfg["r_max"])
+        self.plan = C.c_void_p()
+        check(lib().apax_train_plan_create(C.byref(c), C.byref(self.plan)), "apax_train_plan_create")
+        o32 = (C.c_int64 * 8)()
+        o64 = (C.c_int64 * 3)()
+        check(lib().apax_train_param_layout(self.plan, C.cast(o32, C.c_void_p), C.cast(o64, C.c_void_p)), "apax_train_param_layout")
+        self.off32, self.off64 = list(o32), list(o64)
+        S = cfg["n_species"]
+        self.shapes32 = {"emb": (S, S, cfg["n_radial"], cfg["n_basis"]), "w0": (360, 256), "b0": (256,), "w1": (256, 256),
+                         "b1": (256,), "w2": (256, 1), "b2": (1,)}
+        host32 = np.zeros(self.off32[7], dtype=np.float32)
+        arrays = {"emb": emb}
+        for li in range(3):
+            arrays[f"w{li}"] = np.asarray(ro[f"dense_{li}"]["w"], dtype=np.float32)
+            arrays[f"b{li}"] = np.asarray(ro[f"dense_{li}"]["b"], dtype=np.float32)
+        for k, name in enumerate(_NAMES32):
+            a = arrays[name]
+            if tuple(a.shape) != self.shapes32[name]:
+                raise _lib.ApaxB200Error(_lib.ERR_INVALID_ARG, "TrainState", f"{name} has shape {a.shape}")
+            host32[self.off32[k]: self.off32[k] + a.size] = a.reshape(-1)
+        ss = tree["scale_shift"]
+        host64 = np.concatenate([np.broadcast_to(np.asarray(ss["scale_per_element"], dtype=np.float64).reshape(-1), (S,)),
+                                 np.broadcast_to(np.asarray(ss["shift_per_element"], dtype=np.float64).reshape(-1), (S,))])
+        self.theta32 = torch.as_tensor(host32).to(dev)
+        self.theta64 = torch.as_tensor(host64).to(dev)
+        self.grad32 = torch.zeros_like(self.theta32)
+        self.grad64 = torch.zeros_like(self.theta64)
+        self.m32, self.v32 = torch.zeros_like(self.theta32), torch.zeros_like(self.theta32)
+        self.m64, self.v64 = torch.zeros_like(self.theta64), torch.zeros_like(self.theta64)
+        self.count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.tx = tx
+        self._opt_c = tx.to_c()
+
+    @property
+    def step(self) -> int:
+        return int(self.count.item())
+
+    def _tree(self, t32: torch.Tensor, t64: torch.Tensor) -> dict:
+        h32, h64 = t32.cpu().numpy(), t64.cpu().numpy()
+        S = self.config["n_species"]
+        arr = {n: h32[self.off32[k]: self.off32[k] + int(np.prod(self.shapes32[n]))].reshape(self.shapes32[n]).copy()
+               for k, n in enumerate(_NAMES32)}
+        return {"params": {"energy_model": {
+            "representation": {"radial_fn": {"atomic_type_embedding": arr["emb"]}},
+            "readout": {f"dense_{i}": {"w": arr[f"w{i}"], "b": arr[f"b{i}"]} for i in range(3)},
+            "scale_shift": {"scale_per_element": h64[:S].reshape(S, 1).copy(), "shift_per_element": h64[S:2 * S].reshape(S, 1).copy()},
+        }}}
+
+    @property
+    def params(self) -> dict:
+        """The parameter tree in apax's layout (host copy)."""
+        return self._tree(self.theta32, self.theta64)
+
+    @property
+    def grads(self) -> dict:
+        """The gradient of the last loss evaluation, same tree layout (host copy)."""
+        return self._tree(self.grad32, self.grad64)
+
+    def apply_gradients(self) -> "TrainState":
+        """TrainState.apply_gradients with the gradient blocks already on the device (in place)."""
+        check(lib().apax_train_adam_step(_stream_ptr(), self.plan, C.byref(self._opt_c), _ptr(self.theta32), _ptr(self.theta64),
+                                         _ptr(self.grad32), _ptr(self.grad64), _ptr(self.m32), _ptr(self.v32), _ptr(self.m64),
+                                         _ptr(self.v64), _ptr(self.count)), "apax_train_adam_step")
+        return self
+
+    def __del__(self):
+        p = getattr(self, "plan", None)
+        if p is not None and p.value:
+            try:
+                lib().apax_train_plan_destroy(p)
+            except Exception:
+                pass
+            self.plan = None
+
+
+def flatten_batch(inputs: dict, labels: Optional[dict] = None) -> dict:
+    """The reference's padded batch -> concatenated host arrays of the C ABI.  Padding atoms (Z = 0) and padding
+    entries ((0,0) pairs) stay in place; periodic structures carry fractional positions (preprocessing.py:47-54),
+    which become Cartesian here (cart = box . frac, the transform of apax/layers/distances.py:12-14)."""
+    pos = np.asarray(inputs["positions"], dtype=np.float64)
+    B, nmax = pos.shape[0], pos.shape[1]
+    box = np.asarray(inputs["box"], dtype=np.float64).reshape(B, 3, 3) if np.asarray(inputs["box"]).size == B * 9 else None
+    if box is not None and np.any(np.abs(box) > 1e-6):
+        periodic = np.any(np.abs(box) > 1e-6, axis=(1, 2))
+        cart = np.einsum("bij,baj->bai", box, pos)
+        pos = np.where(periodic[:, None, None], cart, pos)
+    idx = np.asarray(inputs["idx"]).astype(np.int64)
+    pmax = idx.shape[2]
+    gidx = idx + (np.arange(B) * nmax)[:, None, None]
+    out = {
+        "R": np.ascontiguousarray(pos.reshape(B * nmax, 3)),
+        "Z": np.ascontiguousarray(np.asarray(inputs["numbers"]).reshape(B * nmax).astype(np.int32)),
+        "idx": np.ascontiguousarray(gidx.transpose(1, 0, 2).reshape(2, B * pmax).astype(np.int32)),
+        "offsets": np.ascontiguousarray(np.asarray(inputs["offsets"], dtype=np.float64).reshape(B * pmax, 3)),
+        "struct_ptr": (np.arange(B + 1) * nmax).astype(np.int32),
+        "pair_ptr": (np.arange(B + 1) * pmax).astype(np.int32),
+        "n_real": np.asarray(inputs["n_atoms"]).astype(np.int32).reshape(B),
+        "B": B, "nmax": nmax, "pmax": pmax,
+    }
+    if labels is not None:
+        out["E_label"] = np.ascontiguousarray(np.asarray(labels["energy"], dtype=np.float64).reshape(B))
+        out["F_label"] = np.ascontiguousarray(np.asarray(labels["forces"], dtype=np.float64).reshape(B * nmax, 3))
+    return out
+
+
+_KEYS = (("R", torch.float64), ("Z", torch.int32), ("idx", torch.int32), ("offsets", torch.float64),
+         ("struct_ptr", torch.int32), ("pair_ptr", torch.int32), ("n_real", torch.int32), ("E_label", torch.float64),
+         ("F_label", torch.float64))
+
+
+class DeviceBatch:
+    """Static device buffers for batches of one shape (B, Nmax, Pmax) + pinned host staging."""
+
+    def __init__(self, B: int, nmax: int, pmax: int):
+        dev = _require_cuda()
+        self.B, self.nmax, self.pmax = B, nmax, pmax
+        n, P = B * nmax, B * pmax
+        shapes = {"R": (n, 3), "Z": (n,), "idx": (2, P), "offsets": (P, 3), "struct_ptr": (B + 1,), "pair_ptr": (B + 1,),
+                  "n_real": (B,), "E_label": (B,), "F_label": (n, 3)}
+        self.dev = {k: torch.empty(shapes[k], dtype=dt, device=dev) for k, dt in _KEYS}
+        self.pin = {k: torch.empty(shapes[k], dtype=dt).pin_memory() for k, dt in _KEYS}
+        self.loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.energy = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.forces = torch.zeros((n, 3), dtype=torch.float64, device=dev)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pin.values())
+
+    def upload(self, flat: dict) -> None:
+        for k, _ in _KEYS:
+            self.pin[k].numpy()[...] = flat[k]
+            self.dev[k].copy_(self.pin[k], non_blocking=True)
+
+
+class TrainStep:
+    """update_step of trainer.py:332-336 for one batch shape: loss + gradients, all-reduce over ranks, Adam.
+
+    With `graph=True` the device work of a step is captured once in a CUDA graph (~35 small kernels: the step is
+    launch-latency bound) and replayed; new batches are copied into the static buffers first.
+    """
+
+    def __init__(self, state: TrainState, loss_fn: LossCollection, B: int, nmax: int, pmax: int, graph: bool = False,
+                 world_size: Optional[int] = None):
+        import torch.distributed as dist
+
+        self.state, self.loss_fn = state, loss_fn
+        self.batch = DeviceBatch(B, nmax, pmax)
+        self._loss_c = loss_fn.to_c()
+        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.world = (self.dist.get_world_size() if self.dist else 1) if world_size is None else world_size
+        self.ws = Workspace()
+        n, P = B * nmax, B * pmax
+        self.nbytes = lib().apax_train_workspace_bytes(state.plan, n, P, B)
+        self.buf = self.ws.get(self.nbytes)
+        self.graph = None
+        self._want_graph = graph
+
+    def _device_step(self) -> None:
+        st, b = self.state, self.batch
+        d = b.dev
+        n, P = b.B * b.nmax, b.B * b.pmax
+        check(lib().apax_train_loss_and_grad(
+            _stream_ptr(), st.plan, _ptr(st.theta32), _ptr(st.theta64), _ptr(d["R"]), _ptr(d["Z"]), _ptr(d["idx"]),
+            _ptr(d["offsets"]), _ptr(d["struct_ptr"]), _ptr(d["pair_ptr"]), _ptr(d["n_real"]), b.B, n, P, _ptr(d["E_label"]),
+            _ptr(d["F_label"]), C.byref(self._loss_c), float(b.B * self.world), _ptr(b.loss), _ptr(b.energy), _ptr(b.forces),
+            _ptr(st.grad32), _ptr(st.grad64), C.c_void_p(Workspace.aligned_ptr(self.buf)), C.c_size_t(self.nbytes)),
+            "apax_train_loss_and_grad")
+        if self.dist:   # gradients of the global-batch mean loss: per-rank parts add up (batch_divisor is global)
+            self.dist.all_reduce(st.grad32)
+            self.dist.all_reduce(st.grad64)
+            self.dist.all_reduce(b.loss)
+        st.apply_gradients()
+
+    def __call__(self, inputs: dict, labels: dict):
+        """Returns (loss tensor [1] f64, predictions {"energy": [B], "forces": [B,Nmax,3]} device tensors)."""
+        b = self.batch
+        b.upload(flatten_batch(inputs, labels))
+        self.run_resident()
+        return b.loss, {"energy": b.energy, "forces": b.forces.view(b.B, b.nmax, 3)}
+
+    def run_resident(self) -> None:
+        """One step on the batch already in the device buffers."""
+        if not self._want_graph:
+            self._device_step()
+            return
+        if self.graph is None:
+            # warm up on a side stream (library init, NCCL channels), restoring the state afterwards
+            st = self.state
+            keep = [t.clone() for t in (st.theta32, st.theta64, st.m32, st.v32, st.m64, st.v64, st.count)]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._device_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for t, k in zip((st.theta32, st.theta64, st.m32, st.v32, st.m64, st.v64, st.count), keep):
+                t.copy_(k)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._device_step()
+            for t, k in zip((st.theta32, st.theta64, st.m32, st.v32, st.m64, st.v64, st.count), keep):
+                t.copy_(k)   # capture does not execute, but keep the contract explicit
+        self.graph.replay()
+
+
+def make_step_fns(loss_fn: LossCollection, Metrics=None, model=None, is_ensemble: bool = False, graph: bool = False):
+    """(train_step, val_step) with the reference's calling convention (trainer.py:346-372):
+    train_step((state, batch_metrics), (inputs, labels)) -> ((state, batch_metrics), loss)."""
+    if is_ensemble:
+        raise NotImplementedError("full-ensemble training (vmap over train states) is outside the GMNN hot path")
+    steps = {}
+
+    def _get(state, inputs):
+        pos, idx = np.asarray(inputs["positions"]), np.asarray(inputs["idx"])
+        key = (id(state), pos.shape[0], pos.shape[1], idx.shape[2])
+        if key not in steps:
+            steps[key] = TrainStep(state, loss_fn, pos.shape[0], pos.shape[1], idx.shape[2], graph=graph)
+        return steps[key]
+
+    def train_step(carry, batch):
+        state, batch_metrics = carry
+        inputs, labels = batch
+        loss, _pred = _get(state, inputs)(inputs, labels)
+        return (state, batch_metrics), loss
+
+    def val_step(state, batch, batch_metrics=None):
+        raise NotImplementedError("validation = model.apply on the batch: use apax_b200.md.ase_calc / runtime.energy_forces_batched")
+
+    return train_step, val_step

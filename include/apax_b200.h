@@ -212,6 +212,61 @@ int apax_md_nvt_post_force(apax_stream_t stream, const apax_md_nvt_config* cfg, 
                            const double* mass, int64_t n_atoms, void* state);
 
 /* ------------------------------------------------------------------------------------------------
+ * Training step (BASELINE configs[1]).  Replaces, for the GMNN model with an energy + forces MSE loss,
+ *   calc_loss + jax.value_and_grad w.r.t. params   apax/train/trainer.py:253-263, 332-336
+ *   the vmapped model                              apax/train/run.py:204
+ *   Loss.__call__ ("mse", atoms_exponent)           apax/train/loss.py:12-23, 199-244
+ *   get_opt: clip -> adam(linear schedule) -> zero_nans per parameter group, lr <= 1e-7 freezes a group
+ *                                                   apax/optimizer/get_optimizer.py:62-176
+ * The gradient of the force loss (second order: F = -dE/dR differentiated w.r.t. the weights) is hand-derived
+ * (forward-mode sweep along dL/dF, then one reverse sweep); no floating-point atomics, bitwise reproducible.
+ *
+ * All state is CALLER-owned device memory, so that a host can all-reduce the gradient blocks between the two
+ * calls (data parallelism over structures, apax/train/trainer.py:101-106) and capture the step in a CUDA graph:
+ *   theta32 / grad32 / m32 / v32 : f32 blocks of offsets32[7] elements laid out as apax_train_param_layout says
+ *                                  (atomic_type_embedding [S][S][5][7], dense_0 w [360][256], b, dense_1 w, b, dense_2 w, b)
+ *   theta64 / grad64 / m64 / v64 : f64 [2 S] = scale_per_element, shift_per_element
+ * Batch layout = apax_gm_energy_forces_batched: atoms of all structures concatenated, Cartesian positions,
+ * idx i32 [2][n_pairs] with GLOBAL atom indices, offsets f64 [n_pairs][3] or NULL; struct_ptr / pair_ptr i32
+ * [n_structs+1] give each structure's atom and COO-entry ranges; n_real i32 [n_structs] is inputs["n_atoms"]
+ * (the divisor of loss.py:233; padding atoms have Z = 0).  Entries with idx[0]==idx[1] are padding.
+ *   loss f64 [1], energy f64 [n_structs], forces f64 [n_atoms][3] : outputs (the step's predictions)
+ *   batch_divisor : batch size of the mean at loss.py:241 -- the GLOBAL batch under data parallelism, so that the
+ *                   per-rank loss and gradients simply add up
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct apax_train_plan apax_train_plan;
+typedef struct {
+  double energy_weight, energy_atoms_exponent; /* Loss(name="energy"): weight, atoms_exponent (train_config.py:296-299) */
+  double forces_weight, forces_atoms_exponent; /* Loss(name="forces") */
+} apax_train_loss_config;
+typedef struct {
+  double emb_lr, nn_lr, scale_lr, shift_lr; /* get_opt arguments (get_optimizer.py:90-97) */
+  double gradient_clipping;                 /* optax.clip, element-wise */
+  double end_value;                         /* LinearLR.end_value (lr_config.py:26) */
+  int64_t transition_steps;                 /* n_epochs * steps_per_epoch (get_optimizer.py:54-56) */
+  int64_t transition_begin;                 /* LinearLR.transition_begin */
+  double b1, b2, eps;                       /* optax.adam defaults 0.9, 0.999, 1e-8 */
+} apax_train_opt_config;
+int apax_train_plan_create(const apax_gm_config* cfg, apax_train_plan** out);
+void apax_train_plan_destroy(apax_train_plan* plan);
+/* offsets32[0..6] = element offsets of emb, w0, b0, w1, b1, w2, b2; offsets32[7] = block length.
+ * offsets64[0..1] = scale, shift; offsets64[2] = block length. */
+int apax_train_param_layout(const apax_train_plan* plan, int64_t* offsets32, int64_t* offsets64);
+size_t apax_train_workspace_bytes(const apax_train_plan* plan, int64_t n_atoms, int64_t n_pairs, int64_t n_structs);
+int apax_train_loss_and_grad(apax_stream_t stream, const apax_train_plan* plan, const float* theta32,
+                             const double* theta64, const double* R, const int32_t* Z, const int32_t* idx,
+                             const double* offsets, const int32_t* struct_ptr, const int32_t* pair_ptr,
+                             const int32_t* n_real, int64_t n_structs, int64_t n_atoms, int64_t n_pairs,
+                             const double* E_label, const double* F_label, const apax_train_loss_config* loss_cfg,
+                             double batch_divisor, double* loss, double* energy, double* forces, float* grad32,
+                             double* grad64, void* workspace, size_t workspace_bytes);
+/* One optimizer update, in place.  count_device i64 [1] is the optimizer's step counter (optax `count`), read for the
+ * schedule / bias correction and incremented on the device. */
+int apax_train_adam_step(apax_stream_t stream, const apax_train_plan* plan, const apax_train_opt_config* opt_cfg,
+                         float* theta32, double* theta64, const float* grad32, const double* grad64, float* m32,
+                         float* v32, double* m64, double* v64, int64_t* count_device);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-buffer convenience context: what ASECalculator.calculate does per call
  * (apax/md/ase_calc.py:357-393): positions/cell on the HOST in, neighbour list (min-image when
  * min cell height / 2 > r_max, image list otherwise, :501-522), E+F, results on the HOST out.

@@ -294,12 +294,17 @@ def vmap(fn, in_axes=0, out_axes=0):
     return torch.vmap(fn, in_dims=in_axes, out_dims=out_axes)
 
 
+HIGHER_ORDER = False
+
+
 def value_and_grad(fn, has_aux=False):
     def wrapped(x, *args, **kwargs):
         x = _t(x).detach().clone().requires_grad_(True)
         out = fn(x, *args, **kwargs)
         val = out[0] if has_aux else out
-        (g,) = torch.autograd.grad(val, x)
+        # HIGHER_ORDER: keep the graph of the gradient itself (the training step differentiates the
+        # forces w.r.t. the weights, apax/train/trainer.py:332)
+        (g,) = torch.autograd.grad(val, x, create_graph=HIGHER_ORDER)
         return out, g
 
     return wrapped
@@ -461,7 +466,7 @@ def install(reference_root="/root/reference"):
 
     # ---- apax package stubs with real __path__ (submodules import from the reference tree)
     for pkg in ("apax", "apax.layers", "apax.layers.descriptor", "apax.utils", "apax.utils.jax_md_reduced",
-                "apax.nn", "apax.md"):
+                "apax.nn", "apax.md", "apax.train"):
         m = types.ModuleType(pkg)
         m.__path__ = [reference_root + "/" + pkg.replace(".", "/")]
         mods[pkg] = m

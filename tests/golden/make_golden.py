@@ -218,6 +218,64 @@ def case_md_nvt(n=24, seed=2):
              KE0=float(KE), **snaps)
 
 
+def case_train_step(n_struct=3, seed=21):
+    """Loss and parameter gradients of one training batch, from the reference's own `Loss` / `LossCollection`
+    (apax/train/loss.py:199-259) applied to the reference's own EnergyDerivativeModel (apax/nn/models.py:137-171)
+    the way calc_loss does (apax/train/trainer.py:253-263).  The jax.vmap over structures (apax/train/run.py:204) is
+    written as a loop; jax.value_and_grad w.r.t. the parameters (trainer.py:332) is torch.autograd.grad over a graph
+    that contains the inner value_and_grad (shim HIGHER_ORDER)."""
+    from apax.train.loss import Loss, LossCollection
+
+    from oracle import train_oracle as tor
+
+    inputs, labels = tor.ethanol_training_batch(n_struct, seed=seed, pad_atoms=1, pad_pairs=2)
+    params = syn.gmnn_params(seed=31, random_bias=True, random_scale_shift=True)
+    em = params["params"]["energy_model"]
+    tparams = to_t(params)
+    leaves = []
+
+    def mark(tree):
+        for k, v in tree.items():
+            if isinstance(v, dict):
+                mark(v)
+            else:
+                tree[k] = v.clone().requires_grad_(True)
+                leaves.append((k, tree[k]))
+
+    mark(tparams)
+    m = build_model(np.zeros(3), scale=em["scale_shift"]["scale_per_element"], shift=em["scale_shift"]["shift_per_element"])
+    jax_shim.HIGHER_ORDER = True
+    try:
+        E, F = [], []
+        for s in range(n_struct):
+            res = m.apply(tparams, torch.as_tensor(inputs["positions"][s]), torch.as_tensor(inputs["numbers"][s].astype(np.int64)),
+                          torch.as_tensor(inputs["idx"][s].astype(np.int64)), torch.as_tensor(inputs["box"][s]),
+                          torch.as_tensor(inputs["offsets"][s]))
+            E.append(res["energy"])
+            F.append(res["forces"])
+        predictions = {"energy": torch.stack(E), "forces": torch.stack(F)}
+        loss_fn = LossCollection([Loss(name="energy", loss_type="mse", weight=1.0, atoms_exponent=1),
+                                  Loss(name="forces", loss_type="mse", weight=4.0, atoms_exponent=1)])
+        tin = {"n_atoms": torch.as_tensor(inputs["n_atoms"].astype(np.float64))}
+        tlab = {"energy": torch.as_tensor(labels["energy"]), "forces": torch.as_tensor(labels["forces"])}
+        loss = loss_fn(tin, predictions, tlab)
+        grads = torch.autograd.grad(loss, [t for _, t in leaves], allow_unused=True)
+    finally:
+        jax_shim.HIGHER_ORDER = False
+    names = {"atomic_type_embedding": "emb", "scale_per_element": "scale", "shift_per_element": "shift"}
+    out = {}
+    li = {"w": 0, "b": 0}
+    for (k, t), g in zip(leaves, grads):
+        if k in ("w", "b"):
+            name = f"{k}{li[k]}"
+            li[k] += 1
+        else:
+            name = names[k]
+        out["grad_" + name] = np.zeros(tuple(t.shape)) if g is None else g.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "train_step.npz"), n_struct=n_struct, seed=seed, param_seed=31, loss=float(loss.detach()),
+             energy=predictions["energy"].detach().numpy(), forces=predictions["forces"].detach().numpy(), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     case_descriptor_unit()
@@ -232,3 +290,5 @@ if __name__ == "__main__":
     print("ensemble ok")
     case_md_nvt()
     print("md_nvt ok")
+    case_train_step()
+    print("train_step ok")
