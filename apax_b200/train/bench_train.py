@@ -1,0 +1,136 @@
+"""bench.py --workload train: BASELINE configs[1], the GMNN training step (energy + force loss) on synthetic
+ethanol-shaped 9-atom molecules, batch 32 per GPU, data-parallel over structures with a gradient all-reduce.
+Weak scaling (per-GPU batch fixed).  A "step" is one optimizer update on one batch; the unit stays atom-steps/s
+(atoms in the global batch x steps / s) so that the line is comparable with the E+F workload's metric."""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+
+def _batch(rank: int, batch: int):
+    from . import _synthetic_train as st
+
+    return st.ethanol_training_batch(batch, seed=100 + rank)
+
+
+def run(args, world: int, rank: int, local: int, ClockSampler, metric: str, unit: str, cpu_baseline_fn=None) -> int:
+    import torch
+    import torch.distributed as dist
+
+    from .. import runtime as rt
+    from .. import synthetic as syn
+    from ..optimizer.get_optimizer import get_opt
+    from .loss import Loss, LossCollection
+    from .trainer import TrainState, TrainStep, flatten_batch
+
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = rt.lib()
+    B = args.train_batch
+    inputs, labels = _batch(rank, B)
+    n_atoms = int(np.sum(inputs["n_atoms"]))
+    params = syn.gmnn_params(seed=1234)
+    loss_fn = LossCollection([Loss("energy", "mse", 1.0, 1.0), Loss("forces", "mse", 4.0, 1.0)])
+    tx = get_opt(params, n_epochs=100, steps_per_epoch=1000, emb_lr=0.001, nn_lr=0.001, scale_lr=0.0001, shift_lr=0.003)
+    state = TrainState(params, tx)
+    nmax, pmax = inputs["positions"].shape[1], inputs["idx"].shape[2]
+    step = TrainStep(state, loss_fn, B, nmax, pmax, graph=not args.no_graph)
+    step.batch.upload(flatten_batch(inputs, labels))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step.run_resident()
+    barrier()
+    launches_before = lib.apax_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step.run_resident()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    time.sleep(0.15)
+    clocks = sampler.stop(window_s=ms_total * 1e-3 + 0.15)
+    loss_now = float(step.batch.loss.item())
+    assert np.isfinite(loss_now)
+
+    # launches per step: count them on one un-graphed step (a graph replay re-issues the same kernels)
+    eager = TrainStep(state, loss_fn, B, nmax, pmax, graph=False)
+    eager.batch.upload(flatten_batch(inputs, labels))
+    torch.cuda.synchronize()
+    c0 = lib.apax_kernel_launch_count()
+    eager.run_resident()
+    torch.cuda.synchronize()
+    per_step_launches = int(lib.apax_kernel_launch_count() - c0)
+    records = rt.profile_kernels(lambda: eager.run_resident())
+    kernel_ms = {}
+    for name, ms in records:
+        kernel_ms[name] = kernel_ms.get(name, 0.0) + ms
+
+    # end to end: host batch in (pinned staging, H2D inside), loss read back every step
+    k_e2e = max(3, min(args.steps, 200))
+    for _ in range(3):
+        l, _ = step(inputs, labels)
+        float(l.item())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        l, _ = step(inputs, labels)
+        float(l.item())
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": world * n_atoms * k_e2e / dt, "unit": unit, "h2d_bytes_per_step": int(step.batch.h2d_bytes),
+           "d2h_bytes_per_step": 8, "ms_per_step": dt / k_e2e * 1e3, "steps": k_e2e,
+           "includes": "flattening the padded host batch, pinned-host -> device copies, loss+gradients, gradient all-reduce, "
+                       "Adam, device -> host read of the loss"}
+
+    if rank == 0:
+        ms_per_step = ms_total / args.steps
+        flops = 2.0 * (360 * 256 + 256 * 256) * 10 * n_atoms      # 2 fwd + 2 tangent + 4 bwd + 2 weight-grad (x2 rows) GEMM sweeps
+        dominant = max(kernel_ms, key=kernel_ms.get)
+        line = {
+            "metric": metric, "value": world * n_atoms * args.steps / (ms_total * 1e-3), "unit": unit, "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: GMNN training step (energy + force MSE loss, Adam), synthetic ethanol-shaped "
+                                   "9-atom molecules, batch 32 per GPU, data-parallel gradient all-reduce",
+                       "batch_per_gpu": B, "atoms_per_gpu": n_atoms, "pairs_per_gpu": int(B * pmax),
+                       "structures_per_s": world * B * args.steps / (ms_total * 1e-3),
+                       "cuda_graph": not args.no_graph, "parallelism": f"dp{world}", "loss": loss_now,
+                       "l2": "the step's working set (2.6 MB of parameters, < 10 MB of activations) is L2-resident by nature; "
+                             "no flush between steps"},
+            "clocks": clocks, "gpu_launches": per_step_launches * args.steps,
+            "roofline": {"bound": "latency", "note": "about 35 dependent launches on a few hundred atoms: the step is bound by launch/"
+                         "dependency latency, not by HBM or the tensor pipe; GEMM flops per step below for scale",
+                         "gemm_gflop_per_step": flops / 1e9, "kernel": dominant,
+                         "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(kernel_ms.items(), key=lambda kv: -kv[1])},
+                         "kernel_ms_total_eager": round(sum(kernel_ms.values()), 4), "launches_per_step": per_step_launches},
+            "e2e": e2e,
+        }
+        if not args.no_cpu_baseline and cpu_baseline_fn is not None:
+            line["cpu_baseline"] = cpu_baseline_fn(B, unit)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0

@@ -148,6 +148,24 @@ def flatten_batch(inputs: dict, labels: Optional[dict] = None) -> dict:
     return out
 
 
+def shard_batch(inputs: dict, labels: dict, rank: int, world: int):
+    """This rank's contiguous block of the batch axis -- what sharding the batch over the ("data",) device mesh does
+    in the reference (apax/train/trainer.py:101-106, apax/data/input_pipeline.py:296-300).  The batch size must be
+    divisible by the number of ranks, as there."""
+    B = np.asarray(inputs["positions"]).shape[0]
+    if B % world:
+        raise ValueError(f"batch size {B} is not divisible by {world} ranks")
+    sl = slice(rank * (B // world), (rank + 1) * (B // world))
+    return {k: np.asarray(v)[sl] for k, v in inputs.items()}, {k: np.asarray(v)[sl] for k, v in labels.items()}
+
+
+def allreduce_sum_(dist, tensors) -> None:
+    """Sum the per-rank loss / gradient blocks in place.  With batch_divisor = global batch size every rank's gradient
+    is its share of the gradient of the global-batch mean loss, so a plain sum (no division) is the reference's result."""
+    for t in tensors:
+        dist.all_reduce(t)
+
+
 _KEYS = (("R", torch.float64), ("Z", torch.int32), ("idx", torch.int32), ("offsets", torch.float64),
          ("struct_ptr", torch.int32), ("pair_ptr", torch.int32), ("n_real", torch.int32), ("E_label", torch.float64),
          ("F_label", torch.float64))
@@ -209,9 +227,7 @@ class TrainStep:
             _ptr(st.grad32), _ptr(st.grad64), C.c_void_p(Workspace.aligned_ptr(self.buf)), C.c_size_t(self.nbytes)),
             "apax_train_loss_and_grad")
         if self.dist:   # gradients of the global-batch mean loss: per-rank parts add up (batch_divisor is global)
-            self.dist.all_reduce(st.grad32)
-            self.dist.all_reduce(st.grad64)
-            self.dist.all_reduce(b.loss)
+            allreduce_sum_(self.dist, (st.grad32, st.grad64, b.loss))
         st.apply_gradients()
 
     def __call__(self, inputs: dict, labels: dict):

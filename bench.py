@@ -45,6 +45,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="multi-GPU: strong = the same box split into slabs (BASELINE configs[3]); weak = box grows with N")
+    ap.add_argument("--workload", default="ef", choices=["ef", "train"],
+                    help="ef = BASELINE configs[3] energy+forces (default, the headline); train = configs[1] training step")
+    ap.add_argument("--train-batch", type=int, default=32, help="--workload train: structures per GPU")
+    ap.add_argument("--no-graph", action="store_true", help="--workload train: launch kernels eagerly instead of a CUDA graph")
     ap.add_argument("--verify", action="store_true", help="multi-GPU: compare against a single-GPU evaluation of the whole box")
     return ap.parse_args()
 
@@ -153,6 +157,29 @@ def cpu_baseline(params, n_mol: int, steps: int = 1):
                       f"torch-CPU oracle, {dt:.2f} s each"}
 
 
+def train_cpu_baseline(B: int, unit: str, steps: int = 2):
+    """The restated reference training step (oracle, torch-CPU double backward + Adam) on the same batch shape."""
+    import torch
+
+    from oracle import train_oracle as tor
+
+    from apax_b200 import synthetic as syn
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inputs, labels = tor.ethanol_training_batch(B, seed=100)
+    params = syn.gmnn_params(seed=1234)
+    state = tor.AdamState()
+    _, _, params, state = tor.train_step(params, state, inputs, labels)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, _, params, state = tor.train_step(params, state, inputs, labels)
+    dt = (time.perf_counter() - t0) / steps
+    n = int(np.sum(inputs["n_atoms"]))
+    return {"value": n / dt, "unit": unit, "cores": cores, "kind": "port",
+            "sample": f"{steps} training steps of the torch-CPU oracle on the same batch shape ({B} x 9 atoms), {dt:.2f} s each"}
+
+
 def init_dist(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -164,6 +191,16 @@ def init_dist(args):
 def run_reference(args):
     world, rank, local = init_dist(args)
     if rank != 0:
+        return 0
+    if args.workload == "train":
+        steps = max(1, min(args.steps, 5))
+        cb = train_cpu_baseline(args.train_batch, UNIT, steps=steps)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": steps, "warmup": 1, "ms_per_step": args.train_batch * 9 / cb["value"] * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "BASELINE configs[1]: GMNN training step, ethanol batch", "batch": args.train_batch},
+                          "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                                                      "d2h_bytes_per_step": 0}}), flush=True)
         return 0
     from apax_b200 import synthetic as syn
 
@@ -208,6 +245,10 @@ def run_ours(args):
     import torch
 
     world, rank, local = init_dist(args)
+    if args.workload == "train":
+        from apax_b200.train import bench_train
+
+        return bench_train.run(args, world, rank, local, ClockSampler, METRIC, UNIT, cpu_baseline_fn=train_cpu_baseline)
     if world > 1:
         from apax_b200.md import domain
 
