@@ -171,7 +171,7 @@ struct TrWs {
   float4* geo;                    // [P] (dx,dy,dz, species-pair key as int bits); w < 0: dropped entry
   float4* Q;                      // [P] per-pair force contribution
   float* cbar;                    // [P][35] per-pair embedding-gradient contributions
-  int32_t* present;               // [128] species present
+  int32_t* present;               // [128] species present, [128] ticket of the loss reduction
   float *M, *Md, *Mdb, *Mb2;      // [n][100]
   float *GS, *GB;                 // [2n][360]
   float *Y1, *H1, *Y2, *H2, *YB2, *HB1, *YB1;   // [2n][256]
@@ -191,7 +191,7 @@ size_t carve_tr(void* base, int64_t n, int64_t P, int64_t B, TrWs* w) {
   t.rowp = c.take<int32_t>(P); t.trowp = c.take<int32_t>(P);
   t.geo = c.take<float4>(P); t.Q = c.take<float4>(P);
   t.cbar = c.take<float>(P * 35);
-  t.present = c.take<int32_t>(128);
+  t.present = c.take<int32_t>(132);
   t.M = c.take<float>(n * NPK); t.Md = c.take<float>(n * NPK); t.Mdb = c.take<float>(n * NPK); t.Mb2 = c.take<float>(n * NPK);
   t.GS = c.take<float>(2 * n * NF); t.GB = c.take<float>(2 * n * NF);
   t.Y1 = c.take<float>(2 * n * NH); t.H1 = c.take<float>(2 * n * NH); t.Y2 = c.take<float>(2 * n * NH);
@@ -209,17 +209,42 @@ size_t carve_tr(void* base, int64_t n, int64_t P, int64_t B, TrWs* w) {
 // row (central == a) and transpose row (neighbour == a) in COO order, so all later sums have a fixed order.
 // Dropped: entries with idx[0]==idx[1] (the (0,0) padding, apax/layers/masking.py:10-16) or an index outside the structure.
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int GR_STAGE = 3072;   // COO entries of a structure staged in shared memory (24 KB); longer lists are read in place
 __global__ void __launch_bounds__(128) k_tr_group(const int32_t* __restrict__ idx, int64_t P, const int32_t* __restrict__ struct_ptr,
-                                                  const int32_t* __restrict__ pair_ptr, TrWs w) {
+                                                  const int32_t* __restrict__ pair_ptr, const int32_t* __restrict__ Z,
+                                                  const double* __restrict__ R, const double* __restrict__ offsets, int S,
+                                                  int32_t* __restrict__ atom_struct, TrWs w) {
+  __shared__ int32_t s_i0[GR_STAGE], s_i1[GR_STAGE];
   const int s = blockIdx.x;
   const int a0 = struct_ptr[s], a1 = struct_ptr[s + 1];
-  const int p0 = pair_ptr[s], p1 = pair_ptr[s + 1];
-  const int32_t* i0 = idx;        // neighbour
-  const int32_t* i1 = idx + P;    // central
+  const int p0 = pair_ptr[s], p1 = pair_ptr[s + 1], np = p1 - p0;
+  const bool staged = np <= GR_STAGE;
+  // per COO entry: fp64 displacement R[i1] - R[i0] (+ offsets) cast to fp32 (apax/layers/distances.py:48-67,
+  // gaussian_moment_descriptor.py:33) and the embedding block of the pair: central species first (basis_functions.py:139-141)
+  for (int q = threadIdx.x; q < np; q += blockDim.x) {
+    const int p = p0 + q;
+    const int j = idx[p], c = idx[P + p];
+    if (staged) { s_i0[q] = j; s_i1[q] = c; }
+    float4 g = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    if (j != c && j >= a0 && j < a1 && c >= a0 && c < a1) {
+      double d0 = R[3 * int64_t(c) + 0] - R[3 * int64_t(j) + 0];
+      double d1 = R[3 * int64_t(c) + 1] - R[3 * int64_t(j) + 1];
+      double d2 = R[3 * int64_t(c) + 2] - R[3 * int64_t(j) + 2];
+      if (offsets) { d0 += offsets[3 * int64_t(p) + 0]; d1 += offsets[3 * int64_t(p) + 1]; d2 += offsets[3 * int64_t(p) + 2]; }
+      g = make_float4(float(d0), float(d1), float(d2), __int_as_float(Z[c] * S + Z[j]));
+    }
+    w.geo[p] = g;
+  }
+  __syncthreads();
+  const int32_t* i0 = staged ? s_i0 : idx + p0;        // neighbour
+  const int32_t* i1 = staged ? s_i1 : idx + P + p0;    // central
   for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+    atom_struct[a] = s;
+    w.present[Z[a] & 127] = 1;    // benign race: every writer stores 1
     int nc = 0, nt = 0;
-    for (int p = p0; p < p1; ++p) {
-      const int j = i0[p], c = i1[p];
+#pragma unroll 4
+    for (int q = 0; q < np; ++q) {
+      const int j = i0[q], c = i1[q];
       const bool ok = j != c && j >= a0 && j < a1 && c >= a0 && c < a1;
       nc += ok && c == a;
       nt += ok && j == a;
@@ -239,38 +264,13 @@ __global__ void __launch_bounds__(128) k_tr_group(const int32_t* __restrict__ id
   __syncthreads();
   for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
     int rc = w.rs[a], tc = w.ts[a];
-    for (int p = p0; p < p1; ++p) {
-      const int j = i0[p], c = i1[p];
+    for (int q = 0; q < np; ++q) {
+      const int j = i0[q], c = i1[q];
       const bool ok = j != c && j >= a0 && j < a1 && c >= a0 && c < a1;
-      if (ok && c == a) w.rowp[rc++] = p;
-      if (ok && j == a) w.trowp[tc++] = p;
+      if (ok && c == a) w.rowp[rc++] = p0 + q;
+      if (ok && j == a) w.trowp[tc++] = p0 + q;
     }
   }
-}
-
-// per COO entry: fp64 displacement R[i1] - R[i0] (+ offsets) cast to fp32 (apax/layers/distances.py:48-67,
-// gaussian_moment_descriptor.py:33) and the embedding block of the pair: central species first (basis_functions.py:139-141)
-__global__ void __launch_bounds__(256) k_tr_geom(const double* __restrict__ R, const int32_t* __restrict__ Z,
-                                                 const int32_t* __restrict__ idx, const double* __restrict__ offsets, int S,
-                                                 const int32_t* __restrict__ atom_struct, const int32_t* __restrict__ pair_ptr,
-                                                 TrWs w) {
-  const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= w.P) return;
-  const int j = idx[p], c = idx[w.P + p];
-  float4 g = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-  bool ok = j != c && j >= 0 && c >= 0 && j < w.n && c < w.n;
-  if (ok) {   // same rule as k_tr_group: both atoms in the structure whose COO range holds p
-    const int s = atom_struct[c];
-    ok = atom_struct[j] == s && p >= pair_ptr[s] && p < pair_ptr[s + 1];
-  }
-  if (ok) {
-    double d0 = R[3 * int64_t(c) + 0] - R[3 * int64_t(j) + 0];
-    double d1 = R[3 * int64_t(c) + 1] - R[3 * int64_t(j) + 1];
-    double d2 = R[3 * int64_t(c) + 2] - R[3 * int64_t(j) + 2];
-    if (offsets) { d0 += offsets[3 * p + 0]; d1 += offsets[3 * p + 1]; d2 += offsets[3 * p + 2]; }
-    g = make_float4(float(d0), float(d1), float(d2), __int_as_float(Z[c] * S + Z[j]));
-  }
-  w.geo[p] = g;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -415,57 +415,87 @@ __global__ void __launch_bounds__(128) k_tr_moments(TrWs w, const float* __restr
 //   fwd      g[f]  = sum_t coef M_a M_b M_c
 //   tangent  gd[f] = sum_t coef (Md_a M_b M_c + M_a Md_b M_c + M_a M_b Md_c)
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int CT_ATOMS = 2;   // atoms per block: the term tables (80 KB / 240 KB) are walked once for both
 template <int TANGENT>
 __global__ void __launch_bounds__(384) k_tr_contract(Tables tab, const float* __restrict__ M, const float* __restrict__ Md,
-                                                     float* __restrict__ out) {
-  __shared__ float m[NPK + 1], md[NPK + 1];
-  const int a = blockIdx.x, t = threadIdx.x;
-  if (t < NPK) {
-    m[t] = M[int64_t(a) * NPK + t];
-    md[t] = TANGENT ? Md[int64_t(a) * NPK + t] : 0.f;
+                                                     float* __restrict__ out, int64_t n) {
+  __shared__ float m[CT_ATOMS][NPK + 1], md[CT_ATOMS][NPK + 1];
+  const int64_t a0 = int64_t(blockIdx.x) * CT_ATOMS;
+  const int t = threadIdx.x;
+  for (int e = t; e < CT_ATOMS * (NPK + 1); e += blockDim.x) {
+    const int u = e / (NPK + 1), i = e % (NPK + 1);
+    const bool ok = a0 + u < n && i < NPK;
+    m[u][i] = i == NPK ? 1.f : (ok ? M[(a0 + u) * NPK + i] : 0.f);
+    md[u][i] = (TANGENT && ok) ? Md[(a0 + u) * NPK + i] : 0.f;
   }
-  if (t == NPK) { m[NPK] = 1.f; md[NPK] = 0.f; }
   __syncthreads();
   if (t >= NF) return;
-  float acc = 0.f;
-  for (int q = tab.f_ptr[t]; q < tab.f_ptr[t + 1]; ++q) {
-    const uchar4 s = tab.f_slots[q];
+  float acc[CT_ATOMS];
+#pragma unroll
+  for (int u = 0; u < CT_ATOMS; ++u) acc[u] = 0.f;
+  const int q1 = tab.f_ptr[t + 1];
+#pragma unroll 4
+  for (int q = tab.f_ptr[t]; q < q1; ++q) {
+    const uchar4 sl = tab.f_slots[q];
     const float c = tab.f_coef[q];
-    if (TANGENT) acc += c * (md[s.x] * m[s.y] * m[s.z] + m[s.x] * (md[s.y] * m[s.z] + m[s.y] * md[s.z]));
-    else acc += c * (m[s.x] * m[s.y] * m[s.z]);
+#pragma unroll
+    for (int u = 0; u < CT_ATOMS; ++u) {
+      if (TANGENT) acc[u] += c * (md[u][sl.x] * m[u][sl.y] * m[u][sl.z] + m[u][sl.x] * (md[u][sl.y] * m[u][sl.z] + m[u][sl.y] * md[u][sl.z]));
+      else acc[u] += c * (m[u][sl.x] * m[u][sl.y] * m[u][sl.z]);
+    }
   }
-  out[int64_t(a) * NF + t] = acc;
+#pragma unroll
+  for (int u = 0; u < CT_ATOMS; ++u)
+    if (a0 + u < n) out[(a0 + u) * NF + t] = acc[u];
 }
 
 // reverse:  out[i] = sum_occ coef * ( gb1[f] * M[o1] M[o2]  +  gb2[f] * (Md[o1] M[o2] + M[o1] Md[o2]) )
 // gb2 == nullptr: plain transpose-Jacobian product J(M)^T gb1.  With gb2 = adjoint of the tangent features this adds the
 // second-order term d/d(eps) J(M + eps Md)^T gb2.
-__global__ void __launch_bounds__(128) k_tr_contract_bwd(Tables tab, const float* __restrict__ M, const float* __restrict__ Md,
-                                                         const float* __restrict__ gb1, const float* __restrict__ gb2,
-                                                         float* __restrict__ out) {
-  __shared__ float m[NPK + 1], md[NPK + 1], g1[NF], g2[NF];
-  const int a = blockIdx.x, t = threadIdx.x;
-  for (int i = t; i < NF; i += blockDim.x) {
-    g1[i] = gb1[int64_t(a) * NF + i];
-    g2[i] = gb2 ? gb2[int64_t(a) * NF + i] : 0.f;
-  }
-  if (t < NPK) {
-    m[t] = M[int64_t(a) * NPK + t];
-    md[t] = gb2 ? Md[int64_t(a) * NPK + t] : 0.f;
-  }
-  if (t == NPK) { m[NPK] = 1.f; md[NPK] = 0.f; }
-  __syncthreads();
-  if (t >= NPK) return;
-  float acc = 0.f;
+constexpr int CB_LANES = 8;   // lanes that share one moment slot's occurrence list
+__global__ void __launch_bounds__(NPK * CB_LANES) k_tr_contract_bwd(Tables tab, const float* __restrict__ M, const float* __restrict__ Md,
+                                                                   const float* __restrict__ gb1, const float* __restrict__ gb2,
+                                                                   float* __restrict__ out, int64_t n) {
+  __shared__ float m[CT_ATOMS][NPK + 1], md[CT_ATOMS][NPK + 1], g1[CT_ATOMS][NF], g2[CT_ATOMS][NF];
+  const int64_t a0 = int64_t(blockIdx.x) * CT_ATOMS;
+  const int t = threadIdx.x;
   const bool second = gb2 != nullptr;
-  for (int q = tab.o_ptr[t]; q < tab.o_ptr[t + 1]; ++q) {
-    const int pk = tab.o_pack[q];
-    const int f = pk & 0xffff, o1 = (pk >> 16) & 0xff, o2 = (pk >> 24) & 0xff;
-    float v = g1[f] * (m[o1] * m[o2]);
-    if (second) v += g2[f] * (md[o1] * m[o2] + m[o1] * md[o2]);
-    acc += tab.o_coef[q] * v;
+  for (int e = t; e < CT_ATOMS * NF; e += blockDim.x) {
+    const int u = e / NF, i = e % NF;
+    const bool ok = a0 + u < n;
+    g1[u][i] = ok ? gb1[(a0 + u) * NF + i] : 0.f;
+    g2[u][i] = (second && ok) ? gb2[(a0 + u) * NF + i] : 0.f;
   }
-  out[int64_t(a) * NPK + t] = acc;
+  for (int e = t; e < CT_ATOMS * (NPK + 1); e += blockDim.x) {
+    const int u = e / (NPK + 1), i = e % (NPK + 1);
+    const bool ok = a0 + u < n && i < NPK;
+    m[u][i] = i == NPK ? 1.f : (ok ? M[(a0 + u) * NPK + i] : 0.f);
+    md[u][i] = (second && ok) ? Md[(a0 + u) * NPK + i] : 0.f;
+  }
+  __syncthreads();
+  const int slot = t / CB_LANES, sub = t % CB_LANES;   // blockDim = 800 = 25 full warps
+  float acc[CT_ATOMS];
+#pragma unroll
+  for (int u = 0; u < CT_ATOMS; ++u) acc[u] = 0.f;
+  const int q1 = tab.o_ptr[slot + 1];
+#pragma unroll 4
+  for (int q = tab.o_ptr[slot] + sub; q < q1; q += CB_LANES) {
+    const int pk = tab.o_pack[q];
+    const float c = tab.o_coef[q];
+    const int f = pk & 0xffff, o1 = (pk >> 16) & 0xff, o2 = (pk >> 24) & 0xff;
+#pragma unroll
+    for (int u = 0; u < CT_ATOMS; ++u) {
+      float v = g1[u][f] * (m[u][o1] * m[u][o2]);
+      if (second) v += g2[u][f] * (md[u][o1] * m[u][o2] + m[u][o1] * md[u][o2]);
+      acc[u] += c * v;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < CT_ATOMS; ++u) {
+#pragma unroll
+    for (int o = CB_LANES / 2; o; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+    if (sub == 0 && a0 + u < n) out[(a0 + u) * NPK + slot] = acc[u];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -494,57 +524,142 @@ struct GemmT {
   const float* X3;    // EPI_SECOND: tangent pre-activations
 };
 
+// Block tile 32 x 32, k-tile 32, 256 threads = 4 k-groups x 64 threads; a thread owns a 4 x 4 micro-tile and, inside every
+// k-tile, the two 4-wide k-chunks of its group (intra-block split-K: these GEMMs have only ~72-96 output tiles, so the
+// k-loop must be spread over the warps of an SM); the four partial tiles are added in a fixed order through shared
+// memory.  Operands arrive by 16-byte cp.async in a 3-stage ring, in the orientation they have in global memory:
+//   A_KC : A(i,k) contiguous along k (activations [rows][features])  -> As[i][k];  else contiguous along i -> As[k][i]
+//   B_JC : B(k,j) contiguous along j (weights [in][out], adjoints)   -> Bs[k][j];  else contiguous along k -> Bs[j][k]
+// Rows of a micro-tile are interleaved (ty + 8 r) where the operand is read along k, so that the float4 reads of a warp
+// hit distinct banks (row stride 36 floats).
+constexpr int TG_STAGES = 3, TG_LD = 36;
+
+__device__ __forceinline__ void cp_async16_zfill(float* smem, const float* gmem, bool valid) {
+  const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  const int bytes = valid ? 16 : 0;   // src-size 0: the destination is zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
+}
+
+template <bool A_KC, bool B_JC>
 __global__ void __launch_bounds__(256) k_tr_gemm(GemmT g) {
-  __shared__ float As[32][33], Bs[32][33];
-  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  __shared__ __align__(16) float As[TG_STAGES][32][TG_LD], Bs[TG_STAGES][32][TG_LD];
+  __shared__ float red[4][32][33];
+  const int t = threadIdx.x, grp = t >> 6, tt = t & 63, ty = tt >> 3, tx = tt & 7;
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int k0 = 0; k0 < g.K; k0 += 32) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int e = t + 256 * q;
-      int ii, kk;
-      if (g.a_cs == 1) { ii = e >> 5; kk = e & 31; } else { kk = e >> 5; ii = e & 31; }
-      const int gi = i0 + ii, gk = k0 + kk;
-      As[ii][kk] = (gi < g.M && gk < g.K) ? g.A[gi * g.a_rs + gk * g.a_cs] : 0.f;
-      int jj;
-      if (g.b_cs == 1) { kk = e >> 5; jj = e & 31; } else { jj = e >> 5; kk = e & 31; }
-      const int gj = j0 + jj;
-      const int gk2 = k0 + kk;
-      Bs[kk][jj] = (gj < g.N && gk2 < g.K) ? g.B[gk2 * g.b_rs + gj * g.b_cs] : 0.f;
+  // one 16-byte chunk of each operand per thread and k-tile
+  const int c_hi = t >> 3, c_lo = (t & 7) * 4;   // chunk (row c_hi, elements c_lo .. c_lo+3) of a [32][32] tile
+  auto load_tile = [&](int stage, int k0) {
+    if (A_KC) {   // row = i, elements along k
+      const int gi = i0 + c_hi, gk = k0 + c_lo;
+      const bool ok = gi < g.M && gk < g.K;
+      cp_async16_zfill(&As[stage][c_hi][c_lo], ok ? g.A + int64_t(gi) * g.a_rs + gk : g.A, ok);
+    } else {      // row = k, elements along i
+      const int gk = k0 + c_hi, gi = i0 + c_lo;
+      const bool ok = gi < g.M && gk < g.K;
+      cp_async16_zfill(&As[stage][c_hi][c_lo], ok ? g.A + int64_t(gk) * g.a_cs + gi : g.A, ok);
     }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 32; ++kk) {
-      const float a0 = As[2 * ty][kk], a1 = As[2 * ty + 1][kk];
-      const float b0 = Bs[kk][2 * tx], b1 = Bs[kk][2 * tx + 1];
-      acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+    if (B_JC) {   // row = k, elements along j
+      const int gk = k0 + c_hi, gj = j0 + c_lo;
+      const bool ok = gj < g.N && gk < g.K;
+      cp_async16_zfill(&Bs[stage][c_hi][c_lo], ok ? g.B + int64_t(gk) * g.b_rs + gj : g.B, ok);
+    } else {      // row = j, elements along k
+      const int gj = j0 + c_hi, gk = k0 + c_lo;
+      const bool ok = gj < g.N && gk < g.K;
+      cp_async16_zfill(&Bs[stage][c_hi][c_lo], ok ? g.B + int64_t(gj) * g.b_cs + gk : g.B, ok);
     }
-    __syncthreads();
+  };
+  const int nk = (g.K + 31) / 32;
+#pragma unroll
+  for (int st = 0; st < TG_STAGES - 1; ++st) {
+    if (st < nk) load_tile(st, st * 32);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  for (int kt = 0; kt < nk; ++kt) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(TG_STAGES - 2) : "memory");
+    __syncthreads();   // tile kt has landed for every thread, and everyone is done with tile kt-1
+    if (kt + TG_STAGES - 1 < nk) load_tile((kt + TG_STAGES - 1) % TG_STAGES, (kt + TG_STAGES - 1) * 32);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int st = kt % TG_STAGES;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int kk = (grp + 4 * h) * 4;
+      float a[4][4], b[4][4];   // a[r][kq], b[kq][c]
+      if (A_KC) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float4 v = *reinterpret_cast<const float4*>(&As[st][ty + 8 * r][kk]);
+          a[r][0] = v.x; a[r][1] = v.y; a[r][2] = v.z; a[r][3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(&As[st][kk + q][4 * ty]);
+          a[0][q] = v.x; a[1][q] = v.y; a[2][q] = v.z; a[3][q] = v.w;
+        }
+      }
+      if (B_JC) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(&Bs[st][kk + q][4 * tx]);
+          b[q][0] = v.x; b[q][1] = v.y; b[q][2] = v.z; b[q][3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(&Bs[st][tx + 8 * c][kk]);
+          b[0][c] = v.x; b[1][c] = v.y; b[2][c] = v.z; b[3][c] = v.w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] += a[r][q] * b[q][c];
+    }
   }
 #pragma unroll
-  for (int di = 0; di < 2; ++di)
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int dj = 0; dj < 2; ++dj) {
-      const int i = i0 + 2 * ty + di, j = j0 + 2 * tx + dj;
-      if (i >= g.M || j >= g.N) continue;
-      float v = acc[di][dj];
-      if (g.bias) v += g.bias[j];
-      const int64_t o = int64_t(i) * g.ldc + j;
-      g.C[o] = v;
-      switch (g.epi) {
-        case EPI_ACT: g.C2[o] = swish(v); break;
-        case EPI_TAN: g.C2[o] = dswish(g.X1[o]) * v; break;
-        case EPI_MULD: g.C2[o] = dswish(g.X1[o]) * v; break;
-        case EPI_SECOND: g.C2[o] = dswish(g.X1[o]) * v + g.X2[o] * d2swish(g.X1[o]) * g.X3[o]; break;
-        default: break;
-      }
+    for (int c = 0; c < 4; ++c) red[grp][A_KC ? ty + 8 * r : 4 * ty + r][B_JC ? 4 * tx + c : tx + 8 * c] = acc[r][c];
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e = t + 256 * q, il = e >> 5, jl = e & 31;
+    const int i = i0 + il, j = j0 + jl;
+    if (i >= g.M || j >= g.N) continue;
+    float v = (red[0][il][jl] + red[1][il][jl]) + (red[2][il][jl] + red[3][il][jl]);
+    if (g.bias) v += g.bias[j];
+    const int64_t o = int64_t(i) * g.ldc + j;
+    g.C[o] = v;
+    switch (g.epi) {
+      case EPI_ACT: g.C2[o] = swish(v); break;
+      case EPI_TAN: g.C2[o] = dswish(g.X1[o]) * v; break;
+      case EPI_MULD: g.C2[o] = dswish(g.X1[o]) * v; break;
+      case EPI_SECOND: g.C2[o] = dswish(g.X1[o]) * v + g.X2[o] * d2swish(g.X1[o]) * g.X3[o]; break;
+      default: break;
     }
+  }
 }
 
 int gemm(cudaStream_t s, const GemmT& g) {
   dim3 grid((unsigned)cdiv(g.N, 32), (unsigned)cdiv(g.M, 32));
-  APAX_LAUNCH(k_tr_gemm, grid, dim3(256), 0, s, g);
+  const bool a_kc = g.a_cs == 1, b_jc = g.b_cs == 1;
+  // 16-byte chunks: the contiguous extent of each operand must be a multiple of 4 elements
+  if ((a_kc ? g.K : g.M) % 4 || (b_jc ? g.N : g.K) % 4 || (a_kc ? g.a_rs : g.a_cs) % 4 || (b_jc ? g.b_rs : g.b_cs) % 4)
+    return APAX_ERR_INVALID_ARG;
+  void (*const k_tr_gemm_nn)(GemmT) = k_tr_gemm<true, true>;     // activations x weights
+  void (*const k_tr_gemm_nt)(GemmT) = k_tr_gemm<true, false>;    // adjoints x weights^T
+  void (*const k_tr_gemm_tn)(GemmT) = k_tr_gemm<false, true>;    // activations^T x adjoints (weight gradients)
+  if (a_kc && b_jc) { APAX_LAUNCH(k_tr_gemm_nn, grid, dim3(256), 0, s, g); }
+  else if (a_kc && !b_jc) { APAX_LAUNCH(k_tr_gemm_nt, grid, dim3(256), 0, s, g); }
+  else if (!a_kc && b_jc) { APAX_LAUNCH(k_tr_gemm_tn, grid, dim3(256), 0, s, g); }
+  else return APAX_ERR_INVALID_ARG;
   return APAX_OK;
 }
 
@@ -636,27 +751,37 @@ struct LossArgs {
 };
 __global__ void __launch_bounds__(128) k_tr_forces_loss(TrWs w, const int32_t* __restrict__ struct_ptr,
                                                         const int32_t* __restrict__ n_real, const double* __restrict__ E_lab,
-                                                        const double* __restrict__ F_lab, LossArgs la, double* __restrict__ F_out) {
+                                                        const double* __restrict__ F_lab, LossArgs la, double* __restrict__ F_out,
+                                                        double* __restrict__ loss) {
   __shared__ double red[128];
   const int s = blockIdx.x;
   const double na = double(n_real[s]);
   const double cE = la.wE / (pow(na, la.expE) * la.batch_divisor);
   const double cF = la.wF / (pow(na, la.expF) * la.batch_divisor);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double acc = 0.0;
-  for (int a = struct_ptr[s] + threadIdx.x; a < struct_ptr[s + 1]; a += blockDim.x) {
+  // warp per atom: lanes stride the atom's row (+) and transpose row (-), fixed butterfly sum in fp64
+  for (int a = struct_ptr[s] + wid; a < struct_ptr[s + 1]; a += 4) {
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-    for (int q = w.rs[a]; q < w.re[a]; ++q) {
-      const float4 v = w.Q[w.rowp[q]];
-      f0 += double(v.x); f1 += double(v.y); f2 += double(v.z);
+    const int r0 = w.rs[a], nr = w.re[a] - r0, t0 = w.ts[a], nt = w.te[a] - t0;
+    for (int q = lane; q < nr + nt; q += 32) {
+      const bool row = q < nr;
+      const float4 v = w.Q[row ? w.rowp[r0 + q] : w.trowp[t0 + q - nr]];
+      const double sg = row ? 1.0 : -1.0;
+      f0 += sg * double(v.x); f1 += sg * double(v.y); f2 += sg * double(v.z);
     }
-    for (int q = w.ts[a]; q < w.te[a]; ++q) {
-      const float4 v = w.Q[w.trowp[q]];
-      f0 -= double(v.x); f1 -= double(v.y); f2 -= double(v.z);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      f0 += __shfl_xor_sync(0xffffffffu, f0, o);
+      f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+      f2 += __shfl_xor_sync(0xffffffffu, f2, o);
     }
-    F_out[3 * int64_t(a) + 0] = f0; F_out[3 * int64_t(a) + 1] = f1; F_out[3 * int64_t(a) + 2] = f2;
-    const double e0 = f0 - F_lab[3 * int64_t(a) + 0], e1 = f1 - F_lab[3 * int64_t(a) + 1], e2 = f2 - F_lab[3 * int64_t(a) + 2];
-    w.u[3 * int64_t(a) + 0] = 2.0 * cF * e0; w.u[3 * int64_t(a) + 1] = 2.0 * cF * e1; w.u[3 * int64_t(a) + 2] = 2.0 * cF * e2;
-    acc += cF * (e0 * e0 + e1 * e1 + e2 * e2);
+    if (lane == 0) {
+      F_out[3 * int64_t(a) + 0] = f0; F_out[3 * int64_t(a) + 1] = f1; F_out[3 * int64_t(a) + 2] = f2;
+      const double e0 = f0 - F_lab[3 * int64_t(a) + 0], e1 = f1 - F_lab[3 * int64_t(a) + 1], e2 = f2 - F_lab[3 * int64_t(a) + 2];
+      w.u[3 * int64_t(a) + 0] = 2.0 * cF * e0; w.u[3 * int64_t(a) + 1] = 2.0 * cF * e1; w.u[3 * int64_t(a) + 2] = 2.0 * cF * e2;
+      acc += cF * (e0 * e0 + e1 * e1 + e2 * e2);
+    }
   }
   red[threadIdx.x] = acc;
   __syncthreads();
@@ -669,14 +794,15 @@ __global__ void __launch_bounds__(128) k_tr_forces_loss(TrWs w, const int32_t* _
     w.alpha[s] = 2.0 * cE * dE;
     w.cF[s] = cF;
     w.loss_s[s] = red[0] + cE * dE * dE;
-  }
-}
-
-__global__ void __launch_bounds__(32) k_tr_loss_sum(TrWs w, double* __restrict__ loss) {
-  if (threadIdx.x == 0) {
-    double acc = 0.0;
-    for (int64_t s = 0; s < w.B; ++s) acc += w.loss_s[s];
-    loss[0] = acc;
+    // the last block to get here adds the per-structure losses up in index order (deterministic)
+    __threadfence();
+    if (atomicAdd(w.present + 128, 1) == int(gridDim.x) - 1) {
+      __threadfence();
+      const volatile double* ls = w.loss_s;
+      double acc = 0.0;
+      for (int64_t q = 0; q < w.B; ++q) acc += ls[q];
+      loss[0] = acc;
+    }
   }
 }
 
@@ -704,33 +830,49 @@ __global__ void __launch_bounds__(256) k_tr_head2(TrWs w, const float* __restric
   if (lane == 0) w.e_atom[w.n + a] = acc;
 }
 
-__global__ void __launch_bounds__(256) k_tr_atom_struct(const int32_t* __restrict__ struct_ptr, int64_t B, int32_t* __restrict__ atom_struct) {
-  const int s = blockIdx.x;
-  for (int a = struct_ptr[s] + threadIdx.x; a < struct_ptr[s + 1]; a += blockDim.x) atom_struct[a] = s;
+// gradients of the output layer and of scale / shift, and (second kernel) the bias gradients.
+// Column reductions over atoms use blocks of 8 columns x 32 atom groups with a fixed-order tree, so they are
+// deterministic and spread over 32 blocks.
+constexpr int CR_COLS = 8, CR_GROUPS = 32;
+
+__device__ __forceinline__ float colreduce_finish(float acc, float (*red)[CR_COLS]) {
+  const int c = threadIdx.x % CR_COLS, g = threadIdx.x / CR_COLS;
+  red[g][c] = acc;
+  __syncthreads();
+  for (int o = CR_GROUPS / 2; o; o >>= 1) {
+    if (g < o) red[g][c] += red[g + o][c];
+    __syncthreads();
+  }
+  return red[0][c];
 }
 
-// gradients of the output layer and of scale / shift.  grid: 1 + ceil(S / 4) blocks of 256 threads.
-//   block 0: thread k: w2bar[k] = sum_a s~_a (alpha h2[a][k] - hdot2[a][k]);  thread 0 also b2bar = sum_a alpha s~_a
+//   blocks [0, 32): w2bar[k] = sum_a s~_a (alpha h2[a][k] - hdot2[a][k]);  block 0 also b2bar = sum_a alpha s~_a
 //   other blocks: warp per species z: scalebar[z] = sum_{a: Z_a = z} mask (alpha e_a - edot_a), shiftbar[z] = sum alpha mask
 __global__ void __launch_bounds__(256) k_tr_head_grads(TrWs w, const int32_t* __restrict__ Z, const int32_t* __restrict__ atom_struct,
                                                        const double* __restrict__ scale, int mask_atoms, int S,
                                                        float* __restrict__ w2bar, float* __restrict__ b2bar,
                                                        double* __restrict__ scalebar, double* __restrict__ shiftbar) {
-  if (blockIdx.x == 0) {
-    const int k = threadIdx.x;
+  __shared__ float red[CR_GROUPS][CR_COLS];
+  if (blockIdx.x < NH / CR_COLS) {
+    const int c = threadIdx.x % CR_COLS, g = threadIdx.x / CR_COLS, k = blockIdx.x * CR_COLS + c;
     float acc = 0.f, accb = 0.f;
-    for (int64_t a = 0; a < w.n; ++a) {
+    for (int64_t a = g; a < w.n; a += CR_GROUPS) {
       const int z = Z[a];
       const float st = float((mask_atoms && z == 0) ? 0.0 : scale[z]);
       const float al = float(w.alpha[atom_struct[a]]);
       acc += st * (al * w.H2[a * NH + k] - w.H2[(w.n + a) * NH + k]);
       accb += al * st;
     }
-    w2bar[k] = acc;
-    if (k == 0) b2bar[0] = accb;
+    const float tot = colreduce_finish(acc, red);
+    if (g == 0) w2bar[k] = tot;
+    if (blockIdx.x == 0) {
+      __syncthreads();
+      const float totb = colreduce_finish(accb, red);
+      if (threadIdx.x == 0) b2bar[0] = totb;
+    }
     return;
   }
-  const int z = (blockIdx.x - 1) * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int z = (blockIdx.x - NH / CR_COLS) * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (z >= S) return;
   double sc = 0.0, sh = 0.0;
   if (!(mask_atoms && z == 0)) {
@@ -749,13 +891,17 @@ __global__ void __launch_bounds__(256) k_tr_head_grads(TrWs w, const int32_t* __
   if (lane == 0) { scalebar[z] = sc; shiftbar[z] = sh; }
 }
 
-// bias gradients: column sums of the first n rows of the pre-activation adjoints.  thread per column.
-__global__ void __launch_bounds__(256) k_tr_colsum(const float* __restrict__ X, int64_t n, int ld, float* __restrict__ out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= ld) return;
+// bias gradients: column sums of the first n rows of the two pre-activation adjoints (blockIdx.y picks the layer)
+__global__ void __launch_bounds__(256) k_tr_colsum(const float* __restrict__ X0, float* __restrict__ out0,
+                                                   const float* __restrict__ X1, float* __restrict__ out1, int64_t n, int ld) {
+  __shared__ float red[CR_GROUPS][CR_COLS];
+  const float* X = blockIdx.y ? X1 : X0;
+  float* out = blockIdx.y ? out1 : out0;
+  const int c = threadIdx.x % CR_COLS, g = threadIdx.x / CR_COLS, k = blockIdx.x * CR_COLS + c;
   float acc = 0.f;
-  for (int64_t a = 0; a < n; ++a) acc += X[a * ld + k];
-  out[k] = acc;
+  for (int64_t a = g; a < n; a += CR_GROUPS) acc += X[a * ld + k];
+  const float tot = colreduce_finish(acc, red);
+  if (g == 0) out[k] = tot;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -797,36 +943,58 @@ __global__ void __launch_bounds__(64) k_tr_emb_pair(TrWs w, const int32_t* __res
   }
 }
 
-__global__ void __launch_bounds__(128) k_tr_species_mark(const int32_t* __restrict__ Z, int64_t n, int32_t* __restrict__ present) {
-  const int64_t a = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (a < n) present[Z[a] & 127] = 1;   // benign race: every writer stores 1
-}
-
-// grid (S, S): block (zc, zn) returns at once unless both species are present; else sums the cbar rows whose key matches,
-// thread-strided partial sums then a fixed tree.
+// 256 blocks share the (present species)^2 table blocks; each sums the cbar rows whose key matches: thread-strided
+// partial sums, then a fixed tree.
+constexpr int ER_BLOCKS = 256;
 __global__ void __launch_bounds__(128) k_tr_emb_reduce(TrWs w, int S, float* __restrict__ embbar) {
-  const int zc = blockIdx.y, zn = blockIdx.x;
-  if (!w.present[zc] || !w.present[zn]) return;
   __shared__ float red[128][36];
-  const int key = zc * S + zn;
-  float acc[35];
-#pragma unroll
-  for (int q = 0; q < 35; ++q) acc[q] = 0.f;
-  for (int64_t p = threadIdx.x; p < w.P; p += blockDim.x) {
-    if (__float_as_int(w.geo[p].w) != key) continue;
-    const float* c = w.cbar + p * 35;
-#pragma unroll
-    for (int q = 0; q < 35; ++q) acc[q] += c[q];
+  __shared__ int list[128];
+  __shared__ int n_list;
+  {   // ordered compaction of the present species: one flag per thread, ballot prefix per warp
+    __shared__ int warp_cnt[4];
+    const int z = threadIdx.x, lane = z & 31, wid = z >> 5;
+    const bool on = z < S && w.present[z] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    int base = 0;
+    for (int q = 0; q < wid; ++q) base += warp_cnt[q];
+    if (on) list[base + __popc(bal & ((1u << lane) - 1u))] = z;
+    if (threadIdx.x == 0) n_list = warp_cnt[0] + warp_cnt[1] + warp_cnt[2] + warp_cnt[3];
   }
-#pragma unroll
-  for (int q = 0; q < 35; ++q) red[threadIdx.x][q] = acc[q];
   __syncthreads();
-  for (int o = 64; o; o >>= 1) {
-    if (threadIdx.x < o)
-      for (int q = 0; q < 35; ++q) red[threadIdx.x][q] += red[threadIdx.x + o][q];
+  const int np = n_list;
+  for (int q = blockIdx.x; q < np * np; q += gridDim.x) {
+    const int key = list[q / np] * S + list[q % np];
+    float acc[35];
+#pragma unroll
+    for (int i = 0; i < 35; ++i) acc[i] = 0.f;
+    for (int64_t base = 0; base < w.P; base += 32 * int64_t(blockDim.x)) {
+      unsigned match = 0;   // 32 independent key loads per thread, then only the matching rows are read
+#pragma unroll 8
+      for (int b = 0; b < 32; ++b) {
+        const int64_t p = base + int64_t(b) * blockDim.x + threadIdx.x;
+        if (p < w.P && __float_as_int(w.geo[p].w) == key) match |= 1u << b;
+      }
+      while (match) {
+        const int b = __ffs(match) - 1;
+        match &= match - 1;
+        const float* c = w.cbar + (base + int64_t(b) * blockDim.x + threadIdx.x) * 35;
+#pragma unroll
+        for (int i = 0; i < 35; ++i) acc[i] += c[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 35; ++i) red[threadIdx.x][i] = acc[i];
+    __syncthreads();
+    for (int o = 64; o; o >>= 1) {
+      if (threadIdx.x < o)
+        for (int i = 0; i < 35; ++i) red[threadIdx.x][i] += red[threadIdx.x + o][i];
+      __syncthreads();
+    }
+    if (threadIdx.x < 35) embbar[int64_t(key) * 35 + threadIdx.x] = red[0][threadIdx.x];
     __syncthreads();
   }
-  if (threadIdx.x < 35) embbar[int64_t(key) * 35 + threadIdx.x] = red[0][threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -847,40 +1015,61 @@ __device__ __forceinline__ double sched(double init, int64_t count, const AdamAr
   return (init - a.end_value) * frac + a.end_value;
 }
 
+struct AdamScalars {
+  double lr[4];      // scheduled learning rates: emb, nn, scale, shift (negative: group frozen)
+  double bc1, bc2;   // 1 - b1^t, 1 - b2^t
+};
+static_assert(sizeof(AdamScalars) == 6 * sizeof(int64_t), "opt_state holds count + AdamScalars");
+
+// opt_state: i64 [8] = { optax count, AdamScalars of the step being applied, spare }
+__global__ void k_tr_adam_prep(AdamArgs a, int64_t* opt_state) {
+  const int64_t count = opt_state[0];
+  AdamScalars* sc = reinterpret_cast<AdamScalars*>(opt_state + 1);
+  const double lr0[4] = {a.lr_emb, a.lr_nn, a.lr_scale, a.lr_shift};
+  for (int i = 0; i < 4; ++i) sc->lr[i] = lr0[i] <= 1e-7 ? -1.0 : sched(lr0[i], count, a);   // set_to_zero (get_optimizer.py:74-75)
+  const double t = double(count + 1);
+  sc->bc1 = 1.0 - pow(a.b1, t);
+  sc->bc2 = 1.0 - pow(a.b2, t);
+  opt_state[0] = count + 1;
+}
+
 template <class T>
-__device__ __forceinline__ void adam_one(T& p, T g, T& m, T& v, double lr0, int64_t count, const AdamArgs& a) {
-  if (lr0 <= 1e-7) return;   // optax.set_to_zero (get_optimizer.py:74-75)
+__device__ __forceinline__ void adam_one(T& p, T g, T& m, T& v, double lr, const AdamScalars& sc, const AdamArgs& a) {
+  if (lr < 0.0) return;
   const T c = T(a.clip);
   g = g < -c ? -c : (g > c ? c : g);
   m = T(a.b1) * m + T(1.0 - a.b1) * g;
   v = T(a.b2) * v + T(1.0 - a.b2) * g * g;
-  const double t = double(count + 1);
-  const T mh = m / T(1.0 - pow(a.b1, t));
-  const T vh = v / T(1.0 - pow(a.b2, t));
-  T upd = T(-sched(lr0, count, a)) * (mh / (sqrt(vh) + T(a.eps)));
-  if (upd != upd) upd = T(0);
+  const T mh = m / T(sc.bc1);
+  const T vh = v / T(sc.bc2);
+  T upd = T(-lr) * (mh / (sqrt(vh) + T(a.eps)));
+  if (upd != upd) upd = T(0);   // optax.zero_nans
   p += upd;
 }
 
-__global__ void __launch_bounds__(256) k_tr_adam(AdamArgs a, float* __restrict__ th32, const float* __restrict__ g32,
-                                                 float* __restrict__ m32, float* __restrict__ v32, double* __restrict__ th64,
+// four fp32 parameters per thread (the block length and the embedding/dense boundary are multiples of 64 elements)
+__global__ void __launch_bounds__(256) k_tr_adam(AdamArgs a, float4* __restrict__ th32, const float4* __restrict__ g32,
+                                                 float4* __restrict__ m32, float4* __restrict__ v32, double* __restrict__ th64,
                                                  const double* __restrict__ g64, double* __restrict__ m64,
-                                                 double* __restrict__ v64, const int64_t* __restrict__ count_dev) {
-  const int64_t count = *count_dev;
+                                                 double* __restrict__ v64, const int64_t* __restrict__ opt_state) {
+  const AdamScalars sc = *reinterpret_cast<const AdamScalars*>(opt_state + 1);
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < a.n32) {
-    float p = th32[i], m = m32[i], v = v32[i];
-    adam_one<float>(p, g32[i], m, v, i < a.emb_count ? a.lr_emb : a.lr_nn, count, a);
+  if (4 * i < a.n32) {
+    float4 p = th32[i], m = m32[i], v = v32[i];
+    const float4 g = g32[i];
+    const double lr = 4 * i < a.emb_count ? sc.lr[0] : sc.lr[1];
+    adam_one<float>(p.x, g.x, m.x, v.x, lr, sc, a);
+    adam_one<float>(p.y, g.y, m.y, v.y, lr, sc, a);
+    adam_one<float>(p.z, g.z, m.z, v.z, lr, sc, a);
+    adam_one<float>(p.w, g.w, m.w, v.w, lr, sc, a);
     th32[i] = p; m32[i] = m; v32[i] = v;
   }
   if (i < a.n64) {
     double p = th64[i], m = m64[i], v = v64[i];
-    adam_one<double>(p, g64[i], m, v, i < a.S ? a.lr_scale : a.lr_shift, count, a);
+    adam_one<double>(p, g64[i], m, v, i < a.S ? sc.lr[2] : sc.lr[3], sc, a);
     th64[i] = p; m64[i] = m; v64[i] = v;
   }
 }
-
-__global__ void k_tr_count_inc(int64_t* count_dev) { *count_dev += 1; }
 
 }  // namespace
 }  // namespace apax
@@ -1011,15 +1200,12 @@ extern "C" int apax_train_loss_and_grad(apax_stream_t stream_, const apax_train_
   const DescConstT& dc = p->dc;
 
   APAX_CUDA_TRY(cudaMemsetAsync(grad32, 0, sizeof(float) * size_t(p->off32[7]), s));
-  APAX_CUDA_TRY(cudaMemsetAsync(w.present, 0, sizeof(int32_t) * 128, s));
+  APAX_CUDA_TRY(cudaMemsetAsync(w.present, 0, sizeof(int32_t) * 132, s));
   // lists and geometry
-  APAX_LAUNCH(k_tr_group, dim3((unsigned)B), dim3(128), 0, s, idx, P, struct_ptr, pair_ptr, w);
-  APAX_LAUNCH(k_tr_atom_struct, dim3((unsigned)B), dim3(256), 0, s, struct_ptr, B, atom_struct);
-  APAX_LAUNCH(k_tr_geom, dim3((unsigned)cdiv(P, 256)), dim3(256), 0, s, R, Z, idx, offsets, S, atom_struct, pair_ptr, w);
-  APAX_LAUNCH(k_tr_species_mark, dim3((unsigned)cdiv(n, 128)), dim3(128), 0, s, Z, n, w.present);
+  APAX_LAUNCH(k_tr_group, dim3((unsigned)B), dim3(128), 0, s, idx, P, struct_ptr, pair_ptr, Z, R, offsets, S, atom_struct, w);
   // ---- energy
   APAX_LAUNCH(k_tr_moments<0>, dim3((unsigned)n), dim3(128), 0, s, w, emb, idx, dc, w.M);
-  APAX_LAUNCH(k_tr_contract<0>, dim3((unsigned)n), dim3(384), 0, s, tab, w.M, nullptr, w.GS);
+  APAX_LAUNCH(k_tr_contract<0>, dim3((unsigned)cdiv(n, CT_ATOMS)), dim3(384), 0, s, tab, w.M, nullptr, w.GS, n);
   GemmT g{};
   g = GemmT{w.GS, NF, 1, w0, NH, 1, w.Y1, NH, int(n), NH, NF, b0, EPI_ACT, w.H1, nullptr, nullptr, nullptr};
   APAX_TRY(gemm(s, g));
@@ -1032,21 +1218,20 @@ extern "C" int apax_train_loss_and_grad(apax_stream_t stream_, const apax_train_
   APAX_TRY(gemm(s, g));
   g = GemmT{w.YB1 + n * NH, NH, 1, w0, 1, NH, w.GB + n * NF, NF, int(n), NF, NH, nullptr, EPI_NONE, nullptr, nullptr, nullptr, nullptr};
   APAX_TRY(gemm(s, g));
-  APAX_LAUNCH(k_tr_contract_bwd, dim3((unsigned)n), dim3(128), 0, s, tab, w.M, nullptr, w.GB + n * NF, nullptr, w.Mdb);
+  APAX_LAUNCH(k_tr_contract_bwd, dim3((unsigned)cdiv(n, CT_ATOMS)), dim3(NPK * CB_LANES), 0, s, tab, w.M, nullptr, w.GB + n * NF, nullptr, w.Mdb, n);
   APAX_LAUNCH(k_tr_pair_bwd, dim3((unsigned)n), dim3(64), 0, s, w, emb, dc);
   LossArgs la{lc->energy_weight, lc->energy_atoms_exponent, lc->forces_weight, lc->forces_atoms_exponent, batch_divisor};
-  APAX_LAUNCH(k_tr_forces_loss, dim3((unsigned)B), dim3(128), 0, s, w, struct_ptr, n_real, E_label, F_label, la, forces);
-  APAX_LAUNCH(k_tr_loss_sum, dim3(1), dim3(32), 0, s, w, loss);
+  APAX_LAUNCH(k_tr_forces_loss, dim3((unsigned)B), dim3(128), 0, s, w, struct_ptr, n_real, E_label, F_label, la, forces, loss);
   // ---- tangent sweep along u = dL/dF, rows [n, 2n)
   APAX_LAUNCH(k_tr_moments<1>, dim3((unsigned)n), dim3(128), 0, s, w, emb, idx, dc, w.Md);
-  APAX_LAUNCH(k_tr_contract<1>, dim3((unsigned)n), dim3(384), 0, s, tab, w.M, w.Md, w.GS + n * NF);
+  APAX_LAUNCH(k_tr_contract<1>, dim3((unsigned)cdiv(n, CT_ATOMS)), dim3(384), 0, s, tab, w.M, w.Md, w.GS + n * NF, n);
   g = GemmT{w.GS + n * NF, NF, 1, w0, NH, 1, w.Y1 + n * NH, NH, int(n), NH, NF, nullptr, EPI_TAN, w.H1 + n * NH, w.Y1, nullptr, nullptr};
   APAX_TRY(gemm(s, g));
   g = GemmT{w.H1 + n * NH, NH, 1, w1, NH, 1, w.Y2 + n * NH, NH, int(n), NH, NH, nullptr, EPI_TAN, w.H2 + n * NH, w.Y2, nullptr, nullptr};
   APAX_TRY(gemm(s, g));
   // ---- reverse sweep of  sum_s alpha_s E_s - Edot, rows [0, n)
   APAX_LAUNCH(k_tr_head2, dim3((unsigned)cdiv(n * 32, 256)), dim3(256), 0, s, w, w2, Z, atom_struct, scale, mask);
-  APAX_LAUNCH(k_tr_head_grads, dim3((unsigned)(1 + cdiv(S, 8))), dim3(256), 0, s, w, Z, atom_struct, scale, mask, S, g_w2, g_b2,
+  APAX_LAUNCH(k_tr_head_grads, dim3((unsigned)(NH / CR_COLS + cdiv(S, 8))), dim3(256), 0, s, w, Z, atom_struct, scale, mask, S, g_w2, g_b2,
               grad64 + p->off64[0], grad64 + p->off64[1]);
   g = GemmT{w.YB2, NH, 1, w1, 1, NH, w.HB1, NH, int(n), NH, NH, nullptr, EPI_SECOND, w.YB1, w.Y1, w.HB1 + n * NH, w.Y1 + n * NH};
   APAX_TRY(gemm(s, g));
@@ -1057,26 +1242,26 @@ extern "C" int apax_train_loss_and_grad(apax_stream_t stream_, const apax_train_
   APAX_TRY(gemm(s, g));
   g = GemmT{w.GS, 1, NF, w.YB1, NH, 1, g_w0, NH, NF, NH, int(2 * n), nullptr, EPI_NONE, nullptr, nullptr, nullptr, nullptr};
   APAX_TRY(gemm(s, g));
-  APAX_LAUNCH(k_tr_colsum, dim3(1), dim3(256), 0, s, w.YB2, n, NH, g_b1);
-  APAX_LAUNCH(k_tr_colsum, dim3(1), dim3(256), 0, s, w.YB1, n, NH, g_b0);
+  APAX_LAUNCH(k_tr_colsum, dim3(NH / CR_COLS, 2), dim3(256), 0, s, w.YB2, g_b1, w.YB1, g_b0, n, NH);
   // moments' adjoint incl. the second-order term, then the embedding gradient
-  APAX_LAUNCH(k_tr_contract_bwd, dim3((unsigned)n), dim3(128), 0, s, tab, w.M, w.Md, w.GB, w.GB + n * NF, w.Mb2);
+  APAX_LAUNCH(k_tr_contract_bwd, dim3((unsigned)cdiv(n, CT_ATOMS)), dim3(NPK * CB_LANES), 0, s, tab, w.M, w.Md, w.GB, w.GB + n * NF, w.Mb2, n);
   APAX_LAUNCH(k_tr_emb_pair, dim3((unsigned)n), dim3(64), 0, s, w, idx, dc);
-  APAX_LAUNCH(k_tr_emb_reduce, dim3((unsigned)S, (unsigned)S), dim3(128), 0, s, w, S, g_emb);
+  APAX_LAUNCH(k_tr_emb_reduce, dim3(ER_BLOCKS), dim3(128), 0, s, w, S, g_emb);
   return APAX_OK;
 }
 
 extern "C" int apax_train_adam_step(apax_stream_t stream_, const apax_train_plan* p, const apax_train_opt_config* oc,
                                     float* theta32, double* theta64, const float* grad32, const double* grad64, float* m32,
-                                    float* v32, double* m64, double* v64, int64_t* count_device) {
+                                    float* v32, double* m64, double* v64, int64_t* opt_state) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  if (!p || !oc || !theta32 || !theta64 || !grad32 || !grad64 || !m32 || !v32 || !m64 || !v64 || !count_device)
+  if (!p || !oc || !theta32 || !theta64 || !grad32 || !grad64 || !m32 || !v32 || !m64 || !v64 || !opt_state)
     return APAX_ERR_INVALID_ARG;
   if (oc->transition_steps < 1) return APAX_ERR_INVALID_ARG;
   AdamArgs a{oc->emb_lr, oc->nn_lr, oc->scale_lr, oc->shift_lr, oc->gradient_clipping, oc->end_value, oc->b1, oc->b2, oc->eps,
              oc->transition_steps, oc->transition_begin, p->off32[1], p->off32[7], p->off64[2], p->cfg.n_species};
-  APAX_LAUNCH(k_tr_adam, dim3((unsigned)cdiv(std::max(a.n32, a.n64), 256)), dim3(256), 0, s, a, theta32, grad32, m32, v32, theta64,
-              grad64, m64, v64, count_device);
-  APAX_LAUNCH(k_tr_count_inc, dim3(1), dim3(1), 0, s, count_device);
+  APAX_LAUNCH(k_tr_adam_prep, dim3(1), dim3(1), 0, s, a, opt_state);
+  APAX_LAUNCH(k_tr_adam, dim3((unsigned)cdiv(std::max(a.n32 / 4, a.n64), 256)), dim3(256), 0, s, a,
+              reinterpret_cast<float4*>(theta32), reinterpret_cast<const float4*>(grad32), reinterpret_cast<float4*>(m32),
+              reinterpret_cast<float4*>(v32), theta64, grad64, m64, v64, opt_state);
   return APAX_OK;
 }

@@ -72,13 +72,13 @@ class TrainState:
         self.grad64 = torch.zeros_like(self.theta64)
         self.m32, self.v32 = torch.zeros_like(self.theta32), torch.zeros_like(self.theta32)
         self.m64, self.v64 = torch.zeros_like(self.theta64), torch.zeros_like(self.theta64)
-        self.count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.count = torch.zeros(8, dtype=torch.int64, device=dev)   # [0] = optax count, rest: device scratch
         self.tx = tx
         self._opt_c = tx.to_c()
 
     @property
     def step(self) -> int:
-        return int(self.count.item())
+        return int(self.count[0].item())
 
     def _tree(self, t32: torch.Tensor, t64: torch.Tensor) -> dict:
         h32, h64 = t32.cpu().numpy(), t64.cpu().numpy()

@@ -260,11 +260,11 @@ int apax_train_loss_and_grad(apax_stream_t stream, const apax_train_plan* plan, 
                              const double* E_label, const double* F_label, const apax_train_loss_config* loss_cfg,
                              double batch_divisor, double* loss, double* energy, double* forces, float* grad32,
                              double* grad64, void* workspace, size_t workspace_bytes);
-/* One optimizer update, in place.  count_device i64 [1] is the optimizer's step counter (optax `count`), read for the
- * schedule / bias correction and incremented on the device. */
+/* One optimizer update, in place.  opt_state i64 [8], zero-initialised by the caller: [0] is the optimizer's step counter
+ * (optax `count`), read for the schedule / bias correction and incremented on the device; the rest is scratch. */
 int apax_train_adam_step(apax_stream_t stream, const apax_train_plan* plan, const apax_train_opt_config* opt_cfg,
                          float* theta32, double* theta64, const float* grad32, const double* grad64, float* m32,
-                         float* v32, double* m64, double* v64, int64_t* count_device);
+                         float* v32, double* m64, double* v64, int64_t* opt_state);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer convenience context: what ASECalculator.calculate does per call

@@ -127,7 +127,10 @@ def test_periodic_cells_with_offsets_vs_oracle():
     ref64 = tor.loss_and_grads(params, inputs, labels, mode="offsets", cfg=go.fp64_config())
     loss, e, f, grads, _ = _gpu_loss_grads(params, inputs, labels, tor.DEFAULT_LOSS)
     assert abs(loss - ref["loss"]) <= 2e-6 * abs(ref["loss"])
-    assert np.abs(e - ref["energy"]).max() <= 1e-6 * np.abs(ref["energy"]).max()
+    # these random-weight energies nearly cancel (|E| ~ 1 from ~15 atomic terms of either sign), so 1e-6 of |E| is below the
+    # fp32 noise of the sum; accept either that or twice the fp32 oracle's own distance from the fp64 truth
+    e_tol = max(1e-6 * np.abs(ref["energy"]).max(), 2.0 * np.abs(ref["energy"] - ref64["energy"]).max())
+    assert np.abs(e - ref64["energy"]).max() <= e_tol
     _check_grads(grads, ref["grads"], ref64["grads"], where="periodic")
 
 
