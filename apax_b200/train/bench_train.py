@@ -27,8 +27,16 @@ def run(args, world: int, rank: int, local: int, ClockSampler, metric: str, unit
     from .loss import Loss, LossCollection
     from .trainer import TrainState, TrainStep, flatten_batch
 
+    import sys
+
     torch.cuda.set_device(local)
+    # stdout must carry exactly one JSON line: NCCL writes its version banner to file descriptor 1, so whatever a library
+    # prints there goes to stderr and the result line leaves through a saved copy of the descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = rt.lib()
     B = args.train_batch
@@ -67,7 +75,7 @@ def run(args, world: int, rank: int, local: int, ClockSampler, metric: str, unit
         ms_total = float(t.item())
     time.sleep(0.15)
     clocks = sampler.stop(window_s=ms_total * 1e-3 + 0.15)
-    loss_now = float(step.batch.loss.item())
+    loss_now = float(state.loss.item())
     assert np.isfinite(loss_now)
 
     # launches per step: count them on one un-graphed step (a graph replay re-issues the same kernels)
@@ -129,7 +137,8 @@ def run(args, world: int, rank: int, local: int, ClockSampler, metric: str, unit
         }
         if not args.no_cpu_baseline and cpu_baseline_fn is not None:
             line["cpu_baseline"] = cpu_baseline_fn(B, unit)
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

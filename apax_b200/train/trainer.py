@@ -69,7 +69,9 @@ class TrainState:
         self.theta32 = torch.as_tensor(host32).to(dev)
         self.theta64 = torch.as_tensor(host64).to(dev)
         self.grad32 = torch.zeros_like(self.theta32)
-        self.grad64 = torch.zeros_like(self.theta64)
+        # gradient block of scale/shift; the loss of the step sits in the tail so that one all-reduce carries both
+        self.grad64 = torch.zeros(2 * S + 8, dtype=torch.float64, device=dev)
+        self.loss = self.grad64[2 * S: 2 * S + 1]
         self.m32, self.v32 = torch.zeros_like(self.theta32), torch.zeros_like(self.theta32)
         self.m64, self.v64 = torch.zeros_like(self.theta64), torch.zeros_like(self.theta64)
         self.count = torch.zeros(8, dtype=torch.int64, device=dev)   # [0] = optax count, rest: device scratch
@@ -99,7 +101,7 @@ class TrainState:
     @property
     def grads(self) -> dict:
         """The gradient of the last loss evaluation, same tree layout (host copy)."""
-        return self._tree(self.grad32, self.grad64)
+        return self._tree(self.grad32, self.grad64[: 2 * self.config["n_species"]])
 
     def apply_gradients(self) -> "TrainState":
         """TrainState.apply_gradients with the gradient blocks already on the device (in place)."""
@@ -182,7 +184,6 @@ class DeviceBatch:
                   "n_real": (B,), "E_label": (B,), "F_label": (n, 3)}
         self.dev = {k: torch.empty(shapes[k], dtype=dt, device=dev) for k, dt in _KEYS}
         self.pin = {k: torch.empty(shapes[k], dtype=dt).pin_memory() for k, dt in _KEYS}
-        self.loss = torch.zeros(1, dtype=torch.float64, device=dev)
         self.energy = torch.zeros(B, dtype=torch.float64, device=dev)
         self.forces = torch.zeros((n, 3), dtype=torch.float64, device=dev)
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pin.values())
@@ -216,50 +217,60 @@ class TrainStep:
         self.graph = None
         self._want_graph = graph
 
-    def _device_step(self) -> None:
+    def _grad(self) -> None:
         st, b = self.state, self.batch
         d = b.dev
         n, P = b.B * b.nmax, b.B * b.pmax
         check(lib().apax_train_loss_and_grad(
             _stream_ptr(), st.plan, _ptr(st.theta32), _ptr(st.theta64), _ptr(d["R"]), _ptr(d["Z"]), _ptr(d["idx"]),
             _ptr(d["offsets"]), _ptr(d["struct_ptr"]), _ptr(d["pair_ptr"]), _ptr(d["n_real"]), b.B, n, P, _ptr(d["E_label"]),
-            _ptr(d["F_label"]), C.byref(self._loss_c), float(b.B * self.world), _ptr(b.loss), _ptr(b.energy), _ptr(b.forces),
+            _ptr(d["F_label"]), C.byref(self._loss_c), float(b.B * self.world), _ptr(st.loss), _ptr(b.energy), _ptr(b.forces),
             _ptr(st.grad32), _ptr(st.grad64), C.c_void_p(Workspace.aligned_ptr(self.buf)), C.c_size_t(self.nbytes)),
             "apax_train_loss_and_grad")
+
+    def _reduce_and_update(self) -> None:
+        st = self.state
         if self.dist:   # gradients of the global-batch mean loss: per-rank parts add up (batch_divisor is global)
-            allreduce_sum_(self.dist, (st.grad32, st.grad64, b.loss))
+            allreduce_sum_(self.dist, (st.grad32, st.grad64))
         st.apply_gradients()
+
+    def _device_step(self) -> None:
+        self._grad()
+        self._reduce_and_update()
 
     def __call__(self, inputs: dict, labels: dict):
         """Returns (loss tensor [1] f64, predictions {"energy": [B], "forces": [B,Nmax,3]} device tensors)."""
         b = self.batch
         b.upload(flatten_batch(inputs, labels))
         self.run_resident()
-        return b.loss, {"energy": b.energy, "forces": b.forces.view(b.B, b.nmax, 3)}
+        return self.state.loss, {"energy": b.energy, "forces": b.forces.view(b.B, b.nmax, 3)}
 
     def run_resident(self) -> None:
         """One step on the batch already in the device buffers."""
         if not self._want_graph:
             self._device_step()
             return
+        # Single process: the whole step (loss+gradients, Adam) is one graph.  Data parallel: only this library's
+        # kernels are captured; the NCCL all-reduce and the two Adam launches follow eagerly on the same stream.
+        body = self._grad if self.dist else self._device_step
         if self.graph is None:
-            # warm up on a side stream (library init, NCCL channels), restoring the state afterwards
             st = self.state
-            keep = [t.clone() for t in (st.theta32, st.theta64, st.m32, st.v32, st.m64, st.v64, st.count)]
-            side = torch.cuda.Stream()
+            saved = (st.theta32, st.theta64, st.m32, st.v32, st.m64, st.v64, st.count)
+            keep = [t.clone() for t in saved]
+            side = torch.cuda.Stream()   # warm up outside the capture (module load, first-touch), then restore the state
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self._device_step()
+                body()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            for t, k in zip((st.theta32, st.theta64, st.m32, st.v32, st.m64, st.v64, st.count), keep):
+            for t, k in zip(saved, keep):
                 t.copy_(k)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self._device_step()
-            for t, k in zip((st.theta32, st.theta64, st.m32, st.v32, st.m64, st.v64, st.count), keep):
-                t.copy_(k)   # capture does not execute, but keep the contract explicit
+                body()
         self.graph.replay()
+        if self.dist:
+            self._reduce_and_update()
 
 
 def make_step_fns(loss_fn: LossCollection, Metrics=None, model=None, is_ensemble: bool = False, graph: bool = False):
