@@ -1244,7 +1244,7 @@ using namespace apax;
 
 static int validate_cfg(const apax_gm_config* c) {
   if (!c) return APAX_ERR_INVALID_ARG;
-  if (c->n_radial != NR || c->n_basis != NB || c->n_contr != 8 || c->n_hidden1 != NH || c->n_hidden2 != NH)
+  if (c->n_radial != NR || c->n_basis != NB || c->n_contr < 1 || c->n_contr > 8 || c->n_hidden1 != NH || c->n_hidden2 != NH)
     return APAX_ERR_UNSUPPORTED;
   if (c->n_out < 1 || c->n_out > MAX_OUT || c->n_species < 1 || c->n_species > 128) return APAX_ERR_UNSUPPORTED;
   if (!(c->r_max > c->r_min) || !(c->r_min >= 0.f)) return APAX_ERR_INVALID_ARG;
@@ -1268,6 +1268,14 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
   apax_gm_params* p = new apax_gm_params();
   p->cfg = *cfg;
   const int S = cfg->n_species, n_out = cfg->n_out;
+  // n_contr < 8 truncates the feature list c0|c1|...|c7 (gaussian_moment_descriptor.py:101): the caller's first dense layer
+  // has n_feat rows; the kernels always produce all 360 features, the dropped ones meet zero weight rows (and receive a
+  // zero adjoint), which is the same function.
+  static const int kFeatCount[8] = {5, 20, 35, 50, 85, 160, 235, 360};
+  const int n_feat = kFeatCount[cfg->n_contr - 1];
+  std::vector<float> w0_padded(size_t(NF) * NH, 0.0f);
+  std::copy(w0, w0 + size_t(n_feat) * NH, w0_padded.begin());
+  w0 = w0_padded.data();
   // NTKLinear (ntk_linear.py:42-45): y = sqrt(1/in) * x.w + 0.1 * b, folded into the stored weights
   auto wf = [&](int fan_in) { return cfg->use_ntk ? float(sqrt(1.0 / fan_in)) : 1.0f; };
   const float bf = cfg->use_ntk ? 0.1f : 1.0f;
@@ -1285,7 +1293,7 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
     float* ht = new float[size_t(NH) * NFP]();
     for (int k = 0; k < NF; ++k)
       for (int n = 0; n < NH; ++n) {
-        h[size_t(k) * NH + n] = wf(NF) * w0[size_t(k) * NH + n];
+        h[size_t(k) * NH + n] = wf(n_feat) * w0[size_t(k) * NH + n];
         ht[size_t(n) * NFP + k] = h[size_t(k) * NH + n];
       }
     int st = upload(&p->w0, h, size_t(NF) * NH);
@@ -1346,7 +1354,7 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
       delete[] lo;
       return st;
     };
-    const float f0 = wf(NF), f1 = wf(NH);
+    const float f0 = wf(n_feat), f1 = wf(NH);
     APAX_TRY(split_upload(&p->w0_hi, &p->w0_lo, NF, NH, [&](int k, int n) { return f0 * w0[size_t(k) * NH + n]; }));
     APAX_TRY(split_upload(&p->w1_hi, &p->w1_lo, NH, NH, [&](int k, int n) { return f1 * w1[size_t(k) * NH + n]; }));
     APAX_TRY(split_upload(&p->w1t_hi, &p->w1t_lo, NH, NH, [&](int n, int k) { return f1 * w1[size_t(k) * NH + n]; }));

@@ -723,9 +723,15 @@ void i8_quantize_weights(const float* W, int K, int NC, int ldw, int kp, int ncp
   planes.assign(size_t(I8_DIGITS) * ncp * kp, 0);
   if (!given_scale) i8_weight_scales(W, K, NC, ldw, kp, col_scale, false);
   const size_t plane_stride = size_t(ncp) * kp;
+  float min_scale = 0.0f;
+  for (int k = 0; k < K; ++k)
+    if (col_scale[k] > 0.0f && (min_scale == 0.0f || col_scale[k] < min_scale)) min_scale = col_scale[k];
+  if (min_scale == 0.0f) min_scale = 1.0f;
   for (int k = 0; k < K; ++k) {
     if (!(col_scale[k] > 0.0f)) {
-      col_scale[k] = 1.0f;   // all-zero weight row: any scale will do, the digits stay zero
+      // all-zero weight row (a feature dropped by n_contr < 8): its digits stay zero; the scale is the smallest real one
+      // so that the ignored activation cannot dominate the row maximum that fixes the atoms' exponents
+      col_scale[k] = min_scale * 0.00390625f;
       continue;
     }
     const double c = double(col_scale[k]);

@@ -64,7 +64,7 @@ def _descriptor_params(emb, statics):
     if key not in _cache:
         zeros = lambda *s: np.zeros(s, dtype=np.float32)  # noqa: E731
         tree = {"representation": {"radial_fn": {"atomic_type_embedding": emb}},
-                "readout": {"dense_0": {"w": zeros(360, 256), "b": zeros(256)}, "dense_1": {"w": zeros(256, 256), "b": zeros(256)},
+                "readout": {"dense_0": {"w": zeros(rt.FEATURE_COUNTS[statics["n_contr"] - 1], 256), "b": zeros(256)}, "dense_1": {"w": zeros(256, 256), "b": zeros(256)},
                             "dense_2": {"w": zeros(256, 1), "b": zeros(1)}},
                 "scale_shift": {"scale_per_element": np.ones((statics["n_species"], 1)),
                                 "shift_per_element": np.zeros((statics["n_species"], 1))}}

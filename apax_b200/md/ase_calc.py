@@ -102,16 +102,20 @@ class ASECalculator:
             torch.cuda.synchronize()
             e, f = e.cpu().numpy(), f.cpu().numpy()
             n_ens = dp.n_out
+            if n_ens == 1:
+                for b in range(len(chunk)):
+                    results.append({"energy": float(e[b, 0]), "forces": f[0, ptr[b]:ptr[b + 1]]})
+                continue
+            # ensemble statistics for the whole chunk at once (models.py:225-233, 256-263), sliced per structure afterwards
+            e_mean = e.mean(axis=1)
+            e_unc = np.sqrt(((e - e_mean[:, None]) ** 2).sum(axis=1) / (n_ens - 1))
+            fm = f.mean(axis=0)
+            f_unc = np.sqrt(((f - fm) ** 2).sum(axis=0) / (n_ens - 1))
+            f_ens = np.ascontiguousarray(np.transpose(f, (1, 2, 0)))
             for b in range(len(chunk)):
-                fb = f[:, ptr[b]:ptr[b + 1]]
-                if n_ens == 1:
-                    results.append({"energy": float(e[b, 0]), "forces": fb[0]})
-                else:
-                    fm = fb.mean(axis=0)
-                    results.append({"energy": float(e[b].mean()), "energy_ensemble": e[b],
-                                    "energy_uncertainty": float(np.sqrt(((e[b] - e[b].mean()) ** 2).sum() / (n_ens - 1))),
-                                    "forces": fm, "forces_uncertainty": np.sqrt(((fb - fm) ** 2).sum(axis=0) / (n_ens - 1)),
-                                    "forces_ensemble": np.transpose(fb, (1, 2, 0))})
+                sl = slice(ptr[b], ptr[b + 1])
+                results.append({"energy": float(e_mean[b]), "energy_ensemble": e[b], "energy_uncertainty": float(e_unc[b]),
+                                "forces": fm[sl], "forces_uncertainty": f_unc[sl], "forces_ensemble": f_ens[sl]})
         return results
 
     def get_potential_energy(self, atoms):

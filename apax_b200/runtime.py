@@ -13,6 +13,7 @@ from ._lib import DISP_DRVEC, DISP_GAS, DISP_MINIMAGE, DISP_OFFSETS, GmConfig, c
 
 MODES = {"gas": DISP_GAS, "offsets": DISP_OFFSETS, "minimage": DISP_MINIMAGE, "drvec": DISP_DRVEC}
 N_FEATURES = 360
+FEATURE_COUNTS = (5, 20, 35, 50, 85, 160, 235, 360)   # c0 | c0..c1 | ... | c0..c7 (gaussian_moment_descriptor.py:56-101)
 
 
 def _require_cuda() -> torch.device:
@@ -71,8 +72,12 @@ class DeviceParams:
         cfg["n_species"] = int(emb.shape[0])
         if emb.shape != (cfg["n_species"], cfg["n_species"], cfg["n_radial"], cfg["n_basis"]):
             raise _lib.ApaxB200Error(_lib.ERR_INVALID_ARG, "DeviceParams", f"embedding shape {emb.shape}")
-        if w[0].shape != (N_FEATURES, 256) or w[1].shape != (256, 256) or w[2].shape[0] != 256:
-            raise _lib.ApaxB200Error(_lib.ERR_UNSUPPORTED, "DeviceParams", "dense shapes must be 360x256, 256x256, 256xn_out")
+        if not 1 <= int(cfg["n_contr"]) <= 8:
+            raise _lib.ApaxB200Error(_lib.ERR_UNSUPPORTED, "DeviceParams", f"n_contr = {cfg['n_contr']}")
+        self.n_features = FEATURE_COUNTS[int(cfg["n_contr"]) - 1]
+        if w[0].shape != (self.n_features, 256) or w[1].shape != (256, 256) or w[2].shape[0] != 256:
+            raise _lib.ApaxB200Error(_lib.ERR_UNSUPPORTED, "DeviceParams",
+                                     f"dense shapes must be {self.n_features}x256, 256x256, 256xn_out (got {w[0].shape}, {w[1].shape}, {w[2].shape})")
         ss = tree["scale_shift"]
         S = cfg["n_species"]
         scale = np.ascontiguousarray(np.broadcast_to(np.asarray(ss["scale_per_element"], dtype=np.float64).reshape(-1), (S,)))
@@ -204,7 +209,7 @@ def descriptor(params: DeviceParams, R, Z, idx, box=None, offsets=None, mode: st
     wp, wb = _gm_ws(n_atoms, n_pairs, params.n_out, workspace)
     check(lib().apax_gm_descriptor(_stream_ptr(), params.handle, _ptr(R), _ptr(Z), _ptr(idx), _ptr(box_d), _ptr(off_d),
                                    n_atoms, n_pairs, MODES[mode], _ptr(g), wp, wb), "apax_gm_descriptor")
-    return g
+    return g if params.n_features == N_FEATURES else g[:, : params.n_features].contiguous()   # n_contr truncation (:101)
 
 
 # ------------------------------------------------------------------------------------------- lists

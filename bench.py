@@ -45,8 +45,11 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="multi-GPU: strong = the same box split into slabs (BASELINE configs[3]); weak = box grows with N")
-    ap.add_argument("--workload", default="ef", choices=["ef", "train"],
-                    help="ef = BASELINE configs[3] energy+forces (default, the headline); train = configs[1] training step")
+    ap.add_argument("--workload", default="ef", choices=["ef", "train", "md", "ensemble"],
+                    help="ef = BASELINE configs[3] energy+forces (default, the headline); train = configs[1] training step; "
+                         "md = configs[2] NVT MD at 12,288 atoms; ensemble = configs[4] 16-head inference on 128-atom cells")
+    ap.add_argument("--cells", type=int, default=4096, help="--workload ensemble: number of 128-atom cells (all ranks)")
+    ap.add_argument("--ensemble-batch", type=int, default=256, help="--workload ensemble: cells per batch_eval call")
     ap.add_argument("--train-batch", type=int, default=32, help="--workload train: structures per GPU")
     ap.add_argument("--no-graph", action="store_true", help="--workload train: launch kernels eagerly instead of a CUDA graph")
     ap.add_argument("--verify", action="store_true", help="multi-GPU: compare against a single-GPU evaluation of the whole box")
@@ -249,6 +252,11 @@ def run_ours(args):
         from apax_b200.train import bench_train
 
         return bench_train.run(args, world, rank, local, ClockSampler, METRIC, UNIT, cpu_baseline_fn=train_cpu_baseline)
+    if args.workload in ("md", "ensemble"):
+        from apax_b200.md import bench_workloads as bw
+
+        fn = bw.run_md if args.workload == "md" else bw.run_ensemble
+        return fn(args, world, rank, local, ClockSampler, METRIC, UNIT)
     if world > 1:
         from apax_b200.md import domain
 

@@ -53,7 +53,7 @@ typedef struct {
   int32_t n_species;      /* 119 */
   int32_t n_radial;       /* 5   (kernels specialised: must be 5) */
   int32_t n_basis;        /* 7   (must be 7) */
-  int32_t n_contr;        /* 8   (must be 8 -> 360 features) */
+  int32_t n_contr;        /* 8   (1..8: the first 5/20/35/50/85/160/235/360 features, gaussian_moment_descriptor.py:101) */
   int32_t n_hidden1;      /* 256 (must be 256) */
   int32_t n_hidden2;      /* 256 (must be 256) */
   int32_t n_out;          /* 1, or n_shallow_ensemble (<= 16) */
@@ -70,7 +70,7 @@ typedef struct {
  * apax/layers/scaling.py:33-38).  Host arrays in, opaque device-resident handle out (weights are
  * uploaded once, transposed/padded copies for the backward GEMMs are made here).
  *   emb_host   f32 [n_species][n_species][n_radial][n_basis]
- *   w0_host    f32 [360][256], b0_host f32 [256]; w1_host f32 [256][256], b1_host f32 [256]
+ *   w0_host    f32 [n_feat][256] (n_feat = 360 for n_contr = 8), b0_host f32 [256]; w1_host f32 [256][256], b1_host f32 [256]
  *   w2_host    f32 [256][n_out], b2_host f32 [n_out]
  *   scale_host, shift_host  f64 [n_species]
  * ---------------------------------------------------------------------------------------------- */
@@ -139,7 +139,8 @@ int apax_gm_compute_partial(apax_stream_t stream, const apax_gm_params* params, 
 
 /* Descriptor only.  Replaces GaussianMomentDescriptor.__call__ behind the builder seam
  * ModelBuilder.build_descriptor (apax/nn/builder.py:79-83,248-260;
- * apax/layers/descriptor/gaussian_moment_descriptor.py:31-103).  g: f32 [n_atoms][360] row-major out. */
+ * apax/layers/descriptor/gaussian_moment_descriptor.py:31-103).  g: f32 [n_atoms][360] row-major out; with
+ * n_contr < 8 the reference's output is the first n_feat columns. */
 int apax_gm_descriptor(apax_stream_t stream, const apax_gm_params* params, const double* R,
                        const int32_t* Z, const int32_t* idx, const double* box, const double* offsets,
                        int64_t n_atoms, int64_t n_pairs, int32_t disp_mode, float* g, void* workspace,

@@ -188,3 +188,31 @@ def test_properties_at_12288_atoms(rt):
     e3, f3 = rt.energy_forces(dp, frac[perm], Z[perm], idx_p, box, None, "minimage")
     assert abs(e3.cpu().numpy()[0] - e[0]) <= 2e-6 * abs(e[0])
     assert force_tolerance_ok(f3.cpu().numpy()[0], f[perm], rel=2e-5, abs_=2e-5)
+
+
+@pytest.mark.parametrize("n_contr,use_ntk", [(5, False), (8, True), (3, True)])
+def test_truncated_contractions_and_ntk_linear(n_contr, use_ntk):
+    """SURVEY.md s8f rank 3 variants: `n_contr < 8` truncates the feature list (gaussian_moment_descriptor.py:101) and
+    `use_ntk` rescales the dense layers (ntk_linear.py:42-45); both against the oracle on a multi-image water cell."""
+    from apax_b200 import runtime as rt
+    from oracle import gmnn_oracle as go
+    from oracle import neighbor_oracle as no
+
+    pos, Z, cell = syn.water_box(16, 4)
+    idx, offsets = no.vesin_idx_offsets(pos, cell, 6.0)
+    frac = pos @ np.linalg.inv(cell)
+    n_feat = rt.FEATURE_COUNTS[n_contr - 1]
+    params = syn.gmnn_params(seed=5, n_features=n_feat, random_bias=True, random_scale_shift=True)
+    cfg = go.GMNNConfig(n_contr=n_contr, use_ntk=use_ntk)
+    ref = go.energy_forces(params, frac, Z, idx, cell.T, offsets, "offsets", cfg)
+    ref64 = go.energy_forces(params, frac, Z, idx, cell.T, offsets, "offsets", go.fp64_config(cfg))
+    dp = rt.DeviceParams(params, {"n_contr": n_contr, "use_ntk": use_ntk})
+    e, f = rt.energy_forces(dp, frac, Z, idx, cell.T, offsets, "offsets")
+    torch.cuda.synchronize()
+    e, f = e.cpu().numpy(), f.cpu().numpy()[0]
+    assert abs(e[0] - ref["energy"]) <= 1e-6 * abs(ref["energy"])
+    assert_force_parity(f, ref["forces"], ref64["forces"], where=f"n_contr={n_contr} ntk={use_ntk}")
+    g = rt.descriptor(dp, frac, Z, idx, cell.T, offsets, "offsets").cpu().numpy()
+    g_ref = go.descriptor_only(params, frac, Z, idx, cell.T, offsets, "offsets", cfg)["g"]
+    assert g.shape == (len(Z), n_feat)
+    assert np.abs(g - g_ref).max() <= 2e-6 * np.abs(g_ref).max()
