@@ -48,6 +48,11 @@ class TrainOptConfig(C.Structure):
                 ("transition_begin", C.c_int64), ("b1", C.c_double), ("b2", C.c_double), ("eps", C.c_double)]
 
 
+class TrainPeers(C.Structure):
+    _fields_ = [("grad32", C.c_void_p * 8), ("grad64", C.c_void_p * 8), ("flags", C.c_void_p * 8), ("world", C.c_int32),
+                ("rank", C.c_int32)]
+
+
 class MdNvtConfig(C.Structure):
     _fields_ = [("chain_length", C.c_int32), ("chain_steps", C.c_int32), ("sy_steps", C.c_int32), ("dt", C.c_double),
                 ("kT", C.c_double), ("tau", C.c_double)]
@@ -93,6 +98,12 @@ SIGNATURES = {
     "apax_train_loss_and_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P,
                                            C.POINTER(TrainLossConfig), C.c_double, _P, _P, _P, _P, _P, _P, C.c_size_t]),
     "apax_train_adam_step": (C.c_int, [_P, _P, C.POINTER(TrainOptConfig), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "apax_peer_alloc": (C.c_int, [_I64, C.POINTER(_P), _P]),
+    "apax_peer_open": (C.c_int, [_P, C.POINTER(_P)]),
+    "apax_peer_close": (C.c_int, [_P]),
+    "apax_peer_free": (C.c_int, [_P]),
+    "apax_train_allreduce_adam_step": (C.c_int, [_P, _P, C.POINTER(TrainOptConfig), C.POINTER(TrainPeers), C.c_uint32, _P, _P, _P, _P,
+                                                 _P, _P, _P, _P]),
     "apax_ctx_create": (C.c_int, [_P, _I64, _I64, C.POINTER(_P)]),
     "apax_ctx_destroy": (None, [_P]),
     "apax_ctx_calculate": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, _I32, _P, _P, _P]),

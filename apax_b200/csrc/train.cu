@@ -17,6 +17,7 @@
 // synchronise, so a whole step (loss+grad, all-reduce, Adam) can be captured in a CUDA graph; the learning-rate schedule is
 // evaluated on the device from a device-resident step counter for the same reason.
 #include <math.h>
+#include <string.h>
 
 #include <algorithm>
 #include <array>
@@ -1071,6 +1072,76 @@ __global__ void __launch_bounds__(256) k_tr_adam(AdamArgs a, float4* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Data parallelism without a library collective: all-reduce + Adam in ONE kernel over NVLink peer memory.
+// Every rank's gradient block lives in memory that its peers have mapped (CUDA IPC).  A rank (1) tells every peer that
+// its block of this step is complete (release store of the step's epoch into the peer's flag array), (2) waits until all
+// peers have said the same (acquire loads of its OWN flag array -- local memory), then (3) each thread loads its four
+// parameters' gradients from every rank's block IN RANK ORDER (remote loads over NVLink for the peers, bypassing L1),
+// adds them up and applies Adam to the local replica.  The sum order is the same on every rank, so replicas stay bitwise
+// identical.  Gradient blocks are double-buffered by the step's parity: a rank can be at most one step ahead of a peer
+// (it cannot pass the barrier of step t+1 before every peer has signalled t+1, i.e. finished reading step t), so the block
+// being read is never the one being written.
+// ---------------------------------------------------------------------------------------------------------------------
+struct PeerArgs {
+  const float4* g32[8];
+  const double* g64[8];
+  uint32_t* flags[8];   // flags[p]: rank p's flag array u32 [8] as mapped here; slot [r] is written by rank r
+  int world, rank;
+  uint32_t epoch;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_tr_adam_peer(AdamArgs a, PeerArgs pa, float4* __restrict__ th32, float4* __restrict__ m32,
+                                                      float4* __restrict__ v32, double* __restrict__ th64, double* __restrict__ m64,
+                                                      double* __restrict__ v64, const int64_t* __restrict__ opt_state,
+                                                      double* __restrict__ loss_out) {
+  if (blockIdx.x == 0 && threadIdx.x < pa.world) {
+    __threadfence_system();
+    st_release_sys(pa.flags[threadIdx.x] + pa.rank, pa.epoch);
+  }
+  if (threadIdx.x < pa.world) {
+    const uint32_t* mine = pa.flags[pa.rank] + threadIdx.x;
+    while (int32_t(ld_acquire_sys(mine) - pa.epoch) < 0) __nanosleep(64);
+  }
+  __syncthreads();
+  const AdamScalars sc = *reinterpret_cast<const AdamScalars*>(opt_state + 1);
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (4 * i < a.n32) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < pa.world; ++r) {
+      const float4 t = __ldcg(pa.g32[r] + i);
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    float4 p = th32[i], m = m32[i], v = v32[i];
+    const double lr = 4 * i < a.emb_count ? sc.lr[0] : sc.lr[1];
+    adam_one<float>(p.x, g.x, m.x, v.x, lr, sc, a);
+    adam_one<float>(p.y, g.y, m.y, v.y, lr, sc, a);
+    adam_one<float>(p.z, g.z, m.z, v.z, lr, sc, a);
+    adam_one<float>(p.w, g.w, m.w, v.w, lr, sc, a);
+    th32[i] = p; m32[i] = m; v32[i] = v;
+  }
+  if (i <= a.n64) {   // i == n64: the loss rides behind the scale/shift gradients
+    double g = 0.0;
+    for (int r = 0; r < pa.world; ++r) g += __ldcg(pa.g64[r] + i);
+    if (i == a.n64) {
+      loss_out[0] = g;
+    } else {
+      double p = th64[i], m = m64[i], v = v64[i];
+      adam_one<double>(p, g, m, v, i < a.S ? sc.lr[2] : sc.lr[3], sc, a);
+      th64[i] = p; m64[i] = m; v64[i] = v;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace apax
 
@@ -1263,5 +1334,67 @@ extern "C" int apax_train_adam_step(apax_stream_t stream_, const apax_train_plan
   APAX_LAUNCH(k_tr_adam, dim3((unsigned)cdiv(std::max(a.n32 / 4, a.n64), 256)), dim3(256), 0, s, a,
               reinterpret_cast<float4*>(theta32), reinterpret_cast<const float4*>(grad32), reinterpret_cast<float4*>(m32),
               reinterpret_cast<float4*>(v32), theta64, grad64, m64, v64, opt_state);
+  return APAX_OK;
+}
+
+// ---- peer-mapped memory (CUDA IPC) for the fused all-reduce + Adam
+extern "C" int apax_peer_alloc(int64_t bytes, void** dev_ptr, void* ipc_handle_out) {
+  if (bytes <= 0 || !dev_ptr || !ipc_handle_out) return APAX_ERR_INVALID_ARG;
+  void* p = nullptr;
+  APAX_CUDA_TRY(cudaMalloc(&p, size_t(bytes)));
+  APAX_CUDA_TRY(cudaMemset(p, 0, size_t(bytes)));
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
+    g_last_error = cudaGetLastError();
+    cudaFree(p);
+    return APAX_ERR_CUDA;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  *dev_ptr = p;
+  return APAX_OK;
+}
+
+extern "C" int apax_peer_open(const void* ipc_handle, void** dev_ptr) {
+  if (!ipc_handle || !dev_ptr) return APAX_ERR_INVALID_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  APAX_CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return APAX_OK;
+}
+
+extern "C" int apax_peer_close(void* dev_ptr) {
+  if (dev_ptr) APAX_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return APAX_OK;
+}
+
+extern "C" int apax_peer_free(void* dev_ptr) {
+  if (dev_ptr) APAX_CUDA_TRY(cudaFree(dev_ptr));
+  return APAX_OK;
+}
+
+extern "C" int apax_train_allreduce_adam_step(apax_stream_t stream_, const apax_train_plan* p, const apax_train_opt_config* oc,
+                                              const apax_train_peers* peers, uint32_t epoch, float* theta32, double* theta64,
+                                              float* m32, float* v32, double* m64, double* v64, int64_t* opt_state,
+                                              double* loss_out) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  if (!p || !oc || !peers || !theta32 || !theta64 || !m32 || !v32 || !m64 || !v64 || !opt_state || !loss_out)
+    return APAX_ERR_INVALID_ARG;
+  if (peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world || oc->transition_steps < 1)
+    return APAX_ERR_INVALID_ARG;
+  PeerArgs pa{};
+  for (int r = 0; r < peers->world; ++r) {
+    if (!peers->grad32[r] || !peers->grad64[r] || !peers->flags[r]) return APAX_ERR_INVALID_ARG;
+    pa.g32[r] = reinterpret_cast<const float4*>(peers->grad32[r]);
+    pa.g64[r] = peers->grad64[r];
+    pa.flags[r] = peers->flags[r];
+  }
+  pa.world = peers->world; pa.rank = peers->rank; pa.epoch = epoch;
+  AdamArgs a{oc->emb_lr, oc->nn_lr, oc->scale_lr, oc->shift_lr, oc->gradient_clipping, oc->end_value, oc->b1, oc->b2, oc->eps,
+             oc->transition_steps, oc->transition_begin, p->off32[1], p->off32[7], p->off64[2], p->cfg.n_species};
+  APAX_LAUNCH(k_tr_adam_prep, dim3(1), dim3(1), 0, s, a, opt_state);
+  APAX_LAUNCH(k_tr_adam_peer, dim3((unsigned)cdiv(std::max(a.n32 / 4, a.n64 + 1), 256)), dim3(256), 0, s, a, pa,
+              reinterpret_cast<float4*>(theta32), reinterpret_cast<float4*>(m32), reinterpret_cast<float4*>(v32), theta64, m64,
+              v64, opt_state, loss_out);
   return APAX_OK;
 }

@@ -194,6 +194,56 @@ class DeviceBatch:
             self.dev[k].copy_(self.pin[k], non_blocking=True)
 
 
+class PeerGradientBlocks:
+    """Gradient blocks of this rank in CUDA-IPC memory mapped by every peer (one allocation: flag array, then two
+    parities of [fp32 block | fp64 block + loss]) for `apax_train_allreduce_adam_step`.  Handles travel through
+    torch.distributed's object all-gather (host plumbing); the data path afterwards is this library's kernel only."""
+
+    def __init__(self, state: TrainState, dist):
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        if self.world > 8:
+            raise _lib.ApaxB200Error(_lib.ERR_UNSUPPORTED, "PeerGradientBlocks", "at most 8 ranks (one NVSwitch domain)")
+        n32, n64 = state.off32[7], state.grad64.numel()
+        b32 = (n32 * 4 + 255) // 256 * 256
+        self.parity_bytes = b32 + (n64 * 8 + 255) // 256 * 256
+        total = 256 + 2 * self.parity_bytes
+        own, handle = C.c_void_p(), C.create_string_buffer(64)
+        check(lib().apax_peer_alloc(total, C.byref(own), C.cast(handle, C.c_void_p)), "apax_peer_alloc")
+        self.own = own
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        self.mapped = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.mapped.append(own.value)
+            else:
+                ptr = C.c_void_p()
+                hb = C.create_string_buffer(handles[r], 64)
+                check(lib().apax_peer_open(C.cast(hb, C.c_void_p), C.byref(ptr)), "apax_peer_open")
+                self.mapped.append(ptr.value)
+        self.peers = []
+        for parity in range(2):
+            rec = _lib.TrainPeers()
+            for r in range(self.world):
+                base = self.mapped[r] + 256 + parity * self.parity_bytes
+                rec.grad32[r], rec.grad64[r], rec.flags[r] = base, base + b32, self.mapped[r]
+            rec.world, rec.rank = self.world, self.rank
+            self.peers.append(rec)
+        self.local32 = [C.c_void_p(self.peers[q].grad32[self.rank]) for q in range(2)]
+        self.local64 = [C.c_void_p(self.peers[q].grad64[self.rank]) for q in range(2)]
+        self.local_loss = [C.c_void_p(self.peers[q].grad64[self.rank] + 8 * 2 * state.config["n_species"]) for q in range(2)]
+        self.epoch = 0
+        dist.barrier()          # every rank has mapped every block before the first kernel touches one
+
+    def close(self):
+        for r, ptr in enumerate(getattr(self, "mapped", [])):
+            if r != self.rank and ptr:
+                lib().apax_peer_close(C.c_void_p(ptr))
+        if getattr(self, "own", None) is not None and self.own.value:
+            lib().apax_peer_free(self.own)
+        self.mapped, self.own = [], None
+
+
 class TrainStep:
     """update_step of trainer.py:332-336 for one batch shape: loss + gradients, all-reduce over ranks, Adam.
 
@@ -202,7 +252,7 @@ class TrainStep:
     """
 
     def __init__(self, state: TrainState, loss_fn: LossCollection, B: int, nmax: int, pmax: int, graph: bool = False,
-                 world_size: Optional[int] = None):
+                 world_size: Optional[int] = None, fused_allreduce: bool = True):
         import torch.distributed as dist
 
         self.state, self.loss_fn = state, loss_fn
@@ -215,49 +265,67 @@ class TrainStep:
         self.nbytes = lib().apax_train_workspace_bytes(state.plan, n, P, B)
         self.buf = self.ws.get(self.nbytes)
         self.graph = None
+        self.graphs = [None, None]
         self._want_graph = graph
+        # data parallel: all-reduce + Adam in one kernel over NVLink peer memory (default), or NCCL + the plain Adam kernels
+        self.peer = PeerGradientBlocks(state, self.dist) if (self.dist and fused_allreduce) else None
+        self.loss = torch.zeros(1, dtype=torch.float64, device=state.theta32.device) if self.peer else state.loss
 
-    def _grad(self) -> None:
+    def _grad(self, parity: int = 0) -> None:
         st, b = self.state, self.batch
         d = b.dev
         n, P = b.B * b.nmax, b.B * b.pmax
+        if self.peer:
+            g32, g64, loss = self.peer.local32[parity], self.peer.local64[parity], self.peer.local_loss[parity]
+        else:
+            g32, g64, loss = _ptr(st.grad32), _ptr(st.grad64), _ptr(st.loss)
         check(lib().apax_train_loss_and_grad(
             _stream_ptr(), st.plan, _ptr(st.theta32), _ptr(st.theta64), _ptr(d["R"]), _ptr(d["Z"]), _ptr(d["idx"]),
             _ptr(d["offsets"]), _ptr(d["struct_ptr"]), _ptr(d["pair_ptr"]), _ptr(d["n_real"]), b.B, n, P, _ptr(d["E_label"]),
-            _ptr(d["F_label"]), C.byref(self._loss_c), float(b.B * self.world), _ptr(st.loss), _ptr(b.energy), _ptr(b.forces),
-            _ptr(st.grad32), _ptr(st.grad64), C.c_void_p(Workspace.aligned_ptr(self.buf)), C.c_size_t(self.nbytes)),
+            _ptr(d["F_label"]), C.byref(self._loss_c), float(b.B * self.world), loss, _ptr(b.energy), _ptr(b.forces),
+            g32, g64, C.c_void_p(Workspace.aligned_ptr(self.buf)), C.c_size_t(self.nbytes)),
             "apax_train_loss_and_grad")
 
-    def _reduce_and_update(self) -> None:
+    def _reduce_and_update(self, parity: int = 0) -> None:
         st = self.state
+        if self.peer:
+            self.peer.epoch += 1
+            check(lib().apax_train_allreduce_adam_step(
+                _stream_ptr(), st.plan, C.byref(st._opt_c), C.byref(self.peer.peers[parity]), self.peer.epoch, _ptr(st.theta32),
+                _ptr(st.theta64), _ptr(st.m32), _ptr(st.v32), _ptr(st.m64), _ptr(st.v64), _ptr(st.count), _ptr(self.loss)),
+                "apax_train_allreduce_adam_step")
+            return
         if self.dist:   # gradients of the global-batch mean loss: per-rank parts add up (batch_divisor is global)
             allreduce_sum_(self.dist, (st.grad32, st.grad64))
         st.apply_gradients()
 
     def _device_step(self) -> None:
-        self._grad()
-        self._reduce_and_update()
+        parity = (self.peer.epoch & 1) if self.peer else 0
+        self._grad(parity)
+        self._reduce_and_update(parity)
 
     def __call__(self, inputs: dict, labels: dict):
         """Returns (loss tensor [1] f64, predictions {"energy": [B], "forces": [B,Nmax,3]} device tensors)."""
         b = self.batch
         b.upload(flatten_batch(inputs, labels))
         self.run_resident()
-        return self.state.loss, {"energy": b.energy, "forces": b.forces.view(b.B, b.nmax, 3)}
+        return self.loss, {"energy": b.energy, "forces": b.forces.view(b.B, b.nmax, 3)}
 
     def run_resident(self) -> None:
         """One step on the batch already in the device buffers."""
         if not self._want_graph:
             self._device_step()
             return
-        # Single process: the whole step (loss+gradients, Adam) is one graph.  Data parallel: only this library's
-        # kernels are captured; the NCCL all-reduce and the two Adam launches follow eagerly on the same stream.
-        body = self._grad if self.dist else self._device_step
-        if self.graph is None:
+        # Single process: the whole step (loss+gradients, Adam) is one graph.  Data parallel: only the gradient kernels are
+        # captured (one graph per gradient-block parity); the fused all-reduce + Adam kernel (or NCCL + Adam) follows
+        # eagerly on the same stream.
+        parity = (self.peer.epoch & 1) if self.peer else 0
+        body = (lambda: self._grad(parity)) if self.dist else self._device_step
+        if self.graphs[parity] is None:
             st = self.state
             saved = (st.theta32, st.theta64, st.m32, st.v32, st.m64, st.v64, st.count)
             keep = [t.clone() for t in saved]
-            side = torch.cuda.Stream()   # warm up outside the capture (module load, first-touch), then restore the state
+            side = torch.cuda.Stream()   # warm up outside the capture (module load, first touch), then restore the state
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 body()
@@ -265,12 +333,12 @@ class TrainStep:
             torch.cuda.synchronize()
             for t, k in zip(saved, keep):
                 t.copy_(k)
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            self.graphs[parity] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graphs[parity]):
                 body()
-        self.graph.replay()
+        self.graphs[parity].replay()
         if self.dist:
-            self._reduce_and_update()
+            self._reduce_and_update(parity)
 
 
 def make_step_fns(loss_fn: LossCollection, Metrics=None, model=None, is_ensemble: bool = False, graph: bool = False):

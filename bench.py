@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=4096, help="--workload ensemble: number of 128-atom cells (all ranks)")
     ap.add_argument("--ensemble-batch", type=int, default=256, help="--workload ensemble: cells per batch_eval call")
     ap.add_argument("--train-batch", type=int, default=32, help="--workload train: structures per GPU")
+    ap.add_argument("--nccl", action="store_true", help="--workload train, N > 1: NCCL all-reduce instead of the fused peer-memory kernel")
     ap.add_argument("--no-graph", action="store_true", help="--workload train: launch kernels eagerly instead of a CUDA graph")
     ap.add_argument("--verify", action="store_true", help="multi-GPU: compare against a single-GPU evaluation of the whole box")
     return ap.parse_args()

@@ -267,6 +267,28 @@ int apax_train_adam_step(apax_stream_t stream, const apax_train_plan* plan, cons
                          float* theta32, double* theta64, const float* grad32, const double* grad64, float* m32,
                          float* v32, double* m64, double* v64, int64_t* opt_state);
 
+/* Data-parallel update without a library collective: all-reduce + Adam fused in one kernel over NVLink peer memory.
+ * Replaces the gradient all-reduce XLA inserts for the sharded batch (apax/train/trainer.py:101-106) plus
+ * state.apply_gradients (:335).  Every rank allocates its gradient blocks with apax_peer_alloc, publishes the 64-byte IPC
+ * handle to its peers (any host channel), and maps theirs with apax_peer_open.  grad32[r] / grad64[r] / flags[r] are rank
+ * r's fp32 block, fp64 block (scale, shift gradients and, behind them, the step's loss) and flag array (u32 [8], zeroed)
+ * AS MAPPED IN THIS PROCESS.  `epoch` must increase by one per step on every rank, and consecutive steps must use two
+ * alternating sets of gradient blocks (the kernel of step t+1 may start while a peer still reads step t's block).
+ * The gradients are summed in rank order, so all replicas stay bitwise identical; loss_out f64 [1] receives the global loss. */
+typedef struct {
+  const float* grad32[8];
+  const double* grad64[8];
+  uint32_t* flags[8];
+  int32_t world, rank;
+} apax_train_peers;
+int apax_peer_alloc(int64_t bytes, void** dev_ptr, void* ipc_handle_out /* 64 bytes */);
+int apax_peer_open(const void* ipc_handle /* 64 bytes */, void** dev_ptr);
+int apax_peer_close(void* dev_ptr);
+int apax_peer_free(void* dev_ptr);
+int apax_train_allreduce_adam_step(apax_stream_t stream, const apax_train_plan* plan, const apax_train_opt_config* opt_cfg,
+                                   const apax_train_peers* peers, uint32_t epoch, float* theta32, double* theta64, float* m32,
+                                   float* v32, double* m64, double* v64, int64_t* opt_state, double* loss_out);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer convenience context: what ASECalculator.calculate does per call
  * (apax/md/ase_calc.py:357-393): positions/cell on the HOST in, neighbour list (min-image when
