@@ -53,6 +53,10 @@ class TrainPeers(C.Structure):
                 ("rank", C.c_int32)]
 
 
+class HaloPeers(C.Structure):
+    _fields_ = [("rows", C.c_void_p * 8), ("header", C.c_void_p * 8), ("world", C.c_int32), ("rank", C.c_int32)]
+
+
 class MdNvtConfig(C.Structure):
     _fields_ = [("chain_length", C.c_int32), ("chain_steps", C.c_int32), ("sy_steps", C.c_int32), ("dt", C.c_double),
                 ("kT", C.c_double), ("tau", C.c_double)]
@@ -104,6 +108,8 @@ SIGNATURES = {
     "apax_peer_free": (C.c_int, [_P]),
     "apax_train_allreduce_adam_step": (C.c_int, [_P, _P, C.POINTER(TrainOptConfig), C.POINTER(TrainPeers), C.c_uint32, _P, _P, _P, _P,
                                                  _P, _P, _P, _P]),
+    "apax_halo_push_rows": (C.c_int, [_P, _P, _P, _P, C.POINTER(HaloPeers), C.c_uint32]),
+    "apax_halo_pull_add_rows": (C.c_int, [_P, _P, _P, _P, C.POINTER(HaloPeers), C.c_uint32, _P, _P, _I32]),
     "apax_ctx_create": (C.c_int, [_P, _I64, _I64, C.POINTER(_P)]),
     "apax_ctx_destroy": (None, [_P]),
     "apax_ctx_calculate": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, _I32, _P, _P, _P]),

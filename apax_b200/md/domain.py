@@ -155,12 +155,86 @@ def evaluate(dec: SlabDecomposition, halo: HaloExchanger, R_local: torch.Tensor,
     return e, f_owned
 
 
+class PeerHalo:
+    """Halo exchange as this library's own kernels over NVLink peer memory (csrc/halo.cu): the rank's local position and
+    force rows live in one CUDA-IPC block that every peer maps; handles and row offsets are exchanged once through
+    torch.distributed's object all-gather (host plumbing), after which no collective library is on the data path."""
+
+    def __init__(self, dec: SlabDecomposition, group=None):
+        import ctypes as C
+
+        from apax_b200 import _lib
+        from apax_b200 import runtime as rt
+
+        self.C, self.rt, self.lib = C, rt, rt.lib()
+        self.dec = dec
+        world, rank = dec.world, dec.rank
+        n_local, n_owned = dec.n_local, dec.n_owned
+        self.rbytes = (n_local * 24 + 255) // 256 * 256
+        total = 256 + 2 * self.rbytes
+        own, handle = C.c_void_p(), C.create_string_buffer(64)
+        _lib.check(self.lib.apax_peer_alloc(total, C.byref(own), C.cast(handle, C.c_void_p)), "apax_peer_alloc")
+        self.own = own
+        meta = [None] * world
+        dist.all_gather_object(meta, (bytes(handle.raw), n_owned, self.rbytes, list(dec.ghost_owner_counts)), group=group)
+        self.mapped = []
+        for r in range(world):
+            if r == rank:
+                self.mapped.append(own.value)
+            else:
+                ptr = C.c_void_p()
+                hb = C.create_string_buffer(meta[r][0], 64)
+                _lib.check(self.lib.apax_peer_open(C.cast(hb, C.c_void_p), C.byref(ptr)), "apax_peer_open")
+                self.mapped.append(ptr.value)
+        self.fwd, self.rev = _lib.HaloPeers(), _lib.HaloPeers()
+        for rec in (self.fwd, self.rev):
+            rec.world, rec.rank = world, rank
+        for r in range(world):
+            _, n_owned_r, rbytes_r, goc_r = meta[r]
+            assert goc_r[rank] == dec.send_counts[r], "inconsistent decomposition between ranks"
+            row0 = n_owned_r + sum(goc_r[:rank])            # ghosts are grouped by owner rank, ascending
+            self.fwd.header[r] = self.rev.header[r] = self.mapped[r]
+            if dec.send_counts[r] > 0:
+                self.fwd.rows[r] = self.mapped[r] + 256 + 24 * row0
+                self.rev.rows[r] = self.mapped[r] + 256 + rbytes_r + 24 * row0
+        self.R = rt.device_view(own.value + 256, (n_local, 3), torch.float64)
+        self.F = rt.device_view(own.value + 256 + self.rbytes, (1, n_local, 3), torch.float64)
+        self.send_local = dec.send_local.to(torch.int64).contiguous()
+        self.send_ptr = np.concatenate([[0], np.cumsum(dec.send_counts)]).astype(np.int64)
+        self.e_global = torch.zeros(1, dtype=torch.float64, device=self.R.device)
+        self.epoch = 0
+        self.bytes_per_step = 2 * int(self.send_ptr[-1] + sum(dec.ghost_owner_counts)) * 24
+        dist.barrier(group=group)        # every block is mapped everywhere before the first kernel touches one
+
+    def forward(self) -> None:
+        self.epoch += 1
+        C, rt = self.C, self.rt
+        rt.check(self.lib.apax_halo_push_rows(rt._stream_ptr(), rt._ptr(self.R), rt._ptr(self.send_local),
+                                              self.send_ptr.ctypes.data_as(C.c_void_p), C.byref(self.fwd), self.epoch),
+                 "apax_halo_push_rows")
+
+    def reverse(self, e_local: torch.Tensor):
+        C, rt = self.C, self.rt
+        rt.check(self.lib.apax_halo_pull_add_rows(rt._stream_ptr(), rt._ptr(self.F), rt._ptr(self.send_local),
+                                                  self.send_ptr.ctypes.data_as(C.c_void_p), C.byref(self.rev), self.epoch,
+                                                  rt._ptr(e_local), rt._ptr(self.e_global), 1), "apax_halo_pull_add_rows")
+        return self.e_global, self.F[0, : self.dec.n_owned]
+
+    def close(self):
+        for r, ptr in enumerate(getattr(self, "mapped", [])):
+            if r != self.dec.rank and ptr:
+                self.lib.apax_peer_close(self.C.c_void_p(ptr))
+        if getattr(self, "own", None) is not None and self.own.value:
+            self.lib.apax_peer_free(self.own)
+        self.mapped, self.own = [], None
+
+
 # --------------------------------------------------------------------------------------------- GPU driver
 class GpuSlabSystem:
     """Owned + ghost atoms of this rank on its GPU, evaluated through the C ABI."""
 
     def __init__(self, params, frac_global: np.ndarray, Z_global: np.ndarray, box: np.ndarray, cutoff: float,
-                 rank: int, world: int, group=None):
+                 rank: int, world: int, group=None, peer_halo: bool = True):
         from apax_b200 import runtime as rt
 
         self.rt = rt
@@ -175,6 +249,12 @@ class GpuSlabSystem:
         self.Z_local = torch.as_tensor(Z_global, dtype=torch.int32, device=dev)[ids].contiguous()
         self.halo = HaloExchanger(self.dec, group)
         self.group = group
+        # default on GPUs: the halo exchange runs as this library's kernels over NVLink peer memory; the NCCL
+        # all_to_all path (HaloExchanger) stays as the comparison and for shallow ensembles (n_out > 1)
+        self.peer = PeerHalo(self.dec, group) if (peer_halo and world > 1 and params.n_out == 1) else None
+        if self.peer:
+            self.peer.R.copy_(self.R_local)
+            self.R_local = self.peer.R
         self.system = None
         self.build_list()
         del frac
@@ -192,13 +272,24 @@ class GpuSlabSystem:
         idx = idx[:, idx[1] < self.dec.n_owned].contiguous()
         self.n_pairs = int(idx.shape[1])
         ws = self.system.ws if self.system is not None else None
-        self.system = rt.PreparedSystem(self.params, self.Z_local, idx, n_central=self.dec.n_owned, workspace=ws)
+        self.system = rt.PreparedSystem(self.params, self.Z_local, idx, n_central=self.dec.n_owned, workspace=ws,
+                                        forces=self.peer.F if self.peer else None)
 
     def local_compute(self, R_local, n_central):
         e, f = self.system.compute(R_local, self.box, None, "minimage")
         return e, f[0]
 
+    def forward_halo(self):
+        if self.peer:
+            self.peer.forward()
+        else:
+            self.halo.forward(self.R_local)
+
     def step(self):
+        if self.peer:
+            self.peer.forward()
+            e_local, _ = self.system.compute(self.R_local, self.box, None, "minimage")
+            return self.peer.reverse(e_local)
         return evaluate(self.dec, self.halo, self.R_local, self.local_compute, self.group)
 
 
@@ -220,7 +311,7 @@ def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: 
     params = syn.gmnn_params(seed=1234)
     dp = rt.DeviceParams(params)
     frac = pos @ np.linalg.inv(cell)
-    sysm = GpuSlabSystem(dp, frac, Z, cell.T.copy(), 6.0, rank, world)
+    sysm = GpuSlabSystem(dp, frac, Z, cell.T.copy(), 6.0, rank, world, peer_halo=not getattr(args, "nccl", False))
     lib = rt.lib()
     sampler = None
     if rank == 0:
@@ -256,7 +347,7 @@ def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: 
 
     def e2e_step():
         sysm.R_local[:n_owned].copy_(h_pos, non_blocking=True)
-        sysm.halo.forward(sysm.R_local)
+        sysm.forward_halo()
         sysm.build_list()
         e_, f_ = sysm.step()
         h_f.copy_(f_, non_blocking=True)
@@ -309,7 +400,8 @@ def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: 
             "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[3]: GMNN default energy+forces, periodic water box, r_max=6 A, "
-                                   "slab domain decomposition, forward/reverse halo exchange + energy all-reduce over NCCL",
+                                   "slab domain decomposition, forward/reverse halo exchange + energy sum " +
+                                   ("as this library's kernels over NVLink peer memory (CUDA IPC)" if sysm.peer else "over NCCL"),
                        "atoms": n, "parallelism": f"{world} slabs along x", "energy": float(e.cpu()[0]),
                        "per_rank_owned_ghost_pairs_halobytes": per_rank,
                        "l2": "working set per step far exceeds the 126 MB L2"},

@@ -166,7 +166,7 @@ class PreparedSystem:
     """A neighbour list prepared once (apax_gm_prepare) and evaluated many times (apax_gm_compute)."""
 
     def __init__(self, params: DeviceParams, Z, idx, n_atoms: Optional[int] = None, n_central: Optional[int] = None,
-                 workspace: Optional[Workspace] = None):
+                 workspace: Optional[Workspace] = None, forces: Optional[torch.Tensor] = None):
         self.params = params
         self.n_central = n_central
         self.Z = to_device(Z, torch.int32)
@@ -179,7 +179,9 @@ class PreparedSystem:
                                     self.wp, self.wb), "apax_gm_prepare")
         dev = self.Z.device
         self.energy = torch.empty(params.n_out, dtype=torch.float64, device=dev)
-        self.forces = torch.empty((params.n_out, self.n_atoms, 3), dtype=torch.float64, device=dev)
+        # `forces` may be caller-provided memory (e.g. a peer-mapped block for the NVLink halo exchange)
+        self.forces = forces if forces is not None else torch.empty((params.n_out, self.n_atoms, 3), dtype=torch.float64, device=dev)
+        assert tuple(self.forces.shape) == (params.n_out, self.n_atoms, 3) and self.forces.dtype == torch.float64
 
     def compute(self, R: torch.Tensor, box: Optional[torch.Tensor], offsets: Optional[torch.Tensor], mode: str,
                 forces: bool = True):
@@ -342,6 +344,19 @@ class HostContext:
             self.close()
         except Exception:
             pass
+
+
+class _CudaView:
+    """__cuda_array_interface__ carrier: lets torch view device memory this library allocated (apax_peer_alloc)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def device_view(ptr: int, shape, dtype: torch.dtype) -> torch.Tensor:
+    typestr = {torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
+    return torch.as_tensor(_CudaView(ptr, shape, typestr), device=_require_cuda())
 
 
 def profile_kernels(fn, max_records: int = 4096):

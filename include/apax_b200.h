@@ -289,6 +289,30 @@ int apax_train_allreduce_adam_step(apax_stream_t stream, const apax_train_plan* 
                                    const apax_train_peers* peers, uint32_t epoch, float* theta32, double* theta64, float* m32,
                                    float* v32, double* m64, double* v64, int64_t* opt_state, double* loss_out);
 
+/* Halo exchange of the slab-decomposed evaluation (apax_gm_compute_partial) as kernels over NVLink peer memory; no
+ * counterpart in the reference, which is single-device (apax/md/simulate.py:313-354).  Every rank keeps, in one
+ * apax_peer_alloc block mapped by its peers: a 256-byte zeroed header, then its local position rows and its local force
+ * rows (f64 [n_local][3], owned atoms first, then ghosts grouped by owner rank).  `header[r]` is rank r's header and
+ * `rows[r]` the first row, inside rank r's block, of the ghosts that THIS rank owns -- both as mapped in this process
+ * (forward: in r's position rows; reverse: in r's force rows).  send_local i64 [n_send] (device) lists this rank's owned
+ * atoms that are ghosts elsewhere, grouped by destination rank; send_ptr_host i64 [world+1] (host) delimits the groups.
+ * `epoch` increases by one per evaluation on every rank.
+ *   apax_halo_push_rows     : positions of my boundary atoms -> the ghost rows of my neighbours; returns (on the stream)
+ *                             once every peer's rows have landed here as well.
+ *   apax_halo_pull_add_rows : waits until every peer's forces are complete, then adds to my owned atoms the contributions
+ *                             they received as ghosts elsewhere (rank order, deterministic) and sums the ranks' partial
+ *                             energies (energy_local / energy_global f64 [n_out], device). */
+typedef struct {
+  double* rows[8];
+  uint32_t* header[8];
+  int32_t world, rank;
+} apax_halo_peers;
+int apax_halo_push_rows(apax_stream_t stream, const double* local_rows, const int64_t* send_local,
+                        const int64_t* send_ptr_host, const apax_halo_peers* peers, uint32_t epoch);
+int apax_halo_pull_add_rows(apax_stream_t stream, double* local_rows, const int64_t* send_local,
+                            const int64_t* send_ptr_host, const apax_halo_peers* peers, uint32_t epoch,
+                            const double* energy_local, double* energy_global, int32_t n_out);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer convenience context: what ASECalculator.calculate does per call
  * (apax/md/ase_calc.py:357-393): positions/cell on the HOST in, neighbour list (min-image when
