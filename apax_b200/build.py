@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libapax_b200.so")
-SOURCES = ["common.cu", "gm.cu", "nl.cu", "ctx.cu", "tc_gemm.cu", "i8_gemm.cu", "md.cu", "train.cu", "halo.cu"]
+SOURCES = ["common.cu", "gm.cu", "nl.cu", "ctx.cu", "tc_gemm.cu", "i8_gemm.cu", "md.cu", "train.cu", "halo.cu", "ensemble.cu"]
 HEADERS = ["common.cuh", "tc_gemm.cuh", "tc_ptx.cuh", "i8_gemm.cuh", "gm_internal.cuh", "nl_internal.cuh", "contract_gen.cuh", "gen_contract.py",
            os.path.join("..", "..", "include", "apax_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -99,24 +99,35 @@ class ASECalculator:
                     break
                 cap = int(nf * self.padding_factor) + 1024      # "neighbor list overflowed, extending."
             e, f = rt.energy_forces_batched(dp, pos, num, idx[:, :nf].contiguous(), offsets[:nf].contiguous(), ptr)
-            torch.cuda.synchronize()
-            e, f = e.cpu().numpy(), f.cpu().numpy()
             n_ens = dp.n_out
             if n_ens == 1:
+                torch.cuda.synchronize()
+                e, f = e.cpu().numpy(), f.cpu().numpy()
                 for b in range(len(chunk)):
                     results.append({"energy": float(e[b, 0]), "forces": f[0, ptr[b]:ptr[b + 1]]})
                 continue
-            # ensemble statistics for the whole chunk at once (models.py:225-233, 256-263), sliced per structure afterwards
-            e_mean = e.mean(axis=1)
-            e_unc = np.sqrt(((e - e_mean[:, None]) ** 2).sum(axis=1) / (n_ens - 1))
-            fm = f.mean(axis=0)
-            f_unc = np.sqrt(((f - fm) ** 2).sum(axis=0) / (n_ens - 1))
-            f_ens = np.ascontiguousarray(np.transpose(f, (1, 2, 0)))
+            # ensemble statistics (models.py:221-263) for the whole chunk in one kernel pair on the device, results through
+            # pinned staging buffers, sliced per structure afterwards
+            stats = rt.ensemble_stats(e, f)
+            host = [self._to_host(nm, t) for nm, t in zip(("e", "e_mean", "e_unc", "f_mean", "f_unc", "f_ens"), (e,) + stats)]
+            torch.cuda.synchronize()
+            e_h, e_mean, e_unc, fm, f_unc, f_ens = [h.numpy().copy() for h in host]
             for b in range(len(chunk)):
                 sl = slice(ptr[b], ptr[b + 1])
-                results.append({"energy": float(e_mean[b]), "energy_ensemble": e[b], "energy_uncertainty": float(e_unc[b]),
+                results.append({"energy": float(e_mean[b]), "energy_ensemble": e_h[b], "energy_uncertainty": float(e_unc[b]),
                                 "forces": fm[sl], "forces_uncertainty": f_unc[sl], "forces_ensemble": f_ens[sl]})
         return results
+
+    def _to_host(self, name: str, t):
+        """Device tensor -> pinned host staging buffer (cached per name and shape), asynchronously on the current stream."""
+        import torch
+
+        cache = self.__dict__.setdefault("_pinned", {})
+        key = (name, tuple(t.shape), t.dtype)
+        if key not in cache:
+            cache[key] = torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory()
+        cache[key].copy_(t, non_blocking=True)
+        return cache[key]
 
     def get_potential_energy(self, atoms):
         return self.calculate(atoms)["energy"]

@@ -293,6 +293,22 @@ def energy_forces_batched(params: DeviceParams, R, Z, idx, offsets, struct_ptr, 
     return energy, F
 
 
+def ensemble_stats(energy_ens: torch.Tensor, forces_ens: torch.Tensor, want_ensemble: bool = True):
+    """ShallowEnsembleModel statistics (apax/nn/models.py:221-263) on the device: energy_ens [B, n_ens], forces_ens
+    [n_ens, N, 3] -> (e_mean [B], e_unc [B], f_mean [N,3], f_unc [N,3], forces_ensemble [N,3,n_ens] or None)."""
+    dev = _require_cuda()
+    b, n_ens = int(energy_ens.shape[0]), int(energy_ens.shape[1])
+    n = int(forces_ens.shape[1])
+    e_mean = torch.empty(b, dtype=torch.float64, device=dev)
+    e_unc = torch.empty(b, dtype=torch.float64, device=dev)
+    f_mean = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    f_unc = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    f_t = torch.empty((n, 3, n_ens), dtype=torch.float64, device=dev) if want_ensemble else None
+    check(lib().apax_ensemble_stats(_stream_ptr(), _ptr(energy_ens.contiguous()), _ptr(forces_ens.contiguous()), b, n, n_ens,
+                                    _ptr(e_mean), _ptr(e_unc), _ptr(f_mean), _ptr(f_unc), _ptr(f_t)), "apax_ensemble_stats")
+    return e_mean, e_unc, f_mean, f_unc, f_t
+
+
 def nl_needs_rebuild(frac, ref, box, dr_threshold: float) -> torch.Tensor:
     dev = _require_cuda()
     frac = to_device(frac, torch.float64)

@@ -264,7 +264,6 @@ class TrainStep:
         n, P = B * nmax, B * pmax
         self.nbytes = lib().apax_train_workspace_bytes(state.plan, n, P, B)
         self.buf = self.ws.get(self.nbytes)
-        self.graph = None
         self.graphs = [None, None]
         self._want_graph = graph
         # data parallel: all-reduce + Adam in one kernel over NVLink peer memory (default), or NCCL + the plain Adam kernels
@@ -310,6 +309,25 @@ class TrainStep:
         b.upload(flatten_batch(inputs, labels))
         self.run_resident()
         return self.loss, {"energy": b.energy, "forces": b.forces.view(b.B, b.nmax, 3)}
+
+    def evaluate(self, inputs: dict, labels: dict):
+        """calc_loss without the update (the reference's val_step): returns (loss [1] f64, predictions), summed over ranks."""
+        b = self.batch
+        b.upload(flatten_batch(inputs, labels))
+        parity = (self.peer.epoch & 1) if self.peer else 0
+        self._grad(parity)
+        if self.peer:   # this rank's share of the loss sits behind its fp64 gradient block
+            loss = self.rt_view_loss(parity).clone()
+        else:
+            loss = self.state.loss.clone()
+        if self.dist:
+            self.dist.all_reduce(loss)
+        return loss, {"energy": b.energy, "forces": b.forces.view(b.B, b.nmax, 3)}
+
+    def rt_view_loss(self, parity: int) -> torch.Tensor:
+        from ..runtime import device_view
+
+        return device_view(self.peer.local_loss[parity].value, (1,), torch.float64)
 
     def run_resident(self) -> None:
         """One step on the batch already in the device buffers."""
@@ -362,6 +380,9 @@ def make_step_fns(loss_fn: LossCollection, Metrics=None, model=None, is_ensemble
         return (state, batch_metrics), loss
 
     def val_step(state, batch, batch_metrics=None):
-        raise NotImplementedError("validation = model.apply on the batch: use apax_b200.md.ase_calc / runtime.energy_forces_batched")
+        """eval_fn of the reference (trainer.py:340-344, 360-370): loss and predictions of the batch, no update."""
+        inputs, labels = batch
+        loss, pred = _get(state, inputs).evaluate(inputs, labels)
+        return loss, batch_metrics, pred
 
     return train_step, val_step

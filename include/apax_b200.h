@@ -127,6 +127,14 @@ int apax_gm_energy_forces_batched(apax_stream_t stream, const apax_gm_params* pa
                                   const int32_t* struct_ptr, int64_t n_structs, int64_t n_atoms, int64_t n_pairs,
                                   double* energy, double* forces, void* workspace, size_t workspace_bytes);
 
+/* Shallow-ensemble statistics.  Replaces the tail of ShallowEnsembleModel.__call__ (apax/nn/models.py:221-263) for the
+ * outputs of apax_gm_energy_forces(_batched) with n_out = n_ens heads: energy_ens f64 [n_structs][n_ens], forces_ens f64
+ * [n_ens][n_atoms][3] -> e_mean, e_unc f64 [n_structs] (unbiased: divisor 1/(n_ens-1)), f_mean, f_unc f64 [n_atoms][3],
+ * and f_ens_t f64 [n_atoms][3][n_ens] (`forces_ensemble`; may be NULL). */
+int apax_ensemble_stats(apax_stream_t stream, const double* energy_ens, const double* forces_ens, int64_t n_structs,
+                        int64_t n_atoms, int32_t n_ens, double* e_mean, double* e_unc, double* f_mean, double* f_unc,
+                        double* f_ens_t);
+
 /* Domain-decomposed evaluation (no counterpart in the reference, which is single-device:
  * apax/md/simulate.py:313-354).  Atoms [0, n_central) are this rank's owned atoms and are the only
  * centrals (rows of the prepared list); atoms [n_central, n_atoms) are ghosts that only act as

@@ -1,0 +1,40 @@
+"""Multi-GPU paths on a box with at least two GPUs (skipped otherwise; the CPU twins are tests/test_domain_gloo.py and
+tests/test_train_dp_gloo.py): the slab-decomposed E+F with the halo exchange over NVLink peer memory against a single-GPU
+evaluation of the same box, and the data-parallel training step with the fused all-reduce + Adam kernel against NCCL."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+needs_two = pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+
+
+def _torchrun(port, *bench_args, timeout=240):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--gpus", "2", *bench_args]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+@needs_two
+@pytest.mark.parametrize("extra", [(), ("--nccl",)])
+def test_slab_decomposition_matches_single_gpu(extra):
+    line = _torchrun(29611 + len(extra), "--molecules", "20000", "--steps", "2", "--warmup", "3", "--verify", *extra)
+    assert line["n_gpus"] == 2
+    assert line["verify"]["energy_rel_err"] <= 1e-9
+    assert line["verify"]["max_force_violation_x_tolerance"] <= 1.5
+
+
+@needs_two
+def test_fused_allreduce_adam_matches_nccl_and_keeps_replicas_identical():
+    line = _torchrun(29621, "--workload", "train", "--steps", "20", "--warmup", "3", "--no-cpu-baseline", "--verify")
+    v = line["verify"]
+    assert v["replicas_bitwise_identical"]
+    assert v["max_abs_diff_theta32_fused_vs_nccl"] <= 1e-6 and abs(v["loss_fused"] - v["loss_nccl"]) <= 1e-6 * abs(v["loss_nccl"])

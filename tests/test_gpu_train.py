@@ -198,3 +198,24 @@ def test_bitwise_reproducible_and_rank_partition_adds_up():
     for k in NAMES:
         s = halves[0][3][k] + halves[1][3][k]
         assert np.abs(s - g1[k]).max() <= 2e-6 * (np.abs(g1[k]).max() + 1e-30), k
+
+
+def test_val_step_returns_loss_without_updating():
+    from apax_b200.optimizer.get_optimizer import get_opt
+    from apax_b200.train.loss import Loss, LossCollection
+    from apax_b200.train.trainer import TrainState, make_step_fns
+    from oracle import train_oracle as tor
+
+    inputs, labels = tor.ethanol_training_batch(4, seed=3)
+    params = syn.gmnn_params(seed=12, random_bias=True)
+    ref = tor.loss_and_grads(params, inputs, labels)
+    state = TrainState(params, get_opt(params, 1, 10))
+    train_step, val_step = make_step_fns(LossCollection([Loss("energy", "mse", 1.0, 1.0), Loss("forces", "mse", 4.0, 1.0)]))
+    before = state.theta32.clone()
+    loss, _, pred = val_step(state, (inputs, labels))
+    assert abs(float(loss.item()) - ref["loss"]) <= 2e-6 * abs(ref["loss"])
+    assert torch.equal(before, state.theta32) and state.step == 0
+    assert np.abs(pred["forces"].cpu().numpy() - ref["forces"]).max() <= 1e-5 * np.abs(ref["forces"]).max() + 1e-6
+    (state, _), loss2 = train_step((state, None), (inputs, labels))
+    assert state.step == 1 and not torch.equal(before, state.theta32)
+    assert abs(float(loss2.item()) - ref["loss"]) <= 2e-6 * abs(ref["loss"])
