@@ -113,3 +113,21 @@ def test_runtime_fails_loudly_without_gpu():
 
     with pytest.raises(_lib.ApaxB200Error):
         runtime.DeviceParams(syn.gmnn_params())
+
+
+def test_xla_ffi_shim_is_gated_on_jax():
+    """The XLA-FFI layer cannot be compiled without jaxlib's headers; it must say so instead of failing obscurely, and its
+    handlers must cover the C entry points they claim to."""
+    import os
+
+    from apax_b200.ffi import build_ffi as bf
+
+    src = open(os.path.join(os.path.dirname(bf.__file__), "xla_ffi_shim.cc")).read()
+    for fn in ("apax_gm_energy_forces", "apax_gm_descriptor", "apax_nl_build_minimage", "apax_nl_needs_rebuild",
+               "apax_train_loss_and_grad"):
+        assert fn + "(" in src
+    try:
+        import jax  # noqa: F401
+    except Exception:
+        with pytest.raises(bf.FfiUnavailable):
+            bf.build_ffi()
