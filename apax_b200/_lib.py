@@ -34,6 +34,7 @@ class GmConfig(C.Structure):
         ("n_species", C.c_int32), ("n_radial", C.c_int32), ("n_basis", C.c_int32), ("n_contr", C.c_int32),
         ("n_hidden1", C.c_int32), ("n_hidden2", C.c_int32), ("n_out", C.c_int32), ("use_ntk", C.c_int32),
         ("use_embed_norm", C.c_int32), ("mask_atoms", C.c_int32), ("r_min", C.c_float), ("r_max", C.c_float),
+        ("basis_kind", C.c_int32),
     ]
 
 
@@ -101,6 +102,7 @@ SIGNATURES = {
     "apax_train_workspace_bytes": (C.c_size_t, [_P, _I64, _I64, _I64]),
     "apax_train_loss_and_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P,
                                            C.POINTER(TrainLossConfig), C.c_double, _P, _P, _P, _P, _P, _P, C.c_size_t]),
+    "apax_train_energy_forces": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, C.c_size_t]),
     "apax_train_adam_step": (C.c_int, [_P, _P, C.POINTER(TrainOptConfig), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "apax_peer_alloc": (C.c_int, [_I64, C.POINTER(_P), _P]),
     "apax_peer_open": (C.c_int, [_P, C.POINTER(_P)]),

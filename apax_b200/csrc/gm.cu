@@ -1248,6 +1248,7 @@ static int validate_cfg(const apax_gm_config* c) {
     return APAX_ERR_UNSUPPORTED;
   if (c->n_out < 1 || c->n_out > MAX_OUT || c->n_species < 1 || c->n_species > 128) return APAX_ERR_UNSUPPORTED;
   if (!(c->r_max > c->r_min) || !(c->r_min >= 0.f)) return APAX_ERR_INVALID_ARG;
+  if (c->basis_kind != 0) return APAX_ERR_UNSUPPORTED;   // other radial bases: apax_train_energy_forces
   return APAX_OK;
 }
 

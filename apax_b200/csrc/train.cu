@@ -142,9 +142,13 @@ struct Tables {
   const int32_t* o_pack;    // f | o1 << 16 | o2 << 24
 };
 
+constexpr int MAXNB = 16;        // basis functions per radial channel: 7 Gaussians by default, Bessel's config default is 16
+enum { BASIS_GAUSS_LINEAR = 0, BASIS_GAUSS_EXP = 1, BASIS_BESSEL = 2 };
+
 struct DescConstT {
   float r_max, beta, norm, two_beta, pi_f, inv_sqrt_nb;
-  float mu[NB];
+  int nb, kind;
+  float mu[MAXNB];   // Gaussian centres; Bessel: prefactors a_n b_n (basis_functions.py:74-75)
 };
 
 }  // namespace
@@ -171,7 +175,7 @@ struct TrWs {
   int32_t *rowp, *trowp;          // [P] COO positions grouped by central atom / by neighbour atom
   float4* geo;                    // [P] (dx,dy,dz, species-pair key as int bits); w < 0: dropped entry
   float4* Q;                      // [P] per-pair force contribution
-  float* cbar;                    // [P][35] per-pair embedding-gradient contributions
+  float* cbar;                    // [P][5 n_basis] per-pair embedding-gradient contributions
   int32_t* present;               // [128] species present, [128] ticket of the loss reduction
   float *M, *Md, *Mdb, *Mb2;      // [n][100]
   float *GS, *GB;                 // [2n][360]
@@ -184,14 +188,14 @@ struct TrWs {
   double* loss_s;                 // [B]
 };
 
-size_t carve_tr(void* base, int64_t n, int64_t P, int64_t B, TrWs* w) {
+size_t carve_tr(void* base, int64_t n, int64_t P, int64_t B, int nb, TrWs* w) {
   Carver c(base);
   TrWs t{};
   t.n = n; t.P = P; t.B = B;
   t.rs = c.take<int32_t>(n); t.re = c.take<int32_t>(n); t.ts = c.take<int32_t>(n); t.te = c.take<int32_t>(n);
   t.rowp = c.take<int32_t>(P); t.trowp = c.take<int32_t>(P);
   t.geo = c.take<float4>(P); t.Q = c.take<float4>(P);
-  t.cbar = c.take<float>(P * 35);
+  t.cbar = c.take<float>(P * NR * nb);
   t.present = c.take<int32_t>(132);
   t.M = c.take<float>(n * NPK); t.Md = c.take<float>(n * NPK); t.Mdb = c.take<float>(n * NPK); t.Mb2 = c.take<float>(n * NPK);
   t.GS = c.take<float>(2 * n * NF); t.GB = c.take<float>(2 * n * NF);
@@ -280,8 +284,8 @@ __global__ void __launch_bounds__(128) k_tr_group(const int32_t* __restrict__ id
 struct PairT {
   float r, inv_re;        // |d|, 1/(r + 1e-5)
   float n[3];             // d / (r + 1e-5)     (gaussian_moment_descriptor.py:46-48)
-  float G[NB], dG[NB];    // Gaussian basis and d/dr (basis_functions.py:19-56)
-  float fc, dfc;          // cosine cutoff and d/dr (basis_functions.py:82-85; zero slope beyond r_max)
+  float G[MAXNB], dG[MAXNB];   // radial basis and d/dr (basis_functions.py:19-79)
+  float fc, dfc;               // cosine cutoff and d/dr (basis_functions.py:82-85; zero slope beyond r_max)
 };
 
 __device__ __forceinline__ void pair_terms(const float4 g, const DescConstT& dc, PairT& t) {
@@ -289,11 +293,41 @@ __device__ __forceinline__ void pair_terms(const float4 g, const DescConstT& dc,
   t.r = r2 > 0.f ? sqrtf(r2) : 0.f;                      // space.distance / safe_mask (space.py:314-323)
   t.inv_re = 1.0f / (t.r + 1e-5f);
   t.n[0] = g.x * t.inv_re; t.n[1] = g.y * t.inv_re; t.n[2] = g.z * t.inv_re;
+  if (dc.kind == BASIS_BESSEL) {
+    // BesselBasis (basis_functions.py:59-79): a_n b_n (sinc((n+1) r/rc) + sinc((n+2) r/rc)), jnp.sinc(z) = sin(pi z)/(pi z);
+    // d/dr sinc(k r/rc) = (cos(pi k r/rc) - sinc(k r/rc)) / r
+    float sk[MAXNB + 1], dk[MAXNB + 1];
 #pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    const float dm = dc.mu[b] - t.r;
-    t.G[b] = dc.norm * expf(-dc.beta * (dm * dm));
-    t.dG[b] = t.G[b] * dc.two_beta * dm;
+    for (int k = 0; k <= MAXNB; ++k) {
+      if (k <= dc.nb) {
+        const float y = dc.pi_f * (float(k + 1) * t.r / dc.r_max);
+        float sn, cs;
+        sincosf(y, &sn, &cs);
+        sk[k] = y != 0.f ? sn / y : 1.0f;
+        dk[k] = t.r > 0.f ? (cs - sk[k]) / t.r : 0.f;
+      } else {
+        sk[k] = 0.f; dk[k] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < MAXNB; ++b) {
+      t.G[b] = b < dc.nb ? dc.mu[b] * (sk[b] + sk[b + 1]) : 0.f;
+      t.dG[b] = b < dc.nb ? dc.mu[b] * (dk[b] + dk[b + 1]) : 0.f;
+    }
+  } else {
+    // GaussianBasis: exp(-beta (mu_b - s(r))^2) with s(r) = r (linear spacing) or exp(-r) (exponential, :29-37)
+    const float x = dc.kind == BASIS_GAUSS_EXP ? expf(-t.r) : t.r;
+    const float dxdr = dc.kind == BASIS_GAUSS_EXP ? -x : 1.0f;
+#pragma unroll
+    for (int b = 0; b < MAXNB; ++b) {
+      if (b < dc.nb) {
+        const float dm = dc.mu[b] - x;
+        t.G[b] = dc.norm * expf(-dc.beta * (dm * dm));
+        t.dG[b] = t.G[b] * dc.two_beta * dm * dxdr;
+      } else {
+        t.G[b] = 0.f; t.dG[b] = 0.f;
+      }
+    }
   }
   if (t.r < dc.r_max) {
     float sn, cs;
@@ -332,15 +366,17 @@ __device__ __forceinline__ void monomial_grads(const float (&n)[3], float (&gx)[
 // radial channels: rho_r = (sum_b c_rb G_b) * fc,  drho_r/dr;  c = (1/sqrt(n_basis)) * W[Z_central, Z_neighbour]
 __device__ __forceinline__ void radial(const float* __restrict__ emb, int key, const DescConstT& dc, const PairT& t,
                                        float (&rho)[NR], float (&drho)[NR]) {
-  const float* c = emb + int64_t(key) * (NR * NB);
+  const float* c = emb + int64_t(key) * (NR * dc.nb);
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     float s = 0.f, ds = 0.f;
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const float cb = dc.inv_sqrt_nb * c[r * NB + b];
-      s += cb * t.G[b];
-      ds += cb * t.dG[b];
+    for (int b = 0; b < MAXNB; ++b) {
+      if (b < dc.nb) {
+        const float cb = dc.inv_sqrt_nb * c[r * dc.nb + b];
+        s += cb * t.G[b];
+        ds += cb * t.dG[b];
+      }
     }
     rho[r] = s * t.fc;
     drho[r] = ds * t.fc + s * t.dfc;
@@ -779,6 +815,7 @@ __global__ void __launch_bounds__(128) k_tr_forces_loss(TrWs w, const int32_t* _
     }
     if (lane == 0) {
       F_out[3 * int64_t(a) + 0] = f0; F_out[3 * int64_t(a) + 1] = f1; F_out[3 * int64_t(a) + 2] = f2;
+      if (!F_lab) continue;   // energy + forces only (apax_train_energy_forces)
       const double e0 = f0 - F_lab[3 * int64_t(a) + 0], e1 = f1 - F_lab[3 * int64_t(a) + 1], e2 = f2 - F_lab[3 * int64_t(a) + 2];
       w.u[3 * int64_t(a) + 0] = 2.0 * cF * e0; w.u[3 * int64_t(a) + 1] = 2.0 * cF * e1; w.u[3 * int64_t(a) + 2] = 2.0 * cF * e2;
       acc += cF * (e0 * e0 + e1 * e1 + e2 * e2);
@@ -790,14 +827,14 @@ __global__ void __launch_bounds__(128) k_tr_forces_loss(TrWs w, const int32_t* _
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && E_lab) {
     const double dE = w.Es[s] - E_lab[s];
     w.alpha[s] = 2.0 * cE * dE;
     w.cF[s] = cF;
     w.loss_s[s] = red[0] + cE * dE * dE;
     // the last block to get here adds the per-structure losses up in index order (deterministic)
     __threadfence();
-    if (atomicAdd(w.present + 128, 1) == int(gridDim.x) - 1) {
+    if (atomicAdd(w.present + 128, 1) == int(gridDim.x) - 1 && loss) {
       __threadfence();
       const volatile double* ls = w.loss_s;
       double acc = 0.0;
@@ -927,7 +964,7 @@ __global__ void __launch_bounds__(64) k_tr_emb_pair(TrWs w, const int32_t* __res
     monomials20(pt.n, mono);
     monomial_grads(pt.n, gx, gy, gz);
     pair_tangent(g, pt, w.u, a, idx[p], rdot, nd);
-    float* out = w.cbar + int64_t(p) * 35;
+    float* out = w.cbar + int64_t(p) * (NR * dc.nb);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       float rb = 0.f, rdb = 0.f;
@@ -938,8 +975,9 @@ __global__ void __launch_bounds__(64) k_tr_emb_pair(TrWs w, const int32_t* __res
         rdb += A2[r * 20 + k] * mono[k];
       }
 #pragma unroll
-      for (int b = 0; b < NB; ++b)
-        out[r * NB + b] = dc.inv_sqrt_nb * (rb * pt.fc * pt.G[b] + rdb * rdot * (pt.fc * pt.dG[b] + pt.dfc * pt.G[b]));
+      for (int b = 0; b < MAXNB; ++b)
+        if (b < dc.nb)
+          out[r * dc.nb + b] = dc.inv_sqrt_nb * (rb * pt.fc * pt.G[b] + rdb * rdot * (pt.fc * pt.dG[b] + pt.dfc * pt.G[b]));
     }
   }
 }
@@ -947,8 +985,9 @@ __global__ void __launch_bounds__(64) k_tr_emb_pair(TrWs w, const int32_t* __res
 // 256 blocks share the (present species)^2 table blocks; each sums the cbar rows whose key matches: thread-strided
 // partial sums, then a fixed tree.
 constexpr int ER_BLOCKS = 256;
-__global__ void __launch_bounds__(128) k_tr_emb_reduce(TrWs w, int S, float* __restrict__ embbar) {
-  __shared__ float red[128][36];
+__global__ void __launch_bounds__(128) k_tr_emb_reduce(TrWs w, int S, int ne, float* __restrict__ embbar) {
+  constexpr int MAXE = NR * MAXNB;   // coefficients per species pair
+  __shared__ float red[128][MAXE + 1];
   __shared__ int list[128];
   __shared__ int n_list;
   {   // ordered compaction of the present species: one flag per thread, ballot prefix per warp
@@ -967,9 +1006,9 @@ __global__ void __launch_bounds__(128) k_tr_emb_reduce(TrWs w, int S, float* __r
   const int np = n_list;
   for (int q = blockIdx.x; q < np * np; q += gridDim.x) {
     const int key = list[q / np] * S + list[q % np];
-    float acc[35];
+    float acc[MAXE];
 #pragma unroll
-    for (int i = 0; i < 35; ++i) acc[i] = 0.f;
+    for (int i = 0; i < MAXE; ++i) acc[i] = 0.f;
     for (int64_t base = 0; base < w.P; base += 32 * int64_t(blockDim.x)) {
       unsigned match = 0;   // 32 independent key loads per thread, then only the matching rows are read
 #pragma unroll 8
@@ -980,20 +1019,21 @@ __global__ void __launch_bounds__(128) k_tr_emb_reduce(TrWs w, int S, float* __r
       while (match) {
         const int b = __ffs(match) - 1;
         match &= match - 1;
-        const float* c = w.cbar + (base + int64_t(b) * blockDim.x + threadIdx.x) * 35;
+        const float* c = w.cbar + (base + int64_t(b) * blockDim.x + threadIdx.x) * ne;
 #pragma unroll
-        for (int i = 0; i < 35; ++i) acc[i] += c[i];
+        for (int i = 0; i < MAXE; ++i)
+          if (i < ne) acc[i] += c[i];
       }
     }
 #pragma unroll
-    for (int i = 0; i < 35; ++i) red[threadIdx.x][i] = acc[i];
+    for (int i = 0; i < MAXE; ++i) red[threadIdx.x][i] = acc[i];
     __syncthreads();
     for (int o = 64; o; o >>= 1) {
       if (threadIdx.x < o)
-        for (int i = 0; i < 35; ++i) red[threadIdx.x][i] += red[threadIdx.x + o][i];
+        for (int i = 0; i < ne; ++i) red[threadIdx.x][i] += red[threadIdx.x + o][i];
       __syncthreads();
     }
-    if (threadIdx.x < 35) embbar[int64_t(key) * 35 + threadIdx.x] = red[0][threadIdx.x];
+    if (threadIdx.x < ne) embbar[int64_t(key) * ne + threadIdx.x] = red[0][threadIdx.x];
     __syncthreads();
   }
 }
@@ -1152,7 +1192,8 @@ using namespace apax;
 
 extern "C" int apax_train_plan_create(const apax_gm_config* cfg, apax_train_plan** out) {
   if (!cfg || !out) return APAX_ERR_INVALID_ARG;
-  if (cfg->n_radial != NR || cfg->n_basis != NB || cfg->n_contr != 8 || cfg->n_hidden1 != NH || cfg->n_hidden2 != NH ||
+  if (cfg->n_radial != NR || cfg->n_basis < 1 || cfg->n_basis > MAXNB || cfg->basis_kind < 0 || cfg->basis_kind > 2 ||
+      cfg->n_contr != 8 || cfg->n_hidden1 != NH || cfg->n_hidden2 != NH ||
       cfg->n_out != 1 || cfg->use_ntk != 0 || cfg->n_species < 1 || cfg->n_species > 128)
     return APAX_ERR_UNSUPPORTED;
   std::vector<Term> terms = build_terms();
@@ -1204,18 +1245,37 @@ extern "C" int apax_train_plan_create(const apax_gm_config* cfg, apax_train_plan
   ok &= cudaMemcpy(d_opack, o_pack.data(), sizeof(int32_t) * no, cudaMemcpyHostToDevice) == cudaSuccess;
   if (!ok) { cudaFree(p->dev_block); delete p; return APAX_ERR_CUDA; }
   p->tab = Tables{d_fptr, d_fcoef, d_fslots, d_optr, d_ocoef, d_opack};
-  const double beta = double(cfg->n_basis) * cfg->n_basis / (double(cfg->r_max) * cfg->r_max);
-  p->dc.r_max = cfg->r_max;
-  p->dc.beta = float(beta);
-  p->dc.two_beta = float(2.0 * beta);
-  p->dc.norm = float(pow(2.0 * beta / M_PI, 0.25));
-  p->dc.pi_f = float(M_PI);
-  p->dc.inv_sqrt_nb = cfg->use_embed_norm ? float(1.0 / sqrt(double(cfg->n_basis))) : 1.0f;
-  for (int b = 0; b < NB; ++b)
-    p->dc.mu[b] = float(double(cfg->r_min) + (double(cfg->r_max) - double(cfg->r_min)) / cfg->n_basis * b);
+  {
+    const int nb = cfg->n_basis;
+    const double r_min = cfg->r_min, r_max = cfg->r_max;
+    DescConstT& dc = p->dc;
+    dc.r_max = cfg->r_max;
+    dc.pi_f = float(M_PI);
+    dc.nb = nb;
+    dc.kind = cfg->basis_kind;
+    dc.inv_sqrt_nb = cfg->use_embed_norm ? float(1.0 / sqrt(double(nb))) : 1.0f;
+    for (int b = 0; b < MAXNB; ++b) dc.mu[b] = 0.f;
+    if (cfg->basis_kind == BASIS_GAUSS_LINEAR) {          // basis_functions.py:22-28
+      const double beta = double(nb) * nb / (r_max * r_max);
+      dc.beta = float(beta); dc.two_beta = float(2.0 * beta); dc.norm = float(pow(2.0 * beta / M_PI, 0.25));
+      for (int b = 0; b < nb; ++b) dc.mu[b] = float(r_min + (r_max - r_min) / nb * b);
+    } else if (cfg->basis_kind == BASIS_GAUSS_EXP) {      // :29-37
+      const double beta = pow(2.0 / nb * (exp(-r_min) - exp(-r_max)), -2.0);
+      dc.beta = float(beta); dc.two_beta = float(2.0 * beta); dc.norm = 1.0f;
+      for (int b = 0; b < nb; ++b)
+        dc.mu[b] = float(nb > 1 ? exp(-r_max) + (exp(-r_min) - exp(-r_max)) * b / (nb - 1) : exp(-r_max));   // np.linspace
+    } else {                                              // BesselBasis :72-78 (b_n is 1: the square root is of the PRODUCT)
+      dc.beta = dc.two_beta = 0.f; dc.norm = 1.0f;
+      for (int n = 0; n < nb; ++n) {
+        const double a = ((n & 1) ? -1.0 : 1.0) * (sqrt(2.0) * M_PI / pow(r_max, 1.5));
+        const double bb = double(n + 1) * (n + 2) / sqrt(double(n + 1) * (n + 1) * double(n + 2) * (n + 2));
+        dc.mu[n] = float(float(a) * float(bb));
+      }
+    }
+  }
   // parameter block layout: every array starts on a 64-element boundary
   const int64_t S = cfg->n_species;
-  const int64_t sizes[7] = {S * S * NR * NB, int64_t(NF) * NH, NH, int64_t(NH) * NH, NH, NH, 1};
+  const int64_t sizes[7] = {S * S * NR * cfg->n_basis, int64_t(NF) * NH, NH, int64_t(NH) * NH, NH, NH, 1};
   int64_t off = 0;
   for (int i = 0; i < 7; ++i) { p->off32[i] = off; off = round_up(off + sizes[i], 64); }
   p->off32[7] = off;
@@ -1238,26 +1298,27 @@ extern "C" int apax_train_param_layout(const apax_train_plan* p, int64_t* offset
 }
 
 extern "C" size_t apax_train_workspace_bytes(const apax_train_plan* p, int64_t n_atoms, int64_t n_pairs, int64_t n_structs) {
-  (void)p;
-  size_t b = carve_tr(nullptr, n_atoms, n_pairs, n_structs, nullptr);
+  const int nb = p ? p->cfg.n_basis : MAXNB;
+  size_t b = carve_tr(nullptr, n_atoms, n_pairs, n_structs, nb, nullptr);
   return b + size_t(round_up(n_atoms, 64)) * sizeof(int32_t) + 256;   // + atom -> structure map
 }
 
-extern "C" int apax_train_loss_and_grad(apax_stream_t stream_, const apax_train_plan* p, const float* theta32,
-                                        const double* theta64, const double* R, const int32_t* Z, const int32_t* idx,
-                                        const double* offsets, const int32_t* struct_ptr, const int32_t* pair_ptr,
-                                        const int32_t* n_real, int64_t n_structs, int64_t n_atoms, int64_t n_pairs,
-                                        const double* E_label, const double* F_label, const apax_train_loss_config* lc,
-                                        double batch_divisor, double* loss, double* energy, double* forces, float* grad32,
-                                        double* grad64, void* workspace, size_t workspace_bytes) {
+// grads == false: energy and forces only (E_label, F_label, lc, loss, grad32, grad64 unused)
+static int train_run(bool grads, apax_stream_t stream_, const apax_train_plan* p, const float* theta32,
+                     const double* theta64, const double* R, const int32_t* Z, const int32_t* idx,
+                     const double* offsets, const int32_t* struct_ptr, const int32_t* pair_ptr,
+                     const int32_t* n_real, int64_t n_structs, int64_t n_atoms, int64_t n_pairs,
+                     const double* E_label, const double* F_label, const apax_train_loss_config* lc,
+                     double batch_divisor, double* loss, double* energy, double* forces, float* grad32,
+                     double* grad64, void* workspace, size_t workspace_bytes) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  if (!p || !theta32 || !theta64 || !R || !Z || !idx || !struct_ptr || !pair_ptr || !n_real || !E_label || !F_label || !lc ||
-      !loss || !energy || !forces || !grad32 || !grad64 || !workspace)
+  if (!p || !theta32 || !theta64 || !R || !Z || !idx || !struct_ptr || !pair_ptr || !energy || !forces || !workspace)
     return APAX_ERR_INVALID_ARG;
+  if (grads && (!n_real || !E_label || !F_label || !lc || !loss || !grad32 || !grad64)) return APAX_ERR_INVALID_ARG;
   if (n_structs < 1 || n_atoms < 1 || n_pairs < 1 || n_atoms > (int64_t(1) << 24) || n_pairs > (int64_t(1) << 30)) return APAX_ERR_INVALID_ARG;
   if (workspace_bytes < apax_train_workspace_bytes(p, n_atoms, n_pairs, n_structs)) return APAX_ERR_WORKSPACE;
   TrWs w;
-  const size_t used = carve_tr(workspace, n_atoms, n_pairs, n_structs, &w);
+  const size_t used = carve_tr(workspace, n_atoms, n_pairs, n_structs, p->cfg.n_basis, &w);
   int32_t* atom_struct = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + used);
   const int64_t n = n_atoms, P = n_pairs, B = n_structs;
   const int S = p->cfg.n_species, mask = p->cfg.mask_atoms;
@@ -1265,12 +1326,13 @@ extern "C" int apax_train_loss_and_grad(apax_stream_t stream_, const apax_train_
   const float *w0 = theta32 + p->off32[1], *b0 = theta32 + p->off32[2], *w1 = theta32 + p->off32[3], *b1 = theta32 + p->off32[4],
               *w2 = theta32 + p->off32[5], *b2 = theta32 + p->off32[6];
   const double *scale = theta64 + p->off64[0], *shift = theta64 + p->off64[1];
-  float *g_emb = grad32 + p->off32[0], *g_w0 = grad32 + p->off32[1], *g_b0 = grad32 + p->off32[2], *g_w1 = grad32 + p->off32[3],
-        *g_b1 = grad32 + p->off32[4], *g_w2 = grad32 + p->off32[5], *g_b2 = grad32 + p->off32[6];
+  float* const g0 = grads ? grad32 : nullptr;
+  float *g_emb = g0 + p->off32[0], *g_w0 = g0 + p->off32[1], *g_b0 = g0 + p->off32[2], *g_w1 = g0 + p->off32[3],
+        *g_b1 = g0 + p->off32[4], *g_w2 = g0 + p->off32[5], *g_b2 = g0 + p->off32[6];
   const Tables& tab = p->tab;
   const DescConstT& dc = p->dc;
 
-  APAX_CUDA_TRY(cudaMemsetAsync(grad32, 0, sizeof(float) * size_t(p->off32[7]), s));
+  if (grads) APAX_CUDA_TRY(cudaMemsetAsync(grad32, 0, sizeof(float) * size_t(p->off32[7]), s));
   APAX_CUDA_TRY(cudaMemsetAsync(w.present, 0, sizeof(int32_t) * 132, s));
   // lists and geometry
   APAX_LAUNCH(k_tr_group, dim3((unsigned)B), dim3(128), 0, s, idx, P, struct_ptr, pair_ptr, Z, R, offsets, S, atom_struct, w);
@@ -1291,6 +1353,12 @@ extern "C" int apax_train_loss_and_grad(apax_stream_t stream_, const apax_train_
   APAX_TRY(gemm(s, g));
   APAX_LAUNCH(k_tr_contract_bwd, dim3((unsigned)cdiv(n, CT_ATOMS)), dim3(NPK * CB_LANES), 0, s, tab, w.M, nullptr, w.GB + n * NF, nullptr, w.Mdb, n);
   APAX_LAUNCH(k_tr_pair_bwd, dim3((unsigned)n), dim3(64), 0, s, w, emb, dc);
+  if (!grads) {
+    LossArgs la{0.0, 1.0, 0.0, 1.0, 1.0};
+    APAX_LAUNCH(k_tr_forces_loss, dim3((unsigned)B), dim3(128), 0, s, w, struct_ptr, struct_ptr /* unused */, nullptr, nullptr, la,
+                forces, loss);
+    return APAX_OK;
+  }
   LossArgs la{lc->energy_weight, lc->energy_atoms_exponent, lc->forces_weight, lc->forces_atoms_exponent, batch_divisor};
   APAX_LAUNCH(k_tr_forces_loss, dim3((unsigned)B), dim3(128), 0, s, w, struct_ptr, n_real, E_label, F_label, la, forces, loss);
   // ---- tangent sweep along u = dL/dF, rows [n, 2n)
@@ -1317,8 +1385,28 @@ extern "C" int apax_train_loss_and_grad(apax_stream_t stream_, const apax_train_
   // moments' adjoint incl. the second-order term, then the embedding gradient
   APAX_LAUNCH(k_tr_contract_bwd, dim3((unsigned)cdiv(n, CT_ATOMS)), dim3(NPK * CB_LANES), 0, s, tab, w.M, w.Md, w.GB, w.GB + n * NF, w.Mb2, n);
   APAX_LAUNCH(k_tr_emb_pair, dim3((unsigned)n), dim3(64), 0, s, w, idx, dc);
-  APAX_LAUNCH(k_tr_emb_reduce, dim3(ER_BLOCKS), dim3(128), 0, s, w, S, g_emb);
+  APAX_LAUNCH(k_tr_emb_reduce, dim3(ER_BLOCKS), dim3(128), 0, s, w, S, NR * p->cfg.n_basis, g_emb);
   return APAX_OK;
+}
+
+extern "C" int apax_train_loss_and_grad(apax_stream_t stream, const apax_train_plan* p, const float* theta32,
+                                        const double* theta64, const double* R, const int32_t* Z, const int32_t* idx,
+                                        const double* offsets, const int32_t* struct_ptr, const int32_t* pair_ptr,
+                                        const int32_t* n_real, int64_t n_structs, int64_t n_atoms, int64_t n_pairs,
+                                        const double* E_label, const double* F_label, const apax_train_loss_config* lc,
+                                        double batch_divisor, double* loss, double* energy, double* forces, float* grad32,
+                                        double* grad64, void* workspace, size_t workspace_bytes) {
+  return train_run(true, stream, p, theta32, theta64, R, Z, idx, offsets, struct_ptr, pair_ptr, n_real, n_structs, n_atoms, n_pairs,
+                   E_label, F_label, lc, batch_divisor, loss, energy, forces, grad32, grad64, workspace, workspace_bytes);
+}
+
+extern "C" int apax_train_energy_forces(apax_stream_t stream, const apax_train_plan* p, const float* theta32,
+                                        const double* theta64, const double* R, const int32_t* Z, const int32_t* idx,
+                                        const double* offsets, const int32_t* struct_ptr, const int32_t* pair_ptr,
+                                        int64_t n_structs, int64_t n_atoms, int64_t n_pairs, double* energy, double* forces,
+                                        void* workspace, size_t workspace_bytes) {
+  return train_run(false, stream, p, theta32, theta64, R, Z, idx, offsets, struct_ptr, pair_ptr, nullptr, n_structs, n_atoms, n_pairs,
+                   nullptr, nullptr, nullptr, 1.0, nullptr, energy, forces, nullptr, nullptr, workspace, workspace_bytes);
 }
 
 extern "C" int apax_train_adam_step(apax_stream_t stream_, const apax_train_plan* p, const apax_train_opt_config* oc,

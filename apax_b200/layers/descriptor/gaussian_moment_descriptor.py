@@ -21,6 +21,25 @@ class GaussianBasis:
 
 
 @dataclass
+class BesselBasis:
+    """apax/layers/descriptor/basis_functions.py:59-79 (statics only)."""
+    n_basis: int = 7
+    r_max: float = 6.0
+    dtype: Any = "fp32"
+
+
+def basis_kind(basis_fn) -> int:
+    """apax_gm_config.basis_kind: 0 Gaussian linear, 1 Gaussian exponential, 2 Bessel."""
+    if isinstance(basis_fn, BesselBasis):
+        return 2
+    if basis_fn.spacing == "linear":
+        return 0
+    if basis_fn.spacing == "exponential":
+        return 1
+    raise NotImplementedError(f"spacing {basis_fn.spacing} has not been implemented. Available options are: ['linear', 'exponential']")
+
+
+@dataclass
 class RadialFunction:
     """apax/layers/descriptor/basis_functions.py:88-95 (statics only)."""
     n_radial: int = 5
@@ -41,16 +60,22 @@ class GaussianMomentDescriptor:
 
     def statics(self) -> dict:
         b = self.radial_fn.basis_fn
-        if b.spacing != "linear" or self.radial_fn.emb_init != "uniform" or self.dtype not in ("fp32", None) or not self.apply_mask:
+        if self.radial_fn.emb_init != "uniform" or self.dtype not in ("fp32", None) or not self.apply_mask:
             raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "GaussianMomentDescriptor",
-                                        "kernels cover linear Gaussian basis, embedded radial function, fp32, apply_mask=True")
-        return dict(n_basis=b.n_basis, r_min=b.r_min, r_max=b.r_max, n_radial=self.radial_fn.n_radial,
-                    n_species=self.radial_fn.n_species, use_embed_norm=self.radial_fn.use_embed_norm, n_contr=self.n_contr)
+                                        "kernels cover the embedded radial function, fp32, apply_mask=True")
+        return dict(n_basis=b.n_basis, r_min=getattr(b, "r_min", 0.0), r_max=b.r_max, n_radial=self.radial_fn.n_radial,
+                    n_species=self.radial_fn.n_species, use_embed_norm=self.radial_fn.use_embed_norm, n_contr=self.n_contr,
+                    basis_kind=basis_kind(b))
 
     def apply(self, variables: dict, dr_vec, Z, neighbor_idxs):
         """variables = {"params": {"radial_fn": {"atomic_type_embedding": [S,S,5,7]}}} as flax would pass it."""
         emb = variables["params"]["radial_fn"]["atomic_type_embedding"]
-        dp = _descriptor_params(emb, self.statics())
+        st = self.statics()
+        if st["basis_kind"] != 0 or st["n_basis"] != 7:
+            raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "GaussianMomentDescriptor.apply",
+                                        "the stand-alone descriptor entry point covers the default basis only; Bessel / exponential "
+                                        "bases are evaluated through the model (apax_train_energy_forces)")
+        dp = _descriptor_params(emb, st)
         return rt.descriptor(dp, dr_vec, Z, neighbor_idxs, mode="drvec")
 
 

@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ..layers.descriptor.gaussian_moment_descriptor import GaussianBasis, GaussianMomentDescriptor, RadialFunction
+from ..layers.descriptor.gaussian_moment_descriptor import BesselBasis, GaussianBasis, GaussianMomentDescriptor, RadialFunction
 from .models import AtomisticReadout, EnergyDerivativeModel, EnergyModel, PerElementScaleShift, ShallowEnsembleModel
 
 DEFAULT_MODEL_CONFIG = {
@@ -26,8 +26,8 @@ class ModelBuilder:
 
     def build_basis_function(self):
         b = self.config["basis"]
-        if b["name"] != "gaussian":
-            raise NotImplementedError("bessel basis is a next row (SURVEY.md §8f)")
+        if b["name"] == "bessel":                            # apax/nn/builder.py:36-52
+            return BesselBasis(n_basis=b["n_basis"], r_max=b["r_max"], dtype=self.config["descriptor_dtype"])
         return GaussianBasis(n_basis=b["n_basis"], r_min=b["r_min"], r_max=b["r_max"], dtype=self.config["descriptor_dtype"],
                              spacing=b.get("spacing", "linear"))
 

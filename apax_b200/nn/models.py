@@ -81,7 +81,14 @@ class EnergyModel:
 
     def _run(self, params, R, Z, neighbor, box, offsets, forces: bool):
         mode = displacement_mode(self.init_box, self.inference_disp_fn)
-        dp = device_params(params, self.statics())
+        st = self.statics()
+        if st["basis_kind"] != 0 or st["n_basis"] != 7:
+            # Bessel / exponential-spacing bases: the table-driven kernels behind apax_train_*
+            from ..train.trainer import table_model
+
+            e, f = table_model(params, st).energy_forces(R, Z, canonicalize_neighbors(neighbor), box, offsets, mode)
+            return e, f[None]
+        dp = device_params(params, st)
         return rt.energy_forces(dp, R, Z, canonicalize_neighbors(neighbor), box, offsets, mode, forces=forces)
 
     def apply(self, params, R, Z, neighbor, box, offsets, perturbation=None):

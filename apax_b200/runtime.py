@@ -41,7 +41,7 @@ def to_device(x, dtype: torch.dtype) -> torch.Tensor:
 def default_config(n_out: int = 1, **overrides) -> dict:
     """Flax-module defaults of the GMNN path (SURVEY.md §8 header; apax/config/model_config.py:147-227)."""
     cfg = dict(n_species=119, n_radial=5, n_basis=7, n_contr=8, nn=[256, 256], n_out=n_out, use_ntk=False,
-               use_embed_norm=True, mask_atoms=True, r_min=0.5, r_max=6.0)
+               use_embed_norm=True, mask_atoms=True, r_min=0.5, r_max=6.0, basis_kind=0)
     cfg.update(overrides)
     return cfg
 
@@ -87,7 +87,7 @@ class DeviceParams:
         c = GmConfig(n_species=S, n_radial=cfg["n_radial"], n_basis=cfg["n_basis"], n_contr=cfg["n_contr"],
                      n_hidden1=cfg["nn"][0], n_hidden2=cfg["nn"][1], n_out=n_out, use_ntk=int(cfg["use_ntk"]),
                      use_embed_norm=int(cfg["use_embed_norm"]), mask_atoms=int(cfg["mask_atoms"]),
-                     r_min=cfg["r_min"], r_max=cfg["r_max"])
+                     r_min=cfg["r_min"], r_max=cfg["r_max"], basis_kind=int(cfg.get("basis_kind", 0)))
         self._keep = (emb, w, b, scale, shift)
         handle = C.c_void_p()
 

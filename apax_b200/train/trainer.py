@@ -43,7 +43,7 @@ class TrainState:
         c = _lib.GmConfig(n_species=cfg["n_species"], n_radial=cfg["n_radial"], n_basis=cfg["n_basis"], n_contr=cfg["n_contr"],
                           n_hidden1=cfg["nn"][0], n_hidden2=cfg["nn"][1], n_out=1, use_ntk=int(cfg["use_ntk"]),
                           use_embed_norm=int(cfg["use_embed_norm"]), mask_atoms=int(cfg["mask_atoms"]), r_min=cfg["r_min"],
-                          r_max=cfg["r_max"])
+                          r_max=cfg["r_max"], basis_kind=int(cfg.get("basis_kind", 0)))
         self.plan = C.c_void_p()
         check(lib().apax_train_plan_create(C.byref(c), C.byref(self.plan)), "apax_train_plan_create")
         o32 = (C.c_int64 * 8)()
@@ -357,6 +357,62 @@ class TrainStep:
         self.graphs[parity].replay()
         if self.dist:
             self._reduce_and_update(parity)
+
+
+class TableModel:
+    """Energy + forces on the table-driven kernels (apax_train_energy_forces): the evaluation path for model statics the
+    specialised apax_gm_* kernels do not cover (Bessel / exponential-spacing bases, n_basis <= 16)."""
+
+    def __init__(self, params: dict, config: dict):
+        frozen = AdamLinear(emb_lr=0.0, nn_lr=0.0, scale_lr=0.0, shift_lr=0.0, gradient_clipping=1.0, transition_steps=1)
+        self.state = TrainState(params, frozen, config)
+        self.ws = Workspace()
+
+    def energy_forces_batched(self, R, Z, idx, offsets, struct_ptr, pair_ptr):
+        """Concatenated batch as in apax_gm_energy_forces_batched -> (energy [B] f64, forces [N,3] f64) device tensors."""
+        from ..runtime import to_device
+
+        st = self.state
+        R, Z, idx = to_device(R, torch.float64), to_device(Z, torch.int32), to_device(idx, torch.int32)
+        off = None if offsets is None else to_device(offsets, torch.float64)
+        sp, pp = to_device(struct_ptr, torch.int32), to_device(pair_ptr, torch.int32)
+        n, P, B = int(R.shape[0]), int(idx.shape[1]), int(sp.shape[0]) - 1
+        energy = torch.empty(B, dtype=torch.float64, device=R.device)
+        forces = torch.empty((n, 3), dtype=torch.float64, device=R.device)
+        nbytes = lib().apax_train_workspace_bytes(st.plan, n, P, B)
+        buf = self.ws.get(nbytes)
+        check(lib().apax_train_energy_forces(_stream_ptr(), st.plan, _ptr(st.theta32), _ptr(st.theta64), _ptr(R), _ptr(Z), _ptr(idx),
+                                             _ptr(off), _ptr(sp), _ptr(pp), B, n, P, _ptr(energy), _ptr(forces),
+                                             C.c_void_p(Workspace.aligned_ptr(buf)), C.c_size_t(nbytes)), "apax_train_energy_forces")
+        return energy, forces
+
+    def energy_forces(self, R, Z, idx, box, offsets, mode: str):
+        """One structure with the call shape of EnergyDerivativeModel.apply.  Fractional positions of the `offsets` branch
+        become Cartesian (box . R, apax/layers/distances.py:12-14); the min-image branch is not offered on this path."""
+        from ..runtime import to_device
+
+        if mode == "minimage":
+            raise _lib.ApaxB200Error(_lib.ERR_UNSUPPORTED, "TableModel", "min-image displacement with a non-default basis: pass a "
+                                     "list with offsets (apax_nl_build_images)")
+        R = to_device(R, torch.float64)
+        if mode == "offsets":
+            R = R @ to_device(box, torch.float64).T
+        else:
+            offsets = None
+        n, P = int(R.shape[0]), int(np.asarray(idx.shape)[1])
+        e, f = self.energy_forces_batched(R, Z, idx, offsets, np.array([0, n], dtype=np.int32), np.array([0, P], dtype=np.int32))
+        return e, f
+
+
+_table_cache: dict = {}
+
+
+def table_model(params: dict, config: dict) -> TableModel:
+    key = (id(params), tuple(sorted((k, str(v)) for k, v in config.items())))
+    hit = _table_cache.get(key)
+    if hit is None or hit[0] is not params:
+        _table_cache[key] = (params, TableModel(params, config))
+    return _table_cache[key][1]
 
 
 def make_step_fns(loss_fn: LossCollection, Metrics=None, model=None, is_ensemble: bool = False, graph: bool = False):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define APAX_B200_ABI_VERSION 1
+#define APAX_B200_ABI_VERSION 2
 
 typedef struct CUstream_st* apax_stream_t; /* == cudaStream_t */
 
@@ -62,6 +62,10 @@ typedef struct {
   int32_t mask_atoms;     /* mask_by_atom on E_i (apax/nn/models.py:111-112) */
   float r_min;            /* 0.5 */
   float r_max;            /* 6.0 */
+  int32_t basis_kind;     /* radial basis (apax/layers/descriptor/basis_functions.py): 0 GaussianBasis spacing="linear" (:22-28),
+                             1 GaussianBasis spacing="exponential" (:29-37), 2 BesselBasis (:59-79).  The apax_gm_* fast path is
+                             specialised for kind 0 with n_basis = 7; the other kinds (n_basis <= 16) run on the table-driven
+                             kernels behind apax_train_* (energy+forces: apax_train_energy_forces). */
 } apax_gm_config;
 
 /* ------------------------------------------------------------------------------------------------
@@ -233,7 +237,7 @@ int apax_md_nvt_post_force(apax_stream_t stream, const apax_md_nvt_config* cfg, 
  * All state is CALLER-owned device memory, so that a host can all-reduce the gradient blocks between the two
  * calls (data parallelism over structures, apax/train/trainer.py:101-106) and capture the step in a CUDA graph:
  *   theta32 / grad32 / m32 / v32 : f32 blocks of offsets32[7] elements laid out as apax_train_param_layout says
- *                                  (atomic_type_embedding [S][S][5][7], dense_0 w [360][256], b, dense_1 w, b, dense_2 w, b)
+ *                                  (atomic_type_embedding [S][S][5][n_basis], dense_0 w [360][256], b, dense_1 w, b, dense_2 w, b)
  *   theta64 / grad64 / m64 / v64 : f64 [2 S] = scale_per_element, shift_per_element
  * Batch layout = apax_gm_energy_forces_batched: atoms of all structures concatenated, Cartesian positions,
  * idx i32 [2][n_pairs] with GLOBAL atom indices, offsets f64 [n_pairs][3] or NULL; struct_ptr / pair_ptr i32
@@ -269,6 +273,13 @@ int apax_train_loss_and_grad(apax_stream_t stream, const apax_train_plan* plan, 
                              const double* E_label, const double* F_label, const apax_train_loss_config* loss_cfg,
                              double batch_divisor, double* loss, double* energy, double* forces, float* grad32,
                              double* grad64, void* workspace, size_t workspace_bytes);
+/* Energy and forces only, on the same kernels and batch layout (no labels, no gradients): the evaluation path for
+ * model statics the specialised apax_gm_* kernels do not cover (Bessel / exponential-spacing bases, n_basis up to 16);
+ * replaces the vmapped EnergyDerivativeModel.apply (apax/nn/models.py:146-171, apax/train/run.py:204) for those. */
+int apax_train_energy_forces(apax_stream_t stream, const apax_train_plan* plan, const float* theta32, const double* theta64,
+                             const double* R, const int32_t* Z, const int32_t* idx, const double* offsets,
+                             const int32_t* struct_ptr, const int32_t* pair_ptr, int64_t n_structs, int64_t n_atoms,
+                             int64_t n_pairs, double* energy, double* forces, void* workspace, size_t workspace_bytes);
 /* One optimizer update, in place.  opt_state i64 [8], zero-initialised by the caller: [0] is the optimizer's step counter
  * (optax `count`), read for the schedule / bias correction and incremented on the device; the rest is scratch. */
 int apax_train_adam_step(apax_stream_t stream, const apax_train_plan* plan, const apax_train_opt_config* opt_cfg,

@@ -36,6 +36,8 @@ class GMNNConfig:
     n_radial: int = 5         # basis_functions.py:89
     r_min: float = 0.5        # basis_functions.py:14
     r_max: float = 6.0        # basis_functions.py:15
+    basis: str = "gaussian"   # "gaussian" (GaussianBasis) or "bessel" (BesselBasis, basis_functions.py:59-79)
+    spacing: str = "linear"   # GaussianBasis spacing: "linear" (:22-28) or "exponential" (:29-37)
     n_contr: int = 8          # gaussian_moment_descriptor.py:18
     use_ntk: bool = False     # apax/config/model_config.py:184-188
     use_embed_norm: bool = True  # basis_functions.py:93
@@ -124,15 +126,44 @@ def compute_distances(R, idx, box, offsets, mode: str):
 # descriptor  (apax/layers/descriptor/*.py)
 # ---------------------------------------------------------------------------
 def gaussian_basis(dr, cfg: GMNNConfig):
-    """GaussianBasis, linear spacing (basis_functions.py:19-56)."""
+    """GaussianBasis (basis_functions.py:19-56), linear or exponential spacing."""
     dt = dr.dtype
-    betta = cfg.n_basis ** 2 / cfg.r_max ** 2
-    rad_norm = (2.0 * betta / np.pi) ** 0.25
-    shifts = cfg.r_min + (cfg.r_max - cfg.r_min) / cfg.n_basis * np.arange(cfg.n_basis)
+    if cfg.spacing == "linear":
+        betta = cfg.n_basis ** 2 / cfg.r_max ** 2
+        rad_norm = (2.0 * betta / np.pi) ** 0.25
+        shifts = cfg.r_min + (cfg.r_max - cfg.r_min) / cfg.n_basis * np.arange(cfg.n_basis)
+        scaled = dr
+    elif cfg.spacing == "exponential":                                # :29-37
+        betta = (2.0 / cfg.n_basis * (np.exp(-cfg.r_min) - np.exp(-cfg.r_max))) ** -2
+        rad_norm = 1.0
+        shifts = np.linspace(np.exp(-cfg.r_max), np.exp(-cfg.r_min), num=cfg.n_basis, endpoint=True)
+        scaled = torch.exp(-dr)
+    else:
+        raise NotImplementedError(cfg.spacing)
     shifts = torch.as_tensor(shifts, dtype=dt)[None, :]
-    distances = shifts - dr[:, None]
-    basis = torch.exp(-betta * (distances ** 2))
+    distances = shifts - scaled[:, None]
+    basis = torch.exp(-float(betta) * (distances ** 2))
     return rad_norm * basis
+
+
+def bessel_basis(dr, cfg: GMNNConfig):
+    """BesselBasis (basis_functions.py:59-79).  Note :75: the square root is taken of the PRODUCT of the squares, so b == 1."""
+    dt = dr.dtype
+    n = torch.arange(cfg.n_basis, dtype=dt)
+    a = (-1) ** n * torch.as_tensor(np.sqrt(2) * np.pi / (cfg.r_max ** (3 / 2)), dtype=dt)
+    b = (n + 1) * (n + 2) / torch.sqrt((n + 1) ** 2 * (n + 2) ** 2)
+    s1 = _sinc((n + 1) * dr[:, None] / cfg.r_max)
+    s2 = _sinc((n + 2) * dr[:, None] / cfg.r_max)
+    return a * b * (s1 + s2)
+
+
+def _sinc(x):
+    """jnp.sinc: sin(pi x)/(pi x) with finite derivatives of every order at 0 (JAX defines them through the Maclaurin series).
+    torch.sinc's double backward is NaN at 0, which the zero-distance padding entries ((0,0) pairs) would hit; they are
+    multiplied by a zero mask downstream, so any finite derivative there reproduces the reference."""
+    nz = x != 0
+    safe = torch.where(nz, x, torch.ones_like(x))
+    return torch.where(nz, torch.sinc(safe), torch.ones_like(x))
 
 
 def cosine_cutoff(dr, r_max: float):
@@ -145,7 +176,7 @@ def radial_function(dr, Z_i, Z_j, emb, cfg: GMNNConfig):
     """RadialFunction.__call__ (basis_functions.py:129-158); emb [S,S,n_radial,n_basis]."""
     dt = cfg.descriptor_dtype
     dr = dr.to(dt)
-    basis = gaussian_basis(dr, cfg)
+    basis = bessel_basis(dr, cfg) if cfg.basis == "bessel" else gaussian_basis(dr, cfg)
     coeffs = emb[Z_j, Z_i]  # "reverse convention" (:139-141): central species first
     if cfg.use_embed_norm:
         coeffs = torch.as_tensor(1.0 / np.sqrt(cfg.n_basis), dtype=dt) * coeffs

@@ -178,6 +178,7 @@ jnp.einsum = lambda spec, *ops: torch.einsum(spec.replace(" ", ""), *ops)
 jnp.exp = lambda x: torch.exp(_t(x))
 jnp.cos = torch.cos
 jnp.sin = torch.sin
+jnp.sinc = lambda x: torch.sinc(_t(x))
 jnp.sqrt = lambda x: torch.sqrt(_t(x))
 jnp.abs = torch.abs
 jnp.sign = torch.sign

@@ -276,6 +276,37 @@ def case_train_step(n_struct=3, seed=21):
              energy=predictions["energy"].detach().numpy(), forces=predictions["forces"].detach().numpy(), **out)
 
 
+def case_basis_variants(n_mol=6, seed=17):
+    """E+F with the reference's own BesselBasis (n_basis=16, r_max=5: the config-file default, model_config.py:182) and
+    GaussianBasis(spacing="exponential") on a small multi-image water cell; also the raw basis values on a distance grid."""
+    from apax.layers.descriptor.basis_functions import BesselBasis
+
+    pos, Z, cell = syn.water_box(n_mol, seed)
+    out = {"positions": pos, "Z": Z, "cell": cell}
+    dr_grid = np.linspace(0.3, 5.9, 29).astype(np.float32)
+    for name, basis, nb, r_max in (("bessel", BesselBasis(n_basis=16, r_max=5.0, dtype="fp32"), 16, 5.0),
+                                   ("gexp", GaussianBasis(n_basis=7, r_min=0.5, r_max=6.0, dtype="fp32", spacing="exponential"), 7, 6.0)):
+        idx, offsets = no.vesin_idx_offsets(pos, cell, r_max)
+        frac = np.asarray(space.transform(torch.as_tensor(np.linalg.inv(cell)), torch.as_tensor(pos)))
+        params = syn.gmnn_params(seed=41, n_basis=nb, random_bias=True, random_scale_shift=True)
+        em = params["params"]["energy_model"]
+        descriptor = GaussianMomentDescriptor(
+            radial_fn=RadialFunction(n_radial=5, basis_fn=basis, n_species=119, emb_init="uniform", use_embed_norm=True, dtype="fp32"),
+            n_contr=8, dtype="fp32", apply_mask=True)
+        readout = AtomisticReadout(units=[256, 256], activation_fn=variance_preserving_swish, w_init="lecun", b_init="zeros",
+                                   use_ntk=False, n_shallow_ensemble=0, dtype="fp32")
+        scale_shift = PerElementScaleShift(n_species=119, scale=em["scale_shift"]["scale_per_element"],
+                                           shift=em["scale_shift"]["shift_per_element"], dtype="fp64")
+        m = EnergyDerivativeModel(EnergyModel(representation=descriptor, readout=readout, scale_shift=scale_shift,
+                                              init_box=np.array(cell.T), inference_disp_fn=None, mask_atoms=True))
+        res = np_out(m.apply(to_t(params), torch.as_tensor(frac), torch.as_tensor(Z.astype(np.int64)),
+                             torch.as_tensor(idx.astype(np.int64)), torch.as_tensor(cell), torch.as_tensor(offsets)))
+        vals = basis.apply({"params": {}}, torch.as_tensor(dr_grid))
+        out.update({f"{name}_idx": idx, f"{name}_offsets": offsets, f"{name}_frac": frac, f"{name}_energy": res["energy"],
+                    f"{name}_forces": res["forces"], f"{name}_basis": np.asarray(vals.detach() if torch.is_tensor(vals) else vals)})
+    np.savez(os.path.join(HERE, "basis_variants.npz"), dr_grid=dr_grid, param_seed=41, **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     case_descriptor_unit()
@@ -292,3 +323,5 @@ if __name__ == "__main__":
     print("md_nvt ok")
     case_train_step()
     print("train_step ok")
+    case_basis_variants()
+    print("basis_variants ok")

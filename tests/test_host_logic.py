@@ -92,7 +92,7 @@ def test_library_exports_every_declared_symbol():
     handle = _lib.lib()
     for name in declared:
         assert hasattr(handle, name), name
-    assert handle.apax_abi_version() == 1
+    assert handle.apax_abi_version() == 2
     assert handle.apax_gm_workspace_bytes(96, 9000, 1) > 0
     assert handle.apax_nl_workspace_bytes(96, 9000) > 0
 

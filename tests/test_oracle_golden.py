@@ -1,6 +1,7 @@
 """The oracle against fixtures produced by executing the reference's OWN source files
 (tests/golden/make_golden.py, under the torch-backed jax/flax shim).  CPU only."""
 import numpy as np
+import pytest
 import torch
 
 from apax_b200 import synthetic as syn
@@ -92,3 +93,22 @@ def test_md_integrator_against_reference_source(golden):
             assert np.abs(st.chain.p_xi - d[f"p_xi_{step}"]).max() < 1e-13
             assert np.array_equal(st.chain.Q, d[f"Q_{step}"])
             assert abs(st.chain.KE - float(d[f"KE_{step}"])) < 1e-12
+
+
+@pytest.mark.parametrize("name,kw", [("bessel", dict(basis="bessel", n_basis=16, r_max=5.0)), ("gexp", dict(spacing="exponential"))])
+def test_basis_variants_against_reference_source(golden, name, kw):
+    """BesselBasis (basis_functions.py:59-79) and GaussianBasis(spacing="exponential") (:29-37): raw basis values bit-exact,
+    E+F to fp32 rounding, against the fixture written by the reference's own classes."""
+    import torch
+
+    from apax_b200 import synthetic as syn
+    from oracle import gmnn_oracle as go
+
+    d = golden("basis_variants")
+    cfg = go.GMNNConfig(**kw)
+    fn = go.bessel_basis if name == "bessel" else go.gaussian_basis
+    assert np.array_equal(fn(torch.as_tensor(d["dr_grid"]), cfg).numpy(), d[name + "_basis"])
+    params = syn.gmnn_params(seed=int(d["param_seed"]), n_basis=cfg.n_basis, random_bias=True, random_scale_shift=True)
+    ref = go.energy_forces(params, d[name + "_frac"], d["Z"], d[name + "_idx"], d["cell"], d[name + "_offsets"], "offsets", cfg)
+    assert np.abs(ref["forces"] - d[name + "_forces"]).max() <= 1e-6 * np.abs(d[name + "_forces"]).max() + 1e-7
+    assert abs(ref["energy"] - float(d[name + "_energy"])) <= 1e-5
