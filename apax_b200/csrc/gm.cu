@@ -172,18 +172,22 @@ __global__ void __launch_bounds__(256) k_csr_import(const int32_t* __restrict__ 
 // produces): the reverse of slot s = (j in row a) is the slot of a in row j, found by binary search -- no
 // atomics, no sort.  A slot without a partner (a pair exactly at the cutoff that rounding kept on one side only;
 // its force contribution is exactly zero there) maps onto itself with zero weight via tpos = -1.
+// The import of the builder's CSR (row pointers, neighbours, identity source map) is folded in: one pass over the list.
 __global__ void __launch_bounds__(256) k_transpose_symmetric(const int32_t* __restrict__ rowptr, int64_t N,
-                                                             const int32_t* __restrict__ nbr, int32_t* __restrict__ trowptr,
-                                                             int32_t* __restrict__ tpos) {
+                                                             const int32_t* __restrict__ nbr, int32_t* __restrict__ rowptr_out,
+                                                             int32_t* __restrict__ nbr_out, int32_t* __restrict__ src_out,
+                                                             int32_t* __restrict__ trowptr, int32_t* __restrict__ tpos) {
   // warp per row a: lanes take the row's slots; each looks its own atom up in the (sorted) row of the neighbour
   const int64_t a = (int64_t(blockIdx.x) * 256 + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (a > N) return;
-  if (lane == 0) trowptr[a] = rowptr[a];
+  if (lane == 0) { trowptr[a] = rowptr[a]; rowptr_out[a] = rowptr[a]; }
   if (a == N) return;
   const int rb = rowptr[a], re = rowptr[a + 1];
   for (int s = rb + lane; s < re; s += 32) {
     const int j = nbr[s];
+    nbr_out[s] = j;
+    src_out[s] = s;
     int b = __ldg(rowptr + j), e = __ldg(rowptr + j + 1) - 1, found = -1;
     while (b <= e) {
       const int mid = (b + e) >> 1;
@@ -234,13 +238,15 @@ static int gm_prepare_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
 int gm_prepare_from_csr(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const int32_t* Z,
                         const int32_t* rowptr_in, const int32_t* nbr_in, bool symmetric_sorted) {
   const int64_t N = w.n_atoms, P = w.n_pairs;
-  APAX_CUDA_TRY(cudaMemsetAsync(w.tcnt, 0, sizeof(int32_t) * (N + 1), stream));
-  const int64_t n = (P > N + 1 ? P : N + 1);
-  APAX_LAUNCH(k_csr_import, dim3((unsigned)cdiv(n, 256)), dim3(256), 0, stream, rowptr_in, nbr_in, N, P, w.rowptr, w.nbr,
-              w.src, w.tcnt);
-  if (!symmetric_sorted) return gm_prepare_tail(stream, p, w, Z);
-  APAX_LAUNCH(k_transpose_symmetric, dim3((unsigned)cdiv((N + 1) * 32, 256)), dim3(256), 0, stream, w.rowptr, N, w.nbr,
-              w.trowptr, w.tpos);
+  if (!symmetric_sorted) {
+    APAX_CUDA_TRY(cudaMemsetAsync(w.tcnt, 0, sizeof(int32_t) * (N + 1), stream));
+    const int64_t n = (P > N + 1 ? P : N + 1);
+    APAX_LAUNCH(k_csr_import, dim3((unsigned)cdiv(n, 256)), dim3(256), 0, stream, rowptr_in, nbr_in, N, P, w.rowptr, w.nbr,
+                w.src, w.tcnt);
+    return gm_prepare_tail(stream, p, w, Z);
+  }
+  APAX_LAUNCH(k_transpose_symmetric, dim3((unsigned)cdiv((N + 1) * 32, 256)), dim3(256), 0, stream, rowptr_in, N, nbr_in,
+              w.rowptr, w.nbr, w.src, w.trowptr, w.tpos);
   const int S = p->cfg.n_species;
   APAX_CUDA_TRY(cudaMemsetAsync(w.sp_present, 0, sizeof(int32_t) * 128, stream));
   APAX_LAUNCH(k_species_mark, dim3((unsigned)cdiv(N, 128)), dim3(128), 0, stream, Z, N, S, w.sp_present);
@@ -929,6 +935,45 @@ __global__ void k_energy_final(const double* __restrict__ partial, int n_blocks,
 // ================================================================================================
 // host orchestration
 // ================================================================================================
+// ---- stress x volume: dU/d(eps) = sum over list entries of dE/d(dr) (x) dr, for the strain applied as dr' = (I + eps) dr
+// (apax/layers/properties.py:11-42 with periodic_general's perturbation, space.py:277-278).  Fixed-shape two-stage sum in
+// fp64 over the fp32 per-pair values the force pass left in the workspace.
+constexpr int kVirialBlocks = 1024;
+__global__ void __launch_bounds__(256) k_virial_partial(const float4* __restrict__ D, const float4* __restrict__ G,
+                                                        const int32_t* __restrict__ rowptr, int64_t n_central,
+                                                        double* __restrict__ partial) {
+  __shared__ double red[256][9];
+  const int64_t P = rowptr[n_central];
+  const int64_t per = (P + gridDim.x - 1) / gridDim.x;
+  const int64_t b = int64_t(blockIdx.x) * per, e = b + per < P ? b + per : P;
+  double acc[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+  for (int64_t s = b + threadIdx.x; s < e; s += blockDim.x) {
+    const float4 d = D[s], g = G[s];
+    acc[0] += double(d.x) * double(g.x); acc[1] += double(d.x) * double(g.y); acc[2] += double(d.x) * double(g.z);
+    acc[3] += double(d.y) * double(g.x); acc[4] += double(d.y) * double(g.y); acc[5] += double(d.y) * double(g.z);
+    acc[6] += double(d.z) * double(g.x); acc[7] += double(d.z) * double(g.y); acc[8] += double(d.z) * double(g.z);
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) red[threadIdx.x][q] = acc[q];
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int q = 0; q < 9; ++q) red[threadIdx.x][q] += red[threadIdx.x + o][q];
+    __syncthreads();
+  }
+  if (threadIdx.x < 9) partial[blockIdx.x * 9 + threadIdx.x] = red[0][threadIdx.x];
+}
+
+__global__ void __launch_bounds__(32) k_virial_final(const double* __restrict__ partial, int n_blocks, double* __restrict__ out) {
+  if (threadIdx.x < 9) {
+    double acc = 0.0;
+    for (int b = 0; b < n_blocks; ++b) acc += partial[b * 9 + threadIdx.x];
+    out[threadIdx.x] = acc;
+  }
+}
+
 static DescConst make_desc_const(const apax_gm_config& cfg) {
   DescConst dc{};
   dc.r_max = cfg.r_max;
@@ -1518,5 +1563,25 @@ extern "C" int apax_gm_descriptor(apax_stream_t stream, const apax_gm_params* pa
   APAX_TRY(gm_descriptor_impl(stream, params, w, geo));
   APAX_LAUNCH(k_features_to_rowmajor, dim3((unsigned)cdiv(n_atoms, 32), cdiv(NF, 32)), dim3(256), 0, stream, w.GT,
               w.ld, n_atoms, g);
+  return APAX_OK;
+}
+
+extern "C" int apax_gm_stress_times_vol(apax_stream_t stream, const apax_gm_params* params, int64_t n_atoms, int64_t n_pairs,
+                                        double* stress, void* workspace, size_t workspace_bytes) {
+  if (!params || !stress || !workspace) return APAX_ERR_INVALID_ARG;
+  if (params->cfg.n_out != 1) return APAX_ERR_UNSUPPORTED;
+  GmWorkspace w;
+  APAX_TRY(get_ws(params, n_atoms, n_pairs, workspace, workspace_bytes, &w));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // scratch for the per-block partial sums: the int32 [n_pairs] array of the list preparation (idle after prepare); lists
+  // too short to hold 1024 x 9 doubles are summed by one block into the row-force scratch (idle after the force assembly)
+  double* partial = reinterpret_cast<double*>(w.tmp_a);
+  if (size_t(w.n_pairs) * sizeof(int32_t) < size_t(kVirialBlocks) * 9 * sizeof(double)) {
+    APAX_LAUNCH(k_virial_partial, dim3(1), dim3(256), 0, s, w.D, w.G, w.rowptr, w.n_atoms, w.Frow);
+    APAX_LAUNCH(k_virial_final, dim3(1), dim3(32), 0, s, w.Frow, 1, stress);
+    return APAX_OK;
+  }
+  APAX_LAUNCH(k_virial_partial, dim3(kVirialBlocks), dim3(256), 0, s, w.D, w.G, w.rowptr, w.n_atoms, partial);
+  APAX_LAUNCH(k_virial_final, dim3(1), dim3(32), 0, s, partial, kVirialBlocks, stress);
   return APAX_OK;
 }

@@ -136,7 +136,7 @@ def _gm_ws(n_atoms: int, n_pairs: int, n_out: int, ws: Optional[Workspace]):
 
 
 def energy_forces(params: DeviceParams, R, Z, idx, box, offsets, mode: str = "offsets", forces: bool = True,
-                  workspace: Optional[Workspace] = None):
+                  workspace: Optional[Workspace] = None, stress: bool = False):
     """EnergyDerivativeModel.apply (apax/nn/models.py:146-171) on the GPU.
 
     Returns (energy f64 tensor [n_out], forces f64 tensor [n_out, N, 3] or None), asynchronous on the
@@ -159,6 +159,13 @@ def energy_forces(params: DeviceParams, R, Z, idx, box, offsets, mode: str = "of
     check(lib().apax_gm_energy_forces(_stream_ptr(), params.handle, _ptr(R), _ptr(Z), _ptr(idx), _ptr(box_d), _ptr(off_d),
                                       n_atoms, n_pairs, MODES[mode], _ptr(energy), _ptr(F), wp, wb),
           "apax_gm_energy_forces")
+    if stress:
+        if mode != "minimage" or not forces:
+            raise _lib.ApaxB200Error(_lib.ERR_UNSUPPORTED, "energy_forces", "stress is offered on the min-image path (with forces)")
+        st = torch.empty((3, 3), dtype=torch.float64, device=dev)
+        check(lib().apax_gm_stress_times_vol(_stream_ptr(), params.handle, n_atoms, n_pairs, _ptr(st), wp, wb),
+              "apax_gm_stress_times_vol")
+        return energy, F, st
     return energy, F
 
 

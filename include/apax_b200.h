@@ -120,6 +120,17 @@ int apax_gm_compute(apax_stream_t stream, const apax_gm_params* params, const do
                     int64_t n_pairs, int32_t disp_mode, double* energy, double* forces,
                     void* workspace, size_t workspace_bytes);
 
+/* Stress times volume, dU/d(eps) at eps = 0.  Replaces stress_times_vol (apax/layers/properties.py:11-42) as called by
+ * EnergyDerivativeModel with calc_stress (apax/nn/models.py:160-169) for the MINIMAGE displacement, where the reference
+ * applies the strain as dr' = (I + eps) . dr (apax/utils/jax_md_reduced/space.py:277-278):
+ *   stress[i][j] = sum over list entries of dE/d(dr)_i * dr_j.
+ * Call it after apax_gm_compute / apax_gm_energy_forces (n_out == 1) on the SAME workspace: it reduces the per-pair
+ * quantities the force pass left there.  (On the OFFSETS path the reference's disp_fn applies dr' = dr + (I + eps) . dr,
+ * apax/layers/distances.py:16-17, i.e. it differentiates at doubled displacements; this function does not reproduce that.)
+ * stress f64 [3][3], device. */
+int apax_gm_stress_times_vol(apax_stream_t stream, const apax_gm_params* params, int64_t n_atoms, int64_t n_pairs,
+                             double* stress, void* workspace, size_t workspace_bytes);
+
 /* Batched evaluation of many independent structures in one call.  Replaces the vmapped model of
  * ASECalculator.batch_eval (apax/md/ase_calc.py:395-481, jax.vmap over padded structures) and of the training
  * data path (apax/train/run.py:204).  Atoms of all structures are concatenated (no padding needed):

@@ -386,3 +386,32 @@ def fp64_config(cfg: Optional[GMNNConfig] = None) -> GMNNConfig:
     out.descriptor_dtype = torch.float64
     out.readout_dtype = torch.float64
     return out
+
+
+def stress_times_vol(params, R, Z, idx, box, offsets, mode: str, cfg: Optional[GMNNConfig] = None):
+    """stress_times_vol (apax/layers/properties.py:11-42): dU/d(eps) at eps = 0 with perturbation = I + eps handed to the
+    displacement function.  The two periodic branches of the reference treat it differently:
+      "minimage": dR' = (I + eps) . dR                     (periodic_general, space.py:277-278)
+      "offsets" : dR' = dR + (I + eps) . dR (+ offsets)    (disp_fn, apax/layers/distances.py:16-17 -- the energy is thereby
+                  evaluated at doubled displacements; restated as written)
+    Returns the [3,3] f64 array."""
+    cfg = cfg or GMNNConfig()
+    R, Z, idx, box, offsets = _as_inputs(R, Z, idx, box, offsets)
+    eps = torch.zeros((3, 3), dtype=torch.float64, requires_grad=True)
+    P = torch.eye(3, dtype=torch.float64) + eps
+    emb, dense, scale, shift = _params_to_torch(params)
+    if mode == "minimage":
+        d = compute_distances(R, idx, box, torch.zeros_like(offsets), "minimage")
+        d = torch.einsum("ij,nj->ni", P, d)
+    elif mode == "offsets":
+        d = compute_distances(R, idx, box, torch.zeros_like(offsets), "offsets")
+        d = d + torch.einsum("ij,nj->ni", P, d) + offsets
+    else:
+        raise ValueError(mode)
+    g, _ = gaussian_moment_descriptor(d, Z, idx, emb, cfg)
+    h = atomistic_readout(g, dense, cfg)
+    E_i = per_element_scale_shift(h, Z, scale, shift, cfg)
+    if cfg.mask_atoms:
+        E_i = E_i * (Z != 0).to(E_i.dtype)[:, None]
+    (gr,) = torch.autograd.grad(torch.sum(E_i.to(torch.float64)), eps)
+    return gr.numpy()

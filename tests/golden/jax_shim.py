@@ -171,6 +171,7 @@ jnp.array = lambda x, dtype=None: _t(x, dtype).clone() if isinstance(x, _T) else
 jnp.asarray = lambda x, dtype=None: _t(x, dtype)
 jnp.arange = lambda *a, dtype=None: torch.arange(*a, dtype=_to_torch_dtype(dtype))
 jnp.zeros = lambda shape, dtype=None: torch.zeros(tuple(shape) if not isinstance(shape, int) else (shape,), dtype=_to_torch_dtype(dtype) or torch.float64)
+jnp.eye = lambda n, dtype=None: torch.eye(n, dtype=_to_torch_dtype(dtype) or torch.float64)
 jnp.ones = lambda shape, dtype=None: torch.ones(tuple(shape) if not isinstance(shape, int) else (shape,), dtype=_to_torch_dtype(dtype) or torch.float64)
 jnp.full = lambda shape, v, dtype=None: torch.full(tuple(shape), v, dtype=_to_torch_dtype(dtype) or (torch.int64 if isinstance(v, int) else torch.float64))
 jnp.zeros_like = torch.zeros_like

@@ -307,6 +307,25 @@ def case_basis_variants(n_mol=6, seed=17):
     np.savez(os.path.join(HERE, "basis_variants.npz"), dr_grid=dr_grid, param_seed=41, **out)
 
 
+def case_stress(n_mol=64, seed=5):
+    """stress_times_vol (apax/layers/properties.py:11-42) through EnergyDerivativeModel(calc_stress=True) (models.py:160-169) on
+    the min-image path: perturbation applied as (I + eps) . dR by periodic_general (space.py:260-282)."""
+    pos, Z, cell = syn.water_box(n_mol, seed)
+    box = torch.as_tensor(cell.T.copy())
+    disp_fn, _ = space.periodic_general(box, fractional_coordinates=True)
+    nfn = partition.neighbor_list(disp_fn, box, 6.0, 0.0, fractional_coordinates=True, disable_cell_list=True,
+                                  format=partition.Sparse)
+    frac = space.transform(torch.linalg.inv(box), torch.as_tensor(pos))
+    nbrs = nfn.allocate(frac, box=box)
+    params = syn.gmnn_params(seed=1234, random_bias=True)
+    m = build_model(np.array(cell.T), inference_disp_fn=disp_fn)
+    m.calc_stress = True
+    offsets = torch.zeros((nbrs.idx.shape[1], 3), dtype=torch.int64)
+    res = np_out(m.apply(to_t(params), frac, torch.as_tensor(Z.astype(np.int64)), nbrs.idx.long(), box, offsets))
+    np.savez(os.path.join(HERE, "water_stress.npz"), frac=frac.numpy(), Z=Z, cell=cell, box=box.numpy(), idx=nbrs.idx.numpy(),
+             param_seed=1234, energy=res["energy"], forces=res["forces"], stress=res["stress"])
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     case_descriptor_unit()
@@ -325,3 +344,5 @@ if __name__ == "__main__":
     print("train_step ok")
     case_basis_variants()
     print("basis_variants ok")
+    case_stress()
+    print("stress ok")

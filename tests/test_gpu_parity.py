@@ -216,3 +216,22 @@ def test_truncated_contractions_and_ntk_linear(n_contr, use_ntk):
     g_ref = go.descriptor_only(params, frac, Z, idx, cell.T, offsets, "offsets", cfg)["g"]
     assert g.shape == (len(Z), n_feat)
     assert np.abs(g - g_ref).max() <= 2e-6 * np.abs(g_ref).max()
+
+
+def test_stress_times_vol_min_image(golden):
+    """stress x volume on the min-image path against the fixture written by the reference's own
+    stress_times_vol / EnergyDerivativeModel(calc_stress=True) source, and against the oracle in fp64."""
+    from apax_b200.nn.builder import GMNNBuilder
+    from oracle import gmnn_oracle as go
+
+    d = golden("water_stress")
+    params = syn.gmnn_params(seed=int(d["param_seed"]), random_bias=True)
+    model = GMNNBuilder({"calc_stress": True}).build_energy_derivative_model(init_box=d["box"], inference_disp_fn=object())
+    out = model.apply(params, d["frac"], d["Z"], d["idx"], d["box"], None)
+    torch.cuda.synchronize()
+    s = out["stress"].cpu().numpy()
+    ref64 = go.stress_times_vol(params, d["frac"], d["Z"], d["idx"], d["box"], None, "minimage", go.fp64_config())
+    scale = np.abs(ref64).max()
+    assert np.abs(s - d["stress"]).max() <= 2e-6 * scale                      # vs the reference source (fp32 model)
+    assert np.abs(s - ref64).max() <= 2.0 * np.abs(d["stress"] - ref64).max() + 1e-6 * scale
+    assert abs(float(out["energy"].item()) - float(d["energy"])) <= 1e-6 * abs(float(d["energy"]))

@@ -112,3 +112,16 @@ def test_basis_variants_against_reference_source(golden, name, kw):
     ref = go.energy_forces(params, d[name + "_frac"], d["Z"], d[name + "_idx"], d["cell"], d[name + "_offsets"], "offsets", cfg)
     assert np.abs(ref["forces"] - d[name + "_forces"]).max() <= 1e-6 * np.abs(d[name + "_forces"]).max() + 1e-7
     assert abs(ref["energy"] - float(d[name + "_energy"])) <= 1e-5
+
+
+def test_stress_oracle_against_reference_source(golden):
+    """stress_times_vol (apax/layers/properties.py:11-42) restated in the oracle vs the fixture from the reference's own source."""
+    from apax_b200 import synthetic as syn
+    from oracle import gmnn_oracle as go
+
+    d = golden("water_stress")
+    params = syn.gmnn_params(seed=int(d["param_seed"]), random_bias=True)
+    st = go.stress_times_vol(params, d["frac"], d["Z"], d["idx"], d["box"], None, "minimage")
+    assert np.abs(st - d["stress"]).max() <= 1e-6 * np.abs(d["stress"]).max()
+    # symmetric up to rounding (rotational invariance), and the offsets branch's doubled displacement is a different quantity
+    assert np.abs(st - st.T).max() <= 1e-5 * np.abs(st).max()
