@@ -11,6 +11,14 @@ random-init weights, synthetic seeded geometry).  A "step" is one E+F evaluation
   e2e   : the same metric through the host-buffer C-ABI call apax_ctx_calculate: host positions in,
           neighbour list rebuilt on the GPU every step, host energy+forces out (copies inside)
 One JSON line on stdout (rank 0).  The oracle is used only for the cpu_baseline / --impl reference legs.
+
+With N > 1 (torchrun) the same box is cut into N slabs (strong scaling); the halo exchange runs as this library's own
+kernels over NVLink peer memory (--nccl: torch.distributed all_to_all instead).  Other BASELINE configurations, each
+printing the same kind of line in the same unit:
+  --workload train     configs[1]: training step (energy+force loss, Adam), 32 ethanol-shaped molecules per GPU, weak scaling,
+                       gradient all-reduce + Adam fused in one peer-memory kernel (--nccl: NCCL all_reduce)
+  --workload md        configs[2]: NVT Nose-Hoover MD of the 12,288-atom water box, list rebuilt every 10 steps
+  --workload ensemble  configs[4]: 16-head shallow-ensemble inference on 4,096 independent 128-atom cells
 """
 from __future__ import annotations
 

@@ -131,3 +131,17 @@ def test_xla_ffi_shim_is_gated_on_jax():
     except Exception:
         with pytest.raises(bf.FfiUnavailable):
             bf.build_ffi()
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """The drop-in boundary must be bindable from C / cgo / JNI / ctypes: the header compiles as C99 without C++ or CUDA."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "apax_b200.h"\nint main(void) { apax_gm_config c; (void)c; return APAX_B200_ABI_VERSION == 2 ? 0 : 1; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, "-fsyntax-only", str(src)])
