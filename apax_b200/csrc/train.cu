@@ -985,8 +985,7 @@ __global__ void __launch_bounds__(64) k_tr_emb_pair(TrWs w, const int32_t* __res
 // 256 blocks share the (present species)^2 table blocks; each sums the cbar rows whose key matches: thread-strided
 // partial sums, then a fixed tree.
 constexpr int ER_BLOCKS = 256;
-__global__ void __launch_bounds__(128) k_tr_emb_reduce(TrWs w, int S, int ne, float* __restrict__ embbar,
-                                                       uint32_t* __restrict__ species_bitmap) {
+__global__ void __launch_bounds__(128) k_tr_emb_reduce(TrWs w, int S, int ne, float* __restrict__ embbar) {
   constexpr int MAXE = NR * MAXNB;   // coefficients per species pair
   __shared__ float red[128][MAXE + 1];
   __shared__ int list[128];
@@ -1002,8 +1001,6 @@ __global__ void __launch_bounds__(128) k_tr_emb_reduce(TrWs w, int S, int ne, fl
     for (int q = 0; q < wid; ++q) base += warp_cnt[q];
     if (on) list[base + __popc(bal & ((1u << lane) - 1u))] = z;
     if (threadIdx.x == 0) n_list = warp_cnt[0] + warp_cnt[1] + warp_cnt[2] + warp_cnt[3];
-    // species present in this batch, 128 bits: lets the peer-memory all-reduce skip the all-zero embedding rows
-    if (species_bitmap && blockIdx.x == 0 && lane == 0) species_bitmap[wid] = bal;
   }
   __syncthreads();
   const int np = n_list;
@@ -1049,7 +1046,6 @@ struct AdamArgs {
   int64_t transition_steps, transition_begin;
   int64_t emb_count;    // elements [0, emb_count) of the fp32 block are the embedding group
   int64_t n32, n64, S;
-  int64_t emb_row, emb_rows;   // embedding block: emb_rows = S*S rows of emb_row = 5 n_basis elements
 };
 
 __device__ __forceinline__ double sched(double init, int64_t count, const AdamArgs& a) {
@@ -1156,32 +1152,12 @@ __global__ void __launch_bounds__(256) k_tr_adam_peer(AdamArgs a, PeerArgs pa, f
     const uint32_t* mine = pa.flags[pa.rank] + threadIdx.x;
     while (int32_t(ld_acquire_sys(mine) - pa.epoch) < 0) __nanosleep(64);
   }
-  // every rank's species bitmap (written behind its fp64 block by apax_train_loss_and_grad): an embedding row whose
-  // species pair is absent from a rank's batch is all zero there and is not fetched
-  __shared__ uint32_t s_bits[8][4];
-  if (threadIdx.x < pa.world * 4) {
-    const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
-    s_bits[r][q] = __ldcg(reinterpret_cast<const uint32_t*>(pa.g64[r] + a.n64 + 2) + q);
-  }
   __syncthreads();
   const AdamScalars sc = *reinterpret_cast<const AdamScalars*>(opt_state + 1);
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (4 * i < a.n32) {
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    // species pairs touched by elements 4i .. 4i+3 of the embedding block (rows of a.emb_row elements, [S][S] of them)
-    int z0c = -1, z0n = 0, z1c = 0, z1n = 0;
-    if (4 * i + 3 < a.emb_rows * a.emb_row) {   // 32-bit arithmetic: the embedding block has < 2^31 elements
-      const unsigned row = unsigned(a.emb_row), S = unsigned(a.S), e0 = unsigned(4 * i);
-      const unsigned p0 = e0 / row, p1 = (e0 + 3u) / row;
-      z0c = int(p0 / S); z0n = int(p0 % S); z1c = int(p1 / S); z1n = int(p1 % S);
-    }
     for (int r = 0; r < pa.world; ++r) {
-      if (z0c >= 0) {
-        const uint32_t* b = s_bits[r];
-        const bool on0 = ((b[z0c >> 5] >> (z0c & 31)) & 1u) && ((b[z0n >> 5] >> (z0n & 31)) & 1u);
-        const bool on1 = ((b[z1c >> 5] >> (z1c & 31)) & 1u) && ((b[z1n >> 5] >> (z1n & 31)) & 1u);
-        if (!on0 && !on1) continue;
-      }
       const float4 t = __ldcg(pa.g32[r] + i);
       g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
     }
@@ -1409,8 +1385,7 @@ static int train_run(bool grads, apax_stream_t stream_, const apax_train_plan* p
   // moments' adjoint incl. the second-order term, then the embedding gradient
   APAX_LAUNCH(k_tr_contract_bwd, dim3((unsigned)cdiv(n, CT_ATOMS)), dim3(NPK * CB_LANES), 0, s, tab, w.M, w.Md, w.GB, w.GB + n * NF, w.Mb2, n);
   APAX_LAUNCH(k_tr_emb_pair, dim3((unsigned)n), dim3(64), 0, s, w, idx, dc);
-  APAX_LAUNCH(k_tr_emb_reduce, dim3(ER_BLOCKS), dim3(128), 0, s, w, S, NR * p->cfg.n_basis, g_emb,
-              reinterpret_cast<uint32_t*>(grad64 + p->off64[2] + 2));
+  APAX_LAUNCH(k_tr_emb_reduce, dim3(ER_BLOCKS), dim3(128), 0, s, w, S, NR * p->cfg.n_basis, g_emb);
   return APAX_OK;
 }
 
@@ -1442,8 +1417,7 @@ extern "C" int apax_train_adam_step(apax_stream_t stream_, const apax_train_plan
     return APAX_ERR_INVALID_ARG;
   if (oc->transition_steps < 1) return APAX_ERR_INVALID_ARG;
   AdamArgs a{oc->emb_lr, oc->nn_lr, oc->scale_lr, oc->shift_lr, oc->gradient_clipping, oc->end_value, oc->b1, oc->b2, oc->eps,
-             oc->transition_steps, oc->transition_begin, p->off32[1], p->off32[7], p->off64[2], p->cfg.n_species,
-             int64_t(NR) * p->cfg.n_basis, int64_t(p->cfg.n_species) * p->cfg.n_species};
+             oc->transition_steps, oc->transition_begin, p->off32[1], p->off32[7], p->off64[2], p->cfg.n_species};
   APAX_LAUNCH(k_tr_adam_prep, dim3(1), dim3(1), 0, s, a, opt_state);
   APAX_LAUNCH(k_tr_adam, dim3((unsigned)cdiv(std::max(a.n32 / 4, a.n64), 256)), dim3(256), 0, s, a,
               reinterpret_cast<float4*>(theta32), reinterpret_cast<const float4*>(grad32), reinterpret_cast<float4*>(m32),
@@ -1505,8 +1479,7 @@ extern "C" int apax_train_allreduce_adam_step(apax_stream_t stream_, const apax_
   }
   pa.world = peers->world; pa.rank = peers->rank; pa.epoch = epoch;
   AdamArgs a{oc->emb_lr, oc->nn_lr, oc->scale_lr, oc->shift_lr, oc->gradient_clipping, oc->end_value, oc->b1, oc->b2, oc->eps,
-             oc->transition_steps, oc->transition_begin, p->off32[1], p->off32[7], p->off64[2], p->cfg.n_species,
-             int64_t(NR) * p->cfg.n_basis, int64_t(p->cfg.n_species) * p->cfg.n_species};
+             oc->transition_steps, oc->transition_begin, p->off32[1], p->off32[7], p->off64[2], p->cfg.n_species};
   APAX_LAUNCH(k_tr_adam_prep, dim3(1), dim3(1), 0, s, a, opt_state);
   APAX_LAUNCH(k_tr_adam_peer, dim3((unsigned)cdiv(std::max(a.n32 / 4, a.n64 + 1), 256)), dim3(256), 0, s, a, pa,
               reinterpret_cast<float4*>(theta32), reinterpret_cast<float4*>(m32), reinterpret_cast<float4*>(v32), theta64, m64,

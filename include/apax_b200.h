@@ -249,9 +249,7 @@ int apax_md_nvt_post_force(apax_stream_t stream, const apax_md_nvt_config* cfg, 
  * calls (data parallelism over structures, apax/train/trainer.py:101-106) and capture the step in a CUDA graph:
  *   theta32 / grad32 / m32 / v32 : f32 blocks of offsets32[7] elements laid out as apax_train_param_layout says
  *                                  (atomic_type_embedding [S][S][5][n_basis], dense_0 w [360][256], b, dense_1 w, b, dense_2 w, b)
- *   theta64 / grad64 / m64 / v64 : f64 [2 S] = scale_per_element, shift_per_element.  grad64 has 8 more elements: [2S] and
- *                                  [2S+1] are the caller's (the mirrors put the step's loss in [2S]); apax_train_loss_and_grad
- *                                  writes the 128-bit set of species present in the batch into [2S+2], [2S+3]
+ *   theta64 / grad64 / m64 / v64 : f64 [2 S] = scale_per_element, shift_per_element
  * Batch layout = apax_gm_energy_forces_batched: atoms of all structures concatenated, Cartesian positions,
  * idx i32 [2][n_pairs] with GLOBAL atom indices, offsets f64 [n_pairs][3] or NULL; struct_ptr / pair_ptr i32
  * [n_structs+1] give each structure's atom and COO-entry ranges; n_real i32 [n_structs] is inputs["n_atoms"]
