@@ -114,6 +114,7 @@ SIGNATURES = {
     "apax_halo_push_rows": (C.c_int, [_P, _P, _P, _P, C.POINTER(HaloPeers), C.c_uint32]),
     "apax_halo_pull_add_rows": (C.c_int, [_P, _P, _P, _P, C.POINTER(HaloPeers), C.c_uint32, _P, _P, _I32]),
     "apax_ensemble_stats": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, _P]),
+    "apax_md_nvt_run": (C.c_int, [_P, C.POINTER(MdNvtConfig), _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, C.c_size_t, _I32]),
     "apax_ctx_create": (C.c_int, [_P, _I64, _I64, C.POINTER(_P)]),
     "apax_ctx_destroy": (None, [_P]),
     "apax_ctx_calculate": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, _I32, _P, _P, _P]),

@@ -235,3 +235,21 @@ extern "C" int apax_md_nvt_post_force(apax_stream_t stream, const apax_md_nvt_co
   APAX_LAUNCH(k_md_scale, dim3((unsigned)cdiv(3 * n_atoms, 256)), dim3(256), 0, stream, P, st, 3 * n_atoms);
   return APAX_OK;
 }
+
+// Several MD steps between two neighbour-list decisions in ONE call: the inner loop of apax's MD driver
+// (apax/md/simulate.py:313-354; jax.lax.fori_loop over `apply_fn`) without returning to the host language between steps.
+// Each step is apax_md_nvt_pre_force -> apax_gm_compute (MINIMAGE, the list prepared in `workspace`) -> apax_md_nvt_post_force,
+// all asynchronous on `stream`; at 10^4 atoms a step is ~26 short kernels, so the host-side cost per launch is what counts.
+extern "C" int apax_md_nvt_run(apax_stream_t stream, const apax_md_nvt_config* cfg, const apax_gm_params* params, double* R_frac,
+                               double* P, double* F, const double* mass, const int32_t* Z, const double* box, int64_t n_atoms,
+                               int64_t n_pairs, void* state, double* energy, void* workspace, size_t workspace_bytes,
+                               int32_t n_steps) {
+  if (n_steps < 0) return APAX_ERR_INVALID_ARG;
+  for (int32_t i = 0; i < n_steps; ++i) {
+    APAX_TRY(apax_md_nvt_pre_force(stream, cfg, R_frac, P, F, mass, box, n_atoms, state));
+    APAX_TRY(apax_gm_compute(stream, params, R_frac, Z, box, nullptr, n_atoms, n_pairs, APAX_DISP_MINIMAGE, energy, F, workspace,
+                             workspace_bytes));
+    APAX_TRY(apax_md_nvt_post_force(stream, cfg, P, F, mass, n_atoms, state));
+  }
+  return APAX_OK;
+}

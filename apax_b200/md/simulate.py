@@ -92,6 +92,26 @@ def run_nvt(params, atoms, model_config=None, *, dt: float, kT: float, n_steps: 
         return orig_force(R)
 
     init_fn2, apply_fn = nvt_nose_hoover(stepping_force, None, dt, kT, chain_length, chain_steps, sy_steps, tau)
+    if rebuild_every is not None and on_step is None and dp.n_out == 1:
+        # fixed rebuild cadence: all steps between two list builds go down in ONE library call (apax_md_nvt_run), as the
+        # reference runs them inside one jitted fori_loop (apax/md/simulate.py:313-354)
+        import ctypes as C
+
+        e_dev = torch.zeros(1, dtype=torch.float64, device=state.position.device)
+        done = 0
+        while done < n_steps:
+            if done > 0 and done % rebuild_every == 0:
+                maybe_rebuild(done)
+            k = min(rebuild_every - done % rebuild_every, n_steps - done)
+            ps = system["prepared"]
+            state.force = state.force.contiguous()
+            rt.check(rt.lib().apax_md_nvt_run(rt._stream_ptr(), C.byref(apply_fn.cfg), dp.handle, rt._ptr(state.position),
+                                              rt._ptr(state.momentum), rt._ptr(state.force), rt._ptr(state.mass), rt._ptr(ps.Z),
+                                              rt._ptr(box_d), ps.n_atoms, ps.n_pairs, rt._ptr(state.chain), rt._ptr(e_dev), ps.wp,
+                                              ps.wb, int(k)), "apax_md_nvt_run")
+            done += k
+        counters["steps"] = n_steps
+        return state, counters
     for _ in range(n_steps):
         counters["steps"] += 1
         state = apply_fn(state, box=box_d)

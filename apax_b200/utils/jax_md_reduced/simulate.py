@@ -70,4 +70,5 @@ def nvt_nose_hoover(energy_or_force_fn: Callable, shift_fn=None, dt: float = 1e-
                                            rt._ptr(state.mass), n, rt._ptr(state.chain)), "apax_md_nvt_post_force")
         return state
 
+    apply_fn.cfg = cfg        # for apax_md_nvt_run (several steps per call)
     return init_fn, apply_fn

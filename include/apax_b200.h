@@ -234,6 +234,13 @@ int apax_md_nvt_pre_force(apax_stream_t stream, const apax_md_nvt_config* cfg, d
                           const double* F, const double* mass, const double* box, int64_t n_atoms, void* state);
 int apax_md_nvt_post_force(apax_stream_t stream, const apax_md_nvt_config* cfg, double* P, const double* F,
                            const double* mass, int64_t n_atoms, void* state);
+/* n_steps steps in one call -- the jax.lax.fori_loop over apply_fn between two neighbour-list decisions
+ * (apax/md/simulate.py:313-354): pre_force -> apax_gm_compute (MINIMAGE, list already prepared in `workspace` with
+ * apax_gm_prepare, n_out == 1) -> post_force, repeated.  F holds the forces of the current positions on entry and on
+ * exit; energy f64 [1] receives the last step's potential energy. */
+int apax_md_nvt_run(apax_stream_t stream, const apax_md_nvt_config* cfg, const apax_gm_params* params, double* R_frac,
+                    double* P, double* F, const double* mass, const int32_t* Z, const double* box, int64_t n_atoms,
+                    int64_t n_pairs, void* state, double* energy, void* workspace, size_t workspace_bytes, int32_t n_steps);
 
 /* ------------------------------------------------------------------------------------------------
  * Training step (BASELINE configs[1]).  Replaces, for the GMNN model with an energy + forces MSE loss,

@@ -116,3 +116,27 @@ def test_nvt_kernels_against_reference_fixture(golden):
             assert np.abs(ch["p_xi"][:5] - d[f"p_xi_{step}"]).max() < 1e-11
             assert np.array_equal(ch["Q"][:5], d[f"Q_{step}"])
             assert abs(ch["KE"] - float(d[f"KE_{step}"])) < 1e-11
+
+
+def test_multi_step_call_follows_the_per_step_loop():
+    """apax_md_nvt_run (all steps between two list builds in one library call) against the per-step host loop: same
+    integrator and forces; the lists are rebuilt from positions one half-step apart, both valid thanks to the skin, so
+    the trajectories agree to fp32 summation noise."""
+    from apax_b200.md.ase_calc import Atoms
+    from apax_b200.md.simulate import run_nvt
+
+    pos, Z, cell = syn.water_box(64, 5)
+    params = syn.gmnn_params(seed=4)
+    params["params"]["energy_model"]["scale_shift"]["scale_per_element"][:] = 0.02
+    mass = np.array([MASS[int(z)] for z in Z])
+    rng = np.random.default_rng(3)
+    p0 = rng.normal(size=(len(Z), 3)) * np.sqrt(mass * 0.0259)[:, None]
+    p0 -= p0.mean(0)
+    kw = dict(dt=0.02, kT=0.0259, n_steps=25, masses=mass, momentum=p0, rebuild_every=10)
+    fast, c_fast = run_nvt(params, Atoms(pos, Z, cell), **kw)
+    slow, c_slow = run_nvt(params, Atoms(pos, Z, cell), on_step=lambda i, s: None, **kw)
+    assert c_fast["steps"] == c_slow["steps"] == 25 and c_fast["rebuilds"] == c_slow["rebuilds"] == 2
+    dR = (fast.position - slow.position).cpu().numpy()
+    dR -= np.round(dR)
+    assert np.abs(dR).max() < 1e-7
+    assert np.abs((fast.momentum - slow.momentum).cpu().numpy()).max() < 1e-5 * np.abs(slow.momentum.cpu().numpy()).max()
