@@ -219,3 +219,34 @@ def test_val_step_returns_loss_without_updating():
     (state, _), loss2 = train_step((state, None), (inputs, labels))
     assert state.step == 1 and not torch.equal(before, state.theta32)
     assert abs(float(loss2.item()) - ref["loss"]) <= 2e-6 * abs(ref["loss"])
+
+
+def test_periodic_128_atom_cells_training_gradients():
+    """Training on realistic periodic structures: two 128-atom water cells (multi-image lists, ~11.6 k entries each, more
+    entries per structure than the shared-memory staging of the list grouping holds) against the oracle."""
+    from oracle import gmnn_oracle as go
+    from oracle import neighbor_oracle as no
+    from oracle import train_oracle as tor
+
+    rng = np.random.default_rng(5)
+    items = []
+    for s in range(2):
+        pos, Z, cell = syn.cell_128(40 + s)
+        idx, off = no.vesin_idx_offsets(pos, cell, 6.0)
+        items.append((pos @ np.linalg.inv(cell), Z, cell.T.copy(), idx, off))
+    pmax = max(it[3].shape[1] for it in items)
+    assert pmax > 3072
+    inputs = {"positions": np.stack([it[0] for it in items]), "numbers": np.stack([it[1] for it in items]).astype(np.int32),
+              "idx": np.zeros((2, 2, pmax), dtype=np.int32), "box": np.stack([it[2] for it in items]),
+              "offsets": np.zeros((2, pmax, 3)), "n_atoms": np.array([128, 128], dtype=np.int32)}
+    for s, it in enumerate(items):
+        inputs["idx"][s, :, : it[3].shape[1]] = it[3]
+        inputs["offsets"][s, : it[3].shape[1]] = it[4]
+    labels = {"energy": rng.normal(size=2) * 10, "forces": rng.normal(size=(2, 128, 3))}
+    params = syn.gmnn_params(seed=6, random_bias=True, random_scale_shift=True)
+    ref = tor.loss_and_grads(params, inputs, labels, mode="offsets")
+    ref64 = tor.loss_and_grads(params, inputs, labels, mode="offsets", cfg=go.fp64_config())
+    loss, e, f, grads, _ = _gpu_loss_grads(params, inputs, labels, tor.DEFAULT_LOSS)
+    assert abs(loss - ref["loss"]) <= 2e-6 * abs(ref["loss"])
+    assert np.abs(f - ref64["forces"]).max() <= 2.0 * np.abs(ref["forces"] - ref64["forces"]).max() + 1e-5 * np.abs(ref["forces"]).max()
+    _check_grads(grads, ref["grads"], ref64["grads"], where="periodic-128")
