@@ -58,6 +58,12 @@ class HaloPeers(C.Structure):
     _fields_ = [("rows", C.c_void_p * 8), ("header", C.c_void_p * 8), ("world", C.c_int32), ("rank", C.c_int32)]
 
 
+class GmCorrections(C.Structure):
+    _fields_ = [("zbl_on", C.c_int32), ("zbl_r_max", C.c_float), ("zbl_coefficients", C.c_float * 4), ("zbl_rep_scale", C.c_float),
+                ("exp_on", C.c_int32), ("exp_r_max", C.c_float), ("exp_rep_scale_host", C.c_void_p),
+                ("exp_rep_prefactor_host", C.c_void_p)]
+
+
 class MdNvtConfig(C.Structure):
     _fields_ = [("chain_length", C.c_int32), ("chain_steps", C.c_int32), ("sy_steps", C.c_int32), ("dt", C.c_double),
                 ("kT", C.c_double), ("tau", C.c_double)]
@@ -74,6 +80,7 @@ SIGNATURES = {
     "apax_profile_enable": (C.c_int, [C.c_int]),
     "apax_profile_collect": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "apax_gm_params_create": (C.c_int, [C.POINTER(GmConfig), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
+    "apax_gm_params_set_corrections": (C.c_int, [_P, C.POINTER(GmCorrections)]),
     "apax_gm_params_destroy": (None, [_P]),
     "apax_gm_params_status": (C.c_int, [_P]),
     "apax_gm_workspace_bytes": (C.c_size_t, [_I64, _I64, _I32]),

@@ -49,6 +49,7 @@ size_t carve_gm_workspace(void* base, int64_t n_atoms, int64_t n_pairs, int32_t 
   w.scan_scratch = c.take<int32_t>(scan_scratch_ints(N + 1));
   w.sp_present = c.take<int32_t>(128);
   w.sp_map = c.take<int32_t>(128);
+  w.sp_z = c.take<int32_t>(128);
   w.n_sp = c.take<int32_t>(4);
   w.embc = c.take<float>(int64_t(n_species) * n_species * EMB_STRIDE);
   w.P = c.take<double4>(N + 1);
@@ -125,7 +126,8 @@ __global__ void __launch_bounds__(128) k_species_mark(const int32_t* __restrict_
 
 __global__ void __launch_bounds__(256) k_species_build(const int32_t* __restrict__ present, int S,
                                                        const float* __restrict__ emb, int32_t* __restrict__ sp_map,
-                                                       int32_t* __restrict__ n_sp_out, float* __restrict__ embc) {
+                                                       int32_t* __restrict__ n_sp_out, float* __restrict__ embc,
+                                                       int32_t* __restrict__ sp_z) {
   __shared__ int zs[128];
   __shared__ int n_sp;
   if (threadIdx.x == 0) {
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(256) k_species_build(const int32_t* __restrict
     for (int z = 0; z < S; ++z) {
       if (present[z]) {
         sp_map[z] = n;
+        sp_z[n] = z;
         zs[n++] = z;
       } else {
         sp_map[z] = 0;
@@ -212,7 +215,7 @@ static int gm_prepare_tail(cudaStream_t stream, const apax_gm_params_impl* p, co
   }
   APAX_CUDA_TRY(cudaMemsetAsync(w.sp_present, 0, sizeof(int32_t) * 128, stream));
   APAX_LAUNCH(k_species_mark, dim3((unsigned)cdiv(N, 128)), dim3(128), 0, stream, Z, N, S, w.sp_present);
-  APAX_LAUNCH(k_species_build, dim3(1), dim3(256), 0, stream, w.sp_present, S, p->emb, w.sp_map, w.n_sp, w.embc);
+  APAX_LAUNCH(k_species_build, dim3(1), dim3(256), 0, stream, w.sp_present, S, p->emb, w.sp_map, w.n_sp, w.embc, w.sp_z);
   return APAX_OK;
 }
 
@@ -250,7 +253,7 @@ int gm_prepare_from_csr(cudaStream_t stream, const apax_gm_params_impl* p, const
   const int S = p->cfg.n_species;
   APAX_CUDA_TRY(cudaMemsetAsync(w.sp_present, 0, sizeof(int32_t) * 128, stream));
   APAX_LAUNCH(k_species_mark, dim3((unsigned)cdiv(N, 128)), dim3(128), 0, stream, Z, N, S, w.sp_present);
-  APAX_LAUNCH(k_species_build, dim3(1), dim3(256), 0, stream, w.sp_present, S, p->emb, w.sp_map, w.n_sp, w.embc);
+  APAX_LAUNCH(k_species_build, dim3(1), dim3(256), 0, stream, w.sp_present, S, p->emb, w.sp_map, w.n_sp, w.embc, w.sp_z);
   return APAX_OK;
 }
 
@@ -590,6 +593,10 @@ __global__ void __launch_bounds__(256) k_force_gather(GmWorkspace ws, double* __
     if (t < 0) continue;  // unmatched boundary pair of a symmetric list: zero contribution
     const float4 d = ws.D[t];
     tx += double(d.x); ty += double(d.y); tz += double(d.z);
+    if (d.w != 0.0f) {   // empirical corrections: the pair's dE_corr/dr / r rides in .w, the vector is rebuilt in fp64
+      const float4 g = ws.G[t];
+      tx += double(d.w) * double(g.x); ty += double(d.w) * double(g.y); tz += double(d.w) * double(g.z);
+    }
   }
 #pragma unroll
   for (int o = LPA / 2; o > 0; o >>= 1) {
@@ -935,6 +942,116 @@ __global__ void k_energy_final(const double* __restrict__ partial, int n_blocks,
 // ================================================================================================
 // host orchestration
 // ================================================================================================
+// ---- pairwise empirical corrections (apax/layers/empirical.py): ZBLRepulsion (:25-86) and ExponentialRepulsion (:89-126).
+// E_corr = w * sum over list entries of E_ij(r) with w = 0.5 softplus(rep_scale) (ZBL) or 1 (exponential); both are
+// evaluated in fp32 per entry and summed in fp64, like the reference (fp64_sum).  The distance is clipped to
+// [0.02, r_max] (zero slope outside), the cosine cutoff ends at the correction's own r_max.
+__device__ __forceinline__ void corr_pair(const CorrConst& cc, float r, int zi, int zj, float& e, float& dedr) {
+  e = 0.f; dedr = 0.f;
+  const float pi_f = 3.14159265358979323846f;
+  if (cc.zbl_on) {
+    const float dr = fminf(fmaxf(r, 0.02f), cc.zbl_rmax);
+    const bool inside = r > 0.02f && r < cc.zbl_rmax;
+    float sn, cs;
+    sincosf(pi_f * dr / cc.zbl_rmax, &sn, &cs);
+    const float fc = 0.5f * (cs + 1.0f), dfc = -0.5f * (pi_f / cc.zbl_rmax) * sn;
+    const float fi = float(zi), fj = float(zj);
+    const float a_div = powf(fi, 0.23f) + powf(fj, 0.23f), k = a_div / 0.46850f;
+    const float dist = dr * k;
+    float f = 0.f, df = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float t = cc.zbl_c[q] * expf(-cc.zbl_e[q] * dist);
+      f += t;
+      df -= cc.zbl_e[q] * k * t;
+    }
+    const float pref = fi * fj / dr;
+    const float w = 0.5f * cc.zbl_scale;
+    e += w * (pref * f * fc);
+    if (inside) dedr += w * pref * (-f * fc / dr + df * fc + f * dfc);
+  }
+  if (cc.exp_on) {
+    const float dr = fminf(fmaxf(r, 0.02f), cc.exp_rmax);
+    const bool inside = r > 0.02f && r < cc.exp_rmax;
+    float sn, cs;
+    sincosf(pi_f * dr / cc.exp_rmax, &sn, &cs);
+    const float fc = 0.5f * (cs + 1.0f), dfc = -0.5f * (pi_f / cc.exp_rmax) * sn;
+    const float ri = cc.exp_r[zi], rj = cc.exp_r[zj];
+    const float k = (ri + rj) / (ri * rj);
+    const float f = cc.exp_a[zi] * cc.exp_a[zj] * expf(-dr * k) / (dr * dr);
+    e += f * fc;
+    if (inside) dedr += f * (-k - 2.0f / dr) * fc + f * dfc;
+  }
+}
+
+// warp per central atom.  FORCES = 0: Eatom[h][atom] += correction energy of the atom's row, for every head (before the
+// energy sums).  FORCES = 1: D[slot].w = dE_corr/dr / r and Frow[atom] += the row sum of the vectors (after k_pair_bwd, before
+// the gather).
+template <int FORCES>
+__global__ void __launch_bounds__(256) k_pair_corrections(GmWorkspace ws, PairGeom geo, CorrConst cc, int n_out) {
+  const int64_t atom = (int64_t(blockIdx.x) * 256 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (atom >= ws.n_central) return;
+  const int n_sp = *ws.n_sp;
+  const float r_far = 1.0001f * fmaxf(cc.zbl_on ? cc.zbl_rmax : 0.f, cc.exp_on ? cc.exp_rmax : 0.f);
+  const bool plain = geo.mode == APAX_DISP_GAS || geo.mode == APAX_DISP_DRVEC;
+  double box[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) box[i] = plain ? 0.0 : __ldg(geo.box + i);
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+  for (int s = ws.rowptr[atom] + lane; s < ws.rowptr[atom + 1]; s += 32) {
+    const float4 g = ws.G[s];
+    const float r2 = g.x * g.x + g.y * g.y + g.z * g.z;
+    if (!(r2 < r_far * r_far)) continue;
+    // The reference takes the distance of these terms from the fp64 displacement (self.distance(dr_vec).astype(dtype),
+    // empirical.py:56) -- the repulsion is steep enough for the fp32 rounding of the displacement to show -- so the few
+    // entries in range get their displacement again in fp64 (distances.py:48-67, as in k_pair_fwd).
+    double d0, d1, d2;
+    const int64_t coo = ws.src[s];
+    if (geo.mode == APAX_DISP_DRVEC) {
+      d0 = geo.R[3 * coo]; d1 = geo.R[3 * coo + 1]; d2 = geo.R[3 * coo + 2];
+    } else {
+      const int64_t j = ws.nbr[s];
+      double v0 = geo.R[3 * atom] - geo.R[3 * j], v1 = geo.R[3 * atom + 1] - geo.R[3 * j + 1], v2 = geo.R[3 * atom + 2] - geo.R[3 * j + 2];
+      if (geo.mode == APAX_DISP_MINIMAGE) { v0 = wrap_unit(v0); v1 = wrap_unit(v1); v2 = wrap_unit(v2); }
+      if (geo.mode == APAX_DISP_GAS) {
+        d0 = v0; d1 = v1; d2 = v2;
+      } else {
+        d0 = box[0] * v0 + box[1] * v1 + box[2] * v2;
+        d1 = box[3] * v0 + box[4] * v1 + box[5] * v2;
+        d2 = box[6] * v0 + box[7] * v1 + box[8] * v2;
+        if (geo.offsets) { d0 += geo.offsets[3 * coo]; d1 += geo.offsets[3 * coo + 1]; d2 += geo.offsets[3 * coo + 2]; }
+      }
+    }
+    const double r64sq = d0 * d0 + d1 * d1 + d2 * d2;
+    const float r = r64sq > 0.0 ? float(sqrt(r64sq)) : 0.f;
+    const int pt = __float_as_int(g.w);
+    float e, dedr;
+    corr_pair(cc, r, ws.sp_z[pt / n_sp], ws.sp_z[pt % n_sp], e, dedr);
+    if (FORCES) {
+      // the correction's share of dE/d(dr) is kept apart from the descriptor's fp32 value: its scalar dE_corr/dr / r goes
+      // into the spare lane of D and the vector is formed in fp64 wherever it is summed (here, in the transpose gather and
+      // in the virial), as the reference accumulates it in the fp64 position gradient
+      const float k = r > 0.f ? dedr / r : 0.f;
+      reinterpret_cast<float*>(ws.D + s)[3] = k;
+      acc0 += double(k) * double(g.x); acc1 += double(k) * double(g.y); acc2 += double(k) * double(g.z);
+    } else {
+      acc0 += double(e);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+    if (FORCES) { acc1 += __shfl_xor_sync(0xffffffffu, acc1, o); acc2 += __shfl_xor_sync(0xffffffffu, acc2, o); }
+  }
+  if (lane != 0) return;
+  if (FORCES) {
+    ws.Frow[3 * atom + 0] += acc0; ws.Frow[3 * atom + 1] += acc1; ws.Frow[3 * atom + 2] += acc2;
+  } else {
+    for (int h = 0; h < n_out; ++h) ws.Eatom[int64_t(h) * ws.ld + atom] += acc0;
+  }
+}
+
 // ---- stress x volume: dU/d(eps) = sum over list entries of dE/d(dr) (x) dr, for the strain applied as dr' = (I + eps) dr
 // (apax/layers/properties.py:11-42 with periodic_general's perturbation, space.py:277-278).  Fixed-shape two-stage sum in
 // fp64 over the fp32 per-pair values the force pass left in the workspace.
@@ -951,9 +1068,12 @@ __global__ void __launch_bounds__(256) k_virial_partial(const float4* __restrict
   for (int q = 0; q < 9; ++q) acc[q] = 0.0;
   for (int64_t s = b + threadIdx.x; s < e; s += blockDim.x) {
     const float4 d = D[s], g = G[s];
-    acc[0] += double(d.x) * double(g.x); acc[1] += double(d.x) * double(g.y); acc[2] += double(d.x) * double(g.z);
-    acc[3] += double(d.y) * double(g.x); acc[4] += double(d.y) * double(g.y); acc[5] += double(d.y) * double(g.z);
-    acc[6] += double(d.z) * double(g.x); acc[7] += double(d.z) * double(g.y); acc[8] += double(d.z) * double(g.z);
+    const double dx = double(d.x) + double(d.w) * double(g.x);   // .w: empirical corrections (0 without them)
+    const double dy = double(d.y) + double(d.w) * double(g.y);
+    const double dz = double(d.z) + double(d.w) * double(g.z);
+    acc[0] += dx * double(g.x); acc[1] += dx * double(g.y); acc[2] += dx * double(g.z);
+    acc[3] += dy * double(g.x); acc[4] += dy * double(g.y); acc[5] += dy * double(g.z);
+    acc[6] += dz * double(g.x); acc[7] += dz * double(g.y); acc[8] += dz * double(g.z);
   }
 #pragma unroll
   for (int q = 0; q < 9; ++q) red[threadIdx.x][q] = acc[q];
@@ -1066,8 +1186,11 @@ static int readout_mode() {
   return mode;
 }
 
-static int energy_sums(cudaStream_t stream, const GmWorkspace& w, int n_out, double* energy) {
+static int energy_sums(cudaStream_t stream, const GmWorkspace& w, int n_out, double* energy, const CorrConst* cc = nullptr,
+                       const PairGeom* geo = nullptr) {
   const int64_t N = w.n_central, ld = w.ld;
+  if (cc && geo && (cc->zbl_on || cc->exp_on))   // the corrections' energy joins the per-atom energies before they are summed
+    APAX_LAUNCH(k_pair_corrections<0>, dim3((unsigned)cdiv(N * 32, 256)), dim3(256), 0, stream, w, *geo, *cc, n_out);
   if (w.n_seg > 0) {
     APAX_LAUNCH(k_energy_segments, dim3((unsigned)w.n_seg, n_out), dim3(32), 0, stream, w.Eatom, ld, w.seg_ptr, n_out, energy);
     return APAX_OK;
@@ -1090,7 +1213,7 @@ static int readout_head_and_energy(cudaStream_t stream, const apax_gm_params_imp
     APAX_LAUNCH(k_head<MAX_OUT>, dim3((unsigned)m_tiles), dim3(128), 0, stream, w.H2T, h2_lo, ld, N, p->w2, p->b2,
                 n_out, geo.Z, p->cfg.n_species, p->scale, p->shift, p->cfg.mask_atoms, w.Eatom, w.ebar);
   }
-  return energy_sums(stream, w, n_out, energy);
+  return energy_sums(stream, w, n_out, energy, &p->corr, &geo);
 }
 
 // ---- readout forward + (per head) backward down to dE/dg in GT, on the fp32 CUDA cores
@@ -1217,7 +1340,7 @@ static int readout_i8(cudaStream_t stream, const apax_gm_params_impl* p, const G
       APAX_LAUNCH(k_head_scale_shift<MAX_OUT>, dim3((unsigned)m_tiles), dim3(128), 0, stream, h_out, ld, N, p->b2, n_out,
                   geo.Z, p->cfg.n_species, p->scale, p->shift, p->cfg.mask_atoms, w.Eatom, w.ebar);
     }
-    return energy_sums(stream, w, n_out, energy);
+    return energy_sums(stream, w, n_out, energy, &p->corr, &geo);
   }
   {  // dE/dy1 = swish'(y1) * ebar * (W1 w2[head]) . swish'(y2)  -> digit planes
     const I8Planes act{d2q, ld, NH, ld * int64_t(NH), 4};
@@ -1266,6 +1389,8 @@ static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
     APAX_TRY(readout(head));
     APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(N, kContractThreads)), dim3(kContractThreads), 0, stream, w);
     APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc);
+    if (p->corr.zbl_on || p->corr.exp_on)
+      APAX_LAUNCH(k_pair_corrections<1>, dim3((unsigned)cdiv(N * 32, 256)), dim3(256), 0, stream, w, geo, p->corr, n_out);
     APAX_DISPATCH_LPA(pick_lpa(w.n_atoms), launch_force_gather, stream, w, forces + int64_t(head) * w.n_atoms * 3);
   }
   return APAX_OK;
@@ -1461,6 +1586,8 @@ extern "C" void apax_gm_params_destroy(apax_gm_params* p) {
   cudaFree(p->b1); cudaFree(p->w2); cudaFree(p->b2); cudaFree(p->scale); cudaFree(p->shift);
   cudaFree(p->w1t_head);
   cudaFree(p->eye);
+  if (p->corr.exp_r) cudaFree(const_cast<float*>(p->corr.exp_r));
+  if (p->corr.exp_a) cudaFree(const_cast<float*>(p->corr.exp_a));
   cudaFree(p->w0_hi); cudaFree(p->w0_lo); cudaFree(p->w1_hi); cudaFree(p->w1_lo); cudaFree(p->w1t_hi);
   cudaFree(p->w1t_lo); cudaFree(p->w0t_hi); cudaFree(p->w0t_lo); cudaFree(p->tc_err);
   cudaFree(p->q_w0); cudaFree(p->q_w1); cudaFree(p->q_w1th); cudaFree(p->q_w0t);
@@ -1583,5 +1710,33 @@ extern "C" int apax_gm_stress_times_vol(apax_stream_t stream, const apax_gm_para
   }
   APAX_LAUNCH(k_virial_partial, dim3(kVirialBlocks), dim3(256), 0, s, w.D, w.G, w.rowptr, w.n_atoms, partial);
   APAX_LAUNCH(k_virial_final, dim3(1), dim3(32), 0, s, partial, kVirialBlocks, stress);
+  return APAX_OK;
+}
+
+extern "C" int apax_gm_params_set_corrections(apax_gm_params* p, const apax_gm_corrections* c) {
+  if (!p || !c) return APAX_ERR_INVALID_ARG;
+  auto softplus = [](double x) { return x > 30.0 ? x : log1p(exp(x)); };
+  CorrConst cc{};
+  if (c->zbl_on) {
+    if (!(c->zbl_r_max > 0.02f)) return APAX_ERR_INVALID_ARG;
+    static const float kExp[4] = {3.19980f, 0.94229f, 0.4029f, 0.20162f};   // empirical.py:45
+    cc.zbl_on = 1;
+    cc.zbl_rmax = c->zbl_r_max;
+    cc.zbl_scale = float(softplus(double(c->zbl_rep_scale)));                // jax.nn.softplus(rep_scale) (:70)
+    for (int q = 0; q < 4; ++q) { cc.zbl_c[q] = float(softplus(double(c->zbl_coefficients[q]))); cc.zbl_e[q] = kExp[q]; }
+  }
+  if (c->exp_on) {
+    if (!(c->exp_r_max > 0.02f) || !c->exp_rep_scale_host || !c->exp_rep_prefactor_host) return APAX_ERR_INVALID_ARG;
+    const int S = p->cfg.n_species;
+    std::vector<float> r(S), a(S);
+    for (int z = 0; z < S; ++z) { r[z] = fabsf(c->exp_rep_scale_host[z]); a[z] = fabsf(c->exp_rep_prefactor_host[z]); }   // :113-117
+    float *dr = nullptr, *da = nullptr;
+    APAX_TRY(upload(&dr, r.data(), size_t(S)));
+    APAX_TRY(upload(&da, a.data(), size_t(S)));
+    cc.exp_on = 1; cc.exp_rmax = c->exp_r_max; cc.exp_r = dr; cc.exp_a = da;
+  }
+  if (p->corr.exp_r) cudaFree(const_cast<float*>(p->corr.exp_r));
+  if (p->corr.exp_a) cudaFree(const_cast<float*>(p->corr.exp_a));
+  p->corr = cc;
   return APAX_OK;
 }

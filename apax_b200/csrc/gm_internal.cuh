@@ -14,8 +14,20 @@ constexpr int EMB_STRIDE = 36;  // 35 coefficients padded to 9 float4
 constexpr int MAX_SP_SMEM = 8;  // compact species tables up to 8x8 are staged in shared memory
 constexpr int MAX_OUT = 16;
 
+// pairwise empirical corrections (apax/layers/empirical.py:25-126), parameters already in their positive form
+struct CorrConst {
+  int zbl_on;
+  float zbl_rmax, zbl_scale;      // rep_scale after softplus
+  float zbl_c[4], zbl_e[4];       // coefficients after softplus, exponents
+  int exp_on;
+  float exp_rmax;
+  const float* exp_r;             // [S] |rep_scale|   (device)
+  const float* exp_a;             // [S] |rep_prefactor|
+};
+
 struct apax_gm_params_impl {
   apax_gm_config cfg;
+  CorrConst corr;                 // all zero: no corrections
   // device copies
   float* emb;    // [S][S][5][7], pre-multiplied by 1/sqrt(n_basis) when use_embed_norm
   float* w0;     // [360][256]
@@ -71,6 +83,7 @@ struct GmWorkspace {
   int32_t* sp_present;  // [128]
   int32_t* sp_map;      // [128] Z -> compact id
   int32_t* n_sp;        // [1]
+  int32_t* sp_z;        // [128] compact id -> atomic number
   float* embc;          // [n_sp*n_sp][36]
   // per atom: (x, y, z, compact species id as int bits) -- one aligned 32-byte gather per neighbour
   double4* P;

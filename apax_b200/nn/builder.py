@@ -6,7 +6,8 @@ from __future__ import annotations
 import numpy as np
 
 from ..layers.descriptor.gaussian_moment_descriptor import BesselBasis, GaussianBasis, GaussianMomentDescriptor, RadialFunction
-from .models import AtomisticReadout, EnergyDerivativeModel, EnergyModel, PerElementScaleShift, ShallowEnsembleModel
+from .models import (AtomisticReadout, EnergyDerivativeModel, EnergyModel, ExponentialRepulsion, PerElementScaleShift,
+                     ShallowEnsembleModel, ZBLRepulsion)
 
 DEFAULT_MODEL_CONFIG = {
     "name": "gmnn", "basis": {"name": "gaussian", "n_basis": 7, "r_min": 0.5, "r_max": 6.0, "spacing": "linear"},
@@ -46,6 +47,20 @@ class ModelBuilder:
                                 use_ntk=head_config["use_ntk"], n_shallow_ensemble=n_shallow,
                                 dtype=head_config.get("readout_dtype", "fp32"), activation_fn=self.config["activation_fn"])
 
+    def build_corrections(self, apply_mask: bool = True):
+        """apax/nn/builder.py:146-158: [{"name": "zbl" | "exponential", "r_max": ...}, ...]."""
+        out = []
+        for c in self.config["empirical_corrections"]:
+            c = dict(c)
+            name = c.pop("name")
+            if name == "zbl":
+                out.append(ZBLRepulsion(apply_mask=apply_mask, **c))
+            elif name == "exponential":
+                out.append(ExponentialRepulsion(apply_mask=apply_mask, **c))
+            else:
+                raise NotImplementedError(f"empirical correction '{name}' is not on the CUDA path")
+        return out
+
     def build_scale_shift(self, scale, shift):
         return PerElementScaleShift(n_species=self.n_species, scale=scale, shift=shift, dtype=self.config["scale_shift_dtype"])
 
@@ -53,7 +68,7 @@ class ModelBuilder:
                            inference_disp_fn=None):
         return EnergyModel(representation=self.build_descriptor(apply_mask), readout=self.build_readout(self.config),
                            scale_shift=self.build_scale_shift(scale, shift), property_heads=list(self.config["property_heads"]),
-                           corrections=list(self.config["empirical_corrections"]), init_box=init_box,
+                           corrections=self.build_corrections(apply_mask=apply_mask), init_box=init_box,
                            inference_disp_fn=inference_disp_fn)
 
     def build_energy_derivative_model(self, scale=1.0, shift=0.0, apply_mask=True, init_box=np.array([0.0, 0.0, 0.0]),

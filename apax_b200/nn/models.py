@@ -27,6 +27,22 @@ class AtomisticReadout:
 
 
 @dataclass
+class ZBLRepulsion:
+    """apax/layers/empirical.py:25-27 (statics only; parameters live in the tree under corrections_<i>)."""
+    r_max: float = 2.0
+    apply_mask: bool = True
+    dtype: Any = "fp32"
+
+
+@dataclass
+class ExponentialRepulsion:
+    """apax/layers/empirical.py:89-91 (statics only)."""
+    r_max: float = 2.0
+    apply_mask: bool = True
+    dtype: Any = "fp32"
+
+
+@dataclass
 class PerElementScaleShift:
     """apax/layers/scaling.py:10-14 (statics only; values live in the parameter tree)."""
     n_species: int = 119
@@ -71,17 +87,28 @@ class EnergyModel:
     inference_disp_fn: Any = None
 
     def statics(self) -> dict:
-        if self.property_heads or self.corrections:
-            raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "EnergyModel", "property heads / empirical corrections")
+        if self.property_heads:
+            raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "EnergyModel", "property heads")
+        corr = {}
+        for c in self.corrections:
+            if isinstance(c, ZBLRepulsion):
+                corr["zbl_r_max"] = float(c.r_max)
+            elif isinstance(c, ExponentialRepulsion):
+                corr["exp_r_max"] = float(c.r_max)
+            else:
+                raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "EnergyModel", f"empirical correction {type(c).__name__}")
         if list(self.readout.units) != [256, 256] or self.readout.activation_fn != "variance_preserving_swish":
             raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "EnergyModel", "readout must be [256,256] + vp-swish")
         cfg = self.representation.statics()
         cfg.update(nn=list(self.readout.units), use_ntk=self.readout.use_ntk, mask_atoms=self.mask_atoms)
+        cfg.update(corr)
         return cfg
 
     def _run(self, params, R, Z, neighbor, box, offsets, forces: bool):
         mode = displacement_mode(self.init_box, self.inference_disp_fn)
         st = self.statics()
+        if (st["basis_kind"] != 0 or st["n_basis"] != 7) and self.corrections:
+            raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "EnergyModel", "empirical corrections with a non-default basis")
         if st["basis_kind"] != 0 or st["n_basis"] != 7:
             # Bessel / exponential-spacing bases: the table-driven kernels behind apax_train_*
             from ..train.trainer import table_model

@@ -90,6 +90,32 @@ class DeviceParams:
                      r_min=cfg["r_min"], r_max=cfg["r_max"], basis_kind=int(cfg.get("basis_kind", 0)))
         self._keep = (emb, w, b, scale, shift)
         handle = C.c_void_p()
+        # pairwise empirical corrections (EnergyModel.corrections, apax/nn/models.py:127-130): flax names the list entries
+        # corrections_0, corrections_1, ...; a ZBL block holds "coefficients", an exponential block "rep_prefactor"
+        corr, corr_keep = None, []
+        for key in sorted(k for k in tree if str(k).startswith("corrections_")):
+            blk = tree[key]
+            corr = corr or _lib.GmCorrections()
+            if "coefficients" in blk:
+                if cfg.get("zbl_r_max") is None:
+                    raise _lib.ApaxB200Error(_lib.ERR_INVALID_ARG, "DeviceParams", "ZBL parameters without zbl_r_max in the config")
+                co = np.asarray(blk["coefficients"], dtype=np.float32).reshape(4)
+                corr.zbl_on, corr.zbl_r_max = 1, float(cfg["zbl_r_max"])
+                corr.zbl_rep_scale = float(np.asarray(blk["rep_scale"], dtype=np.float32).reshape(-1)[0])
+                for q in range(4):
+                    corr.zbl_coefficients[q] = float(co[q])
+            elif "rep_prefactor" in blk:
+                if cfg.get("exp_r_max") is None:
+                    raise _lib.ApaxB200Error(_lib.ERR_INVALID_ARG, "DeviceParams", "repulsion parameters without exp_r_max in the config")
+                rs = np.ascontiguousarray(np.asarray(blk["rep_scale"], dtype=np.float32).reshape(-1))
+                pf = np.ascontiguousarray(np.asarray(blk["rep_prefactor"], dtype=np.float32).reshape(-1))
+                if rs.shape[0] != S or pf.shape[0] != S:
+                    raise _lib.ApaxB200Error(_lib.ERR_INVALID_ARG, "DeviceParams", "rep_scale / rep_prefactor must have n_species entries")
+                corr_keep += [rs, pf]
+                corr.exp_on, corr.exp_r_max = 1, float(cfg["exp_r_max"])
+                corr.exp_rep_scale_host, corr.exp_rep_prefactor_host = rs.ctypes.data, pf.ctypes.data
+            else:
+                raise _lib.ApaxB200Error(_lib.ERR_UNSUPPORTED, "DeviceParams", f"empirical correction {key} (only ZBL / exponential)")
 
         def hp(a):
             return a.ctypes.data_as(C.c_void_p)
@@ -97,6 +123,8 @@ class DeviceParams:
         check(lib().apax_gm_params_create(C.byref(c), hp(emb), hp(w[0]), hp(b[0]), hp(w[1]), hp(b[1]), hp(w[2]), hp(b[2]),
                                           hp(scale), hp(shift), C.byref(handle)), "apax_gm_params_create")
         self.handle = handle
+        if corr is not None:
+            check(lib().apax_gm_params_set_corrections(handle, C.byref(corr)), "apax_gm_params_set_corrections")
 
     def __del__(self):
         h = getattr(self, "handle", None)

@@ -88,6 +88,23 @@ void apax_gm_params_destroy(apax_gm_params* p);
  * while these parameters were in use (results of that call are then invalid). */
 int apax_gm_params_status(const apax_gm_params* p);
 
+/* Pairwise empirical corrections added to the model energy (EnergyModel.corrections, apax/nn/models.py:127-130), with
+ * the parameters as they sit in the Flax tree (raw, i.e. before softplus / abs):
+ *   ZBLRepulsion        (apax/layers/empirical.py:25-86):  coefficients f32 [4], rep_scale, r_max
+ *   ExponentialRepulsion (:89-126): rep_scale f32 [n_species], rep_prefactor f32 [n_species] (host arrays), r_max
+ * They take part in every later apax_gm_* evaluation with these parameters (energy, forces, stress, all heads). */
+typedef struct {
+  int32_t zbl_on;
+  float zbl_r_max;
+  float zbl_coefficients[4];
+  float zbl_rep_scale;
+  int32_t exp_on;
+  float exp_r_max;
+  const float* exp_rep_scale_host;
+  const float* exp_rep_prefactor_host;
+} apax_gm_corrections;
+int apax_gm_params_set_corrections(apax_gm_params* p, const apax_gm_corrections* corrections);
+
 /* ------------------------------------------------------------------------------------------------
  * Energy + forces given a neighbour list.  Replaces EnergyDerivativeModel.apply
  * (apax/nn/models.py:146-171 = jax.value_and_grad of EnergyModel.__call__, :87-134).

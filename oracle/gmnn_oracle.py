@@ -38,6 +38,8 @@ class GMNNConfig:
     r_max: float = 6.0        # basis_functions.py:15
     basis: str = "gaussian"   # "gaussian" (GaussianBasis) or "bessel" (BesselBasis, basis_functions.py:59-79)
     spacing: str = "linear"   # GaussianBasis spacing: "linear" (:22-28) or "exponential" (:29-37)
+    zbl_r_max: Optional[float] = None   # ZBLRepulsion in EnergyModel.corrections (apax/layers/empirical.py:25-86); None = absent
+    exp_r_max: Optional[float] = None   # ExponentialRepulsion (:89-126)
     n_contr: int = 8          # gaussian_moment_descriptor.py:18
     use_ntk: bool = False     # apax/config/model_config.py:184-188
     use_embed_norm: bool = True  # basis_functions.py:93
@@ -288,6 +290,62 @@ def per_element_scale_shift(h, Z, scale, shift, cfg: GMNNConfig):
     return scale.to(dt)[Zl] * h.to(dt) + shift.to(dt)[Zl]
 
 
+def _correction_prelude(dr_vec, Z, idx, r_max: float):
+    """Common head of the empirical terms (empirical.py:51-63 / 104-115): species of both ends, fp32 distance clipped to
+    [0.02, r_max], cosine cutoff on the clipped distance."""
+    n = Z.shape[0]
+    Zl = Z.long()
+    Z_i, Z_j = Zl[idx[0].long().clamp(0, n - 1)], Zl[idx[1].long().clamp(0, n - 1)]
+    dr = safe_distance(dr_vec).to(torch.float32)
+    dr = torch.clamp(dr, min=0.02, max=r_max)
+    cos_cutoff = 0.5 * (torch.cos(np.pi * dr / r_max) + 1.0)
+    return Z_i, Z_j, dr, cos_cutoff
+
+
+def zbl_repulsion(dr_vec, Z, idx, coefficients, rep_scale, r_max: float, apply_mask: bool = True):
+    """ZBLRepulsion.__call__ (apax/layers/empirical.py:48-86); coefficients [4,1] and rep_scale [1] as stored (pre-softplus)."""
+    Z_i, Z_j, dr, cos_cutoff = _correction_prelude(dr_vec, Z, idx, r_max)
+    a_exp, a_num = 0.23, 0.46850
+    coeffs = torch.nn.functional.softplus(coefficients.to(torch.float32).reshape(4, 1))
+    exponents = torch.tensor([3.19980, 0.94229, 0.4029, 0.20162], dtype=torch.float32).reshape(4, 1)
+    scale = torch.nn.functional.softplus(rep_scale.to(torch.float32).reshape(-1))[0]
+    a_divisor = Z_i.to(torch.float32) ** a_exp + Z_j.to(torch.float32) ** a_exp
+    dist = dr * a_divisor / a_num
+    f = torch.sum(coeffs * torch.exp(-exponents * dist), dim=0)
+    E_ij = Z_i.to(torch.float32) * Z_j.to(torch.float32) / dr * f * cos_cutoff
+    if apply_mask:
+        E_ij = E_ij * ((idx[0] - idx[1]) != 0).to(E_ij.dtype)
+    return 0.5 * scale * torch.sum(E_ij.to(torch.float64))
+
+
+def exponential_repulsion(dr_vec, Z, idx, rscale, prefactor, r_max: float, apply_mask: bool = True):
+    """ExponentialRepulsion.__call__ (apax/layers/empirical.py:101-126); rscale, prefactor [n_species] as stored."""
+    Z_i, Z_j, dr, cos_cutoff = _correction_prelude(dr_vec, Z, idx, r_max)
+    A = torch.abs(prefactor.to(torch.float32))
+    Rr = torch.abs(rscale.to(torch.float32))
+    A_i, A_j, R_i, R_j = A[Z_i], A[Z_j], Rr[Z_i], Rr[Z_j]
+    f = A_i * A_j * torch.exp(-dr * (R_i + R_j) / (R_i * R_j)) / dr ** 2
+    E_ij = f * cos_cutoff
+    if apply_mask:
+        E_ij = E_ij * ((idx[0] - idx[1]) != 0).to(E_ij.dtype)
+    return torch.sum(E_ij.to(torch.float64))
+
+
+def corrections_energy(params, dr_vec, Z, idx, cfg: GMNNConfig):
+    """Sum of the empirical terms present in the parameter tree (EnergyModel.__call__, models.py:127-130): flax names the
+    entries of the `corrections` list corrections_0, corrections_1, ...; a ZBL block holds "coefficients", an exponential
+    block "rep_prefactor"."""
+    em = params["params"]["energy_model"] if "params" in params else params
+    total = torch.zeros((), dtype=torch.float64)
+    for key in sorted(k for k in em if k.startswith("corrections_")):
+        blk = {k: torch.as_tensor(np.asarray(v)) for k, v in em[key].items()}
+        if "coefficients" in blk:
+            total = total + zbl_repulsion(dr_vec, Z, idx, blk["coefficients"], blk["rep_scale"], cfg.zbl_r_max, cfg.apply_mask)
+        elif "rep_prefactor" in blk:
+            total = total + exponential_repulsion(dr_vec, Z, idx, blk["rep_scale"], blk["rep_prefactor"], cfg.exp_r_max, cfg.apply_mask)
+    return total
+
+
 def _params_to_torch(params: dict):
     em = params["params"]["energy_model"] if "params" in params else params
     emb = torch.as_tensor(np.asarray(em["representation"]["radial_fn"]["atomic_type_embedding"]))
@@ -317,6 +375,7 @@ def energy_model(params, R, Z, idx, box, offsets, mode: str, cfg: GMNNConfig, re
         energy = torch.sum(E_i.to(torch.float64), dim=0)        # fp64_sum, math.py:7-12
     else:
         energy = torch.sum(E_i.to(torch.float64))
+    energy = energy + corrections_energy(params, dr_vec, Z, idx, cfg)   # models.py:127-130 (zero without corrections)
     if return_aux:
         return energy, {"g": g, "moments": moments, "E_i": E_i, "dr_vec": dr_vec}
     return energy

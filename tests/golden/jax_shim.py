@@ -182,6 +182,7 @@ jnp.sin = torch.sin
 jnp.sinc = lambda x: torch.sinc(_t(x))
 jnp.sqrt = lambda x: torch.sqrt(_t(x))
 jnp.abs = torch.abs
+jnp.log = lambda x: torch.log(_t(x))
 jnp.sign = torch.sign
 jnp.maximum = lambda a, b: torch.maximum(_t(a), _t(b))
 jnp.dot = lambda a, b: torch.matmul(a, b)
@@ -423,6 +424,7 @@ def install(reference_root="/root/reference"):
     jnn = types.ModuleType("jax.nn")
     jnn.swish = lambda x: x * torch.sigmoid(x)
     jnn.silu = jnn.swish
+    jnn.softplus = lambda x: torch.nn.functional.softplus(_t(x))
     inits = types.ModuleType("jax.nn.initializers")
     inits.Initializer = object
     jnn.initializers = inits
@@ -463,6 +465,7 @@ def install(reference_root="/root/reference"):
         setattr(units, k, 1.0)
     ase.units = units
     data = types.ModuleType("ase.data")
+    data.covalent_radii = np.full(119, 1.0)   # only the initialiser of ExponentialRepulsion reads it; parameters are passed explicitly
     ase.data = data
     mods.update({"ase": ase, "ase.units": units, "ase.data": data})
 

@@ -326,6 +326,40 @@ def case_stress(n_mol=64, seed=5):
              param_seed=1234, energy=res["energy"], forces=res["forces"], stress=res["stress"])
 
 
+def case_corrections(n_mol=8, seed=23):
+    """EnergyDerivativeModel with the reference's own ZBLRepulsion + ExponentialRepulsion (apax/layers/empirical.py) in
+    EnergyModel.corrections, on a small multi-image water cell squeezed so that O-H pairs sit inside the corrections' range."""
+    from apax.layers.empirical import ExponentialRepulsion, ZBLRepulsion
+
+    pos, Z, cell = syn.water_box(n_mol, seed)
+    idx, offsets = no.vesin_idx_offsets(pos, cell, 6.0)
+    frac = np.asarray(space.transform(torch.as_tensor(np.linalg.inv(cell)), torch.as_tensor(pos)))
+    rng = np.random.default_rng(3)
+    params = syn.gmnn_params(seed=43, random_bias=True, random_scale_shift=True)
+    em = params["params"]["energy_model"]
+    em["corrections_0"] = {"coefficients": rng.normal(size=(4, 1)).astype(np.float32), "rep_scale": np.array([-1.7], dtype=np.float32)}
+    em["corrections_1"] = {"rep_scale": rng.uniform(0.3, 1.2, size=119).astype(np.float32) * rng.choice([-1, 1], size=119),
+                           "rep_prefactor": rng.uniform(1.0, 20.0, size=119).astype(np.float32)}
+    em["corrections_1"]["rep_scale"] = em["corrections_1"]["rep_scale"].astype(np.float32)
+    descriptor = GaussianMomentDescriptor(
+        radial_fn=RadialFunction(n_radial=5, basis_fn=GaussianBasis(n_basis=7, r_min=0.5, r_max=6.0, dtype="fp32"),
+                                 n_species=119, emb_init="uniform", use_embed_norm=True, dtype="fp32"),
+        n_contr=8, dtype="fp32", apply_mask=True)
+    readout = AtomisticReadout(units=[256, 256], activation_fn=variance_preserving_swish, w_init="lecun", b_init="zeros",
+                               use_ntk=False, n_shallow_ensemble=0, dtype="fp32")
+    scale_shift = PerElementScaleShift(n_species=119, scale=em["scale_shift"]["scale_per_element"],
+                                       shift=em["scale_shift"]["shift_per_element"], dtype="fp64")
+    corrections = [ZBLRepulsion(dtype="fp32", apply_mask=True, r_max=1.8), ExponentialRepulsion(dtype="fp32", apply_mask=True, r_max=1.5)]
+    m = EnergyDerivativeModel(EnergyModel(representation=descriptor, readout=readout, scale_shift=scale_shift, corrections=corrections,
+                                          init_box=np.array(cell.T), inference_disp_fn=None, mask_atoms=True))
+    res = np_out(m.apply(to_t(params), torch.as_tensor(frac), torch.as_tensor(Z.astype(np.int64)),
+                         torch.as_tensor(idx.astype(np.int64)), torch.as_tensor(cell), torch.as_tensor(offsets)))
+    np.savez(os.path.join(HERE, "water_corrections.npz"), frac=frac, Z=Z, cell=cell, idx=idx, offsets=offsets, param_seed=43,
+             zbl_coefficients=em["corrections_0"]["coefficients"], zbl_rep_scale=em["corrections_0"]["rep_scale"],
+             exp_rep_scale=em["corrections_1"]["rep_scale"], exp_rep_prefactor=em["corrections_1"]["rep_prefactor"],
+             zbl_r_max=1.8, exp_r_max=1.5, energy=res["energy"], forces=res["forces"])
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     case_descriptor_unit()
@@ -346,3 +380,5 @@ if __name__ == "__main__":
     print("basis_variants ok")
     case_stress()
     print("stress ok")
+    case_corrections()
+    print("corrections ok")

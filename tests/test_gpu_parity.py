@@ -235,3 +235,28 @@ def test_stress_times_vol_min_image(golden):
     assert np.abs(s - d["stress"]).max() <= 2e-6 * scale                      # vs the reference source (fp32 model)
     assert np.abs(s - ref64).max() <= 2.0 * np.abs(d["stress"] - ref64).max() + 1e-6 * scale
     assert abs(float(out["energy"].item()) - float(d["energy"])) <= 1e-6 * abs(float(d["energy"]))
+
+
+def test_empirical_corrections_zbl_and_exponential(golden):
+    """ZBLRepulsion + ExponentialRepulsion in EnergyModel.corrections against the fixture written by
+    the reference's own apax/layers/empirical.py, and against the oracle in fp64."""
+    from apax_b200.nn.builder import GMNNBuilder
+    from oracle import gmnn_oracle as go
+
+    d = golden("water_corrections")
+    params = syn.gmnn_params(seed=int(d["param_seed"]), random_bias=True, random_scale_shift=True)
+    em = params["params"]["energy_model"]
+    em["corrections_0"] = {"coefficients": d["zbl_coefficients"], "rep_scale": d["zbl_rep_scale"]}
+    em["corrections_1"] = {"rep_scale": d["exp_rep_scale"], "rep_prefactor": d["exp_rep_prefactor"]}
+    cfg = {"empirical_corrections": [{"name": "zbl", "r_max": float(d["zbl_r_max"])}, {"name": "exponential", "r_max": float(d["exp_r_max"])}]}
+    model = GMNNBuilder(cfg).build_energy_derivative_model(init_box=d["cell"].T)
+    out = model.apply(params, d["frac"], d["Z"], d["idx"], d["cell"], d["offsets"])
+    torch.cuda.synchronize()
+    e, f = float(out["energy"].item()), out["forces"].cpu().numpy()
+    ocfg = go.GMNNConfig(zbl_r_max=float(d["zbl_r_max"]), exp_r_max=float(d["exp_r_max"]))
+    ref64 = go.energy_forces(params, d["frac"], d["Z"], d["idx"], d["cell"], d["offsets"], "offsets", go.fp64_config(ocfg))
+    assert abs(e - float(d["energy"])) <= 1e-6 * abs(float(d["energy"]))
+    assert_force_parity(f, d["forces"], ref64["forces"], where="corrections")
+    plain = syn.gmnn_params(seed=int(d["param_seed"]), random_bias=True, random_scale_shift=True)
+    e0 = GMNNBuilder().build_energy_derivative_model(init_box=d["cell"].T).apply(plain, d["frac"], d["Z"], d["idx"], d["cell"], d["offsets"])
+    assert abs(float(e0["energy"].item()) - e) > 1.0      # the corrections are a large part of this energy

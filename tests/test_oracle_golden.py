@@ -125,3 +125,19 @@ def test_stress_oracle_against_reference_source(golden):
     assert np.abs(st - d["stress"]).max() <= 1e-6 * np.abs(d["stress"]).max()
     # symmetric up to rounding (rotational invariance), and the offsets branch's doubled displacement is a different quantity
     assert np.abs(st - st.T).max() <= 1e-5 * np.abs(st).max()
+
+
+def test_empirical_corrections_against_reference_source(golden):
+    """ZBLRepulsion / ExponentialRepulsion (apax/layers/empirical.py:25-126) restated in the oracle vs the reference's own source."""
+    from apax_b200 import synthetic as syn
+    from oracle import gmnn_oracle as go
+
+    d = golden("water_corrections")
+    params = syn.gmnn_params(seed=int(d["param_seed"]), random_bias=True, random_scale_shift=True)
+    em = params["params"]["energy_model"]
+    em["corrections_0"] = {"coefficients": d["zbl_coefficients"], "rep_scale": d["zbl_rep_scale"]}
+    em["corrections_1"] = {"rep_scale": d["exp_rep_scale"], "rep_prefactor": d["exp_rep_prefactor"]}
+    cfg = go.GMNNConfig(zbl_r_max=float(d["zbl_r_max"]), exp_r_max=float(d["exp_r_max"]))
+    ref = go.energy_forces(params, d["frac"], d["Z"], d["idx"], d["cell"], d["offsets"], "offsets", cfg)
+    assert abs(ref["energy"] - float(d["energy"])) <= 1e-7 * abs(float(d["energy"]))
+    assert np.abs(ref["forces"] - d["forces"]).max() <= 1e-6 * np.abs(d["forces"]).max()
