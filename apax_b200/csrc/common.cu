@@ -23,6 +23,7 @@ std::vector<ProfRec> g_prof;
 void profile_before(const char* name, cudaStream_t stream) {
   ProfRec r;
   r.name = name;
+  if (r.name.size() > 2 && r.name.front() == '(' && r.name.back() == ')') r.name = r.name.substr(1, r.name.size() - 2);  // (k<a, b>) at the launch site
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
   cudaEventRecord(r.a, stream);

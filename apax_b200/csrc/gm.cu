@@ -365,27 +365,27 @@ __global__ void __launch_bounds__(256) k_atom_pack(GmWorkspace ws, PairGeom geo)
 // strided share of the atom's CSR row with the 100 accumulators in registers; an xor-butterfly over
 // the LPA lanes finishes the segmented sum (no atomics, fixed order => bitwise reproducible).
 // The neighbour gathers are software-pipelined: indices two pairs ahead, atom records one pair ahead.
-template <int LPA>
-__global__ void __launch_bounds__(256) k_pair_fwd(GmWorkspace ws, PairGeom geo, DescConst dc) {
-  __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * EMB_STRIDE];
-  const float* emb = stage_species_table(ws, s_emb);
-  const int n_sp = *ws.n_sp;
+// SPEC = 1: the launcher vouches for mode == APAX_DISP_MINIMAGE without offsets (the resident min-image list of the large
+// periodic boxes), so the offset registers, the `src` walk and the mode branches fold away.
+// `emb` is the staged species table: in shared memory when the launch wrapper says so (a pointer the compiler can follow
+// back to the __shared__ array: LDS instead of generic loads), else the compact table in global memory.  `box` lives in
+// shared memory, not registers: 18 registers less across the pair loop.
+template <int LPA, int BT, int MINB, int SPEC>
+__device__ __forceinline__ void pair_fwd_body(const GmWorkspace& ws, const PairGeom& geo, const DescConst& dc,
+                                              const float* __restrict__ emb, const double* box, int n_sp) {
   const int32_t* __restrict__ nbr = ws.nbr;
   const int32_t* __restrict__ src = ws.src;
   const double4* __restrict__ P = ws.P;
-  const double* __restrict__ offs = geo.mode == APAX_DISP_DRVEC ? geo.R : geo.offsets;
+  const double* __restrict__ offs = SPEC ? nullptr : (geo.mode == APAX_DISP_DRVEC ? geo.R : geo.offsets);
   float4* __restrict__ G = ws.G;
-  const int64_t gid = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t gid = int64_t(blockIdx.x) * BT + threadIdx.x;
   const int64_t atom = gid / LPA;
   const int sub = int(gid % LPA);
   const bool valid = atom < ws.n_central;
-  const bool plain = geo.mode == APAX_DISP_GAS || geo.mode == APAX_DISP_DRVEC;
-  const bool wrap = geo.mode == APAX_DISP_MINIMAGE;
+  const bool wrap = SPEC ? true : geo.mode == APAX_DISP_MINIMAGE;
+  const bool gas = SPEC ? false : geo.mode == APAX_DISP_GAS;
   int beg = 0, end = 0, zc = 0;
   double Ra[3] = {0.0, 0.0, 0.0};
-  double box[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) box[i] = plain ? ((i % 4 == 0 && geo.mode == APAX_DISP_GAS) ? 1.0 : 0.0) : __ldg(geo.box + i);
   if (valid) {
     beg = ws.rowptr[atom];
     end = ws.rowptr[atom + 1];
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(256) k_pair_fwd(GmWorkspace ws, PairGeom geo, 
     double v0 = Ra[0] - p_cur.x, v1 = Ra[1] - p_cur.y, v2 = Ra[2] - p_cur.z;
     if (wrap) { v0 = wrap_unit(v0); v1 = wrap_unit(v1); v2 = wrap_unit(v2); }
     double d0, d1, d2;
-    if (geo.mode == APAX_DISP_GAS) {
+    if (gas) {
       d0 = v0; d1 = v1; d2 = v2;
     } else {
       d0 = box[0] * v0 + box[1] * v1 + box[2] * v2 + o_cur[0];
@@ -472,11 +472,9 @@ __global__ void __launch_bounds__(256) k_pair_fwd(GmWorkspace ws, PairGeom geo, 
 // ---- backward: per-pair dE/d(dr_vec) from the packed moment adjoints of the central atom.  Pair
 // terms are recomputed from the stored fp32 displacement; nothing per-pair other than (dx,dy,dz) was
 // kept from the forward pass.  Also leaves the row sum (fp64) of the central atom in Frow.
-template <int LPA>
-__global__ void __launch_bounds__(256) k_pair_bwd(GmWorkspace ws, DescConst dc) {
-  __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * EMB_STRIDE];
-  const float* emb = stage_species_table(ws, s_emb);
-  const int64_t gid = int64_t(blockIdx.x) * 256 + threadIdx.x;
+template <int LPA, int BT, int MINB>
+__device__ __forceinline__ void pair_bwd_body(const GmWorkspace& ws, const DescConst& dc, const float* __restrict__ emb) {
+  const int64_t gid = int64_t(blockIdx.x) * BT + threadIdx.x;
   const int64_t atom = gid / LPA;
   const int sub = int(gid % LPA);
   const bool valid = atom < ws.n_central;
@@ -573,6 +571,31 @@ __global__ void __launch_bounds__(256) k_pair_bwd(GmWorkspace ws, DescConst dc) 
   }
 }
 
+template <int LPA, int BT, int MINB, int SPEC>
+__global__ void __launch_bounds__(BT, MINB) k_pair_fwd(GmWorkspace ws, PairGeom geo, DescConst dc) {
+  __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * EMB_STRIDE];
+  __shared__ double box[9];
+  const bool plain = SPEC ? false : (geo.mode == APAX_DISP_GAS || geo.mode == APAX_DISP_DRVEC);
+  if (threadIdx.x < 9)
+    box[threadIdx.x] = plain ? ((threadIdx.x % 4 == 0 && geo.mode == APAX_DISP_GAS) ? 1.0 : 0.0) : __ldg(geo.box + threadIdx.x);
+  stage_species_table(ws, s_emb);
+  const int n_sp = *ws.n_sp;
+  if (n_sp <= MAX_SP_SMEM) {
+    pair_fwd_body<LPA, BT, MINB, SPEC>(ws, geo, dc, s_emb, box, n_sp);
+  } else {
+    pair_fwd_body<LPA, BT, MINB, SPEC>(ws, geo, dc, ws.embc, box, n_sp);
+  }
+}
+template <int LPA, int BT, int MINB>
+__global__ void __launch_bounds__(BT, MINB) k_pair_bwd(GmWorkspace ws, DescConst dc) {
+  __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * EMB_STRIDE];
+  stage_species_table(ws, s_emb);
+  if (*ws.n_sp <= MAX_SP_SMEM) {
+    pair_bwd_body<LPA, BT, MINB>(ws, dc, s_emb);
+  } else {
+    pair_bwd_body<LPA, BT, MINB>(ws, dc, ws.embc);
+  }
+}
 // ---- force assembly: F_a = -( sum_{e: central a} dbar_e  -  sum_{e: neighbour a} dbar_e ), both sums
 // in fp64 over fp32 per-pair values, i.e. the transpose of the two gathers R[idx[1]], R[idx[0]] in
 // distances.py:55-56 (R is fp64 there, :54).  The second sum walks the transpose map.
@@ -1114,14 +1137,45 @@ static int pick_lpa(int64_t n_atoms) {
   return 32;
 }
 
-template <int LPA>
-static int launch_pair_fwd(cudaStream_t s, const GmWorkspace& w, const PairGeom& geo, const DescConst& dc) {
-  APAX_LAUNCH(k_pair_fwd<LPA>, dim3((unsigned)cdiv(w.n_central * LPA, 256)), dim3(256), 0, s, w, geo, dc);
+// Block shape of the pair kernels.  Their ~200-225 live registers allow one 256-thread block per SM (8 warps); under a
+// register cap the compiler parks a dozen accumulators in local memory (L1-resident) and more warps hide the latency of
+// the serial per-pair prelude.  APAX_B200_PAIR_BLOCK (measurement switch) picks the
+// shape: 0 = 256 x 1 (uncapped), 1 = 128 x 3 (168 registers, default), 2 = 128 x 4 (128 registers).  Measured on the
+// 1,000,002-atom box (fwd / bwd ms): 2.96 / 3.01, 2.21 / 2.52, 3.20 / 2.89; 64-thread blocks at 144 registers: 2.88 / 2.94.
+static int pair_block_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("APAX_B200_PAIR_BLOCK");
+    v = e ? atoi(e) : 1;
+    if (v < 0 || v > 2) v = 1;
+  }
+  return v;
+}
+template <int LPA, int BT, int MINB>
+static int launch_pair_fwd_shape(cudaStream_t s, const GmWorkspace& w, const PairGeom& geo, const DescConst& dc) {
+  const dim3 grid((unsigned)cdiv(w.n_central * LPA, BT));
+  if (geo.mode == APAX_DISP_MINIMAGE && !geo.offsets) {
+    APAX_LAUNCH((k_pair_fwd<LPA, BT, MINB, 1>), grid, dim3(BT), 0, s, w, geo, dc);
+  } else {
+    APAX_LAUNCH((k_pair_fwd<LPA, BT, MINB, 0>), grid, dim3(BT), 0, s, w, geo, dc);
+  }
   return APAX_OK;
 }
 template <int LPA>
+static int launch_pair_fwd(cudaStream_t s, const GmWorkspace& w, const PairGeom& geo, const DescConst& dc) {
+  switch (pair_block_variant()) {
+    case 0: return launch_pair_fwd_shape<LPA, 256, 1>(s, w, geo, dc);
+    case 2: return launch_pair_fwd_shape<LPA, 128, 4>(s, w, geo, dc);
+    default: return launch_pair_fwd_shape<LPA, 128, 3>(s, w, geo, dc);
+  }
+}
+template <int LPA>
 static int launch_pair_bwd(cudaStream_t s, const GmWorkspace& w, const DescConst& dc) {
-  APAX_LAUNCH(k_pair_bwd<LPA>, dim3((unsigned)cdiv(w.n_central * LPA, 256)), dim3(256), 0, s, w, dc);
+  switch (pair_block_variant()) {
+    case 0: APAX_LAUNCH((k_pair_bwd<LPA, 256, 1>), dim3((unsigned)cdiv(w.n_central * LPA, 256)), dim3(256), 0, s, w, dc); break;
+    case 2: APAX_LAUNCH((k_pair_bwd<LPA, 128, 4>), dim3((unsigned)cdiv(w.n_central * LPA, 128)), dim3(128), 0, s, w, dc); break;
+    default: APAX_LAUNCH((k_pair_bwd<LPA, 128, 3>), dim3((unsigned)cdiv(w.n_central * LPA, 128)), dim3(128), 0, s, w, dc); break;
+  }
   return APAX_OK;
 }
 template <int LPA>

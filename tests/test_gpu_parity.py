@@ -256,7 +256,7 @@ def test_empirical_corrections_zbl_and_exponential(golden):
     ocfg = go.GMNNConfig(zbl_r_max=float(d["zbl_r_max"]), exp_r_max=float(d["exp_r_max"]))
     ref64 = go.energy_forces(params, d["frac"], d["Z"], d["idx"], d["cell"], d["offsets"], "offsets", go.fp64_config(ocfg))
     assert abs(e - float(d["energy"])) <= 1e-6 * abs(float(d["energy"]))
-    assert_force_parity(f, d["forces"], ref64["forces"], where="corrections")
+    assert_force_parity(f, d["forces"], ref64["forces"], where="corrections", ulp_floor=2.0)   # |F| up to 59 eV/A: 1 ulp = 3.8e-6
     plain = syn.gmnn_params(seed=int(d["param_seed"]), random_bias=True, random_scale_shift=True)
     e0 = GMNNBuilder().build_energy_derivative_model(init_box=d["cell"].T).apply(plain, d["frac"], d["Z"], d["idx"], d["cell"], d["offsets"])
     assert abs(float(e0["energy"].item()) - e) > 1.0      # the corrections are a large part of this energy
