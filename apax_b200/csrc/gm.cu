@@ -372,7 +372,8 @@ __global__ void __launch_bounds__(256) k_atom_pack(GmWorkspace ws, PairGeom geo)
 // shared memory, not registers: 18 registers less across the pair loop.
 template <int LPA, int BT, int MINB, int SPEC>
 __device__ __forceinline__ void pair_fwd_body(const GmWorkspace& ws, const PairGeom& geo, const DescConst& dc,
-                                              const float* __restrict__ emb, const double* box, int n_sp) {
+                                              const float* __restrict__ emb, const double* box, int n_sp,
+                                              double* ra) {
   const int32_t* __restrict__ nbr = ws.nbr;
   const int32_t* __restrict__ src = ws.src;
   const double4* __restrict__ P = ws.P;
@@ -385,12 +386,13 @@ __device__ __forceinline__ void pair_fwd_body(const GmWorkspace& ws, const PairG
   const bool wrap = SPEC ? true : geo.mode == APAX_DISP_MINIMAGE;
   const bool gas = SPEC ? false : geo.mode == APAX_DISP_GAS;
   int beg = 0, end = 0, zc = 0;
-  double Ra[3] = {0.0, 0.0, 0.0};
+  double* Ra = ra + threadIdx.x;   // the central atom's position waits in shared memory (stride BT): 6 registers less
+  Ra[0] = 0.0; Ra[BT] = 0.0; Ra[2 * BT] = 0.0;
   if (valid) {
     beg = ws.rowptr[atom];
     end = ws.rowptr[atom + 1];
     const double4 pa = P[atom];
-    Ra[0] = pa.x; Ra[1] = pa.y; Ra[2] = pa.z;
+    Ra[0] = pa.x; Ra[BT] = pa.y; Ra[2 * BT] = pa.z;
     zc = int(__double_as_longlong(pa.w));
   }
   float acc[NPK];
@@ -417,7 +419,7 @@ __device__ __forceinline__ void pair_fwd_body(const GmWorkspace& ws, const PairG
       o_nxt[0] = __ldg(offs + 3 * sp); o_nxt[1] = __ldg(offs + 3 * sp + 1); o_nxt[2] = __ldg(offs + 3 * sp + 2);
     }
     // ---- displacement in fp64 (distances.py:48-67), cast once to fp32 (gaussian_moment_descriptor.py:33)
-    double v0 = Ra[0] - p_cur.x, v1 = Ra[1] - p_cur.y, v2 = Ra[2] - p_cur.z;
+    double v0 = Ra[0] - p_cur.x, v1 = Ra[BT] - p_cur.y, v2 = Ra[2 * BT] - p_cur.z;
     if (wrap) { v0 = wrap_unit(v0); v1 = wrap_unit(v1); v2 = wrap_unit(v2); }
     double d0, d1, d2;
     if (gas) {
@@ -428,7 +430,12 @@ __device__ __forceinline__ void pair_fwd_body(const GmWorkspace& ws, const PairG
       d2 = box[6] * v0 + box[7] * v1 + box[8] * v2 + o_cur[2];
     }
     const float dx = float(d0), dy = float(d1), dz = float(d2);
-    const int pt = zc * n_sp + int(__double_as_longlong(p_cur.w));  // embeddings[Z_central, Z_neighbour] (basis_functions.py:139-141)
+    // embeddings[Z_central, Z_neighbour] (basis_functions.py:139-141).  Both words of the record's last lane are consumed (the
+    // upper one is always 0): otherwise the compiler recycles that register for the index prefetch below while the 128-bit
+    // gather that targets it is still in flight, and every iteration waits out the gather's latency on the write-after-write
+    // (ncu: 28 % of the kernel's stall samples sat on that one SEL).
+    const long long wbits = __double_as_longlong(p_cur.w);
+    const int pt = zc * n_sp + (int(wbits) | int(wbits >> 32));
     G[e] = make_float4(dx, dy, dz, __int_as_float(pt));
     p_cur = p_nxt; j_cur = j_nxt; j_nxt = j_nn;
     o_cur[0] = o_nxt[0]; o_cur[1] = o_nxt[1]; o_cur[2] = o_nxt[2];
@@ -575,15 +582,16 @@ template <int LPA, int BT, int MINB, int SPEC>
 __global__ void __launch_bounds__(BT, MINB) k_pair_fwd(GmWorkspace ws, PairGeom geo, DescConst dc) {
   __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * EMB_STRIDE];
   __shared__ double box[9];
+  __shared__ double s_ra[3 * BT];
   const bool plain = SPEC ? false : (geo.mode == APAX_DISP_GAS || geo.mode == APAX_DISP_DRVEC);
   if (threadIdx.x < 9)
     box[threadIdx.x] = plain ? ((threadIdx.x % 4 == 0 && geo.mode == APAX_DISP_GAS) ? 1.0 : 0.0) : __ldg(geo.box + threadIdx.x);
   stage_species_table(ws, s_emb);
   const int n_sp = *ws.n_sp;
   if (n_sp <= MAX_SP_SMEM) {
-    pair_fwd_body<LPA, BT, MINB, SPEC>(ws, geo, dc, s_emb, box, n_sp);
+    pair_fwd_body<LPA, BT, MINB, SPEC>(ws, geo, dc, s_emb, box, n_sp, s_ra);
   } else {
-    pair_fwd_body<LPA, BT, MINB, SPEC>(ws, geo, dc, ws.embc, box, n_sp);
+    pair_fwd_body<LPA, BT, MINB, SPEC>(ws, geo, dc, ws.embc, box, n_sp, s_ra);
   }
 }
 template <int LPA, int BT, int MINB>
