@@ -1117,6 +1117,47 @@ __global__ void __launch_bounds__(256) k_virial_partial(const float4* __restrict
   if (threadIdx.x < 9) partial[blockIdx.x * 9 + threadIdx.x] = red[0][threadIdx.x];
 }
 
+// The OFFSETS branch as the reference computes it: disp_fn (apax/layers/distances.py:12-22) hands back dR + (I + eps) . dR and
+// the offsets are added afterwards (:62-66), so dU/d(eps) = sum over entries of dE/d(dr') (x) dR with dR = box . (R[i1] - R[i0])
+// in fp64 and dE/d(dr') taken at dr' = 2 dR + offsets (the force pass that ran just before, with the doubled box).
+__global__ void __launch_bounds__(256) k_virial_partial_rows(GmWorkspace ws, const double* __restrict__ R,
+                                                             const double* __restrict__ box, double* __restrict__ partial) {
+  __shared__ double red[8][9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double b[9], acc[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) { b[q] = __ldg(box + q); acc[q] = 0.0; }
+  for (int64_t atom = int64_t(blockIdx.x) * 8 + warp; atom < ws.n_central; atom += int64_t(gridDim.x) * 8) {
+    const double ax = R[3 * atom], ay = R[3 * atom + 1], az = R[3 * atom + 2];
+    for (int s = ws.rowptr[atom] + lane; s < ws.rowptr[atom + 1]; s += 32) {
+      const int64_t j = ws.nbr[s];
+      const double v0 = ax - R[3 * j], v1 = ay - R[3 * j + 1], v2 = az - R[3 * j + 2];
+      const double r0 = b[0] * v0 + b[1] * v1 + b[2] * v2;
+      const double r1 = b[3] * v0 + b[4] * v1 + b[5] * v2;
+      const double r2 = b[6] * v0 + b[7] * v1 + b[8] * v2;
+      const float4 d = ws.D[s], g = ws.G[s];
+      const double dx = double(d.x) + double(d.w) * double(g.x);   // .w: empirical corrections (0 without them)
+      const double dy = double(d.y) + double(d.w) * double(g.y);
+      const double dz = double(d.z) + double(d.w) * double(g.z);
+      acc[0] += dx * r0; acc[1] += dx * r1; acc[2] += dx * r2;
+      acc[3] += dy * r0; acc[4] += dy * r1; acc[5] += dy * r2;
+      acc[6] += dz * r0; acc[7] += dz * r1; acc[8] += dz * r2;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    if (lane == 0) red[warp][q] = acc[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double t = 0.0;
+    for (int w8 = 0; w8 < 8; ++w8) t += red[w8][threadIdx.x];
+    partial[blockIdx.x * 9 + threadIdx.x] = t;
+  }
+}
+
 __global__ void __launch_bounds__(32) k_virial_final(const double* __restrict__ partial, int n_blocks, double* __restrict__ out) {
   if (threadIdx.x < 9) {
     double acc = 0.0;
@@ -1771,6 +1812,25 @@ extern "C" int apax_gm_stress_times_vol(apax_stream_t stream, const apax_gm_para
     return APAX_OK;
   }
   APAX_LAUNCH(k_virial_partial, dim3(kVirialBlocks), dim3(256), 0, s, w.D, w.G, w.rowptr, w.n_atoms, partial);
+  APAX_LAUNCH(k_virial_final, dim3(1), dim3(32), 0, s, partial, kVirialBlocks, stress);
+  return APAX_OK;
+}
+
+extern "C" int apax_gm_stress_times_vol_offsets(apax_stream_t stream, const apax_gm_params* params, const double* R,
+                                                const double* box, int64_t n_atoms, int64_t n_pairs, double* stress,
+                                                void* workspace, size_t workspace_bytes) {
+  if (!params || !stress || !workspace || !R || !box) return APAX_ERR_INVALID_ARG;
+  if (params->cfg.n_out != 1) return APAX_ERR_UNSUPPORTED;
+  GmWorkspace w;
+  APAX_TRY(get_ws(params, n_atoms, n_pairs, workspace, workspace_bytes, &w));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  double* partial = reinterpret_cast<double*>(w.tmp_a);   // as in apax_gm_stress_times_vol
+  if (size_t(w.n_pairs) * sizeof(int32_t) < size_t(kVirialBlocks) * 9 * sizeof(double)) {
+    APAX_LAUNCH(k_virial_partial_rows, dim3(1), dim3(256), 0, s, w, R, box, w.Frow);
+    APAX_LAUNCH(k_virial_final, dim3(1), dim3(32), 0, s, w.Frow, 1, stress);
+    return APAX_OK;
+  }
+  APAX_LAUNCH(k_virial_partial_rows, dim3(kVirialBlocks), dim3(256), 0, s, w, R, box, partial);
   APAX_LAUNCH(k_virial_final, dim3(1), dim3(32), 0, s, partial, kVirialBlocks, stress);
   return APAX_OK;
 }

@@ -134,14 +134,15 @@ class EnergyDerivativeModel:
     def apply(self, params, R, Z, neighbor, box, offsets):
         """-> {"energy": f64 scalar, "forces": [N,3] f64} (models.py:146-171)."""
         if self.calc_stress:
-            # stress_times_vol (apax/layers/properties.py:11-42): offered where the reference applies the strain as
-            # (I + eps) . dr, i.e. on the min-image path (DESIGN.md on the offsets branch's doubled displacements)
+            # stress_times_vol (apax/layers/properties.py:11-42).  Min-image path: strain applied as (I + eps) . dr
+            # (space.py:277-278); offsets path: as the reference's disp_fn does it, dR + (I + eps) . dR (+ offsets), i.e. at
+            # doubled displacements (apax/layers/distances.py:12-22) -- reproduced as written.
             em = self.energy_model
             mode = displacement_mode(em.init_box, em.inference_disp_fn)
             st = em.statics()
-            if mode != "minimage" or st["basis_kind"] != 0 or st["n_basis"] != 7:
+            if mode not in ("minimage", "offsets") or st["basis_kind"] != 0 or st["n_basis"] != 7:
                 raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "EnergyDerivativeModel",
-                                            "calc_stress: min-image displacement with the default basis only")
+                                            "calc_stress: periodic displacement with the default basis only")
             e, f, s = rt.energy_forces(device_params(params, st), R, Z, canonicalize_neighbors(neighbor), box, offsets, mode,
                                        stress=True)
             return {"energy": e[0], "forces": f[0], "stress": s}

@@ -188,11 +188,21 @@ def energy_forces(params: DeviceParams, R, Z, idx, box, offsets, mode: str = "of
                                       n_atoms, n_pairs, MODES[mode], _ptr(energy), _ptr(F), wp, wb),
           "apax_gm_energy_forces")
     if stress:
-        if mode != "minimage" or not forces:
-            raise _lib.ApaxB200Error(_lib.ERR_UNSUPPORTED, "energy_forces", "stress is offered on the min-image path (with forces)")
+        if mode not in ("minimage", "offsets") or not forces:
+            raise _lib.ApaxB200Error(_lib.ERR_UNSUPPORTED, "energy_forces", "stress needs a periodic displacement (with forces)")
         st = torch.empty((3, 3), dtype=torch.float64, device=dev)
-        check(lib().apax_gm_stress_times_vol(_stream_ptr(), params.handle, n_atoms, n_pairs, _ptr(st), wp, wb),
-              "apax_gm_stress_times_vol")
+        if mode == "minimage":
+            check(lib().apax_gm_stress_times_vol(_stream_ptr(), params.handle, n_atoms, n_pairs, _ptr(st), wp, wb),
+                  "apax_gm_stress_times_vol")
+        else:
+            # the reference's disp_fn under a perturbation (apax/layers/distances.py:12-22): dU/d(eps) at doubled displacements
+            box2 = box_d * 2.0
+            e2, F2 = torch.empty_like(energy), torch.empty_like(F)
+            check(lib().apax_gm_energy_forces(_stream_ptr(), params.handle, _ptr(R), _ptr(Z), _ptr(idx), _ptr(box2), _ptr(off_d),
+                                              n_atoms, n_pairs, MODES[mode], _ptr(e2), _ptr(F2), wp, wb),
+                  "apax_gm_energy_forces")
+            check(lib().apax_gm_stress_times_vol_offsets(_stream_ptr(), params.handle, _ptr(R), _ptr(box_d), n_atoms, n_pairs,
+                                                         _ptr(st), wp, wb), "apax_gm_stress_times_vol_offsets")
         return energy, F, st
     return energy, F
 

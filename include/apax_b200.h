@@ -143,10 +143,20 @@ int apax_gm_compute(apax_stream_t stream, const apax_gm_params* params, const do
  *   stress[i][j] = sum over list entries of dE/d(dr)_i * dr_j.
  * Call it after apax_gm_compute / apax_gm_energy_forces (n_out == 1) on the SAME workspace: it reduces the per-pair
  * quantities the force pass left there.  (On the OFFSETS path the reference's disp_fn applies dr' = dr + (I + eps) . dr,
- * apax/layers/distances.py:16-17, i.e. it differentiates at doubled displacements; this function does not reproduce that.)
+ * apax/layers/distances.py:16-17, i.e. it differentiates at doubled displacements: apax_gm_stress_times_vol_offsets below.)
  * stress f64 [3][3], device. */
 int apax_gm_stress_times_vol(apax_stream_t stream, const apax_gm_params* params, int64_t n_atoms, int64_t n_pairs,
                              double* stress, void* workspace, size_t workspace_bytes);
+
+/* The same quantity on the OFFSETS displacement, exactly as the reference computes it: under a perturbation its disp_fn
+ * returns dR + (I + eps) . dR with dR = box . (R[i1] - R[i0]) and the offsets are added afterwards
+ * (apax/layers/distances.py:12-22, 62-66), i.e. dU/d(eps) is taken at dr' = 2 dR + offsets:
+ *   stress[i][j] = sum over list entries of dE/d(dr')_i * dR_j          (dR in fp64).
+ * Protocol: (1) apax_gm_energy_forces with box2 = 2 * box, the same offsets and APAX_DISP_OFFSETS into scratch energy / force
+ * buffers -- the evaluation at dr'; (2) this call with the ORIGINAL box and the same R on the SAME workspace.
+ * R f64 [n_atoms][3], box f64 [3][3], stress f64 [3][3]: device. */
+int apax_gm_stress_times_vol_offsets(apax_stream_t stream, const apax_gm_params* params, const double* R, const double* box,
+                                     int64_t n_atoms, int64_t n_pairs, double* stress, void* workspace, size_t workspace_bytes);
 
 /* Batched evaluation of many independent structures in one call.  Replaces the vmapped model of
  * ASECalculator.batch_eval (apax/md/ase_calc.py:395-481, jax.vmap over padded structures) and of the training

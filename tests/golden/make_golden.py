@@ -326,6 +326,22 @@ def case_stress(n_mol=64, seed=5):
              param_seed=1234, energy=res["energy"], forces=res["forces"], stress=res["stress"])
 
 
+def case_stress_offsets(n_mol=32, seed=7):
+    """stress_times_vol through EnergyDerivativeModel(calc_stress=True) on the vesin / offsets path (inference_disp_fn=None): the
+    reference's disp_fn applies the perturbation as dR + (I + eps) . dR and adds the offsets afterwards
+    (apax/layers/distances.py:12-22, 62-66), so dU/d(eps) is taken at doubled displacements -- recorded as the source computes it."""
+    pos, Z, cell = syn.water_box(n_mol, seed)
+    idx, offsets = no.vesin_idx_offsets(pos, cell, 6.0)
+    frac = np.asarray(space.transform(torch.as_tensor(np.linalg.inv(cell)), torch.as_tensor(pos)))
+    params = syn.gmnn_params(seed=77, random_bias=True)
+    m = build_model(np.array(cell.T), inference_disp_fn=None)
+    m.calc_stress = True
+    res = np_out(m.apply(to_t(params), torch.as_tensor(frac), torch.as_tensor(Z.astype(np.int64)), torch.as_tensor(idx.astype(np.int64)),
+                         torch.as_tensor(cell), torch.as_tensor(offsets)))
+    np.savez(os.path.join(HERE, "water_stress_offsets.npz"), frac=frac, Z=Z, cell=cell, idx=idx, offsets=offsets, param_seed=77,
+             energy=res["energy"], forces=res["forces"], stress=res["stress"])
+
+
 def case_corrections(n_mol=8, seed=23):
     """EnergyDerivativeModel with the reference's own ZBLRepulsion + ExponentialRepulsion (apax/layers/empirical.py) in
     EnergyModel.corrections, on a small multi-image water cell squeezed so that O-H pairs sit inside the corrections' range."""
@@ -382,3 +398,5 @@ if __name__ == "__main__":
     print("stress ok")
     case_corrections()
     print("corrections ok")
+    case_stress_offsets()
+    print("stress_offsets ok")

@@ -260,3 +260,24 @@ def test_empirical_corrections_zbl_and_exponential(golden):
     plain = syn.gmnn_params(seed=int(d["param_seed"]), random_bias=True, random_scale_shift=True)
     e0 = GMNNBuilder().build_energy_derivative_model(init_box=d["cell"].T).apply(plain, d["frac"], d["Z"], d["idx"], d["cell"], d["offsets"])
     assert abs(float(e0["energy"].item()) - e) > 1.0      # the corrections are a large part of this energy
+
+
+def test_stress_times_vol_offsets_branch(golden):
+    """calc_stress on the vesin / offsets path: dU/d(eps) at doubled displacements, as the reference's disp_fn computes it
+    (apax/layers/distances.py:12-22), against the fixture written by the reference's own source and the oracle in fp64."""
+    from apax_b200.nn.builder import GMNNBuilder
+    from oracle import gmnn_oracle as go
+
+    d = golden("water_stress_offsets")
+    params = syn.gmnn_params(seed=int(d["param_seed"]), random_bias=True)
+    model = GMNNBuilder({"calc_stress": True}).build_energy_derivative_model(init_box=d["cell"].T)
+    out = model.apply(params, d["frac"], d["Z"], d["idx"], d["cell"], d["offsets"])
+    torch.cuda.synchronize()
+    s = out["stress"].cpu().numpy()
+    ref64 = go.stress_times_vol(params, d["frac"], d["Z"], d["idx"], d["cell"], d["offsets"], "offsets", go.fp64_config())
+    scale = np.abs(d["stress"]).max()
+    assert np.abs(s - d["stress"]).max() <= 2e-6 * scale                      # vs the reference source (fp32 model)
+    assert np.abs(s - ref64).max() <= 2.0 * np.abs(d["stress"] - ref64).max() + 1e-6 * scale
+    # energy and forces of the same call are those of the unperturbed evaluation
+    assert abs(float(out["energy"].item()) - float(d["energy"])) <= 1e-6 * abs(float(d["energy"]))
+    assert_force_parity(out["forces"].cpu().numpy(), d["forces"], where="stress_offsets")

@@ -127,6 +127,19 @@ def test_stress_oracle_against_reference_source(golden):
     assert np.abs(st - st.T).max() <= 1e-5 * np.abs(st).max()
 
 
+def test_stress_offsets_oracle_against_reference_source(golden):
+    """The offsets branch of stress_times_vol as the reference's disp_fn computes it (apax/layers/distances.py:12-22: the strain
+    acts on dR + (I + eps) . dR, offsets added afterwards) vs the fixture from the reference's own source."""
+    from apax_b200 import synthetic as syn
+    from oracle import gmnn_oracle as go
+
+    d = golden("water_stress_offsets")
+    params = syn.gmnn_params(seed=int(d["param_seed"]), random_bias=True)
+    st = go.stress_times_vol(params, d["frac"], d["Z"], d["idx"], d["cell"], d["offsets"], "offsets")
+    assert np.abs(st - d["stress"]).max() <= 1e-6 * np.abs(d["stress"]).max()
+    assert np.abs(st - st.T).max() > 1e-2 * np.abs(st).max()      # not a physical stress: the doubled displacement breaks the symmetry
+
+
 def test_empirical_corrections_against_reference_source(golden):
     """ZBLRepulsion / ExponentialRepulsion (apax/layers/empirical.py:25-126) restated in the oracle vs the reference's own source."""
     from apax_b200 import synthetic as syn
