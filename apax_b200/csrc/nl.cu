@@ -252,7 +252,75 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
   const int grp = threadIdx.x / LG;
   const int64_t base = PASS == 1 ? int64_t(w.rowptr[atom]) : PASS == 2 ? atom * int64_t(stride) : 0;
   int count = 0;
-  const int m0 = (valid && !(PASS == 1 && w.rowcnt[atom] <= stride)) ? g.m[0] : -1;
+  int m0 = (valid && !(PASS == 1 && w.rowcnt[atom] <= stride)) ? g.m[0] : -1;
+  // what happens to an accepted candidate (both scan forms)
+  auto accept = [&](int j, int packed) {
+    if (FILL) {
+      const int slot = atomicAdd(&s_cnt[grp], 1);   // shared-memory counter of the lane group
+      if (PASS == 2) {
+        if (slot < stride) scratch[base + slot] = j;
+      } else if (base + slot < w.capacity) {
+        w.nbr_tmp[base + slot] = j;
+        if (MODE == 1) w.shift_tmp[base + slot] = packed;
+      }
+    } else {
+      ++count;
+    }
+  };
+  // Min-image scan over at most 27 cells, software-pipelined: the lane group first fetches all cell ranges at once (one
+  // exposed latency instead of 27 dependent ones), then every lane walks its share of the candidates as ONE stream with the
+  // next candidate's record already in flight while the current one is tested (ncu: 38 % of this kernel's stall samples sat
+  // on the first use of the just-issued candidate load).  Same candidates and the same predicate as the loop nest below; the
+  // order in which accepted pairs land is irrelevant, rows are sorted afterwards.
+  if (MODE == 0) {
+    constexpr int kMaxCells = 27;
+    const int n1 = 2 * g.m[1] + 1, n2 = 2 * g.m[2] + 1;
+    const int ncell = (2 * g.m[0] + 1) * n1 * n2;   // uniform over the grid
+    if (ncell <= kMaxCells) {
+      __shared__ int s_cb[256 / LG][kMaxCells], s_ce[256 / LG][kMaxCells];
+      if (m0 >= 0) {
+        for (int cc = sub; cc < ncell; cc += LG) {
+          const int q0 = c[0] + cc / (n2 * n1) - g.m[0], q1 = c[1] + (cc / n2) % n1 - g.m[1], q2 = c[2] + cc % n2 - g.m[2];
+          const int s0 = q0 >= 0 ? q0 / g.nc[0] : -((-q0 + g.nc[0] - 1) / g.nc[0]);
+          const int s1 = q1 >= 0 ? q1 / g.nc[1] : -((-q1 + g.nc[1] - 1) / g.nc[1]);
+          const int s2 = q2 >= 0 ? q2 / g.nc[2] : -((-q2 + g.nc[2] - 1) / g.nc[2]);
+          const int cid = ((q0 - s0 * g.nc[0]) * g.nc[1] + (q1 - s1 * g.nc[1])) * g.nc[2] + (q2 - s2 * g.nc[2]);
+          s_cb[grp][cc] = w.cellptr[cid];
+          s_ce[grp][cc] = w.cellptr[cid + 1];
+        }
+      }
+      __syncwarp();
+      if (m0 >= 0) {
+        int cc = 0, t = s_cb[grp][0] + sub, ce = s_ce[grp][0];
+        while (t >= ce && ++cc < ncell) { t = s_cb[grp][cc] + sub; ce = s_ce[grp][cc]; }
+        float4 q_nxt = cc < ncell ? w.cell_pos[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+        while (cc < ncell) {
+          const float4 q = q_nxt;
+          t += LG;
+          while (t >= ce && ++cc < ncell) { t = s_cb[grp][cc] + sub; ce = s_ce[grp][cc]; }
+          if (cc < ncell) q_nxt = w.cell_pos[t];
+          const int j = __float_as_int(q.w);
+          float u0 = fa[0] - q.x, u1 = fa[1] - q.y, u2 = fa[2] - q.z;
+          u0 -= rintf(u0); u1 -= rintf(u1); u2 -= rintf(u2);
+          const float e0 = Bf[0] * u0 + Bf[1] * u1 + Bf[2] * u2;
+          const float e1 = Bf[3] * u0 + Bf[4] * u1 + Bf[5] * u2;
+          const float e2 = Bf[6] * u0 + Bf[7] * u1 + Bf[8] * u2;
+          const float d2f = e0 * e0 + e1 * e1 + e2 * e2;
+          bool keep;
+          if (d2f > c2_hi || j == atom) {
+            keep = false;
+          } else if (d2f < c2_lo) {
+            keep = true;
+          } else {
+            const double bx = pos[3 * int64_t(j)], by = pos[3 * int64_t(j) + 1], bz = pos[3 * int64_t(j) + 2];
+            keep = metric_sq_minimage(g.B, ax, ay, az, bx, by, bz) < g.cutoff_sq;
+          }
+          if (keep) accept(j, 0);
+        }
+      }
+      m0 = -1;   // done: the loop nest below is skipped
+    }
+  }
   for (int d0 = -m0; d0 <= m0; ++d0) {
     const int q0 = c[0] + d0;
     const int s0 = q0 >= 0 ? q0 / g.nc[0] : -((-q0 + g.nc[0] - 1) / g.nc[0]);
@@ -306,19 +374,7 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
                    S0 >= -127 && S0 <= 127 && S1 >= -127 && S1 <= 127 && S2 >= -127 && S2 <= 127;
             packed = pack_shift(S0, S1, S2);
           }
-          if (keep) {
-            if (FILL) {
-              const int slot = atomicAdd(&s_cnt[grp], 1);   // shared-memory counter of the lane group
-              if (PASS == 2) {
-                if (slot < stride) scratch[base + slot] = j;
-              } else if (base + slot < w.capacity) {
-                w.nbr_tmp[base + slot] = j;
-                if (MODE == 1) w.shift_tmp[base + slot] = packed;
-              }
-            } else {
-              ++count;
-            }
-          }
+          if (keep) accept(j, packed);
         }
       }
     }
