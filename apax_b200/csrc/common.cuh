@@ -52,6 +52,15 @@ void profile_after(cudaStream_t stream);
     APAX_TRY(::apax::check_launch());                              \
   } while (0)
 
+// the same with an explicit profile label (template instantiations whose arguments are template parameters at the launch site)
+#define APAX_LAUNCH_AS(label, kernel, grid, block, smem, stream, ...) \
+  do {                                                                \
+    if (::apax::g_profile_on) ::apax::profile_before(label, (stream)); \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);       \
+    if (::apax::g_profile_on) ::apax::profile_after((stream));        \
+    APAX_TRY(::apax::check_launch());                                 \
+  } while (0)
+
 constexpr int kNumSM = 148;  // B200
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
