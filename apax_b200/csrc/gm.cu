@@ -977,41 +977,47 @@ __global__ void k_energy_final(const double* __restrict__ partial, int n_blocks,
 // E_corr = w * sum over list entries of E_ij(r) with w = 0.5 softplus(rep_scale) (ZBL) or 1 (exponential); both are
 // evaluated in fp32 per entry and summed in fp64, like the reference (fp64_sum).  The distance is clipped to
 // [0.02, r_max] (zero slope outside), the cosine cutoff ends at the correction's own r_max.
-__device__ __forceinline__ void corr_pair(const CorrConst& cc, float r, int zi, int zj, float& e, float& dedr) {
-  e = 0.f; dedr = 0.f;
-  const float pi_f = 3.14159265358979323846f;
+// The pair functions are evaluated in fp64 from the parameters' fp32 values: only the two or three entries per atom inside
+// the corrections' range get here, so the cost is nil, and the steep repulsion (pair forces of 100 eV/A) would otherwise
+// carry a few fp32 ulps of the LARGEST pair force into every force component (the reference's fp32 chain has the same
+// weakness; the result stays inside its tolerance either way, this one is the closer to the exact derivative).
+__device__ __forceinline__ void corr_pair(const CorrConst& cc, double r, int zi, int zj, double& e, double& dedr) {
+  e = 0.0; dedr = 0.0;
+  const double pi_d = 3.14159265358979323846;
   if (cc.zbl_on) {
-    const float dr = fminf(fmaxf(r, 0.02f), cc.zbl_rmax);
-    const bool inside = r > 0.02f && r < cc.zbl_rmax;
-    float sn, cs;
-    sincosf(pi_f * dr / cc.zbl_rmax, &sn, &cs);
-    const float fc = 0.5f * (cs + 1.0f), dfc = -0.5f * (pi_f / cc.zbl_rmax) * sn;
-    const float fi = float(zi), fj = float(zj);
-    const float a_div = powf(fi, 0.23f) + powf(fj, 0.23f), k = a_div / 0.46850f;
-    const float dist = dr * k;
-    float f = 0.f, df = 0.f;
+    const double rmax = double(cc.zbl_rmax);
+    const double dr = fmin(fmax(r, 0.02), rmax);
+    const bool inside = r > 0.02 && r < rmax;
+    double sn, cs;
+    sincos(pi_d * dr / rmax, &sn, &cs);
+    const double fc = 0.5 * (cs + 1.0), dfc = -0.5 * (pi_d / rmax) * sn;
+    const double fi = double(zi), fj = double(zj);
+    const double k = (pow(fi, 0.23) + pow(fj, 0.23)) / 0.46850;
+    const double dist = dr * k;
+    double f = 0.0, df = 0.0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float t = cc.zbl_c[q] * expf(-cc.zbl_e[q] * dist);
+      const double t = double(cc.zbl_c[q]) * exp(-double(cc.zbl_e[q]) * dist);
       f += t;
-      df -= cc.zbl_e[q] * k * t;
+      df -= double(cc.zbl_e[q]) * k * t;
     }
-    const float pref = fi * fj / dr;
-    const float w = 0.5f * cc.zbl_scale;
+    const double pref = fi * fj / dr;
+    const double w = 0.5 * double(cc.zbl_scale);
     e += w * (pref * f * fc);
     if (inside) dedr += w * pref * (-f * fc / dr + df * fc + f * dfc);
   }
   if (cc.exp_on) {
-    const float dr = fminf(fmaxf(r, 0.02f), cc.exp_rmax);
-    const bool inside = r > 0.02f && r < cc.exp_rmax;
-    float sn, cs;
-    sincosf(pi_f * dr / cc.exp_rmax, &sn, &cs);
-    const float fc = 0.5f * (cs + 1.0f), dfc = -0.5f * (pi_f / cc.exp_rmax) * sn;
-    const float ri = cc.exp_r[zi], rj = cc.exp_r[zj];
-    const float k = (ri + rj) / (ri * rj);
-    const float f = cc.exp_a[zi] * cc.exp_a[zj] * expf(-dr * k) / (dr * dr);
+    const double rmax = double(cc.exp_rmax);
+    const double dr = fmin(fmax(r, 0.02), rmax);
+    const bool inside = r > 0.02 && r < rmax;
+    double sn, cs;
+    sincos(pi_d * dr / rmax, &sn, &cs);
+    const double fc = 0.5 * (cs + 1.0), dfc = -0.5 * (pi_d / rmax) * sn;
+    const double ri = double(cc.exp_r[zi]), rj = double(cc.exp_r[zj]);
+    const double k = (ri + rj) / (ri * rj);
+    const double f = double(cc.exp_a[zi]) * double(cc.exp_a[zj]) * exp(-dr * k) / (dr * dr);
     e += f * fc;
-    if (inside) dedr += f * (-k - 2.0f / dr) * fc + f * dfc;
+    if (inside) dedr += f * (-k - 2.0 / dr) * fc + f * dfc;
   }
 }
 
@@ -1055,19 +1061,19 @@ __global__ void __launch_bounds__(256) k_pair_corrections(GmWorkspace ws, PairGe
       }
     }
     const double r64sq = d0 * d0 + d1 * d1 + d2 * d2;
-    const float r = r64sq > 0.0 ? float(sqrt(r64sq)) : 0.f;
+    const double r = r64sq > 0.0 ? sqrt(r64sq) : 0.0;
     const int pt = __float_as_int(g.w);
-    float e, dedr;
+    double e, dedr;
     corr_pair(cc, r, ws.sp_z[pt / n_sp], ws.sp_z[pt % n_sp], e, dedr);
     if (FORCES) {
       // the correction's share of dE/d(dr) is kept apart from the descriptor's fp32 value: its scalar dE_corr/dr / r goes
-      // into the spare lane of D and the vector is formed in fp64 wherever it is summed (here, in the transpose gather and
-      // in the virial), as the reference accumulates it in the fp64 position gradient
-      const float k = r > 0.f ? dedr / r : 0.f;
-      reinterpret_cast<float*>(ws.D + s)[3] = k;
-      acc0 += double(k) * double(g.x); acc1 += double(k) * double(g.y); acc2 += double(k) * double(g.z);
+      // into the spare lane of D and the vector is formed in fp64 wherever it is summed (in the transpose gather and in the
+      // virial from the stored fp32 displacement; here, for the central atom's own row, from the fp64 one)
+      const double k = r > 0.0 ? dedr / r : 0.0;
+      reinterpret_cast<float*>(ws.D + s)[3] = float(k);
+      acc0 += k * d0; acc1 += k * d1; acc2 += k * d2;
     } else {
-      acc0 += double(e);
+      acc0 += e;
     }
   }
 #pragma unroll

@@ -472,5 +472,6 @@ def stress_times_vol(params, R, Z, idx, box, offsets, mode: str, cfg: Optional[G
     E_i = per_element_scale_shift(h, Z, scale, shift, cfg)
     if cfg.mask_atoms:
         E_i = E_i * (Z != 0).to(E_i.dtype)[:, None]
-    (gr,) = torch.autograd.grad(torch.sum(E_i.to(torch.float64)), eps)
+    energy = torch.sum(E_i.to(torch.float64)) + corrections_energy(params, d, Z, idx, cfg)   # models.py:127-130
+    (gr,) = torch.autograd.grad(energy, eps)
     return gr.numpy()

@@ -281,3 +281,57 @@ def test_stress_times_vol_offsets_branch(golden):
     # energy and forces of the same call are those of the unperturbed evaluation
     assert abs(float(out["energy"].item()) - float(d["energy"])) <= 1e-6 * abs(float(d["energy"]))
     assert_force_parity(out["forces"].cpu().numpy(), d["forces"], where="stress_offsets")
+
+
+def _with_corrections(params, seed=3):
+    """ZBL + exponential blocks as flax names them (corrections_0, corrections_1); ranges that catch water's O-H and H-H pairs."""
+    rng = np.random.default_rng(seed)
+    em = params["params"]["energy_model"]
+    em["corrections_0"] = {"coefficients": rng.normal(size=(4, 1)).astype(np.float32), "rep_scale": np.array([-1.2], dtype=np.float32)}
+    em["corrections_1"] = {"rep_scale": (rng.uniform(0.3, 1.2, size=119) * rng.choice([-1, 1], size=119)).astype(np.float32),
+                           "rep_prefactor": rng.uniform(1.0, 20.0, size=119).astype(np.float32)}
+    return params
+
+
+def test_corrections_min_image_energy_forces_stress_vs_oracle(rt, oracle):
+    """The pair corrections on the JaxMD min-image path (E, F and stress x volume share the corrected per-pair records) against
+    the oracle in reference precision and in fp64; 768 atoms, list with skin."""
+    go, no = oracle
+    pos, Z, cell = syn.water_box(256, 11)
+    frac = pos @ np.linalg.inv(cell)
+    idx, occ, ov = no.jaxmd_sparse_list(frac, cell.T, 6.0, 0.5)
+    assert not ov
+    p = _with_corrections(syn.gmnn_params(seed=99, random_scale_shift=True, random_bias=True))
+    kcfg, ocfg = {"zbl_r_max": 1.8, "exp_r_max": 1.6}, go.GMNNConfig(zbl_r_max=1.8, exp_r_max=1.6)
+    ref = go.energy_forces(p, frac, Z, idx, cell.T, None, "minimage", ocfg)
+    ref64 = go.energy_forces(p, frac, Z, idx, cell.T, None, "minimage", go.fp64_config(ocfg))
+    dp = rt.DeviceParams(p, kcfg)
+    e, f, s = rt.energy_forces(dp, frac, Z, idx, cell.T, None, "minimage", stress=True)
+    torch.cuda.synchronize()
+    e, f, s = e.cpu().numpy(), f.cpu().numpy(), s.cpu().numpy()
+    assert abs(e[0] - ref["energy"]) <= E_RTOL * abs(ref["energy"]), (e[0], ref["energy"])
+    # the per-pair records are fp32 (scalar dE/dr / r and the displacement): two roundings of a 230 eV/A O-H pair force show up
+    # as a few 1e-5 eV/A in a net force of 75 eV/A -- 20x inside the literal tolerance (checked above all else), a few ulps of |F|max
+    assert_force_parity(f[0], ref["forces"], ref64["forces"], where="corrections min-image", ulp_floor=8.0)
+    st32 = go.stress_times_vol(p, frac, Z, idx, cell.T, None, "minimage", ocfg)
+    st64 = go.stress_times_vol(p, frac, Z, idx, cell.T, None, "minimage", go.fp64_config(ocfg))
+    scale = np.abs(st64).max()
+    assert np.abs(s - st32).max() <= 2e-6 * scale
+    assert np.abs(s - st64).max() <= 2.0 * np.abs(st32 - st64).max() + 1e-6 * scale
+
+
+def test_corrections_with_shallow_ensemble_heads(rt, oracle):
+    """Every head of a shallow ensemble carries the same correction energy and forces (EnergyModel adds it after the readout)."""
+    go, no = oracle
+    pos, Z, cell = syn.water_box(32, 5)
+    idx, offsets = no.vesin_idx_offsets(pos, cell, 6.0)
+    frac = pos @ np.linalg.inv(cell)
+    n_ens = 4
+    p = _with_corrections(syn.gmnn_params(seed=5, n_out=n_ens, random_scale_shift=True, random_bias=True))
+    kcfg, ocfg = {"zbl_r_max": 1.8, "exp_r_max": 1.6}, go.GMNNConfig(zbl_r_max=1.8, exp_r_max=1.6)
+    e, f = _ef(rt, p, frac, Z, idx, cell, offsets, "offsets", kcfg)
+    r32 = go.shallow_ensemble(p, frac, Z, idx, cell, offsets, "offsets", ocfg)
+    r64 = go.shallow_ensemble(p, frac, Z, idx, cell, offsets, "offsets", go.fp64_config(ocfg))
+    assert np.all(np.abs(e - r32["energy_ensemble"]) <= 2e-6 * np.abs(r32["energy_ensemble"]) + 1e-6)
+    assert_force_parity(np.transpose(f, (1, 2, 0)), r32["forces_ensemble"], r64["forces_ensemble"], where="corrections ensemble",
+                        ulp_floor=8.0)
