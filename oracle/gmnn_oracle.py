@@ -48,6 +48,8 @@ class GMNNConfig:
     descriptor_dtype: torch.dtype = torch.float32
     readout_dtype: torch.dtype = torch.float32
     scale_shift_dtype: torch.dtype = torch.float64
+    correction_dtype: torch.dtype = torch.float32   # the reference's corrections run in fp32 whatever the model dtypes are; fp64_config
+                                                    # leaves it alone, the finite-difference self-checks set it to float64
 
 
 # ---------------------------------------------------------------------------
@@ -290,39 +292,40 @@ def per_element_scale_shift(h, Z, scale, shift, cfg: GMNNConfig):
     return scale.to(dt)[Zl] * h.to(dt) + shift.to(dt)[Zl]
 
 
-def _correction_prelude(dr_vec, Z, idx, r_max: float):
+def _correction_prelude(dr_vec, Z, idx, r_max: float, dt=torch.float32):
     """Common head of the empirical terms (empirical.py:51-63 / 104-115): species of both ends, fp32 distance clipped to
     [0.02, r_max], cosine cutoff on the clipped distance."""
     n = Z.shape[0]
     Zl = Z.long()
     Z_i, Z_j = Zl[idx[0].long().clamp(0, n - 1)], Zl[idx[1].long().clamp(0, n - 1)]
-    dr = safe_distance(dr_vec).to(torch.float32)
+    dr = safe_distance(dr_vec).to(dt)
     dr = torch.clamp(dr, min=0.02, max=r_max)
     cos_cutoff = 0.5 * (torch.cos(np.pi * dr / r_max) + 1.0)
     return Z_i, Z_j, dr, cos_cutoff
 
 
-def zbl_repulsion(dr_vec, Z, idx, coefficients, rep_scale, r_max: float, apply_mask: bool = True):
-    """ZBLRepulsion.__call__ (apax/layers/empirical.py:48-86); coefficients [4,1] and rep_scale [1] as stored (pre-softplus)."""
-    Z_i, Z_j, dr, cos_cutoff = _correction_prelude(dr_vec, Z, idx, r_max)
+def zbl_repulsion(dr_vec, Z, idx, coefficients, rep_scale, r_max: float, apply_mask: bool = True, dt=torch.float32):
+    """ZBLRepulsion.__call__ (apax/layers/empirical.py:48-86); coefficients [4,1] and rep_scale [1] as stored (pre-softplus).
+    dt: arithmetic type of the term (the reference: its `dtype` attribute, fp32)."""
+    Z_i, Z_j, dr, cos_cutoff = _correction_prelude(dr_vec, Z, idx, r_max, dt)
     a_exp, a_num = 0.23, 0.46850
-    coeffs = torch.nn.functional.softplus(coefficients.to(torch.float32).reshape(4, 1))
-    exponents = torch.tensor([3.19980, 0.94229, 0.4029, 0.20162], dtype=torch.float32).reshape(4, 1)
-    scale = torch.nn.functional.softplus(rep_scale.to(torch.float32).reshape(-1))[0]
-    a_divisor = Z_i.to(torch.float32) ** a_exp + Z_j.to(torch.float32) ** a_exp
+    coeffs = torch.nn.functional.softplus(coefficients.to(dt).reshape(4, 1))
+    exponents = torch.tensor([3.19980, 0.94229, 0.4029, 0.20162], dtype=dt).reshape(4, 1)
+    scale = torch.nn.functional.softplus(rep_scale.to(dt).reshape(-1))[0]
+    a_divisor = Z_i.to(dt) ** a_exp + Z_j.to(dt) ** a_exp
     dist = dr * a_divisor / a_num
     f = torch.sum(coeffs * torch.exp(-exponents * dist), dim=0)
-    E_ij = Z_i.to(torch.float32) * Z_j.to(torch.float32) / dr * f * cos_cutoff
+    E_ij = Z_i.to(dt) * Z_j.to(dt) / dr * f * cos_cutoff
     if apply_mask:
         E_ij = E_ij * ((idx[0] - idx[1]) != 0).to(E_ij.dtype)
     return 0.5 * scale * torch.sum(E_ij.to(torch.float64))
 
 
-def exponential_repulsion(dr_vec, Z, idx, rscale, prefactor, r_max: float, apply_mask: bool = True):
+def exponential_repulsion(dr_vec, Z, idx, rscale, prefactor, r_max: float, apply_mask: bool = True, dt=torch.float32):
     """ExponentialRepulsion.__call__ (apax/layers/empirical.py:101-126); rscale, prefactor [n_species] as stored."""
-    Z_i, Z_j, dr, cos_cutoff = _correction_prelude(dr_vec, Z, idx, r_max)
-    A = torch.abs(prefactor.to(torch.float32))
-    Rr = torch.abs(rscale.to(torch.float32))
+    Z_i, Z_j, dr, cos_cutoff = _correction_prelude(dr_vec, Z, idx, r_max, dt)
+    A = torch.abs(prefactor.to(dt))
+    Rr = torch.abs(rscale.to(dt))
     A_i, A_j, R_i, R_j = A[Z_i], A[Z_j], Rr[Z_i], Rr[Z_j]
     f = A_i * A_j * torch.exp(-dr * (R_i + R_j) / (R_i * R_j)) / dr ** 2
     E_ij = f * cos_cutoff
@@ -340,9 +343,11 @@ def corrections_energy(params, dr_vec, Z, idx, cfg: GMNNConfig):
     for key in sorted(k for k in em if k.startswith("corrections_")):
         blk = {k: torch.as_tensor(np.asarray(v)) for k, v in em[key].items()}
         if "coefficients" in blk:
-            total = total + zbl_repulsion(dr_vec, Z, idx, blk["coefficients"], blk["rep_scale"], cfg.zbl_r_max, cfg.apply_mask)
+            total = total + zbl_repulsion(dr_vec, Z, idx, blk["coefficients"], blk["rep_scale"], cfg.zbl_r_max, cfg.apply_mask,
+                                          cfg.correction_dtype)
         elif "rep_prefactor" in blk:
-            total = total + exponential_repulsion(dr_vec, Z, idx, blk["rep_scale"], blk["rep_prefactor"], cfg.exp_r_max, cfg.apply_mask)
+            total = total + exponential_repulsion(dr_vec, Z, idx, blk["rep_scale"], blk["rep_prefactor"], cfg.exp_r_max, cfg.apply_mask,
+                                                  cfg.correction_dtype)
     return total
 
 

@@ -145,3 +145,24 @@ def test_public_header_is_plain_c(tmp_path):
     src.write_text('#include "apax_b200.h"\nint main(void) { apax_gm_config c; (void)c; return APAX_B200_ABI_VERSION == 2 ? 0 : 1; }\n')
     inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
     subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, "-fsyntax-only", str(src)])
+
+
+def test_builder_empirical_corrections_and_stress_statics():
+    """apax/nn/builder.py:146-158: the `empirical_corrections` list of the model config becomes ZBL / exponential entries of
+    EnergyModel.corrections; their ranges reach the kernel statics; unknown names are refused (no silent skip)."""
+    import pytest
+
+    from apax_b200.nn.builder import GMNNBuilder
+    from apax_b200.nn.models import ExponentialRepulsion, ZBLRepulsion
+
+    cfg = {"empirical_corrections": [{"name": "zbl", "r_max": 1.8}, {"name": "exponential", "r_max": 1.5}], "calc_stress": True}
+    model = GMNNBuilder(cfg).build_energy_derivative_model(init_box=np.eye(3) * 10.0)
+    kinds = [type(c) for c in model.energy_model.corrections]
+    assert kinds == [ZBLRepulsion, ExponentialRepulsion]
+    st = model.energy_model.statics()
+    assert st["zbl_r_max"] == 1.8 and st["exp_r_max"] == 1.5
+    assert model.calc_stress
+    with pytest.raises(NotImplementedError):
+        GMNNBuilder({"empirical_corrections": [{"name": "d3", "r_max": 2.0}]}).build_energy_derivative_model(init_box=np.eye(3))
+    plain = GMNNBuilder().build_energy_derivative_model(init_box=np.eye(3) * 10.0)
+    assert plain.energy_model.corrections == [] and "zbl_r_max" not in plain.energy_model.statics()

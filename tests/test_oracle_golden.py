@@ -154,3 +154,59 @@ def test_empirical_corrections_against_reference_source(golden):
     ref = go.energy_forces(params, d["frac"], d["Z"], d["idx"], d["cell"], d["offsets"], "offsets", cfg)
     assert abs(ref["energy"] - float(d["energy"])) <= 1e-7 * abs(float(d["energy"]))
     assert np.abs(ref["forces"] - d["forces"]).max() <= 1e-6 * np.abs(d["forces"]).max()
+
+
+def _water_with_corrections(n_mol=8, seed=3):
+    from apax_b200 import synthetic as syn
+    from oracle import gmnn_oracle as go, neighbor_oracle as no
+
+    pos, Z, cell = syn.water_box(n_mol, seed)
+    idx, offsets = no.vesin_idx_offsets(pos, cell, 6.0)
+    frac = pos @ np.linalg.inv(cell)
+    rng = np.random.default_rng(seed)
+    p = syn.gmnn_params(seed=17, random_bias=True, random_scale_shift=True)
+    em = p["params"]["energy_model"]
+    em["corrections_0"] = {"coefficients": rng.normal(size=(4, 1)).astype(np.float32), "rep_scale": np.array([-1.2], dtype=np.float32)}
+    em["corrections_1"] = {"rep_scale": (rng.uniform(0.3, 1.2, size=119) * rng.choice([-1, 1], size=119)).astype(np.float32),
+                           "rep_prefactor": rng.uniform(1.0, 20.0, size=119).astype(np.float32)}
+    cfg = go.fp64_config(go.GMNNConfig(zbl_r_max=1.8, exp_r_max=1.6))
+    cfg.correction_dtype = torch.float64      # finite differences need the whole energy in fp64 (the reference's terms run in fp32)
+    return go, p, frac, Z, idx, cell, offsets, cfg
+
+
+def test_oracle_corrections_forces_match_finite_differences():
+    """Self-check of the oracle's correction terms: fp64 forces vs central differences of the fp64 energy, and the
+    terms really act (the energy without the correction blocks differs)."""
+    go, p, frac, Z, idx, cell, offsets, cfg = _water_with_corrections()
+    ref = go.energy_forces(p, frac, Z, idx, cell, offsets, "offsets", cfg)
+    h = 1e-6
+    rng = np.random.default_rng(0)
+    for a, k in zip(rng.integers(0, len(Z), 6), rng.integers(0, 3, 6)):
+        dpos = np.zeros_like(frac)
+        dpos[a, k] = h
+        dfrac = dpos @ np.linalg.inv(cell)           # a Cartesian step of h along k, in fractional coordinates
+        ep = go.energy_forces(p, frac + dfrac, Z, idx, cell, offsets, "offsets", cfg)["energy"]
+        em_ = go.energy_forces(p, frac - dfrac, Z, idx, cell, offsets, "offsets", cfg)["energy"]
+        fd = -(ep - em_) / (2 * h)
+        assert abs(fd - ref["forces"][a, k]) <= 1e-5 * max(1.0, abs(fd)), (a, k, fd, ref["forces"][a, k])
+    plain = {"params": {"energy_model": {k: v for k, v in p["params"]["energy_model"].items() if not k.startswith("corrections_")}}}
+    assert abs(go.energy_forces(plain, frac, Z, idx, cell, offsets, "offsets", cfg)["energy"] - ref["energy"]) > 1.0
+
+
+def test_oracle_stress_with_corrections_matches_strain_finite_differences():
+    """stress_times_vol of the oracle on the min-image branch incl. the correction terms vs central differences in the strain
+    (dr' = (I + eps) . dr applied to the box: box' = (I + eps) . box leaves the fractional coordinates alone)."""
+    from oracle import neighbor_oracle as no
+
+    go, p, frac, Z, _idx, cell, _off, cfg = _water_with_corrections(n_mol=64, seed=4)
+    idx, occ, ov = no.jaxmd_sparse_list(frac, cell.T, 6.0, 0.0)
+    assert not ov
+    st = go.stress_times_vol(p, frac, Z, idx, cell.T, None, "minimage", cfg)
+    h = 1e-6
+    for (i, j) in ((0, 0), (0, 1), (2, 1)):
+        eps = np.zeros((3, 3))
+        eps[i, j] = h
+        ep = go.energy_forces(p, frac, Z, idx, (np.eye(3) + eps) @ cell.T, None, "minimage", cfg)["energy"]
+        em_ = go.energy_forces(p, frac, Z, idx, (np.eye(3) - eps) @ cell.T, None, "minimage", cfg)["energy"]
+        fd = (ep - em_) / (2 * h)
+        assert abs(fd - st[i, j]) <= 1e-5 * max(1.0, np.abs(st).max()), (i, j, fd, st[i, j])
