@@ -10,7 +10,8 @@
 //
 // Replaces, behind apax's Flax modules: EnergyDerivativeModel.apply (apax/nn/models.py:146-171), the jax_md neighbour list
 // (apax/utils/jax_md_reduced/partition.py:478-787), GaussianMomentDescriptor.__call__
-// (apax/layers/descriptor/gaussian_moment_descriptor.py:31-103) and update_step (apax/train/trainer.py:332-336).
+// (apax/layers/descriptor/gaussian_moment_descriptor.py:31-103), stress_times_vol (apax/layers/properties.py:11-42) and update_step
+// (apax/train/trainer.py:332-336).  Empirical corrections travel with the parameter handle (apax_gm_params_set_corrections).
 #include <cstdint>
 
 #include "apax_b200.h"
@@ -41,6 +42,37 @@ ffi::Error EnergyForces(cudaStream_t stream, int64_t params, int32_t disp_mode, 
                                       disp_mode, energy->typed_data(), forces->typed_data(), workspace->typed_data(),
                                       workspace->element_count()),
                 "apax_gm_energy_forces");
+}
+
+// ---- energy + forces + stress x volume (EnergyDerivativeModel with calc_stress, apax/nn/models.py:160-169) ------------------
+// MINIMAGE: the strain enters as (I + eps) . dr (space.py:277-278) and the virial is reduced from the records the force pass
+// left in the workspace.  OFFSETS: the reference's disp_fn differentiates at doubled displacements
+// (apax/layers/distances.py:12-22); the caller passes box2 = 2 * box (a trivial XLA op) and two scratch results for the second
+// force pass, as include/apax_b200.h describes for apax_gm_stress_times_vol_offsets.
+ffi::Error EnergyForcesStress(cudaStream_t stream, int64_t params, int32_t disp_mode, ffi::Buffer<ffi::F64> R, ffi::Buffer<ffi::S32> Z,
+                              ffi::Buffer<ffi::S32> idx, ffi::Buffer<ffi::F64> box, ffi::AnyBuffer offsets, ffi::AnyBuffer box2,
+                              ffi::ResultBuffer<ffi::F64> energy, ffi::ResultBuffer<ffi::F64> forces,
+                              ffi::ResultBuffer<ffi::F64> stress, ffi::ResultBuffer<ffi::F64> energy2,
+                              ffi::ResultBuffer<ffi::F64> forces2, ffi::ResultBuffer<ffi::U8> workspace) {
+  const int64_t n = R.dimensions()[0], p = idx.dimensions()[1];
+  auto s = reinterpret_cast<apax_stream_t>(stream);
+  auto prm = reinterpret_cast<const apax_gm_params*>(params);
+  int rc = apax_gm_energy_forces(s, prm, R.typed_data(), Z.typed_data(), idx.typed_data(), box.typed_data(), opt<double>(offsets), n, p,
+                                 disp_mode, energy->typed_data(), forces->typed_data(), workspace->typed_data(),
+                                 workspace->element_count());
+  if (rc != APAX_OK) return status(rc, "apax_gm_energy_forces");
+  if (disp_mode == APAX_DISP_MINIMAGE)
+    return status(apax_gm_stress_times_vol(s, prm, n, p, stress->typed_data(), workspace->typed_data(), workspace->element_count()),
+                  "apax_gm_stress_times_vol");
+  if (disp_mode != APAX_DISP_OFFSETS || box2.element_count() != 9)
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument, "stress needs a periodic displacement (and box2 = 2 box on the offsets path)");
+  rc = apax_gm_energy_forces(s, prm, R.typed_data(), Z.typed_data(), idx.typed_data(), opt<double>(box2), opt<double>(offsets), n, p,
+                             disp_mode, energy2->typed_data(), forces2->typed_data(), workspace->typed_data(),
+                             workspace->element_count());
+  if (rc != APAX_OK) return status(rc, "apax_gm_energy_forces (doubled box)");
+  return status(apax_gm_stress_times_vol_offsets(s, prm, R.typed_data(), box.typed_data(), n, p, stress->typed_data(),
+                                                 workspace->typed_data(), workspace->element_count()),
+                "apax_gm_stress_times_vol_offsets");
 }
 
 // ---- descriptor only (the ModelBuilder.build_descriptor seam, apax/nn/builder.py:79-83) -------------------------------
@@ -100,6 +132,13 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(ApaxEnergyForces, EnergyForces,
                               APAX_FFI_STREAM.Attr<int64_t>("params").Attr<int32_t>("disp_mode")
                                   .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::S32>>().Arg<ffi::Buffer<ffi::S32>>()
                                   .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::U8>>(),
+                              {ffi::Traits::kCmdBufferCompatible});
+XLA_FFI_DEFINE_HANDLER_SYMBOL(ApaxEnergyForcesStress, EnergyForcesStress,
+                              APAX_FFI_STREAM.Attr<int64_t>("params").Attr<int32_t>("disp_mode")
+                                  .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::S32>>().Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>()
                                   .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::U8>>(),
                               {ffi::Traits::kCmdBufferCompatible});
 XLA_FFI_DEFINE_HANDLER_SYMBOL(ApaxDescriptor, Descriptor,

@@ -166,3 +166,51 @@ def test_builder_empirical_corrections_and_stress_statics():
         GMNNBuilder({"empirical_corrections": [{"name": "d3", "r_max": 2.0}]}).build_energy_derivative_model(init_box=np.eye(3))
     plain = GMNNBuilder().build_energy_derivative_model(init_box=np.eye(3) * 10.0)
     assert plain.energy_model.corrections == [] and "zbl_r_max" not in plain.energy_model.statics()
+
+
+_FFI_STUB = r"""
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+typedef struct CUstream_st* cudaStream_t;
+namespace xla { namespace ffi {
+enum class ErrorCode { kInvalidArgument, kInternal };
+struct Error { Error() {} Error(ErrorCode, std::string) {} static Error Success() { return Error(); } };
+enum DT { F64, S32, F32, U8 };
+template <DT> struct Native;
+template <> struct Native<F64> { using t = double; };
+template <> struct Native<S32> { using t = int32_t; };
+template <> struct Native<F32> { using t = float; };
+template <> struct Native<U8> { using t = uint8_t; };
+template <DT D> struct Buffer {
+  std::vector<int64_t> dimensions() const { return {}; }
+  typename Native<D>::t* typed_data() const { return nullptr; }
+  size_t element_count() const { return 0; }
+};
+struct AnyBuffer { size_t element_count() const { return 0; } void* untyped_data() const { return nullptr; } };
+template <DT D> struct ResultBuffer { Buffer<D>* operator->() const { return nullptr; } };
+struct Traits { static constexpr int kCmdBufferCompatible = 1; };
+}}
+#define XLA_FFI_DEFINE_HANDLER_SYMBOL(...)
+"""
+
+
+def test_xla_ffi_shim_parses_against_a_stub_of_the_ffi_api(tmp_path):
+    """jaxlib's headers are absent, so the shim cannot be built here; a stub of the few FFI types it touches at least keeps its
+    handler bodies (argument order and types of every forwarded C-ABI call, include/apax_b200.h) under the compiler's eye."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        import pytest
+
+        pytest.skip("no g++")
+    inc = tmp_path / "xla" / "ffi" / "api"
+    inc.mkdir(parents=True)
+    (inc / "ffi.h").write_text(_FFI_STUB)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", f"-I{tmp_path}", f"-I{os.path.join(root, 'include')}",
+                          os.path.join(root, "apax_b200", "ffi", "xla_ffi_shim.cc")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
