@@ -21,6 +21,8 @@ _ERR_NAMES = {-1: "APAX_ERR_INVALID_ARG", -2: "APAX_ERR_UNSUPPORTED", -3: "APAX_
               -5: "APAX_ERR_OVERFLOW"}
 
 DISP_GAS, DISP_OFFSETS, DISP_MINIMAGE, DISP_DRVEC = 0, 1, 2, 3
+OPT_READOUT, OPT_PAIR_BLOCK = 0, 1
+READOUT_KINDS = {"simt": 0, "tc": 1, "i8": 2}
 
 
 class ApaxB200Error(RuntimeError):
@@ -81,6 +83,7 @@ SIGNATURES = {
     "apax_profile_collect": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "apax_gm_params_create": (C.c_int, [C.POINTER(GmConfig), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     "apax_gm_params_set_corrections": (C.c_int, [_P, C.POINTER(GmCorrections)]),
+    "apax_gm_params_set_option": (C.c_int, [_P, _I32, _I32]),
     "apax_gm_params_destroy": (None, [_P]),
     "apax_gm_params_status": (C.c_int, [_P]),
     "apax_gm_workspace_bytes": (C.c_size_t, [_I64, _I64, _I32]),
@@ -93,6 +96,7 @@ SIGNATURES = {
     "apax_gm_stress_times_vol_offsets": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, C.c_size_t]),
     "apax_gm_descriptor": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, C.c_size_t]),
     "apax_i8_gemm_test": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _P, _P, _I32]),
+    "apax_i8_set_debug": (C.c_int, [_I32, _I32]),
     "apax_i8_mma_probe": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P]),
     "apax_tc_gemm_test": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _P, _I64, _P, _P, _P, _I32]),
     "apax_nl_workspace_bytes": (C.c_size_t, [_I64, _I64]),
@@ -119,12 +123,15 @@ SIGNATURES = {
     "apax_peer_free": (C.c_int, [_P]),
     "apax_train_allreduce_adam_step": (C.c_int, [_P, _P, C.POINTER(TrainOptConfig), C.POINTER(TrainPeers), C.c_uint32, _P, _P, _P, _P,
                                                  _P, _P, _P, _P]),
+    "apax_train_peers_status": (C.c_int, [C.POINTER(TrainPeers)]),
+    "apax_halo_status": (C.c_int, [C.POINTER(HaloPeers)]),
     "apax_halo_push_rows": (C.c_int, [_P, _P, _P, _P, C.POINTER(HaloPeers), C.c_uint32]),
     "apax_halo_pull_add_rows": (C.c_int, [_P, _P, _P, _P, C.POINTER(HaloPeers), C.c_uint32, _P, _P, _I32]),
     "apax_ensemble_stats": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, _P]),
     "apax_md_nvt_run": (C.c_int, [_P, C.POINTER(MdNvtConfig), _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, C.c_size_t, _I32]),
     "apax_ctx_create": (C.c_int, [_P, _I64, _I64, C.POINTER(_P)]),
     "apax_ctx_destroy": (None, [_P]),
+    "apax_ctx_stress": (C.c_int, [_P, _P]),
     "apax_ctx_calculate": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, _I32, _P, _P, _P]),
 }
 

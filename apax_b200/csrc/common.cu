@@ -3,6 +3,7 @@
 
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -11,8 +12,23 @@ namespace apax {
 std::atomic<int64_t> g_launch_count{0};
 thread_local cudaError_t g_last_error = cudaSuccess;
 
+int num_sms() {
+  static std::atomic<int> cached[64];   // per device ordinal; 0 = not queried yet
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
+// Per-launch event timing is a measurement aid (bench.py, tools/): one global switch and one record list behind a mutex,
+// so enabling it while several host threads launch is safe (their records interleave in launch order).
 bool g_profile_on = false;
 namespace {
+std::mutex g_prof_mutex;
 struct ProfRec {
   std::string name;
   cudaEvent_t a, b;
@@ -26,10 +42,14 @@ void profile_before(const char* name, cudaStream_t stream) {
   if (r.name.size() > 2 && r.name.front() == '(' && r.name.back() == ')') r.name = r.name.substr(1, r.name.size() - 2);  // (k<a, b>) at the launch site
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
+  g_prof_mutex.lock();   // held across the launch so that profile_after finds its own record last
   cudaEventRecord(r.a, stream);
   g_prof.push_back(r);
 }
-void profile_after(cudaStream_t stream) { cudaEventRecord(g_prof.back().b, stream); }
+void profile_after(cudaStream_t stream) {
+  cudaEventRecord(g_prof.back().b, stream);
+  g_prof_mutex.unlock();
+}
 
 // ------------------------------------------------------------------------------------------------
 // Exclusive scan: 3 launches (block sums, scan of block sums, apply).  1024 elements per block.
@@ -164,6 +184,7 @@ const char* apax_last_cuda_error(void) { return cudaGetErrorString(apax::g_last_
 int64_t apax_kernel_launch_count(void) { return apax::g_launch_count.load(); }
 
 int apax_profile_enable(int on) {
+  std::lock_guard<std::mutex> guard(apax::g_prof_mutex);
   for (auto& r : apax::g_prof) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
@@ -174,6 +195,7 @@ int apax_profile_enable(int on) {
 }
 
 int apax_profile_collect(char* names, int name_stride, float* ms, int max_records) {
+  std::lock_guard<std::mutex> guard(apax::g_prof_mutex);
   int n = 0;
   for (auto& r : apax::g_prof) {
     if (n >= max_records) break;

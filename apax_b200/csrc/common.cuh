@@ -61,7 +61,38 @@ void profile_after(cudaStream_t stream);
     APAX_TRY(::apax::check_launch());                                 \
   } while (0)
 
-constexpr int kNumSM = 148;  // B200
+// number of SMs of the current device (queried once per device; 148 on a B200)
+int num_sms();
+
+#ifdef __CUDACC__
+// Bounded cross-GPU spin: waits until *flag has reached `epoch` (wrap-safe), at most kPeerSpinTimeoutNs.  A peer that died,
+// threw on the host or issued a different number of exchanges would otherwise hang this GPU for good; on a time-out the
+// sticky error word `err` (in this rank's own header) is set -- the host surfaces it as APAX_ERR_CUDA (apax_halo_status,
+// apax_train_peers_status) -- and the kernel carries on with whatever data is there (the results of that call are invalid).
+constexpr unsigned long long kPeerSpinTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool peer_spin_until(const uint32_t* flag, uint32_t epoch, uint32_t* err) {
+  auto reached = [&]() {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    return int32_t(v - epoch) >= 0;
+  };
+  if (reached()) return true;
+  const unsigned long long t0 = global_timer_ns();
+  while (!reached()) {
+    __nanosleep(64);
+    if (global_timer_ns() - t0 > kPeerSpinTimeoutNs) {
+      atomicExch(err, 1u);
+      return false;
+    }
+  }
+  return true;
+}
+#endif
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int64_t cdiv(int64_t x, int64_t m) { return (x + m - 1) / m; }

@@ -18,7 +18,7 @@ struct apax_ctx {
   double* frac;      // [N][3]
   double* ref_frac;  // [N][3] positions at the last list build
   int32_t* Z;
-  double* mats;      // cell[9] | box = cell^T [9] | inverse box [9] | identity [9]
+  double* mats;      // cell[9] | box = cell^T [9] | inverse box [9] | identity [9] | 2 x identity [9] | stress out [9]
   int32_t* idx;      // [2][cap] (only when a COO copy is wanted; unused on the fast path)
   double* offsets;   // [cap][3]
   int32_t* counters; // n_found, rebuild flag
@@ -36,12 +36,15 @@ struct apax_ctx {
   int32_t* h_counters;
   uint8_t* h_overflow;
   double* h_out;  // energy[n_out] then forces
+  int32_t* list_Z; // host copy of the atomic numbers the list (and its compact species table) was prepared for
   // state
   int64_t list_atoms;
   int list_minimage;
   double list_cutoff;
   double list_cell[9];
   int64_t n_pairs;
+  int evaluated;     // the workspace holds the per-pair values of a completed energy+forces evaluation (for apax_ctx_stress)
+  double* scratch_ef; // [1 + 3 max_atoms] second evaluation of the offsets-branch stress (allocated on first use)
 };
 
 namespace {
@@ -95,7 +98,7 @@ extern "C" int apax_ctx_create(const apax_gm_params* params, int64_t max_atoms, 
   APAX_CUDA_TRY(cudaMalloc(&c->frac, sizeof(double) * 3 * max_atoms));
   APAX_CUDA_TRY(cudaMalloc(&c->ref_frac, sizeof(double) * 3 * max_atoms));
   APAX_CUDA_TRY(cudaMalloc(&c->Z, sizeof(int32_t) * max_atoms));
-  APAX_CUDA_TRY(cudaMalloc(&c->mats, sizeof(double) * 36));
+  APAX_CUDA_TRY(cudaMalloc(&c->mats, sizeof(double) * 54));
   APAX_CUDA_TRY(cudaMalloc(&c->offsets, sizeof(double) * 3 * max_pairs));
   APAX_CUDA_TRY(cudaMalloc(&c->counters, sizeof(int32_t) * 4));
   APAX_CUDA_TRY(cudaMalloc(&c->overflow, 4));
@@ -107,10 +110,11 @@ extern "C" int apax_ctx_create(const apax_gm_params* params, int64_t max_atoms, 
   APAX_CUDA_TRY(cudaMalloc(&c->nl_ws, c->nl_ws_bytes));
   APAX_CUDA_TRY(cudaMallocHost(&c->h_pos, sizeof(double) * 3 * max_atoms));
   APAX_CUDA_TRY(cudaMallocHost(&c->h_Z, sizeof(int32_t) * max_atoms));
-  APAX_CUDA_TRY(cudaMallocHost(&c->h_mats, sizeof(double) * 36));
+  APAX_CUDA_TRY(cudaMallocHost(&c->h_mats, sizeof(double) * 54));
   APAX_CUDA_TRY(cudaMallocHost(&c->h_counters, sizeof(int32_t) * 4));
   APAX_CUDA_TRY(cudaMallocHost(&c->h_overflow, 4));
   APAX_CUDA_TRY(cudaMallocHost(&c->h_out, sizeof(double) * (n_out + 3 * max_atoms * n_out)));
+  c->list_Z = new int32_t[max_atoms];
   c->list_atoms = -1;
   *out = c;
   return APAX_OK;
@@ -121,10 +125,11 @@ extern "C" void apax_ctx_destroy(apax_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->pos); cudaFree(c->frac); cudaFree(c->ref_frac); cudaFree(c->Z); cudaFree(c->mats);
   cudaFree(c->offsets); cudaFree(c->counters); cudaFree(c->overflow); cudaFree(c->energy); cudaFree(c->forces);
-  cudaFree(c->gm_ws); cudaFree(c->nl_ws);
+  cudaFree(c->gm_ws); cudaFree(c->nl_ws); cudaFree(c->scratch_ef);
   cudaFreeHost(c->h_pos); cudaFreeHost(c->h_Z); cudaFreeHost(c->h_mats); cudaFreeHost(c->h_counters);
   cudaFreeHost(c->h_overflow); cudaFreeHost(c->h_out);
   cudaStreamDestroy(c->stream);
+  delete[] c->list_Z;
   delete c;
 }
 
@@ -137,6 +142,7 @@ extern "C" int apax_ctx_calculate(apax_ctx* c, const double* positions_host, con
   const int n_out = p->cfg.n_out;
   const int64_t N = n_atoms, cap = c->max_pairs;
   cudaStream_t s = c->stream;
+  c->evaluated = 0;
   double det = cell_host[0] * (cell_host[4] * cell_host[8] - cell_host[5] * cell_host[7]) -
                cell_host[1] * (cell_host[3] * cell_host[8] - cell_host[5] * cell_host[6]) +
                cell_host[2] * (cell_host[3] * cell_host[7] - cell_host[4] * cell_host[6]);
@@ -158,10 +164,11 @@ extern "C" int apax_ctx_calculate(apax_ctx* c, const double* positions_host, con
     for (int j = 0; j < 3; ++j) m[9 + 3 * i + j] = cell_host[3 * j + i];  // box = cell.T (ase_calc.py:42-43)
   host_invert3(m + 9, m + 18);
   for (int i = 0; i < 9; ++i) m[27 + i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int i = 0; i < 9; ++i) m[36 + i] = (i % 4 == 0) ? 2.0 : 0.0;
   APAX_CUDA_TRY(cudaMemcpyAsync(c->pos, pos_pinned ? positions_host : c->h_pos, sizeof(double) * 3 * N,
                                 cudaMemcpyHostToDevice, s));
   APAX_CUDA_TRY(cudaMemcpyAsync(c->Z, z_pinned ? numbers_host : c->h_Z, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s));
-  APAX_CUDA_TRY(cudaMemcpyAsync(c->mats, c->h_mats, sizeof(double) * 36, cudaMemcpyHostToDevice, s));
+  APAX_CUDA_TRY(cudaMemcpyAsync(c->mats, c->h_mats, sizeof(double) * 45, cudaMemcpyHostToDevice, s));
   const double* d_cell = c->mats;
   const double* d_box = c->mats + 9;
   const double* d_binv = c->mats + 18;
@@ -176,7 +183,11 @@ extern "C" int apax_ctx_calculate(apax_ctx* c, const double* positions_host, con
   bool same_cell = true;
   for (int i = 0; i < 9; ++i) same_cell = same_cell && c->list_cell[i] == cell_host[i];
   const double cutoff = double(p->cfg.r_max) + (minimage ? dr_threshold : 0.0);
-  bool need = rebuild || c->list_atoms != N || c->list_minimage != int(minimage) || !same_cell ||
+  // The prepared list carries the compact species table (sp_map / embc): a change of atomic numbers at fixed N, cell and
+  // within-skin positions must re-run the preparation, as the reference re-initialises on any change of `numbers`
+  // (apax/md/ase_calc.py:366-370).
+  const bool same_numbers = c->list_atoms == N && memcmp(c->list_Z, numbers_host, sizeof(int32_t) * N) == 0;
+  bool need = rebuild || c->list_atoms != N || c->list_minimage != int(minimage) || !same_cell || !same_numbers ||
               c->list_cutoff != cutoff || !minimage;  // the vesin path recomputes every call (ase_calc.py:386-387)
   if (minimage) APAX_LAUNCH(k_to_frac, dim3((unsigned)cdiv(N, 256)), dim3(256), 0, s, c->pos, d_binv, N, c->frac);
   if (minimage && !need) {
@@ -209,6 +220,7 @@ extern "C" int apax_ctx_calculate(apax_ctx* c, const double* positions_host, con
     }
     APAX_TRY(gm_prepare_from_csr(s, p, gw, c->Z, nw.rowptr_c, nw.nbr, /*symmetric_sorted=*/minimage));
     c->list_atoms = N;
+    memcpy(c->list_Z, numbers_host, sizeof(int32_t) * N);
     c->list_minimage = int(minimage);
     c->list_cutoff = cutoff;
     for (int i = 0; i < 9; ++i) c->list_cell[i] = cell_host[i];
@@ -232,5 +244,43 @@ extern "C" int apax_ctx_calculate(apax_ctx* c, const double* positions_host, con
   memcpy(energy_host, c->h_out, sizeof(double) * n_out);
   if (forces_host && !f_pinned) memcpy(forces_host, c->h_out + n_out, sizeof(double) * 3 * N * n_out);
   if (n_pairs_host) *n_pairs_host = c->n_pairs;
+  c->evaluated = forces_host != nullptr;
+  return APAX_OK;
+}
+
+// The `stress` entry of the calculator's results for the structure of the last apax_ctx_calculate (with forces, n_out == 1):
+// EnergyDerivativeModel(calc_stress=True) (apax/nn/models.py:160-169, stress_times_vol, apax/layers/properties.py:11-42) followed
+// by ProcessStress (apax/md/function_transformations.py:140-159): stress = (dU/d eps)^T / det(box).  On the min-image path the
+// per-pair values of the force pass are reduced; on the image-list (vesin) path the reference's disp_fn differentiates at
+// doubled displacements (apax/layers/distances.py:16-17), which costs a second force pass -- see apax_gm_stress_times_vol_offsets.
+extern "C" int apax_ctx_stress(apax_ctx* c, double* stress_host) {
+  if (!c || !stress_host) return APAX_ERR_INVALID_ARG;
+  const apax_gm_params_impl* p = c->params;
+  if (p->cfg.n_out != 1) return APAX_ERR_UNSUPPORTED;
+  if (!c->evaluated || c->list_atoms < 1) return APAX_ERR_INVALID_ARG;   // nothing evaluated (or no forces were asked for)
+  const int64_t N = c->list_atoms, cap = c->max_pairs;
+  cudaStream_t s = c->stream;
+  double* d_stress = c->mats + 45;
+  const apax_gm_params* pub = reinterpret_cast<const apax_gm_params*>(p);
+  if (c->list_minimage) {
+    APAX_TRY(apax_gm_stress_times_vol(reinterpret_cast<apax_stream_t>(s), pub, N, cap, d_stress, c->gm_ws, c->gm_ws_bytes));
+  } else {
+    if (!c->scratch_ef) APAX_CUDA_TRY(cudaMalloc(&c->scratch_ef, sizeof(double) * (1 + 3 * c->max_atoms)));
+    GmWorkspace gw;
+    carve_gm_workspace(c->gm_ws, N, cap, 1, 128, &gw);
+    // evaluation at dr' = 2 (r_c - r_n) + S.cell, then the virial against the undoubled differences
+    APAX_TRY(gm_compute_device(s, p, gw, c->pos, c->Z, c->mats + 36, c->offsets, APAX_DISP_OFFSETS, c->scratch_ef, c->scratch_ef + 1));
+    APAX_TRY(apax_gm_stress_times_vol_offsets(reinterpret_cast<apax_stream_t>(s), pub, c->pos, c->mats + 27, N, cap, d_stress,
+                                              c->gm_ws, c->gm_ws_bytes));
+    c->evaluated = 0;   // the workspace now holds the doubled evaluation: a further stress call needs a fresh calculate
+  }
+  double st[9];
+  APAX_CUDA_TRY(cudaMemcpyAsync(c->h_mats + 45, d_stress, sizeof(double) * 9, cudaMemcpyDeviceToHost, s));
+  APAX_CUDA_TRY(cudaStreamSynchronize(s));
+  memcpy(st, c->h_mats + 45, sizeof(st));
+  const double* a = c->list_cell;
+  const double vol = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) stress_host[3 * i + j] = st[3 * j + i] / vol;   // val.T / V, V = det(box) = det(cell)
   return APAX_OK;
 }

@@ -1194,18 +1194,9 @@ static int pick_lpa(int64_t n_atoms) {
 
 // Block shape of the pair kernels.  Their ~200-225 live registers allow one 256-thread block per SM (8 warps); under a
 // register cap the compiler parks a dozen accumulators in local memory (L1-resident) and more warps hide the latency of
-// the serial per-pair prelude.  APAX_B200_PAIR_BLOCK (measurement switch) picks the
-// shape: 0 = 256 x 1 (uncapped), 1 = 128 x 3 (168 registers, default), 2 = 128 x 4 (128 registers).  Measured on the
-// 1,000,002-atom box (fwd / bwd ms): 2.96 / 3.01, 2.21 / 2.52, 3.20 / 2.89; 64-thread blocks at 144 registers: 2.88 / 2.94.
-static int pair_block_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("APAX_B200_PAIR_BLOCK");
-    v = e ? atoi(e) : 1;
-    if (v < 0 || v > 2) v = 1;
-  }
-  return v;
-}
+// the serial per-pair prelude.  apax_gm_params_set_option(APAX_OPT_PAIR_BLOCK) picks the shape (a measurement switch, results
+// are bitwise the same): 0 = 256 x 1 (uncapped), 1 = 128 x 3 (168 registers, default), 2 = 128 x 4 (128 registers).  Measured
+// on the 1,000,002-atom box (fwd / bwd ms): 2.96 / 3.01, 2.21 / 2.52, 3.20 / 2.89; 64-thread blocks at 144 registers: 2.88 / 2.94.
 template <int LPA, int BT, int MINB>
 static int launch_pair_fwd_shape(cudaStream_t s, const GmWorkspace& w, const PairGeom& geo, const DescConst& dc) {
   const dim3 grid((unsigned)cdiv(w.n_central * LPA, BT));
@@ -1217,16 +1208,16 @@ static int launch_pair_fwd_shape(cudaStream_t s, const GmWorkspace& w, const Pai
   return APAX_OK;
 }
 template <int LPA>
-static int launch_pair_fwd(cudaStream_t s, const GmWorkspace& w, const PairGeom& geo, const DescConst& dc) {
-  switch (pair_block_variant()) {
+static int launch_pair_fwd(cudaStream_t s, const GmWorkspace& w, const PairGeom& geo, const DescConst& dc, int variant) {
+  switch (variant) {
     case 0: return launch_pair_fwd_shape<LPA, 256, 1>(s, w, geo, dc);
     case 2: return launch_pair_fwd_shape<LPA, 128, 4>(s, w, geo, dc);
     default: return launch_pair_fwd_shape<LPA, 128, 3>(s, w, geo, dc);
   }
 }
 template <int LPA>
-static int launch_pair_bwd(cudaStream_t s, const GmWorkspace& w, const DescConst& dc) {
-  switch (pair_block_variant()) {
+static int launch_pair_bwd(cudaStream_t s, const GmWorkspace& w, const DescConst& dc, int variant) {
+  switch (variant) {
     case 0: APAX_LAUNCH_AS("k_pair_bwd<LPA>", (k_pair_bwd<LPA, 256, 1>), dim3((unsigned)cdiv(w.n_central * LPA, 256)), dim3(256), 0, s, w, dc); break;
     case 2: APAX_LAUNCH_AS("k_pair_bwd<LPA>", (k_pair_bwd<LPA, 128, 4>), dim3((unsigned)cdiv(w.n_central * LPA, 128)), dim3(128), 0, s, w, dc); break;
     default: APAX_LAUNCH_AS("k_pair_bwd<LPA>", (k_pair_bwd<LPA, 128, 3>), dim3((unsigned)cdiv(w.n_central * LPA, 128)), dim3(128), 0, s, w, dc); break;
@@ -1267,7 +1258,7 @@ static int gm_descriptor_impl(cudaStream_t stream, const apax_gm_params_impl* p,
   const DescConst dc = make_desc_const(p->cfg);
   const int lpa = pick_lpa(w.n_central);
   APAX_LAUNCH(k_atom_pack, dim3((unsigned)cdiv(w.n_atoms, 256)), dim3(256), 0, stream, w, geo);
-  APAX_DISPATCH_LPA(lpa, launch_pair_fwd, stream, w, geo, dc);
+  APAX_DISPATCH_LPA(lpa, launch_pair_fwd, stream, w, geo, dc, p->pair_block);
   const dim3 grid_c((unsigned)cdiv(w.n_central, kContractThreads));
   if (feature_mode == 1) {
     APAX_LAUNCH(k_contract_fwd<1>, grid_c, dim3(kContractThreads), 0, stream, w);
@@ -1279,21 +1270,14 @@ static int gm_descriptor_impl(cudaStream_t stream, const apax_gm_params_impl* p,
   return APAX_OK;
 }
 
-// Readout implementation switch (APAX_B200_READOUT).
-//   i8 (default): exact integer tensor-core GEMMs with fused epilogues (i8_gemm.cuh) -- no rounding inside the
+// Readout implementation, a field of the parameter handle (apax_gm_params_set_option(APAX_OPT_READOUT)); nothing is read
+// from the environment.
+//   APAX_READOUT_I8 (default): exact integer tensor-core GEMMs with fused epilogues (i8_gemm.cuh) -- no rounding inside the
 //                 reduction at all, every parity test holds, ~2x faster than the CUDA-core path.
-//   simt:         fp32 CUDA-core GEMMs (the first correct path; kept as the cross-check the i8 tests compare with).
-//   tc:           tcgen05 3xTF32 GEMMs -- ~1e-6 accurate per output but BIASED (the tensor core's fp32 accumulator
+//   APAX_READOUT_SIMT: fp32 CUDA-core GEMMs (the first correct path; kept as the cross-check the i8 tests compare with).
+//   APAX_READOUT_TC:   tcgen05 3xTF32 GEMMs -- ~1e-6 accurate per output but BIASED (the tensor core's fp32 accumulator
 //                 truncates instead of rounding), ~8e-6 relative on total energies: not parity-safe.
-enum { READOUT_SIMT = 0, READOUT_TC = 1, READOUT_I8 = 2 };
-static int readout_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("APAX_B200_READOUT");
-    mode = (e && strcmp(e, "tc") == 0) ? READOUT_TC : (e && strcmp(e, "simt") == 0) ? READOUT_SIMT : READOUT_I8;
-  }
-  return mode;
-}
+enum { READOUT_SIMT = APAX_READOUT_SIMT, READOUT_TC = APAX_READOUT_TC, READOUT_I8 = APAX_READOUT_I8 };
 
 static int energy_sums(cudaStream_t stream, const GmWorkspace& w, int n_out, double* energy, const CorrConst* cc = nullptr,
                        const PairGeom* geo = nullptr) {
@@ -1477,7 +1461,7 @@ static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
   const int n_out = p->cfg.n_out;
   const DescConst dc = make_desc_const(p->cfg);
   const int lpa = pick_lpa(N);
-  const int mode = readout_mode();
+  const int mode = p->readout_mode;
   auto readout = [&](int head) {
     return mode == READOUT_I8   ? readout_i8(stream, p, w, geo, energy, head)
            : mode == READOUT_TC ? readout_tc(stream, p, w, geo, energy, head)
@@ -1497,7 +1481,7 @@ static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
     // every backward pass reads only what the forward pass left behind (D1, D2 / its planes, ebar): nothing to redo
     APAX_TRY(readout(head));
     APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(N, kContractThreads)), dim3(kContractThreads), 0, stream, w);
-    APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc);
+    APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc, p->pair_block);
     if (p->corr.zbl_on || p->corr.exp_on)
       APAX_LAUNCH(k_pair_corrections<1>, dim3((unsigned)cdiv(N * 32, 256)), dim3(256), 0, stream, w, geo, p->corr, n_out);
     APAX_DISPATCH_LPA(pick_lpa(w.n_atoms), launch_force_gather, stream, w, forces + int64_t(head) * w.n_atoms * 3);
@@ -1547,6 +1531,8 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
   if (!emb || !w0 || !b0 || !w1 || !b1 || !w2 || !b2 || !scale || !shift || !out) return APAX_ERR_INVALID_ARG;
   apax_gm_params* p = new apax_gm_params();
   p->cfg = *cfg;
+  p->readout_mode = APAX_READOUT_I8;
+  p->pair_block = 1;
   const int S = cfg->n_species, n_out = cfg->n_out;
   // n_contr < 8 truncates the feature list c0|c1|...|c7 (gaussian_moment_descriptor.py:101): the caller's first dense layer
   // has n_feat rows; the kernels always produce all 360 features, the dropped ones meet zero weight rows (and receive a
@@ -1702,6 +1688,22 @@ extern "C" void apax_gm_params_destroy(apax_gm_params* p) {
   cudaFree(p->q_w0); cudaFree(p->q_w1); cudaFree(p->q_w1th); cudaFree(p->q_w0t);
   cudaFree(p->cs_g); cudaFree(p->cs_h1); cudaFree(p->cs_d2); cudaFree(p->cs_x1);
   delete p;
+}
+
+extern "C" int apax_gm_params_set_option(apax_gm_params* p, int32_t option, int32_t value) {
+  if (!p) return APAX_ERR_INVALID_ARG;
+  switch (option) {
+    case APAX_OPT_READOUT:
+      if (value != APAX_READOUT_I8 && value != APAX_READOUT_SIMT && value != APAX_READOUT_TC) return APAX_ERR_INVALID_ARG;
+      p->readout_mode = value;
+      return APAX_OK;
+    case APAX_OPT_PAIR_BLOCK:
+      if (value < 0 || value > 2) return APAX_ERR_INVALID_ARG;
+      p->pair_block = value;
+      return APAX_OK;
+    default:
+      return APAX_ERR_INVALID_ARG;
+  }
 }
 
 extern "C" int apax_gm_params_status(const apax_gm_params* p) {

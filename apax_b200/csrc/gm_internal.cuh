@@ -28,6 +28,8 @@ struct CorrConst {
 struct apax_gm_params_impl {
   apax_gm_config cfg;
   CorrConst corr;                 // all zero: no corrections
+  int readout_mode;               // APAX_READOUT_* (apax_gm_params_set_option)
+  int pair_block;                 // block shape of the pair kernels, 0..2 (measurement switch)
   // device copies
   float* emb;    // [S][S][5][7], pre-multiplied by 1/sqrt(n_basis) when use_embed_norm
   float* w0;     // [360][256]

@@ -4,7 +4,8 @@
 //
 // Every rank keeps its local position rows R[n_local][3] and force rows F[n_local][3] (owned atoms first, then ghosts
 // grouped by owner rank) in CUDA-IPC memory that its peers have mapped (apax_peer_alloc / apax_peer_open), behind a
-// 256-byte header: u32 fwd_flags[8] | u32 rev_flags[8] | u32 ticket | pad | f64 energy[16] at byte 128.
+// 256-byte header: u32 fwd_flags[8] | u32 rev_flags[8] | u32 ticket | u32 error (sticky: a barrier timed out) | pad |
+// f64 energy[16] at byte 128.
 //
 //   forward  (apax_halo_push_rows)     : pack-and-store -- each boundary atom's position goes straight into the ghost row
 //                                        of the neighbouring rank's R (remote stores); the last block to finish publishes
@@ -24,7 +25,7 @@
 namespace apax {
 namespace {
 
-constexpr int HDR_FWD = 0, HDR_REV = 8, HDR_TICKET = 16;   // u32 slots of the header
+constexpr int HDR_FWD = 0, HDR_REV = 8, HDR_TICKET = 16, HDR_ERR = 17;   // u32 slots of the header
 constexpr int HDR_ENERGY_BYTE = 128;
 
 struct HaloArgs {
@@ -38,14 +39,9 @@ struct HaloArgs {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void wait_flags(const uint32_t* mine, int world, uint32_t epoch) {
-  if (threadIdx.x < world)
-    while (int32_t(ld_acquire_sys(mine + threadIdx.x) - epoch) < 0) __nanosleep(64);
+// every peer's flag in MY header has reached `epoch`, or the wait timed out (error word set, see peer_spin_until)
+__device__ __forceinline__ void wait_flags(uint32_t* my_hdr, int first_slot, int world, uint32_t epoch) {
+  if (threadIdx.x < world) peer_spin_until(my_hdr + first_slot + threadIdx.x, epoch, my_hdr + HDR_ERR);
   __syncthreads();
 }
 
@@ -74,7 +70,7 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloArgs h, const double* __r
     __threadfence_system();
     st_release_sys(h.hdr[threadIdx.x] + HDR_FWD + h.rank, h.epoch);
   }
-  wait_flags(h.hdr[h.rank] + HDR_FWD, h.world, h.epoch);
+  wait_flags(h.hdr[h.rank], HDR_FWD, h.world, h.epoch);
 }
 
 // phase 0: publish + wait (all blocks), then pull from rank `src` only; later launches (phase 1) just pull from their rank.
@@ -85,7 +81,7 @@ __global__ void __launch_bounds__(256) k_halo_pull(HaloArgs h, double* __restric
       __threadfence_system();
       st_release_sys(h.hdr[threadIdx.x] + HDR_REV + h.rank, h.epoch);
     }
-    wait_flags(h.hdr[h.rank] + HDR_REV, h.world, h.epoch);
+    wait_flags(h.hdr[h.rank], HDR_REV, h.world, h.epoch);
     if (blockIdx.x == 0 && threadIdx.x < n_out) {   // energy: sum of the ranks' partial energies in rank order
       double e = 0.0;
       for (int r = 0; r < h.world; ++r)
@@ -134,7 +130,7 @@ extern "C" int apax_halo_push_rows(apax_stream_t stream_, const double* local_ro
   APAX_TRY(fill(h, peers, send_ptr_host, epoch));
   const int64_t n_send = h.send_ptr[h.world];
   if (n_send > 0 && !send_local) return APAX_ERR_INVALID_ARG;
-  const int64_t blocks = std::min<int64_t>(std::max<int64_t>(cdiv(n_send, 256), 1), 4 * kNumSM);
+  const int64_t blocks = std::min<int64_t>(std::max<int64_t>(cdiv(n_send, 256), 1), 4 * int64_t(num_sms()));
   APAX_LAUNCH(k_halo_push, dim3((unsigned)blocks), dim3(256), 0, s, h, local_rows, send_local);
   return APAX_OK;
 }
@@ -151,10 +147,18 @@ extern "C" int apax_halo_pull_add_rows(apax_stream_t stream_, double* local_rows
   for (int r = 0; r < h.world; ++r) {   // one launch per source rank, in rank order: contributions to one atom never race
     const int64_t cnt = h.send_ptr[r + 1] - h.send_ptr[r];
     if (cnt == 0) continue;
-    const int64_t blocks = std::min<int64_t>(cdiv(cnt, 256), 4 * kNumSM);
+    const int64_t blocks = std::min<int64_t>(cdiv(cnt, 256), 4 * int64_t(num_sms()));
     APAX_LAUNCH(k_halo_pull, dim3((unsigned)blocks), dim3(256), 0, s, h, local_rows, send_local, r, phase, n_out, energy_global);
     phase = 1;
   }
   if (phase == 0) APAX_LAUNCH(k_halo_pull, dim3(1), dim3(256), 0, s, h, local_rows, send_local, -1, 0, n_out, energy_global);
   return APAX_OK;
+}
+
+extern "C" int apax_halo_status(const apax_halo_peers* peers) {
+  // synchronising query of this rank's sticky barrier-time-out word (0 = healthy)
+  if (!peers || peers->rank < 0 || peers->rank >= 8 || !peers->header[peers->rank]) return APAX_ERR_INVALID_ARG;
+  uint32_t err = 0;
+  APAX_CUDA_TRY(cudaMemcpy(&err, peers->header[peers->rank] + HDR_ERR, sizeof(err), cudaMemcpyDeviceToHost));
+  return err == 0 ? APAX_OK : APAX_ERR_CUDA;
 }

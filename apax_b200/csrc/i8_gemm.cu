@@ -750,6 +750,9 @@ void i8_quantize_weights(const float* W, int K, int NC, int ldw, int kp, int ncp
   for (int k = K; k < kp; ++k) col_scale[k] = 1.0f;
 }
 
+// measurement switches of tools/trace_i8.py (apax_i8_set_debug); both 0 in normal operation
+static std::atomic<int> g_i8_dbg_flags{0}, g_i8_trace{0};
+
 int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const I8Epilogue& epi_in, int32_t* err_flag) {
   const I8Epilogue& epi0 = epi_in;
   (void)epi0;
@@ -763,8 +766,8 @@ int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const
     APAX_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   I8Epilogue epi = epi_in;
-  if (const char* f = getenv("APAX_I8_DBG")) epi.dbg_flags = atoi(f);
-  static const bool trace = getenv("APAX_I8_TRACE") != nullptr;   // measurement only: per-launch cycle counters to stderr
+  if (g_i8_dbg_flags.load(std::memory_order_relaxed)) epi.dbg_flags = g_i8_dbg_flags.load(std::memory_order_relaxed);
+  const bool trace = g_i8_trace.load(std::memory_order_relaxed) != 0;   // measurement only (apax_i8_set_debug): per-launch cycle counters to stderr
   static long long* trace_buf = nullptr;
   if (trace) {
     if (!trace_buf) APAX_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&trace_buf), 256 * 8 * sizeof(long long)));
@@ -826,6 +829,12 @@ int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const
 
 // Test / measurement entry: out[nc][ld] = act^T . wgt through the integer tensor-core path (plain store
 // epilogue).  act: device fp32 [k][ld]; wgt: device fp32 [k][nc].  Allocates its own scratch (test only).
+extern "C" int apax_i8_set_debug(int32_t dbg_flags, int32_t trace) {
+  apax::g_i8_dbg_flags.store(dbg_flags);
+  apax::g_i8_trace.store(trace);
+  return APAX_OK;
+}
+
 extern "C" int apax_i8_gemm_test(apax_stream_t stream_, const float* act, int64_t k, int64_t ld, int64_t n_atoms,
                                  const float* wgt, int64_t nc, float* out, int32_t* err_flag, int64_t* dbg,
                                  int32_t act_planes) {

@@ -1148,10 +1148,8 @@ __global__ void __launch_bounds__(256) k_tr_adam_peer(AdamArgs a, PeerArgs pa, f
     __threadfence_system();
     st_release_sys(pa.flags[threadIdx.x] + pa.rank, pa.epoch);
   }
-  if (threadIdx.x < pa.world) {
-    const uint32_t* mine = pa.flags[pa.rank] + threadIdx.x;
-    while (int32_t(ld_acquire_sys(mine) - pa.epoch) < 0) __nanosleep(64);
-  }
+  if (threadIdx.x < pa.world)   // bounded: a time-out sets the sticky error word behind the eight flags (apax_train_peers_status)
+    peer_spin_until(pa.flags[pa.rank] + threadIdx.x, pa.epoch, pa.flags[pa.rank] + 8);
   __syncthreads();
   const AdamScalars sc = *reinterpret_cast<const AdamScalars*>(opt_state + 1);
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -1485,4 +1483,12 @@ extern "C" int apax_train_allreduce_adam_step(apax_stream_t stream_, const apax_
               reinterpret_cast<float4*>(theta32), reinterpret_cast<float4*>(m32), reinterpret_cast<float4*>(v32), theta64, m64,
               v64, opt_state, loss_out);
   return APAX_OK;
+}
+
+extern "C" int apax_train_peers_status(const apax_train_peers* peers) {
+  // synchronising query of this rank's sticky barrier-time-out word (0 = healthy)
+  if (!peers || peers->rank < 0 || peers->rank >= 8 || !peers->flags[peers->rank]) return APAX_ERR_INVALID_ARG;
+  uint32_t err = 0;
+  APAX_CUDA_TRY(cudaMemcpy(&err, peers->flags[peers->rank] + 8, sizeof(err), cudaMemcpyDeviceToHost));
+  return err == 0 ? APAX_OK : APAX_ERR_CUDA;
 }

@@ -23,7 +23,7 @@ class Atoms:
 
 
 class ASECalculator:
-    implemented_properties = ["energy", "forces"]
+    implemented_properties = ["energy", "forces"]   # + "stress" when the model config sets calc_stress (ase_calc.py:180-181)
 
     def __init__(self, params: dict, model_config: Optional[dict] = None, dr_threshold: float = 0.5,
                  padding_factor: float = 1.5, max_pairs_per_atom: int = 160):
@@ -36,6 +36,8 @@ class ASECalculator:
         self.max_pairs_per_atom = max_pairs_per_atom
         self.ctx: Optional[rt.HostContext] = None
         self.results: dict = {}
+        self.numbers: Optional[np.ndarray] = None
+        self.implemented_properties = ["energy", "forces"] + (["stress"] if self.builder.config.get("calc_stress") else [])
 
     def _cell(self, atoms) -> np.ndarray:
         cell = atoms.cell
@@ -51,9 +53,11 @@ class ASECalculator:
             self.ctx.close()
         self.ctx = rt.HostContext(self.dp, n, self.max_pairs)
         self.n_atoms = n
+        self.numbers = np.array(atoms.numbers, dtype=np.int32)
 
     def calculate(self, atoms, properties=("energy",), system_changes=None):
-        if self.ctx is None or len(atoms.numbers) != self.n_atoms:
+        # re-initialise on ANY change of the atomic numbers, not only of their count (ase_calc.py:366-370)
+        if self.ctx is None or len(atoms.numbers) != self.n_atoms or not np.array_equal(self.numbers, atoms.numbers):
             self.initialize(atoms)
         cell = self._cell(atoms)
         try:
@@ -66,6 +70,8 @@ class ASECalculator:
             e, f = self.ctx.calculate(atoms.positions, atoms.numbers, cell, dr_threshold=self.dr_threshold)
         if self.dp.n_out == 1:
             self.results = {"energy": float(e[0]), "forces": f[0]}
+            if "stress" in self.implemented_properties:      # ProcessStress (function_transformations.py:140-159)
+                self.results["stress"] = self.ctx.stress()
         else:
             n_ens = self.dp.n_out
             fm = f.mean(axis=0)

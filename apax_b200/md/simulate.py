@@ -34,12 +34,17 @@ def create_energy_fn(model: EnergyModel, params, numbers, n_models: int = 1, sha
 
 def run_nvt(params, atoms, model_config=None, *, dt: float, kT: float, n_steps: int, dr_threshold: float = 0.5,
             rebuild_every: int | None = None, masses=None, momentum=None, seed: int = 0, chain_length: int = 5,
-            chain_steps: int = 2, sy_steps: int = 3, tau=None, on_step=None):
+            chain_steps: int = 2, sy_steps: int = 3, tau=None, on_step=None, strict_skin: bool = True):
     """The MD driver of apax/md/simulate.py (md_setup :440-561 + run_sim :218-437) for the NVT Nose-Hoover
     ensemble, with everything inside the step loop on the GPU: fractional positions, min-image list with skin
     (rebuilt on the reference's skin criterion, partition.py:771-779, or every `rebuild_every` steps as
     BASELINE config 3 words it), GMNN energy+forces, integrator.  Units are the caller's (ASE: eV, A, amu =>
-    time in A sqrt(amu/eV)).  Returns the final NVTNoseHooverState and a dict of counters."""
+    time in A sqrt(amu/eV)).  Returns the final NVTNoseHooverState and a dict of counters.
+
+    With a fixed cadence the list is not consulted between rebuilds, so after every chunk the reference's skin criterion
+    (any atom moved more than dr_threshold / 2 since the list was built, partition.py:771-779) is evaluated on the device;
+    chunks that violated it are counted in counters["skin_violations"] and, with `strict_skin`, raise at the end of the
+    run -- neighbours may have been missed and the trajectory is then not the reference's."""
     import numpy as np
 
     from ..nn.builder import GMNNBuilder
@@ -98,6 +103,7 @@ def run_nvt(params, atoms, model_config=None, *, dt: float, kT: float, n_steps: 
         import ctypes as C
 
         e_dev = torch.zeros(1, dtype=torch.float64, device=state.position.device)
+        violations = torch.zeros(1, dtype=torch.int32, device=state.position.device)
         done = 0
         while done < n_steps:
             if done > 0 and done % rebuild_every == 0:
@@ -110,7 +116,14 @@ def run_nvt(params, atoms, model_config=None, *, dt: float, kT: float, n_steps: 
                                               rt._ptr(box_d), ps.n_atoms, ps.n_pairs, rt._ptr(state.chain), rt._ptr(e_dev), ps.wp,
                                               ps.wb, int(k)), "apax_md_nvt_run")
             done += k
+            # skin criterion against the positions the current list was built from (no host synchronisation here)
+            violations += rt.nl_needs_rebuild(state.position, system["nbrs"].reference_position, box_d, dr_threshold)
         counters["steps"] = n_steps
+        counters["skin_violations"] = int(violations.item())
+        if strict_skin and counters["skin_violations"]:
+            raise rt._lib.ApaxB200Error(rt._lib.ERR_OVERFLOW, "run_nvt",
+                                        f"{counters['skin_violations']} chunk(s) of {rebuild_every} steps moved an atom further than "
+                                        f"dr_threshold/2 = {dr_threshold / 2}: lower rebuild_every or use the skin criterion")
         return state, counters
     for _ in range(n_steps):
         counters["steps"] += 1

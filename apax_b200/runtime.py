@@ -123,6 +123,13 @@ class DeviceParams:
         check(lib().apax_gm_params_create(C.byref(c), hp(emb), hp(w[0]), hp(b[0]), hp(w[1]), hp(b[1]), hp(w[2]), hp(b[2]),
                                           hp(scale), hp(shift), C.byref(handle)), "apax_gm_params_create")
         self.handle = handle
+        # implementation switches live in the handle (apax_gm_params_set_option), never in the environment
+        if cfg.get("readout") is not None:
+            check(lib().apax_gm_params_set_option(handle, _lib.OPT_READOUT, _lib.READOUT_KINDS[str(cfg["readout"])]),
+                  "apax_gm_params_set_option(readout)")
+        if cfg.get("pair_block") is not None:
+            check(lib().apax_gm_params_set_option(handle, _lib.OPT_PAIR_BLOCK, int(cfg["pair_block"])),
+                  "apax_gm_params_set_option(pair_block)")
         if corr is not None:
             check(lib().apax_gm_params_set_corrections(handle, C.byref(corr)), "apax_gm_params_set_corrections")
 
@@ -394,6 +401,13 @@ class HostContext:
         self.n_pairs = npairs.value
         check(code, "apax_ctx_calculate")
         return e, f
+
+    def stress(self) -> np.ndarray:
+        """`stress` of the structure evaluated by the last calculate(forces=True): ProcessStress applied to
+        stress_times_vol (apax/md/function_transformations.py:140-159), [3,3] f64."""
+        st = np.empty((3, 3), dtype=np.float64)
+        check(lib().apax_ctx_stress(self.handle, st.ctypes.data_as(C.c_void_p)), "apax_ctx_stress")
+        return st
 
     def close(self):
         if self.handle is not None and self.handle.value:

@@ -88,6 +88,16 @@ void apax_gm_params_destroy(apax_gm_params* p);
  * while these parameters were in use (results of that call are then invalid). */
 int apax_gm_params_status(const apax_gm_params* p);
 
+/* Implementation switches of a parameter handle (never read from the environment; the numerics path of a process is what
+ * its host code set here).  APAX_OPT_READOUT: which kernels run the per-element MLP (apax/layers/readout.py:22-50) --
+ * APAX_READOUT_I8 (default) exact integer tensor-core GEMMs, APAX_READOUT_SIMT fp32 CUDA-core GEMMs (cross-check),
+ * APAX_READOUT_TC tcgen05 3xTF32 (biased accumulation, NOT parity-safe; measurement only).  APAX_OPT_PAIR_BLOCK: block shape
+ * of the pair kernels, 0..2 (results are bitwise identical; measurement only).  Not to be called while an evaluation with
+ * these parameters is being enqueued from another thread. */
+typedef enum { APAX_OPT_READOUT = 0, APAX_OPT_PAIR_BLOCK = 1 } apax_gm_option;
+typedef enum { APAX_READOUT_SIMT = 0, APAX_READOUT_TC = 1, APAX_READOUT_I8 = 2 } apax_readout_kind;
+int apax_gm_params_set_option(apax_gm_params* p, int32_t option, int32_t value);
+
 /* Pairwise empirical corrections added to the model energy (EnergyModel.corrections, apax/nn/models.py:127-130), with
  * the parameters as they sit in the Flax tree (raw, i.e. before softplus / abs):
  *   ZBLRepulsion        (apax/layers/empirical.py:25-86):  coefficients f32 [4], rep_scale, r_max
@@ -336,7 +346,8 @@ int apax_train_adam_step(apax_stream_t stream, const apax_train_plan* plan, cons
  * Replaces the gradient all-reduce XLA inserts for the sharded batch (apax/train/trainer.py:101-106) plus
  * state.apply_gradients (:335).  Every rank allocates its gradient blocks with apax_peer_alloc, publishes the 64-byte IPC
  * handle to its peers (any host channel), and maps theirs with apax_peer_open.  grad32[r] / grad64[r] / flags[r] are rank
- * r's fp32 block, fp64 block (scale, shift gradients and, behind them, the step's loss) and flag array (u32 [8], zeroed)
+ * r's fp32 block, fp64 block (scale, shift gradients and, behind them, the step's loss) and flag array (u32 [16], zeroed:
+ * eight epoch flags, then a sticky error word)
  * AS MAPPED IN THIS PROCESS.  `epoch` must increase by one per step on every rank, and consecutive steps must use two
  * alternating sets of gradient blocks (the kernel of step t+1 may start while a peer still reads step t's block).
  * The gradients are summed in rank order, so all replicas stay bitwise identical; loss_out f64 [1] receives the global loss. */
@@ -353,6 +364,10 @@ int apax_peer_free(void* dev_ptr);
 int apax_train_allreduce_adam_step(apax_stream_t stream, const apax_train_plan* plan, const apax_train_opt_config* opt_cfg,
                                    const apax_train_peers* peers, uint32_t epoch, float* theta32, double* theta64, float* m32,
                                    float* v32, double* m64, double* v64, int64_t* opt_state, double* loss_out);
+/* The cross-GPU waits inside the peer-memory kernels are bounded (30 s): a peer that died, raised on the host or issued a
+ * different number of steps cannot hang this GPU.  A time-out sets a sticky word in this rank's own flag block and the
+ * results of that step are invalid; this synchronising query returns APAX_ERR_CUDA once that has happened, else 0. */
+int apax_train_peers_status(const apax_train_peers* peers);
 
 /* Halo exchange of the slab-decomposed evaluation (apax_gm_compute_partial) as kernels over NVLink peer memory; no
  * counterpart in the reference, which is single-device (apax/md/simulate.py:313-354).  Every rank keeps, in one
@@ -377,6 +392,8 @@ int apax_halo_push_rows(apax_stream_t stream, const double* local_rows, const in
 int apax_halo_pull_add_rows(apax_stream_t stream, double* local_rows, const int64_t* send_local,
                             const int64_t* send_ptr_host, const apax_halo_peers* peers, uint32_t epoch,
                             const double* energy_local, double* energy_global, int32_t n_out);
+/* Synchronising health query (see apax_train_peers_status): APAX_ERR_CUDA once one of this rank's halo barriers timed out. */
+int apax_halo_status(const apax_halo_peers* peers);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer convenience context: what ASECalculator.calculate does per call
@@ -395,6 +412,13 @@ void apax_ctx_destroy(apax_ctx* ctx);
 int apax_ctx_calculate(apax_ctx* ctx, const double* positions_host, const int32_t* numbers_host,
                        const double* cell_host, int64_t n_atoms, double dr_threshold, int32_t rebuild,
                        double* energy_host, double* forces_host, int64_t* n_pairs_host);
+/* The `stress` entry of the calculator's results for the structure of the LAST apax_ctx_calculate (which must have asked for
+ * forces; n_out == 1): EnergyDerivativeModel with calc_stress (apax/nn/models.py:160-169 -> stress_times_vol,
+ * apax/layers/properties.py:11-42) followed by ProcessStress (apax/md/function_transformations.py:140-159),
+ * stress = (dU/d eps)^T / det(box).  stress_host f64 [3][3].  On the image-list path the reference differentiates at doubled
+ * displacements (apax/layers/distances.py:16-17), which costs a second force pass; a further stress call then needs a new
+ * apax_ctx_calculate first (APAX_ERR_INVALID_ARG otherwise). */
+int apax_ctx_stress(apax_ctx* ctx, double* stress_host);
 
 /* Test entry of the exact integer tensor-core readout GEMM (tcgen05.mma kind::i8, four base-256 digit planes per
  * operand, int32 accumulators): out[nc][ld] = act^T . wgt with act a device fp32 [k][ld] feature-major matrix and
@@ -403,6 +427,10 @@ int apax_ctx_calculate(apax_ctx* ctx, const double* positions_host, const int32_
 int apax_i8_gemm_test(apax_stream_t stream, const float* act, int64_t k, int64_t ld, int64_t n_atoms, const float* wgt,
                       int64_t nc, float* out, int32_t* err_flag, int64_t* dbg_cycles /* nullable, [n_sm][8] */,
                       int32_t act_planes /* 3 or 4 digit planes for the activations */);
+
+/* Measurement only (tools/trace_i8.py): dbg_flags != 0 overrides the kernels' debug switches (skip phases), trace != 0
+ * makes every readout GEMM print its per-role cycle counters to stderr (synchronising).  Both 0 in normal operation. */
+int apax_i8_set_debug(int32_t dbg_flags, int32_t trace);
 
 /* Measurement only: tcgen05.mma kind::i8 issue rate (M = 128, N = n; `iters` rounds of ten MMAs; pattern 0 / 1 / 2:
  * one accumulator / four accumulators / the readout GEMM's digit-pair schedule; negative: none) and tensor-memory
@@ -426,7 +454,8 @@ int64_t apax_kernel_launch_count(void);
 /* Per-launch device timing for measurement: while enabled, every kernel of this library is
  * bracketed by CUDA events on its launching stream.  apax_profile_collect waits for them and writes
  * up to max_records (kernel name, milliseconds) pairs in launch order; returns the count (>= 0).
- * apax_profile_enable(0/1) also clears the record list.  Not thread-safe; off by default. */
+ * apax_profile_enable(0/1) also clears the record list.  A measurement aid behind one process-wide switch (guarded by a
+ * mutex); off by default, and the only mutable global state of the library besides the launch counter. */
 int apax_profile_enable(int on);
 int apax_profile_collect(char* names_host, int name_stride, float* ms_host, int max_records);
 
