@@ -92,6 +92,7 @@ SIGNATURES = {
     "apax_gm_compute": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, C.c_size_t]),
     "apax_gm_compute_partial": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, C.c_size_t]),
     "apax_gm_energy_forces_batched": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, C.c_size_t]),
+    "apax_gm_atomic_energies": (C.c_int, [_P, _P, _I64, _I64, _P, _P, C.c_size_t]),
     "apax_gm_stress_times_vol": (C.c_int, [_P, _P, _I64, _I64, _P, _P, C.c_size_t]),
     "apax_gm_stress_times_vol_offsets": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, C.c_size_t]),
     "apax_gm_descriptor": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, C.c_size_t]),

@@ -1804,6 +1804,17 @@ extern "C" int apax_gm_descriptor(apax_stream_t stream, const apax_gm_params* pa
   return APAX_OK;
 }
 
+extern "C" int apax_gm_atomic_energies(apax_stream_t stream, const apax_gm_params* params, int64_t n_atoms, int64_t n_pairs,
+                                       double* e_atoms, void* workspace, size_t workspace_bytes) {
+  if (!params || !e_atoms || !workspace) return APAX_ERR_INVALID_ARG;
+  GmWorkspace w;
+  APAX_TRY(get_ws(params, n_atoms, n_pairs, workspace, workspace_bytes, &w));
+  // Eatom is [n_out][ld] (ld = n_atoms rounded up to 128): a strided copy to the caller's dense [n_out][n_atoms]
+  APAX_CUDA_TRY(cudaMemcpy2DAsync(e_atoms, sizeof(double) * n_atoms, w.Eatom, sizeof(double) * w.ld, sizeof(double) * n_atoms,
+                                  size_t(params->cfg.n_out), cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  return APAX_OK;
+}
+
 extern "C" int apax_gm_stress_times_vol(apax_stream_t stream, const apax_gm_params* params, int64_t n_atoms, int64_t n_pairs,
                                         double* stress, void* workspace, size_t workspace_bytes) {
   if (!params || !stress || !workspace) return APAX_ERR_INVALID_ARG;

@@ -248,6 +248,13 @@ class PreparedSystem:
                                         _ptr(self.forces if forces else None), self.wp, self.wb), "apax_gm_compute")
         return self.energy, (self.forces if forces else None)
 
+    def atomic_energies(self) -> torch.Tensor:
+        """Per-atom energies E_i [n_out, n_atoms] f64 of the last compute() (models.py:109-122, before fp64_sum)."""
+        out = torch.empty((self.params.n_out, self.n_atoms), dtype=torch.float64, device=self.Z.device)
+        check(lib().apax_gm_atomic_energies(_stream_ptr(), self.params.handle, self.n_atoms, self.n_pairs, _ptr(out), self.wp,
+                                            self.wb), "apax_gm_atomic_energies")
+        return out
+
 
 def descriptor(params: DeviceParams, R, Z, idx, box=None, offsets=None, mode: str = "gas",
                workspace: Optional[Workspace] = None) -> torch.Tensor:

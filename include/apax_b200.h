@@ -147,6 +147,13 @@ int apax_gm_compute(apax_stream_t stream, const apax_gm_params* params, const do
                     int64_t n_pairs, int32_t disp_mode, double* energy, double* forces,
                     void* workspace, size_t workspace_bytes);
 
+/* Per-atom energies E_i of the last apax_gm_compute / apax_gm_energy_forces on this workspace: what EnergyModel.__call__
+ * sums at apax/nn/models.py:109-122 (scale/shift and atom mask applied, empirical corrections included), i.e. the
+ * reference's atomic energies before fp64_sum.  e_atoms f64 [n_out][n_atoms], device.  With apax_gm_compute_partial the
+ * entries of ghost atoms are unspecified. */
+int apax_gm_atomic_energies(apax_stream_t stream, const apax_gm_params* params, int64_t n_atoms, int64_t n_pairs,
+                            double* e_atoms, void* workspace, size_t workspace_bytes);
+
 /* Stress times volume, dU/d(eps) at eps = 0.  Replaces stress_times_vol (apax/layers/properties.py:11-42) as called by
  * EnergyDerivativeModel with calc_stress (apax/nn/models.py:160-169) for the MINIMAGE displacement, where the reference
  * applies the strain as dr' = (I + eps) . dr (apax/utils/jax_md_reduced/space.py:277-278):

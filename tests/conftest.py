@@ -32,34 +32,104 @@ def max_force_violation(f, f_ref, rel=1e-5, abs_=1e-6):
     return float(np.max(np.abs(f - f_ref) / (rel * np.abs(f_ref) + abs_)))
 
 
-def assert_force_parity(f, f_ref32, f_ref64=None, n_atoms=None, where="", ulp_floor=0.0):
-    """Force parity against the reference-precision (fp32) result `f_ref32`.
+_PARITY_REPORT = {}
 
-    north_star's tolerance is 1e-5 relative + 1e-6 eV/A absolute, element-wise.  Two independent fp32
-    evaluations of this model cannot meet that bound at the element-wise MAX: the reference's own source
-    (golden fixtures) sits at 1.4x of it against the all-fp64 oracle on the 36-atom fixture, the fp32 oracle at
-    0.75x (96 atoms) ... 1.7x (DESIGN.md "Numerics").  The criterion is therefore "inside the tolerance, or no
-    further from the reference than the reference is from the truth":
-      (a) worst element vs f_ref32 <= max(1, 1.5 * worst element of f_ref32 vs f_ref64)
-          (two independent evaluations with the same noise differ by sqrt(2) of it);
-      (b) >= 99 % of the elements inside the literal tolerance (or, if the reference itself has fewer than that
-          inside it against the fp64 truth, at most 2 % fewer than the reference);
-      (c) the CUDA path's own error against the fp64 truth (max and rms) <= 1.25x the reference's.
-    Without f_ref64 only the literal tolerance (a with bound 1) and (b) apply.
+
+def record_parity(where: str, **values):
+    """Measured margins of a parity test, stored per test: written to gpurun_out/force_parity_report.json at the end of the
+    session (the committed copy of a full GPU run lives under profiles/)."""
+    _PARITY_REPORT[where] = {k: (float(v) if isinstance(v, (int, float, np.floating, np.integer)) else v) for k, v in values.items()}
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _PARITY_REPORT:
+        return
+    import json
+
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    path = os.path.join(out_dir, "force_parity_report.json")
+    data = {}
+    if os.path.exists(path):
+        try:
+            with open(path) as fh:
+                data = json.load(fh)
+        except Exception:
+            data = {}
+    data.update(_PARITY_REPORT)
+    with open(path, "w") as fh:
+        json.dump(data, fh, indent=1, sort_keys=True)
+
+
+def assert_force_parity(f, f_ref32, f_ref64=None, n_atoms=None, where="", ulp_floor=0.0, literal=None):
+    """Force parity against the reference-precision (fp32) result `f_ref32`; every call records its margins.
+
+    north_star's tolerance is 1e-5 relative + 1e-6 eV/A absolute, element-wise.  What is measured and stored per test
+    (units of that tolerance, worst element): kernel vs f_ref32, and -- with the all-fp64 oracle `f_ref64` -- kernel vs fp64
+    and f_ref32 vs fp64, plus the rms errors.  What is asserted:
+
+      literal (`literal=True`, and automatically whenever the reference-precision result itself sits within HALF the
+      tolerance of the fp64 truth, i.e. its own rounding noise leaves room): worst element vs f_ref32 <= 1.0 AND, when
+      f_ref64 is given, worst element of the kernel vs the fp64 truth <= 1.0.
+      otherwise (systems of ~1000 atoms and more: the fp32 rounding noise of ANY reference-precision evaluation of this
+      model exceeds the tolerance at the worst of thousands of elements -- the reference's own source is 1.4x away from
+      the fp64 truth on the 36-atom golden fixture, the fp32 oracle 1.2-1.5x at 1536 atoms; tools/study_force_precision.py
+      shows the noise comes from every fp32 stage, not one; DESIGN.md "Numerics"):
+        (a) worst element vs f_ref32 <= max(1, 1.5 x the reference's own worst element vs fp64)
+            (two independent evaluations with equal noise differ by sqrt(2) of it);
+        (b) >= 99 % of the elements inside the literal tolerance (or at most 2 % fewer than the reference has vs fp64);
+        (c) the kernel is no further from the fp64 truth than the reference-precision evaluation: rms error <= 1.1 x the
+            reference's, worst element (in units of the tolerance) <= max(1, 1.25 x the reference's).
+    Without f_ref64 the literal tolerance applies.
     """
-    viol = np.abs(f - f_ref32) / (1e-5 * np.abs(f_ref32) + 1e-6)
-    bound, frac_bound = 1.0, 0.99
-    if f_ref64 is not None:
-        ref_noise = np.abs(f_ref32 - f_ref64) / (1e-5 * np.abs(f_ref64) + 1e-6)
-        bound = max(1.0, 1.5 * float(ref_noise.max()))
-        frac_bound = min(0.99, float(np.mean(ref_noise <= 1.0)) - 0.02)
-    assert viol.max() <= bound, f"{where}: worst element at {viol.max():.3f}x tolerance (bound {bound:.3f})"
+    tol32 = 1e-5 * np.abs(f_ref32) + 1e-6
+    viol = np.abs(f - f_ref32) / tol32
+    k32 = float(viol.max())
+    rec = {"n_elements": int(np.size(f)), "kernel_vs_ref32_x_tol": k32, "frac_within_tol_vs_ref32": float(np.mean(viol <= 1.0))}
+    if f_ref64 is None:
+        record_parity(where, **rec, criterion="literal")
+        assert k32 <= 1.0, f"{where}: worst element at {k32:.3f}x tolerance (literal)"
+        return rec
+    tol64 = 1e-5 * np.abs(f_ref64) + 1e-6
+    err_k, err_o = np.abs(f - f_ref64), np.abs(f_ref32 - f_ref64)
+    k64, o64 = float((err_k / tol64).max()), float((err_o / tol64).max())
+    rms_k, rms_o = float(np.sqrt((err_k ** 2).mean())), float(np.sqrt((err_o ** 2).mean()))
+    if literal is None:
+        literal = o64 <= 0.5
+    rec.update(kernel_vs_fp64_x_tol=k64, ref32_vs_fp64_x_tol=o64, kernel_rms_err=rms_k, ref32_rms_err=rms_o,
+               frac_within_tol_vs_fp64=float(np.mean(err_k / tol64 <= 1.0)), criterion="literal" if literal else "relative")
+    record_parity(where, **rec)
+    print(f"[parity] {where}: kernel-vs-ref32 {k32:.3f}  kernel-vs-fp64 {k64:.3f}  ref32-vs-fp64 {o64:.3f} (x tolerance); "
+          f"rms err kernel {rms_k:.2e} ref32 {rms_o:.2e}")
+    if literal:
+        assert k32 <= 1.0, f"{where}: worst element vs reference precision at {k32:.3f}x tolerance (literal)"
+        assert k64 <= 1.0, f"{where}: worst element vs fp64 at {k64:.3f}x tolerance (literal)"
+        return rec
+    bound = max(1.0, 1.5 * o64)
+    frac_bound = min(0.99, float(np.mean(err_o / tol64 <= 1.0)) - 0.02)
+    assert k32 <= bound, f"{where}: worst element at {k32:.3f}x tolerance (bound {bound:.3f})"
     assert np.mean(viol <= 1.0) >= frac_bound, f"{where}: {np.mean(viol <= 1.0):.4f} of elements within tolerance (bound {frac_bound:.4f})"
-    if f_ref64 is not None:
-        err_k, err_o = np.abs(f - f_ref64), np.abs(f_ref32 - f_ref64)
-        # ulp_floor > 0: forces so large (steep pair repulsion) that the reference's own error is about one fp32 ulp of
-        # them -- a ratio of two one-ulp errors carries no information, so the bound never drops below ulp_floor ulps
-        floor = ulp_floor * float(np.finfo(np.float32).eps) * float(np.abs(f_ref64).max())
-        assert err_k.max() <= max(1.25 * err_o.max() + 1e-7, floor), f"{where}: max err {err_k.max():.2e} vs reference {err_o.max():.2e}"
-        rms_k, rms_o = np.sqrt((err_k ** 2).mean()), np.sqrt((err_o ** 2).mean())
-        assert rms_k <= max(1.25 * rms_o + 1e-8, 0.5 * floor), f"{where}: rms err {rms_k:.2e} vs reference {rms_o:.2e}"
+    # ulp_floor > 0: forces so large (steep pair repulsion) that the reference's own error is about one fp32 ulp of
+    # them -- a ratio of two one-ulp errors carries no information, so the bound never drops below ulp_floor ulps
+    floor = ulp_floor * float(np.finfo(np.float32).eps) * float(np.abs(f_ref64).max())
+    assert k64 <= max(1.0, 1.25 * o64) or err_k.max() <= floor, f"{where}: kernel-vs-fp64 {k64:.3f}x vs reference {o64:.3f}x"
+    assert rms_k <= max(1.1 * rms_o + 1e-8, 0.5 * floor), f"{where}: rms err {rms_k:.2e} vs reference {rms_o:.2e}"
+    return rec
+
+
+def assert_energy_parity(e, e_ref32, e_ref64=None, where=""):
+    """Energies (scalar or per head) against the reference-precision result: north_star's 1e-6 relative, literal.  Where a
+    head's total energy is small by cancellation of atomic energies the relative figure of ANY fp32 evaluation degrades; with
+    the fp64 truth given, such an element may instead be no further from the truth than 1.25 x the reference-precision
+    result is.  The margins are recorded either way."""
+    e, e_ref32 = np.atleast_1d(np.asarray(e, dtype=np.float64)), np.atleast_1d(np.asarray(e_ref32, dtype=np.float64))
+    rel32 = np.abs(e - e_ref32) / np.abs(e_ref32)
+    rec = {"max_rel_err_vs_ref32": float(rel32.max())}
+    ok = rel32 <= 1e-6
+    if e_ref64 is not None:
+        e_ref64 = np.atleast_1d(np.asarray(e_ref64, dtype=np.float64))
+        err_k, err_o = np.abs(e - e_ref64), np.abs(e_ref32 - e_ref64)
+        rec.update(max_rel_err_vs_fp64=float((err_k / np.abs(e_ref64)).max()), ref32_max_rel_err_vs_fp64=float((err_o / np.abs(e_ref64)).max()))
+        ok = ok | (err_k <= np.maximum(1e-6 * np.abs(e_ref64), 1.25 * err_o))
+    record_parity(where + ": energy", **rec)
+    assert np.all(ok), f"{where}: energy rel err {rel32.max():.2e} (1e-6)"

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from apax_b200 import synthetic as syn
-from conftest import assert_force_parity
+from conftest import assert_energy_parity, assert_force_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -56,7 +56,7 @@ def test_batched_image_lists_and_ensemble_forces():
         frac = pos_l[b] @ np.linalg.inv(cells[b])
         ref = go.shallow_ensemble(params, frac, Z_l[b], i_b, cells[b].T, off_b, "offsets")
         ref64 = go.shallow_ensemble(params, frac, Z_l[b], i_b, cells[b].T, off_b, "offsets", go.fp64_config())
-        assert np.all(np.abs(e[b] - ref["energy_ensemble"]) <= 1e-6 * np.abs(ref["energy_ensemble"]) + 1e-6)
+        assert_energy_parity(e[b], ref["energy_ensemble"], ref64["energy_ensemble"], where=f"batched cell {b}")
         f_b = np.transpose(f[:, ptr[b]:ptr[b + 1]], (1, 2, 0))
         assert_force_parity(f_b, ref["forces_ensemble"], ref64["forces_ensemble"], where=f"cell {b}")
 
@@ -74,5 +74,5 @@ def test_batch_eval_mirror():
         s = single.calculate(a)
         # same model, different (equally valid) neighbour order inside a row => fp32 summation order differs
         assert abs(r["energy"] - s["energy"]) <= 1e-6 * abs(s["energy"])
-        assert np.all(np.abs(r["forces"] - s["forces"]) <= 1e-5 * np.abs(s["forces"]) + 2e-6)
+        assert_force_parity(r["forces"], s["forces"], where="batch_eval vs calculate")      # literal tolerance
         assert r["forces_ensemble"].shape == (128, 3, 4) and np.abs(r["forces_uncertainty"] - s["forces_uncertainty"]).max() < 1e-5
