@@ -96,6 +96,7 @@ SIGNATURES = {
     "apax_gm_stress_times_vol": (C.c_int, [_P, _P, _I64, _I64, _P, _P, C.c_size_t]),
     "apax_gm_stress_times_vol_offsets": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, C.c_size_t]),
     "apax_gm_descriptor": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, C.c_size_t]),
+    "apax_gm_descriptor_vjp": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, C.c_size_t]),
     "apax_i8_gemm_test": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _P, _P, _I32]),
     "apax_i8_set_debug": (C.c_int, [_I32, _I32]),
     "apax_i8_mma_probe": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P]),

@@ -721,6 +721,37 @@ __global__ void __launch_bounds__(256) k_features_to_rowmajor(const float* __res
   }
 }
 
+// row-major [N][360] -> feature-major [360][ld] (the feature adjoints handed to apax_gm_descriptor_vjp)
+__global__ void __launch_bounds__(256) k_features_from_rowmajor(const float* __restrict__ g, int64_t ld, int64_t N,
+                                                                float* __restrict__ GT) {
+  __shared__ float tile[32][33];
+  const int64_t a0 = int64_t(blockIdx.x) * 32;
+  const int f0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t a = a0 + r;
+    const int f = f0 + tx;
+    tile[r][tx] = (a < N && f < NF) ? g[a * NF + f] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int f = f0 + r;
+    const int64_t a = a0 + tx;
+    if (f < NF && a < ld) GT[int64_t(f) * ld + a] = tile[tx][r];
+  }
+}
+
+// per-slot dE/d(dr_vec) (fp32, CSR order) -> the caller's COO order in fp64; entries the preparation dropped (padding) stay 0
+__global__ void __launch_bounds__(256) k_pair_grad_to_coo(const float4* __restrict__ D, const int32_t* __restrict__ src,
+                                                          const int32_t* __restrict__ rowptr, int64_t n_central,
+                                                          double* __restrict__ out) {
+  const int64_t s = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (s >= rowptr[n_central]) return;
+  const float4 d = D[s];
+  const int64_t e = src[s];
+  out[3 * e + 0] = double(d.x); out[3 * e + 1] = double(d.y); out[3 * e + 2] = double(d.z);
+}
+
 // ================================================================================================
 // readout: fp32 SIMT GEMM on feature-major activations.
 //   YT[n][m] = sum_k W[k][n] * X(k, m),  n in [0,NC), m in [0,ld)
@@ -910,6 +941,11 @@ __global__ void __launch_bounds__(128) k_head_scale_shift(const float* __restric
 }
 
 __device__ __forceinline__ int64_t cdiv_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__global__ void __launch_bounds__(256) k_negate_f64(double* __restrict__ x, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i < n) x[i] = -x[i];
+}
 
 // ---- dE/dy2 = ebar * w2[:,head] * swish'(y2) as an exact (tf32 hi, lo) pair: input of the backward tensor-core GEMM
 __global__ void __launch_bounds__(256) k_ybar2(const float* __restrict__ D2T, const float* __restrict__ ebar,
@@ -1801,6 +1837,45 @@ extern "C" int apax_gm_descriptor(apax_stream_t stream, const apax_gm_params* pa
   APAX_TRY(gm_descriptor_impl(stream, params, w, geo));
   APAX_LAUNCH(k_features_to_rowmajor, dim3((unsigned)cdiv(n_atoms, 32), cdiv(NF, 32)), dim3(256), 0, stream, w.GT,
               w.ld, n_atoms, g);
+  return APAX_OK;
+}
+
+extern "C" int apax_gm_descriptor_vjp(apax_stream_t stream_, const apax_gm_params* params, const double* R, const int32_t* Z,
+                                      const int32_t* idx, const double* box, const double* offsets, int64_t n_atoms,
+                                      int64_t n_pairs, int32_t disp_mode, const float* g_bar, double* dr_vec_bar, double* R_bar,
+                                      void* workspace, size_t workspace_bytes) {
+  GmWorkspace w;
+  APAX_TRY(get_ws(params, n_atoms, n_pairs, workspace, workspace_bytes, &w));
+  if (!R || !Z || !g_bar || (!dr_vec_bar && !R_bar) || (n_pairs > 0 && !idx)) return APAX_ERR_INVALID_ARG;
+  if (disp_mode < APAX_DISP_GAS || disp_mode > APAX_DISP_DRVEC) return APAX_ERR_INVALID_ARG;
+  if ((disp_mode == APAX_DISP_OFFSETS || disp_mode == APAX_DISP_MINIMAGE) && !box) return APAX_ERR_INVALID_ARG;
+  if (disp_mode == APAX_DISP_DRVEC && R_bar) return APAX_ERR_INVALID_ARG;   // no positions in that mode
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const apax_gm_params_impl* p = params;
+  APAX_TRY(gm_prepare_impl(stream, p, w, Z, idx));
+  const PairGeom geo = make_geom(p, R, Z, box, offsets, disp_mode);
+  const DescConst dc = make_desc_const(p->cfg);
+  const int lpa = pick_lpa(w.n_central);
+  // forward pair pass: the packed moments (the contractions are polynomial in them) and the per-pair displacements
+  APAX_LAUNCH(k_atom_pack, dim3((unsigned)cdiv(w.n_atoms, 256)), dim3(256), 0, stream, w, geo);
+  APAX_DISPATCH_LPA(lpa, launch_pair_fwd, stream, w, geo, dc, p->pair_block);
+  // reverse: g_bar -> moment adjoints -> per-pair dE/d(dr_vec)
+  APAX_LAUNCH(k_features_from_rowmajor, dim3((unsigned)cdiv(w.ld, 32), cdiv(NF, 32)), dim3(256), 0, stream, g_bar, w.ld, n_atoms,
+              w.GT);
+  APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(w.n_central, kContractThreads)), dim3(kContractThreads), 0, stream, w);
+  APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc, p->pair_block);
+  if (dr_vec_bar) {
+    APAX_CUDA_TRY(cudaMemsetAsync(dr_vec_bar, 0, sizeof(double) * 3 * size_t(n_pairs), stream));
+    if (n_pairs > 0)
+      APAX_LAUNCH(k_pair_grad_to_coo, dim3((unsigned)cdiv(n_pairs, 256)), dim3(256), 0, stream, w.D, w.src, w.rowptr, w.n_central,
+                  dr_vec_bar);
+  }
+  if (R_bar) {
+    // dr_vec = T(R[idx[1]] - R[idx[0]]) with the identity Jacobian of space.transform (space.py:93-97): the transpose of the two
+    // gathers, exactly what the force assembly computes with the opposite sign
+    APAX_DISPATCH_LPA(pick_lpa(w.n_atoms), launch_force_gather, stream, w, R_bar);
+    APAX_LAUNCH(k_negate_f64, dim3((unsigned)cdiv(3 * n_atoms, 256)), dim3(256), 0, stream, R_bar, 3 * n_atoms);
+  }
   return APAX_OK;
 }
 

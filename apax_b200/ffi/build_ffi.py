@@ -33,6 +33,18 @@ def build_ffi() -> str:
     return out
 
 
+# XLA-FFI target name -> handler symbol of xla_ffi_shim.cc: every handler the shim defines
+FFI_TARGETS = (
+    ("apax_energy_forces", "ApaxEnergyForces"),
+    ("apax_energy_forces_stress", "ApaxEnergyForcesStress"),
+    ("apax_descriptor", "ApaxDescriptor"),
+    ("apax_descriptor_vjp", "ApaxDescriptorVjp"),
+    ("apax_nl_minimage", "ApaxNeighborListMinImage"),
+    ("apax_nl_needs_rebuild", "ApaxNeedsRebuild"),
+    ("apax_train_loss_and_grad", "ApaxTrainLossAndGrad"),
+)
+
+
 def register(lib_path: str | None = None) -> None:
     """jax.ffi.register_ffi_target for every handler of the shim (platform "CUDA")."""
     import ctypes
@@ -40,7 +52,5 @@ def register(lib_path: str | None = None) -> None:
     import jax
 
     lib = ctypes.CDLL(lib_path or build_ffi())
-    for target, symbol in (("apax_energy_forces", "ApaxEnergyForces"), ("apax_descriptor", "ApaxDescriptor"),
-                           ("apax_nl_minimage", "ApaxNeighborListMinImage"), ("apax_nl_needs_rebuild", "ApaxNeedsRebuild"),
-                           ("apax_train_loss_and_grad", "ApaxTrainLossAndGrad")):
+    for target, symbol in FFI_TARGETS:
         jax.ffi.register_ffi_target(target, jax.ffi.pycapsule(getattr(lib, symbol)), platform="CUDA")

@@ -1,8 +1,8 @@
 // XLA-FFI custom-call layer over the C ABI of libapax_b200.so (include/apax_b200.h) -- the binding `north_star` names for
 // keeping apax's host code in Python/JAX.  One handler per C entry point; every handler only unpacks XLA buffers and
 // forwards them (no arithmetic here).  Buffers are XLA-owned device memory, the stream comes from the call frame, scratch
-// is a result buffer sized by the host with apax_*_workspace_bytes.  The library never allocates, never synchronises and
-// keeps no mutable global state, so the handlers may run on any XLA runtime thread and inside CUDA-graph capture.
+// is a result buffer sized by the host with apax_*_workspace_bytes.  The library's device-side entry points never allocate, never synchronise and
+// keep no mutable global state besides a launch counter and the opt-in measurement switches, so the handlers may run on any XLA runtime thread and inside CUDA-graph capture.
 //
 // jaxlib's headers (xla/ffi/api/ffi.h) are NOT in this repository's build image, so this file is compiled only by
 // apax_b200/ffi/build_ffi.py when `jax.ffi.include_dir()` exists; INTEGRATION.md s2 shows the Python side
@@ -86,6 +86,21 @@ ffi::Error Descriptor(cudaStream_t stream, int64_t params, int32_t disp_mode, ff
                 "apax_gm_descriptor");
 }
 
+// ---- VJP of the descriptor: the backward rule a jax.custom_vjp around the same seam needs -------------------------------
+// want = 1: cotangent of dr_vec [P,3] (result d_dr); 2: cotangent of the positions [N,3] (result d_R); 3: both.  The result
+// that is not wanted is a zero-sized buffer.
+ffi::Error DescriptorVjp(cudaStream_t stream, int64_t params, int32_t disp_mode, ffi::Buffer<ffi::F64> R, ffi::Buffer<ffi::S32> Z,
+                         ffi::Buffer<ffi::S32> idx, ffi::AnyBuffer box, ffi::AnyBuffer offsets, ffi::Buffer<ffi::F32> g_bar,
+                         ffi::ResultBuffer<ffi::F64> d_dr, ffi::ResultBuffer<ffi::F64> d_R, ffi::ResultBuffer<ffi::U8> workspace) {
+  const int64_t n = Z.dimensions()[0], p = idx.dimensions()[1];
+  return status(apax_gm_descriptor_vjp(reinterpret_cast<apax_stream_t>(stream), reinterpret_cast<const apax_gm_params*>(params),
+                                       R.typed_data(), Z.typed_data(), idx.typed_data(), opt<double>(box), opt<double>(offsets), n, p,
+                                       disp_mode, g_bar.typed_data(), d_dr->element_count() ? d_dr->typed_data() : nullptr,
+                                       d_R->element_count() ? d_R->typed_data() : nullptr, workspace->typed_data(),
+                                       workspace->element_count()),
+                "apax_gm_descriptor_vjp");
+}
+
 // ---- min-image neighbour list (partition.neighbor_list allocate/update) ------------------------------------------------
 ffi::Error NeighborListMinImage(cudaStream_t stream, double cutoff, ffi::Buffer<ffi::F64> frac, ffi::Buffer<ffi::F64> box,
                                 ffi::ResultBuffer<ffi::S32> idx, ffi::ResultBuffer<ffi::S32> n_found,
@@ -146,6 +161,12 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(ApaxDescriptor, Descriptor,
                                   .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::S32>>().Arg<ffi::Buffer<ffi::S32>>()
                                   .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
                                   .Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::U8>>(),
+                              {ffi::Traits::kCmdBufferCompatible});
+XLA_FFI_DEFINE_HANDLER_SYMBOL(ApaxDescriptorVjp, DescriptorVjp,
+                              APAX_FFI_STREAM.Attr<int64_t>("params").Attr<int32_t>("disp_mode")
+                                  .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::S32>>().Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::U8>>(),
                               {ffi::Traits::kCmdBufferCompatible});
 XLA_FFI_DEFINE_HANDLER_SYMBOL(ApaxNeighborListMinImage, NeighborListMinImage,
                               APAX_FFI_STREAM.Attr<double>("cutoff").Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()

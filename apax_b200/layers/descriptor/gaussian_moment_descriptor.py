@@ -78,6 +78,17 @@ class GaussianMomentDescriptor:
         dp = _descriptor_params(emb, st)
         return rt.descriptor(dp, dr_vec, Z, neighbor_idxs, mode="drvec")
 
+    def vjp(self, variables: dict, dr_vec, Z, neighbor_idxs, g_bar):
+        """Backward rule of `apply` with respect to dr_vec (apax_gm_descriptor_vjp): g_bar [N, n_feat] -> dr_vec_bar [P,3] f64.
+        This is the pair (fwd, bwd) a JAX host registers as jax.custom_vjp around the descriptor seam
+        (apax_b200/ffi/jax_binding.py::descriptor)."""
+        emb = variables["params"]["radial_fn"]["atomic_type_embedding"]
+        st = self.statics()
+        if st["basis_kind"] != 0 or st["n_basis"] != 7:
+            raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "GaussianMomentDescriptor.vjp", "default basis only")
+        dp = _descriptor_params(emb, st)
+        return rt.descriptor_vjp(dp, dr_vec, Z, neighbor_idxs, g_bar, mode="drvec")[0]
+
 
 _cache: dict = {}
 

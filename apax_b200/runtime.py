@@ -273,6 +273,32 @@ def descriptor(params: DeviceParams, R, Z, idx, box=None, offsets=None, mode: st
     return g if params.n_features == N_FEATURES else g[:, : params.n_features].contiguous()   # n_contr truncation (:101)
 
 
+def descriptor_vjp(params: DeviceParams, R, Z, idx, g_bar, box=None, offsets=None, mode: str = "gas", want_dr_vec: bool = True,
+                   want_R: bool = False, workspace: Optional[Workspace] = None):
+    """VJP of the descriptor (apax_gm_descriptor_vjp): g_bar [N, n_feat] f32 -> (dr_vec_bar [P,3] f64 or None,
+    R_bar [N,3] f64 or None).  With mode="drvec", R is dr_vec [P,3] and only dr_vec_bar exists."""
+    dev = _require_cuda()
+    R = to_device(R, torch.float64)
+    Z = to_device(Z, torch.int32)
+    idx = to_device(idx, torch.int32)
+    n_atoms, n_pairs = int(Z.shape[0]), int(idx.shape[1])
+    gb = to_device(g_bar, torch.float32)
+    if gb.shape != (n_atoms, params.n_features):
+        raise _lib.ApaxB200Error(_lib.ERR_INVALID_ARG, "descriptor_vjp", f"g_bar shape {tuple(gb.shape)}")
+    if params.n_features != N_FEATURES:   # n_contr truncation: the dropped features carry a zero cotangent
+        full = torch.zeros((n_atoms, N_FEATURES), dtype=torch.float32, device=dev)
+        full[:, : params.n_features] = gb
+        gb = full
+    box_d = None if box is None else to_device(box, torch.float64)
+    off_d = None if offsets is None else to_device(offsets, torch.float64)
+    d_dr = torch.empty((n_pairs, 3), dtype=torch.float64, device=dev) if want_dr_vec else None
+    d_R = torch.empty((n_atoms, 3), dtype=torch.float64, device=dev) if want_R else None
+    wp, wb = _gm_ws(n_atoms, n_pairs, params.n_out, workspace)
+    check(lib().apax_gm_descriptor_vjp(_stream_ptr(), params.handle, _ptr(R), _ptr(Z), _ptr(idx), _ptr(box_d), _ptr(off_d), n_atoms,
+                                       n_pairs, MODES[mode], _ptr(gb), _ptr(d_dr), _ptr(d_R), wp, wb), "apax_gm_descriptor_vjp")
+    return d_dr, d_R
+
+
 # ------------------------------------------------------------------------------------------- lists
 def nl_build_minimage(frac, box, cutoff: float, capacity: int):
     """JaxMD Sparse min-image list (partition.py:478-787): idx i32 [2,capacity] padded with N,

@@ -213,6 +213,21 @@ int apax_gm_descriptor(apax_stream_t stream, const apax_gm_params* params, const
                        int64_t n_atoms, int64_t n_pairs, int32_t disp_mode, float* g, void* workspace,
                        size_t workspace_bytes);
 
+/* Vector-Jacobian product of the descriptor: the backward half of the same seam, so that a JAX host can wrap the
+ * descriptor ALONE in jax.custom_vjp and keep its own readout (ModelBuilder.build_descriptor, apax/nn/builder.py:79-83,
+ * 248-260; the call it replaces is `representation(dr_vec, Z, idx)` at apax/nn/models.py:107 under jax.grad,
+ * apax/utils/jax_md_reduced/quantity.py:52-54).  Inputs as apax_gm_descriptor, plus
+ *   g_bar      f32 [n_atoms][360] row-major: the cotangent of g (columns beyond the n_contr truncation must be zero)
+ *   dr_vec_bar f64 [n_pairs][3] out, COO order, or NULL: cotangent of dr_vec -- the VJP of `representation` itself; with
+ *              APAX_DISP_DRVEC (`R` is dr_vec) this is the whole backward rule.  Entries with idx[0]==idx[1] (padding) get 0.
+ *   R_bar      f64 [n_atoms][3] out, or NULL: cotangent of the positions for the three displacement branches, with the identity
+ *              Jacobian of space.transform (apax/utils/jax_md_reduced/space.py:93-97), i.e. Cartesian also for fractional R.
+ * The forward pair pass is recomputed here (nothing is kept from apax_gm_descriptor), so the call is self-contained. */
+int apax_gm_descriptor_vjp(apax_stream_t stream, const apax_gm_params* params, const double* R, const int32_t* Z,
+                           const int32_t* idx, const double* box, const double* offsets, int64_t n_atoms, int64_t n_pairs,
+                           int32_t disp_mode, const float* g_bar, double* dr_vec_bar, double* R_bar, void* workspace,
+                           size_t workspace_bytes);
+
 /* ------------------------------------------------------------------------------------------------
  * Neighbour lists.
  * (1) apax_nl_build_minimage replaces partition.neighbor_list(...).allocate/update with

@@ -123,14 +123,40 @@ def test_xla_ffi_shim_is_gated_on_jax():
     from apax_b200.ffi import build_ffi as bf
 
     src = open(os.path.join(os.path.dirname(bf.__file__), "xla_ffi_shim.cc")).read()
-    for fn in ("apax_gm_energy_forces", "apax_gm_descriptor", "apax_nl_build_minimage", "apax_nl_needs_rebuild",
-               "apax_train_loss_and_grad"):
+    for fn in ("apax_gm_energy_forces", "apax_gm_descriptor", "apax_gm_descriptor_vjp", "apax_gm_stress_times_vol",
+               "apax_gm_stress_times_vol_offsets", "apax_nl_build_minimage", "apax_nl_needs_rebuild", "apax_train_loss_and_grad"):
         assert fn + "(" in src
+    # every handler the shim defines is registered by build_ffi.register() (and vice versa)
+    import re
+
+    defined = set(re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((\w+),", src))
+    assert defined == {sym for _, sym in bf.FFI_TARGETS} and len(defined) == 7
     try:
         import jax  # noqa: F401
     except Exception:
         with pytest.raises(bf.FfiUnavailable):
             bf.build_ffi()
+
+
+def test_jax_binding_is_importable_and_gated():
+    """apax_b200/ffi/jax_binding.py (the jax.ffi.ffi_call / jax.custom_vjp side of the shim) imports without jax, names only
+    targets the shim defines, and every entry point raises FfiUnavailable -- not an obscure error -- where jax is absent."""
+    import inspect
+    import re
+
+    from apax_b200.ffi import jax_binding as jb
+
+    src = inspect.getsource(jb)
+    used = set(re.findall(r'ffi_call\("(\w+)"', src))
+    assert used == {t for t, _ in jb.FFI_TARGETS}, used ^ {t for t, _ in jb.FFI_TARGETS}
+    assert src.count("custom_vjp") >= 4 and "defvjp" in src          # energy and descriptor rules
+    try:
+        import jax  # noqa: F401
+    except Exception:
+        for fn, args in ((jb.register, ()), (jb.make_energy_fn, (0, None)), (jb.make_descriptor, (0,)),
+                         (jb.neighbor_list_minimage, (None, None, 6.0, 10)), (jb.needs_rebuild, (None, None, None, 0.5))):
+            with pytest.raises(jb.FfiUnavailable):
+                fn(*args)
 
 
 def test_public_header_is_plain_c(tmp_path):
