@@ -89,6 +89,7 @@ SIGNATURES = {
     "apax_gm_workspace_bytes": (C.c_size_t, [_I64, _I64, _I32]),
     "apax_gm_energy_forces": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, C.c_size_t]),
     "apax_gm_prepare": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, C.c_size_t]),
+    "apax_gm_prepare_minimage": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, C.c_double, _I64, _P, _P, _P, C.c_size_t, _P, C.c_size_t]),
     "apax_gm_compute": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, C.c_size_t]),
     "apax_gm_compute_partial": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, C.c_size_t]),
     "apax_gm_energy_forces_batched": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, C.c_size_t]),

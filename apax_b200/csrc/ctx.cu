@@ -284,3 +284,25 @@ extern "C" int apax_ctx_stress(apax_ctx* c, double* stress_host) {
     for (int j = 0; j < 3; ++j) stress_host[3 * i + j] = st[3 * j + i] / vol;   // val.T / V, V = det(box) = det(cell)
   return APAX_OK;
 }
+
+// Neighbour list + list preparation in one asynchronous call, all on the device: the min-image cell list of nl.cu feeds the
+// fused CSR import (binary-search transpose, no COO round trip, no row sort) -- what apax_ctx_calculate does internally, for
+// callers that keep positions on the device (MD between host callbacks, the slab-decomposed evaluation).
+extern "C" int apax_gm_prepare_minimage(apax_stream_t stream_, const apax_gm_params* params, const double* frac, const int32_t* Z,
+                                        const double* box, int64_t n_atoms, int64_t n_central, double cutoff, int64_t capacity,
+                                        int32_t* n_found, uint8_t* overflow, void* gm_workspace, size_t gm_workspace_bytes,
+                                        void* nl_workspace, size_t nl_workspace_bytes) {
+  if (!params || !frac || !Z || !box || !n_found || !overflow || !gm_workspace || !nl_workspace) return APAX_ERR_INVALID_ARG;
+  if (n_atoms < 1 || n_central < 1 || n_central > n_atoms || capacity < 1 || !(cutoff > 0.0)) return APAX_ERR_INVALID_ARG;
+  if (n_atoms >= (int64_t(1) << 31) - 256 || capacity >= (int64_t(1) << 31) - 256) return APAX_ERR_UNSUPPORTED;
+  if (((reinterpret_cast<uintptr_t>(gm_workspace) | reinterpret_cast<uintptr_t>(nl_workspace)) & 255) != 0) return APAX_ERR_INVALID_ARG;
+  const apax_gm_params_impl* p = reinterpret_cast<const apax_gm_params_impl*>(params);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  GmWorkspace gw;
+  NlWorkspace nw;
+  if (carve_gm_workspace(gm_workspace, n_atoms, capacity, p->cfg.n_out, 128, &gw) > gm_workspace_bytes) return APAX_ERR_WORKSPACE;
+  if (carve_nl_workspace(nl_workspace, n_atoms, capacity, &nw) > nl_workspace_bytes) return APAX_ERR_WORKSPACE;
+  APAX_CUDA_TRY(cudaMemsetAsync(overflow, 0, 1, s));
+  APAX_TRY(nl_build_minimage_csr(s, frac, box, n_atoms, cutoff, capacity, nw, nullptr, n_found, overflow));
+  return gm_prepare_from_csr(s, p, gw, Z, nw.rowptr_c, nw.nbr, /*symmetric_sorted=*/true, n_central);
+}

@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(256) k_csr_import(const int32_t* __restrict__ 
 __global__ void __launch_bounds__(256) k_transpose_symmetric(const int32_t* __restrict__ rowptr, int64_t N,
                                                              const int32_t* __restrict__ nbr, int32_t* __restrict__ rowptr_out,
                                                              int32_t* __restrict__ nbr_out, int32_t* __restrict__ src_out,
-                                                             int32_t* __restrict__ trowptr, int32_t* __restrict__ tpos) {
+                                                             int32_t* __restrict__ trowptr, int32_t* __restrict__ tpos,
+                                                             int64_t n_central) {
   // warp per row a: lanes take the row's slots; each looks its own atom up in the (sorted) row of the neighbour
   const int64_t a = (int64_t(blockIdx.x) * 256 + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -198,7 +199,8 @@ __global__ void __launch_bounds__(256) k_transpose_symmetric(const int32_t* __re
       if (v == int(a)) { found = mid; break; }
       if (v < int(a)) b = mid + 1; else e = mid - 1;
     }
-    tpos[s] = found;
+    // rows of non-central atoms (ghosts of a domain-decomposed box) are never evaluated: their slots carry no contribution
+    tpos[s] = j < n_central ? found : -1;
   }
 }
 
@@ -239,7 +241,7 @@ static int gm_prepare_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
 // list already in CSR form (rows = central atoms, e.g. straight from nl.cu): no COO pass, no row sort.
 // symmetric_sorted: every pair appears in both directions and rows are sorted by neighbour (min-image builder).
 int gm_prepare_from_csr(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const int32_t* Z,
-                        const int32_t* rowptr_in, const int32_t* nbr_in, bool symmetric_sorted) {
+                        const int32_t* rowptr_in, const int32_t* nbr_in, bool symmetric_sorted, int64_t n_central) {
   const int64_t N = w.n_atoms, P = w.n_pairs;
   if (!symmetric_sorted) {
     APAX_CUDA_TRY(cudaMemsetAsync(w.tcnt, 0, sizeof(int32_t) * (N + 1), stream));
@@ -249,7 +251,7 @@ int gm_prepare_from_csr(cudaStream_t stream, const apax_gm_params_impl* p, const
     return gm_prepare_tail(stream, p, w, Z);
   }
   APAX_LAUNCH(k_transpose_symmetric, dim3((unsigned)cdiv((N + 1) * 32, 256)), dim3(256), 0, stream, rowptr_in, N, nbr_in,
-              w.rowptr, w.nbr, w.src, w.trowptr, w.tpos);
+              w.rowptr, w.nbr, w.src, w.trowptr, w.tpos, n_central < 0 ? N : n_central);
   const int S = p->cfg.n_species;
   APAX_CUDA_TRY(cudaMemsetAsync(w.sp_present, 0, sizeof(int32_t) * 128, stream));
   APAX_LAUNCH(k_species_mark, dim3((unsigned)cdiv(N, 128)), dim3(128), 0, stream, Z, N, S, w.sp_present);

@@ -118,7 +118,8 @@ size_t carve_gm_workspace(void* base, int64_t n_atoms, int64_t n_pairs, int32_t 
 
 // exported to ctx.cu
 int gm_prepare_from_csr(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const int32_t* Z,
-                        const int32_t* rowptr_in, const int32_t* nbr_in, bool symmetric_sorted = false);
+                        const int32_t* rowptr_in, const int32_t* nbr_in, bool symmetric_sorted = false,
+                        int64_t n_central = -1 /* symmetric lists: rows >= n_central are not evaluated (ghosts) */);
 struct PairGeom;
 int gm_compute_device(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const double* R,
                       const int32_t* Z, const double* box, const double* offsets, int mode, double* energy,

@@ -257,23 +257,23 @@ class GpuSlabSystem:
             self.R_local = self.peer.R
         self.system = None
         self.build_list()
+        self.check_list()
         del frac
 
     def build_list(self):
-        """Min-image list over owned+ghost atoms, rows restricted to the owned (central) atoms."""
+        """Min-image list over owned + ghost atoms, built and prepared on the device in one asynchronous library call
+        (apax_gm_prepare_minimage): rows of the ghosts exist (they receive force contributions) but only the owned atoms are
+        evaluated as centrals.  No host synchronisation here; `check_list()` reads the overflow flag."""
         rt = self.rt
-        n_local = self.dec.n_local
-        cap = int(n_local * 100) + 4096
-        idx, n_found, overflow = rt.nl_build_minimage(self.R_local, self.box, self.cutoff, cap)
-        nf = int(n_found.item())
-        if int(overflow.item()):
-            raise RuntimeError("neighbour list capacity exceeded")
-        idx = idx[:, :nf]
-        idx = idx[:, idx[1] < self.dec.n_owned].contiguous()
-        self.n_pairs = int(idx.shape[1])
-        ws = self.system.ws if self.system is not None else None
-        self.system = rt.PreparedSystem(self.params, self.Z_local, idx, n_central=self.dec.n_owned, workspace=ws,
-                                        forces=self.peer.F if self.peer else None)
+        if self.system is None:
+            cap = int(self.dec.n_local * 100) + 4096
+            self.system = rt.PreparedMinimageSystem(self.params, self.Z_local, cap, n_central=self.dec.n_owned,
+                                                    forces=self.peer.F if self.peer else None)
+        self.system.build(self.R_local, self.box, self.cutoff)
+
+    def check_list(self) -> int:
+        self.n_pairs = self.system.check()
+        return self.n_pairs
 
     def local_compute(self, R_local, n_central):
         e, f = self.system.compute(R_local, self.box, None, "minimage")
@@ -285,18 +285,31 @@ class GpuSlabSystem:
         else:
             self.halo.forward(self.R_local)
 
-    def step(self):
+    def step(self, push: bool = True):
+        """One E+F evaluation of the box.  push=False: the ghost positions are already current (a forward halo was issued for
+        the list build of the same positions), so the exchange protocol's one-push-per-evaluation invariant holds."""
         if self.peer:
-            self.peer.forward()
+            if push:
+                self.peer.forward()
             e_local, _ = self.system.compute(self.R_local, self.box, None, "minimage")
             return self.peer.reverse(e_local)
+        if not push:
+            e_local, f_local = self.local_compute(self.R_local, self.dec.n_owned)
+            f_owned = self.halo.reverse(f_local)
+            e = e_local.clone()
+            if self.dec.world > 1:
+                dist.all_reduce(e, group=self.group)
+            return e, f_owned
         return evaluate(self.dec, self.halo, self.R_local, self.local_compute, self.group)
+
+    def status(self) -> None:
+        """Raise if one of this rank's bounded peer barriers ever timed out (a peer died or fell out of step)."""
+        if self.peer:
+            self.rt.check(self.rt.lib().apax_halo_status(self.peer.C.byref(self.peer.fwd)), "apax_halo_status")
 
 
 def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: str) -> int:
-    from apax_b200 import runtime as rt
-    from apax_b200 import synthetic as syn
-
+    """Stand-alone multi-GPU headline: owns stdout's single JSON line and the process group."""
     torch.cuda.set_device(local)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     # stdout must carry exactly one JSON line: NCCL writes its version banner to file descriptor 1, so everything any
@@ -305,6 +318,21 @@ def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: 
     json_fd = os.dup(1)
     os.dup2(2, 1)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = measure_multi_gpu(args, world, rank, local, metric, unit)
+    if rank == 0:
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
+
+
+def measure_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: str):
+    """BASELINE configs[3] on `world` GPUs (process group initialised by the caller): returns the result line on rank 0."""
+    from apax_b200 import runtime as rt
+    from apax_b200 import synthetic as syn
+
+    torch.cuda.set_device(local)
     n_mol = args.molecules * (world if args.scaling == "weak" else 1)
     pos, Z, cell = syn.water_box(n_mol, 0)
     n = len(Z)
@@ -336,24 +364,47 @@ def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: 
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = lib.apax_kernel_launch_count() - launches0
-    clocks = sampler.stop(window_s=float(ms.item()) * 1e-3 + 0.1) if sampler else None
+    # the sampler ticks every 100 ms: a 40 ms timed region would hold no sample, so the window reaches back over the warm-up
+    # steps as well (the same kernels under the same load)
+    clocks = sampler.stop(window_s=max(float(ms.item()) * 1e-3 + 0.1, 1.0)) if sampler else None
+    sysm.status()
+
+    # ---- per-kernel device times of this rank (CUDA events around every launch), max over ranks per kernel
+    prof_steps = 3
+    records = rt.profile_kernels(lambda: [sysm.step() for _ in range(prof_steps)])
+    dist.barrier()
+    per_kernel = {}
+    for name, t in records:
+        per_kernel.setdefault(name, []).append(t)
+    names = sorted(per_kernel)
+    all_names = [None] * world
+    dist.all_gather_object(all_names, names)
+    names = sorted(set().union(*[set(x) for x in all_names]))
+    mine = torch.tensor([float(np.sum(per_kernel.get(k, [0.0]))) / prof_steps for k in names], dtype=torch.float64, device="cuda")
+    kmax, ksum = mine.clone(), mine.clone()
+    dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ksum, op=dist.ReduceOp.SUM)
+    kernel_ms_max = {k: float(v) for k, v in zip(names, kmax.tolist())}
+    kernel_ms_mean = {k: float(v) / world for k, v in zip(names, ksum.tolist())}
 
     # ---- end to end: owned positions from pinned host memory in, list rebuilt, E+F, owned forces to the host
     n_owned = sysm.dec.n_owned
     h_pos = torch.empty((n_owned, 3), dtype=torch.float64).pin_memory()
     h_pos.copy_(sysm.R_local[:n_owned].cpu())
     h_f = torch.empty((n_owned, 3), dtype=torch.float64).pin_memory()
+    h_e = torch.empty(1, dtype=torch.float64).pin_memory()
     k_e2e = max(2, min(args.steps, 5))
 
     def e2e_step():
         sysm.R_local[:n_owned].copy_(h_pos, non_blocking=True)
-        sysm.forward_halo()
+        sysm.forward_halo()          # ghost positions for the list build AND for the evaluation: one push per evaluation
         sysm.build_list()
-        e_, f_ = sysm.step()
+        e_, f_ = sysm.step(push=False)
         h_f.copy_(f_, non_blocking=True)
-        e_h = e_.cpu()
+        h_e.copy_(e_, non_blocking=True)
         torch.cuda.synchronize()
-        return e_h
+        sysm.check_list()            # overflow flag of the rebuilt list (already on its way with the results)
+        return h_e
 
     e2e_step()
     dist.barrier()
@@ -363,38 +414,57 @@ def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: 
     dist.barrier()
     dt = torch.tensor([(time.perf_counter() - t0) / k_e2e], dtype=torch.float64, device="cuda")
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    sysm.status()
 
-    verify = None
-    if getattr(args, "verify", False):
-        # rank 0 evaluates the whole box alone and every rank compares its owned atoms against it
-        ref_e = torch.zeros(1, dtype=torch.float64, device="cuda")
-        ref_f = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
-        if rank == 0:
-            fr = rt.to_device(frac, torch.float64)
-            bx = rt.to_device(cell.T.copy(), torch.float64)
-            cap = int(n * 96) + 4096
-            idx, n_found, _ = rt.nl_build_minimage(fr, bx, 6.0, cap)
-            single = rt.PreparedSystem(dp, Z, idx[:, : int(n_found.item())].contiguous())
-            e1, f1 = single.compute(fr, bx, None, "minimage")
-            ref_e.copy_(e1)
-            ref_f.copy_(f1[0])
-            del single, idx
-        dist.broadcast(ref_e, 0)
-        dist.broadcast(ref_f, 0)
-        mine = ref_f[sysm.dec.owned]
-        viol = (torch.abs(f - mine) / (1e-5 * torch.abs(mine) + 1e-6)).max()
-        dist.all_reduce(viol, op=dist.ReduceOp.MAX)
-        verify = {"energy_rel_err": float(torch.abs(e[0] - ref_e[0]) / torch.abs(ref_e[0])),
-                  "max_force_violation_x_tolerance": float(viol)}
+    # ---- verify (always): rank 0 evaluates the whole box alone and every rank compares its owned atoms against it
+    e, f = sysm.step()
+    ref_e = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ref_f = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+    if rank == 0:
+        fr = rt.to_device(frac, torch.float64)
+        bx = rt.to_device(cell.T.copy(), torch.float64)
+        single = rt.PreparedMinimageSystem(dp, Z, int(n * 96) + 4096)
+        single.build(fr, bx, 6.0)
+        single.check()
+        e1, f1 = single.compute(fr, bx, None, "minimage")
+        ref_e.copy_(e1)
+        ref_f.copy_(f1[0])
+        del single
+    dist.broadcast(ref_e, 0)
+    dist.broadcast(ref_f, 0)
+    mine_f = ref_f[sysm.dec.owned]
+    viol = (torch.abs(f - mine_f) / (1e-5 * torch.abs(mine_f) + 1e-6)).max()
+    dist.all_reduce(viol, op=dist.ReduceOp.MAX)
+    verify = {"against": "single-GPU evaluation of the whole box by the same library (rank 0)",
+              "energy_rel_err": float(torch.abs(e[0] - ref_e[0]) / torch.abs(ref_e[0])),
+              "max_force_violation_x_tolerance": float(viol)}
+    del ref_f
 
     stats = torch.tensor([sysm.dec.n_owned, sysm.dec.n_local - sysm.dec.n_owned, sysm.n_pairs, sysm.halo.bytes_per_step],
                          dtype=torch.float64, device="cuda")
     gathered = [torch.zeros_like(stats) for _ in range(world)]
     dist.all_gather(gathered, stats)
+    line = None
     if rank == 0:
+        import bench as _bench
+
         ms_total = float(ms.item())
         value = n * args.steps / (ms_total * 1e-3)
         per_rank = [[int(v) for v in g.tolist()] for g in gathered]
+        dominant = max(kernel_ms_max, key=kernel_ms_max.get)
+        peak, peak_src = _bench.measured_peaks()
+        nbar = 85.842                                              # valid pairs per atom of this box at 6.0 A (bench N=1 measures it)
+        b_alg = 52.0 + 8.0 * nbar
+        atoms_per_launch = max(p[0] for p in per_rank)             # the slowest rank's launch covers its owned atoms
+        achieved = atoms_per_launch * b_alg / (kernel_ms_max[dominant] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "kernel": dominant, "kernel_ms_per_launch": kernel_ms_max[dominant], "atoms_per_launch": atoms_per_launch,
+                    "algorithmic_bytes_per_atom_step": b_alg, "peak_source": peak_src,
+                    "binding_resource": "fp32 issue slots (pair kernels) / tensor pipe + epilogue issue (readout): see the N=1 line's compute block",
+                    "step_achieved_GBps": n * b_alg / (ms_total / args.steps * 1e-3) / 1e9,
+                    "kernel_ms_per_step_max_over_ranks": {k: round(v, 4) for k, v in sorted(kernel_ms_max.items(), key=lambda kv: -kv[1])},
+                    "kernel_ms_per_step_mean_over_ranks": {k: round(v, 4) for k, v in sorted(kernel_ms_mean.items(), key=lambda kv: -kv[1])},
+                    "kernel_ms_sum_max": round(sum(kernel_ms_max.values()), 4), "kernel_ms_sum_mean": round(sum(kernel_ms_mean.values()), 4)}
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -403,18 +473,16 @@ def bench_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit: 
                                    "slab domain decomposition, forward/reverse halo exchange + energy sum " +
                                    ("as this library's kernels over NVLink peer memory (CUDA IPC)" if sysm.peer else "over NCCL"),
                        "atoms": n, "parallelism": f"{world} slabs along x", "energy": float(e.cpu()[0]),
-                       "per_rank_owned_ghost_pairs_halobytes": per_rank,
+                       "per_rank_owned_ghost_listentries_halobytes": per_rank,
                        "l2": "working set per step far exceeds the 126 MB L2"},
-            "clocks": clocks, "gpu_launches": int(launches),
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "verify": verify,
             "e2e": {"value": n / float(dt.item()), "unit": unit, "h2d_bytes_per_step": int(n * 24),
                     "d2h_bytes_per_step": int(n * 24 + 8 * world), "ms_per_step": float(dt.item()) * 1e3, "steps": k_e2e,
                     "includes": "per rank: pinned-host -> device copy of owned positions, forward halo, neighbour-list "
-                                "rebuild + preparation, E+F, reverse halo, energy all-reduce, device -> pinned-host copy "
-                                "of owned forces and the energy"},
+                                "rebuild + preparation (one fused device-side call), E+F, reverse halo, energy sum, device -> "
+                                "pinned-host copy of owned forces and the energy"},
         }
-        if verify:
-            line["verify"] = verify
-        sys.stdout.flush()
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
-    dist.destroy_process_group()
-    return 0
+    if sysm.peer:
+        dist.barrier()
+        sysm.peer.close()
+    return line

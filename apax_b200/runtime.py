@@ -256,6 +256,43 @@ class PreparedSystem:
         return out
 
 
+class PreparedMinimageSystem(PreparedSystem):
+    """Min-image neighbour list built on the device and prepared in the same call (apax_gm_prepare_minimage): positions stay
+    on the GPU, the list never takes COO form.  `build(frac, box, cutoff)` may be called again whenever the list must be
+    rebuilt; `check()` reads the overflow flag (one small synchronising copy)."""
+
+    def __init__(self, params: DeviceParams, Z, capacity: int, n_central: Optional[int] = None,
+                 forces: Optional[torch.Tensor] = None):
+        dev = _require_cuda()
+        self.params = params
+        self.Z = to_device(Z, torch.int32)
+        self.n_atoms = int(self.Z.shape[0])
+        self.n_central = n_central
+        self.n_pairs = int(capacity)          # the workspace is carved for the capacity; compute calls pass the same number
+        self.ws, self.nl_ws = Workspace(), Workspace()
+        self.wp, self.wb = _gm_ws(self.n_atoms, self.n_pairs, params.n_out, self.ws)
+        nbytes = lib().apax_nl_workspace_bytes(self.n_atoms, self.n_pairs)
+        self.nlp, self.nlb = C.c_void_p(Workspace.aligned_ptr(self.nl_ws.get(nbytes))), C.c_size_t(nbytes)
+        self.n_found = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.overflow = torch.zeros(1, dtype=torch.uint8, device=dev)
+        self.energy = torch.empty(params.n_out, dtype=torch.float64, device=dev)
+        self.forces = forces if forces is not None else torch.empty((params.n_out, self.n_atoms, 3), dtype=torch.float64, device=dev)
+        assert tuple(self.forces.shape) == (params.n_out, self.n_atoms, 3) and self.forces.dtype == torch.float64
+
+    def build(self, frac: torch.Tensor, box: torch.Tensor, cutoff: float) -> None:
+        check(lib().apax_gm_prepare_minimage(_stream_ptr(), self.params.handle, _ptr(frac), _ptr(self.Z), _ptr(box), self.n_atoms,
+                                             self.n_atoms if self.n_central is None else self.n_central, float(cutoff), self.n_pairs,
+                                             _ptr(self.n_found), _ptr(self.overflow), self.wp, self.wb, self.nlp, self.nlb),
+              "apax_gm_prepare_minimage")
+
+    def check(self) -> int:
+        """Entries found; raises if the list did not fit the capacity."""
+        nf, ov = int(self.n_found.item()), int(self.overflow.item())
+        if ov or nf > self.n_pairs:
+            raise _lib.ApaxB200Error(_lib.ERR_OVERFLOW, "PreparedMinimageSystem", f"{nf} list entries exceed the capacity {self.n_pairs}")
+        return nf
+
+
 def descriptor(params: DeviceParams, R, Z, idx, box=None, offsets=None, mode: str = "gas",
                workspace: Optional[Workspace] = None) -> torch.Tensor:
     """GaussianMomentDescriptor features [N, 360] f32; with mode="drvec", R is dr_vec [P,3]."""

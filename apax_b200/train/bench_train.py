@@ -18,16 +18,11 @@ def _batch(rank: int, batch: int):
 
 
 def run(args, world: int, rank: int, local: int, ClockSampler, metric: str, unit: str, cpu_baseline_fn=None) -> int:
+    """Stand-alone `--workload train`: owns stdout's single JSON line and the process group."""
+    import sys
+
     import torch
     import torch.distributed as dist
-
-    from .. import runtime as rt
-    from .. import synthetic as syn
-    from ..optimizer.get_optimizer import get_opt
-    from .loss import Loss, LossCollection
-    from .trainer import TrainState, TrainStep, flatten_batch
-
-    import sys
 
     torch.cuda.set_device(local)
     # stdout must carry exactly one JSON line: NCCL writes its version banner to file descriptor 1, so whatever a library
@@ -38,6 +33,29 @@ def run(args, world: int, rank: int, local: int, ClockSampler, metric: str, unit
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = measure(args, world, rank, local, ClockSampler, metric, unit, cpu_baseline_fn)
+    if rank == 0:
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def measure(args, world: int, rank: int, local: int, ClockSampler, metric: str, unit: str, cpu_baseline_fn=None):
+    """One measurement of the training-step workload on an initialised process group (world > 1); returns the result
+    line on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    from .. import runtime as rt
+    from .. import synthetic as syn
+    from ..optimizer.get_optimizer import get_opt
+    from .loss import Loss, LossCollection
+    from .trainer import TrainState, TrainStep, flatten_batch
+
+    torch.cuda.set_device(local)
     lib = rt.lib()
     B = args.train_batch
     inputs, labels = _batch(rank, B)
@@ -133,6 +151,7 @@ def run(args, world: int, rank: int, local: int, ClockSampler, metric: str, unit
            "includes": "flattening the padded host batch, pinned-host -> device copies, loss+gradients, gradient all-reduce, "
                        "Adam, device -> host read of the loss"}
 
+    line = None
     if rank == 0:
         ms_per_step = ms_total / args.steps
         flops = 2.0 * (360 * 256 + 256 * 256) * 10 * n_atoms      # 2 fwd + 2 tangent + 4 bwd + 2 weight-grad (x2 rows) GEMM sweeps
@@ -162,9 +181,9 @@ def run(args, world: int, rank: int, local: int, ClockSampler, metric: str, unit
             line["verify"] = verify
         if not args.no_cpu_baseline and cpu_baseline_fn is not None:
             line["cpu_baseline"] = cpu_baseline_fn(B, unit)
-        sys.stdout.flush()
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+        if step.peer is not None:
+            line["config"]["peer_barrier_status"] = int(lib.apax_train_peers_status(step.peer.peers[0]))
+    if step.peer is not None:
+        barrier()           # no rank unmaps a peer block another rank may still read
+        step.peer.close()
+    return line if rank == 0 else None

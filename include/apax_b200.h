@@ -154,6 +154,22 @@ int apax_gm_compute(apax_stream_t stream, const apax_gm_params* params, const do
 int apax_gm_atomic_energies(apax_stream_t stream, const apax_gm_params* params, int64_t n_atoms, int64_t n_pairs,
                             double* e_atoms, void* workspace, size_t workspace_bytes);
 
+/* Neighbour-list build AND list preparation in one asynchronous call, everything on the device: replaces
+ * partition.neighbor_list(...).allocate / update (apax/utils/jax_md_reduced/partition.py:478-787, Sparse, min-image,
+ * fractional coordinates) followed by the consumption of neighbor.idx in the model (apax/nn/models.py:100-107) for callers
+ * whose positions live on the device.  The list goes straight from the cell-list builder's CSR into the prepared workspace
+ * (no COO round trip); afterwards apax_gm_compute / apax_gm_compute_partial / apax_md_nvt_run are called with
+ * n_pairs = capacity.  Atoms [0, n_central) are evaluated as centrals (n_central = n_atoms for a whole box; the owned atoms
+ * of a slab otherwise, ghosts behind them).
+ *   frac f64 [n_atoms][3], Z i32 [n_atoms], box f64 [3][3] (columns = lattice vectors), cutoff = r_max + dr_threshold
+ *   n_found i32 [1] out: list entries found (over ALL n_atoms rows); overflow u8 [1] out: 1 if n_found > capacity -- the
+ *   caller must check it before trusting results (PEC.NEIGHBOR_LIST_OVERFLOW, partition.py:734)
+ *   gm_workspace >= apax_gm_workspace_bytes(n_atoms, capacity, n_out); nl_workspace >= apax_nl_workspace_bytes(n_atoms, capacity) */
+int apax_gm_prepare_minimage(apax_stream_t stream, const apax_gm_params* params, const double* frac, const int32_t* Z,
+                             const double* box, int64_t n_atoms, int64_t n_central, double cutoff, int64_t capacity,
+                             int32_t* n_found, uint8_t* overflow, void* gm_workspace, size_t gm_workspace_bytes,
+                             void* nl_workspace, size_t nl_workspace_bytes);
+
 /* Stress times volume, dU/d(eps) at eps = 0.  Replaces stress_times_vol (apax/layers/properties.py:11-42) as called by
  * EnergyDerivativeModel with calc_stress (apax/nn/models.py:160-169) for the MINIMAGE displacement, where the reference
  * applies the strain as dr' = (I + eps) . dr (apax/utils/jax_md_reduced/space.py:277-278):

@@ -117,3 +117,62 @@ def test_energy_fn_for_md():
         fm[a] -= dc @ inv
         fd = -(float(energy_fn(fp, nbrs, box)) - float(energy_fn(fm, nbrs, box))) / (2 * h)
         assert abs(fd - f[a, k]) < 2e-2 * max(1.0, abs(f[a, k]))
+
+
+def test_calculator_stress_both_neighbour_paths():
+    """`stress` through the calculator (apax_ctx_stress): EnergyDerivativeModel(calc_stress) followed by ProcessStress
+    (apax/md/function_transformations.py:140-159: val.T / det(box)), on the min-image path and on the image-list path (where
+    the reference differentiates at doubled displacements), against the oracle's stress_times_vol."""
+    from apax_b200.md.ase_calc import ASECalculator, Atoms
+    from oracle import gmnn_oracle as go
+    from oracle import neighbor_oracle as no
+
+    params = syn.gmnn_params(seed=8, random_bias=True)
+    calc = ASECalculator(params, model_config={"calc_stress": True}, dr_threshold=0.5)
+    assert "stress" in calc.implemented_properties
+    for n_mol, seed, mode in ((120, 2, "minimage"), (32, 0, "offsets")):
+        pos, Z, cell = syn.water_box(n_mol, seed)
+        res = calc.calculate(Atoms(pos, Z, cell))
+        frac = pos @ np.linalg.inv(cell)
+        if mode == "minimage":
+            idx, off, box = no.jaxmd_sparse_pairs(frac, cell.T, 6.0), None, cell.T
+        else:
+            idx, off = no.vesin_idx_offsets(pos, cell, 6.0)
+            box = cell                                                   # the vesin path hands box = atoms.cell.array (ase_calc.py:388-390)
+            frac = pos @ np.linalg.inv(cell)
+        st32 = go.stress_times_vol(params, frac if mode == "minimage" else (np.linalg.inv(box) @ pos.T).T, Z, idx, box, off, mode)
+        st64 = go.stress_times_vol(params, frac if mode == "minimage" else (np.linalg.inv(box) @ pos.T).T, Z, idx, box, off, mode, go.fp64_config())
+        vol = np.linalg.det(cell)
+        ref32, ref64 = st32.T / vol, st64.T / vol
+        scale = np.abs(ref64).max()
+        assert res["stress"].shape == (3, 3)
+        assert np.abs(res["stress"] - ref32).max() <= 4e-6 * scale, (mode, np.abs(res["stress"] - ref32).max() / scale)
+        assert np.abs(res["stress"] - ref64).max() <= 2.0 * np.abs(ref32 - ref64).max() + 1e-6 * scale, mode
+    plain = ASECalculator(params)
+    assert "stress" not in plain.calculate(Atoms(pos, Z, cell))
+
+
+def test_changed_atomic_numbers_reprepare_the_list():
+    """A change of `numbers` at fixed N, cell and within-skin positions must not reuse the compact species table of the old
+    list (the reference re-initialises on any change of numbers, apax/md/ase_calc.py:366-370)."""
+    from apax_b200 import runtime as rt
+    from apax_b200.md.ase_calc import ASECalculator, Atoms
+
+    pos, Z, cell = syn.water_box(120, 2)                                 # min-image path: the list survives between calls
+    params = syn.gmnn_params(seed=8)
+    Z2 = Z.copy()
+    h = np.nonzero(Z == 1)[0]
+    Z2[h[::7]] = 9                                                        # a species that was absent from the first list
+    dp = rt.DeviceParams(params)
+    ctx = rt.HostContext(dp, len(Z), 130 * len(Z))
+    ctx.calculate(pos, Z.astype(np.int32), cell, dr_threshold=0.5)
+    e_reused, f_reused = ctx.calculate(pos, Z2.astype(np.int32), cell, dr_threshold=0.5)      # same positions: skin test says "keep"
+    fresh = rt.HostContext(dp, len(Z), 130 * len(Z))
+    e_fresh, f_fresh = fresh.calculate(pos, Z2.astype(np.int32), cell, dr_threshold=0.5)
+    assert np.array_equal(e_reused, e_fresh) and np.array_equal(f_reused, f_fresh)
+    e_old, _ = fresh.calculate(pos, Z.astype(np.int32), cell, dr_threshold=0.5)
+    assert abs(e_old[0] - e_fresh[0]) > 1e-3                              # the species really matter
+    calc = ASECalculator(params, dr_threshold=0.5)
+    r1 = calc.calculate(Atoms(pos, Z, cell))
+    r2 = calc.calculate(Atoms(pos, Z2, cell))
+    assert abs(r2["energy"] - e_fresh[0]) <= 1e-12 * abs(e_fresh[0]) and r1["energy"] != r2["energy"]
