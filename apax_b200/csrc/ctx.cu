@@ -140,6 +140,7 @@ extern "C" int apax_ctx_calculate(apax_ctx* c, const double* positions_host, con
   if (n_atoms > c->max_atoms) return APAX_ERR_OVERFLOW;
   const apax_gm_params_impl* p = c->params;
   const int n_out = p->cfg.n_out;
+  const int n_f = (p->mean_forces && n_out > 1) ? 1 : n_out;   // rows of the force output (apax_gm_params_set_option)
   const int64_t N = n_atoms, cap = c->max_pairs;
   cudaStream_t s = c->stream;
   c->evaluated = 0;
@@ -238,11 +239,11 @@ extern "C" int apax_ctx_calculate(apax_ctx* c, const double* positions_host, con
   APAX_CUDA_TRY(cudaMemcpyAsync(c->h_out, c->energy, sizeof(double) * n_out, cudaMemcpyDeviceToHost, s));
   const bool f_pinned = forces_host && is_pinned(forces_host);
   if (forces_host)
-    APAX_CUDA_TRY(cudaMemcpyAsync(f_pinned ? forces_host : c->h_out + n_out, c->forces, sizeof(double) * 3 * N * n_out,
+    APAX_CUDA_TRY(cudaMemcpyAsync(f_pinned ? forces_host : c->h_out + n_out, c->forces, sizeof(double) * 3 * N * n_f,
                                   cudaMemcpyDeviceToHost, s));
   APAX_CUDA_TRY(cudaStreamSynchronize(s));
   memcpy(energy_host, c->h_out, sizeof(double) * n_out);
-  if (forces_host && !f_pinned) memcpy(forces_host, c->h_out + n_out, sizeof(double) * 3 * N * n_out);
+  if (forces_host && !f_pinned) memcpy(forces_host, c->h_out + n_out, sizeof(double) * 3 * N * n_f);
   if (n_pairs_host) *n_pairs_host = c->n_pairs;
   c->evaluated = forces_host != nullptr;
   return APAX_OK;

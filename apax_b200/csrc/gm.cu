@@ -1435,6 +1435,9 @@ static int32_t* i8_rowmax_buffer(const GmWorkspace& w) {
 static int readout_i8(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w, const PairGeom& geo,
                       double* energy, int head) {
   const int64_t N = w.n_central, ld = w.ld;
+  // rows the GEMMs sweep: the evaluated (central) atoms only, in whole 128-atom tiles.  The plane arrays keep the stride of
+  // ALL local atoms (ld), but ghost rows of a domain-decomposed box are never quantised, multiplied or read.
+  const int64_t rows = round_up(N, 128);
   const int n_out = p->cfg.n_out;
   int8_t* gq = reinterpret_cast<int8_t*>(w.GLT);
   int8_t* h1q = reinterpret_cast<int8_t*>(w.H1LT);
@@ -1446,9 +1449,9 @@ static int readout_i8(cudaStream_t stream, const apax_gm_params_impl* p, const G
   int32_t* rowmax = i8_rowmax_buffer(w);   // filled by k_contract_fwd<2>
   const I8Planes w0{p->q_w0, NH, NFP, int64_t(NH) * NFP, 4}, w1{p->q_w1, NH, NH, int64_t(NH) * NH, 4};
   if (head < 0) {
-    APAX_TRY(i8_quantize_rows(stream, w.GT, ld, N, NF, NFP, 4, p->cs_g, gq, e_g, rowmax, /*have_rowmax=*/true));
+    APAX_TRY(i8_quantize_rows(stream, w.GT, ld, N, NF, NFP, 4, p->cs_g, gq, e_g, rowmax, /*have_rowmax=*/true, rows));
     {  // layer 0: 360 -> 256; swish' kept in fp32 for the backward pass, swish goes on as digit planes
-      const I8Planes act{gq, ld, NFP, ld * int64_t(NFP), 4};
+      const I8Planes act{gq, rows, NFP, ld * int64_t(NFP), 4};
       I8Epilogue e{};
       e.mode = I8_EPI_ACT_Q; e.ld = ld; e.n_valid = NH; e.row_exp = e_g; e.bias = p->b0; e.aux = w.D1T;
       e.q_planes = h1q; e.q_kp = NH; e.q_plane_stride = ld * int64_t(NH); e.q_col_scale = p->cs_h1; e.q_row_exp = e_h1;
@@ -1456,7 +1459,7 @@ static int readout_i8(cudaStream_t stream, const apax_gm_params_impl* p, const G
       APAX_TRY(i8_gemm(stream, act, w0, e, p->tc_err));
     }
     {  // layer 1: 256 -> 256, output layer contracted in the epilogue; swish' goes on as fixed-scale digit planes
-      const I8Planes act{h1q, ld, NH, ld * int64_t(NH), 4};
+      const I8Planes act{h1q, rows, NH, ld * int64_t(NH), 4};
       I8Epilogue e{};
       e.mode = I8_EPI_ACT_HEAD; e.ld = ld; e.n_valid = NH; e.row_exp = e_h1; e.bias = p->b1;
       e.q_planes = d2q; e.q_kp = NH; e.q_plane_stride = ld * int64_t(NH); e.q_col_scale = p->cs_d2; e.q_fixed_exp = p->d2_exp;
@@ -1474,7 +1477,7 @@ static int readout_i8(cudaStream_t stream, const apax_gm_params_impl* p, const G
     return energy_sums(stream, w, n_out, energy, &p->corr, &geo);
   }
   {  // dE/dy1 = swish'(y1) * ebar * (W1 w2[head]) . swish'(y2)  -> digit planes
-    const I8Planes act{d2q, ld, NH, ld * int64_t(NH), 4};
+    const I8Planes act{d2q, rows, NH, ld * int64_t(NH), 4};
     const I8Planes wth{p->q_w1th + size_t(head) * 4 * NH * NH, NH, NH, int64_t(NH) * NH, 4};
     I8Epilogue e{};
     e.mode = I8_EPI_MULD_Q; e.ld = ld; e.n_valid = NH; e.row_exp = nullptr; e.fixed_exp = p->d2_exp; e.aux = w.D1T;
@@ -1484,7 +1487,7 @@ static int readout_i8(cudaStream_t stream, const apax_gm_params_impl* p, const G
     APAX_TRY(i8_gemm(stream, act, wth, e, p->tc_err));
   }
   {  // dE/dg = W0 . dE/dy1 (384 padded rows, fp32 for the contraction backward)
-    const I8Planes act{h1q, ld, NH, ld * int64_t(NH), 4};
+    const I8Planes act{h1q, rows, NH, ld * int64_t(NH), 4};
     const I8Planes w0t{p->q_w0t, NFP, NH, int64_t(NFP) * NH, 4};
     I8Epilogue e{};
     e.mode = I8_EPI_STORE; e.ld = ld; e.n_valid = NFP; e.row_exp = e_x1; e.out = w.GT;
@@ -1515,14 +1518,20 @@ static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
   }
   APAX_TRY(readout(-1));
   if (!forces) return APAX_OK;
-  for (int head = 0; head < n_out; ++head) {
+  // mean_forces (apax_gm_params_set_option): ONE backward pass with the mean head's output weights (slot n_out of the folded
+  // backward weights) gives -d(mean_h E_h)/dR, instead of one pass per head
+  const bool mean_only = p->mean_forces && n_out > 1;
+  if (mean_only && mode == READOUT_TC) return APAX_ERR_UNSUPPORTED;
+  const int n_passes = mean_only ? 1 : n_out;
+  for (int pass = 0; pass < n_passes; ++pass) {
+    const int head = mean_only ? n_out : pass;
     // every backward pass reads only what the forward pass left behind (D1, D2 / its planes, ebar): nothing to redo
     APAX_TRY(readout(head));
     APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(N, kContractThreads)), dim3(kContractThreads), 0, stream, w);
     APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc, p->pair_block);
     if (p->corr.zbl_on || p->corr.exp_on)
       APAX_LAUNCH(k_pair_corrections<1>, dim3((unsigned)cdiv(N * 32, 256)), dim3(256), 0, stream, w, geo, p->corr, n_out);
-    APAX_DISPATCH_LPA(pick_lpa(w.n_atoms), launch_force_gather, stream, w, forces + int64_t(head) * w.n_atoms * 3);
+    APAX_DISPATCH_LPA(pick_lpa(w.n_atoms), launch_force_gather, stream, w, forces + int64_t(pass) * w.n_atoms * 3);
   }
   return APAX_OK;
 }
@@ -1571,6 +1580,7 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
   p->cfg = *cfg;
   p->readout_mode = APAX_READOUT_I8;
   p->pair_block = 1;
+  p->mean_forces = 0;
   const int S = cfg->n_species, n_out = cfg->n_out;
   // n_contr < 8 truncates the feature list c0|c1|...|c7 (gaussian_moment_descriptor.py:101): the caller's first dense layer
   // has n_feat rows; the kernels always produce all 360 features, the dropped ones meet zero weight rows (and receive a
@@ -1624,13 +1634,23 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
     float* h = new float[size_t(NH) * n_out];
     for (size_t i = 0; i < size_t(NH) * n_out; ++i) h[i] = wf(NH) * w2[i];
     int st = upload(&p->w2, h, size_t(NH) * n_out);
-    // w1t_head[head][k][n] = W1[n][k] * w2[k][head]  (reduction index k = layer-1 output feature)
-    float* hh = new float[size_t(n_out) * NH * NH];
-    for (int hd = 0; hd < n_out; ++hd)
-      for (int k = 0; k < NH; ++k)
-        for (int n = 0; n < NH; ++n)
-          hh[(size_t(hd) * NH + k) * NH + n] = (wf(NH) * w1[size_t(n) * NH + k]) * h[size_t(k) * n_out + hd];
-    if (!st) st = upload(&p->w1t_head, hh, size_t(n_out) * NH * NH);
+    // w1t_head[head][k][n] = W1[n][k] * w2[k][head]  (reduction index k = layer-1 output feature); slot n_out holds the
+    // mean head w2_mean[k] = mean_h w2[k][h]: the gradient of the MEAN energy (ShallowEnsembleModel with force_variance=False,
+    // apax/nn/models.py:265-267, and the MD energy_fn of a shallow ensemble, apax/md/simulate.py:55-58) in one backward pass
+    float* hh = new float[size_t(n_out + 1) * NH * NH];
+    for (int hd = 0; hd <= n_out; ++hd)
+      for (int k = 0; k < NH; ++k) {
+        float w2k = 0.0f;
+        if (hd < n_out) {
+          w2k = h[size_t(k) * n_out + hd];
+        } else {
+          double acc = 0.0;
+          for (int q = 0; q < n_out; ++q) acc += double(h[size_t(k) * n_out + q]);
+          w2k = float(acc / n_out);
+        }
+        for (int n = 0; n < NH; ++n) hh[(size_t(hd) * NH + k) * NH + n] = (wf(NH) * w1[size_t(n) * NH + k]) * w2k;
+      }
+    if (!st) st = upload(&p->w1t_head, hh, size_t(n_out + 1) * NH * NH);
     delete[] hh;
     delete[] h;
     if (st) return st;
@@ -1680,15 +1700,23 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
       i8_quantize_weights(W.data(), NH, NH, NH, NH, NH, planes, cs);
       APAX_TRY(upload(&p->q_w1, planes.data(), planes.size()));
       APAX_TRY(upload(&p->cs_h1, cs.data(), cs.size()));
-      // backward layer 1: one weight matrix per head, one scale vector for all of them
-      std::vector<float> Wh(size_t(n_out) * NH * NH);
-      for (int hd = 0; hd < n_out; ++hd)
-        for (int k = 0; k < NH; ++k)
-          for (int n = 0; n < NH; ++n)
-            Wh[(size_t(hd) * NH + k) * NH + n] = (f1 * w1[size_t(n) * NH + k]) * (f1 * w2[size_t(k) * n_out + hd]);
-      for (int hd = 0; hd < n_out; ++hd) i8_weight_scales(Wh.data() + size_t(hd) * NH * NH, NH, NH, NH, NH, cs, hd > 0);
+      // backward layer 1: one weight matrix per head (+ the mean head in slot n_out), one scale vector for all of them
+      std::vector<float> Wh(size_t(n_out + 1) * NH * NH);
+      for (int hd = 0; hd <= n_out; ++hd)
+        for (int k = 0; k < NH; ++k) {
+          float w2k = 0.0f;
+          if (hd < n_out) {
+            w2k = f1 * w2[size_t(k) * n_out + hd];
+          } else {
+            double acc = 0.0;
+            for (int q = 0; q < n_out; ++q) acc += double(f1 * w2[size_t(k) * n_out + q]);
+            w2k = float(acc / n_out);
+          }
+          for (int n = 0; n < NH; ++n) Wh[(size_t(hd) * NH + k) * NH + n] = (f1 * w1[size_t(n) * NH + k]) * w2k;
+        }
+      for (int hd = 0; hd <= n_out; ++hd) i8_weight_scales(Wh.data() + size_t(hd) * NH * NH, NH, NH, NH, NH, cs, hd > 0);
       std::vector<int8_t> all;
-      for (int hd = 0; hd < n_out; ++hd) {
+      for (int hd = 0; hd <= n_out; ++hd) {
         i8_quantize_weights(Wh.data() + size_t(hd) * NH * NH, NH, NH, NH, NH, NH, planes, cs, true);
         all.insert(all.end(), planes.begin(), planes.end());
       }
@@ -1734,6 +1762,10 @@ extern "C" int apax_gm_params_set_option(apax_gm_params* p, int32_t option, int3
     case APAX_OPT_READOUT:
       if (value != APAX_READOUT_I8 && value != APAX_READOUT_SIMT && value != APAX_READOUT_TC) return APAX_ERR_INVALID_ARG;
       p->readout_mode = value;
+      return APAX_OK;
+    case APAX_OPT_MEAN_FORCES:
+      if (value != 0 && value != 1) return APAX_ERR_INVALID_ARG;
+      p->mean_forces = value;
       return APAX_OK;
     case APAX_OPT_PAIR_BLOCK:
       if (value < 0 || value > 2) return APAX_ERR_INVALID_ARG;

@@ -30,6 +30,7 @@ struct apax_gm_params_impl {
   CorrConst corr;                 // all zero: no corrections
   int readout_mode;               // APAX_READOUT_* (apax_gm_params_set_option)
   int pair_block;                 // block shape of the pair kernels, 0..2 (measurement switch)
+  int mean_forces;                // n_out > 1: forces[1][N][3] of the MEAN energy in one backward pass instead of per head
   // device copies
   float* emb;    // [S][S][5][7], pre-multiplied by 1/sqrt(n_basis) when use_embed_norm
   float* w0;     // [360][256]
@@ -37,7 +38,7 @@ struct apax_gm_params_impl {
   float* b0;     // [256]
   float* w1;     // [256][256]
   float* w1t;    // [256][256]
-  float* w1t_head;  // [n_out][256][256]  W1^T with the head's output weights folded in (backward GEMM)
+  float* w1t_head;  // [n_out + 1][256][256]  W1^T with the head's output weights folded in (backward GEMM); last: the mean head
   float* b1;     // [256]
   float* w2;     // [256][n_out]
   float* b2;     // [n_out]
@@ -52,7 +53,7 @@ struct apax_gm_params_impl {
   // integer tensor-core readout (i8_gemm.cuh): weight digit planes [4][outputs][k] and per-feature scales
   int8_t* q_w0;     // [4][256][384]          layer 0
   int8_t* q_w1;     // [4][256][256]          layer 1
-  int8_t* q_w1th;   // [n_out][4][256][256]   backward through layer 1, head weights folded in
+  int8_t* q_w1th;   // [n_out + 1][4][256][256]   backward through layer 1, head weights folded in (last: the mean head)
   int8_t* q_w0t;    // [4][384][256]          backward through layer 0
   float* cs_g;      // [384] scales of the descriptor features (layer 0 reduction)
   float* cs_h1;     // [256] scales of swish(y1)          (layer 1 reduction)

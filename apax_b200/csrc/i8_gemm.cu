@@ -691,9 +691,12 @@ int prepare_i8(Kern kern) {
 }  // namespace
 
 int i8_quantize_rows(cudaStream_t stream, const float* xt, int64_t ld, int64_t n_valid_rows, int K, int kp, int n_planes,
-                     const float* col_scale, int8_t* planes, int32_t* row_exp, int32_t* rowmax_bits, bool have_rowmax) {
-  if (ld % 128 != 0 || kp % 64 != 0 || K > kp || (n_planes != 3 && n_planes != 4)) return APAX_ERR_INVALID_ARG;
-  const dim3 grid((unsigned)(ld / 128), (unsigned)(kp / 64));
+                     const float* col_scale, int8_t* planes, int32_t* row_exp, int32_t* rowmax_bits, bool have_rowmax,
+                     int64_t n_rows) {
+  if (n_rows <= 0) n_rows = ld;   // rows to emit (whole 128-row tiles; rows >= n_valid_rows get zero digits); default: all
+  if (ld % 128 != 0 || n_rows % 128 != 0 || n_rows > ld || kp % 64 != 0 || K > kp || (n_planes != 3 && n_planes != 4))
+    return APAX_ERR_INVALID_ARG;
+  const dim3 grid((unsigned)(n_rows / 128), (unsigned)(kp / 64));
   if (!have_rowmax) {   // otherwise the producer of xt already left the maxima of the first n_valid_rows rows
     APAX_CUDA_TRY(cudaMemsetAsync(rowmax_bits, 0, sizeof(int32_t) * ld, stream));
     APAX_LAUNCH(k_i8_rowmax, grid, dim3(128), 0, stream, xt, ld, n_valid_rows, K, col_scale, rowmax_bits);

@@ -87,7 +87,8 @@ struct I8Epilogue {
 // activations: feature-major fp32 [K][ld] -> digit planes [n_planes][ld][kp] + per-atom exponents
 int i8_quantize_rows(cudaStream_t stream, const float* xt, int64_t ld, int64_t n_valid_rows, int K, int kp, int n_planes,
                      const float* col_scale /* [kp] powers of two */, int8_t* planes, int32_t* row_exp,
-                     int32_t* rowmax /* [ld] float bits of the scaled row maxima */, bool have_rowmax = false);
+                     int32_t* rowmax /* [ld] float bits of the scaled row maxima */, bool have_rowmax = false,
+                     int64_t n_rows = 0 /* rows to emit, multiple of 128; 0 = ld */);
 
 // weights (host): W[k][n] (row stride ldw) -> planes [4][ncp][kp] of W[k][n] / c[k].  col_scale: computed here from
 // the row maxima of W (given_scale = false), or taken as given (shared between several weight matrices).

@@ -58,15 +58,34 @@ class SlabDecomposition:
         return torch.cat([self.owned, self.ghosts])
 
 
-def slab_of(frac_x: torch.Tensor, world: int) -> torch.Tensor:
-    s = torch.floor(_wrap01(frac_x) * world).to(torch.int64)
+def slab_bounds(frac_x: torch.Tensor, world: int, balanced: bool = True) -> torch.Tensor:
+    """Slab faces b[0] = 0 < b[1] < ... < b[W] = 1 along the first fractional axis.  balanced: the faces sit at the
+    k/W quantiles of the atoms' coordinates, so that every rank owns the same number of atoms (+-1) -- for a homogeneous
+    liquid that also balances the pair count, which is what the per-step cost follows; otherwise equal widths."""
+    b = torch.arange(world + 1, dtype=torch.float64, device=frac_x.device) / world
+    if balanced and world > 1:
+        xs, _ = torch.sort(_wrap01(frac_x.to(torch.float64)))
+        n = xs.numel()
+        for k in range(1, world):
+            i = (k * n) // world
+            b[k] = 0.5 * (xs[i - 1] + xs[i])
+    return b
+
+
+def slab_of(frac_x: torch.Tensor, world: int, bounds: Optional[torch.Tensor] = None) -> torch.Tensor:
+    x = _wrap01(frac_x)
+    if bounds is None:
+        s = torch.floor(x * world).to(torch.int64)
+    else:
+        s = torch.bucketize(x.to(torch.float64), bounds[1:-1].contiguous(), right=True)
     return torch.clamp(s, 0, world - 1)
 
 
-def ghost_mask(frac_x: torch.Tensor, slab: torch.Tensor, rank: int, world: int, cutoff_frac: float) -> torch.Tensor:
-    """Atoms not owned by `rank` whose periodic distance along x to the slab [rank/W, (rank+1)/W) is < cutoff_frac."""
+def ghost_mask(frac_x: torch.Tensor, slab: torch.Tensor, rank: int, world: int, cutoff_frac: float,
+               bounds: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Atoms not owned by `rank` whose periodic distance along x to the slab [b[rank], b[rank+1]) is < cutoff_frac."""
     x = _wrap01(frac_x)
-    lo, hi = rank / world, (rank + 1) / world
+    lo, hi = (rank / world, (rank + 1) / world) if bounds is None else (float(bounds[rank]), float(bounds[rank + 1]))
     d_lo = torch.abs(x - lo)
     d_lo = torch.minimum(d_lo, 1.0 - d_lo)
     d_hi = torch.abs(x - hi)
@@ -74,19 +93,25 @@ def ghost_mask(frac_x: torch.Tensor, slab: torch.Tensor, rank: int, world: int, 
     return (slab != rank) & (torch.minimum(d_lo, d_hi) < cutoff_frac)
 
 
-def decompose(frac: torch.Tensor, box: torch.Tensor, cutoff: float, rank: int, world: int) -> SlabDecomposition:
+def decompose(frac: torch.Tensor, box: torch.Tensor, cutoff: float, rank: int, world: int,
+              balanced: bool = True) -> SlabDecomposition:
     """Every rank runs this on the same global fractional positions; results are consistent by
     construction (pure function of the inputs)."""
     binv = torch.linalg.inv(box.to(torch.float64))
     height_x = 1.0 / float(torch.linalg.norm(binv[0]))
     cutoff_frac = cutoff / height_x
-    if world > 1 and 1.0 / world < cutoff_frac:
-        raise ValueError(f"slab thickness {height_x / world:.3f} A is below the cutoff {cutoff} A: use fewer ranks")
     fx = frac[:, 0].to(torch.float64)
-    slab = slab_of(fx, world)
+    bounds = slab_bounds(fx, world, balanced)
+    thinnest = float(torch.min(bounds[1:] - bounds[:-1]))
+    if balanced and world > 1 and thinnest < cutoff_frac:      # quantile faces would make a slab thinner than the cutoff
+        bounds = slab_bounds(fx, world, False)
+        thinnest = float(torch.min(bounds[1:] - bounds[:-1]))
+    if world > 1 and thinnest < cutoff_frac:
+        raise ValueError(f"slab thickness {height_x * thinnest:.3f} A is below the cutoff {cutoff} A: use fewer ranks")
+    slab = slab_of(fx, world, bounds)
     ids = torch.arange(frac.shape[0], device=frac.device)
     owned = ids[slab == rank]
-    gm = ghost_mask(fx, slab, rank, world, cutoff_frac) if world > 1 else torch.zeros_like(slab, dtype=torch.bool)
+    gm = ghost_mask(fx, slab, rank, world, cutoff_frac, bounds) if world > 1 else torch.zeros_like(slab, dtype=torch.bool)
     ghost_ids = ids[gm]
     owner = slab[ghost_ids]
     order = torch.argsort(owner * frac.shape[0] + ghost_ids)
@@ -100,7 +125,7 @@ def decompose(frac: torch.Tensor, box: torch.Tensor, cutoff: float, rank: int, w
         if r == rank or world == 1:
             send_counts.append(0)
             continue
-        m = ghost_mask(fx, slab, r, world, cutoff_frac) & (slab == rank)
+        m = ghost_mask(fx, slab, r, world, cutoff_frac, bounds) & (slab == rank)
         loc = g2l[ids[m]]
         send_local.append(loc)
         send_counts.append(int(loc.numel()))

@@ -14,7 +14,8 @@ from .. import runtime as rt
 def create_energy_fn(model: EnergyModel, params, numbers, n_models: int = 1, shallow: bool = False):
     if n_models > 1 and not shallow:
         raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "create_energy_fn", "full (vmapped-parameter) ensembles")
-    dp = device_params(params, model.statics())
+    # the integrators differentiate the MEAN energy of a shallow ensemble (simulate.py:55-58): one backward pass
+    dp = device_params(params, {**model.statics(), "mean_forces": True})
     mode = displacement_mode(model.init_box, model.inference_disp_fn)
     Z = rt.to_device(numbers, torch.int32)
     state = {}

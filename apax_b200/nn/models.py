@@ -159,6 +159,16 @@ class ShallowEnsembleModel:
 
     def apply(self, params, R, Z, neighbor, box, offsets):
         """models.py:209-275: energy statistics over heads, per-head forces and their statistics."""
+        if not self.force_variance:
+            # forces_mean = -jax.grad(mean_energy_fn) (models.py:265-267): ONE backward pass with the mean head's output weights
+            em = self.energy_model
+            dp = device_params(params, {**em.statics(), "mean_forces": True})
+            e_ens, f_mean = rt.energy_forces(dp, R, Z, canonicalize_neighbors(neighbor), box, offsets,
+                                             displacement_mode(em.init_box, em.inference_disp_fn))
+            n_ens = e_ens.shape[0]
+            e_mean = e_ens.mean()
+            return {"energy": e_mean, "energy_ensemble": e_ens,
+                    "energy_uncertainty": torch.sqrt(torch.sum((e_ens - e_mean) ** 2) / (n_ens - 1)), "forces": f_mean[0]}
         e_ens, f_ens = self.energy_model._run(params, R, Z, neighbor, box, offsets, forces=True)
         n_ens = e_ens.shape[0]
         divisor = 1.0 / (n_ens - 1)

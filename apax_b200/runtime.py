@@ -127,6 +127,10 @@ class DeviceParams:
         if cfg.get("readout") is not None:
             check(lib().apax_gm_params_set_option(handle, _lib.OPT_READOUT, _lib.READOUT_KINDS[str(cfg["readout"])]),
                   "apax_gm_params_set_option(readout)")
+        self.n_force_heads = n_out            # rows of the `forces` output: one per head, or one with mean_forces
+        if cfg.get("mean_forces"):
+            check(lib().apax_gm_params_set_option(handle, _lib.OPT_MEAN_FORCES, 1), "apax_gm_params_set_option(mean_forces)")
+            self.n_force_heads = 1
         if cfg.get("pair_block") is not None:
             check(lib().apax_gm_params_set_option(handle, _lib.OPT_PAIR_BLOCK, int(cfg["pair_block"])),
                   "apax_gm_params_set_option(pair_block)")
@@ -189,7 +193,7 @@ def energy_forces(params: DeviceParams, R, Z, idx, box, offsets, mode: str = "of
     if off_d is not None and off_d.dim() == 1:  # simulate.py:71 passes a broadcast [0,0,0]
         off_d = None if not bool(off_d.any()) else off_d.expand(n_pairs, 3).contiguous()
     energy = torch.empty(params.n_out, dtype=torch.float64, device=dev)
-    F = torch.empty((params.n_out, n_atoms, 3), dtype=torch.float64, device=dev) if forces else None
+    F = torch.empty((params.n_force_heads, n_atoms, 3), dtype=torch.float64, device=dev) if forces else None
     wp, wb = _gm_ws(n_atoms, n_pairs, params.n_out, workspace)
     check(lib().apax_gm_energy_forces(_stream_ptr(), params.handle, _ptr(R), _ptr(Z), _ptr(idx), _ptr(box_d), _ptr(off_d),
                                       n_atoms, n_pairs, MODES[mode], _ptr(energy), _ptr(F), wp, wb),
@@ -232,8 +236,8 @@ class PreparedSystem:
         dev = self.Z.device
         self.energy = torch.empty(params.n_out, dtype=torch.float64, device=dev)
         # `forces` may be caller-provided memory (e.g. a peer-mapped block for the NVLink halo exchange)
-        self.forces = forces if forces is not None else torch.empty((params.n_out, self.n_atoms, 3), dtype=torch.float64, device=dev)
-        assert tuple(self.forces.shape) == (params.n_out, self.n_atoms, 3) and self.forces.dtype == torch.float64
+        self.forces = forces if forces is not None else torch.empty((params.n_force_heads, self.n_atoms, 3), dtype=torch.float64, device=dev)
+        assert tuple(self.forces.shape) == (params.n_force_heads, self.n_atoms, 3) and self.forces.dtype == torch.float64
 
     def compute(self, R: torch.Tensor, box: Optional[torch.Tensor], offsets: Optional[torch.Tensor], mode: str,
                 forces: bool = True):
@@ -276,8 +280,8 @@ class PreparedMinimageSystem(PreparedSystem):
         self.n_found = torch.zeros(1, dtype=torch.int32, device=dev)
         self.overflow = torch.zeros(1, dtype=torch.uint8, device=dev)
         self.energy = torch.empty(params.n_out, dtype=torch.float64, device=dev)
-        self.forces = forces if forces is not None else torch.empty((params.n_out, self.n_atoms, 3), dtype=torch.float64, device=dev)
-        assert tuple(self.forces.shape) == (params.n_out, self.n_atoms, 3) and self.forces.dtype == torch.float64
+        self.forces = forces if forces is not None else torch.empty((params.n_force_heads, self.n_atoms, 3), dtype=torch.float64, device=dev)
+        assert tuple(self.forces.shape) == (params.n_force_heads, self.n_atoms, 3) and self.forces.dtype == torch.float64
 
     def build(self, frac: torch.Tensor, box: torch.Tensor, cutoff: float) -> None:
         check(lib().apax_gm_prepare_minimage(_stream_ptr(), self.params.handle, _ptr(frac), _ptr(self.Z), _ptr(box), self.n_atoms,
@@ -407,7 +411,7 @@ def energy_forces_batched(params: DeviceParams, R, Z, idx, offsets, struct_ptr, 
     off_d = None if offsets is None else to_device(offsets, torch.float64)
     n_atoms, n_pairs, b = int(R.shape[0]), int(idx.shape[1]), int(sp.shape[0]) - 1
     energy = torch.empty((b, params.n_out), dtype=torch.float64, device=dev)
-    F = torch.empty((params.n_out, n_atoms, 3), dtype=torch.float64, device=dev) if forces else None
+    F = torch.empty((params.n_force_heads, n_atoms, 3), dtype=torch.float64, device=dev) if forces else None
     wp, wb = _gm_ws(n_atoms, n_pairs, params.n_out, workspace)
     check(lib().apax_gm_energy_forces_batched(_stream_ptr(), params.handle, _ptr(R), _ptr(Z), _ptr(idx), _ptr(off_d), _ptr(sp),
                                               b, n_atoms, n_pairs, _ptr(energy), _ptr(F), wp, wb),
@@ -461,8 +465,8 @@ class HostContext:
         n = pos.shape[0]
         e = np.empty(self.params.n_out, dtype=np.float64)
         if out_forces is not None:
-            assert out_forces.dtype == np.float64 and out_forces.shape == (self.params.n_out, n, 3) and out_forces.flags.c_contiguous
-        f = (out_forces if out_forces is not None else np.empty((self.params.n_out, n, 3), dtype=np.float64)) if forces else None
+            assert out_forces.dtype == np.float64 and out_forces.shape == (self.params.n_force_heads, n, 3) and out_forces.flags.c_contiguous
+        f = (out_forces if out_forces is not None else np.empty((self.params.n_force_heads, n, 3), dtype=np.float64)) if forces else None
         npairs = C.c_int64(0)
         code = lib().apax_ctx_calculate(self.handle, pos.ctypes.data_as(C.c_void_p), num.ctypes.data_as(C.c_void_p),
                                         cel.ctypes.data_as(C.c_void_p), n, float(dr_threshold), int(rebuild),

@@ -92,9 +92,12 @@ int apax_gm_params_status(const apax_gm_params* p);
  * its host code set here).  APAX_OPT_READOUT: which kernels run the per-element MLP (apax/layers/readout.py:22-50) --
  * APAX_READOUT_I8 (default) exact integer tensor-core GEMMs, APAX_READOUT_SIMT fp32 CUDA-core GEMMs (cross-check),
  * APAX_READOUT_TC tcgen05 3xTF32 (biased accumulation, NOT parity-safe; measurement only).  APAX_OPT_PAIR_BLOCK: block shape
- * of the pair kernels, 0..2 (results are bitwise identical; measurement only).  Not to be called while an evaluation with
+ * of the pair kernels, 0..2 (results are bitwise identical; measurement only).  APAX_OPT_MEAN_FORCES (shallow ensembles,
+ * n_out > 1): 1 = every later evaluation returns forces f64 [1][n_atoms][3] = -d(mean over heads of E)/dR from ONE backward
+ * pass -- ShallowEnsembleModel with force_variance = False (apax/nn/models.py:265-267) and the mean-energy gradient of the MD
+ * energy function (apax/md/simulate.py:55-58) -- instead of the per-head forces of jacrev.  Not to be called while an evaluation with
  * these parameters is being enqueued from another thread. */
-typedef enum { APAX_OPT_READOUT = 0, APAX_OPT_PAIR_BLOCK = 1 } apax_gm_option;
+typedef enum { APAX_OPT_READOUT = 0, APAX_OPT_PAIR_BLOCK = 1, APAX_OPT_MEAN_FORCES = 2 } apax_gm_option;
 typedef enum { APAX_READOUT_SIMT = 0, APAX_READOUT_TC = 1, APAX_READOUT_I8 = 2 } apax_readout_kind;
 int apax_gm_params_set_option(apax_gm_params* p, int32_t option, int32_t value);
 
@@ -446,7 +449,7 @@ void apax_ctx_destroy(apax_ctx* ctx);
 /* positions_host f64 [n][3] Cartesian, numbers_host i32 [n], cell_host f64 [3][3] rows = lattice
  * vectors (all-zero = gas phase is not supported here: use apax_gm_energy_forces with a list),
  * dr_threshold = skin; rebuild = 1 forces a list rebuild, 0 applies the reference's skin test.
- * energy_host f64 [n_out], forces_host f64 [n_out][n][3]. */
+ * energy_host f64 [n_out], forces_host f64 [n_out][n][3] ([1][n][3] with APAX_OPT_MEAN_FORCES). */
 int apax_ctx_calculate(apax_ctx* ctx, const double* positions_host, const int32_t* numbers_host,
                        const double* cell_host, int64_t n_atoms, double dr_threshold, int32_t rebuild,
                        double* energy_host, double* forces_host, int64_t* n_pairs_host);

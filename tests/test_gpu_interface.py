@@ -176,3 +176,34 @@ def test_changed_atomic_numbers_reprepare_the_list():
     r1 = calc.calculate(Atoms(pos, Z, cell))
     r2 = calc.calculate(Atoms(pos, Z2, cell))
     assert abs(r2["energy"] - e_fresh[0]) <= 1e-12 * abs(e_fresh[0]) and r1["energy"] != r2["energy"]
+
+
+def test_mean_forces_single_backward_pass_matches_per_head_mean(golden):
+    """ShallowEnsembleModel(force_variance=False) (apax/nn/models.py:265-267) and the MD energy function of a shallow ensemble
+    (apax/md/simulate.py:55-58) need only -grad(mean energy): one backward pass with the mean head's output weights
+    (APAX_OPT_MEAN_FORCES) against the mean of the per-head forces and against the reference-source fixture."""
+    from apax_b200 import runtime as rt
+    from apax_b200.nn.builder import GMNNBuilder
+    from oracle import gmnn_oracle as go
+
+    d = golden("water_ensemble")
+    n_ens = int(d["n_ens"])
+    params = syn.gmnn_params(seed=int(d["param_seed"]), n_out=n_ens, random_scale_shift=True, random_bias=True)
+    cfg = {"ensemble": {"kind": "shallow", "n_members": n_ens, "force_variance": False}}
+    model = GMNNBuilder(cfg).build_energy_derivative_model(init_box=d["cell"].T)
+    c0 = rt.lib().apax_kernel_launch_count()
+    out = model.apply(params, d["frac"], d["Z"], d["idx"], d["box"], d["offsets"])
+    torch.cuda.synchronize()
+    launches_mean = rt.lib().apax_kernel_launch_count() - c0
+    assert set(out) == {"energy", "energy_ensemble", "energy_uncertainty", "forces"}
+    r64 = go.shallow_ensemble(params, d["frac"], d["Z"], d["idx"], d["box"], d["offsets"], "offsets", go.fp64_config())
+    assert_force_parity(out["forces"].cpu().numpy(), d["forces"], r64["forces"], where="ShallowEnsembleModel mean forces (one pass)")
+    assert np.allclose(out["energy_ensemble"].cpu().numpy(), d["energy_ensemble"], rtol=1e-6, atol=0)
+    full = GMNNBuilder({"ensemble": {"kind": "shallow", "n_members": n_ens, "force_variance": True}}).build_energy_derivative_model(init_box=d["cell"].T)
+    c0 = rt.lib().apax_kernel_launch_count()
+    ref = full.apply(params, d["frac"], d["Z"], d["idx"], d["box"], d["offsets"])
+    torch.cuda.synchronize()
+    launches_full = rt.lib().apax_kernel_launch_count() - c0
+    assert launches_full > launches_mean + 3 * (n_ens - 1)           # the per-head passes really are gone
+    fm, ff = out["forces"].cpu().numpy(), ref["forces"].cpu().numpy()
+    assert np.all(np.abs(fm - ff) <= 1e-5 * np.abs(ff) + 1e-6)
