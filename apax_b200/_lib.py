@@ -112,6 +112,9 @@ SIGNATURES = {
     "apax_md_nvt_init": (C.c_int, [_P, C.POINTER(MdNvtConfig), _P, _P, _I64, _P]),
     "apax_md_nvt_pre_force": (C.c_int, [_P, C.POINTER(MdNvtConfig), _P, _P, _P, _P, _P, _I64, _P]),
     "apax_md_nvt_post_force": (C.c_int, [_P, C.POINTER(MdNvtConfig), _P, _P, _P, _I64, _P]),
+    "apax_md_nvt_kick_ke": (C.c_int, [_P, C.POINTER(MdNvtConfig), _P, _P, _P, _I64, _I32, _P, _P]),
+    "apax_md_nvt_set_global": (C.c_int, [_P, _P, _P, _I64]),
+    "apax_md_nvt_chain_finish": (C.c_int, [_P, C.POINTER(MdNvtConfig), _P, _I64, _P, _P, _I64]),
     "apax_train_plan_create": (C.c_int, [C.POINTER(GmConfig), C.POINTER(_P)]),
     "apax_train_plan_destroy": (None, [_P]),
     "apax_train_param_layout": (C.c_int, [_P, _P, _P]),
@@ -128,6 +131,7 @@ SIGNATURES = {
                                                  _P, _P, _P, _P]),
     "apax_train_peers_status": (C.c_int, [C.POINTER(TrainPeers)]),
     "apax_halo_status": (C.c_int, [C.POINTER(HaloPeers)]),
+    "apax_peer_allreduce_sum": (C.c_int, [_P, C.POINTER(HaloPeers), C.c_uint32, _P, _P, _I32]),
     "apax_halo_push_rows": (C.c_int, [_P, _P, _P, _P, C.POINTER(HaloPeers), C.c_uint32]),
     "apax_halo_pull_add_rows": (C.c_int, [_P, _P, _P, _P, C.POINTER(HaloPeers), C.c_uint32, _P, _P, _I32]),
     "apax_ensemble_stats": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, _P]),

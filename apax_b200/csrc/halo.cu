@@ -4,8 +4,8 @@
 //
 // Every rank keeps its local position rows R[n_local][3] and force rows F[n_local][3] (owned atoms first, then ghosts
 // grouped by owner rank) in CUDA-IPC memory that its peers have mapped (apax_peer_alloc / apax_peer_open), behind a
-// 256-byte header: u32 fwd_flags[8] | u32 rev_flags[8] | u32 ticket | u32 error (sticky: a barrier timed out) | pad |
-// f64 energy[16] at byte 128.
+// 512-byte header: u32 fwd_flags[8] | u32 rev_flags[8] | u32 ticket | u32 error (sticky: a barrier timed out) | pad |
+// f64 energy[16] at byte 128 | u32 red_flags[8] at byte 256 | f64 red_val[2][16] at byte 320 (small all-reduce, two parities).
 //
 //   forward  (apax_halo_push_rows)     : pack-and-store -- each boundary atom's position goes straight into the ghost row
 //                                        of the neighbouring rank's R (remote stores); the last block to finish publishes
@@ -27,6 +27,8 @@ namespace {
 
 constexpr int HDR_FWD = 0, HDR_REV = 8, HDR_TICKET = 16, HDR_ERR = 17;   // u32 slots of the header
 constexpr int HDR_ENERGY_BYTE = 128;
+constexpr int HDR_RED = 64;            // u32 slot of the small all-reduce's flags (byte 256)
+constexpr int HDR_REDVAL_BYTE = 320;   // f64 [2][16]
 
 struct HaloArgs {
   double* rows[8];       // per rank r: first row (in r's block, as mapped here) that belongs to THIS rank's atoms
@@ -104,6 +106,29 @@ __global__ void k_halo_store_energy(const double* __restrict__ e_local, int n_ou
     reinterpret_cast<double*>(reinterpret_cast<char*>(hdr) + HDR_ENERGY_BYTE)[threadIdx.x] = e_local[threadIdx.x];
 }
 
+// Small all-reduce (sum) of up to 16 doubles over the peer headers: every rank stores its values in its own header (parity
+// epoch & 1), publishes the epoch to every peer, waits for all, and adds the ranks' values in rank order -- every rank gets
+// the bitwise identical sum.  Parities make one call safe against the next (a rank can be at most one call ahead: it needs
+// every peer's flag of call t before it can issue call t+1).
+__global__ void __launch_bounds__(32) k_peer_allreduce(HaloArgs h, const double* __restrict__ local, double* __restrict__ out, int n) {
+  const int par = int(h.epoch & 1u);
+  double* mine = reinterpret_cast<double*>(reinterpret_cast<char*>(h.hdr[h.rank]) + HDR_REDVAL_BYTE) + par * 16;
+  if (threadIdx.x < n) mine[threadIdx.x] = local[threadIdx.x];
+  __syncwarp();
+  if (threadIdx.x < h.world) {
+    __threadfence_system();
+    st_release_sys(h.hdr[threadIdx.x] + HDR_RED + h.rank, h.epoch);
+    peer_spin_until(h.hdr[h.rank] + HDR_RED + threadIdx.x, h.epoch, h.hdr[h.rank] + HDR_ERR);
+  }
+  __syncwarp();
+  if (threadIdx.x < n) {
+    double s = 0.0;
+    for (int r = 0; r < h.world; ++r)
+      s += __ldcg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(h.hdr[r]) + HDR_REDVAL_BYTE) + par * 16 + threadIdx.x);
+    out[threadIdx.x] = s;
+  }
+}
+
 int fill(HaloArgs& h, const apax_halo_peers* p, const int64_t* send_ptr_host, uint32_t epoch) {
   if (!p || !send_ptr_host || p->world < 1 || p->world > 8 || p->rank < 0 || p->rank >= p->world) return APAX_ERR_INVALID_ARG;
   for (int r = 0; r < p->world; ++r) {
@@ -152,6 +177,17 @@ extern "C" int apax_halo_pull_add_rows(apax_stream_t stream_, double* local_rows
     phase = 1;
   }
   if (phase == 0) APAX_LAUNCH(k_halo_pull, dim3(1), dim3(256), 0, s, h, local_rows, send_local, -1, 0, n_out, energy_global);
+  return APAX_OK;
+}
+
+extern "C" int apax_peer_allreduce_sum(apax_stream_t stream_, const apax_halo_peers* peers, uint32_t epoch, const double* local,
+                                       double* global_out, int32_t n) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  if (!local || !global_out || n < 1 || n > 16) return APAX_ERR_INVALID_ARG;
+  HaloArgs h{};
+  const int64_t none[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  APAX_TRY(fill(h, peers, none, epoch));
+  APAX_LAUNCH(k_peer_allreduce, dim3(1), dim3(32), 0, s, h, local, global_out, int(n));
   return APAX_OK;
 }
 

@@ -157,11 +157,18 @@ __global__ void __launch_bounds__(256) k_md_kick_ke(double* __restrict__ P, cons
   if (threadIdx.x == 0) st->partial[blockIdx.x] = sm[0];
 }
 
-__global__ void k_md_ke_final(MdChainState* st, int n_blocks) {
+__global__ void k_md_ke_final(MdChainState* st, int n_blocks, double* ke_out = nullptr) {
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int i = 0; i < n_blocks; ++i) s += st->partial[i];
-    st->KE = s;
+    if (ke_out) *ke_out = s; else st->KE = s;
+  }
+}
+
+__global__ void k_md_set_global(MdChainState* st, const double* __restrict__ ke_global, int dof) {
+  if (threadIdx.x == 0) {
+    st->KE = *ke_global;
+    st->dof = dof;
   }
 }
 
@@ -233,6 +240,37 @@ extern "C" int apax_md_nvt_post_force(apax_stream_t stream, const apax_md_nvt_co
   APAX_LAUNCH(k_md_chain_half, dim3(1), dim3(32), 0, stream, st, dt, cfg->kT, double(float(cfg->tau)), cfg->chain_steps,
               cfg->sy_steps, (const double*)nullptr);
   APAX_LAUNCH(k_md_scale, dim3((unsigned)cdiv(3 * n_atoms, 256)), dim3(256), 0, stream, P, st, 3 * n_atoms);
+  return APAX_OK;
+}
+
+extern "C" int apax_md_nvt_kick_ke(apax_stream_t stream, const apax_md_nvt_config* cfg, double* P, const double* F,
+                                   const double* mass, int64_t n_atoms, int32_t apply_kick, void* state, double* ke_local) {
+  APAX_TRY(md_cfg_ok(cfg));
+  if (!P || !mass || !state || !ke_local || (apply_kick && !F) || n_atoms < 0) return APAX_ERR_INVALID_ARG;
+  MdChainState* st = static_cast<MdChainState*>(state);
+  const double dt = double(float(cfg->dt)), dt_2 = double(float(dt / 2));
+  const int nb = ke_blocks(n_atoms);
+  APAX_LAUNCH(k_md_kick_ke, dim3(nb), dim3(256), 0, stream, P, F, mass, st, dt_2, n_atoms, apply_kick ? 1 : 0);
+  APAX_LAUNCH(k_md_ke_final, dim3(1), dim3(32), 0, stream, st, nb, ke_local);
+  return APAX_OK;
+}
+
+extern "C" int apax_md_nvt_set_global(apax_stream_t stream, void* state, const double* ke_global, int64_t n_atoms_global) {
+  if (!state || !ke_global || n_atoms_global < 1 || 3 * n_atoms_global > 2147483647LL) return APAX_ERR_INVALID_ARG;
+  APAX_LAUNCH(k_md_set_global, dim3(1), dim3(32), 0, stream, static_cast<MdChainState*>(state), ke_global, int(3 * n_atoms_global));
+  return APAX_OK;
+}
+
+extern "C" int apax_md_nvt_chain_finish(apax_stream_t stream, const apax_md_nvt_config* cfg, double* P, int64_t n_atoms, void* state,
+                                        const double* ke_global, int64_t n_atoms_global) {
+  APAX_TRY(md_cfg_ok(cfg));
+  if (!P || !state || n_atoms < 0) return APAX_ERR_INVALID_ARG;
+  APAX_TRY(apax_md_nvt_set_global(stream, state, ke_global, n_atoms_global));
+  MdChainState* st = static_cast<MdChainState*>(state);
+  const double dt = double(float(cfg->dt));
+  APAX_LAUNCH(k_md_chain_half, dim3(1), dim3(32), 0, stream, st, dt, cfg->kT, double(float(cfg->tau)), cfg->chain_steps,
+              cfg->sy_steps, (const double*)nullptr);
+  if (n_atoms > 0) APAX_LAUNCH(k_md_scale, dim3((unsigned)cdiv(3 * n_atoms, 256)), dim3(256), 0, stream, P, st, 3 * n_atoms);
   return APAX_OK;
 }
 

@@ -180,28 +180,34 @@ def evaluate(dec: SlabDecomposition, halo: HaloExchanger, R_local: torch.Tensor,
     return e, f_owned
 
 
+HALO_HEADER_BYTES = 512      # csrc/halo.cu: flags, ticket, error word, energies, small all-reduce slots
+
+
 class PeerHalo:
     """Halo exchange as this library's own kernels over NVLink peer memory (csrc/halo.cu): the rank's local position and
-    force rows live in one CUDA-IPC block that every peer maps; handles and row offsets are exchanged once through
-    torch.distributed's object all-gather (host plumbing), after which no collective library is on the data path."""
+    force rows live in one CUDA-IPC block that every peer maps; handles are exchanged ONCE through torch.distributed's object
+    all-gather (host plumbing), after which no collective library is on the data path.  The block is allocated for
+    `capacity_rows` local atoms (owned + ghosts); `configure(dec)` installs a decomposition -- row offsets and send lists
+    -- and may be called again when atoms have migrated (domain-decomposed MD)."""
 
-    def __init__(self, dec: SlabDecomposition, group=None):
+    def __init__(self, dec: SlabDecomposition, group=None, capacity_rows: Optional[int] = None):
         import ctypes as C
 
         from apax_b200 import _lib
         from apax_b200 import runtime as rt
 
-        self.C, self.rt, self.lib = C, rt, rt.lib()
-        self.dec = dec
+        self.C, self.rt, self.lib, self._lib, self.group = C, rt, rt.lib(), _lib, group
         world, rank = dec.world, dec.rank
-        n_local, n_owned = dec.n_local, dec.n_owned
-        self.rbytes = (n_local * 24 + 255) // 256 * 256
-        total = 256 + 2 * self.rbytes
+        self.world, self.rank = world, rank
+        self.capacity = int(capacity_rows or dec.n_local)
+        self.rbytes = (self.capacity * 24 + 255) // 256 * 256
+        total = HALO_HEADER_BYTES + 2 * self.rbytes
         own, handle = C.c_void_p(), C.create_string_buffer(64)
         _lib.check(self.lib.apax_peer_alloc(total, C.byref(own), C.cast(handle, C.c_void_p)), "apax_peer_alloc")
         self.own = own
         meta = [None] * world
-        dist.all_gather_object(meta, (bytes(handle.raw), n_owned, self.rbytes, list(dec.ghost_owner_counts)), group=group)
+        dist.all_gather_object(meta, (bytes(handle.raw), self.rbytes), group=group)
+        self.peer_rbytes = [m[1] for m in meta]
         self.mapped = []
         for r in range(world):
             if r == rank:
@@ -211,25 +217,37 @@ class PeerHalo:
                 hb = C.create_string_buffer(meta[r][0], 64)
                 _lib.check(self.lib.apax_peer_open(C.cast(hb, C.c_void_p), C.byref(ptr)), "apax_peer_open")
                 self.mapped.append(ptr.value)
+        self.e_global = torch.zeros(1, dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
+        self.epoch = 0
+        self.red_epoch = 0
+        self.configure(dec)
+
+    def configure(self, dec: SlabDecomposition) -> None:
+        """Install a decomposition: where my boundary atoms' rows live inside each peer's block, and what I send."""
+        _lib, rt, world, rank = self._lib, self.rt, self.world, self.rank
+        if dec.n_local > self.capacity:
+            raise _lib.ApaxB200Error(_lib.ERR_OVERFLOW, "PeerHalo", f"{dec.n_local} local atoms exceed the block capacity {self.capacity}")
+        self.dec = dec
+        meta = [None] * world
+        dist.all_gather_object(meta, (dec.n_owned, list(dec.ghost_owner_counts)), group=self.group)
         self.fwd, self.rev = _lib.HaloPeers(), _lib.HaloPeers()
         for rec in (self.fwd, self.rev):
             rec.world, rec.rank = world, rank
         for r in range(world):
-            _, n_owned_r, rbytes_r, goc_r = meta[r]
+            n_owned_r, goc_r = meta[r]
             assert goc_r[rank] == dec.send_counts[r], "inconsistent decomposition between ranks"
             row0 = n_owned_r + sum(goc_r[:rank])            # ghosts are grouped by owner rank, ascending
             self.fwd.header[r] = self.rev.header[r] = self.mapped[r]
             if dec.send_counts[r] > 0:
-                self.fwd.rows[r] = self.mapped[r] + 256 + 24 * row0
-                self.rev.rows[r] = self.mapped[r] + 256 + rbytes_r + 24 * row0
-        self.R = rt.device_view(own.value + 256, (n_local, 3), torch.float64)
-        self.F = rt.device_view(own.value + 256 + self.rbytes, (1, n_local, 3), torch.float64)
+                self.fwd.rows[r] = self.mapped[r] + HALO_HEADER_BYTES + 24 * row0
+                self.rev.rows[r] = self.mapped[r] + HALO_HEADER_BYTES + self.peer_rbytes[r] + 24 * row0
+        n_local = dec.n_local
+        self.R = rt.device_view(self.own.value + HALO_HEADER_BYTES, (n_local, 3), torch.float64)
+        self.F = rt.device_view(self.own.value + HALO_HEADER_BYTES + self.rbytes, (1, n_local, 3), torch.float64)
         self.send_local = dec.send_local.to(torch.int64).contiguous()
         self.send_ptr = np.concatenate([[0], np.cumsum(dec.send_counts)]).astype(np.int64)
-        self.e_global = torch.zeros(1, dtype=torch.float64, device=self.R.device)
-        self.epoch = 0
         self.bytes_per_step = 2 * int(self.send_ptr[-1] + sum(dec.ghost_owner_counts)) * 24
-        dist.barrier(group=group)        # every block is mapped everywhere before the first kernel touches one
+        dist.barrier(group=self.group)   # every rank has its new layout before the first kernel of the new epoch touches a peer
 
     def forward(self) -> None:
         self.epoch += 1
@@ -245,9 +263,17 @@ class PeerHalo:
                                                   rt._ptr(e_local), rt._ptr(self.e_global), 1), "apax_halo_pull_add_rows")
         return self.e_global, self.F[0, : self.dec.n_owned]
 
+    def allreduce_sum(self, local: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """Sum of up to 16 doubles over the ranks through the peer headers, identical on every rank (apax_peer_allreduce_sum)."""
+        self.red_epoch += 1
+        rt = self.rt
+        rt.check(self.lib.apax_peer_allreduce_sum(rt._stream_ptr(), self.C.byref(self.fwd), self.red_epoch, rt._ptr(local), rt._ptr(out),
+                                                  int(local.numel())), "apax_peer_allreduce_sum")
+        return out
+
     def close(self):
         for r, ptr in enumerate(getattr(self, "mapped", [])):
-            if r != self.dec.rank and ptr:
+            if r != self.rank and ptr:
                 self.lib.apax_peer_close(self.C.c_void_p(ptr))
         if getattr(self, "own", None) is not None and self.own.value:
             self.lib.apax_peer_free(self.own)

@@ -266,14 +266,14 @@ class PreparedMinimageSystem(PreparedSystem):
     rebuilt; `check()` reads the overflow flag (one small synchronising copy)."""
 
     def __init__(self, params: DeviceParams, Z, capacity: int, n_central: Optional[int] = None,
-                 forces: Optional[torch.Tensor] = None):
+                 forces: Optional[torch.Tensor] = None, workspaces: Optional[tuple] = None):
         dev = _require_cuda()
         self.params = params
         self.Z = to_device(Z, torch.int32)
         self.n_atoms = int(self.Z.shape[0])
         self.n_central = n_central
         self.n_pairs = int(capacity)          # the workspace is carved for the capacity; compute calls pass the same number
-        self.ws, self.nl_ws = Workspace(), Workspace()
+        self.ws, self.nl_ws = workspaces if workspaces is not None else (Workspace(), Workspace())   # reusable across re-creations
         self.wp, self.wb = _gm_ws(self.n_atoms, self.n_pairs, params.n_out, self.ws)
         nbytes = lib().apax_nl_workspace_bytes(self.n_atoms, self.n_pairs)
         self.nlp, self.nlb = C.c_void_p(Workspace.aligned_ptr(self.nl_ws.get(nbytes))), C.c_size_t(nbytes)

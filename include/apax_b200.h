@@ -312,6 +312,19 @@ int apax_md_nvt_pre_force(apax_stream_t stream, const apax_md_nvt_config* cfg, d
                           const double* F, const double* mass, const double* box, int64_t n_atoms, void* state);
 int apax_md_nvt_post_force(apax_stream_t stream, const apax_md_nvt_config* cfg, double* P, const double* F,
                            const double* mass, int64_t n_atoms, void* state);
+/* The same step for a box whose atoms are spread over several ranks (spatial domain decomposition): the Nose-Hoover chain
+ * is replicated and driven by the GLOBAL kinetic energy, so apax_md_nvt_post_force splits at the reduction:
+ *   apax_md_nvt_kick_ke      : P += dt/2 F on this rank's atoms (apply_kick != 0), ke_local f64 [1] = their kinetic energy
+ *   -- caller sums ke_local over the ranks (apax_peer_allreduce_sum) --
+ *   apax_md_nvt_chain_finish : chain half step with ke_global f64 [1] and dof = 3 N_global, momentum rescale of this rank's atoms
+ * apax_md_nvt_pre_force is used unchanged on the owned atoms (the chain state then already holds the global KE and dof).
+ * For the initial state: apax_md_nvt_init on the owned atoms, apax_md_nvt_kick_ke with apply_kick = 0, the reduction, then
+ * apax_md_nvt_set_global. */
+int apax_md_nvt_kick_ke(apax_stream_t stream, const apax_md_nvt_config* cfg, double* P, const double* F, const double* mass,
+                        int64_t n_atoms, int32_t apply_kick, void* state, double* ke_local);
+int apax_md_nvt_set_global(apax_stream_t stream, void* state, const double* ke_global, int64_t n_atoms_global);
+int apax_md_nvt_chain_finish(apax_stream_t stream, const apax_md_nvt_config* cfg, double* P, int64_t n_atoms, void* state,
+                             const double* ke_global, int64_t n_atoms_global);
 /* n_steps steps in one call -- the jax.lax.fori_loop over apply_fn between two neighbour-list decisions
  * (apax/md/simulate.py:313-354): pre_force -> apax_gm_compute (MINIMAGE, list already prepared in `workspace` with
  * apax_gm_prepare, n_out == 1) -> post_force, repeated.  F holds the forces of the current positions on entry and on
@@ -412,7 +425,7 @@ int apax_train_peers_status(const apax_train_peers* peers);
 
 /* Halo exchange of the slab-decomposed evaluation (apax_gm_compute_partial) as kernels over NVLink peer memory; no
  * counterpart in the reference, which is single-device (apax/md/simulate.py:313-354).  Every rank keeps, in one
- * apax_peer_alloc block mapped by its peers: a 256-byte zeroed header, then its local position rows and its local force
+ * apax_peer_alloc block mapped by its peers: a 512-byte zeroed header, then its local position rows and its local force
  * rows (f64 [n_local][3], owned atoms first, then ghosts grouped by owner rank).  `header[r]` is rank r's header and
  * `rows[r]` the first row, inside rank r's block, of the ghosts that THIS rank owns -- both as mapped in this process
  * (forward: in r's position rows; reverse: in r's force rows).  send_local i64 [n_send] (device) lists this rank's owned
@@ -435,6 +448,11 @@ int apax_halo_pull_add_rows(apax_stream_t stream, double* local_rows, const int6
                             const double* energy_local, double* energy_global, int32_t n_out);
 /* Synchronising health query (see apax_train_peers_status): APAX_ERR_CUDA once one of this rank's halo barriers timed out. */
 int apax_halo_status(const apax_halo_peers* peers);
+/* Sum of n <= 16 doubles over the ranks through the same peer headers (kinetic energy and the skin flag of the
+ * domain-decomposed MD loop): global_out[i] = sum over ranks of local[i], added in rank order so that every rank holds the
+ * bitwise identical result.  `epoch` is this reduction's own counter (+1 per call on every rank); only peers->header is used. */
+int apax_peer_allreduce_sum(apax_stream_t stream, const apax_halo_peers* peers, uint32_t epoch, const double* local,
+                            double* global_out, int32_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer convenience context: what ASECalculator.calculate does per call
