@@ -229,6 +229,57 @@ def measure_ensemble(args, world, rank, local, ClockSampler, metric, unit, cells
     return line
 
 
+# ------------------------------------------------------------------------------------------- large-system MD (north_star)
+def measure_md_slab(args, world, rank, local, ClockSampler, metric, unit, steps: int = 30, molecules=None):
+    """NVT MD of the 1,000,002-atom box spread over `world` GPUs (apax_b200/md/domain_md.py::SlabNVT): slab decomposition,
+    halo exchange over NVLink peer memory every step, list rebuilt (with atom migration) every 10 steps."""
+    import torch
+    import torch.distributed as dist
+
+    from .. import synthetic as syn
+    from .ase_calc import Atoms
+    from .domain_md import SlabNVT
+
+    torch.cuda.set_device(local)
+    pos, Z, cell = syn.water_box(molecules or args.molecules, 0)
+    n = len(Z)
+    params = syn.gmnn_params(seed=1234)
+    masses = np.where(Z == 8, 15.999, 1.008)
+    fs = 0.09822694788464063
+    dt, kT = 0.25 * fs, 300.0 * 8.617333262e-5
+    rng = np.random.default_rng(0)
+    p0 = rng.normal(size=(n, 3)) * np.sqrt(masses * kT)[:, None]
+    p0 -= p0.mean(0)
+    md = SlabNVT(params, Atoms(positions=pos, numbers=Z, cell=cell), None, dt=dt, kT=kT, dr_threshold=0.5, rebuild_every=10,
+                 masses=masses, momentum=p0)
+    md.run(10)                                                      # warm-up: ten steps and the first rebuild
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    md.run(steps)
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    Rg, Pg, Fg, e = md.state()
+    ok = bool(torch.isfinite(Rg).all() and torch.isfinite(Pg).all())
+    counters = dict(md.counters)
+    md.close()
+    if rank != 0:
+        return None
+    wall = float(wall.item())
+    return {"metric": metric, "value": n * steps / wall, "unit": unit, "n_gpus": world, "steps": steps, "warmup": 10,
+            "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "north_star large-system MD: NVT Nose-Hoover MD with GMNN on the 1,000,002-atom periodic water box, "
+                                   "slab decomposition over the GPUs, halo exchange over NVLink peer memory every step, list (6.0 + 0.5 A "
+                                   "skin) rebuilt with atom migration every 10 steps", "atoms": n, "parallelism": f"{world} slabs along x",
+                       "rebuilds": counters["rebuilds"], "migrated_atoms": counters["migrated"], "finite": ok,
+                       "timing": "wall clock over the step loop incl. the list rebuilds inside it, max over ranks"},
+            "e2e": {"value": n * steps / wall, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "ms_per_step": wall / steps * 1e3}}
+
+
 def run_md(args, world, rank, local, ClockSampler, metric, unit, cpu_baseline_fn=None) -> int:
     return _standalone(lambda *a: measure_md(*a, cpu_baseline_fn=cpu_baseline_fn), args, world, rank, local, ClockSampler, metric, unit)
 

@@ -369,6 +369,9 @@ def other_workloads(args, world, rank, local):
     a = copy.copy(args)
     attempt("configs[4] ensemble", lambda: bw.measure_ensemble(a, world, rank, local, ClockSampler, METRIC, UNIT, cells=args.cells, reps=2,
                                                                cpu_baseline_fn=ensemble_cpu_baseline if cpu else None))
+    if world > 1:   # north_star "large-system MD": the headline box under NVT across the GPUs
+        a = copy.copy(args)
+        attempt("large-system md (slab NVT)", lambda: bw.measure_md_slab(a, world, rank, local, ClockSampler, METRIC, UNIT, steps=30))
     return out
 
 
