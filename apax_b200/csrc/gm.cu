@@ -372,7 +372,10 @@ __global__ void __launch_bounds__(256) k_atom_pack(GmWorkspace ws, PairGeom geo)
 // `emb` is the staged species table: in shared memory when the launch wrapper says so (a pointer the compiler can follow
 // back to the __shared__ array: LDS instead of generic loads), else the compact table in global memory.  `box` lives in
 // shared memory, not registers: 18 registers less across the pair loop.
-template <int LPA, int BT, int MINB, int SPEC>
+// F2 = 1: the 100 accumulations per pair are issued as 50 packed FFMA2 (fma.rn.f32x2, sm_100): the same roundings element
+// by element (results are bitwise those of F2 = 0), half the issue slots -- a scalar three-register FFMA issues at 0.57 per
+// clock and sub-partition on a B200 (tools/probes/probe_ffma2.cu: 42 Tflop/s), FFMA2 carries 1.56x the flops.
+template <int LPA, int BT, int MINB, int SPEC, int F2>
 __device__ __forceinline__ void pair_fwd_body(const GmWorkspace& ws, const PairGeom& geo, const DescConst& dc,
                                               const float* __restrict__ emb, const double* box, int n_sp,
                                               double* ra) {
@@ -397,9 +400,10 @@ __device__ __forceinline__ void pair_fwd_body(const GmWorkspace& ws, const PairG
     Ra[0] = pa.x; Ra[BT] = pa.y; Ra[2 * BT] = pa.z;
     zc = int(__double_as_longlong(pa.w));
   }
-  float acc[NPK];
+  float2 acc2[NPK / 2];              // (acc[2i], acc[2i+1]): adjacent monomials of one radial channel
+  float* acc = reinterpret_cast<float*>(acc2);
 #pragma unroll
-  for (int k = 0; k < NPK; ++k) acc[k] = 0.0f;
+  for (int k = 0; k < NPK / 2; ++k) acc2[k] = make_float2(0.0f, 0.0f);
 
   int e = beg + sub;
   const int safe = valid ? int(atom) : 0;
@@ -462,8 +466,15 @@ __device__ __forceinline__ void pair_fwd_body(const GmWorkspace& ws, const PairG
 #pragma unroll
       for (int b = 0; b < NB; ++b) pr = fmaf(c[rr * NB + b], gb[b], pr);
       const float rho = pr * fc;
+      if (F2) {
+        const float2 rho2 = make_float2(rho, rho);
 #pragma unroll
-      for (int k = 0; k < 20; ++k) acc[rr * 20 + k] = fmaf(rho, mono[k], acc[rr * 20 + k]);
+        for (int k = 0; k < 10; ++k)
+          acc2[rr * 10 + k] = __ffma2_rn(rho2, make_float2(mono[2 * k], mono[2 * k + 1]), acc2[rr * 10 + k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 20; ++k) acc[rr * 20 + k] = fmaf(rho, mono[k], acc[rr * 20 + k]);
+      }
     }
   }
 #pragma unroll
@@ -481,14 +492,15 @@ __device__ __forceinline__ void pair_fwd_body(const GmWorkspace& ws, const PairG
 // ---- backward: per-pair dE/d(dr_vec) from the packed moment adjoints of the central atom.  Pair
 // terms are recomputed from the stored fp32 displacement; nothing per-pair other than (dx,dy,dz) was
 // kept from the forward pass.  Also leaves the row sum (fp64) of the central atom in Frow.
-template <int LPA, int BT, int MINB>
+template <int LPA, int BT, int MINB, int F2>
 __device__ __forceinline__ void pair_bwd_body(const GmWorkspace& ws, const DescConst& dc, const float* __restrict__ emb) {
   const int64_t gid = int64_t(blockIdx.x) * BT + threadIdx.x;
   const int64_t atom = gid / LPA;
   const int sub = int(gid % LPA);
   const bool valid = atom < ws.n_central;
   int beg = 0, end = 0;
-  float a[NPK];
+  float2 a2[NPK / 2];                // (a[2i], a[2i+1]) for the packed FFMA2 form
+  float* a = reinterpret_cast<float*>(a2);
   if (valid) {
     beg = ws.rowptr[atom];
     end = ws.rowptr[atom + 1];
@@ -529,9 +541,10 @@ __device__ __forceinline__ void pair_bwd_body(const GmWorkspace& ws, const DescC
       const float fcp = -0.5f * (dc.pi_f / dc.r_max) * sn;
       float mono[20];
       monomials(x, y, z, mono);
-      float B[20];
+      float2 B2[10];
+      float* B = reinterpret_cast<float*>(B2);
 #pragma unroll
-      for (int k = 0; k < 20; ++k) B[k] = 0.0f;
+      for (int k = 0; k < 10; ++k) B2[k] = make_float2(0.0f, 0.0f);
       float rbar = 0.0f;
 #pragma unroll
       for (int rr = 0; rr < NR; ++rr) {
@@ -544,10 +557,21 @@ __device__ __forceinline__ void pair_bwd_body(const GmWorkspace& ws, const DescC
         const float rho = pr * fc;
         const float drho = fmaf(fcp, pr, fc * qr);  // d rho_r / dr
         float rhobar = 0.0f;
+        if (F2) {   // packed: even and odd monomials in the two halves, joined at the end (20 terms: well inside the fp32 noise budget)
+          const float2 rho2 = make_float2(rho, rho);
+          float2 rb2 = make_float2(0.0f, 0.0f);
 #pragma unroll
-        for (int k = 0; k < 20; ++k) {
-          rhobar = fmaf(a[rr * 20 + k], mono[k], rhobar);
-          B[k] = fmaf(rho, a[rr * 20 + k], B[k]);
+          for (int k = 0; k < 10; ++k) {
+            rb2 = __ffma2_rn(a2[rr * 10 + k], make_float2(mono[2 * k], mono[2 * k + 1]), rb2);
+            B2[k] = __ffma2_rn(rho2, a2[rr * 10 + k], B2[k]);
+          }
+          rhobar = rb2.x + rb2.y;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 20; ++k) {
+            rhobar = fmaf(a[rr * 20 + k], mono[k], rhobar);
+            B[k] = fmaf(rho, a[rr * 20 + k], B[k]);
+          }
         }
         rbar = fmaf(rhobar, drho, rbar);
       }
@@ -580,7 +604,7 @@ __device__ __forceinline__ void pair_bwd_body(const GmWorkspace& ws, const DescC
   }
 }
 
-template <int LPA, int BT, int MINB, int SPEC>
+template <int LPA, int BT, int MINB, int SPEC, int F2 = 0>
 __global__ void __launch_bounds__(BT, MINB) k_pair_fwd(GmWorkspace ws, PairGeom geo, DescConst dc) {
   __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * EMB_STRIDE];
   __shared__ double box[9];
@@ -591,19 +615,19 @@ __global__ void __launch_bounds__(BT, MINB) k_pair_fwd(GmWorkspace ws, PairGeom 
   stage_species_table(ws, s_emb);
   const int n_sp = *ws.n_sp;
   if (n_sp <= MAX_SP_SMEM) {
-    pair_fwd_body<LPA, BT, MINB, SPEC>(ws, geo, dc, s_emb, box, n_sp, s_ra);
+    pair_fwd_body<LPA, BT, MINB, SPEC, F2>(ws, geo, dc, s_emb, box, n_sp, s_ra);
   } else {
-    pair_fwd_body<LPA, BT, MINB, SPEC>(ws, geo, dc, ws.embc, box, n_sp, s_ra);
+    pair_fwd_body<LPA, BT, MINB, SPEC, F2>(ws, geo, dc, ws.embc, box, n_sp, s_ra);
   }
 }
-template <int LPA, int BT, int MINB>
+template <int LPA, int BT, int MINB, int F2 = 0>
 __global__ void __launch_bounds__(BT, MINB) k_pair_bwd(GmWorkspace ws, DescConst dc) {
   __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * EMB_STRIDE];
   stage_species_table(ws, s_emb);
   if (*ws.n_sp <= MAX_SP_SMEM) {
-    pair_bwd_body<LPA, BT, MINB>(ws, dc, s_emb);
+    pair_bwd_body<LPA, BT, MINB, F2>(ws, dc, s_emb);
   } else {
-    pair_bwd_body<LPA, BT, MINB>(ws, dc, ws.embc);
+    pair_bwd_body<LPA, BT, MINB, F2>(ws, dc, ws.embc);
   }
 }
 // ---- force assembly: F_a = -( sum_{e: central a} dbar_e  -  sum_{e: neighbour a} dbar_e ), both sums
@@ -1235,13 +1259,17 @@ static int pick_lpa(int64_t n_atoms) {
 // the serial per-pair prelude.  apax_gm_params_set_option(APAX_OPT_PAIR_BLOCK) picks the shape (a measurement switch, results
 // are bitwise the same): 0 = 256 x 1 (uncapped), 1 = 128 x 3 (168 registers, default), 2 = 128 x 4 (128 registers).  Measured
 // on the 1,000,002-atom box (fwd / bwd ms): 2.96 / 3.01, 2.21 / 2.52, 3.20 / 2.89; 64-thread blocks at 144 registers: 2.88 / 2.94.
-template <int LPA, int BT, int MINB>
+// Round 2 (profiles/r02i_pair_ffma2.txt, r02d_pair_pipeline_ab.txt): packed FFMA2 accumulation 1.79 -> 1.73 ms forward
+// (bitwise the same, now the default) but 2.33 -> 2.55 ms backward (more spills under the 168-register cap, long-scoreboard
+// stalls 12 -> 26 % of the samples: variant 3 only); explicit software pipelining of the per-pair prelude against the
+// accumulation of the previous pair: 2.86 / 3.12 ms (spills) -- dropped.  Variant 4 = the round-1 scalar kernels.
+template <int LPA, int BT, int MINB, int F2 = 0>
 static int launch_pair_fwd_shape(cudaStream_t s, const GmWorkspace& w, const PairGeom& geo, const DescConst& dc) {
   const dim3 grid((unsigned)cdiv(w.n_central * LPA, BT));
   if (geo.mode == APAX_DISP_MINIMAGE && !geo.offsets) {
-    APAX_LAUNCH_AS("k_pair_fwd<LPA>", (k_pair_fwd<LPA, BT, MINB, 1>), grid, dim3(BT), 0, s, w, geo, dc);
+    APAX_LAUNCH_AS("k_pair_fwd<LPA>", (k_pair_fwd<LPA, BT, MINB, 1, F2>), grid, dim3(BT), 0, s, w, geo, dc);
   } else {
-    APAX_LAUNCH_AS("k_pair_fwd<LPA>", (k_pair_fwd<LPA, BT, MINB, 0>), grid, dim3(BT), 0, s, w, geo, dc);
+    APAX_LAUNCH_AS("k_pair_fwd<LPA>", (k_pair_fwd<LPA, BT, MINB, 0, F2>), grid, dim3(BT), 0, s, w, geo, dc);
   }
   return APAX_OK;
 }
@@ -1250,7 +1278,8 @@ static int launch_pair_fwd(cudaStream_t s, const GmWorkspace& w, const PairGeom&
   switch (variant) {
     case 0: return launch_pair_fwd_shape<LPA, 256, 1>(s, w, geo, dc);
     case 2: return launch_pair_fwd_shape<LPA, 128, 4>(s, w, geo, dc);
-    default: return launch_pair_fwd_shape<LPA, 128, 3>(s, w, geo, dc);
+    case 4: return launch_pair_fwd_shape<LPA, 128, 3, 0>(s, w, geo, dc);
+    default: return launch_pair_fwd_shape<LPA, 128, 3, 1>(s, w, geo, dc);   // 1 (default) and 3: packed FFMA2 accumulation
   }
 }
 template <int LPA>
@@ -1258,6 +1287,7 @@ static int launch_pair_bwd(cudaStream_t s, const GmWorkspace& w, const DescConst
   switch (variant) {
     case 0: APAX_LAUNCH_AS("k_pair_bwd<LPA>", (k_pair_bwd<LPA, 256, 1>), dim3((unsigned)cdiv(w.n_central * LPA, 256)), dim3(256), 0, s, w, dc); break;
     case 2: APAX_LAUNCH_AS("k_pair_bwd<LPA>", (k_pair_bwd<LPA, 128, 4>), dim3((unsigned)cdiv(w.n_central * LPA, 128)), dim3(128), 0, s, w, dc); break;
+    case 3: APAX_LAUNCH_AS("k_pair_bwd<LPA>", (k_pair_bwd<LPA, 128, 3, 1>), dim3((unsigned)cdiv(w.n_central * LPA, 128)), dim3(128), 0, s, w, dc); break;
     default: APAX_LAUNCH_AS("k_pair_bwd<LPA>", (k_pair_bwd<LPA, 128, 3>), dim3((unsigned)cdiv(w.n_central * LPA, 128)), dim3(128), 0, s, w, dc); break;
   }
   return APAX_OK;
@@ -1768,7 +1798,7 @@ extern "C" int apax_gm_params_set_option(apax_gm_params* p, int32_t option, int3
       p->mean_forces = value;
       return APAX_OK;
     case APAX_OPT_PAIR_BLOCK:
-      if (value < 0 || value > 2) return APAX_ERR_INVALID_ARG;
+      if (value < 0 || value > 4) return APAX_ERR_INVALID_ARG;
       p->pair_block = value;
       return APAX_OK;
     default:
