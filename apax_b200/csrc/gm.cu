@@ -705,6 +705,81 @@ __global__ void __launch_bounds__(kContractThreads, 256 / kContractThreads) k_co
   if (MODE == 2 && live) ws.q_rowmax[atom] = __float_as_int(mx < 3.0e38f ? mx : 3.4e38f);   // NaN / inf rows quantise to zero
 }
 
+// ---- features AND their digit planes in one kernel (the integer tensor-core readout's input): thread == atom in both
+// phases.  Phase 1 runs the contraction program, parks the 360 features of the block's 128 atoms in a per-block slot of
+// the (idle) feature buffer -- written and re-read by the same thread within microseconds, so the slot lives in L2 -- and
+// keeps the row maximum of the scaled features.  Phase 2 re-reads its own column 64 features at a time, converts to
+// fixed point at the row's exponent and emits the four base-256 digit planes through a 32 KB shared-memory tile as full
+// 64-byte row segments (the layout of k_i8_quantize).  Against k_contract_fwd<2> + k_i8_quantize this drops one launch,
+// the fp32 feature matrix' trip through HBM (1.44 KB/atom written, 1.5 KB/atom read) and the row-maximum array.
+// Persistent blocks (grid <= 2 per SM), each owning the slot `blockIdx.x` of [NFP][128] floats.
+__global__ void __launch_bounds__(kContractThreads, 256 / kContractThreads)
+k_contract_fwd_quantize(GmWorkspace ws, const float* __restrict__ col_scale, int8_t* __restrict__ planes,
+                        int32_t* __restrict__ row_exp, int64_t n_tiles) {
+  static_assert(kContractThreads == 128, "one thread per atom of a 128-atom GEMM tile");
+  __shared__ __align__(16) uint8_t tile[I8_DIGITS][128 * 64];
+  const int tid = threadIdx.x;
+  float* slot = ws.GT + int64_t(blockIdx.x) * NFP * 128 + tid;     // this thread's column of the block's slot, row stride 128
+  const int64_t plane_stride = ws.ld * int64_t(NFP);
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t m0 = t * 128, atom_raw = m0 + tid;
+    const bool live = atom_raw < ws.n_central;
+    const int64_t atom = live ? atom_raw : ws.n_central - 1;
+    float m[NPK];
+#pragma unroll
+    for (int k = 0; k < NPK; ++k) m[k] = ws.MT[int64_t(k) * ws.ld + atom];
+    float mx = 0.0f;
+    gm_contract_forward(m, [&](int f, float v) {
+      mx = fmaxf(mx, fabsf(v * __ldg(col_scale + f)));
+      slot[f * 128] = v;
+    });
+    if (!(mx < 3.0e38f)) mx = 3.4e38f;   // NaN / inf rows quantise to zero
+    int e;
+    float sc, sc2;
+    i8_row_scale(live ? mx : 0.0f, I8_DIGITS, e, sc, sc2);          // rows beyond n_central (tile padding): zero digits
+    row_exp[atom_raw] = e;
+#pragma unroll 1
+    for (int kc = 0; kc < NFP; kc += 64) {
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        const int k0 = kc + g * 16;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (k0 + j < NF) ? slot[(k0 + j) * 128] : 0.0f;
+        uint32_t w[I8_DIGITS][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t ew[4], tb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + 4 * q + j;
+            const float c = (k < NF) ? __ldg(col_scale + k) : 0.0f;
+            ew[j] = i8_digit_word<I8_DIGITS>(sc != 0.0f ? ((v[4 * q + j] * c) * sc) * sc2 : 0.0f);
+          }
+          i8_transpose4(ew, tb);
+#pragma unroll
+          for (int d = 0; d < I8_DIGITS; ++d) w[d][q] = tb[I8_DIGITS - 1 - d];
+        }
+        const int piece = g ^ ((tid >> 1) & 3);   // 16-byte pieces of a row are xor-swizzled: conflict-free both ways
+#pragma unroll
+        for (int d = 0; d < I8_DIGITS; ++d)
+          *reinterpret_cast<uint4*>(&tile[d][tid * 64 + piece * 16]) = make_uint4(w[d][0], w[d][1], w[d][2], w[d][3]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int d = 0; d < I8_DIGITS; ++d) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int idx = tid + 128 * j, r = idx >> 2, p = idx & 3;
+          const uint4 val = *reinterpret_cast<const uint4*>(&tile[d][r * 64 + (p ^ ((r >> 1) & 3)) * 16]);
+          *reinterpret_cast<uint4*>(planes + d * plane_stride + (m0 + r) * int64_t(NFP) + kc + p * 16) = val;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kContractThreads, 256 / kContractThreads) k_contract_bwd(GmWorkspace ws) {
   const int64_t atom_raw = int64_t(blockIdx.x) * kContractThreads + threadIdx.x;
   const bool live = atom_raw < ws.n_central;
@@ -1328,7 +1403,13 @@ static int gm_descriptor_impl(cudaStream_t stream, const apax_gm_params_impl* p,
   APAX_LAUNCH(k_atom_pack, dim3((unsigned)cdiv(w.n_atoms, 256)), dim3(256), 0, stream, w, geo);
   APAX_DISPATCH_LPA(lpa, launch_pair_fwd, stream, w, geo, dc, p->pair_block);
   const dim3 grid_c((unsigned)cdiv(w.n_central, kContractThreads));
-  if (feature_mode == 1) {
+  if (feature_mode == 3) {
+    // fused with the layer-0 quantiser of the integer readout: persistent blocks, at most two per SM, one slot each
+    const int64_t n_tiles = cdiv(w.n_central, 128);
+    const int64_t blocks = n_tiles < 2 * int64_t(num_sms()) ? n_tiles : 2 * int64_t(num_sms());
+    APAX_LAUNCH(k_contract_fwd_quantize, dim3((unsigned)blocks), dim3(kContractThreads), 0, stream, w, w.q_cs, w.q_planes, w.q_row_exp,
+                n_tiles);
+  } else if (feature_mode == 1) {
     APAX_LAUNCH(k_contract_fwd<1>, grid_c, dim3(kContractThreads), 0, stream, w);
   } else if (feature_mode == 2) {
     APAX_LAUNCH(k_contract_fwd<2>, grid_c, dim3(kContractThreads), 0, stream, w);
@@ -1479,7 +1560,8 @@ static int readout_i8(cudaStream_t stream, const apax_gm_params_impl* p, const G
   int32_t* rowmax = i8_rowmax_buffer(w);   // filled by k_contract_fwd<2>
   const I8Planes w0{p->q_w0, NH, NFP, int64_t(NH) * NFP, 4}, w1{p->q_w1, NH, NH, int64_t(NH) * NH, 4};
   if (head < 0) {
-    APAX_TRY(i8_quantize_rows(stream, w.GT, ld, N, NF, NFP, 4, p->cs_g, gq, e_g, rowmax, /*have_rowmax=*/true, rows));
+    if (!w.q_planes)   // otherwise the contraction kernel has emitted the descriptor's digit planes and exponents itself
+      APAX_TRY(i8_quantize_rows(stream, w.GT, ld, N, NF, NFP, 4, p->cs_g, gq, e_g, rowmax, /*have_rowmax=*/true, rows));
     {  // layer 0: 360 -> 256; swish' kept in fp32 for the backward pass, swish goes on as digit planes
       const I8Planes act{gq, rows, NFP, ld * int64_t(NFP), 4};
       I8Epilogue e{};
@@ -1533,16 +1615,19 @@ static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
   const DescConst dc = make_desc_const(p->cfg);
   const int lpa = pick_lpa(N);
   const int mode = p->readout_mode;
+  GmWorkspace wq = w;
   auto readout = [&](int head) {
-    return mode == READOUT_I8   ? readout_i8(stream, p, w, geo, energy, head)
+    return mode == READOUT_I8   ? readout_i8(stream, p, wq, geo, energy, head)
            : mode == READOUT_TC ? readout_tc(stream, p, w, geo, energy, head)
                                 : readout_simt(stream, p, w, geo, energy, head);
   };
   if (mode == READOUT_I8) {
-    GmWorkspace wq = w;   // the contraction kernel leaves the row maxima of the scaled features for the quantiser
+    // the contraction kernel emits the layer-0 digit planes and row exponents itself (k_contract_fwd_quantize)
     wq.q_cs = p->cs_g;
     wq.q_rowmax = i8_rowmax_buffer(w);
-    APAX_TRY(gm_descriptor_impl(stream, p, wq, geo, 2));
+    wq.q_planes = reinterpret_cast<int8_t*>(w.GLT);
+    wq.q_row_exp = reinterpret_cast<int32_t*>(w.H1T + int64_t(MAX_OUT) * w.ld);     // e_g of readout_i8
+    APAX_TRY(gm_descriptor_impl(stream, p, wq, geo, 3));
   } else {
     APAX_TRY(gm_descriptor_impl(stream, p, w, geo, mode == READOUT_TC ? 1 : 0));
   }

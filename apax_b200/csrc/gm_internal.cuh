@@ -112,6 +112,8 @@ struct GmWorkspace {
   // integer tensor-core readout: the contraction kernel also leaves each atom's scaled feature maximum (set per call)
   const float* q_cs;   // [384] per-feature scales of layer 0, or null
   int32_t* q_rowmax;   // [ld] float bits of max_k |g[k] c[k]|
+  int8_t* q_planes;    // fused contraction + quantiser: layer-0 digit planes [4][ld][384] (null: separate quantiser)
+  int32_t* q_row_exp;  // ... and the row exponents [ld]
 };
 
 size_t carve_gm_workspace(void* base, int64_t n_atoms, int64_t n_pairs, int32_t n_out, int32_t n_species,

@@ -40,11 +40,6 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
   return (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float exp2_int(int e) {
-  if (e >= -126 && e <= 127) return __int_as_float((e + 127) << 23);
-  return ldexpf(1.0f, e);
-}
-
 // 1 / x for finite x >= 1: SFU approximation (1 ulp) + one Newton step
 __device__ __forceinline__ float rcp_newton(float x) {
   float r;
@@ -146,41 +141,6 @@ __device__ __forceinline__ void umma_i8_burst(uint32_t tm0, uint32_t tm1, uint32
       ::"r"(tm0), "r"(tm1), "r"(tm2), "r"(tm3), "l"(a00), "l"(a01), "l"(a02), "l"(a03), "l"(a10), "l"(a11), "l"(a12),
       "l"(a13), "l"(b0), "l"(b1), "r"(id256), "r"(id192), "r"(id128), "r"(id64), "r"(acc_first), "r"(have3), "r"(have_kb1)
       : "memory");
-}
-
-// ---- digits.  Balanced base-256 digits of I = rn(v), all at once: adding 128 to each low byte (with the
-// carries that produces) turns the balanced digits into offset-binary bytes, flipping their top bits back gives
-// two's complement.  P digits: byte P-1 = leading digit d0 ... byte 0 = d_{P-1}.
-template <int P>
-__device__ __forceinline__ uint32_t i8_digit_word(float v) {
-  constexpr uint32_t kOff = P == 4 ? 0x00808080u : 0x00008080u;
-  return (uint32_t(__float2int_rn(v)) + kOff) ^ kOff;   // |I| < 2^(8 P - 2)
-}
-// 4 x 4 byte transpose: words e[j] of elements j = 0..3  ->  tb[b] = byte b of the four elements (element 0 lowest)
-__device__ __forceinline__ void i8_transpose4(const uint32_t (&e)[4], uint32_t (&tb)[4]) {
-  const uint32_t t0 = __byte_perm(e[0], e[1], 0x5140);  // e0.b0 e1.b0 e0.b1 e1.b1
-  const uint32_t t1 = __byte_perm(e[2], e[3], 0x5140);
-  const uint32_t t2 = __byte_perm(e[0], e[1], 0x7362);  // e0.b2 e1.b2 e0.b3 e1.b3
-  const uint32_t t3 = __byte_perm(e[2], e[3], 0x7362);
-  tb[0] = __byte_perm(t0, t1, 0x5410);
-  tb[1] = __byte_perm(t0, t1, 0x7632);
-  tb[2] = __byte_perm(t2, t3, 0x5410);
-  tb[3] = __byte_perm(t2, t3, 0x7632);
-}
-
-// exponent e (row maximum 2^-e in [32, 64)) and two in-range powers of two whose product is 2^(8 (P - 1) - e)
-__device__ __forceinline__ void i8_row_scale(float mx, int P, int& e, float& sc, float& sc2) {
-  e = 0;
-  sc = 0.0f;
-  sc2 = 0.0f;                         // zero / padding / non-finite rows quantise to all-zero digits
-  if (mx > 0.0f && mx < 3.0e38f) {
-    int ex;
-    frexpf(mx, &ex);                  // mx = f 2^ex, f in [0.5, 1)
-    e = ex - 6;
-    const int tot = 8 * (P - 1) - e, h = tot / 2;
-    sc = exp2_int(h);
-    sc2 = exp2_int(tot - h);
-  }
 }
 
 // sixteen values (already multiplied by their column scales) -> four 16-byte plane pieces at planes + p * stride
