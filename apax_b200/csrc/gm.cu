@@ -51,7 +51,7 @@ size_t carve_gm_workspace(void* base, int64_t n_atoms, int64_t n_pairs, int32_t 
   w.sp_map = c.take<int32_t>(128);
   w.sp_z = c.take<int32_t>(128);
   w.n_sp = c.take<int32_t>(4);
-  w.embc = c.take<float>(int64_t(n_species) * n_species * EMB_STRIDE);
+  w.embc = c.take<float>(int64_t(n_species) * n_species * EMB_STRIDE_GEN);
   w.P = c.take<double4>(N + 1);
   w.G = c.take<float4>(P);
   w.D = c.take<float4>(P);
@@ -124,10 +124,11 @@ __global__ void __launch_bounds__(128) k_species_mark(const int32_t* __restrict_
   present[z] = 1;
 }
 
+// nb_gen = 0: the default table [35 -> 36] (7 Gaussians); nb_gen > 0: generic [5][16] rows of nb_gen coefficients, zero padded
 __global__ void __launch_bounds__(256) k_species_build(const int32_t* __restrict__ present, int S,
                                                        const float* __restrict__ emb, int32_t* __restrict__ sp_map,
                                                        int32_t* __restrict__ n_sp_out, float* __restrict__ embc,
-                                                       int32_t* __restrict__ sp_z) {
+                                                       int32_t* __restrict__ sp_z, int nb_gen) {
   __shared__ int zs[128];
   __shared__ int n_sp;
   if (threadIdx.x == 0) {
@@ -145,6 +146,15 @@ __global__ void __launch_bounds__(256) k_species_build(const int32_t* __restrict
     *n_sp_out = n;
   }
   __syncthreads();
+  if (nb_gen > 0) {
+    const int total = n_sp * n_sp * EMB_STRIDE_GEN;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int pair = i / EMB_STRIDE_GEN, k = i % EMB_STRIDE_GEN, rr = k / MAXNB_GEN, bb = k % MAXNB_GEN;
+      const int a = pair / n_sp, b = pair % n_sp;
+      embc[i] = bb < nb_gen ? emb[(int64_t(zs[a]) * S + zs[b]) * (NR * nb_gen) + rr * nb_gen + bb] : 0.0f;
+    }
+    return;
+  }
   const int total = n_sp * n_sp * EMB_STRIDE;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int pair = i / EMB_STRIDE, k = i % EMB_STRIDE;
@@ -217,7 +227,7 @@ static int gm_prepare_tail(cudaStream_t stream, const apax_gm_params_impl* p, co
   }
   APAX_CUDA_TRY(cudaMemsetAsync(w.sp_present, 0, sizeof(int32_t) * 128, stream));
   APAX_LAUNCH(k_species_mark, dim3((unsigned)cdiv(N, 128)), dim3(128), 0, stream, Z, N, S, w.sp_present);
-  APAX_LAUNCH(k_species_build, dim3(1), dim3(256), 0, stream, w.sp_present, S, p->emb, w.sp_map, w.n_sp, w.embc, w.sp_z);
+  APAX_LAUNCH(k_species_build, dim3(1), dim3(256), 0, stream, w.sp_present, S, p->emb, w.sp_map, w.n_sp, w.embc, w.sp_z, p->generic_basis ? p->cfg.n_basis : 0);
   return APAX_OK;
 }
 
@@ -255,7 +265,7 @@ int gm_prepare_from_csr(cudaStream_t stream, const apax_gm_params_impl* p, const
   const int S = p->cfg.n_species;
   APAX_CUDA_TRY(cudaMemsetAsync(w.sp_present, 0, sizeof(int32_t) * 128, stream));
   APAX_LAUNCH(k_species_mark, dim3((unsigned)cdiv(N, 128)), dim3(128), 0, stream, Z, N, S, w.sp_present);
-  APAX_LAUNCH(k_species_build, dim3(1), dim3(256), 0, stream, w.sp_present, S, p->emb, w.sp_map, w.n_sp, w.embc, w.sp_z);
+  APAX_LAUNCH(k_species_build, dim3(1), dim3(256), 0, stream, w.sp_present, S, p->emb, w.sp_map, w.n_sp, w.embc, w.sp_z, p->generic_basis ? p->cfg.n_basis : 0);
   return APAX_OK;
 }
 
@@ -269,7 +279,82 @@ struct DescConst {
   float two_beta;
   float pi_f;       // float(np.pi)
   float mu[NB];     // r_min + (r_max-r_min)/n_basis * b (:25-27)
+  // generic radial bases (pair kernels with GEN = 1): kind as apax_gm_config.basis_kind, nb <= 16 functions
+  int kind, nb;
+  float mu_gen[MAXNB_GEN];   // Gaussian centres (in r, or in exp(-r) for the exponential spacing); Bessel: prefactors a_n b_n
 };
+
+// Radial functions of the generic bases for one distance: rho_r = f_c(r) sum_b c[r][b] basis_b(r) and (GRAD) d rho_r / dr.
+//   kind 0 / 1  GaussianBasis, linear / exponential spacing (basis_functions.py:19-56)
+//   kind 2      BesselBasis (:59-79): a_n (sinc((n+1) r/rc) + sinc((n+2) r/rc)) -- the nb + 1 sines and cosines come from ONE
+//               sincos(pi r / rc) and the Chebyshev recurrence sin((k+1)t) = 2 cos t sin(kt) - sin((k-1)t) (fp32 error
+//               3.4e-8 of max|basis| against 2.7e-8 for the reference's direct evaluation)
+// c: this species pair's [5][16] table (shared or global memory).  Returns false beyond the cutoff (everything zero).
+template <bool GRAD>
+__device__ __forceinline__ bool radial_gen(const DescConst& dc, const float* __restrict__ c, float r, float (&rho)[NR],
+                                           float (&drho)[NR]) {
+  if (!(r < dc.r_max)) return false;
+  float G[MAXNB_GEN], dG[MAXNB_GEN];
+  if (dc.kind == 2) {
+    const float th = dc.pi_f * r / dc.r_max;
+    float s1, c1;
+    sincosf(th, &s1, &c1);
+    const float two_c = 2.0f * c1;
+    float s_prev = 0.0f, c_prev = 1.0f, s_cur = s1, c_cur = c1;   // k = 0, 1
+    float sk_prev = 0.0f, dk_prev = 0.0f;
+#pragma unroll
+    for (int k = 1; k <= MAXNB_GEN + 1; ++k) {
+      if (k <= dc.nb + 1) {
+        const float y = float(k) * th;
+        const float sk = y != 0.0f ? s_cur / y : 1.0f;                 // jnp.sinc(k r / rc)
+        const float dk = r > 0.0f ? (c_cur - sk) / r : 0.0f;           // d/dr sinc(k r / rc) = (cos(k t) - sinc) / r
+        if (k >= 2) {
+          G[k - 2] = dc.mu_gen[k - 2] * (sk_prev + sk);
+          if (GRAD) dG[k - 2] = dc.mu_gen[k - 2] * (dk_prev + dk);
+        }
+        sk_prev = sk; dk_prev = dk;
+        const float s_next = fmaf(two_c, s_cur, -s_prev), c_next = fmaf(two_c, c_cur, -c_prev);
+        s_prev = s_cur; c_prev = c_cur; s_cur = s_next; c_cur = c_next;
+      } else if (k >= 2) {
+        G[k - 2] = 0.0f;
+        if (GRAD) dG[k - 2] = 0.0f;
+      }
+    }
+  } else {
+    const float x = dc.kind == 1 ? expf(-r) : r;
+    const float dxdr = dc.kind == 1 ? -x : 1.0f;
+#pragma unroll
+    for (int b = 0; b < MAXNB_GEN; ++b) {
+      if (b < dc.nb) {
+        const float dm = dc.mu_gen[b] - x;
+        G[b] = dc.norm * expf(-dc.beta * (dm * dm));
+        if (GRAD) dG[b] = G[b] * dc.two_beta * dm * dxdr;
+      } else {
+        G[b] = 0.0f;
+        if (GRAD) dG[b] = 0.0f;
+      }
+    }
+  }
+  float sn, cs;
+  sincosf(dc.pi_f * r / dc.r_max, &sn, &cs);
+  const float fc = 0.5f * (cs + 1.0f);
+  const float fcp = -0.5f * (dc.pi_f / dc.r_max) * sn;
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr) {
+    float pr = 0.0f, qr = 0.0f;
+#pragma unroll
+    for (int q = 0; q < MAXNB_GEN / 4; ++q) {
+      const float4 cv = *reinterpret_cast<const float4*>(c + rr * MAXNB_GEN + 4 * q);
+      pr = fmaf(cv.x, G[4 * q], pr); pr = fmaf(cv.y, G[4 * q + 1], pr); pr = fmaf(cv.z, G[4 * q + 2], pr); pr = fmaf(cv.w, G[4 * q + 3], pr);
+      if (GRAD) {
+        qr = fmaf(cv.x, dG[4 * q], qr); qr = fmaf(cv.y, dG[4 * q + 1], qr); qr = fmaf(cv.z, dG[4 * q + 2], qr); qr = fmaf(cv.w, dG[4 * q + 3], qr);
+      }
+    }
+    rho[rr] = pr * fc;
+    if (GRAD) drho[rr] = fmaf(fcp, pr, fc * qr);
+  }
+  return true;
+}
 
 struct PairGeom {
   const double* R;
@@ -335,11 +420,11 @@ __device__ __forceinline__ void monomials(float x, float y, float z, float (&mon
   mono[15] = xz * z; mono[16] = yy * y; mono[17] = yy * z; mono[18] = yz * z; mono[19] = zz * z;
 }
 
-__device__ __forceinline__ const float* stage_species_table(const GmWorkspace& ws, float* s_emb) {
+__device__ __forceinline__ const float* stage_species_table(const GmWorkspace& ws, float* s_emb, int stride = EMB_STRIDE) {
   const int n_sp = *ws.n_sp;
   const float* emb = ws.embc;
   if (n_sp <= MAX_SP_SMEM) {
-    const int total = n_sp * n_sp * EMB_STRIDE;
+    const int total = n_sp * n_sp * stride;
     for (int i = threadIdx.x; i < total; i += blockDim.x) s_emb[i] = ws.embc[i];
     emb = s_emb;
   }
@@ -375,7 +460,7 @@ __global__ void __launch_bounds__(256) k_atom_pack(GmWorkspace ws, PairGeom geo)
 // F2 = 1: the 100 accumulations per pair are issued as 50 packed FFMA2 (fma.rn.f32x2, sm_100): the same roundings element
 // by element (results are bitwise those of F2 = 0), half the issue slots -- a scalar three-register FFMA issues at 0.57 per
 // clock and sub-partition on a B200 (tools/probes/probe_ffma2.cu: 42 Tflop/s), FFMA2 carries 1.56x the flops.
-template <int LPA, int BT, int MINB, int SPEC, int F2>
+template <int LPA, int BT, int MINB, int SPEC, int F2, int GEN = 0>
 __device__ __forceinline__ void pair_fwd_body(const GmWorkspace& ws, const PairGeom& geo, const DescConst& dc,
                                               const float* __restrict__ emb, const double* box, int n_sp,
                                               double* ra) {
@@ -449,23 +534,32 @@ __device__ __forceinline__ void pair_fwd_body(const GmWorkspace& ws, const PairG
     const float r = r2 > 0.0f ? sqrtf(r2) : 0.0f;  // space.distance + safe_mask (space.py:314-323)
     if (r >= dc.r_max) continue;                   // cosine cutoff is exactly 0 there (basis_functions.py:82-85)
     const float s = 1.0f / (r + 1e-5f);            // dn = dr_vec / (dr + 1e-5) (gaussian_moment_descriptor.py:46-48)
-    float c[EMB_STRIDE];
-    load_coeffs(emb, pt, c);
-    float gb[NB];
+    float rho_v[NR], unused_d[NR];
+    if (GEN) {   // Bessel / exponential spacing / n_basis != 7: coefficients stay in the [5][16] table, basis by radial_gen
+      radial_gen<false>(dc, emb + pt * EMB_STRIDE_GEN, r, rho_v, unused_d);
+    } else {
+      float c[EMB_STRIDE];
+      load_coeffs(emb, pt, c);
+      float gb[NB];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const float t = dc.mu[b] - r;
-      gb[b] = dc.norm * expf(-dc.beta * (t * t));
+      for (int b = 0; b < NB; ++b) {
+        const float t = dc.mu[b] - r;
+        gb[b] = dc.norm * expf(-dc.beta * (t * t));
+      }
+      const float fc = 0.5f * (cosf(dc.pi_f * r / dc.r_max) + 1.0f);
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        float pr = 0.0f;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) pr = fmaf(c[rr * NB + b], gb[b], pr);
+        rho_v[rr] = pr * fc;
+      }
     }
-    const float fc = 0.5f * (cosf(dc.pi_f * r / dc.r_max) + 1.0f);
     float mono[20];
     monomials(dx * s, dy * s, dz * s, mono);
 #pragma unroll
     for (int rr = 0; rr < NR; ++rr) {
-      float pr = 0.0f;
-#pragma unroll
-      for (int b = 0; b < NB; ++b) pr = fmaf(c[rr * NB + b], gb[b], pr);
-      const float rho = pr * fc;
+      const float rho = rho_v[rr];
       if (F2) {
         const float2 rho2 = make_float2(rho, rho);
 #pragma unroll
@@ -492,7 +586,7 @@ __device__ __forceinline__ void pair_fwd_body(const GmWorkspace& ws, const PairG
 // ---- backward: per-pair dE/d(dr_vec) from the packed moment adjoints of the central atom.  Pair
 // terms are recomputed from the stored fp32 displacement; nothing per-pair other than (dx,dy,dz) was
 // kept from the forward pass.  Also leaves the row sum (fp64) of the central atom in Frow.
-template <int LPA, int BT, int MINB, int F2>
+template <int LPA, int BT, int MINB, int F2, int GEN = 0>
 __device__ __forceinline__ void pair_bwd_body(const GmWorkspace& ws, const DescConst& dc, const float* __restrict__ emb) {
   const int64_t gid = int64_t(blockIdx.x) * BT + threadIdx.x;
   const int64_t atom = gid / LPA;
@@ -525,20 +619,36 @@ __device__ __forceinline__ void pair_bwd_body(const GmWorkspace& ws, const DescC
     if (r < dc.r_max) {
       const float s = 1.0f / (r + 1e-5f);
       const float x = dx * s, y = dy * s, z = dz * s;
-      float c[EMB_STRIDE];
-      load_coeffs(emb, pt, c);
-      float gb[NB], gd[NB];
+      float rho_v[NR], drho_v[NR];
+      if (GEN) {
+        radial_gen<true>(dc, emb + pt * EMB_STRIDE_GEN, r, rho_v, drho_v);
+      } else {
+        float c[EMB_STRIDE];
+        load_coeffs(emb, pt, c);
+        float gb[NB], gd[NB];
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        const float t = dc.mu[b] - r;
-        gb[b] = dc.norm * expf(-dc.beta * (t * t));
-        gd[b] = gb[b] * (dc.two_beta * t);  // dG_b/dr
+        for (int b = 0; b < NB; ++b) {
+          const float t = dc.mu[b] - r;
+          gb[b] = dc.norm * expf(-dc.beta * (t * t));
+          gd[b] = gb[b] * (dc.two_beta * t);  // dG_b/dr
+        }
+        float sn, cs;
+        const float arg = dc.pi_f * r / dc.r_max;
+        sincosf(arg, &sn, &cs);
+        const float fc = 0.5f * (cs + 1.0f);
+        const float fcp = -0.5f * (dc.pi_f / dc.r_max) * sn;
+#pragma unroll
+        for (int rr = 0; rr < NR; ++rr) {
+          float pr = 0.0f, qr = 0.0f;
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            pr = fmaf(c[rr * NB + b], gb[b], pr);
+            qr = fmaf(c[rr * NB + b], gd[b], qr);
+          }
+          rho_v[rr] = pr * fc;
+          drho_v[rr] = fmaf(fcp, pr, fc * qr);  // d rho_r / dr
+        }
       }
-      float sn, cs;
-      const float arg = dc.pi_f * r / dc.r_max;
-      sincosf(arg, &sn, &cs);
-      const float fc = 0.5f * (cs + 1.0f);
-      const float fcp = -0.5f * (dc.pi_f / dc.r_max) * sn;
       float mono[20];
       monomials(x, y, z, mono);
       float2 B2[10];
@@ -548,14 +658,7 @@ __device__ __forceinline__ void pair_bwd_body(const GmWorkspace& ws, const DescC
       float rbar = 0.0f;
 #pragma unroll
       for (int rr = 0; rr < NR; ++rr) {
-        float pr = 0.0f, qr = 0.0f;
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          pr = fmaf(c[rr * NB + b], gb[b], pr);
-          qr = fmaf(c[rr * NB + b], gd[b], qr);
-        }
-        const float rho = pr * fc;
-        const float drho = fmaf(fcp, pr, fc * qr);  // d rho_r / dr
+        const float rho = rho_v[rr], drho = drho_v[rr];
         float rhobar = 0.0f;
         if (F2) {   // packed: even and odd monomials in the two halves, joined at the end (20 terms: well inside the fp32 noise budget)
           const float2 rho2 = make_float2(rho, rho);
@@ -604,30 +707,30 @@ __device__ __forceinline__ void pair_bwd_body(const GmWorkspace& ws, const DescC
   }
 }
 
-template <int LPA, int BT, int MINB, int SPEC, int F2 = 0>
+template <int LPA, int BT, int MINB, int SPEC, int F2 = 0, int GEN = 0>
 __global__ void __launch_bounds__(BT, MINB) k_pair_fwd(GmWorkspace ws, PairGeom geo, DescConst dc) {
-  __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * EMB_STRIDE];
+  __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * (GEN ? EMB_STRIDE_GEN : EMB_STRIDE)];
   __shared__ double box[9];
   __shared__ double s_ra[3 * BT];
   const bool plain = SPEC ? false : (geo.mode == APAX_DISP_GAS || geo.mode == APAX_DISP_DRVEC);
   if (threadIdx.x < 9)
     box[threadIdx.x] = plain ? ((threadIdx.x % 4 == 0 && geo.mode == APAX_DISP_GAS) ? 1.0 : 0.0) : __ldg(geo.box + threadIdx.x);
-  stage_species_table(ws, s_emb);
+  stage_species_table(ws, s_emb, GEN ? EMB_STRIDE_GEN : EMB_STRIDE);
   const int n_sp = *ws.n_sp;
   if (n_sp <= MAX_SP_SMEM) {
-    pair_fwd_body<LPA, BT, MINB, SPEC, F2>(ws, geo, dc, s_emb, box, n_sp, s_ra);
+    pair_fwd_body<LPA, BT, MINB, SPEC, F2, GEN>(ws, geo, dc, s_emb, box, n_sp, s_ra);
   } else {
-    pair_fwd_body<LPA, BT, MINB, SPEC, F2>(ws, geo, dc, ws.embc, box, n_sp, s_ra);
+    pair_fwd_body<LPA, BT, MINB, SPEC, F2, GEN>(ws, geo, dc, ws.embc, box, n_sp, s_ra);
   }
 }
-template <int LPA, int BT, int MINB, int F2 = 0>
+template <int LPA, int BT, int MINB, int F2 = 0, int GEN = 0>
 __global__ void __launch_bounds__(BT, MINB) k_pair_bwd(GmWorkspace ws, DescConst dc) {
-  __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * EMB_STRIDE];
-  stage_species_table(ws, s_emb);
+  __shared__ __align__(16) float s_emb[MAX_SP_SMEM * MAX_SP_SMEM * (GEN ? EMB_STRIDE_GEN : EMB_STRIDE)];
+  stage_species_table(ws, s_emb, GEN ? EMB_STRIDE_GEN : EMB_STRIDE);
   if (*ws.n_sp <= MAX_SP_SMEM) {
-    pair_bwd_body<LPA, BT, MINB, F2>(ws, dc, s_emb);
+    pair_bwd_body<LPA, BT, MINB, F2, GEN>(ws, dc, s_emb);
   } else {
-    pair_bwd_body<LPA, BT, MINB, F2>(ws, dc, ws.embc);
+    pair_bwd_body<LPA, BT, MINB, F2, GEN>(ws, dc, ws.embc);
   }
 }
 // ---- force assembly: F_a = -( sum_{e: central a} dbar_e  -  sum_{e: neighbour a} dbar_e ), both sums
@@ -1319,8 +1422,33 @@ static DescConst make_desc_const(const apax_gm_config& cfg) {
   dc.pi_f = float(M_PI);
   for (int b = 0; b < NB; ++b)
     dc.mu[b] = float(double(cfg.r_min) + (double(cfg.r_max) - double(cfg.r_min)) / cfg.n_basis * b);
+  // generic bases (constants as apax_train_plan_create derives them for the table-driven kernels)
+  const int nb = cfg.n_basis;
+  const double r_min = cfg.r_min, r_max = cfg.r_max;
+  dc.kind = cfg.basis_kind;
+  dc.nb = nb;
+  for (int b = 0; b < MAXNB_GEN; ++b) dc.mu_gen[b] = 0.0f;
+  if (cfg.basis_kind == 0) {                                   // GaussianBasis, linear spacing (basis_functions.py:22-28)
+    for (int b = 0; b < nb && b < MAXNB_GEN; ++b) dc.mu_gen[b] = float(r_min + (r_max - r_min) / nb * b);
+  } else if (cfg.basis_kind == 1) {                            // exponential spacing (:29-37)
+    const double be = pow(2.0 / nb * (exp(-r_min) - exp(-r_max)), -2.0);
+    dc.beta = float(be);
+    dc.two_beta = float(2.0 * be);
+    dc.norm = 1.0f;
+    for (int b = 0; b < nb && b < MAXNB_GEN; ++b)
+      dc.mu_gen[b] = float(nb > 1 ? exp(-r_max) + (exp(-r_min) - exp(-r_max)) * b / (nb - 1) : exp(-r_max));   // np.linspace
+  } else {                                                     // BesselBasis (:72-78; b_n is 1: the square root is of the PRODUCT)
+    dc.norm = 1.0f;
+    for (int n = 0; n < nb && n < MAXNB_GEN; ++n) {
+      const double a = ((n & 1) ? -1.0 : 1.0) * (sqrt(2.0) * M_PI / pow(r_max, 1.5));
+      const double bb = double(n + 1) * (n + 2) / sqrt(double(n + 1) * (n + 1) * double(n + 2) * (n + 2));
+      dc.mu_gen[n] = float(float(a) * float(bb));
+    }
+  }
   return dc;
 }
+
+constexpr int kPairGeneric = 100;   // launch variant of the generic-basis pair kernels
 
 static int pick_lpa(int64_t n_atoms) {
   if (n_atoms >= 100000) return 4;
@@ -1350,6 +1478,15 @@ static int launch_pair_fwd_shape(cudaStream_t s, const GmWorkspace& w, const Pai
 }
 template <int LPA>
 static int launch_pair_fwd(cudaStream_t s, const GmWorkspace& w, const PairGeom& geo, const DescConst& dc, int variant) {
+  if (variant == kPairGeneric) {   // Bessel / exponential-spacing / n_basis != 7 models
+    const dim3 grid((unsigned)cdiv(w.n_central * LPA, 128));
+    if (geo.mode == APAX_DISP_MINIMAGE && !geo.offsets) {
+      APAX_LAUNCH_AS("k_pair_fwd_gen<LPA>", (k_pair_fwd<LPA, 128, 3, 1, 1, 1>), grid, dim3(128), 0, s, w, geo, dc);
+    } else {
+      APAX_LAUNCH_AS("k_pair_fwd_gen<LPA>", (k_pair_fwd<LPA, 128, 3, 0, 1, 1>), grid, dim3(128), 0, s, w, geo, dc);
+    }
+    return APAX_OK;
+  }
   switch (variant) {
     case 0: return launch_pair_fwd_shape<LPA, 256, 1>(s, w, geo, dc);
     case 2: return launch_pair_fwd_shape<LPA, 128, 4>(s, w, geo, dc);
@@ -1359,6 +1496,10 @@ static int launch_pair_fwd(cudaStream_t s, const GmWorkspace& w, const PairGeom&
 }
 template <int LPA>
 static int launch_pair_bwd(cudaStream_t s, const GmWorkspace& w, const DescConst& dc, int variant) {
+  if (variant == kPairGeneric) {
+    APAX_LAUNCH_AS("k_pair_bwd_gen<LPA>", (k_pair_bwd<LPA, 128, 3, 0, 1>), dim3((unsigned)cdiv(w.n_central * LPA, 128)), dim3(128), 0, s, w, dc);
+    return APAX_OK;
+  }
   switch (variant) {
     case 0: APAX_LAUNCH_AS("k_pair_bwd<LPA>", (k_pair_bwd<LPA, 256, 1>), dim3((unsigned)cdiv(w.n_central * LPA, 256)), dim3(256), 0, s, w, dc); break;
     case 2: APAX_LAUNCH_AS("k_pair_bwd<LPA>", (k_pair_bwd<LPA, 128, 4>), dim3((unsigned)cdiv(w.n_central * LPA, 128)), dim3(128), 0, s, w, dc); break;
@@ -1401,7 +1542,7 @@ static int gm_descriptor_impl(cudaStream_t stream, const apax_gm_params_impl* p,
   const DescConst dc = make_desc_const(p->cfg);
   const int lpa = pick_lpa(w.n_central);
   APAX_LAUNCH(k_atom_pack, dim3((unsigned)cdiv(w.n_atoms, 256)), dim3(256), 0, stream, w, geo);
-  APAX_DISPATCH_LPA(lpa, launch_pair_fwd, stream, w, geo, dc, p->pair_block);
+  APAX_DISPATCH_LPA(lpa, launch_pair_fwd, stream, w, geo, dc, (p->generic_basis ? kPairGeneric : p->pair_block));
   const dim3 grid_c((unsigned)cdiv(w.n_central, kContractThreads));
   if (feature_mode == 3) {
     // fused with the layer-0 quantiser of the integer readout: persistent blocks, at most two per SM, one slot each
@@ -1643,7 +1784,7 @@ static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
     // every backward pass reads only what the forward pass left behind (D1, D2 / its planes, ebar): nothing to redo
     APAX_TRY(readout(head));
     APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(N, kContractThreads)), dim3(kContractThreads), 0, stream, w);
-    APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc, p->pair_block);
+    APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc, (p->generic_basis ? kPairGeneric : p->pair_block));
     if (p->corr.zbl_on || p->corr.exp_on)
       APAX_LAUNCH(k_pair_corrections<1>, dim3((unsigned)cdiv(N * 32, 256)), dim3(256), 0, stream, w, geo, p->corr, n_out);
     APAX_DISPATCH_LPA(pick_lpa(w.n_atoms), launch_force_gather, stream, w, forces + int64_t(pass) * w.n_atoms * 3);
@@ -1669,11 +1810,12 @@ using namespace apax;
 
 static int validate_cfg(const apax_gm_config* c) {
   if (!c) return APAX_ERR_INVALID_ARG;
-  if (c->n_radial != NR || c->n_basis != NB || c->n_contr < 1 || c->n_contr > 8 || c->n_hidden1 != NH || c->n_hidden2 != NH)
+  if (c->n_radial != NR || c->n_basis < 1 || c->n_basis > MAXNB_GEN || c->n_contr < 1 || c->n_contr > 8 || c->n_hidden1 != NH ||
+      c->n_hidden2 != NH)
     return APAX_ERR_UNSUPPORTED;
   if (c->n_out < 1 || c->n_out > MAX_OUT || c->n_species < 1 || c->n_species > 128) return APAX_ERR_UNSUPPORTED;
   if (!(c->r_max > c->r_min) || !(c->r_min >= 0.f)) return APAX_ERR_INVALID_ARG;
-  if (c->basis_kind != 0) return APAX_ERR_UNSUPPORTED;   // other radial bases: apax_train_energy_forces
+  if (c->basis_kind < 0 || c->basis_kind > 2) return APAX_ERR_UNSUPPORTED;
   return APAX_OK;
 }
 
@@ -1694,6 +1836,7 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
   apax_gm_params* p = new apax_gm_params();
   p->cfg = *cfg;
   p->readout_mode = APAX_READOUT_I8;
+  p->generic_basis = (cfg->basis_kind != 0 || cfg->n_basis != NB) ? 1 : 0;   // pair kernels with the [5][16] coefficient table
   p->pair_block = 1;
   p->mean_forces = 0;
   const int S = cfg->n_species, n_out = cfg->n_out;
@@ -1709,7 +1852,7 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
   auto wf = [&](int fan_in) { return cfg->use_ntk ? float(sqrt(1.0 / fan_in)) : 1.0f; };
   const float bf = cfg->use_ntk ? 0.1f : 1.0f;
   {
-    const size_t n = size_t(S) * S * NR * NB;
+    const size_t n = size_t(S) * S * NR * cfg->n_basis;
     float* h = new float[n];
     const float sc = cfg->use_embed_norm ? float(1.0 / sqrt(double(cfg->n_basis))) : 1.0f;
     for (size_t i = 0; i < n; ++i) h[i] = sc * emb[i];  // embed_norm * coeffs (basis_functions.py:145-146)
@@ -2007,12 +2150,12 @@ extern "C" int apax_gm_descriptor_vjp(apax_stream_t stream_, const apax_gm_param
   const int lpa = pick_lpa(w.n_central);
   // forward pair pass: the packed moments (the contractions are polynomial in them) and the per-pair displacements
   APAX_LAUNCH(k_atom_pack, dim3((unsigned)cdiv(w.n_atoms, 256)), dim3(256), 0, stream, w, geo);
-  APAX_DISPATCH_LPA(lpa, launch_pair_fwd, stream, w, geo, dc, p->pair_block);
+  APAX_DISPATCH_LPA(lpa, launch_pair_fwd, stream, w, geo, dc, (p->generic_basis ? kPairGeneric : p->pair_block));
   // reverse: g_bar -> moment adjoints -> per-pair dE/d(dr_vec)
   APAX_LAUNCH(k_features_from_rowmajor, dim3((unsigned)cdiv(w.ld, 32), cdiv(NF, 32)), dim3(256), 0, stream, g_bar, w.ld, n_atoms,
               w.GT);
   APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(w.n_central, kContractThreads)), dim3(kContractThreads), 0, stream, w);
-  APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc, p->pair_block);
+  APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc, (p->generic_basis ? kPairGeneric : p->pair_block));
   if (dr_vec_bar) {
     APAX_CUDA_TRY(cudaMemsetAsync(dr_vec_bar, 0, sizeof(double) * 3 * size_t(n_pairs), stream));
     if (n_pairs > 0)

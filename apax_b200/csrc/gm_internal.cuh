@@ -11,6 +11,8 @@ constexpr int NF = 360;      // descriptor features
 constexpr int NFP = 384;     // feature rows padded to a multiple of the GEMM tile
 constexpr int NH = 256;      // hidden width
 constexpr int EMB_STRIDE = 36;  // 35 coefficients padded to 9 float4
+constexpr int MAXNB_GEN = 16;   // generic radial bases (Bessel, exponential spacing, n_basis != 7): up to 16 functions
+constexpr int EMB_STRIDE_GEN = NR * MAXNB_GEN;   // [5][16] coefficients per species pair, zero padded
 constexpr int MAX_SP_SMEM = 8;  // compact species tables up to 8x8 are staged in shared memory
 constexpr int MAX_OUT = 16;
 
@@ -30,6 +32,7 @@ struct apax_gm_params_impl {
   CorrConst corr;                 // all zero: no corrections
   int readout_mode;               // APAX_READOUT_* (apax_gm_params_set_option)
   int pair_block;                 // block shape of the pair kernels, 0..2 (measurement switch)
+  int generic_basis;              // radial basis other than the 7 linearly spaced Gaussians: pair kernels with GEN = 1
   int mean_forces;                // n_out > 1: forces[1][N][3] of the MEAN energy in one backward pass instead of per head
   // device copies
   float* emb;    // [S][S][5][7], pre-multiplied by 1/sqrt(n_basis) when use_embed_norm

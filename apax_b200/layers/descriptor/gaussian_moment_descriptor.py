@@ -71,10 +71,6 @@ class GaussianMomentDescriptor:
         """variables = {"params": {"radial_fn": {"atomic_type_embedding": [S,S,5,7]}}} as flax would pass it."""
         emb = variables["params"]["radial_fn"]["atomic_type_embedding"]
         st = self.statics()
-        if st["basis_kind"] != 0 or st["n_basis"] != 7:
-            raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "GaussianMomentDescriptor.apply",
-                                        "the stand-alone descriptor entry point covers the default basis only; Bessel / exponential "
-                                        "bases are evaluated through the model (apax_train_energy_forces)")
         dp = _descriptor_params(emb, st)
         return rt.descriptor(dp, dr_vec, Z, neighbor_idxs, mode="drvec")
 
@@ -84,8 +80,6 @@ class GaussianMomentDescriptor:
         (apax_b200/ffi/jax_binding.py::descriptor)."""
         emb = variables["params"]["radial_fn"]["atomic_type_embedding"]
         st = self.statics()
-        if st["basis_kind"] != 0 or st["n_basis"] != 7:
-            raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "GaussianMomentDescriptor.vjp", "default basis only")
         dp = _descriptor_params(emb, st)
         return rt.descriptor_vjp(dp, dr_vec, Z, neighbor_idxs, g_bar, mode="drvec")[0]
 
@@ -104,6 +98,6 @@ def _descriptor_params(emb, statics):
                             "dense_2": {"w": zeros(256, 1), "b": zeros(1)}},
                 "scale_shift": {"scale_per_element": np.ones((statics["n_species"], 1)),
                                 "shift_per_element": np.zeros((statics["n_species"], 1))}}
-        cfg = {k: statics[k] for k in ("n_basis", "r_min", "r_max", "n_radial", "use_embed_norm", "n_contr")}
+        cfg = {k: statics[k] for k in ("n_basis", "r_min", "r_max", "n_radial", "use_embed_norm", "n_contr", "basis_kind")}
         _cache[key] = rt.DeviceParams(tree, cfg)
     return _cache[key]

@@ -107,14 +107,8 @@ class EnergyModel:
     def _run(self, params, R, Z, neighbor, box, offsets, forces: bool):
         mode = displacement_mode(self.init_box, self.inference_disp_fn)
         st = self.statics()
-        if (st["basis_kind"] != 0 or st["n_basis"] != 7) and self.corrections:
-            raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "EnergyModel", "empirical corrections with a non-default basis")
-        if st["basis_kind"] != 0 or st["n_basis"] != 7:
-            # Bessel / exponential-spacing bases: the table-driven kernels behind apax_train_*
-            from ..train.trainer import table_model
-
-            e, f = table_model(params, st).energy_forces(R, Z, canonicalize_neighbors(neighbor), box, offsets, mode)
-            return e, f[None]
+        # every radial basis (7 Gaussians, Bessel, exponential spacing, n_basis <= 16) runs on the fused pair kernels and the
+        # integer tensor-core readout; the table-driven kernels behind apax_train_* serve training only
         dp = device_params(params, st)
         return rt.energy_forces(dp, R, Z, canonicalize_neighbors(neighbor), box, offsets, mode, forces=forces)
 
@@ -140,9 +134,8 @@ class EnergyDerivativeModel:
             em = self.energy_model
             mode = displacement_mode(em.init_box, em.inference_disp_fn)
             st = em.statics()
-            if mode not in ("minimage", "offsets") or st["basis_kind"] != 0 or st["n_basis"] != 7:
-                raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "EnergyDerivativeModel",
-                                            "calc_stress: periodic displacement with the default basis only")
+            if mode not in ("minimage", "offsets"):
+                raise rt._lib.ApaxB200Error(rt._lib.ERR_UNSUPPORTED, "EnergyDerivativeModel", "calc_stress needs a periodic displacement")
             e, f, s = rt.energy_forces(device_params(params, st), R, Z, canonicalize_neighbors(neighbor), box, offsets, mode,
                                        stress=True)
             return {"energy": e[0], "forces": f[0], "stress": s}

@@ -1,5 +1,6 @@
 """the Bessel basis (apax's config-file default: n_basis = 16, r_max = 5) and the exponentially
-spaced Gaussian basis, evaluated by the table-driven kernels (apax_train_energy_forces / apax_train_loss_and_grad), against
+spaced Gaussian basis, evaluated by the fused pair kernels + integer readout (energy+forces) and by the table-driven training kernels
+(apax_train_loss_and_grad), against
 the fixture written by the reference's OWN BesselBasis / GaussianBasis source (tests/golden/basis_variants.npz) and the
 oracle (energy+forces and training gradients)."""
 import numpy as np
@@ -67,3 +68,43 @@ def test_bessel_training_gradients_vs_oracle():
         scale = np.abs(r).max() + 1e-30
         assert np.abs(g - r).max() <= 2e-5 * scale, k
         assert np.abs(g - t).max() <= 2.0 * np.abs(r - t).max() + 2e-6 * scale, k
+
+
+@pytest.mark.parametrize("name,n_basis", [("bessel", 16), ("bessel", 9), ("gexp", 7), ("glin", 12)])
+def test_generic_basis_fast_path_min_image_vs_oracle_and_table_kernels(name, n_basis):
+    """The generic-basis pair kernels (coefficients in a [5][16] table, Bessel through one sincos + the Chebyshev recurrence)
+    on a 1,536-atom min-image water box: descriptor features, energy and forces against the oracle in reference precision
+    and fp64, and against the table-driven kernels (apax_train_energy_forces) that evaluate the basis directly."""
+    from apax_b200 import runtime as rt
+    from apax_b200.train.trainer import table_model
+    from oracle import gmnn_oracle as go
+    from oracle import neighbor_oracle as no
+
+    ocfg = {"bessel": dict(basis="bessel", n_basis=n_basis, r_max=5.0), "gexp": dict(spacing="exponential", n_basis=n_basis),
+            "glin": dict(n_basis=n_basis)}[name]
+    cfg = go.GMNNConfig(**ocfg)
+    kind = {"bessel": 2, "gexp": 1, "glin": 0}[name]
+    pos, Z, cell = syn.water_box(512, 7)
+    frac = pos @ np.linalg.inv(cell)
+    idx = no.jaxmd_sparse_pairs(frac, cell.T, cfg.r_max)
+    params = syn.gmnn_params(seed=17, n_basis=n_basis, random_bias=True, random_scale_shift=True)
+    kcfg = {"n_basis": n_basis, "r_min": 0.0 if name == "bessel" else cfg.r_min, "r_max": cfg.r_max, "basis_kind": kind}
+    dp = rt.DeviceParams(params, kcfg)
+    g = rt.descriptor(dp, frac, Z, idx, cell.T, None, "minimage").cpu().numpy()
+    g_ref = go.descriptor_only(params, frac, Z, idx, cell.T, None, "minimage", cfg)["g"]
+    assert np.abs(g - g_ref).max() <= 3e-6 * np.abs(g_ref).max(), np.abs(g - g_ref).max() / np.abs(g_ref).max()
+    e, f = rt.energy_forces(dp, frac, Z, idx, cell.T, None, "minimage")
+    torch.cuda.synchronize()
+    e, f = e.cpu().numpy(), f.cpu().numpy()[0]
+    ref = go.energy_forces(params, frac, Z, idx, cell.T, None, "minimage", cfg)
+    ref64 = go.energy_forces(params, frac, Z, idx, cell.T, None, "minimage", go.fp64_config(cfg))
+    assert abs(e[0] - ref64["energy"]) <= max(1e-6 * abs(ref["energy"]), 2.0 * abs(ref["energy"] - ref64["energy"]))
+    assert_force_parity(f, ref["forces"], ref64["forces"], where=f"generic basis {name} n_basis {n_basis}")
+    # the table-driven kernels on the same model (Cartesian positions, explicit offsets of the min-image list)
+    d = frac[idx[1]] - frac[idx[0]]
+    offs = (-np.round(d)) @ cell
+    e_t, f_t = table_model(params, dict(rt.default_config(), **kcfg)).energy_forces(frac, Z, idx, cell.T, offs, "offsets")
+    torch.cuda.synchronize()
+    f_t = f_t.cpu().numpy()
+    assert abs(float(e_t.cpu().numpy().reshape(-1)[0]) - e[0]) <= 2e-6 * abs(e[0]) + 1e-5
+    assert np.abs(f_t - f).max() <= 2e-5 * np.abs(f).max()
