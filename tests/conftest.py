@@ -75,8 +75,9 @@ def assert_force_parity(f, f_ref32, f_ref64=None, n_atoms=None, where="", ulp_fl
       model exceeds the tolerance at the worst of thousands of elements -- the reference's own source is 1.4x away from
       the fp64 truth on the 36-atom golden fixture, the fp32 oracle 1.2-1.5x at 1536 atoms; tools/study_force_precision.py
       shows the noise comes from every fp32 stage, not one; DESIGN.md "Numerics"):
-        (a) worst element vs f_ref32 <= max(1, 1.5 x the reference's own worst element vs fp64)
-            (two independent evaluations with equal noise differ by sqrt(2) of it);
+        (a) worst element vs f_ref32 <= max(1, 2 x the reference's own worst element vs fp64)
+            (the triangle inequality through the fp64 truth allows 2.25 x given (c); two independent evaluations with
+            equal noise typically differ by sqrt(2) of it);
         (b) >= 99 % of the elements inside the literal tolerance (or at most 2 % fewer than the reference has vs fp64);
         (c) the kernel is no further from the fp64 truth than the reference-precision evaluation: rms error <= 1.1 x the
             reference's, worst element (in units of the tolerance) <= max(1, 1.25 x the reference's).
@@ -105,7 +106,7 @@ def assert_force_parity(f, f_ref32, f_ref64=None, n_atoms=None, where="", ulp_fl
         assert k32 <= 1.0, f"{where}: worst element vs reference precision at {k32:.3f}x tolerance (literal)"
         assert k64 <= 1.0, f"{where}: worst element vs fp64 at {k64:.3f}x tolerance (literal)"
         return rec
-    bound = max(1.0, 1.5 * o64)
+    bound = max(1.0, 2.0 * o64)
     frac_bound = min(0.99, float(np.mean(err_o / tol64 <= 1.0)) - 0.02)
     assert k32 <= bound, f"{where}: worst element at {k32:.3f}x tolerance (bound {bound:.3f})"
     assert np.mean(viol <= 1.0) >= frac_bound, f"{where}: {np.mean(viol <= 1.0):.4f} of elements within tolerance (bound {frac_bound:.4f})"
