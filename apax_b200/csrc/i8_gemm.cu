@@ -19,10 +19,26 @@ constexpr uint32_t I8_B_STAGE = I8_DIGITS * I8_B_TILE;         // 16 KB: one k-b
 constexpr uint32_t I8_ACC_COLS = I8_DIGITS * I8_BN;            // 256 columns: one accumulator set (orders 0..3)
 constexpr uint32_t I8_TMEM_COLS = 2 * I8_ACC_COLS;             // two sets = the SM's whole tensor memory
 constexpr int I8_MAX_B_STAGES = 8;
-constexpr int I8_EPI_WARPS = 8;                                // two warps per TMEM lane quarter
-constexpr int I8_EPI_THREADS = 32 * I8_EPI_WARPS;
-constexpr int I8_MMA_WARP2 = 2 + I8_EPI_WARPS;                 // second MMA-issuing warp (odd tiles)
-constexpr int I8_THREADS = 96 + I8_EPI_THREADS;                // warp 0 TMA, warps 1 and 10 MMA, warps 2-9 epilogue
+// Warp roles.  W = 0 (352 threads): warp 0 TMA, warps 1 and 10 MMA issuers, warps 2-9 epilogue (two per TMEM lane quarter, 32
+// output columns each).  W = 1 (640 threads, "wide epilogue"): the epilogue is what bounds these GEMMs (66 instructions per
+// output element issued by two warps per scheduler at 0.4 IPC), so sixteen epilogue warps (four per
+// quarter, 16 columns each) in four aligned warp groups, the control warps (0 TMA, 1 and 2 MMA, 3 idle) in a group of their
+// own, and setmaxnreg moves registers from the control group (96 -> 32) to the epilogue groups (96 -> 112).
+// MEASURED (1M atoms, four GEMMs, profiles/r02p_gemm_wide_epilogue.txt): 8 warps 4.14 ms; 16 warps at the 96 registers a
+// 640-thread CTA gets, no setmaxnreg: 4.74 ms (the epilogue spills); with setmaxnreg 32 / 112 (the register pool is only what
+// the CTA's own warps release, so 112 for the epilogue forces the control group down to 32): 10.0 ms -- the MMA-issuing warp
+// spills on the critical path.  The register file cannot hold sixteen epilogue warps of this epilogue; W = 0 ships.
+template <int W>
+struct I8Roles {
+  static constexpr int kEpiBase = W ? 4 : 2;                   // first epilogue warp
+  static constexpr int kEpiWarps = W ? 16 : 8;
+  static constexpr int kEpiThreads = 32 * kEpiWarps;
+  static constexpr int kMma2 = W ? 2 : 10;                     // second MMA-issuing warp (odd tiles)
+  static constexpr int kThreads = W ? 640 : 352;
+  static constexpr int kParts = kEpiWarps / 4;                 // warps sharing a lane quarter split the 64 columns
+  static constexpr int kPW = I8_BN / kParts;                   // columns per epilogue thread and sub-tile: 32 or 16
+};
+constexpr int I8_THREADS = I8Roles<0>::kThreads;
 constexpr uint32_t I8_SMEM_LIMIT = 232448;                     // 227 KB per CTA
 constexpr float kSwishI8 = 1.6765324703310907f;                // apax/layers/activation.py:8
 
@@ -86,8 +102,9 @@ __device__ __forceinline__ void mbar_wait_soft(uint32_t bar, uint32_t parity, in
   atomicExch(err, 1);
   *dead = 1;
 }
-__device__ __forceinline__ void epi_bar_sync() {   // named barrier 1: the 256 epilogue threads only
-  asm volatile("bar.sync 1, %0;" ::"n"(I8_EPI_THREADS) : "memory");
+template <int NT>
+__device__ __forceinline__ void epi_bar_sync() {   // named barrier 1: the epilogue threads only
+  asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
 }
 
 // All MMAs of up to two 64-byte k-blocks as ONE instruction burst.  The tensor pipe queues only an MMA or two, so
@@ -182,6 +199,12 @@ __device__ __forceinline__ void i8_emit32(const float (&v)[32], float sc, float 
   for (int d = 0; d < I8_DIGITS; ++d) st_global_v8(dst + d * plane_stride, w[d]);
 }
 
+template <int N>
+__device__ __forceinline__ void i8_emit_cols(const float (&v)[N], float sc, float sc2, int8_t* dst, int64_t plane_stride) {
+  static_assert(N == 16 || N == 32, "16 or 32 columns per epilogue thread");
+  if constexpr (N == 32) i8_emit32(v, sc, sc2, dst, plane_stride); else i8_emit16(v, sc, sc2, dst, plane_stride);
+}
+
 // int32 accumulators of the four orders -> fp32.  Order 0 (|.| < 2^22) and the rounded-down tails of orders 2 and 3
 // go through the exact magic-number conversion on the ALU pipes, order 1 through I2F; the shifts drop at most
 // 2^-15 of an order-0 unit, far below the fp32 rounding of the result.
@@ -199,8 +222,8 @@ __device__ __forceinline__ float i8_combine(uint32_t r0, uint32_t r1, uint32_t r
 // ================================================================================================
 // The GEMM.  MODE: epilogue (I8_EPI_*), NOUT: heads accumulated by I8_EPI_ACT_HEAD (1 or I8_MAX_HEADS).
 // ================================================================================================
-template <int MODE, int NOUT>
-__global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant__ CUtensorMap tm_a,
+template <int MODE, int NOUT, int W = 0>
+__global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __grid_constant__ CUtensorMap tm_a,
                                                            const __grid_constant__ CUtensorMap tm_b, int num_kb,
                                                            int a_planes, int a_res, int num_m_tiles, int num_n_sub,
                                                            int b_stages, I8Epilogue epi, int32_t* err) {
@@ -213,8 +236,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
   __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ int cta_dead;
-  __shared__ float xmax[2][I8_BM];            // row-maximum exchange between the two column halves
-  __shared__ float xhead[I8_BM * NOUT];       // head partial sums of the second column half
+  using R = I8Roles<W>;
+  constexpr int PARTS = R::kParts, PW = R::kPW;
+  __shared__ float xmax[PARTS][I8_BM];                   // row-maximum exchange between the column parts
+  __shared__ float xhead[(PARTS - 1) * I8_BM * NOUT];    // head partial sums of the parts 1 ..
   // per-output constants of the epilogue (bias, next layer's feature scales, head weights for one head): broadcast
   // shared-memory reads instead of global loads inside the element loop
   __shared__ float s_bias[I8_MAX_KB * I8_KC], s_qcs[I8_MAX_KB * I8_KC], s_whead[I8_MAX_KB * I8_KC];
@@ -230,7 +255,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
   const uint32_t smem_b = smem_a + uint32_t(num_kb * a_res) * I8_A_TILE;
   const uint32_t stage_bytes = I8_B_STAGE + uint32_t(a_planes - a_res) * I8_A_TILE;
 
-  for (int n = threadIdx.x; n < num_n_sub * I8_BN; n += I8_THREADS) {
+  for (int n = threadIdx.x; n < num_n_sub * I8_BN; n += R::kThreads) {
     s_bias[n] = (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_ACT_HEAD) ? epi.bias[n] : 0.0f;
     s_qcs[n] = MODE != I8_EPI_STORE ? epi.q_col_scale[n] : 0.0f;
     s_whead[n] = (MODE == I8_EPI_ACT_HEAD && NOUT == 1) ? epi.w_head[n] : 0.0f;
@@ -247,7 +272,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&acc_full[i]), 1);
-      mbar_init(smem_u32(&acc_empty[i]), I8_EPI_THREADS);
+      mbar_init(smem_u32(&acc_empty[i]), R::kEpiThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -260,6 +285,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (W) {   // registers follow the work: control warp group down, epilogue warp groups up (whole aligned groups of four warps)
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");   // frees 4 x 32 x 64 registers ...
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");  // ... exactly what 16 x 32 x 16 more need (the pool is the CTA's own)
+    }
+  }
   const uint32_t tmem_d = tmem_base_slot;
   const int my_m_tiles = (num_m_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
 
@@ -301,7 +333,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
         }
       }
     }
-  } else if (warp == 1 || warp == I8_MMA_WARP2) {
+  } else if (warp == 1 || warp == R::kMma2) {
     // ------------------------------------------------------------------ MMA issuers (warp-uniform, elected lane issues)
     // Two warps: one owns the even tiles (accumulator set 0), the other the odd ones (set 1).  The tensor pipe queues
     // only an MMA or two, so a single issuer leaves it idle during every hand-shake (barrier polls, descriptors,
@@ -373,10 +405,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
       }
     }
     if (epi.dbg && lane == 0 && mma_id == 0) epi.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
-  } else if (warp < I8_MMA_WARP2) {
+  } else if (warp >= R::kEpiBase && warp < R::kEpiBase + R::kEpiWarps) {
     // -------------------------------------------------------------------- epilogue warps: lane == atom
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;          // the two warps of a quarter split the 64 columns
+    const int half = (warp - R::kEpiBase) >> 2;   // column part of this warp: the warps of a quarter split the 64 columns
     const int row = q * 32 + lane;
     float* scratch = (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_MULD_Q)
                          ? epi.scratch + int64_t(blockIdx.x) * num_n_sub * I8_BN * I8_BM + row
@@ -400,10 +432,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
       }
       for (int j = 0; j < num_n_sub && ok; ++j, ++tile) {
         const uint32_t buf = tile & 1, use = tile >> 1;
-        float auxv[32];   // MULD_Q: the multipliers of this sub-tile, requested before the wait so that their latency hides
+        float auxv[PW];   // MULD_Q: the multipliers of this sub-tile, requested before the wait so that their latency hides
         if (MODE == I8_EPI_MULD_Q) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) auxv[i] = epi.aux[int64_t(j * I8_BN + half * 32 + i) * epi.ld + m];
+          for (int i = 0; i < PW; ++i) auxv[i] = epi.aux[int64_t(j * I8_BN + half * PW + i) * epi.ld + m];
         }
         const long long c0 = clock64();
         ok = mbar_wait(smem_u32(&acc_full[buf]), use & 1, err);
@@ -416,17 +448,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
           mbar_arrive(smem_u32(&acc_empty[buf]));
           continue;
         }
-        float dq[32];                                       // ACT_HEAD: swish' values to be quantised
+        float dq[PW];                                       // ACT_HEAD: swish' values to be quantised
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = half * 32 + cc * 16;
+        for (int cc = 0; cc < PW / 16; ++cc) {
+          const int c = half * PW + cc * 16;
           uint32_t r0[16], r1[16], r2[16], r3[16];          // sixteen columns of the four orders
           tmem_ld16_u32(taddr + c, r0);
           tmem_ld16_u32(taddr + I8_BN + c, r1);
           tmem_ld16_u32(taddr + 2 * I8_BN + c, r2);
           tmem_ld16_u32(taddr + 3 * I8_BN + c, r3);
           tmem_ld_wait();
-          if (cc == 1) {  // everything is in registers: hand the accumulator set back before the math
+          if (cc == PW / 16 - 1) {  // everything is in registers: hand the accumulator set back before the math
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(smem_u32(&acc_empty[buf]));
           }
@@ -471,53 +503,59 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_i8_gemm(const __grid_constant
           }
         }
         if (MODE == I8_EPI_ACT_HEAD)
-          i8_emit32(dq, qsc, qsc2, epi.q_planes + m * epi.q_kp + j * I8_BN + half * 32, epi.q_plane_stride);
+          i8_emit_cols<PW>(dq, qsc, qsc2, epi.q_planes + m * epi.q_kp + j * I8_BN + half * PW, epi.q_plane_stride);
       }
       if (!ok) break;
       // ---- end of the output sweep of this atom tile
       if (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_MULD_Q) {
-        // This thread staged the columns [j*64 + half*32, +32) of every sub-tile itself: re-read them (L2) and emit
-        // digits, one 32-byte sector per plane and sub-tile.  The loads do not depend on the row maximum, so the first
-        // batch is requested before the exchange.
+        // This thread staged the columns [j*64 + half*PW, +PW) of every sub-tile itself: re-read them (L2) and emit
+        // digits, one 32-byte sector (16 bytes with the wide epilogue) per plane and sub-tile.  The loads do not depend on
+        // the row maximum, so the first batch is requested before the exchange.
         const long long p0 = clock64();
-        float cur[32];
+        float cur[PW];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) cur[i] = scratch[(half * 32 + i) * I8_BM];
+        for (int i = 0; i < PW; ++i) cur[i] = scratch[(half * PW + i) * I8_BM];
         xmax[half][row] = mx;
-        epi_bar_sync();
-        mx = fmaxf(xmax[0][row], xmax[1][row]);
-        epi_bar_sync();
+        epi_bar_sync<R::kEpiThreads>();
+#pragma unroll
+        for (int pp = 0; pp < PARTS; ++pp) mx = fmaxf(mx, xmax[pp][row]);
+        epi_bar_sync<R::kEpiThreads>();
         int e;
         float sc, sc2;
         i8_row_scale(mx, 4, e, sc, sc2);
         if (half == 0) epi.q_row_exp[m] = e;
 #pragma unroll 1
         for (int j = 0; j < num_n_sub; ++j) {
-          const int nb = j * I8_BN + half * 32;
+          const int nb = j * I8_BN + half * PW;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) cur[i] *= s_qcs[nb + i];
-          i8_emit32(cur, sc, sc2, epi.q_planes + m * epi.q_kp + nb, epi.q_plane_stride);
+          for (int i = 0; i < PW; ++i) cur[i] *= s_qcs[nb + i];
+          i8_emit_cols<PW>(cur, sc, sc2, epi.q_planes + m * epi.q_kp + nb, epi.q_plane_stride);
           if (j + 1 < num_n_sub) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) cur[i] = scratch[(nb + I8_BN + i) * I8_BM];
+            for (int i = 0; i < PW; ++i) cur[i] = scratch[(nb + I8_BN + i) * I8_BM];
           }
         }
         w_phase2 += clock64() - p0;
       } else if (MODE == I8_EPI_ACT_HEAD) {
-        if (half == 1) {
+        if (half > 0) {
 #pragma unroll
-          for (int k = 0; k < NOUT; ++k) xhead[row * NOUT + k] = hacc[k];
+          for (int k = 0; k < NOUT; ++k) xhead[((half - 1) * I8_BM + row) * NOUT + k] = hacc[k];
         }
-        epi_bar_sync();
+        epi_bar_sync<R::kEpiThreads>();
         if (half == 0) {
 #pragma unroll
           for (int k = 0; k < NOUT; ++k)
-            if (k < epi.n_out) epi.h_out[int64_t(k) * epi.ld + m] = hacc[k] + xhead[row * NOUT + k];
+            if (k < epi.n_out) {
+              float h = hacc[k];
+#pragma unroll
+              for (int pp = 1; pp < PARTS; ++pp) h += xhead[((pp - 1) * I8_BM + row) * NOUT + k];
+              epi.h_out[int64_t(k) * epi.ld + m] = h;
+            }
         }
-        epi_bar_sync();
+        epi_bar_sync<R::kEpiThreads>();
       }
     }
-    if (epi.dbg && threadIdx.x == 64) {
+    if (epi.dbg && threadIdx.x == R::kEpiBase * 32) {
       epi.dbg[blockIdx.x * 8 + 4] = clock64() - t_begin;
       epi.dbg[blockIdx.x * 8 + 5] = w_wait;
       epi.dbg[blockIdx.x * 8 + 6] = w_phase2;
@@ -635,17 +673,23 @@ int prepare_i8(Kern kern) {
 }
 
 // one named launch per epilogue so that launch lists and the per-kernel profile tell the four GEMMs apart
-#define I8_LAUNCH(name, MODE, NOUT)                                                                                  \
+#define I8_LAUNCH_W(name, MODE, NOUT, WIDE)                                                                          \
   do {                                                                                                               \
-    auto name = k_i8_gemm<MODE, NOUT>;                                                                               \
+    auto name = k_i8_gemm<MODE, NOUT, WIDE>;                                                                         \
     static bool prepared = false;                                                                                    \
     if (!prepared) {                                                                                                 \
       APAX_TRY(prepare_i8(name));                                                                                    \
       prepared = true;                                                                                               \
     }                                                                                                                \
-    APAX_LAUNCH(name, dim3((unsigned)L.grid), dim3(I8_THREADS), L.smem, stream, L.ta, L.tb, L.num_kb, L.a_planes,    \
-                L.a_res, L.num_m_tiles, L.num_n_sub, L.b_stages, epi, err_flag);                                     \
+    APAX_LAUNCH(name, dim3((unsigned)L.grid), dim3(I8Roles<WIDE>::kThreads), L.smem, stream, L.ta, L.tb, L.num_kb,   \
+                L.a_planes, L.a_res, L.num_m_tiles, L.num_n_sub, L.b_stages, epi, err_flag);                         \
     return APAX_OK;                                                                                                  \
+  } while (0)
+// the eight-warp kernels, or (apax_i8_set_debug flag 16) the wide-epilogue variant
+#define I8_LAUNCH(name, MODE, NOUT)                 \
+  do {                                              \
+    if (wide) I8_LAUNCH_W(name, MODE, NOUT, 1);     \
+    I8_LAUNCH_W(name, MODE, NOUT, 0);               \
   } while (0)
 
 }  // namespace
@@ -764,7 +808,11 @@ int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const
   trace_grid = L.grid;
   // as many activation planes as fit stay resident next to a ring of at least three weight stages; the least
   // significant planes (used by the fewest MMAs) travel with the stages otherwise
-  const uint32_t budget = I8_SMEM_LIMIT - 10240 /* static + alignment */;
+  // the eight-warp epilogue ships; apax_i8_set_debug flag 16 selects the sixteen-warp kernels (measurement: slower, see I8Roles)
+  const bool wide = (g_i8_dbg_flags.load(std::memory_order_relaxed) & 16) != 0;
+  // static shared memory + alignment: the many-head epilogue of the wide kernel keeps three partial head sums per row
+  const uint32_t static_reserve = (wide && epi.mode == I8_EPI_ACT_HEAD && epi.n_out > 1) ? 36864 : 10240;
+  const uint32_t budget = I8_SMEM_LIMIT - static_reserve;
   L.a_res = L.a_planes;
   uint32_t a_bytes, stage_bytes;
   for (;; --L.a_res) {
