@@ -9,6 +9,7 @@
 // are elementwise kernels and a fixed-shape fp64 reduction.  dtypes follow the reference: fp64 state, time
 // steps and chain masses rounded to fp32 where it casts with f32().
 #include <math.h>
+#include <stddef.h>
 
 #include "common.cuh"
 
@@ -38,68 +39,94 @@ __constant__ double kSY7[7] = {0.784513610477560, 0.235573213359357, -1.17767998
 
 __device__ __forceinline__ double f32r(double x) { return double(float(x)); }
 
-// substep_fn (simulate.py:436-473)
+// substep_fn (simulate.py:436-473).  One thread integrates the chain, so the serial fp64 divisions are what this costs: the
+// chain masses are constant within a call, their reciprocals are taken once (x / Q -> x * (1/Q): one ulp, 1e-16 relative).
 __device__ double chain_substep(MdChainState& c, double delta, double kT) {
   const int M = c.chain_length - 1;
   const double delta_2 = f32r(delta / 2.0), delta_4 = f32r(delta_2 / 2.0), delta_8 = f32r(delta_4 / 2.0);
-  double p_old[kMaxChain];
-  double G = c.p_xi[M - 1] * c.p_xi[M - 1] / c.Q[M - 1] - kT;
+  double p_old[kMaxChain], iq[kMaxChain];
+  for (int m = 0; m <= M; ++m) iq[m] = 1.0 / c.Q[m];
+  double G = c.p_xi[M - 1] * c.p_xi[M - 1] * iq[M - 1] - kT;
   c.p_xi[M] += delta_4 * G;
   for (int m = 0; m <= M; ++m) p_old[m] = c.p_xi[m];
   double carry = c.p_xi[M];
   for (int m = M - 1; m >= 1; --m) {
-    G = p_old[m - 1] * p_old[m - 1] / c.Q[m - 1] - kT;
-    const double s = exp(-delta_8 * carry / c.Q[m + 1]);
+    G = p_old[m - 1] * p_old[m - 1] * iq[m - 1] - kT;
+    const double s = exp(-delta_8 * carry * iq[m + 1]);
     carry = s * (s * p_old[m] + delta_4 * G);
     c.p_xi[m] = carry;
   }
   G = 2.0 * c.KE - c.dof * kT;
-  double s = exp(-delta_8 * c.p_xi[1] / c.Q[1]);
+  double s = exp(-delta_8 * c.p_xi[1] * iq[1]);
   c.p_xi[0] = s * (s * c.p_xi[0] + delta_4 * G);
-  s = exp(-delta_2 * c.p_xi[0] / c.Q[0]);
+  s = exp(-delta_2 * c.p_xi[0] * iq[0]);
   c.KE *= s * s;
   const double p_scale = s;
-  for (int m = 0; m <= M; ++m) c.xi[m] += delta_2 * c.p_xi[m] / c.Q[m];
+  for (int m = 0; m <= M; ++m) c.xi[m] += delta_2 * c.p_xi[m] * iq[m];
   G = 2.0 * c.KE - c.dof * kT;
   for (int m = 0; m <= M; ++m) p_old[m] = c.p_xi[m];
   for (int m = 0; m < M; ++m) {
-    const double sc = exp(-delta_8 * p_old[m + 1] / c.Q[m + 1]);
+    const double sc = exp(-delta_8 * p_old[m + 1] * iq[m + 1]);
     const double upd = sc * (sc * p_old[m] + delta_4 * G);
-    G = upd * upd / c.Q[m] - kT;
+    G = upd * upd * iq[m] - kT;
     c.p_xi[m] = upd;
   }
   c.p_xi[M] += delta_4 * G;
   return p_scale;
 }
 
-// update_chain_mass_fn + half_step_chain_fn (simulate.py:475-495); one thread
-__global__ void k_md_chain_half(MdChainState* st, double dt, double kT, double tau, int chain_steps, int sy_steps,
-                                const double* __restrict__ box) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  MdChainState c = *st;
-  const float q = float(kT) * (float(tau) * float(tau));
-  for (int m = 0; m < c.chain_length; ++m) c.Q[m] = double(m == 0 ? q * float(c.dof) : q);
-  double total = 1.0;
-  if (chain_steps == 1 && sy_steps == 1) {
-    total = chain_substep(c, dt, kT);
-  } else {
-    const double delta = f32r(dt / chain_steps);
-    const double* ws = sy_steps == 3 ? kSY3 : (sy_steps == 5 ? kSY5 : kSY7);
-    for (int i = 0; i < chain_steps * sy_steps; ++i) {
-      const double w = sy_steps == 1 ? 1.0 : ws[i % sy_steps];
-      total *= chain_substep(c, f32r(delta * w), kT);
+// update_chain_mass_fn + half_step_chain_fn (simulate.py:475-495).  The chain is a few dozen scalars integrated by ONE thread;
+// the state's head (everything before the 2 KB of reduction partials) travels through shared memory, loaded and stored by the
+// whole warp -- a single thread copying the full struct from and to global memory cost 37 us per launch, 13 % of a 12,288-atom
+// MD step (tools/md_step_profile.py).
+constexpr int kChainHeadDoubles = int(offsetof(MdChainState, partial) / sizeof(double));
+// n_partial > 0: the kinetic energy is first summed from the per-block partials of k_md_kick_ke (fixed order: lane-strided
+// partial sums joined by a butterfly), which saves the separate k_md_ke_final launch of the post-force half.
+__global__ void __launch_bounds__(32) k_md_chain_half(MdChainState* st, double dt, double kT, double tau, int chain_steps, int sy_steps,
+                                                      const double* __restrict__ box, int n_partial = 0) {
+  if (blockIdx.x != 0) return;
+  __shared__ MdChainState sc;
+  double* sd = reinterpret_cast<double*>(&sc);
+  const double* gd = reinterpret_cast<const double*>(st);
+  for (int i = threadIdx.x; i < kChainHeadDoubles; i += 32) sd[i] = gd[i];
+  if (threadIdx.x == 0) { sc.dof = st->dof; sc.chain_length = st->chain_length; }
+  if (n_partial > 0) {
+    double ke = 0.0;
+    for (int i = threadIdx.x; i < n_partial; i += 32) ke += st->partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ke += __shfl_xor_sync(0xffffffffu, ke, o);
+    __syncwarp();
+    if (threadIdx.x == 0) sc.KE = ke;
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    MdChainState& c = sc;
+    const float q = float(kT) * (float(tau) * float(tau));
+    for (int m = 0; m < c.chain_length; ++m) c.Q[m] = double(m == 0 ? q * float(c.dof) : q);
+    double total = 1.0;
+    if (chain_steps == 1 && sy_steps == 1) {
+      total = chain_substep(c, dt, kT);
+    } else {
+      const double delta = f32r(dt / chain_steps);
+      const double* ws = sy_steps == 3 ? kSY3 : (sy_steps == 5 ? kSY5 : kSY7);
+      for (int i = 0; i < chain_steps * sy_steps; ++i) {
+        const double w = sy_steps == 1 ? 1.0 : ws[i % sy_steps];
+        total *= chain_substep(c, f32r(delta * w), kT);
+      }
+    }
+    c.scale = total;
+    if (box) {  // inverse of the (possibly time-dependent) box for the fractional position update
+      const double* a = box;
+      const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+      const double id = 1.0 / det;
+      c.inv_box[0] = (a[4] * a[8] - a[5] * a[7]) * id; c.inv_box[1] = (a[2] * a[7] - a[1] * a[8]) * id; c.inv_box[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+      c.inv_box[3] = (a[5] * a[6] - a[3] * a[8]) * id; c.inv_box[4] = (a[0] * a[8] - a[2] * a[6]) * id; c.inv_box[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+      c.inv_box[6] = (a[3] * a[7] - a[4] * a[6]) * id; c.inv_box[7] = (a[1] * a[6] - a[0] * a[7]) * id; c.inv_box[8] = (a[0] * a[4] - a[1] * a[3]) * id;
     }
   }
-  c.scale = total;
-  if (box) {  // inverse of the (possibly time-dependent) box for the fractional position update
-    const double* a = box;
-    const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
-    const double id = 1.0 / det;
-    c.inv_box[0] = (a[4] * a[8] - a[5] * a[7]) * id; c.inv_box[1] = (a[2] * a[7] - a[1] * a[8]) * id; c.inv_box[2] = (a[1] * a[5] - a[2] * a[4]) * id;
-    c.inv_box[3] = (a[5] * a[6] - a[3] * a[8]) * id; c.inv_box[4] = (a[0] * a[8] - a[2] * a[6]) * id; c.inv_box[5] = (a[2] * a[3] - a[0] * a[5]) * id;
-    c.inv_box[6] = (a[3] * a[7] - a[4] * a[6]) * id; c.inv_box[7] = (a[1] * a[6] - a[0] * a[7]) * id; c.inv_box[8] = (a[0] * a[4] - a[1] * a[3]) * id;
-  }
-  *st = c;
+  __syncwarp();
+  double* go = reinterpret_cast<double*>(st);
+  for (int i = threadIdx.x; i < kChainHeadDoubles; i += 32) go[i] = sd[i];
 }
 
 // P <- P*scale + dt/2 F ; R <- mod(R + inv_box.(dt P / m), 1)      (momentum_step, position_step, periodic_shift)
@@ -236,9 +263,8 @@ extern "C" int apax_md_nvt_post_force(apax_stream_t stream, const apax_md_nvt_co
   const double dt = double(float(cfg->dt)), dt_2 = double(float(dt / 2));
   const int nb = ke_blocks(n_atoms);
   APAX_LAUNCH(k_md_kick_ke, dim3(nb), dim3(256), 0, stream, P, F, mass, st, dt_2, n_atoms, 1);
-  APAX_LAUNCH(k_md_ke_final, dim3(1), dim3(32), 0, stream, st, nb);
   APAX_LAUNCH(k_md_chain_half, dim3(1), dim3(32), 0, stream, st, dt, cfg->kT, double(float(cfg->tau)), cfg->chain_steps,
-              cfg->sy_steps, (const double*)nullptr);
+              cfg->sy_steps, (const double*)nullptr, nb);
   APAX_LAUNCH(k_md_scale, dim3((unsigned)cdiv(3 * n_atoms, 256)), dim3(256), 0, stream, P, st, 3 * n_atoms);
   return APAX_OK;
 }
