@@ -43,6 +43,13 @@ struct apax_ctx {
   double list_cutoff;
   double list_cell[9];
   int64_t n_pairs;
+  // CUDA graph of the image-list path (small cells are launch-latency bound: ~45 dependent launches on 96 atoms)
+  cudaGraphExec_t graph_exec;
+  int64_t graph_N;
+  int graph_forces, graph_tag;
+  int64_t graph_launches;   // kernels inside the graph: added to the library's launch counter on every replay
+  int64_t image_shape_N;
+  int image_shape_calls;
   int evaluated;     // the workspace holds the per-pair values of a completed energy+forces evaluation (for apax_ctx_stress)
   double* scratch_ef; // [1 + 3 max_atoms] second evaluation of the offsets-branch stress (allocated on first use)
 };
@@ -128,9 +135,42 @@ extern "C" void apax_ctx_destroy(apax_ctx* c) {
   cudaFree(c->gm_ws); cudaFree(c->nl_ws); cudaFree(c->scratch_ef);
   cudaFreeHost(c->h_pos); cudaFreeHost(c->h_Z); cudaFreeHost(c->h_mats); cudaFreeHost(c->h_counters);
   cudaFreeHost(c->h_overflow); cudaFreeHost(c->h_out);
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   cudaStreamDestroy(c->stream);
   delete[] c->list_Z;
   delete c;
+}
+
+// Everything the image-list (vesin-replacement) path does between the host staging buffers, asynchronous on the context's
+// stream and free of host synchronisation, so that it can be captured once in a CUDA graph and replayed: H2D of positions /
+// numbers / matrices, cell-list image search, offsets, list preparation, E+F, D2H of the counters and the results.  The
+// overflow flag is checked by the caller AFTER the results have arrived (every kernel respects the capacity).
+static int enqueue_image_path(apax_ctx* c, int64_t N, bool want_forces) {
+  const apax_gm_params_impl* p = c->params;
+  const int n_out = p->cfg.n_out;
+  const int n_f = (p->mean_forces && n_out > 1) ? 1 : n_out;
+  const int64_t cap = c->max_pairs;
+  cudaStream_t s = c->stream;
+  APAX_CUDA_TRY(cudaMemcpyAsync(c->pos, c->h_pos, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, s));
+  APAX_CUDA_TRY(cudaMemcpyAsync(c->Z, c->h_Z, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s));
+  APAX_CUDA_TRY(cudaMemcpyAsync(c->mats, c->h_mats, sizeof(double) * 45, cudaMemcpyHostToDevice, s));
+  GmWorkspace gw;
+  NlWorkspace nw;
+  carve_gm_workspace(c->gm_ws, N, cap, n_out, 128, &gw);
+  carve_nl_workspace(c->nl_ws, N, cap, &nw);
+  APAX_CUDA_TRY(cudaMemsetAsync(c->overflow, 0, 4, s));
+  APAX_TRY(nl_build_images_csr(s, c->pos, c->mats, 1, N, double(p->cfg.r_max), cap, nw, nullptr, nullptr, nullptr, c->counters,
+                               c->overflow));
+  APAX_CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  APAX_CUDA_TRY(cudaMemcpyAsync(c->h_overflow, c->overflow, 1, cudaMemcpyDeviceToHost, s));
+  APAX_TRY(nl_emit_offsets(s, nw, N, c->offsets));
+  APAX_TRY(gm_prepare_from_csr(s, p, gw, c->Z, nw.rowptr_c, nw.nbr, /*symmetric_sorted=*/false));
+  APAX_TRY(gm_compute_device(s, p, gw, c->pos, c->Z, c->mats + 27, c->offsets, APAX_DISP_OFFSETS, c->energy,
+                             want_forces ? c->forces : nullptr));
+  APAX_CUDA_TRY(cudaMemcpyAsync(c->h_out, c->energy, sizeof(double) * n_out, cudaMemcpyDeviceToHost, s));
+  if (want_forces)
+    APAX_CUDA_TRY(cudaMemcpyAsync(c->h_out + n_out, c->forces, sizeof(double) * 3 * N * n_f, cudaMemcpyDeviceToHost, s));
+  return APAX_OK;
 }
 
 extern "C" int apax_ctx_calculate(apax_ctx* c, const double* positions_host, const int32_t* numbers_host,
@@ -166,6 +206,59 @@ extern "C" int apax_ctx_calculate(apax_ctx* c, const double* positions_host, con
   host_invert3(m + 9, m + 18);
   for (int i = 0; i < 9; ++i) m[27 + i] = (i % 4 == 0) ? 1.0 : 0.0;
   for (int i = 0; i < 9; ++i) m[36 + i] = (i % 4 == 0) ? 2.0 : 0.0;
+  const bool minimage = minimage_ok(cell_host, p->cfg.r_max);
+  if (!minimage && !g_profile_on) {
+    // ---- image-list path (recomputed on every call, apax/md/ase_calc.py:386-387), replayed from a CUDA graph: the first call
+    // at a shape runs eagerly (one-time initialisations), the second is captured, later ones are ONE graph launch.  Inputs go
+    // through the context's pinned staging buffers (fixed addresses for the graph's copy nodes).
+    memcpy(c->h_pos, positions_host, sizeof(double) * 3 * N);
+    memcpy(c->h_Z, numbers_host, sizeof(int32_t) * N);
+    const bool want_forces = forces_host != nullptr;
+    const int tag = p->readout_mode * 1000 + p->pair_block * 10 + p->mean_forces + (p->corr.zbl_on ? 100000 : 0) + (p->corr.exp_on ? 200000 : 0);
+    if (c->image_shape_N != N) { c->image_shape_N = N; c->image_shape_calls = 0; }
+    const bool have_graph = c->graph_exec && c->graph_N == N && c->graph_forces == int(want_forces) && c->graph_tag == tag;
+    if (!have_graph && c->image_shape_calls >= 1) {
+      if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      APAX_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+      const int64_t launches_before = g_launch_count.load();
+      const int rc_cap = enqueue_image_path(c, N, want_forces);
+      c->graph_launches = g_launch_count.load() - launches_before;
+      g_launch_count.fetch_sub(c->graph_launches);   // captured, not executed: counted when the graph is launched
+      const cudaError_t e_end = cudaStreamEndCapture(s, &graph);
+      if (rc_cap != APAX_OK || e_end != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        c->image_shape_calls = -1000000;   // capture is not possible here: stay on the eager path
+      } else {
+        const cudaError_t e_inst = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e_inst != cudaSuccess) { c->graph_exec = nullptr; cudaGetLastError(); c->image_shape_calls = -1000000; }
+        else { c->graph_N = N; c->graph_forces = int(want_forces); c->graph_tag = tag; }
+      }
+    }
+    if (c->graph_exec && c->graph_N == N && c->graph_forces == int(want_forces) && c->graph_tag == tag) {
+      APAX_CUDA_TRY(cudaGraphLaunch(c->graph_exec, s));
+      g_launch_count.fetch_add(c->graph_launches);
+    } else {
+      APAX_TRY(enqueue_image_path(c, N, want_forces));
+    }
+    ++c->image_shape_calls;
+    APAX_CUDA_TRY(cudaStreamSynchronize(s));
+    c->n_pairs = c->h_counters[0];
+    if (n_pairs_host) *n_pairs_host = c->n_pairs;
+    c->list_atoms = -1;                       // the min-image bookkeeping does not apply to this path
+    if (c->h_overflow[0] || c->n_pairs > cap) return APAX_ERR_OVERFLOW;   // caller re-creates the context with more capacity
+    memcpy(energy_host, c->h_out, sizeof(double) * n_out);
+    if (forces_host) memcpy(forces_host, c->h_out + n_out, sizeof(double) * 3 * N * n_f);
+    c->list_atoms = N;
+    memcpy(c->list_Z, numbers_host, sizeof(int32_t) * N);
+    c->list_minimage = 0;
+    c->list_cutoff = double(p->cfg.r_max);
+    for (int i = 0; i < 9; ++i) c->list_cell[i] = cell_host[i];
+    c->evaluated = want_forces;
+    return APAX_OK;
+  }
   APAX_CUDA_TRY(cudaMemcpyAsync(c->pos, pos_pinned ? positions_host : c->h_pos, sizeof(double) * 3 * N,
                                 cudaMemcpyHostToDevice, s));
   APAX_CUDA_TRY(cudaMemcpyAsync(c->Z, z_pinned ? numbers_host : c->h_Z, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s));
@@ -180,7 +273,6 @@ extern "C" int apax_ctx_calculate(apax_ctx* c, const double* positions_host, con
   carve_gm_workspace(c->gm_ws, N, cap, n_out, 128, &gw);
   carve_nl_workspace(c->nl_ws, N, cap, &nw);
 
-  const bool minimage = minimage_ok(cell_host, p->cfg.r_max);
   bool same_cell = true;
   for (int i = 0; i < 9; ++i) same_cell = same_cell && c->list_cell[i] == cell_host[i];
   const double cutoff = double(p->cfg.r_max) + (minimage ? dr_threshold : 0.0);
