@@ -83,45 +83,91 @@ class ASECalculator:
     def batch_eval(self, atoms_list, batch_size: int = 64, silent: bool = True):
         """ASECalculator.batch_eval (apax/md/ase_calc.py:395-481): evaluate many structures, `batch_size` at a
         time, each batch in ONE neighbour-list call and ONE energy+forces call (atoms concatenated instead of the
-        reference's padding to the largest structure).  Returns a list of result dicts."""
+        reference's padding to the largest structure).  Returns a list of result dicts.
+
+        The batches are software-pipelined: batch b is enqueued completely (lists, E+F, ensemble statistics, copies into
+        pinned staging buffers) before the host waits for batch b-1's copies and slices its results, so the host-side work
+        of one batch hides behind the GPU work of the next.  No synchronisation happens inside a batch: the list is
+        evaluated at its capacity (padding entries are (0,0) pairs, which contribute exactly nothing) and the overflow flag
+        travels back with the results; an overflowing batch is simply redone with a larger capacity."""
         import torch
 
         model = self.builder.build_energy_derivative_model(init_box=self._cell(atoms_list[0]).T)
         em = getattr(model, "energy_model", model)
         dp = device_params(self.params, em.statics())
         r_max = float(dp.config["r_max"])
-        results = []
-        for s in range(0, len(atoms_list), batch_size):
-            chunk = atoms_list[s:s + batch_size]
+        n_ens = dp.n_out
+        results = [None] * len(atoms_list)
+        state = self.__dict__.setdefault("_batch_state", {"pairs_per_atom": None})
+
+        def enqueue(start, chunk, cap, parity):
             pos = np.concatenate([np.asarray(a.positions, dtype=np.float64) for a in chunk])
             num = np.concatenate([np.asarray(a.numbers, dtype=np.int32) for a in chunk])
             cells = np.stack([self._cell(a) for a in chunk])
             ptr = np.concatenate([[0], np.cumsum([len(a.numbers) for a in chunk])]).astype(np.int32)
-            cap = int(len(num) * self.max_pairs_per_atom)
-            while True:
-                idx, _, offsets, n_found, overflow = rt.nl_build_images_batched(pos, cells, ptr, r_max, cap)
-                nf = int(n_found.item())
-                if not int(overflow.item()):
-                    break
-                cap = int(nf * self.padding_factor) + 1024      # "neighbor list overflowed, extending."
-            e, f = rt.energy_forces_batched(dp, pos, num, idx[:, :nf].contiguous(), offsets[:nf].contiguous(), ptr)
-            n_ens = dp.n_out
+            idx, _, offsets, n_found, overflow = rt.nl_build_images_batched(pos, cells, ptr, r_max, cap)
+            e, f = rt.energy_forces_batched(dp, pos, num, idx, offsets, ptr)       # whole capacity: the tail is (0,0) padding
+            tag = f"p{parity}"
             if n_ens == 1:
-                torch.cuda.synchronize()
-                e, f = e.cpu().numpy(), f.cpu().numpy()
-                for b in range(len(chunk)):
-                    results.append({"energy": float(e[b, 0]), "forces": f[0, ptr[b]:ptr[b + 1]]})
-                continue
-            # ensemble statistics (models.py:221-263) for the whole chunk in one kernel pair on the device, results through
-            # pinned staging buffers, sliced per structure afterwards
-            stats = rt.ensemble_stats(e, f)
-            host = [self._to_host(nm, t) for nm, t in zip(("e", "e_mean", "e_unc", "f_mean", "f_unc", "f_ens"), (e,) + stats)]
-            torch.cuda.synchronize()
-            e_h, e_mean, e_unc, fm, f_unc, f_ens = [h.numpy().copy() for h in host]
-            for b in range(len(chunk)):
+                host = [self._to_host(tag + nm, t) for nm, t in zip(("nf", "ov", "e", "f"), (n_found, overflow, e, f))]
+            else:
+                stats = rt.ensemble_stats(e, f)
+                host = [self._to_host(tag + nm, t) for nm, t in
+                        zip(("nf", "ov", "e", "e_mean", "e_unc", "f_mean", "f_unc", "f_ens"), (n_found, overflow, e) + stats)]
+            ev = torch.cuda.Event()
+            ev.record()
+            return {"start": start, "chunk": chunk, "ptr": ptr, "host": host, "event": ev, "cap": cap, "n_atoms": len(num)}
+
+        def finalize(rec):
+            rec["event"].synchronize()
+            host = rec["host"]
+            nf, ov = int(host[0].numpy()[0]), int(host[1].numpy()[0])
+            if ov or nf > rec["cap"]:
+                return int(nf * self.padding_factor) + 1024          # "neighbor list overflowed, extending."
+            state["pairs_per_atom"] = max(state["pairs_per_atom"] or 0.0, nf / rec["n_atoms"])
+            ptr, start = rec["ptr"], rec["start"]
+            if n_ens == 1:
+                e, f = host[2].numpy().copy(), host[3].numpy().copy()
+                for b in range(len(rec["chunk"])):
+                    results[start + b] = {"energy": float(e[b, 0]), "forces": f[0, ptr[b]:ptr[b + 1]]}
+                return None
+            e_h, e_mean, e_unc, fm, f_unc, f_ens = [h.numpy().copy() for h in host[2:]]
+            for b in range(len(rec["chunk"])):
                 sl = slice(ptr[b], ptr[b + 1])
-                results.append({"energy": float(e_mean[b]), "energy_ensemble": e_h[b], "energy_uncertainty": float(e_unc[b]),
-                                "forces": fm[sl], "forces_uncertainty": f_unc[sl], "forces_ensemble": f_ens[sl]})
+                results[start + b] = {"energy": float(e_mean[b]), "energy_ensemble": e_h[b], "energy_uncertainty": float(e_unc[b]),
+                                      "forces": fm[sl], "forces_uncertainty": f_unc[sl], "forces_ensemble": f_ens[sl]}
+            return None
+
+        def capacity(chunk):
+            n = sum(len(a.numbers) for a in chunk)
+            ppa = state["pairs_per_atom"]
+            return int(n * self.max_pairs_per_atom) if ppa is None else int(n * ppa * 1.15) + 1024
+
+        def run_sync(start, chunk, cap):
+            while True:
+                need = finalize(enqueue(start, chunk, cap, 0))
+                if need is None:
+                    return
+                cap = need
+
+        pending, parity = None, 0
+        for s in range(0, len(atoms_list), batch_size):
+            chunk = atoms_list[s:s + batch_size]
+            if state["pairs_per_atom"] is None:          # first batch ever: size the later ones from its occupancy
+                run_sync(s, chunk, capacity(chunk))
+                continue
+            rec = enqueue(s, chunk, capacity(chunk), parity)
+            parity ^= 1
+            if pending is not None:
+                need = finalize(pending)
+                if need is not None:
+                    rec["event"].synchronize()           # drain, then redo the overflowing batch on its own
+                    run_sync(pending["start"], pending["chunk"], need)
+            pending = rec
+        if pending is not None:
+            need = finalize(pending)
+            if need is not None:
+                run_sync(pending["start"], pending["chunk"], need)
         return results
 
     def _to_host(self, name: str, t):
