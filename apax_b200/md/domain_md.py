@@ -30,6 +30,34 @@ import torch.distributed as dist
 from . import domain
 
 
+def gather_owned_rows(dec, group, world: int, R_owned, P_owned, F_owned, Rg, Pg, Fg) -> None:
+    """Every rank's owned (id, R, P, F) rows into the replicated global arrays Rg / Pg / Fg [N,3] (one all-gather; rows
+    padded to the largest owner).  Pure torch + torch.distributed: the CPU twin of the MD loop (tests, gloo) uses the same code."""
+    no = dec.n_owned
+    counts = [None] * world
+    dist.all_gather_object(counts, no, group=group)
+    m = max(counts)
+    buf = torch.zeros((m, 10), dtype=torch.float64, device=Rg.device)
+    buf[:no, 0] = dec.owned.to(torch.float64)
+    buf[:no, 1:4] = R_owned
+    buf[:no, 4:7] = P_owned
+    buf[:no, 7:10] = F_owned
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    for r, part in enumerate(parts):
+        ids = part[: counts[r], 0].to(torch.int64)
+        Rg[ids] = part[: counts[r], 1:4]
+        Pg[ids] = part[: counts[r], 4:7]
+        Fg[ids] = part[: counts[r], 7:10]
+
+
+def redistribute_from_global(Rg, Pg, Fg, Mg, box, cutoff: float, rank: int, world: int):
+    """Ownership and ghosts re-derived from the gathered positions (a pure function of them: identical on every rank) and the
+    state that travels with the atoms: (decomposition, local positions [owned, then ghosts], owned momenta / forces / masses)."""
+    dec = domain.decompose(Rg, box, cutoff, rank, world)
+    return dec, Rg[dec.local_ids].clone(), Pg[dec.owned].contiguous(), Fg[dec.owned].contiguous(), Mg[dec.owned].contiguous()
+
+
 class SlabNVT:
     def __init__(self, params: dict, atoms, model_config: Optional[dict] = None, *, dt: float, kT: float, group=None,
                  dr_threshold: float = 0.5, rebuild_every: Optional[int] = None, masses=None, momentum=None, chain_length: int = 5,
@@ -92,7 +120,8 @@ class SlabNVT:
         """Ownership, ghosts, peer layout and neighbour list from the gathered global state."""
         rt = self.rt
         old_owned = None if first else self.dec.owned
-        dec = domain.decompose(self.Rg, self.box, self.r_max + self.skin, self.rank, self.world)
+        dec, R_loc, P_own, F_own, M_own = redistribute_from_global(self.Rg, self.Pg, self.Fg, self.Mg, self.box, self.r_max + self.skin,
+                                                                   self.rank, self.world)
         if first:
             cap_rows = int(dec.n_local * self.capacity_factor) + 1024
             self.peer = domain.PeerHalo(dec, self.group, capacity_rows=cap_rows)
@@ -104,11 +133,11 @@ class SlabNVT:
         ids = dec.local_ids
         no = dec.n_owned
         self.R = self.peer.R                                   # [n_local, 3] in the peer block: owned rows, then ghost rows
-        self.R.copy_(self.Rg[ids])
+        self.R.copy_(R_loc)
         self.F = self.peer.F                                   # [1, n_local, 3]
-        self.F[0, :no].copy_(self.Fg[dec.owned])
-        self.P = self.Pg[dec.owned].contiguous()
-        self.mass = self.Mg[dec.owned].contiguous()
+        self.F[0, :no].copy_(F_own)
+        self.P = P_own
+        self.mass = M_own
         self.R_ref = self.R[:no].clone()
         cap = int(dec.n_local * self.pairs_per_atom) + 4096
         self.system = rt.PreparedMinimageSystem(self.dp, self.Zg[ids].contiguous(), cap, n_central=no, forces=self.F,
@@ -121,24 +150,9 @@ class SlabNVT:
         self.counters["rebuilds"] += 0 if first else 1
 
     def _gather(self) -> None:
-        """Every rank's owned (id, R, P, F) rows into the replicated global arrays (one all-gather; rows padded to the largest
-        owner)."""
+        """Every rank's owned (id, R, P, F) rows into the replicated global arrays."""
         no = self.dec.n_owned
-        counts = [None] * self.world
-        dist.all_gather_object(counts, no, group=self.group)
-        m = max(counts)
-        buf = torch.zeros((m, 10), dtype=torch.float64, device=self.R.device)
-        buf[:no, 0] = self.dec.owned.to(torch.float64)
-        buf[:no, 1:4] = self.R[:no]
-        buf[:no, 4:7] = self.P
-        buf[:no, 7:10] = self.F[0, :no]
-        parts = [torch.empty_like(buf) for _ in range(self.world)]
-        dist.all_gather(parts, buf, group=self.group)
-        for r, part in enumerate(parts):
-            ids = part[: counts[r], 0].to(torch.int64)
-            self.Rg[ids] = part[: counts[r], 1:4]
-            self.Pg[ids] = part[: counts[r], 4:7]
-            self.Fg[ids] = part[: counts[r], 7:10]
+        gather_owned_rows(self.dec, self.group, self.world, self.R[:no], self.P, self.F[0, :no], self.Rg, self.Pg, self.Fg)
 
     def _forces(self) -> None:
         self.peer.forward()
