@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define APAX_B200_ABI_VERSION 2
+#define APAX_B200_ABI_VERSION 3 /* 3: options, descriptor VJP, prepare_minimage, ctx stress, 512-byte halo header, slab-MD entry points */
 
 typedef struct CUstream_st* apax_stream_t; /* == cudaStream_t */
 

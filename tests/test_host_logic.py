@@ -92,7 +92,7 @@ def test_library_exports_every_declared_symbol():
     handle = _lib.lib()
     for name in declared:
         assert hasattr(handle, name), name
-    assert handle.apax_abi_version() == 2
+    assert handle.apax_abi_version() == 3
     assert handle.apax_gm_workspace_bytes(96, 9000, 1) > 0
     assert handle.apax_nl_workspace_bytes(96, 9000) > 0
 
@@ -168,7 +168,7 @@ def test_public_header_is_plain_c(tmp_path):
     if not gcc:
         pytest.skip("no gcc")
     src = tmp_path / "hdr.c"
-    src.write_text('#include "apax_b200.h"\nint main(void) { apax_gm_config c; (void)c; return APAX_B200_ABI_VERSION == 2 ? 0 : 1; }\n')
+    src.write_text('#include "apax_b200.h"\nint main(void) { apax_gm_config c; (void)c; return APAX_B200_ABI_VERSION == 3 ? 0 : 1; }\n')
     inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
     subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, "-fsyntax-only", str(src)])
 
