@@ -100,17 +100,26 @@ def run_nvt(params, atoms, model_config=None, *, dt: float, kT: float, n_steps: 
     init_fn2, apply_fn = nvt_nose_hoover(stepping_force, None, dt, kT, chain_length, chain_steps, sy_steps, tau)
     if rebuild_every is not None and on_step is None and dp.n_out == 1:
         # fixed rebuild cadence: all steps between two list builds go down in ONE library call (apax_md_nvt_run), as the
-        # reference runs them inside one jitted fori_loop (apax/md/simulate.py:313-354)
+        # reference runs them inside one jitted fori_loop (apax/md/simulate.py:313-354); the list is built AND prepared on the
+        # device in one asynchronous call (apax_gm_prepare_minimage) -- positions never leave the GPU, no COO round trip
         import ctypes as C
 
+        n_atoms = int(state.position.shape[0])
+        occupancy = int((nbrs.idx[1] < n_atoms).sum().item())
+        ps = rt.PreparedMinimageSystem(dp, Z, int(occupancy * 1.25) + 4096)
+        ps.build(state.position, box_d, r_max + dr_threshold)
+        ref_pos = state.position.clone()
         e_dev = torch.zeros(1, dtype=torch.float64, device=state.position.device)
         violations = torch.zeros(1, dtype=torch.int32, device=state.position.device)
+        overflowed = torch.zeros(1, dtype=torch.int32, device=state.position.device)
         done = 0
         while done < n_steps:
             if done > 0 and done % rebuild_every == 0:
-                maybe_rebuild(done)
+                ps.build(state.position, box_d, r_max + dr_threshold)
+                overflowed += ps.overflow.to(torch.int32)
+                ref_pos.copy_(state.position)
+                counters["rebuilds"] += 1
             k = min(rebuild_every - done % rebuild_every, n_steps - done)
-            ps = system["prepared"]
             state.force = state.force.contiguous()
             rt.check(rt.lib().apax_md_nvt_run(rt._stream_ptr(), C.byref(apply_fn.cfg), dp.handle, rt._ptr(state.position),
                                               rt._ptr(state.momentum), rt._ptr(state.force), rt._ptr(state.mass), rt._ptr(ps.Z),
@@ -118,9 +127,11 @@ def run_nvt(params, atoms, model_config=None, *, dt: float, kT: float, n_steps: 
                                               ps.wb, int(k)), "apax_md_nvt_run")
             done += k
             # skin criterion against the positions the current list was built from (no host synchronisation here)
-            violations += rt.nl_needs_rebuild(state.position, system["nbrs"].reference_position, box_d, dr_threshold)
+            violations += rt.nl_needs_rebuild(state.position, ref_pos, box_d, dr_threshold)
         counters["steps"] = n_steps
         counters["skin_violations"] = int(violations.item())
+        if int(overflowed.item()):
+            raise rt._lib.ApaxB200Error(rt._lib.ERR_OVERFLOW, "run_nvt", "neighbour list capacity exceeded during the run")
         if strict_skin and counters["skin_violations"]:
             raise rt._lib.ApaxB200Error(rt._lib.ERR_OVERFLOW, "run_nvt",
                                         f"{counters['skin_violations']} chunk(s) of {rebuild_every} steps moved an atom further than "
