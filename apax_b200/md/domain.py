@@ -222,14 +222,20 @@ class PeerHalo:
         self.red_epoch = 0
         self.configure(dec)
 
-    def configure(self, dec: SlabDecomposition) -> None:
-        """Install a decomposition: where my boundary atoms' rows live inside each peer's block, and what I send."""
+    def configure(self, dec: SlabDecomposition, barrier: bool = True) -> None:
+        """Install a decomposition: where my boundary atoms' rows live inside each peer's block, and what I send.
+        `barrier=False` leaves the ordering against the peers' first kernels of the new epoch to the caller (SlabNVT
+        closes every re-decomposition with a device-level rendezvous, which covers it without a host round trip)."""
         _lib, rt, world, rank = self._lib, self.rt, self.world, self.rank
         if dec.n_local > self.capacity:
             raise _lib.ApaxB200Error(_lib.ERR_OVERFLOW, "PeerHalo", f"{dec.n_local} local atoms exceed the block capacity {self.capacity}")
         self.dec = dec
-        meta = [None] * world
-        dist.all_gather_object(meta, (dec.n_owned, list(dec.ghost_owner_counts)), group=self.group)
+        # one small device all-gather (n_owned, ghosts per owner) instead of a pickled object exchange
+        mine = torch.tensor([dec.n_owned] + [int(c) for c in dec.ghost_owner_counts], dtype=torch.int64, device=self.e_global.device)
+        table = torch.empty((world, world + 1), dtype=torch.int64, device=self.e_global.device)
+        dist.all_gather_into_tensor(table, mine, group=self.group)
+        table = table.cpu().tolist()
+        meta = [(row[0], row[1:]) for row in table]
         self.fwd, self.rev = _lib.HaloPeers(), _lib.HaloPeers()
         for rec in (self.fwd, self.rev):
             rec.world, rec.rank = world, rank
@@ -247,7 +253,8 @@ class PeerHalo:
         self.send_local = dec.send_local.to(torch.int64).contiguous()
         self.send_ptr = np.concatenate([[0], np.cumsum(dec.send_counts)]).astype(np.int64)
         self.bytes_per_step = 2 * int(self.send_ptr[-1] + sum(dec.ghost_owner_counts)) * 24
-        dist.barrier(group=self.group)   # every rank has its new layout before the first kernel of the new epoch touches a peer
+        if barrier:
+            dist.barrier(group=self.group)   # every rank has its new layout before the first kernel of the new epoch touches a peer
 
     def forward(self) -> None:
         self.epoch += 1

@@ -118,18 +118,32 @@ class SlabNVT:
     # ------------------------------------------------------------------------------------------ data movement
     def _redistribute(self, first: bool = False) -> None:
         """Ownership, ghosts, peer layout and neighbour list from the gathered global state."""
+        import time
+
         rt = self.rt
-        old_owned = None if first else self.dec.owned
+        prof = getattr(self, "profile", None)      # optional {phase: seconds} accumulator (synchronising; measurement only)
+
+        def mark(name, t0):
+            if prof is not None:
+                torch.cuda.synchronize()
+                prof[name] = prof.get(name, 0.0) + time.perf_counter() - t0
+            return time.perf_counter()
+
+        t = time.perf_counter()
         dec, R_loc, P_own, F_own, M_own = redistribute_from_global(self.Rg, self.Pg, self.Fg, self.Mg, self.box, self.r_max + self.skin,
                                                                    self.rank, self.world)
+        t = mark("decompose", t)
         if first:
             cap_rows = int(dec.n_local * self.capacity_factor) + 1024
             self.peer = domain.PeerHalo(dec, self.group, capacity_rows=cap_rows)
         else:
-            self.peer.configure(dec)
-            if old_owned.numel() != dec.owned.numel() or not torch.equal(old_owned, dec.owned):
-                self.counters["migrated"] += int((~torch.isin(dec.owned, old_owned)).sum().item())
+            self.peer.configure(dec, barrier=False)
+            # atoms I own now that I did not own before (ownership kept as a per-atom flag: no set operations on 10^5 ids)
+            self.counters["migrated"] += int((~self.owned_flag[dec.owned]).sum().item())
+        t = mark("configure", t)
         self.dec = dec
+        self.owned_flag = torch.zeros(self.n, dtype=torch.bool, device=self.Rg.device)
+        self.owned_flag[dec.owned] = True
         ids = dec.local_ids
         no = dec.n_owned
         self.R = self.peer.R                                   # [n_local, 3] in the peer block: owned rows, then ghost rows
@@ -139,14 +153,18 @@ class SlabNVT:
         self.P = P_own
         self.mass = M_own
         self.R_ref = self.R[:no].clone()
+        t = mark("copies", t)
         cap = int(dec.n_local * self.pairs_per_atom) + 4096
         self.system = rt.PreparedMinimageSystem(self.dp, self.Zg[ids].contiguous(), cap, n_central=no, forces=self.F,
                                                 workspaces=self.workspaces)
+        t = mark("system", t)
         self.system.build(self.R, self.box, self.r_max + self.skin)
         self.system.check()
+        t = mark("list", t)
         # device-level rendezvous: no peer may push next step's ghost positions into my block before the copy above has run
         # (the host barrier inside configure() orders the host code only)
         self.peer.allreduce_sum(self.flag_d, self.flag_g)
+        t = mark("rendezvous", t)
         self.counters["rebuilds"] += 0 if first else 1
 
     def _gather(self) -> None:
