@@ -137,8 +137,8 @@ def measure_md(args, world, rank, local, ClockSampler, metric, unit, steps=None,
     wall = time.perf_counter() - t0
     ms = ev0.elapsed_time(ev1)
     launches = int(lib.apax_kernel_launch_count() - c0)
-    time.sleep(0.15)
-    clocks = sampler.stop(window_s=wall + 0.15)
+    held = sampler.hold(lambda: go(steps), ms, seconds=0.7)          # whole runs of the same length, untimed
+    clocks = sampler.stop(window_s=wall + held)
     R = state.position.cpu().numpy()
     assert np.isfinite(R).all() and np.isfinite(state.momentum.cpu().numpy()).all()
     line = {"metric": metric, "value": n * steps / (ms * 1e-3), "unit": unit, "n_gpus": 1, "steps": steps,
@@ -206,8 +206,8 @@ def measure_ensemble(args, world, rank, local, ClockSampler, metric, unit, cells
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wall = float(t.item())
     launches = int(lib.apax_kernel_launch_count() - c0)
-    time.sleep(0.15)
-    clocks = sampler.stop(window_s=wall + 0.15)
+    held = sampler.hold(go, wall / reps * 1e3, seconds=0.7)         # `wall` is the all-reduced figure: same count on every rank
+    clocks = sampler.stop(window_s=wall + held)
     assert len(res) == len(atoms_list) and np.isfinite(res[0]["forces_uncertainty"]).all()
     if rank != 0:
         return None

@@ -391,6 +391,12 @@ def measure_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit
     from apax_b200 import synthetic as syn
 
     torch.cuda.set_device(local)
+    sampler = None
+    if rank == 0:                       # started before the set-up: nvidia-smi takes about a second to deliver its first tick
+        import bench as _bench
+
+        sampler = _bench.ClockSampler(local)
+        sampler.start()
     n_mol = args.molecules * (world if args.scaling == "weak" else 1)
     pos, Z, cell = syn.water_box(n_mol, 0)
     n = len(Z)
@@ -399,12 +405,6 @@ def measure_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit
     frac = pos @ np.linalg.inv(cell)
     sysm = GpuSlabSystem(dp, frac, Z, cell.T.copy(), 6.0, rank, world, peer_halo=not getattr(args, "nccl", False))
     lib = rt.lib()
-    sampler = None
-    if rank == 0:
-        import bench as _bench
-
-        sampler = _bench.ClockSampler(local)
-        sampler.start()
     for _ in range(max(3, args.warmup)):
         e, f = sysm.step()
     torch.cuda.synchronize()
@@ -422,6 +422,14 @@ def measure_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = lib.apax_kernel_launch_count() - launches0
+    # the timed region may be shorter than one 100 ms sampler tick: hold the same load (untimed, same count on every rank)
+    ms_step = float(ms.item()) / args.steps
+    held_steps = int(min(5000, max(1, -(-700.0 // max(ms_step, 1e-3)))))
+    for _ in range(held_steps):
+        sysm.step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = sampler.stop(window_s=(args.steps + held_steps) * ms_step * 1e-3) if sampler else None
     sysm.status()
 
     # ---- per-kernel device times of this rank (CUDA events around every launch), max over ranks per kernel
@@ -499,10 +507,6 @@ def measure_multi_gpu(args, world: int, rank: int, local: int, metric: str, unit
                          dtype=torch.float64, device="cuda")
     gathered = [torch.zeros_like(stats) for _ in range(world)]
     dist.all_gather(gathered, stats)
-    # the sampler ticks every 100 ms and the timed region may be only tens of milliseconds long, so the clock summary covers
-    # the whole measurement (warm-up, timed steps, per-kernel profile, end-to-end steps, verification): the same kernels
-    # under the same load
-    clocks = sampler.stop(window_s=0.0) if sampler else None
     line = None
     if rank == 0:
         import bench as _bench

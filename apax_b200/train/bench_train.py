@@ -91,8 +91,9 @@ def measure(args, world: int, rank: int, local: int, ClockSampler, metric: str, 
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    time.sleep(0.15)
-    clocks = sampler.stop(window_s=ms_total * 1e-3 + 0.15)
+    held = sampler.hold(step.run_resident, ms_total / args.steps, seconds=0.7)
+    barrier()
+    clocks = sampler.stop(window_s=ms_total * 1e-3 + held)
     loss_now = float(step.loss.item())
     assert np.isfinite(loss_now)
 

@@ -87,6 +87,19 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def hold(self, step_fn, ms_per_step: float, seconds: float = 0.7) -> float:
+        """Keep the device under the measured load for about `seconds` more (untimed repeats of the timed step) so that
+        the 100 ms sampler collects several ticks under load even when the timed region itself is shorter than one tick.
+        The repeat count follows from `ms_per_step` alone, so every rank of a multi-GPU run issues the same number of
+        steps when it passes the all-reduced figure.  Returns the seconds of load added (for stop()'s window)."""
+        import torch
+
+        n = int(min(5000, max(1, -(-seconds * 1e3 // max(ms_per_step, 1e-3)))))
+        for _ in range(n):
+            step_fn()
+        torch.cuda.synchronize()
+        return n * ms_per_step * 1e-3
+
     def stop(self, window_s: float = 0.0):
         """Summarise the samples of the last `window_s` seconds (the timed region); 0 = all samples."""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -474,9 +487,9 @@ def measure_single_gpu(args, local):
     torch.cuda.synchronize()
     ms_total = ev0.elapsed_time(ev1)
     launches = lib.apax_kernel_launch_count() - launches0
-    time.sleep(0.15)
-    clocks = sampler.stop(window_s=ms_total * 1e-3 + 0.15)
     ms_per_step = ms_total / args.steps
+    held = sampler.hold(step, ms_per_step)
+    clocks = sampler.stop(window_s=ms_total * 1e-3 + held)
     value = n * args.steps / (ms_total * 1e-3)
     energy = float(e.cpu().numpy()[0])
     f_h = f.cpu().numpy()[0]
