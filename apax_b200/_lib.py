@@ -21,7 +21,7 @@ _ERR_NAMES = {-1: "APAX_ERR_INVALID_ARG", -2: "APAX_ERR_UNSUPPORTED", -3: "APAX_
               -5: "APAX_ERR_OVERFLOW"}
 
 DISP_GAS, DISP_OFFSETS, DISP_MINIMAGE, DISP_DRVEC = 0, 1, 2, 3
-OPT_READOUT, OPT_PAIR_BLOCK, OPT_MEAN_FORCES = 0, 1, 2
+OPT_READOUT, OPT_PAIR_BLOCK, OPT_MEAN_FORCES, OPT_CONTRACT_SPLIT = 0, 1, 2, 3
 READOUT_KINDS = {"simt": 0, "tc": 1, "i8": 2}
 
 

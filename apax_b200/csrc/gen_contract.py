@@ -229,6 +229,38 @@ def emit_forward(blocks):
     return lines
 
 
+def split_blocks(blocks, n_parts):
+    """Greedy balance of the (independent) blocks over n_parts by product-term count -> list of block lists."""
+    cost = lambda b: sum(len(terms) for _, terms in b.stmts)
+    parts, load = [[] for _ in range(n_parts)], [0] * n_parts
+    for b in sorted(blocks, key=cost, reverse=True):
+        k = load.index(min(load))
+        parts[k].append(b)
+        load[k] += cost(b)
+    return parts, load
+
+
+def emit_forward_parts(blocks, n_parts):
+    """The forward program cut into n_parts independent pieces (whole blocks each) behind a warp-uniform switch: small
+    systems run one atom on n_parts warps.  No barriers inside: the warps of a CTA execute different pieces."""
+    parts, load = split_blocks(blocks, n_parts)
+    lines = [f"  // product terms per part: {load}", "  switch (part) {"]
+    for k, bl in enumerate(parts):
+        lines.append(f"  case {k}: {{")
+        for b in bl:
+            lines.append("  {")
+            for target, terms in b.stmts:
+                if target[0] == "t":
+                    lines.append(f"    const float {target[1]} = {emit_sum(terms)};")
+                else:
+                    lines.append(f"    store({target[1]}, {emit_sum(terms)});")
+            lines.append("  }")
+        lines.append("  } break;")
+    lines.append("  default: break;")
+    lines.append("  }")
+    return lines
+
+
 def emit_backward(blocks, prefetch=2):
     """Reverse mode, block by block.  The feature adjoints gbar(f) of a block are loaded `prefetch`
     blocks ahead of their use (function-scope variables g<f>), so the global-load latency overlaps the
@@ -484,39 +516,45 @@ def emit_backward_looped(types, off):
     D, NFX = GM_RING_DEPTH, GM_RING_NF
     L = []
     L.append("  // c0: the rank-0 moments are features themselves")
+    L.append("  if (part == 0) {")
     for r in range(NR):
-        L.append(f"  a[{r * NM}] += gt[int64_t({off['c0'] + r}) * ld];")
+        L.append(f"    a[{r * NM}] += gt[int64_t({off['c0'] + r}) * ld];")
+    L.append("  }")
     for ty in types:
         n, nf, name = len(ty["instances"]), ty["nf"], ty["name"]
         (r0, r1), (s0, s1) = ty["kr"], ty["ks"]
-        L.append(f"  // ---- {name}: {n} (r, s) instances of one generic block")
+        L.append(f"  // ---- {name}: {n} (r, s) instances of one generic block; this part takes q = part, part + NP, ...")
+        L.append("  // (one fetch pipeline running across the type boundaries was measured: no gain, the fill latency is not what binds)")
         L.append("  {")
         L.append("#pragma unroll 1")
-        L.append(f"    for (int q = 0; q < {min(D - 1, n)}; ++q) {{")
+        L.append(f"    for (int k = 0; k < {D - 1}; ++k) {{")
+        L.append("      const int q = part + k * NP;")
+        L.append(f"      if (q < {n}) {{")
         for j in range(nf):
-            L.append(f"      if (gm_tab_{name}_f[q][{j}] >= 0) gm_cp_async4(ring + ((q % {D}) * {NFX} + {j}) * ring_stride, gt + int64_t(gm_tab_{name}_f[q][{j}]) * ld);")
+            L.append(f"        if (gm_tab_{name}_f[q][{j}] >= 0) gm_cp_async4(ring + (k * {NFX} + {j}) * ring_stride, gt + int64_t(gm_tab_{name}_f[q][{j}]) * ld);")
+        L.append("      }")
         L.append("      gm_cp_async_commit();")
         L.append("    }")
         L.append("#pragma unroll 1")
-        L.append(f"    for (int q = 0; q < {n}; ++q) {{")
-        L.append(f"      const int qn = q + {D - 1};")
+        L.append(f"    for (int k = 0, q = part; q < {n}; ++k, q += NP) {{")
+        L.append(f"      const int qn = q + {D - 1} * NP, slot = k % {D}, slot_n = (k + {D - 1}) % {D};")
         L.append(f"      if (qn < {n}) {{")
         for j in range(nf):
-            L.append(f"        if (gm_tab_{name}_f[qn][{j}] >= 0) gm_cp_async4(ring + ((qn % {D}) * {NFX} + {j}) * ring_stride, gt + int64_t(gm_tab_{name}_f[qn][{j}]) * ld);")
+            L.append(f"        if (gm_tab_{name}_f[qn][{j}] >= 0) gm_cp_async4(ring + (slot_n * {NFX} + {j}) * ring_stride, gt + int64_t(gm_tab_{name}_f[qn][{j}]) * ld);")
         L.append("      }")
         L.append("      gm_cp_async_commit();")
         L.append(f"      gm_cp_async_wait<{D - 1}>();   // everything but the {D - 1} youngest groups has landed: instance q is complete")
         L.append(f"      float gc[{nf}];")
         for j in range(nf):
-            L.append(f"      gc[{j}] = gm_tab_{name}_f[q][{j}] >= 0 ? ring[((q % {D}) * {NFX} + {j}) * ring_stride] : 0.0f;")
+            L.append(f"      gc[{j}] = gm_tab_{name}_f[q][{j}] >= 0 ? ring[(slot * {NFX} + {j}) * ring_stride] : 0.0f;")
         L.append(f"      const int r = gm_tab_{name}_rs[q][0], s = gm_tab_{name}_rs[q][1];")
         L.append("      float mr[20], ms[20], ar[20], as_[20];")
         L.append(f"      gm_load_channel<{r0}, {r1}>(m, r, mr);")
         L.append(f"      gm_load_channel<{s0}, {s1}>(m, s, ms);")
         L.append("#pragma unroll")
-        L.append(f"      for (int k = {r0}; k < {r1}; ++k) ar[k] = 0.0f;")
+        L.append(f"      for (int k2 = {r0}; k2 < {r1}; ++k2) ar[k2] = 0.0f;")
         L.append("#pragma unroll")
-        L.append(f"      for (int k = {s0}; k < {s1}; ++k) as_[k] = 0.0f;")
+        L.append(f"      for (int k2 = {s0}; k2 < {s1}; ++k2) as_[k2] = 0.0f;")
         b = ty["block"]
         temps = [t for t, _ in b.stmts if t[0] == "t"]
         for target, terms in b.stmts:
@@ -603,6 +641,13 @@ def main(out_path):
     src.extend(emit_forward(blocks))
     src.append("}")
     src.append("")
+    src.append("#define GM_FWD_PARTS 4")
+    src.append("// the same program in GM_FWD_PARTS independent pieces (whole blocks; `part` is warp-uniform): no barriers inside")
+    src.append("template <class Store>")
+    src.append("__device__ __forceinline__ void gm_contract_forward_part(const float (&m)[GM_N_PACKED], int part, Store store) {")
+    src.extend(emit_forward_parts(blocks, 4))
+    src.append("}")
+    src.append("")
     src.append("template <class LoadGbar>")
     src.append("__device__ __forceinline__ void gm_contract_backward(const float (&m)[GM_N_PACKED], float (&a)[GM_N_PACKED], LoadGbar gbar) {")
     src.extend(emit_backward(blocks))
@@ -616,8 +661,12 @@ def main(out_path):
     src.append(f"#define GM_RING_FLOATS_PER_THREAD {GM_RING_DEPTH * GM_RING_NF}")
     src.append("// gt: this atom's column of the feature-major adjoints (row stride ld); ring: this thread's slot 0 of a shared-memory")
     src.append("// ring of GM_RING_FLOATS_PER_THREAD floats per thread, consecutive slots ring_stride floats apart")
+    src.append("// NP > 1: the instances of every type are dealt round-robin to NP parts (one warp each, `part` warp-uniform); the")
+    src.append("// caller sums the NP partial adjoints.  NP == 1, part == 0 is the whole program.")
+    src.append("template <int NP>")
     src.append("__device__ __forceinline__ void gm_contract_backward_looped(const float (&m)[GM_N_PACKED], float (&a)[GM_N_PACKED],")
-    src.append("                                                            const float* gt, int64_t ld, float* ring, int ring_stride) {")
+    src.append("                                                            const float* gt, int64_t ld, float* ring, int ring_stride,")
+    src.append("                                                            int part = 0) {")
     src.extend(emit_backward_looped(types, off))
     src.append("}")
     src.append("")

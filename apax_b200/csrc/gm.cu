@@ -901,10 +901,128 @@ __global__ void __launch_bounds__(kContractThreads, 256 / kContractThreads) k_co
   // looped form of the reverse program: one generic block per contraction type (~15 KB of code instead of ~200 KB of
   // straight-line code that ran at 12 % issue utilisation behind instruction-fetch stalls)
   __shared__ float s_ring[GM_RING_FLOATS_PER_THREAD * kContractThreads];   // feature adjoints in flight (cp.async)
-  gm_contract_backward_looped(m, a, gt, ld, s_ring + threadIdx.x, kContractThreads);
+  gm_contract_backward_looped<1>(m, a, gt, ld, s_ring + threadIdx.x, kContractThreads);
   if (live) {
 #pragma unroll
     for (int k = 0; k < NPK; ++k) ws.AT[int64_t(k) * ws.ld + atom] = a[k];
+  }
+}
+
+// ---- small systems: one atom on kSplit warps.  Thread-per-atom leaves 12,288 atoms with one warp per scheduler on 96 SMs
+// and the kernel's duration is then the latency of ONE warp walking the whole program (55 us backward, 41 us forward).
+// The contraction blocks are independent, so here a CTA is 32 atoms x kSplit warps: warp w runs part w of the program
+// (forward: whole blocks; backward: every kSplit-th (r, s) instance of each type) on the same 32 atoms.
+constexpr int kSplit = GM_FWD_PARTS;
+static_assert(kSplit == 4 && kContractThreads == 32 * kSplit, "split contraction kernels: 4 warps per 32-atom group");
+
+// Features + digit planes, the split twin of k_contract_fwd_quantize: groups of 32 atoms (grid-stride), feature slot
+// [NFP][32] per block; the row maximum is joined across the warps through shared memory and the 64-feature chunks of
+// phase 2 are dealt to the warps (chunk kc/64 = w, w + 4).  n_groups covers the 128-row tile padding (zero digits).
+__global__ void __launch_bounds__(kContractThreads, 256 / kContractThreads)
+k_contract_fwd_quantize_split(GmWorkspace ws, const float* __restrict__ col_scale, int8_t* __restrict__ planes,
+                              int32_t* __restrict__ row_exp, int64_t n_groups) {
+  __shared__ __align__(16) uint8_t tile[kSplit][I8_DIGITS][32 * 64];
+  __shared__ float s_mx[kSplit][32];
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+  float* slot = ws.GT + int64_t(blockIdx.x) * NFP * 32 + lane;     // this atom's column of the block's slot, row stride 32
+  const int64_t plane_stride = ws.ld * int64_t(NFP);
+  for (int64_t t = blockIdx.x; t < n_groups; t += gridDim.x) {
+    const int64_t m0 = t * 32, atom_raw = m0 + lane;
+    const bool live = atom_raw < ws.n_central;
+    const int64_t atom = live ? atom_raw : ws.n_central - 1;
+    float m[NPK];
+#pragma unroll
+    for (int k = 0; k < NPK; ++k) m[k] = ws.MT[int64_t(k) * ws.ld + atom];
+    float mx = 0.0f;
+    gm_contract_forward_part(m, part, [&](int f, float v) {
+      mx = fmaxf(mx, fabsf(v * __ldg(col_scale + f)));
+      slot[f * 32] = v;
+    });
+    s_mx[part][lane] = mx;
+    __syncthreads();                       // every warp's features are in the slot, every partial maximum in s_mx
+    mx = fmaxf(fmaxf(s_mx[0][lane], s_mx[1][lane]), fmaxf(s_mx[2][lane], s_mx[3][lane]));
+    if (!(mx < 3.0e38f)) mx = 3.4e38f;   // NaN / inf rows quantise to zero
+    int e;
+    float sc, sc2;
+    i8_row_scale(live ? mx : 0.0f, I8_DIGITS, e, sc, sc2);          // rows beyond n_central (tile padding): zero digits
+    if (part == 0) row_exp[atom_raw] = e;
+#pragma unroll 1
+    for (int kc = part * 64; kc < NFP; kc += kSplit * 64) {
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        const int k0 = kc + g * 16;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (k0 + j < NF) ? slot[(k0 + j) * 32] : 0.0f;
+        uint32_t w[I8_DIGITS][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t ew[4], tb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = k0 + 4 * q + j;
+            const float c = (k < NF) ? __ldg(col_scale + k) : 0.0f;
+            ew[j] = i8_digit_word<I8_DIGITS>(sc != 0.0f ? ((v[4 * q + j] * c) * sc) * sc2 : 0.0f);
+          }
+          i8_transpose4(ew, tb);
+#pragma unroll
+          for (int d = 0; d < I8_DIGITS; ++d) w[d][q] = tb[I8_DIGITS - 1 - d];
+        }
+        const int piece = g ^ ((lane >> 1) & 3);   // 16-byte pieces of a row are xor-swizzled: conflict-free both ways
+#pragma unroll
+        for (int d = 0; d < I8_DIGITS; ++d)
+          *reinterpret_cast<uint4*>(&tile[part][d][lane * 64 + piece * 16]) = make_uint4(w[d][0], w[d][1], w[d][2], w[d][3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int d = 0; d < I8_DIGITS; ++d) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int idx = lane + 32 * j, r = idx >> 2, p = idx & 3;
+          const uint4 val = *reinterpret_cast<const uint4*>(&tile[part][d][r * 64 + (p ^ ((r >> 1) & 3)) * 16]);
+          *reinterpret_cast<uint4*>(planes + d * plane_stride + (m0 + r) * int64_t(NFP) + kc + p * 16) = val;
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();                       // the slot and s_mx are rewritten by the next group
+  }
+}
+
+// Reverse mode, split twin of k_contract_bwd: each warp accumulates the adjoint of its instances; the four partial
+// adjoints are joined pairwise through shared memory (2 x 100 x 32 floats) in a fixed order.
+__global__ void __launch_bounds__(kContractThreads, 256 / kContractThreads) k_contract_bwd_split(GmWorkspace ws) {
+  __shared__ float s_ring[GM_RING_FLOATS_PER_THREAD * kContractThreads];   // feature adjoints in flight (cp.async)
+  __shared__ float s_red[2][NPK][32];
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int64_t atom_raw = int64_t(blockIdx.x) * 32 + lane;
+  const bool live = atom_raw < ws.n_central;
+  const int64_t atom = live ? atom_raw : ws.n_central - 1;
+  float m[NPK], a[NPK];
+#pragma unroll
+  for (int k = 0; k < NPK; ++k) {
+    m[k] = ws.MT[int64_t(k) * ws.ld + atom];
+    a[k] = 0.0f;
+  }
+  gm_contract_backward_looped<kSplit>(m, a, ws.GT + atom, ws.ld, s_ring + threadIdx.x, kContractThreads, part);
+  if (part >= 2) {
+#pragma unroll
+    for (int k = 0; k < NPK; ++k) s_red[part - 2][k][lane] = a[k];
+  }
+  __syncthreads();
+  if (part < 2) {
+#pragma unroll
+    for (int k = 0; k < NPK; ++k) a[k] += s_red[part][k][lane];        // 0 += 2, 1 += 3
+  }
+  __syncthreads();
+  if (part == 1) {
+#pragma unroll
+    for (int k = 0; k < NPK; ++k) s_red[0][k][lane] = a[k];
+  }
+  __syncthreads();
+  if (part == 0 && live) {
+#pragma unroll
+    for (int k = 0; k < NPK; ++k) ws.AT[int64_t(k) * ws.ld + atom] = a[k] + s_red[0][k][lane];
   }
 }
 
@@ -1539,6 +1657,15 @@ static PairGeom make_geom(const apax_gm_params_impl* p, const double* R, const i
   return geo;
 }
 
+// moment adjoints from the feature adjoints in GT: thread per atom, or one atom on four warps for small systems
+static int launch_contract_bwd(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w) {
+  if (w.n_central <= p->contract_split)
+    APAX_LAUNCH(k_contract_bwd_split, dim3((unsigned)cdiv(w.n_central, 32)), dim3(kContractThreads), 0, stream, w);
+  else
+    APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(w.n_central, kContractThreads)), dim3(kContractThreads), 0, stream, w);
+  return APAX_OK;
+}
+
 // descriptor forward: moments + contractions -> GT
 static int gm_descriptor_impl(cudaStream_t stream, const apax_gm_params_impl* p, const GmWorkspace& w,
                               const PairGeom& geo, int feature_mode = 0) {
@@ -1550,9 +1677,15 @@ static int gm_descriptor_impl(cudaStream_t stream, const apax_gm_params_impl* p,
   if (feature_mode == 3) {
     // fused with the layer-0 quantiser of the integer readout: persistent blocks, at most two per SM, one slot each
     const int64_t n_tiles = cdiv(w.n_central, 128);
-    const int64_t blocks = n_tiles < 2 * int64_t(num_sms()) ? n_tiles : 2 * int64_t(num_sms());
-    APAX_LAUNCH(k_contract_fwd_quantize, dim3((unsigned)blocks), dim3(kContractThreads), 0, stream, w, w.q_cs, w.q_planes, w.q_row_exp,
-                n_tiles);
+    if (w.n_central <= p->contract_split) {       // small system: 32-atom groups, one atom on four warps
+      const int64_t n_groups = 4 * n_tiles, cap = 8 * int64_t(num_sms());
+      APAX_LAUNCH(k_contract_fwd_quantize_split, dim3((unsigned)(n_groups < cap ? n_groups : cap)), dim3(kContractThreads), 0, stream,
+                  w, w.q_cs, w.q_planes, w.q_row_exp, n_groups);
+    } else {
+      const int64_t blocks = n_tiles < 2 * int64_t(num_sms()) ? n_tiles : 2 * int64_t(num_sms());
+      APAX_LAUNCH(k_contract_fwd_quantize, dim3((unsigned)blocks), dim3(kContractThreads), 0, stream, w, w.q_cs, w.q_planes,
+                  w.q_row_exp, n_tiles);
+    }
   } else if (feature_mode == 1) {
     APAX_LAUNCH(k_contract_fwd<1>, grid_c, dim3(kContractThreads), 0, stream, w);
   } else if (feature_mode == 2) {
@@ -1786,7 +1919,7 @@ static int gm_compute_impl(cudaStream_t stream, const apax_gm_params_impl* p, co
     const int head = mean_only ? n_out : pass;
     // every backward pass reads only what the forward pass left behind (D1, D2 / its planes, ebar): nothing to redo
     APAX_TRY(readout(head));
-    APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(N, kContractThreads)), dim3(kContractThreads), 0, stream, w);
+    APAX_TRY(launch_contract_bwd(stream, p, w));
     APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc, (p->generic_basis ? kPairGeneric : p->pair_block));
     if (p->corr.zbl_on || p->corr.exp_on)
       APAX_LAUNCH(k_pair_corrections<1>, dim3((unsigned)cdiv(N * 32, 256)), dim3(256), 0, stream, w, geo, p->corr, n_out);
@@ -1842,6 +1975,7 @@ extern "C" int apax_gm_params_create(const apax_gm_config* cfg, const float* emb
   p->generic_basis = (cfg->basis_kind != 0 || cfg->n_basis != NB) ? 1 : 0;   // pair kernels with the [5][16] coefficient table
   p->pair_block = 1;
   p->mean_forces = 0;
+  p->contract_split = 8192;    // one wave of 32-atom groups on 148 SMs x 2 CTAs; tools/split_ab.py: -16 % at 1,026 atoms, break-even at 12,288
   const int S = cfg->n_species, n_out = cfg->n_out;
   // n_contr < 8 truncates the feature list c0|c1|...|c7 (gaussian_moment_descriptor.py:101): the caller's first dense layer
   // has n_feat rows; the kernels always produce all 360 features, the dropped ones meet zero weight rows (and receive a
@@ -2028,6 +2162,10 @@ extern "C" int apax_gm_params_set_option(apax_gm_params* p, int32_t option, int3
       if (value != 0 && value != 1) return APAX_ERR_INVALID_ARG;
       p->mean_forces = value;
       return APAX_OK;
+    case APAX_OPT_CONTRACT_SPLIT:
+      if (value < 0) return APAX_ERR_INVALID_ARG;
+      p->contract_split = value;
+      return APAX_OK;
     case APAX_OPT_PAIR_BLOCK:
       if (value < 0 || value > 4) return APAX_ERR_INVALID_ARG;
       p->pair_block = value;
@@ -2157,7 +2295,7 @@ extern "C" int apax_gm_descriptor_vjp(apax_stream_t stream_, const apax_gm_param
   // reverse: g_bar -> moment adjoints -> per-pair dE/d(dr_vec)
   APAX_LAUNCH(k_features_from_rowmajor, dim3((unsigned)cdiv(w.ld, 32), cdiv(NF, 32)), dim3(256), 0, stream, g_bar, w.ld, n_atoms,
               w.GT);
-  APAX_LAUNCH(k_contract_bwd, dim3((unsigned)cdiv(w.n_central, kContractThreads)), dim3(kContractThreads), 0, stream, w);
+  APAX_TRY(launch_contract_bwd(stream, p, w));
   APAX_DISPATCH_LPA(lpa, launch_pair_bwd, stream, w, dc, (p->generic_basis ? kPairGeneric : p->pair_block));
   if (dr_vec_bar) {
     APAX_CUDA_TRY(cudaMemsetAsync(dr_vec_bar, 0, sizeof(double) * 3 * size_t(n_pairs), stream));

@@ -33,6 +33,7 @@ struct apax_gm_params_impl {
   int readout_mode;               // APAX_READOUT_* (apax_gm_params_set_option)
   int pair_block;                 // block shape of the pair kernels, 0..2 (measurement switch)
   int generic_basis;              // radial basis other than the 7 linearly spaced Gaussians: pair kernels with GEN = 1
+  int contract_split;             // central atoms up to which the contraction kernels run one atom on four warps (0 = never)
   int mean_forces;                // n_out > 1: forces[1][N][3] of the MEAN energy in one backward pass instead of per head
   // device copies
   float* emb;    // [S][S][5][7], pre-multiplied by 1/sqrt(n_basis) when use_embed_norm

@@ -131,6 +131,9 @@ class DeviceParams:
         if cfg.get("mean_forces"):
             check(lib().apax_gm_params_set_option(handle, _lib.OPT_MEAN_FORCES, 1), "apax_gm_params_set_option(mean_forces)")
             self.n_force_heads = 1
+        if cfg.get("contract_split") is not None:
+            check(lib().apax_gm_params_set_option(handle, _lib.OPT_CONTRACT_SPLIT, int(cfg["contract_split"])),
+                  "apax_gm_params_set_option(contract_split)")
         if cfg.get("pair_block") is not None:
             check(lib().apax_gm_params_set_option(handle, _lib.OPT_PAIR_BLOCK, int(cfg["pair_block"])),
                   "apax_gm_params_set_option(pair_block)")

@@ -95,9 +95,12 @@ int apax_gm_params_status(const apax_gm_params* p);
  * of the pair kernels, 0..2 (results are bitwise identical; measurement only).  APAX_OPT_MEAN_FORCES (shallow ensembles,
  * n_out > 1): 1 = every later evaluation returns forces f64 [1][n_atoms][3] = -d(mean over heads of E)/dR from ONE backward
  * pass -- ShallowEnsembleModel with force_variance = False (apax/nn/models.py:265-267) and the mean-energy gradient of the MD
- * energy function (apax/md/simulate.py:55-58) -- instead of the per-head forces of jacrev.  Not to be called while an evaluation with
+ * energy function (apax/md/simulate.py:55-58) -- instead of the per-head forces of jacrev.  APAX_OPT_CONTRACT_SPLIT: systems of
+ * at most `value` central atoms run the contraction kernels with one atom on four warps (small systems are bound by the
+ * latency of one warp walking the whole contraction program); 0 = never; default 8192 (one wave of 32-atom groups).  Results differ from the one-thread
+ * form only in the summation order of the moment adjoints (fp32 rounding).  Not to be called while an evaluation with
  * these parameters is being enqueued from another thread. */
-typedef enum { APAX_OPT_READOUT = 0, APAX_OPT_PAIR_BLOCK = 1, APAX_OPT_MEAN_FORCES = 2 } apax_gm_option;
+typedef enum { APAX_OPT_READOUT = 0, APAX_OPT_PAIR_BLOCK = 1, APAX_OPT_MEAN_FORCES = 2, APAX_OPT_CONTRACT_SPLIT = 3 } apax_gm_option;
 typedef enum { APAX_READOUT_SIMT = 0, APAX_READOUT_TC = 1, APAX_READOUT_I8 = 2 } apax_readout_kind;
 int apax_gm_params_set_option(apax_gm_params* p, int32_t option, int32_t value);
 

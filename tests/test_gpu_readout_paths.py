@@ -46,3 +46,26 @@ def test_option_rejects_unknown_values():
     assert rt.lib().apax_gm_params_set_option(dp.handle, _lib.OPT_READOUT, 7) == _lib.ERR_INVALID_ARG
     assert rt.lib().apax_gm_params_set_option(dp.handle, 99, 0) == _lib.ERR_INVALID_ARG
     assert rt.lib().apax_gm_params_set_option(dp.handle, _lib.OPT_PAIR_BLOCK, 0) == _lib.OK
+
+
+@pytest.mark.parametrize("n_mol,n_out", [(1500, 1), (45, 1), (300, 3)])
+def test_split_contraction_kernels_match_thread_per_atom_kernels(n_mol, n_out):
+    """Small systems run the contraction kernels with one atom on four warps (APAX_OPT_CONTRACT_SPLIT, default up to 8,192
+    central atoms); config {"contract_split": 0} forces the thread-per-atom kernels.  Every feature is computed by the same
+    instruction sequence in both forms, so the digit planes and the energies are bitwise identical; the moment adjoints
+    are summed in a different order, so forces agree at fp32 rounding level."""
+    from apax_b200 import runtime as rt
+
+    pos, Z, cell = syn.water_box(n_mol, seed=7)
+    out = {}
+    for split in (0, 1 << 20):
+        dp = rt.DeviceParams(syn.gmnn_params(seed=3, n_out=n_out, random_scale_shift=True, random_bias=True),
+                             {"n_out": n_out, "contract_split": split})
+        ctx = rt.HostContext(dp, len(Z), 120 * len(Z))
+        e, f = ctx.calculate(pos, Z.astype(np.int32), cell, dr_threshold=0.0, rebuild=True)
+        ctx.close()
+        out[split] = (np.asarray(e).copy(), np.asarray(f).copy())
+    (e0, f0), (e1, f1) = out[0], out[1 << 20]
+    assert np.array_equal(e0, e1)
+    fmax = np.abs(f0).max()
+    assert np.isfinite(f1).all() and np.abs(f1 - f0).max() <= 2e-6 * fmax, np.abs(f1 - f0).max() / fmax
