@@ -213,20 +213,22 @@ __global__ void __launch_bounds__(256) k_cell_pack(const double* __restrict__ po
 //           already captured by a PASS 2 scan and are skipped).
 //   PASS 2: count AND park the first `stride` accepted neighbours of every atom in a fixed-stride scratch row, so
 //           that one scan suffices whenever no row exceeds the stride.
-template <int MODE, int PASS>
+// LGT lanes per atom: LG for large systems; a whole warp for the few-hundred-atom image lists, whose 27+ image cells x N
+// candidates per atom are otherwise walked by eight lanes (96 atoms: 84 + 107 us of a 0.47 ms calculator call).
+template <int MODE, int PASS, int LGT = LG>
 __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos, int64_t N,
                                                  const NlGrid* __restrict__ gridp, NlWorkspace w, int stride,
                                                  int32_t* __restrict__ scratch) {
   constexpr bool FILL = PASS != 0;
   __shared__ NlGrid g;
-  __shared__ int s_cnt[256 / LG];   // PASS 1 / 2: running slot counter of each lane group
+  __shared__ int s_cnt[256 / LGT];   // PASS 1 / 2: running slot counter of each lane group
   if (threadIdx.x == 0) g = *gridp;
-  if (threadIdx.x < 256 / LG) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x < 256 / LGT) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const int64_t gid = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  const bool valid = gid / LG < N;
-  const int64_t atom = valid ? gid / LG : 0;  // out-of-range lanes stay alive for the shuffles below
-  const int sub = int(gid % LG);
+  const bool valid = gid / LGT < N;
+  const int64_t atom = valid ? gid / LGT : 0;  // out-of-range lanes stay alive for the shuffles below
+  const int sub = int(gid % LGT);
   const double ax = pos[3 * atom], ay = pos[3 * atom + 1], az = pos[3 * atom + 2];
   int c[3];
   {
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
     c2_lo = (cut - delta) * (cut - delta);
     c2_hi = (cut + delta) * (cut + delta);
   }
-  const int grp = threadIdx.x / LG;
+  const int grp = threadIdx.x / LGT;
   const int64_t base = PASS == 1 ? int64_t(w.rowptr[atom]) : PASS == 2 ? atom * int64_t(stride) : 0;
   int count = 0;
   int m0 = (valid && !(PASS == 1 && w.rowcnt[atom] <= stride)) ? g.m[0] : -1;
@@ -277,9 +279,9 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
     const int n1 = 2 * g.m[1] + 1, n2 = 2 * g.m[2] + 1;
     const int ncell = (2 * g.m[0] + 1) * n1 * n2;   // uniform over the grid
     if (ncell <= kMaxCells) {
-      __shared__ int s_cb[256 / LG][kMaxCells], s_ce[256 / LG][kMaxCells];
+      __shared__ int s_cb[256 / LGT][kMaxCells], s_ce[256 / LGT][kMaxCells];
       if (m0 >= 0) {
-        for (int cc = sub; cc < ncell; cc += LG) {
+        for (int cc = sub; cc < ncell; cc += LGT) {
           const int q0 = c[0] + cc / (n2 * n1) - g.m[0], q1 = c[1] + (cc / n2) % n1 - g.m[1], q2 = c[2] + cc % n2 - g.m[2];
           const int s0 = q0 >= 0 ? q0 / g.nc[0] : -((-q0 + g.nc[0] - 1) / g.nc[0]);
           const int s1 = q1 >= 0 ? q1 / g.nc[1] : -((-q1 + g.nc[1] - 1) / g.nc[1]);
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
         float4 q_nxt = cc < ncell ? w.cell_pos[t] : make_float4(0.f, 0.f, 0.f, 0.f);
         while (cc < ncell) {
           const float4 q = q_nxt;
-          t += LG;
+          t += LGT;
           while (t >= ce && ++cc < ncell) { t = s_cb[grp][cc] + sub; ce = s_ce[grp][cc]; }
           if (cc < ncell) q_nxt = w.cell_pos[t];
           const int j = __float_as_int(q.w);
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
         const int k2 = q2 - s2 * g.nc[2];
         const int cid = (k0 * g.nc[1] + k1) * g.nc[2] + k2;
         const int cb = w.cellptr[cid], ce = w.cellptr[cid + 1];
-        for (int t = cb + sub; t < ce; t += LG) {
+        for (int t = cb + sub; t < ce; t += LGT) {
           int j = 0;
           bool keep = false;
           int packed = 0;
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(256) k_nl_scan(const double* __restrict__ pos,
   }
   if (PASS == 0) {
 #pragma unroll
-    for (int o = LG / 2; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    for (int o = LGT / 2; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
     if (valid && sub == 0) w.rowcnt[atom] = count;
   } else if (PASS == 2) {
     __syncwarp();
@@ -554,7 +556,8 @@ static int nl_build_common(cudaStream_t stream, const double* pos, const double*
               w.cell_tmp);
   APAX_TRY(rowsort_i32(stream, w.cellptr, N, w.cell_tmp, nullptr, w.cell_atoms, nullptr));
   if (MODE == 0) APAX_LAUNCH(k_cell_pack, dim3((unsigned)cdiv(N, 256)), dim3(256), 0, stream, pos, N, w.cell_atoms, w.cell_pos);
-  const dim3 grid_scan((unsigned)cdiv(N * LG, 256));
+  const bool wide = MODE == 1 && N <= 2048;      // small image lists: a warp per atom
+  const dim3 grid_scan((unsigned)cdiv(N * (wide ? 32 : LG), 256));
   // Min-image lists carry no shifts, so the two shift buffers (2 x capacity ints, contiguous up to alignment padding)
   // serve as fixed-stride scratch rows and ONE candidate scan both counts and captures the neighbours; only rows
   // longer than the stride (none for ordinary densities: the stride is ~twice the mean row) are re-scanned.
@@ -573,14 +576,14 @@ static int nl_build_common(cudaStream_t stream, const double* pos, const double*
     APAX_LAUNCH(k_nl_scan_single, grid_scan, dim3(256), 0, stream, pos, N, w.grid, w, stride, scratch);
   } else {
     APAX_CUDA_TRY(cudaMemsetAsync(w.rowcnt, 0, sizeof(int32_t) * (N + 1), stream));
-    auto k_nl_scan_count = k_nl_scan<MODE, 0>;
+    auto k_nl_scan_count = wide ? k_nl_scan<MODE, 0, 32> : k_nl_scan<MODE, 0>;
     APAX_LAUNCH(k_nl_scan_count, grid_scan, dim3(256), 0, stream, pos, N, w.grid, w, 0, scratch);
   }
   APAX_TRY(exclusive_scan_i32(stream, w.rowcnt, w.rowptr, N, w.scan_scratch));
   APAX_LAUNCH(k_nl_finish_count, dim3((unsigned)cdiv(N + 1, 256)), dim3(256), 0, stream, N, capacity, w.rowptr,
               w.rowptr_c, n_found, overflow);
   {
-    auto k_nl_scan_fill = k_nl_scan<MODE, 1>;   // with a stride: only the rows the single scan could not hold
+    auto k_nl_scan_fill = wide ? k_nl_scan<MODE, 1, 32> : k_nl_scan<MODE, 1>;   // with a stride: only the rows the single scan could not hold
     APAX_LAUNCH(k_nl_scan_fill, grid_scan, dim3(256), 0, stream, pos, N, w.grid, w, stride > 0 ? stride : -1, scratch);
   }
   if (stride > 0) {
@@ -680,16 +683,37 @@ __global__ void __launch_bounds__(128) k_nlb_scan(const double* __restrict__ pos
   const int wc0 = wrap[3 * c], wc1 = wrap[3 * c + 1], wc2 = wrap[3 * c + 2];
   int count = 0;
   const int base = FILL ? rowptr[c] : 0;
+  // fp32 pre-filter (as in the min-image scan): the displacement to the image with S = d is formed in fp64 once per partner
+  // and rounded; the 27+ lattice translations are subtracted in fp32.  Candidates whose approximate distance is outside
+  // cutoff +- delta are decided there, only the thin shell around the cutoff pays for the exact fp64 predicate -- the pair
+  // set is unchanged.  delta >> the fp32 error of a few subtractions at the magnitude of the farthest image.
+  float Cf[9], mag = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Cf[k] = float(g.C[k]);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) mag += float(g.m[a] + 2) * (fabsf(Cf[3 * a]) + fabsf(Cf[3 * a + 1]) + fabsf(Cf[3 * a + 2]));
+  const float cut = sqrtf(float(cutoff_sq));
+  const float delta = 1e-3f + 1e-5f * mag;
+  const float c_in = fmaxf(cut - delta, 0.f);
+  const float c2_lo = c_in * c_in, c2_hi = (cut + delta) * (cut + delta);
   for (int i = struct_ptr[b]; i < struct_ptr[b + 1]; ++i) {
     const double ix = pos[3 * int64_t(i)], iy = pos[3 * int64_t(i) + 1], iz = pos[3 * int64_t(i) + 2];
     const int d0 = wrap[3 * int64_t(i)] - wc0, d1 = wrap[3 * int64_t(i) + 1] - wc1, d2 = wrap[3 * int64_t(i) + 2] - wc2;
-    for (int n0 = -g.m[0]; n0 <= g.m[0]; ++n0)
-      for (int n1 = -g.m[1]; n1 <= g.m[1]; ++n1)
+    const float bx = float((cx - ix) + (double(d0) * g.C[0] + double(d1) * g.C[3] + double(d2) * g.C[6]));
+    const float by = float((cy - iy) + (double(d0) * g.C[1] + double(d1) * g.C[4] + double(d2) * g.C[7]));
+    const float bz = float((cz - iz) + (double(d0) * g.C[2] + double(d1) * g.C[5] + double(d2) * g.C[8]));
+    for (int n0 = -g.m[0]; n0 <= g.m[0]; ++n0) {
+      const float t0x = bx - float(n0) * Cf[0], t0y = by - float(n0) * Cf[1], t0z = bz - float(n0) * Cf[2];
+      for (int n1 = -g.m[1]; n1 <= g.m[1]; ++n1) {
+        const float t1x = t0x - float(n1) * Cf[3], t1y = t0y - float(n1) * Cf[4], t1z = t0z - float(n1) * Cf[5];
         for (int n2 = -g.m[2]; n2 <= g.m[2]; ++n2) {
+          const float ex = t1x - float(n2) * Cf[6], ey = t1y - float(n2) * Cf[7], ez = t1z - float(n2) * Cf[8];
+          const float d2f = ex * ex + ey * ey + ez * ez;
+          if (d2f > c2_hi) continue;
           const int S0 = d0 - n0, S1 = d1 - n1, S2 = d2 - n2;  // D = r_c - r_i + S.cell
           if (i == c && S0 == 0 && S1 == 0 && S2 == 0) continue;
           if (S0 < -127 || S0 > 127 || S1 < -127 || S1 > 127 || S2 < -127 || S2 > 127) continue;
-          if (dist_sq_image(g.C, cx, cy, cz, ix, iy, iz, S0, S1, S2) < cutoff_sq) {
+          if (d2f < c2_lo || dist_sq_image(g.C, cx, cy, cz, ix, iy, iz, S0, S1, S2) < cutoff_sq) {
             if (FILL) {
               const int slot = base + count;
               if (slot < capacity) {
@@ -700,6 +724,8 @@ __global__ void __launch_bounds__(128) k_nlb_scan(const double* __restrict__ pos
             ++count;
           }
         }
+      }
+    }
   }
   if (!FILL) rowcnt[c] = count;
 }

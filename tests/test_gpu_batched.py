@@ -76,3 +76,42 @@ def test_batch_eval_mirror():
         assert abs(r["energy"] - s["energy"]) <= 1e-6 * abs(s["energy"])
         assert_force_parity(r["forces"], s["forces"], where="batch_eval vs calculate")      # literal tolerance
         assert r["forces_ensemble"].shape == (128, 3, 4) and np.abs(r["forces_uncertainty"] - s["forces_uncertainty"]).max() < 1e-5
+
+
+def test_batched_image_lists_skewed_cells_and_cutoff_shell():
+    """The batched scan decides most candidates in fp32 and only the shell around the cutoff in fp64: the pair set must
+    stay bit-exact for strongly sheared small cells (image range 2-3 per axis), atoms far outside their cell (non-zero
+    wrap), and pairs placed within 1e-9 A on either side of the cutoff."""
+    from apax_b200 import runtime as rt
+    from oracle import neighbor_oracle as no
+
+    rng = np.random.default_rng(11)
+    pos_l, cells, ptr = [], [], [0]
+    for s in range(5):
+        L = [3.1, 4.0, 5.5, 7.3, 12.5][s]
+        c = np.diag(rng.uniform(0.9, 1.3, 3) * L) + rng.uniform(-0.35, 0.35, (3, 3)) * L * (s % 2 + 0.2)
+        n = [5, 9, 14, 23, 40][s]
+        p = rng.uniform(-1.5, 2.5, (n, 3)) @ c                     # fractional coordinates in [-1.5, 2.5)
+        if s == 4:                                                 # partners straddling the cutoff by +-1e-9 A
+            u = rng.normal(size=(6, 3))
+            u /= np.linalg.norm(u, axis=1)[:, None]
+            for k in range(6):
+                p[2 * k + 1] = p[2 * k] + u[k] * (6.0 + (1e-9 if k % 2 else -1e-9)) + np.array([1, -1, 0]) @ c * (k % 3 - 1)
+        pos_l.append(p)
+        cells.append(c)
+        ptr.append(ptr[-1] + n)
+    R, cells_a, ptr_a = np.concatenate(pos_l), np.stack(cells), np.array(ptr, dtype=np.int32)
+    cap = 4000 * len(R)
+    idx, shifts, offsets, n_found, ov = rt.nl_build_images_batched(R, cells_a, ptr_a, 6.0, cap)
+    nf = int(n_found.item())
+    assert not int(ov.item())
+    idx_h, sh_h = idx[:, :nf].cpu().numpy(), shifts[:nf].cpu().numpy()
+    total = 0
+    for b in range(5):
+        ii, jj, ss = no.vesin_full_list(pos_l[b], cells[b], 6.0)
+        sel = (idx_h[1] >= ptr[b]) & (idx_h[1] < ptr[b + 1])
+        got = set(zip((idx_h[0, sel] - ptr[b]).tolist(), (idx_h[1, sel] - ptr[b]).tolist(), map(tuple, sh_h[sel].tolist())))
+        want = set(zip(ii.tolist(), jj.tolist(), map(tuple, ss.tolist())))
+        assert got == want, (b, len(got), len(want))
+        total += len(ii)
+    assert total == nf
