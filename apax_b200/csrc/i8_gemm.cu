@@ -420,6 +420,10 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
       const int64_t m = int64_t(int(blockIdx.x) + mt * int(gridDim.x)) * I8_BM + row;
       const float scale = exp2_int(epi.row_exp ? epi.row_exp[m] : epi.fixed_exp);
       const float rmul = (MODE == I8_EPI_MULD_Q && epi.row_mul) ? epi.row_mul[m] : 1.0f;
+      // swish' of layer 0 (written by ACT_Q, read by MULD_Q): tile-major [atom tile][output][128]
+      float* aux_tile = (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_MULD_Q)
+                            ? epi.aux + int64_t(int(blockIdx.x) + mt * int(gridDim.x)) * (num_n_sub * I8_BN) * I8_BM + row
+                            : nullptr;
       float mx = 0.0f;
       float hacc[NOUT];
 #pragma unroll
@@ -434,8 +438,9 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
         const uint32_t buf = tile & 1, use = tile >> 1;
         float auxv[PW];   // MULD_Q: the multipliers of this sub-tile, requested before the wait so that their latency hides
         if (MODE == I8_EPI_MULD_Q) {
+          const float* ap = aux_tile + int64_t(j * I8_BN + half * PW) * I8_BM;   // one 64-bit base, immediate offsets below
 #pragma unroll
-          for (int i = 0; i < PW; ++i) auxv[i] = epi.aux[int64_t(j * I8_BN + half * PW + i) * epi.ld + m];
+          for (int i = 0; i < PW; ++i) auxv[i] = ap[i * I8_BM];
         }
         const long long c0 = clock64();
         ok = mbar_wait(smem_u32(&acc_full[buf]), use & 1, err);
@@ -463,7 +468,12 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
             mbar_arrive(smem_u32(&acc_empty[buf]));
           }
           const int nb = j * I8_BN + c;                     // first output of this chunk
-          float* gp = (MODE == I8_EPI_STORE ? epi.out : epi.aux) + int64_t(nb) * epi.ld + m;   // walks down the feature rows
+          float* gp = epi.out + int64_t(nb) * epi.ld + m;   // STORE: walks down the feature rows of the [n][ld] output
+          // ACT_Q / MULD_Q: the derivative matrix and the staging rows are tile-major [atom tile][output][128 atoms], so
+          // every element of the chunk is one 64-bit base plus a compile-time offset (with [n][ld] addressing the sweep
+          // spent 7 of its 44 instructions per element on 64-bit address arithmetic)
+          float* ap = MODE == I8_EPI_ACT_Q ? aux_tile + int64_t(nb) * I8_BM : nullptr;
+          float* sp = (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_MULD_Q) ? scratch + int64_t(nb) * I8_BM : nullptr;
           const bool all_valid = MODE != I8_EPI_STORE || nb + 16 <= epi.n_valid;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -481,8 +491,8 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
               const float h = cs * z;
               const float d = cs * fmaf(z, 1.0f - sg, 1.0f);
               if (MODE == I8_EPI_ACT_Q) {
-                *gp = d;
-                scratch[(nb + i) * I8_BM] = h;
+                ap[i * I8_BM] = d;
+                sp[i * I8_BM] = h;
                 mx = fmaxf(mx, fabsf(h * s_qcs[n]));
               } else {
                 if (NOUT == 1) {
@@ -496,10 +506,10 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
               }
             } else {
               const float t = y * auxv[ri] * rmul;
-              scratch[(nb + i) * I8_BM] = t;
+              sp[i * I8_BM] = t;
               mx = fmaxf(mx, fabsf(t * s_qcs[n]));
             }
-            gp += epi.ld;
+            if (MODE == I8_EPI_STORE) gp += epi.ld;
           }
         }
         if (MODE == I8_EPI_ACT_HEAD)
@@ -513,8 +523,9 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
         // the row maximum, so the first batch is requested before the exchange.
         const long long p0 = clock64();
         float cur[PW];
+        const float* rp = scratch + int64_t(half * PW) * I8_BM;
 #pragma unroll
-        for (int i = 0; i < PW; ++i) cur[i] = scratch[(half * PW + i) * I8_BM];
+        for (int i = 0; i < PW; ++i) cur[i] = rp[i * I8_BM];
         xmax[half][row] = mx;
         epi_bar_sync<R::kEpiThreads>();
 #pragma unroll
@@ -531,8 +542,9 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
           for (int i = 0; i < PW; ++i) cur[i] *= s_qcs[nb + i];
           i8_emit_cols<PW>(cur, sc, sc2, epi.q_planes + m * epi.q_kp + nb, epi.q_plane_stride);
           if (j + 1 < num_n_sub) {
+            rp += I8_BN * I8_BM;
 #pragma unroll
-            for (int i = 0; i < PW; ++i) cur[i] = scratch[(nb + I8_BN + i) * I8_BM];
+            for (int i = 0; i < PW; ++i) cur[i] = rp[i * I8_BM];
           }
         }
         w_phase2 += clock64() - p0;

@@ -67,7 +67,7 @@ struct I8Epilogue {
   int fixed_exp;
   float* out;              // STORE: [n][ld]
   const float* bias;       // ACT_*: [n]
-  float* aux;              // ACT_Q: swish' written [n][ld];  MULD_Q: multiplier read
+  float* aux;              // ACT_Q: swish' written, MULD_Q: multiplier read -- tile-major [atom tile][n_outputs][128 atoms]
   const float* row_mul;    // MULD_Q: per-atom factor [ld] (may be null)
   // digit planes produced for the next GEMM (always four planes of a [rows][q_kp] matrix)
   int8_t* q_planes;
