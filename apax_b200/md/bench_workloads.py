@@ -188,12 +188,12 @@ def measure_ensemble(args, world, rank, local, ClockSampler, metric, unit, cells
     def go():
         return calc.batch_eval(atoms_list, batch_size=bs)
 
+    sampler = ClockSampler(local, enabled=(rank == 0))             # started before the warm-up: nvidia-smi needs ~1 s to tick
+    sampler.start()
     go()                                                           # warm-up (one full pass)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     c0 = lib.apax_kernel_launch_count()
     reps = max(1, reps or args.steps)
     t0 = time.perf_counter()

@@ -74,7 +74,7 @@ def measure(args, world: int, rank: int, local: int, ClockSampler, metric: str, 
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, enabled=(rank == 0))
     sampler.start()
     for _ in range(max(3, args.warmup)):
         step.run_resident()

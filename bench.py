@@ -72,12 +72,15 @@ class ClockSampler:
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, enabled: bool = True):
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.enabled = enabled      # multi-GPU runs sample on rank 0 only: eight polling nvidia-smi processes slow the host side
 
     def start(self):
+        if not self.enabled:
+            return
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
