@@ -833,6 +833,17 @@ int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const
     if (a_bytes + 3 * stage_bytes <= budget) break;
     if (L.a_res == 0) return APAX_ERR_INVALID_ARG;
   }
+  // measurement (apax_i8_set_debug flags 32 / 64): one / two fewer resident planes than fit, i.e. a deeper weight ring
+  // (more bytes in flight) paid for with re-streamed activation planes
+  {
+    const int dbgf = g_i8_dbg_flags.load(std::memory_order_relaxed);
+    int drop = ((dbgf & 32) ? 1 : 0) + ((dbgf & 64) ? 2 : 0);
+    while (drop-- > 0 && L.a_res > 1 && L.a_res * L.num_kb * int(I8_A_TILE) > 100 * 1024) {
+      --L.a_res;
+      a_bytes = uint32_t(L.num_kb * L.a_res) * I8_A_TILE;
+      stage_bytes = I8_B_STAGE + uint32_t(L.a_planes - L.a_res) * I8_A_TILE;
+    }
+  }
   L.b_stages = int((budget - a_bytes) / stage_bytes);
   if (L.b_stages > I8_MAX_B_STAGES) L.b_stages = I8_MAX_B_STAGES;
   L.smem = a_bytes + uint32_t(L.b_stages) * stage_bytes + 1024;

@@ -19,7 +19,7 @@ system = rt.PreparedMinimageSystem(dp, Z, int(n * 96) + 4096)
 system.build(frac, box, 6.0)
 system.check()
 ref = None
-for flag, name in ((0, "8 epilogue warps"), (16, "16 epilogue warps")):
+for flag, name in ((0, "shipped"), (32, "one fewer resident plane (K = 384: 2 resident, 3 x 32 KB stages)"), (64, "two fewer (K = 384: 1 resident, 4 x 40 KB stages, two MMA warps)")):
     rt.lib().apax_i8_set_debug(flag, 0)
     for _ in range(3):
         e, f = system.compute(frac, box, None, "minimage")
