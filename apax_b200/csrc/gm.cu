@@ -824,7 +824,10 @@ k_contract_fwd_quantize(GmWorkspace ws, const float* __restrict__ col_scale, int
                         int32_t* __restrict__ row_exp, int64_t n_tiles) {
   static_assert(kContractThreads == 128, "one thread per atom of a 128-atom GEMM tile");
   __shared__ __align__(16) uint8_t tile[I8_DIGITS][128 * 64];
+  __shared__ float s_cs[NFP];            // per-feature powers of two (0 for the padding features): broadcast shared-memory reads
   const int tid = threadIdx.x;
+  for (int k = tid; k < NFP; k += kContractThreads) s_cs[k] = k < NF ? col_scale[k] : 0.0f;
+  __syncthreads();
   float* slot = ws.GT + int64_t(blockIdx.x) * NFP * 128 + tid;     // this thread's column of the block's slot, row stride 128
   const int64_t plane_stride = ws.ld * int64_t(NFP);
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -836,7 +839,7 @@ k_contract_fwd_quantize(GmWorkspace ws, const float* __restrict__ col_scale, int
     for (int k = 0; k < NPK; ++k) m[k] = ws.MT[int64_t(k) * ws.ld + atom];
     float mx = 0.0f;
     gm_contract_forward(m, [&](int f, float v) {
-      mx = fmaxf(mx, fabsf(v * __ldg(col_scale + f)));
+      mx = fmaxf(mx, fabsf(v * s_cs[f]));
       slot[f * 128] = v;
     });
     if (!(mx < 3.0e38f)) mx = 3.4e38f;   // NaN / inf rows quantise to zero
@@ -844,44 +847,50 @@ k_contract_fwd_quantize(GmWorkspace ws, const float* __restrict__ col_scale, int
     float sc, sc2;
     i8_row_scale(live ? mx : 0.0f, I8_DIGITS, e, sc, sc2);          // rows beyond n_central (tile padding): zero digits
     row_exp[atom_raw] = e;
-#pragma unroll 1
-    for (int kc = 0; kc < NFP; kc += 64) {
-#pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-        const int k0 = kc + g * 16;
-        float v[16];
+    // Phase 2 walks the 24 groups of 16 features with the NEXT group's slot values already in flight: ncu had 23 % of the
+    // kernel's stall samples on the first use of the just-loaded values (L2 latency, 8 warps per SM to hide it).
+    float nxt[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (k0 + j < NF) ? slot[(k0 + j) * 128] : 0.0f;
-        uint32_t w[I8_DIGITS][4];
+    for (int j = 0; j < 16; ++j) nxt[j] = slot[j * 128];
+#pragma unroll 1
+    for (int grp = 0; grp < NFP / 16; ++grp) {
+      const int k0 = grp * 16, g = grp & 3, kc = k0 & ~63;
+      float v[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t ew[4], tb[4];
+      for (int j = 0; j < 16; ++j) v[j] = nxt[j];
+      if (grp + 1 < NFP / 16) {
+        const float* np_ = slot + (k0 + 16) * 128;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) nxt[j] = (k0 + 16 + j < NF) ? np_[j * 128] : 0.0f;
+      }
+      uint32_t w[I8_DIGITS][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t ew[4], tb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          ew[j] = i8_digit_word<I8_DIGITS>(sc != 0.0f ? ((v[4 * q + j] * s_cs[k0 + 4 * q + j]) * sc) * sc2 : 0.0f);
+        i8_transpose4(ew, tb);
+#pragma unroll
+        for (int d = 0; d < I8_DIGITS; ++d) w[d][q] = tb[I8_DIGITS - 1 - d];
+      }
+      const int piece = g ^ ((tid >> 1) & 3);   // 16-byte pieces of a row are xor-swizzled: conflict-free both ways
+#pragma unroll
+      for (int d = 0; d < I8_DIGITS; ++d)
+        *reinterpret_cast<uint4*>(&tile[d][tid * 64 + piece * 16]) = make_uint4(w[d][0], w[d][1], w[d][2], w[d][3]);
+      if (g == 3) {                              // a 64-feature chunk of the tile is staged: write it out as 64-byte row segments
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < I8_DIGITS; ++d) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int k = k0 + 4 * q + j;
-            const float c = (k < NF) ? __ldg(col_scale + k) : 0.0f;
-            ew[j] = i8_digit_word<I8_DIGITS>(sc != 0.0f ? ((v[4 * q + j] * c) * sc) * sc2 : 0.0f);
+            const int idx = tid + 128 * j, r = idx >> 2, p = idx & 3;
+            const uint4 val = *reinterpret_cast<const uint4*>(&tile[d][r * 64 + (p ^ ((r >> 1) & 3)) * 16]);
+            __stcs(reinterpret_cast<uint4*>(planes + d * plane_stride + (m0 + r) * int64_t(NFP) + kc + p * 16), val);   // streaming: keeps the feature slot in L2
           }
-          i8_transpose4(ew, tb);
-#pragma unroll
-          for (int d = 0; d < I8_DIGITS; ++d) w[d][q] = tb[I8_DIGITS - 1 - d];
         }
-        const int piece = g ^ ((tid >> 1) & 3);   // 16-byte pieces of a row are xor-swizzled: conflict-free both ways
-#pragma unroll
-        for (int d = 0; d < I8_DIGITS; ++d)
-          *reinterpret_cast<uint4*>(&tile[d][tid * 64 + piece * 16]) = make_uint4(w[d][0], w[d][1], w[d][2], w[d][3]);
+        __syncthreads();
       }
-      __syncthreads();
-#pragma unroll
-      for (int d = 0; d < I8_DIGITS; ++d) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int idx = tid + 128 * j, r = idx >> 2, p = idx & 3;
-          const uint4 val = *reinterpret_cast<const uint4*>(&tile[d][r * 64 + (p ^ ((r >> 1) & 3)) * 16]);
-          *reinterpret_cast<uint4*>(planes + d * plane_stride + (m0 + r) * int64_t(NFP) + kc + p * 16) = val;
-        }
-      }
-      __syncthreads();
     }
   }
 }
@@ -923,7 +932,10 @@ k_contract_fwd_quantize_split(GmWorkspace ws, const float* __restrict__ col_scal
                               int32_t* __restrict__ row_exp, int64_t n_groups) {
   __shared__ __align__(16) uint8_t tile[kSplit][I8_DIGITS][32 * 64];
   __shared__ float s_mx[kSplit][32];
+  __shared__ float s_cs[NFP];            // per-feature powers of two (0 for the padding features)
   const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < NFP; k += kContractThreads) s_cs[k] = k < NF ? col_scale[k] : 0.0f;
+  __syncthreads();
   float* slot = ws.GT + int64_t(blockIdx.x) * NFP * 32 + lane;     // this atom's column of the block's slot, row stride 32
   const int64_t plane_stride = ws.ld * int64_t(NFP);
   for (int64_t t = blockIdx.x; t < n_groups; t += gridDim.x) {
@@ -935,7 +947,7 @@ k_contract_fwd_quantize_split(GmWorkspace ws, const float* __restrict__ col_scal
     for (int k = 0; k < NPK; ++k) m[k] = ws.MT[int64_t(k) * ws.ld + atom];
     float mx = 0.0f;
     gm_contract_forward_part(m, part, [&](int f, float v) {
-      mx = fmaxf(mx, fabsf(v * __ldg(col_scale + f)));
+      mx = fmaxf(mx, fabsf(v * s_cs[f]));
       slot[f * 32] = v;
     });
     s_mx[part][lane] = mx;
@@ -948,22 +960,26 @@ k_contract_fwd_quantize_split(GmWorkspace ws, const float* __restrict__ col_scal
     if (part == 0) row_exp[atom_raw] = e;
 #pragma unroll 1
     for (int kc = part * 64; kc < NFP; kc += kSplit * 64) {
+      float nxt[16];                       // the next group's slot values, in flight while the current group is converted
+#pragma unroll
+      for (int j = 0; j < 16; ++j) nxt[j] = (kc + j < NF) ? slot[(kc + j) * 32] : 0.0f;
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
         const int k0 = kc + g * 16;
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (k0 + j < NF) ? slot[(k0 + j) * 32] : 0.0f;
+        for (int j = 0; j < 16; ++j) v[j] = nxt[j];
+        if (g < 3) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) nxt[j] = (k0 + 16 + j < NF) ? slot[(k0 + 16 + j) * 32] : 0.0f;
+        }
         uint32_t w[I8_DIGITS][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t ew[4], tb[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int k = k0 + 4 * q + j;
-            const float c = (k < NF) ? __ldg(col_scale + k) : 0.0f;
-            ew[j] = i8_digit_word<I8_DIGITS>(sc != 0.0f ? ((v[4 * q + j] * c) * sc) * sc2 : 0.0f);
-          }
+          for (int j = 0; j < 4; ++j)
+            ew[j] = i8_digit_word<I8_DIGITS>(sc != 0.0f ? ((v[4 * q + j] * s_cs[k0 + 4 * q + j]) * sc) * sc2 : 0.0f);
           i8_transpose4(ew, tb);
 #pragma unroll
           for (int d = 0; d < I8_DIGITS; ++d) w[d][q] = tb[I8_DIGITS - 1 - d];
