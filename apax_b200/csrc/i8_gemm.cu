@@ -174,11 +174,11 @@ __device__ __forceinline__ void i8_emit16(const float (&v)[16], float sc, float 
   }
 #pragma unroll
   for (int d = 0; d < I8_DIGITS; ++d)
-    *reinterpret_cast<uint4*>(dst + d * plane_stride) = make_uint4(w[d][0], w[d][1], w[d][2], w[d][3]);
+    __stcs(reinterpret_cast<uint4*>(dst + d * plane_stride), make_uint4(w[d][0], w[d][1], w[d][2], w[d][3]));
 }
 
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&w)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+  asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
                "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                : "memory");
 }
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
         if (MODE == I8_EPI_MULD_Q) {
           const float* ap = aux_tile + int64_t(j * I8_BN + half * PW) * I8_BM;   // one 64-bit base, immediate offsets below
 #pragma unroll
-          for (int i = 0; i < PW; ++i) auxv[i] = ap[i * I8_BM];
+          for (int i = 0; i < PW; ++i) auxv[i] = __ldcs(ap + i * I8_BM);
         }
         const long long c0 = clock64();
         ok = mbar_wait(smem_u32(&acc_full[buf]), use & 1, err);
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
             const int n = nb + i, ri = cc * 16 + i;
             const float y = i8_combine(r0[i], r1[i], r2[i], r3[i]) * scale;
             if (MODE == I8_EPI_STORE) {
-              if (all_valid || n < epi.n_valid) *gp = y;
+              if (all_valid || n < epi.n_valid) __stcs(gp, y);
             } else if (MODE == I8_EPI_ACT_Q || MODE == I8_EPI_ACT_HEAD) {
               // variance_preserving_swish (activation.py:7-9) and its derivative: SFU exponential (ex2.approx, 2 ulp
               // like libm's expf) and an SFU reciprocal refined by one Newton step (< 1 ulp) -- the epilogue is bound by
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
               const float h = cs * z;
               const float d = cs * fmaf(z, 1.0f - sg, 1.0f);
               if (MODE == I8_EPI_ACT_Q) {
-                ap[i * I8_BM] = d;
+                __stcs(ap + i * I8_BM, d);   // streaming (read once, by the backward GEMM): the staging rows own the L2
                 sp[i * I8_BM] = h;
                 mx = fmaxf(mx, fabsf(h * s_qcs[n]));
               } else {
