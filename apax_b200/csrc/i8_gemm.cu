@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
     const uint32_t tile_step = dual ? 2u : 1u;
     uint32_t bit = 0;   // k-blocks this warp has taken from its ring
     const long long t_begin = clock64();
+    long long w_acc = 0, w_b = 0, w_a = 0;   // cycle counters (trace only): waits for a drained accumulator set, weight stages, atom planes
     // 16-byte-unit offsets of the four activation planes: resident ones relative to the k-block's resident slot,
     // streamed ones relative to the weight stage
     uint32_t a_off[I8_DIGITS];
@@ -357,7 +358,9 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
         const bool first_in_mt = tile < tile_step || int((tile - tile_step) / uint32_t(num_n_sub)) != mt;   // this warp's first sweep of the atom tile
         const bool last_in_mt = int((tile + tile_step) / uint32_t(num_n_sub)) != mt;                        // ... and its last
         const uint32_t buf = tile & 1, use = tile >> 1;
+        long long c0 = clock64();
         mbar_wait_soft(smem_u32(&acc_empty[buf]), (use & 1) ^ 1, err, &cta_dead);   // epilogue has drained this set
+        w_acc += clock64() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc_base = tmem_d + buf * I8_ACC_COLS;
         for (int kb = 0; kb < num_kb; kb += 2, bit += 2) {
@@ -365,12 +368,16 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
           const uint32_t ring0 = dual ? mma_id * ring_size : 0u;
           const uint32_t s0 = ring0 + bit % ring_size, ph0 = (bit / ring_size) & 1;
           const uint32_t s1 = ring0 + (bit + 1) % ring_size, ph1 = ((bit + 1) / ring_size) & 1;
+          c0 = clock64();
           if (first_in_mt) {
             mbar_wait_soft(smem_u32(&a_full[kb]), uint32_t(mt) & 1, err, &cta_dead);
             if (two) mbar_wait_soft(smem_u32(&a_full[kb + 1]), uint32_t(mt) & 1, err, &cta_dead);
           }
+          const long long c1 = clock64();
           mbar_wait_soft(smem_u32(&b_full[s0]), ph0, err, &cta_dead);
           if (two) mbar_wait_soft(smem_u32(&b_full[s1]), ph1, err, &cta_dead);
+          w_a += c1 - c0;
+          w_b += clock64() - c1;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           // Activation digit s meets the weight digits 0 .. 3-s in ONE MMA: the four weight planes of a stage are
           // contiguous 64-row blocks of one K-major tile, so N = 64 (4 - s) output columns are the products
@@ -404,7 +411,12 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
         }
       }
     }
-    if (epi.dbg && lane == 0 && mma_id == 0) epi.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
+    if (epi.dbg && lane == 0 && mma_id == 0) {
+      epi.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
+      epi.dbg[blockIdx.x * 8 + 1] = w_acc;
+      epi.dbg[blockIdx.x * 8 + 2] = w_b;
+      epi.dbg[blockIdx.x * 8 + 3] = w_a;
+    }
   } else if (warp >= R::kEpiBase && warp < R::kEpiBase + R::kEpiWarps) {
     // -------------------------------------------------------------------- epilogue warps: lane == atom
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
@@ -803,8 +815,8 @@ int i8_gemm(cudaStream_t stream, const I8Planes& act, const I8Planes& wgt, const
       double m[8] = {0};
       for (int c = 0; c < *grid; ++c)
         for (int i = 0; i < 8; ++i) m[i] += double(h[c * 8 + i]) / *grid;
-      fprintf(stderr, "[i8 trace] mode %d grid %d: mma warp %.0f clk | epilogue total %.0f wait %.0f phase2 %.0f\n", mode, *grid,
-              m[0], m[4], m[5], m[6]);
+      fprintf(stderr, "[i8 trace] mode %d grid %d: mma warp %.0f clk (waits: accumulator %.0f, weight stages %.0f, atom planes %.0f) | "
+                      "epilogue total %.0f wait %.0f phase2 %.0f\n", mode, *grid, m[0], m[1], m[2], m[3], m[4], m[5], m[6]);
     }
   };
   int trace_grid = 0;
