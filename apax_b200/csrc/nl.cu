@@ -425,43 +425,73 @@ __global__ void __launch_bounds__(256) k_nl_rowsort(const int32_t* __restrict__ 
   }
 }
 
-// Rank sort from the single-scan scratch (min-image lists): the row is staged in shared memory, every element's
-// rank is its number of smaller row mates, and only ranks below the capacity-clamped row length are written --
-// i.e. a truncated list keeps the FIRST pairs in the reference's order (partition.py:656-664).
+// Row sort from the single-scan scratch (min-image lists): one warp per row.  Rows of up to 256 neighbours are sorted in
+// registers by a bitonic network (element e = q * 32 + lane: exchanges at distance >= 32 are register swaps inside a lane,
+// the others one shuffle each; padding keys INT_MAX sink to the end) -- 28 / 36 compare-exchange steps instead of the
+// cnt^2 / 32 comparisons per lane of a rank sort (ncu: that kernel was issue-bound at 96 %, 43 k instructions per row).
+// Only the first len_c (capacity-clamped) elements are written, i.e. a truncated list keeps the FIRST pairs in the
+// reference's order (partition.py:656-664).  Longer rows: rank sort straight from global memory.
 constexpr int kRowSortMax = 256;
+
+template <int NQ>
+__device__ __forceinline__ void warp_bitonic_sort(int (&k)[NQ], int lane) {
+#pragma unroll
+  for (int size = 2; size <= NQ * 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int dq = stride >> 5;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int pq = q ^ dq;
+          if (q < pq) {
+            const bool up = ((q * 32) & size) == 0;          // bit `size` of e lives in q here (size >= 64)
+            const int lo = min(k[q], k[pq]), hi = max(k[q], k[pq]);
+            k[q] = up ? lo : hi;
+            k[pq] = up ? hi : lo;
+          }
+        }
+      } else {
+        const bool lower = (lane & stride) == 0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int other = __shfl_xor_sync(0xffffffffu, k[q], stride);
+          const bool up = ((q * 32 + lane) & size) == 0;
+          k[q] = (lower == up) ? min(k[q], other) : max(k[q], other);
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_nl_rowsort_strided(const int32_t* __restrict__ rowptr,
                                                             const int32_t* __restrict__ rowptr_c,
                                                             const int32_t* __restrict__ rowcnt, int64_t N,
                                                             const int32_t* __restrict__ scratch, int stride,
                                                             const int32_t* __restrict__ nbr_tmp,
                                                             int32_t* __restrict__ nbr_out) {
-  __shared__ int32_t s_row[8][kRowSortMax];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * 8 + wib;
   if (row >= N) return;
   const int cnt = rowcnt[row];
   const int b = rowptr_c[row], len_c = rowptr_c[row + 1] - b;
   const int32_t* src = cnt <= stride ? scratch + row * int64_t(stride) : nbr_tmp + rowptr[row];
-  if (cnt <= kRowSortMax) {
-    for (int i = lane; i < cnt; i += 32) s_row[wib][i] = src[i];
-    __syncwarp();
-    for (int i0 = 0; i0 < cnt; i0 += 128) {   // four keys per lane share every broadcast read
-      int key[4], rank[4];
+  if (cnt <= 128) {
+    int k[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int i = i0 + q * 32 + lane;
-        key[q] = i < cnt ? s_row[wib][i] : 0x7fffffff;
-        rank[q] = 0;
-      }
-      for (int j = 0; j < cnt; ++j) {
-        const int v = s_row[wib][j];
+    for (int q = 0; q < 4; ++q) k[q] = q * 32 + lane < cnt ? src[q * 32 + lane] : 0x7fffffff;
+    warp_bitonic_sort<4>(k, lane);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rank[q] += (v < key[q]);
-      }
+    for (int q = 0; q < 4; ++q)
+      if (q * 32 + lane < len_c) nbr_out[b + q * 32 + lane] = k[q];      // len_c <= cnt: padding keys are never written
+  } else if (cnt <= kRowSortMax) {
+    int k[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (i0 + q * 32 + lane < cnt && rank[q] < len_c) nbr_out[b + rank[q]] = key[q];
-    }
+    for (int q = 0; q < 8; ++q) k[q] = q * 32 + lane < cnt ? src[q * 32 + lane] : 0x7fffffff;
+    warp_bitonic_sort<8>(k, lane);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q * 32 + lane < len_c) nbr_out[b + q * 32 + lane] = k[q];
   } else {   // very long rows: rank straight from global memory
     for (int i = lane; i < cnt; i += 32) {
       const int key = src[i];
