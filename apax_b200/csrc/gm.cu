@@ -203,6 +203,28 @@ __global__ void __launch_bounds__(256) k_transpose_symmetric(const int32_t* __re
     nbr_out[s] = j;
     src_out[s] = s;
     int b = __ldg(rowptr + j), e = __ldg(rowptr + j + 1) - 1, found = -1;
+    // Interpolated start: neighbour indices of a row are roughly uniform over [0, N), so a sits near position cnt a / N.
+    // One probe there and one at the far end of an 8-slot window narrow the search to the sector(s) around the guess --
+    // the plain binary search spent 70 % of the kernel's stall samples on seven dependent probes scattered over the row's
+    // three cache lines (6.5 GB of DRAM reads for a 0.36 GB list).  A wrong guess (indices not uniform) only costs the
+    // two probes: the binary search below then runs on the remaining range.
+    if (e - b >= 16) {
+      const int g = b + int((int64_t(e - b + 1) * a) / N);
+      const int gc = g > e ? e : g;
+      const int v = __ldg(nbr + gc);
+      if (v == int(a)) {
+        found = gc;
+        b = e + 1;
+      } else if (v < int(a)) {
+        b = gc + 1;
+        const int w = gc + 8 < e ? gc + 8 : e;
+        if (b <= e) { if (__ldg(nbr + w) >= int(a)) e = w; else b = w + 1; }
+      } else {
+        e = gc - 1;
+        const int w = gc - 8 > b ? gc - 8 : b;
+        if (b <= e) { if (__ldg(nbr + w) <= int(a)) b = w; else e = w - 1; }
+      }
+    }
     while (b <= e) {
       const int mid = (b + e) >> 1;
       const int v = __ldg(nbr + mid);
