@@ -407,6 +407,23 @@ def energy_forces(params, R, Z, idx, box, offsets, mode: str, cfg: Optional[GMNN
     return {"energy": float(energy.detach()), "forces": (-grad).numpy()}
 
 
+def energy_forces_checked(params, R, Z, idx, box, offsets, mode: str, cfg: Optional[GMNNConfig] = None, max_tries: int = 4):
+    """energy_forces, evaluated until two consecutive evaluations agree (energy to 1e-10 relative, forces to 1e-9 of their
+    maximum).  Why: on the 16-thread hosts of the GPU pool the FIRST multi-threaded torch-CPU evaluation of a fresh process
+    returned a different result in ~6 % of the processes (same inputs; energy off by 1.8e-5 relative, always the same wrong
+    value; every later evaluation correct -- observed from __graft_entry__.smoke(), which printed both sides).  The checker
+    must not be the flaky part of a parity check, so callers that evaluate it once per process use this wrapper."""
+    prev = energy_forces(params, R, Z, idx, box, offsets, mode, cfg)
+    for _ in range(max_tries - 1):
+        cur = energy_forces(params, R, Z, idx, box, offsets, mode, cfg)
+        fmax = max(float(np.abs(cur["forces"]).max()), 1e-30)
+        if abs(cur["energy"] - prev["energy"]) <= 1e-10 * max(abs(cur["energy"]), 1e-30) and \
+                float(np.abs(cur["forces"] - prev["forces"]).max()) <= 1e-9 * fmax:
+            return cur
+        prev = cur
+    raise RuntimeError("the torch-CPU oracle did not reproduce its own result in %d evaluations" % max_tries)
+
+
 def descriptor_only(params, R, Z, idx, box, offsets, mode: str, cfg: Optional[GMNNConfig] = None):
     """Features g [N,360] and packed moments, for kernel-stage parity tests."""
     cfg = cfg or GMNNConfig()

@@ -15,6 +15,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _oracle_warm_up():
+    """One small, checked evaluation of the torch-CPU oracle before any test uses it: on the GPU pool's 16-thread hosts the
+    FIRST multi-threaded evaluation of a fresh process was off in ~6 % of the processes (oracle.gmnn_oracle.energy_forces_checked
+    has the observation); every later evaluation reproduced.  The checker must not be the flaky side of a parity test."""
+    from apax_b200 import synthetic as syn
+    from oracle import gmnn_oracle as go
+    from oracle import neighbor_oracle as no
+
+    pos, Z, cell = syn.water_box(8, 3)
+    ii, jj, ss = no.vesin_full_list(pos, cell, 6.0)
+    go.energy_forces_checked(syn.gmnn_params(seed=1), pos @ np.linalg.inv(cell), Z, np.stack([ii, jj]).astype(np.int32), cell.T,
+                             ss.astype(np.float64) @ cell, "offsets")
+    yield
+
+
 @pytest.fixture(scope="session")
 def golden():
     def load(name):
