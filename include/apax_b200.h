@@ -490,8 +490,11 @@ int apax_i8_gemm_test(apax_stream_t stream, const float* act, int64_t k, int64_t
                       int64_t nc, float* out, int32_t* err_flag, int64_t* dbg_cycles /* nullable, [n_sm][8] */,
                       int32_t act_planes /* 3 or 4 digit planes for the activations */);
 
-/* Measurement only (tools/trace_i8.py): dbg_flags != 0 overrides the kernels' debug switches (skip phases), trace != 0
- * makes every readout GEMM print its per-role cycle counters to stderr (synchronising).  Both 0 in normal operation. */
+/* Measurement only (tools/trace_i8.py, tools/gemm_ab.py): dbg_flags != 0 overrides the kernels' debug switches -- 1 the
+ * epilogue skips the drain, 2 the producer signals without loading, 16 the sixteen-warp epilogue kernels, 32 / 64 one / two
+ * fewer resident activation planes than fit (a deeper weight ring) --, trace != 0 makes every readout GEMM print its per-role
+ * cycle counters (MMA warp: waits for accumulator / weight stages / atom planes; epilogue: waits, digit emission) to stderr
+ * (synchronising).  Both 0 in normal operation; results with flags 1 or 2 are meaningless. */
 int apax_i8_set_debug(int32_t dbg_flags, int32_t trace);
 
 /* Measurement only: tcgen05.mma kind::i8 issue rate (M = 128, N = n; `iters` rounds of ten MMAs; pattern 0 / 1 / 2:
