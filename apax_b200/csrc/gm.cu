@@ -552,7 +552,7 @@ __device__ __forceinline__ void pair_fwd_body(const GmWorkspace& ws, const PairG
     // (ncu: 28 % of the kernel's stall samples sat on that one SEL).
     const long long wbits = __double_as_longlong(p_cur.w);
     const int pt = zc * n_sp + (int(wbits) | int(wbits >> 32));
-    G[e] = make_float4(dx, dy, dz, __int_as_float(pt));
+    __stcs(G + e, make_float4(dx, dy, dz, __int_as_float(pt)));   // streaming: read once (backward pass); the atom records own the L2
     p_cur = p_nxt; j_cur = j_nxt; j_nxt = j_nn;
     o_cur[0] = o_nxt[0]; o_cur[1] = o_nxt[1]; o_cur[2] = o_nxt[2];
     const float r2 = dx * dx + dy * dy + dz * dz;
@@ -635,7 +635,7 @@ __device__ __forceinline__ void pair_bwd_body(const GmWorkspace& ws, const DescC
   float4 g_nxt = beg + sub < end ? __ldg(Gp + beg + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int e = beg + sub; e < end; e += LPA) {
     const float4 g = g_nxt;
-    if (e + LPA < end) g_nxt = __ldg(Gp + e + LPA);  // next pair's geometry is in flight during this pair's math
+    if (e + LPA < end) g_nxt = __ldcs(Gp + e + LPA);  // next pair's geometry is in flight during this pair's math (streaming load)
     const float dx = g.x, dy = g.y, dz = g.z;
     const int pt = __float_as_int(g.w);
     const float r2 = dx * dx + dy * dy + dz * dz;
@@ -719,7 +719,7 @@ __device__ __forceinline__ void pair_bwd_body(const GmWorkspace& ws, const DescC
       out.z = fmaf(radial, dz, s * nz);
       sx += double(out.x); sy += double(out.y); sz += double(out.z);
     }
-    Dp[e] = out;
+    __stcs(Dp + e, out);
   }
 #pragma unroll
   for (int o = LPA / 2; o > 0; o >>= 1) {
