@@ -550,13 +550,18 @@ __global__ void __launch_bounds__(I8Roles<W>::kThreads, 1) k_i8_gemm(const __gri
 #pragma unroll 1
         for (int j = 0; j < num_n_sub; ++j) {
           const int nb = j * I8_BN + half * PW;
+          float nxt[PW];                     // the next sub-tile's staged values travel while this one is converted
+          if (j + 1 < num_n_sub) {
+            rp += I8_BN * I8_BM;
+#pragma unroll
+            for (int i = 0; i < PW; ++i) nxt[i] = rp[i * I8_BM];
+          }
 #pragma unroll
           for (int i = 0; i < PW; ++i) cur[i] *= s_qcs[nb + i];
           i8_emit_cols<PW>(cur, sc, sc2, epi.q_planes + m * epi.q_kp + nb, epi.q_plane_stride);
           if (j + 1 < num_n_sub) {
-            rp += I8_BN * I8_BM;
 #pragma unroll
-            for (int i = 0; i < PW; ++i) cur[i] = rp[i * I8_BM];
+            for (int i = 0; i < PW; ++i) cur[i] = nxt[i];
           }
         }
         w_phase2 += clock64() - p0;
