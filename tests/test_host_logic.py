@@ -240,3 +240,22 @@ def test_xla_ffi_shim_parses_against_a_stub_of_the_ffi_api(tmp_path):
     res = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", f"-I{tmp_path}", f"-I{os.path.join(root, 'include')}",
                           os.path.join(root, "apax_b200", "ffi", "xla_ffi_shim.cc")], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
+
+
+def test_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) must print exactly one JSON line on stdout with the
+    contract's keys, on a machine without a GPU."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "atom_steps_per_s" and d["unit"] == "atom-steps/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
